@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- fish 3-D Poisson CG + geometric-multigrid solve (BASELINE.json metric).
+
+A "step" is one complete KSP solve of the fish.c 3-D manuexp problem (c/ch6/fish.c, options
+`-fsh_dim 3 -da_refine 8 -pc_type mg -pc_mg_levels 7 -mg_levels_ksp_type chebyshev -mg_levels_ksp_max_it 2
+-mg_levels_pc_type jacobi -ksp_rtol 1e-10`) on a 513^3 grid (135 M unknowns):
+value = unknowns / solve seconds (MDOF/s), with b = F(u0) already resident in HBM.
+`e2e` is the same solve through the C ABI's host-buffer entry point (p4b_cg_solve_host): b is
+copied from pinned host memory, solved, and x copied back, all inside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--refine R]
+
+N > 1: launched by torchrun, one rank per GPU; the grid is split into z-slabs (strong scaling:
+the total problem is fixed), ghost planes and dot products go over NCCL.
+--impl reference: the CPU restatement of the same algorithm (oracle/) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OPTIONS = ("-fsh_dim 3 -da_refine {refine} -pc_type mg -pc_mg_levels {levels} -mg_levels_ksp_type chebyshev "
+           "-mg_levels_ksp_max_it 2 -mg_levels_pc_type jacobi -ksp_rtol 1e-10")
+ALG_BYTES = {"apply_dot": "16N", "residual": "24N", "cheb_zero": "16N", "cheb_first": "24N", "cheb_next": "32N",
+             "restrict": "8N+8Nc", "prolong_add": "16N+8Nc", "axpy2": "48N", "dot2": "16N", "aypx": "24N",
+             "resid_restrict": "16N+8Nc"}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.p = index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([s.strip() for s in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference(refine, levels, threads=None, repeats=1):
+    """Time the CPU restatement (oracle/) of the identical algorithm; returns (MDOF/s, info)."""
+    from oracle import fish_cpu
+    return fish_cpu.timed_solve(refine=refine, levels=levels, rtol=1e-10, threads=threads, repeats=repeats)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    refine = args.cpu_refine
+    levels = max(2, refine - 1)
+    cores = os.cpu_count()
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference(refine, levels, threads=cores)
+        if i >= args.warmup:
+            vals.append(r)
+    secs = sum(v["seconds"] for v in vals) / len(vals)
+    n = vals[0]["n"]
+    mdofs = n / secs / 1e6
+    m = 2 ** (refine + 1) + 1
+    line = {
+        "impl": "reference", "metric": "fish3d_cg_gmg_solve_mdof_per_s", "value": mdofs, "unit": "MDOF/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "fish.c 3-D Poisson manuexp 513^3, CG + V-cycle GMG, Chebyshev(2)/Jacobi, rtol 1e-10",
+                   "options": OPTIONS.format(refine=8, levels=7)},
+        "cpu_baseline": {"value": mdofs, "unit": "MDOF/s", "cores": vals[0]["threads"], "kind": "port",
+                         "sample": "same algorithm and options on a %d^3 grid (%d unknowns), %d KSP its, OpenMP C "
+                                   "restatement oracle/fish_cpu.c (PETSc/MPI are not installable here)"
+                                   % (m, n, vals[0]["its"])},
+        "e2e": {"value": mdofs, "unit": "MDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "ksp_its": vals[0]["its"],
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--refine", type=int, default=8, help="-da_refine (8 = 513^3, 7 = 257^3)")
+    ap.add_argument("--levels", type=int, default=0, help="-pc_mg_levels (default refine-1: coarse grid 9^3)")
+    ap.add_argument("--cpu-refine", type=int, default=7, help="grid of the bounded CPU baseline sample (7 = 257^3)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from p4pdes_b200 import lib as L
+    from p4pdes_b200.fish import Context, Multigrid, mg_options
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = Context(local_rank, distributed=world > 1)
+    lib = ctx.lib
+
+    refine = args.refine
+    levels = args.levels or max(2, refine - 1)
+    g = L.refined_grid(3, refine)
+    ndof = g.n
+    mg = Multigrid(ctx, g, mg_options(levels=levels, fuse=not args.no_fuse))
+    nloc = mg.nlocal
+    b = ctx.empty(nloc)
+    x = ctx.empty(nloc)
+    uex = ctx.empty(nloc)
+    u0 = ctx.empty(nloc)
+    mg.fish_setup("manuexp", True, b=b, u0=u0, uexact=uex)
+    ctx.sync()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident solves -------------------------------------------------------------------
+    res = None
+    for _ in range(args.warmup):
+        res = mg.cg_solve(b, x, rtol=1e-10)
+    mg.profile(True)
+    mg.profile_reset()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.p4b_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(ctx.stream)
+    for _ in range(args.steps):
+        res = mg.cg_solve(b, x, rtol=1e-10)
+    ev1.record(ctx.stream)
+    barrier()
+    launches = lib.p4b_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_step = ms_total / args.steps
+    stats = mg.profile_stats()
+    mg.profile(False)
+
+    # correctness of what was timed: error norms of u = u0 - y against the exact solution (fish.c:248-280)
+    ctx.axpy(-1.0, x, u0)
+    ctx.axpy(-1.0, uex, u0)
+    errinf = ctx.norminf(u0)
+    err2h = ctx.norm2(u0) / ((g.mx - 1) * (g.my - 1) * (g.mz - 1)) ** 0.5
+
+    # ---- end to end: pinned host buffers through p4b_cg_solve_host -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        bh = torch.empty(nloc, dtype=torch.float64).pin_memory()
+        xh = torch.empty(nloc, dtype=torch.float64).pin_memory()
+        bh.copy_(b)
+        torch.cuda.synchronize()
+        mg.cg_solve_host(bh, xh, rtol=1e-10)
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ctx.stream)
+        nst = max(1, min(args.steps, 3))
+        for _ in range(nst):
+            mg.cg_solve_host(bh, xh, rtol=1e-10)
+        e1.record(ctx.stream)
+        barrier()
+        wall = (time.perf_counter() - t0) / nst
+        ms_e2e = max_over_ranks(max(e0.elapsed_time(e1) / nst, 0.0))
+        e2e = {"value": ndof / (ms_e2e * 1e-3) / 1e6, "unit": "MDOF/s", "h2d_bytes_per_step": 8 * nloc * world,
+               "d2h_bytes_per_step": 8 * nloc * world, "ms_per_step": ms_e2e, "wall_ms_per_step": wall * 1e3,
+               "api": "p4b_cg_solve_host (pinned host b -> device, solve, x -> pinned host)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant finest-level kernel ------------------------------------------------
+    peak, peak_src = peaks()
+    roof = None
+    table = {}
+    if stats:
+        total_ms = sum(s["ms"] for s in stats.values())
+        for name, s in sorted(stats.items(), key=lambda kv: -kv[1]["ms"]):
+            table[name] = {"launches": s["launches"], "ms_per_launch": s["ms"] / s["launches"],
+                           "GBs": s["bytes"] / s["ms"] / 1e6, "frac": s["bytes"] / s["ms"] / 1e6 / peak,
+                           "share_of_fine_level_ms": s["ms"] / total_ms, "alg_bytes": ALG_BYTES[name]}
+        top = max(stats, key=lambda k: stats[k]["ms"])
+        s = stats[top]
+        ach = s["bytes"] / s["ms"] / 1e6
+        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": None,
+                "alg_bytes_per_launch": s["bytes"] / s["launches"], "launches": s["launches"],
+                "ms_per_launch": s["ms"] / s["launches"],
+                "fine_level_kernel_ms_share_of_step": total_ms / (ms_step * args.steps)}
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            roof["traffic"] = json.load(open(tp)).get(top)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = cpu_reference(args.cpu_refine, max(2, args.cpu_refine - 1), threads=os.cpu_count())
+            m = 2 ** (args.cpu_refine + 1) + 1
+            cpu = {"value": r["n"] / r["seconds"] / 1e6, "unit": "MDOF/s", "cores": r["threads"], "kind": "port",
+                   "solve_s": r["seconds"], "ksp_its": r["its"],
+                   "sample": "one solve, same algorithm/options, %d^3 grid (%d unknowns); OpenMP C restatement "
+                             "oracle/fish_cpu.c, not PETSc (PETSc/MPI absent from the image)" % (m, r["n"])}
+        except Exception as exc:  # the baseline is a reported number, never a reason to lose the GPU line
+            cpu = {"value": None, "unit": "MDOF/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (exc,)}
+
+    m = g.mx
+    line = {
+        "metric": "fish3d_cg_gmg_solve_mdof_per_s", "value": ndof / (ms_step * 1e-3) / 1e6, "unit": "MDOF/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "solve_s": ms_step * 1e-3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "fish.c 3-D Poisson manuexp %d^3 (%d unknowns), CG + V-cycle GMG, Chebyshev(2)/Jacobi, "
+                               "rtol 1e-10" % (m, ndof),
+                   "options": OPTIONS.format(refine=refine, levels=levels), "levels": mg.nlevels,
+                   "parallelism": "z-slabs x%d" % world, "l2": "inputs (%.2f GB per vector) exceed the 126 MB L2"
+                   % (8 * ndof / 1e9), "fused": not args.no_fuse},
+        "ksp_its": res.its, "ksp_reason": L.REASONS.get(res.reason), "rnorm0": res.rnorm0, "rnorm": res.rnorm,
+        "errinf": errinf, "err2h": err2h,
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": table,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,184 @@
+/* p4b200.h -- thin C ABI over the sm_100a CUDA kernels of the fish/DMDA hot path.
+ *
+ * Plain pointers and sizes only (no torch, no C++ types).  Device pointers are raw
+ * CUDA device addresses; `stream` arguments are a cudaStream_t cast to void*.
+ * Every function returns 0 on success and a non-zero PetscErrorCode-style int on
+ * failure (p4b_last_error() gives the text), mirroring the reference's
+ * `PetscCall(...)` convention (c/ch6/fish.c:145 ff).
+ *
+ * What each entry point replaces in the reference run (paths under /root/reference;
+ * [PETSc] = the un-vendored PETSc library reached from that call site):
+ *
+ *   p4b_poisson_function     c/ch6/poissonfunctions.c:4-115   Poisson{1,2,3}DFunctionLocal
+ *   p4b_initial_state        c/ch6/poissonfunctions.c:260-346 InitialState
+ *   p4b_fish_sample          c/ch6/fish.c:15-82               u_exact / f_rhs tables
+ *   p4b_stencil_apply        [PETSc] MatMult on the matrix of poissonfunctions.c:117-258
+ *   p4b_stencil_residual     [PETSc] MatResidual (PCMG, c/ch6/fish.c:239 -> SNESSolve)
+ *   p4b_cheb_jacobi          [PETSc] KSPSolve_Chebyshev + PCApply_Jacobi (-mg_levels_*)
+ *   p4b_restrict             [PETSc] MatRestrict with the DMDA Q1 interpolation (R = P^T)
+ *   p4b_prolong_add          [PETSc] MatInterpolateAdd
+ *   p4b_vec_*                [PETSc] VecAXPY/VecAYPX/VecDot/VecNorm (fish.c:254-257, KSPCG)
+ *   p4b_mg_create/apply      [PETSc] PCSetUp_MG / PCApply_MG  (-pc_type mg)
+ *   p4b_cg_solve             [PETSc] KSPSolve_CG              (fish.c:233 KSPSetType(ksp,KSPCG))
+ *   p4b_fish_solve_host      [PETSc] SNESSolve_KSPONLY        (fish.c:231,239)
+ *
+ * There is no CPU fallback behind any of these: without a CUDA device they fail.
+ */
+#ifndef P4B200_H_
+#define P4B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P4B_VERSION 100
+#define P4B_MAX_LEVELS 16
+#define P4B_MAX_HIST 256
+
+typedef struct p4b_ctx p4b_ctx;   /* device + stream (+ NCCL communicator when nranks > 1) */
+typedef struct p4b_mg p4b_mg;     /* level hierarchy, smoother data, CG workspace */
+
+/* The DMDA of fish.c:199-220 plus the PoissonCtx of poissonfunctions.h:43-54. */
+typedef struct {
+    int dim;             /* 1, 2 or 3 */
+    int mx, my, mz;      /* global node counts; unused dimensions are 1 */
+    double Lx, Ly, Lz;   /* domain (0,Lx) x (0,Ly) x (0,Lz) */
+    double cx, cy, cz;   /* coefficients in -cx u_xx - cy u_yy - cz u_zz = f */
+} p4b_grid;
+
+enum { P4B_CYCLE_V = 1, P4B_CYCLE_W = 2 };
+enum { P4B_SMOOTH_CHEBYSHEV = 0, P4B_SMOOTH_RICHARDSON = 1 };
+enum { P4B_PC_NONE = 0, P4B_PC_JACOBI = 1, P4B_PC_MG = 2 };
+enum { P4B_PROBLEM_MANUPOLY = 0, P4B_PROBLEM_MANUEXP = 1, P4B_PROBLEM_ZERO = 2 };
+enum { P4B_CONVERGED_RTOL = 2, P4B_CONVERGED_ATOL = 3, P4B_DIVERGED_ITS = -3, P4B_DIVERGED_NAN = -9 };
+
+/* -pc_mg_* and -mg_levels_* options. */
+typedef struct {
+    int levels;          /* -pc_mg_levels; 0 = coarsen down to the 3^d grid */
+    int cycle;           /* P4B_CYCLE_V | P4B_CYCLE_W  (-pc_mg_cycle_type) */
+    int smoother;        /* P4B_SMOOTH_*               (-mg_levels_ksp_type); PC is always Jacobi */
+    int smooth_its;      /* -mg_levels_ksp_max_it (PETSc default 2) */
+    double emin, emax;   /* -mg_levels_ksp_chebyshev_eigenvalues; emax <= 0 => estimate */
+    double est_lo, est_hi; /* esteig transform applied to the analytic lambda_max (0.1, 1.1) */
+    int fuse;            /* 1 = fused kernels (default); 0 = one kernel per PETSc operation */
+    int use_graph;       /* 1 = replay the coarse part of the cycle as a CUDA graph */
+} p4b_mg_opts;
+
+typedef struct {
+    int its;                       /* number of CG alpha updates (-ksp_converged_reason) */
+    int reason;                    /* P4B_CONVERGED_* / P4B_DIVERGED_* */
+    double rnorm0, rnorm;          /* preconditioned residual norms ||M^-1 r|| (first / last) */
+    int nhist;                     /* entries used in hist */
+    double hist[P4B_MAX_HIST];     /* ||M^-1 r_i||, what -ksp_monitor prints */
+    double solve_ms;               /* device time of the solve (CUDA events on the ctx stream) */
+} p4b_ksp_result;
+
+/* kernel classes for the built-in profiler (finest-level launches only) */
+enum {
+    P4B_K_APPLY_DOT = 0,   /* w = A p, (p,w)                       16 N */
+    P4B_K_RESIDUAL,        /* r = b - A x                          24 N */
+    P4B_K_CHEB_ZERO,       /* x = q(A) b   zero-guess Chebyshev(2) 16 N */
+    P4B_K_CHEB_FIRST,      /* p1 = x + s D^-1 (b - A x)            24 N */
+    P4B_K_CHEB_NEXT,       /* p+ = (1-w) p- + w p + w s D^-1 (b-Ap) 32 N */
+    P4B_K_RESTRICT,        /* b_c = P^T r                          8 N + 8 N_c */
+    P4B_K_PROLONG,         /* x += P x_c                           16 N + 8 N_c */
+    P4B_K_AXPY2,           /* x += a p ; r -= a w                  48 N */
+    P4B_K_DOT2,            /* (z,z), (z,r)                         16 N */
+    P4B_K_AYPX,            /* p = z + b p                          24 N */
+    P4B_K_RESID_RESTRICT,  /* b_c = P^T (b - A x) fused            16 N + 8 N_c */
+    P4B_K_NCLASSES
+};
+
+typedef struct {
+    long long launches;    /* launches of this class on the finest level since the last reset */
+    double ms;             /* summed CUDA-event time of those launches */
+    double bytes;          /* summed algorithmic bytes (the table above x points of the level) */
+} p4b_kernel_stat;
+
+/* ---- library ---- */
+int p4b_version(void);
+const char *p4b_last_error(void);
+int p4b_device_count(int *n);
+
+/* ---- context ---- */
+int p4b_ctx_create(int device, void *stream, p4b_ctx **ctx);
+int p4b_ctx_destroy(p4b_ctx *ctx);
+int p4b_ctx_sync(p4b_ctx *ctx);
+/* multi-GPU: rank 0 makes a 128-byte id, the host side ships it to the other ranks (torch.distributed
+ * in this repo), every rank calls p4b_comm_init.  Halo planes and dot products then go over NCCL. */
+int p4b_comm_unique_id(void *id128);
+int p4b_comm_init(p4b_ctx *ctx, const void *id128, int rank, int nranks);
+/* DMDA-style ownership of the slowest dimension: the first (m % nranks) ranks own one more plane. */
+int p4b_slab_range(int m, int nranks, int rank, int *start, int *count);
+
+/* ---- device memory helpers for C hosts (the PETSc-shaped shim); Python uses torch tensors ---- */
+int p4b_malloc(p4b_ctx *ctx, size_t bytes, void **dptr);
+int p4b_free(p4b_ctx *ctx, void *dptr);
+int p4b_memcpy_h2d(p4b_ctx *ctx, void *dst, const void *src, size_t bytes);
+int p4b_memcpy_d2h(p4b_ctx *ctx, void *dst, const void *src, size_t bytes);
+
+/* ---- single-slab building blocks (whole grid on this device; arrays are mx*my*mz doubles) ---- */
+int p4b_stencil_apply(p4b_ctx *ctx, const p4b_grid *g, const double *u, double *y);
+int p4b_stencil_residual(p4b_ctx *ctx, const p4b_grid *g, const double *b, const double *u, double *r);
+/* its Chebyshev/Jacobi steps on A x = b; x is updated in place; work holds one vector */
+int p4b_cheb_jacobi(p4b_ctx *ctx, const p4b_grid *g, double emin, double emax, int its, int zero_guess,
+                    const double *b, double *x, double *work);
+/* fine grid g; coarse arrays have ((mx-1)/2+1) ... nodes per used dimension */
+int p4b_restrict(p4b_ctx *ctx, const p4b_grid *gfine, const double *rfine, double *bcoarse);
+int p4b_prolong_add(p4b_ctx *ctx, const p4b_grid *gfine, const double *xcoarse, double *xfine);
+int p4b_residual_restrict(p4b_ctx *ctx, const p4b_grid *gfine, const double *b, const double *x, double *bcoarse);
+int p4b_lambda_max_jacobi(const p4b_grid *g, double *lam);
+
+int p4b_vec_dot(p4b_ctx *ctx, size_t n, const double *x, const double *y, double *result_host);
+int p4b_vec_norm2(p4b_ctx *ctx, size_t n, const double *x, double *result_host);
+int p4b_vec_norminf(p4b_ctx *ctx, size_t n, const double *x, double *result_host);
+int p4b_vec_axpy(p4b_ctx *ctx, size_t n, double a, const double *x, double *y);      /* y += a x */
+int p4b_vec_aypx(p4b_ctx *ctx, size_t n, double a, const double *x, double *y);      /* y = x + a y */
+int p4b_vec_set(p4b_ctx *ctx, size_t n, double a, double *y);
+
+/* ---- the fish problem on device ---- */
+/* f = f_rhs, gb = g_bdry = u_exact sampled at every node (any of the three may be NULL) */
+int p4b_fish_sample(p4b_ctx *ctx, const p4b_grid *g, int problem, double *f, double *gb);
+int p4b_initial_state(p4b_ctx *ctx, const p4b_grid *g, const double *gb, int gonboundary, double *u);
+int p4b_poisson_function(p4b_ctx *ctx, const p4b_grid *g, const double *u, const double *f,
+                         const double *gb, double *F);
+
+/* ---- PCMG + KSPCG ---- */
+int p4b_mg_default_opts(p4b_mg_opts *o);
+int p4b_mg_create(p4b_ctx *ctx, const p4b_grid *g, const p4b_mg_opts *o, p4b_mg **mg);
+int p4b_mg_destroy(p4b_mg *mg);
+int p4b_mg_nlevels(p4b_mg *mg, int *nlevels);
+/* level 0 = coarsest; m[3], eig[2] = (emin, emax) used by the smoother on that level */
+int p4b_mg_level_info(p4b_mg *mg, int level, int *m, double *eig);
+/* the slab of the finest grid this rank owns: planes [start, start+count) of the slowest dimension */
+int p4b_mg_local_range(p4b_mg *mg, int *start, int *count, size_t *nlocal);
+/* z = M^-1 r (one multigrid cycle from a zero guess); r, z: nlocal doubles on device */
+int p4b_mg_apply(p4b_mg *mg, const double *r, double *z);
+/* solve A x = b from x = 0 with preconditioned CG; b, x: nlocal doubles on device */
+int p4b_cg_solve(p4b_mg *mg, int pc_type, const double *b, double *x, double rtol, double abstol,
+                 int max_it, p4b_ksp_result *res);
+/* same with HOST buffers of the local slab: H2D(b), solve, D2H(x) */
+int p4b_cg_solve_host(p4b_mg *mg, int pc_type, const double *b_host, double *x_host, double rtol,
+                      double abstol, int max_it, p4b_ksp_result *res);
+/* SNESKSPONLY on host buffers: F0 = F(u), solve J y = F0, u <- u - y.  f, gb, u: local slab on host */
+int p4b_fish_solve_host(p4b_mg *mg, const double *f_host, const double *gb_host, double *u_host,
+                        double rtol, double abstol, int max_it, p4b_ksp_result *res);
+
+/* fish.c's built-in problems on this rank's slab: b = F(u0), u0 = InitialState(zeros[, g on boundary]),
+ * uexact (fish.c:186-187,237-239,248-253).  Outputs are nlocal doubles on device; any may be NULL. */
+int p4b_mg_fish_setup(p4b_mg *mg, int problem, int gonboundary, double *b, double *u0, double *uexact);
+
+/* ---- profiler (CUDA events around finest-level launches on the ctx stream) ---- */
+int p4b_profile_enable(p4b_mg *mg, int on);
+int p4b_profile_reset(p4b_mg *mg);
+int p4b_profile_get(p4b_mg *mg, int kernel_class, p4b_kernel_stat *out);
+/* kernels launched by this library in this process so far (bench.py reports the difference) */
+long long p4b_launch_count(void);
+const char *p4b_kernel_name(int kernel_class);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P4B200_H_ */

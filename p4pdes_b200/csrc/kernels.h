@@ -1,0 +1,66 @@
+// kernels.h -- host-side launchers of the p4b200 CUDA kernels (internal; the C ABI is p4b200.h).
+#pragma once
+#include "common.cuh"
+
+namespace p4b {
+
+// scratch for deterministic grid-wide reductions (owned by the context)
+struct Reducer {
+    double *partials = nullptr;       // 4 * max_blocks doubles
+    unsigned int *ticket = nullptr;   // zero-initialised, re-armed by the kernels
+    int max_blocks = 0;
+};
+
+// The stencil family  (A = the Jacobian of poissonfunctions.c:117-258 on this level):
+//   APPLY      out = A u                                   [+ dot(u, A u) -> dot_out]
+//   LIN        out = cb*u + cg*(b - A u)
+//   LIN_PM1    out = ca*pm1 + cb*u + cg*(b - A u)          (out may alias pm1)
+//   LIN_BU     out = cb*u + cg*(u - A u)                   (b == u, loaded once)
+enum StencilMode { ST_APPLY = 0, ST_APPLY_DOT, ST_LIN, ST_LIN_PM1, ST_LIN_BU };
+
+struct StencilOp {
+    int mode;
+    const double *u;      // stencil operand; ghost planes readable when the slab is interior
+    const double *b;
+    const double *pm1;
+    double *out;
+    double ca, cb, cg;
+    double *dot_out;      // device scalar for ST_APPLY_DOT
+};
+
+int launch_stencil(cudaStream_t st, const LevelDesc &L, const StencilOp &op, const Reducer &red);
+// true when the TMA-staged plane-marching kernel handles this level (big 3-D grids)
+bool stencil_fast_eligible(const LevelDesc &L);
+
+// transfer (DMDA Q1, R = P^T)
+int launch_restrict(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *rf, double *bc);
+int launch_prolong_add(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *xc, double *xf);
+
+// vector kernels (n = local length)
+int launch_dot2(cudaStream_t st, long long n, const double *x, const double *y, double *out2, const Reducer &red);
+int launch_dotn(cudaStream_t st, long long n, const double *x, const double *y, double *out1, const Reducer &red);
+int launch_absmax(cudaStream_t st, long long n, const double *x, double *out1, const Reducer &red);
+// x += a p ; r -= a w   with a = num[0]/den[0] read on device
+int launch_axpy2(cudaStream_t st, long long n, const double *num, const double *den, const double *p,
+                 const double *w, double *x, double *r);
+// p = z + (num/den) p ; first != 0: p = z
+int launch_aypx_dev(cudaStream_t st, long long n, const double *num, const double *den, const double *z, double *p,
+                    int first);
+int launch_axpy(cudaStream_t st, long long n, double a, const double *x, double *y);
+int launch_aypx(cudaStream_t st, long long n, double a, const double *x, double *y);
+int launch_set(cudaStream_t st, long long n, double a, double *y);
+int launch_scale_copy(cudaStream_t st, long long n, double a, const double *x, double *y);   // y = a x
+int launch_axpby_out(cudaStream_t st, long long n, double a, const double *x, double b, const double *y,
+                     double *out);                                                              // out = a x + b y
+
+// dense coarse solve x = Ainv b   (n x n, row-major Ainv)
+int launch_dense_matvec(cudaStream_t st, int n, const double *Ainv, const double *b, double *x);
+
+// fish problem
+int launch_fish_sample(cudaStream_t st, const LevelDesc &L, int dim, int problem, double c0, double c1, double c2,
+                       double *f, double *gb);
+int launch_initial_state(cudaStream_t st, const LevelDesc &L, const double *gb, int gonboundary, double *u);
+int launch_poisson_function(cudaStream_t st, const LevelDesc &L, int dim, double c0, const double *u, const double *f,
+                            const double *gb, double *F);
+
+}  // namespace p4b

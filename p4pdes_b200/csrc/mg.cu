@@ -1,0 +1,1112 @@
+// mg.cu -- context, level hierarchy, multigrid cycle, preconditioned CG and the C ABI (p4b200.h).
+//
+// Restates, B200-first, what PETSc does for `./fish -pc_type mg`:
+//   PCSetUp_MG   -> p4b_mg_create : levels by DMDA coarsening, rediscretised constant-coefficient
+//                   operators (fish.c:7), Chebyshev targets, dense inverse of the coarsest operator
+//   PCApply_MG   -> Mg::cycle     : multiplicative V/W cycle, R = P^T, Chebyshev/Jacobi smoothing
+//   KSPSolve_CG  -> Mg::cg        : preconditioned-norm CG; all scalars stay on the device, one
+//                   8-byte D2H per iteration for the convergence test
+// Multi-GPU: slabs of the slowest dimension, ghost planes by grouped ncclSend/ncclRecv, dot products
+// by ncclAllReduce, small levels replicated (the PCREDUNDANT idea applied to whole levels).
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "kernels.h"
+
+namespace p4b {
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+long long g_launch_count = 0;
+void set_error(const std::string &m) { g_err = m; }
+int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code ? code : 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen: the library has no link-time NCCL dependency, so a single-GPU host never
+// needs it and a torch process reuses the libnccl.so.2 torch already loaded.
+// ------------------------------------------------------------------------------------------------
+struct Nccl {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static Nccl g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.h) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *nm : names) {
+        h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(80, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define LD(field, sym)                                                   \
+    *(void **)(&g_nccl.field) = dlsym(h, sym);                           \
+    if (!g_nccl.field) return fail(80, "libnccl lacks symbol %s", sym)
+    LD(GetUniqueId, "ncclGetUniqueId");
+    LD(CommInitRank, "ncclCommInitRank");
+    LD(CommDestroy, "ncclCommDestroy");
+    LD(AllReduce, "ncclAllReduce");
+    LD(Broadcast, "ncclBroadcast");
+    LD(Send, "ncclSend");
+    LD(Recv, "ncclRecv");
+    LD(GroupStart, "ncclGroupStart");
+    LD(GroupEnd, "ncclGroupEnd");
+    LD(GetErrorString, "ncclGetErrorString");
+#undef LD
+    g_nccl.h = h;
+    return 0;
+}
+
+#define P4B_NCCL(call)                                                                                 \
+    do {                                                                                               \
+        ncclResult_t r_ = (call);                                                                      \
+        if (r_ != ncclSuccess)                                                                         \
+            return p4b::fail(81, "%s:%d NCCL error %d (%s) in %s", __FILE__, __LINE__, (int)r_,        \
+                             g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?", #call);          \
+    } while (0)
+
+}  // namespace p4b
+
+using namespace p4b;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct p4b_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    Reducer red;
+    double *d_scal = nullptr;      // 16 device doubles: CG scalars
+    double *h_scal = nullptr;      // 16 pinned host doubles
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static int ctx_allreduce(p4b_ctx *c, double *d, int count) {
+    if (c->nranks == 1) return 0;
+    P4B_NCCL(g_nccl.AllReduce(d, d, (size_t)count, ncclFloat64, ncclSum, c->comm, c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// grid -> level descriptor
+// ------------------------------------------------------------------------------------------------
+static int make_desc(const p4b_grid *g, LevelDesc *L) {
+    if (!g || g->dim < 1 || g->dim > 3) return fail(1, "invalid dim for DMDA creation");
+    if (g->cx <= 0 || g->cy <= 0 || g->cz <= 0) return fail(2, "positivity required for coefficients cx,cy,cz");
+    const int m[3] = {g->mx, g->dim >= 2 ? g->my : 1, g->dim >= 3 ? g->mz : 1};
+    for (int d = 0; d < g->dim; d++)
+        if (m[d] < 3) return fail(60, "grid needs at least 3 nodes per dimension (got %d)", m[d]);
+    memset(L, 0, sizeof *L);
+    const double hx = g->Lx / (m[0] - 1);
+    const double hy = g->dim >= 2 ? g->Ly / (m[1] - 1) : 1.0;
+    const double hz = g->dim >= 3 ? g->Lz / (m[2] - 1) : 1.0;
+    if (g->dim == 1) {   // poissonfunctions.c:13-21,130-137
+        L->nx = m[0]; L->ny = 1; L->nz = 1;
+        L->ax = 1; L->ay = 0; L->az = 0;
+        L->cx = g->cx / hx; L->cy = 0; L->cz = 0;
+        L->diag = g->cx * 2.0 / hx;
+        L->vol = hx;
+        L->hx = hx; L->hy = 1; L->hz = 1;
+    } else if (g->dim == 2) {   // :37-40 ; the y direction lives in slot z
+        L->nx = m[0]; L->ny = 1; L->nz = m[1];
+        L->ax = 1; L->ay = 0; L->az = 1;
+        const double scx = g->cx * hy / hx, scy = g->cy * hx / hy;
+        L->cx = scx; L->cy = 0; L->cz = scy;
+        L->diag = 2.0 * (scx + scy);
+        L->vol = hx * hy;
+        L->hx = hx; L->hy = 1; L->hz = hy;
+    } else {   // :77-81
+        L->nx = m[0]; L->ny = m[1]; L->nz = m[2];
+        L->ax = L->ay = L->az = 1;
+        const double dvol = hx * hy * hz;
+        L->cx = g->cx * dvol / (hx * hx);
+        L->cy = g->cy * dvol / (hy * hy);
+        L->cz = g->cz * dvol / (hz * hz);
+        L->diag = 2.0 * (L->cx + L->cy + L->cz);
+        L->vol = dvol;
+        L->hx = hx; L->hy = hy; L->hz = hz;
+    }
+    L->zs = 0;
+    L->zm = L->nz;
+    return 0;
+}
+
+static bool can_coarsen(const p4b_grid &g) {
+    const int m[3] = {g.mx, g.my, g.mz};
+    for (int d = 0; d < g.dim; d++)
+        if (m[d] <= 3 || (m[d] - 1) % 2) return false;
+    return true;
+}
+static p4b_grid coarsen(const p4b_grid &g) {
+    p4b_grid c = g;
+    c.mx = (g.mx - 1) / 2 + 1;
+    if (g.dim >= 2) c.my = (g.my - 1) / 2 + 1;
+    if (g.dim >= 3) c.mz = (g.mz - 1) / 2 + 1;
+    return c;
+}
+
+static double lambda_max(const LevelDesc &L) {
+    const double PI = 3.14159265358979323846;
+    double num = 0, den = 0;
+    if (L.ax) { num += L.cx * cos(PI / (L.nx - 1)); den += L.cx; }
+    if (L.ay) { num += L.cy * cos(PI / (L.ny - 1)); den += L.cy; }
+    if (L.az) { num += L.cz * cos(PI / (L.nz - 1)); den += L.cz; }
+    return 1.0 + num / den;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hierarchy
+// ------------------------------------------------------------------------------------------------
+struct Level {
+    p4b_grid g;
+    LevelDesc d;                 // what the kernels see: this rank's slab (distributed) or the whole grid (replicated)
+    LevelDesc own;               // replicated level fed from a distributed one: the part this rank restricts into
+    bool replicated = false;
+    double emin = 0, emax = 0, lam = 0;
+    std::vector<double> omega;   // Chebyshev omega_i, i >= 1
+    double scale = 0;            // 2/(emax+emin)
+    double *x = nullptr, *b = nullptr, *t = nullptr;   // first owned element of each ghosted vector
+    std::vector<int> zs_all, zm_all;                   // ownership of every rank (2K rule) on this level
+};
+
+struct Prof {
+    bool on = false;
+    struct Rec { int cls; cudaEvent_t a, b; double bytes; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    p4b_kernel_stat stat[P4B_K_NCLASSES];
+};
+
+struct p4b_mg {
+    p4b_ctx *ctx = nullptr;
+    p4b_mg_opts o;
+    std::vector<Level> lev;      // lev[0] coarsest
+    int top = 0;
+    double *arena = nullptr;
+    size_t arena_doubles = 0;
+    double *Ainv = nullptr;      // dense inverse of the coarsest operator
+    int n0 = 0;
+    double *p = nullptr, *w = nullptr, *fbuf = nullptr, *gbuf = nullptr;   // CG vectors / fish scratch
+    Prof prof;
+    cudaGraphExec_t coarse_graph = nullptr;
+    int graph_level = -1;
+};
+
+static double alg_bytes(int cls, double N, double Nc) {
+    switch (cls) {
+        case P4B_K_APPLY_DOT: return 16 * N;
+        case P4B_K_RESIDUAL: return 24 * N;
+        case P4B_K_CHEB_ZERO: return 16 * N;
+        case P4B_K_CHEB_FIRST: return 24 * N;
+        case P4B_K_CHEB_NEXT: return 32 * N;
+        case P4B_K_RESTRICT: return 8 * N + 8 * Nc;
+        case P4B_K_PROLONG: return 16 * N + 8 * Nc;
+        case P4B_K_AXPY2: return 48 * N;
+        case P4B_K_DOT2: return 16 * N;
+        case P4B_K_AYPX: return 24 * N;
+        case P4B_K_RESID_RESTRICT: return 16 * N + 8 * Nc;
+    }
+    return 0;
+}
+
+static const char *k_names[P4B_K_NCLASSES] = {"apply_dot", "residual", "cheb_zero", "cheb_first", "cheb_next", "restrict",
+                                              "prolong_add", "axpy2", "dot2", "aypx", "resid_restrict"};
+
+// RAII-free profiling bracket: only finest-level launches are timed
+struct ProfScope {
+    p4b_mg *m;
+    int idx = -1;
+    ProfScope(p4b_mg *mg, int level, int cls) : m(mg) {
+        if (!m->prof.on || level != m->top) return;
+        Prof &P = m->prof;
+        while (P.pool.size() < P.used + 2) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            P.pool.push_back(e);
+        }
+        Prof::Rec r;
+        r.cls = cls;
+        r.a = P.pool[P.used++];
+        r.b = P.pool[P.used++];
+        const Level &L = m->lev[level];
+        const double N = (double)L.d.nlocal();
+        const double Nc = level > 0 ? (double)m->lev[level - 1].d.nglobal() / (m->ctx->nranks) : 0.0;
+        r.bytes = alg_bytes(cls, N, Nc);
+        cudaEventRecord(r.a, m->ctx->stream);
+        idx = (int)P.recs.size();
+        P.recs.push_back(r);
+    }
+    ~ProfScope() {
+        if (idx >= 0) cudaEventRecord(m->prof.recs[idx].b, m->ctx->stream);
+    }
+};
+
+static void prof_collect(p4b_mg *m) {
+    Prof &P = m->prof;
+    if (!P.on) return;
+    cudaStreamSynchronize(m->ctx->stream);
+    for (auto &r : P.recs) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        P.stat[r.cls].launches++;
+        P.stat[r.cls].ms += ms;
+        P.stat[r.cls].bytes += r.bytes;
+    }
+    P.recs.clear();
+    P.used = 0;
+}
+
+// ghost-plane exchange of a ghosted vector on a distributed level ([PETSc] DMGlobalToLocal)
+static int halo(p4b_mg *m, int l, double *v) {
+    p4b_ctx *c = m->ctx;
+    Level &L = m->lev[l];
+    if (c->nranks == 1 || L.replicated) return 0;
+    const size_t plane = (size_t)L.d.plane();
+    const bool lo = L.d.zs > 0, hi = L.d.zs + L.d.zm < L.d.nz;
+    P4B_NCCL(g_nccl.GroupStart());
+    if (lo) {
+        P4B_NCCL(g_nccl.Send(v, plane, ncclFloat64, c->rank - 1, c->comm, c->stream));
+        P4B_NCCL(g_nccl.Recv(v - plane, plane, ncclFloat64, c->rank - 1, c->comm, c->stream));
+    }
+    if (hi) {
+        P4B_NCCL(g_nccl.Send(v + (size_t)(L.d.zm - 1) * plane, plane, ncclFloat64, c->rank + 1, c->comm, c->stream));
+        P4B_NCCL(g_nccl.Recv(v + (size_t)L.d.zm * plane, plane, ncclFloat64, c->rank + 1, c->comm, c->stream));
+    }
+    P4B_NCCL(g_nccl.GroupEnd());
+    return 0;
+}
+
+// make a replicated level's vector complete on every rank: each rank broadcasts the planes it owns
+static int gather_replicated(p4b_mg *m, int l, double *v) {
+    p4b_ctx *c = m->ctx;
+    Level &L = m->lev[l];
+    if (c->nranks == 1) return 0;
+    const size_t plane = (size_t)L.d.plane();
+    P4B_NCCL(g_nccl.GroupStart());
+    for (int r = 0; r < c->nranks; r++) {
+        if (L.zm_all[r] <= 0) continue;
+        double *part = v + (size_t)L.zs_all[r] * plane;
+        P4B_NCCL(g_nccl.Broadcast(part, part, (size_t)L.zm_all[r] * plane, ncclFloat64, r, c->comm, c->stream));
+    }
+    P4B_NCCL(g_nccl.GroupEnd());
+    return 0;
+}
+
+// ---- smoothers ---------------------------------------------------------------------------------
+static int smooth(p4b_mg *m, int l, bool zero_guess) {
+    Level &L = m->lev[l];
+    cudaStream_t st = m->ctx->stream;
+    const Reducer &red = m->ctx->red;
+    const int its = m->o.smooth_its;
+    if (its <= 0) {
+        if (zero_guess) P4B_CHECK(launch_set(st, L.d.nlocal(), 0.0, L.x));
+        return 0;
+    }
+    StencilOp op;
+    memset(&op, 0, sizeof op);
+    const double s1 = (m->o.smoother == P4B_SMOOTH_RICHARDSON ? 1.0 : L.scale) / L.d.diag;
+    if (m->o.smoother == P4B_SMOOTH_RICHARDSON) {
+        // [PETSc] KSPSolve_Richardson: x <- x + B (b - A x), B = D^-1
+        for (int i = 0; i < its; i++) {
+            if (i == 0 && zero_guess) {
+                ProfScope ps(m, l, P4B_K_CHEB_ZERO);
+                P4B_CHECK(launch_scale_copy(st, L.d.nlocal(), s1, L.b, L.t));
+            } else {
+                P4B_CHECK(halo(m, l, L.x));
+                ProfScope ps(m, l, P4B_K_CHEB_FIRST);
+                op.mode = ST_LIN; op.u = L.x; op.b = L.b; op.out = L.t; op.cb = 1.0; op.cg = s1;
+                P4B_CHECK(launch_stencil(st, L.d, op, red));
+            }
+            std::swap(L.x, L.t);
+        }
+        return 0;
+    }
+    // [PETSc] KSPSolve_Chebyshev, first kind; `its` = number of preconditioner applications
+    if (zero_guess && m->o.fuse && its == 2) {
+        // p1 = s1 b ; p2 = w p1 + w s1 (b - A p1)  ==  cb*b + cg*(b - A b)  with cg = w s1^2, cb = w s1 + w s1 - cg
+        const double w1 = L.omega[0];
+        const double cg = w1 * s1 * s1;
+        const double cb = 2.0 * w1 * s1 - cg;
+        P4B_CHECK(halo(m, l, L.b));
+        ProfScope ps(m, l, P4B_K_CHEB_ZERO);
+        op.mode = ST_LIN_BU; op.u = L.b; op.out = L.x; op.cb = cb; op.cg = cg;
+        return launch_stencil(st, L.d, op, red);
+    }
+    double *pm1 = L.x, *pk = L.t;
+    bool pm1_zero = zero_guess;
+    if (zero_guess) {
+        ProfScope ps(m, l, P4B_K_CHEB_ZERO);
+        P4B_CHECK(launch_scale_copy(st, L.d.nlocal(), s1, L.b, pk));
+    } else {
+        P4B_CHECK(halo(m, l, pm1));
+        ProfScope ps(m, l, P4B_K_CHEB_FIRST);
+        op.mode = ST_LIN; op.u = pm1; op.b = L.b; op.out = pk; op.cb = 1.0; op.cg = s1;
+        P4B_CHECK(launch_stencil(st, L.d, op, red));
+    }
+    for (int i = 1; i < its; i++) {
+        const double w = L.omega[i - 1];
+        P4B_CHECK(halo(m, l, pk));
+        ProfScope ps(m, l, P4B_K_CHEB_NEXT);
+        op.u = pk; op.b = L.b; op.out = pm1; op.cb = w; op.cg = w * s1;
+        if (pm1_zero) {
+            op.mode = ST_LIN;
+        } else {
+            op.mode = ST_LIN_PM1; op.pm1 = pm1; op.ca = 1.0 - w;
+        }
+        P4B_CHECK(launch_stencil(st, L.d, op, red));
+        std::swap(pm1, pk);
+        pm1_zero = false;
+    }
+    // the newest iterate is in pk
+    if (pk != L.x) std::swap(L.x, L.t);
+    return 0;
+}
+
+static int coarse_solve(p4b_mg *m) {
+    Level &L = m->lev[0];
+    return launch_dense_matvec(m->ctx->stream, m->n0, m->Ainv, L.b, L.x);
+}
+
+static int cycle(p4b_mg *m, int l, bool zero_guess) {
+    if (l == 0) return coarse_solve(m);
+    Level &L = m->lev[l];
+    Level &C = m->lev[l - 1];
+    cudaStream_t st = m->ctx->stream;
+    const Reducer &red = m->ctx->red;
+    P4B_CHECK(smooth(m, l, zero_guess));
+    {   // r = b - A x  -> t ;  b_{l-1} = P^T r
+        P4B_CHECK(halo(m, l, L.x));
+        {
+            ProfScope ps(m, l, P4B_K_RESIDUAL);
+            StencilOp op;
+            memset(&op, 0, sizeof op);
+            op.mode = ST_LIN; op.u = L.x; op.b = L.b; op.out = L.t; op.cb = 0.0; op.cg = 1.0;
+            P4B_CHECK(launch_stencil(st, L.d, op, red));
+        }
+        P4B_CHECK(halo(m, l, L.t));
+        const bool boundary = C.replicated && !L.replicated;
+        const LevelDesc &Cd = boundary ? C.own : C.d;
+        double *bc = boundary ? C.b + (size_t)C.own.zs * C.d.plane() : C.b;
+        {
+            ProfScope ps(m, l, P4B_K_RESTRICT);
+            P4B_CHECK(launch_restrict(st, L.d, Cd, L.t, bc));
+        }
+        if (boundary) P4B_CHECK(gather_replicated(m, l - 1, C.b));
+    }
+    const int cycles = (l == 1 || m->o.cycle == P4B_CYCLE_V) ? 1 : 2;
+    for (int c = 0; c < cycles; c++) P4B_CHECK(cycle(m, l - 1, c == 0));
+    P4B_CHECK(halo(m, l - 1, C.x));
+    {
+        ProfScope ps(m, l, P4B_K_PROLONG);
+        P4B_CHECK(launch_prolong_add(st, L.d, C.d, C.x, L.x));
+    }
+    return smooth(m, l, false);
+}
+
+// z = M^-1 r with r already in lev[top].b ; result in lev[top].x
+static int mg_apply_internal(p4b_mg *m) { return cycle(m, m->top, true); }
+
+// ------------------------------------------------------------------------------------------------
+// setup
+// ------------------------------------------------------------------------------------------------
+static int build_coarse_inverse(p4b_mg *m) {
+    const LevelDesc &L = m->lev[0].d;
+    const long long n = L.nglobal();
+    if (n > 2400) return fail(61, "coarsest grid has %lld nodes (> 2400): increase -pc_mg_levels", n);
+    m->n0 = (int)n;
+    std::vector<double> A((size_t)n * n, 0.0);
+    auto bd = [&](int i, int j, int k) {
+        return (L.ax && (i == 0 || i == L.nx - 1)) || (L.ay && (j == 0 || j == L.ny - 1)) ||
+               (L.az && (k == 0 || k == L.nz - 1));
+    };
+    auto id = [&](int i, int j, int k) { return ((size_t)k * L.ny + j) * L.nx + i; };
+    for (int k = 0; k < L.nz; k++)
+        for (int j = 0; j < L.ny; j++)
+            for (int i = 0; i < L.nx; i++) {
+                const size_t p = id(i, j, k);
+                A[p * n + p] = L.diag;
+                if (bd(i, j, k)) continue;
+                if (L.ax) {
+                    if (!bd(i - 1, j, k)) A[p * n + id(i - 1, j, k)] = -L.cx;
+                    if (!bd(i + 1, j, k)) A[p * n + id(i + 1, j, k)] = -L.cx;
+                }
+                if (L.ay) {
+                    if (!bd(i, j - 1, k)) A[p * n + id(i, j - 1, k)] = -L.cy;
+                    if (!bd(i, j + 1, k)) A[p * n + id(i, j + 1, k)] = -L.cy;
+                }
+                if (L.az) {
+                    if (!bd(i, j, k - 1)) A[p * n + id(i, j, k - 1)] = -L.cz;
+                    if (!bd(i, j, k + 1)) A[p * n + id(i, j, k + 1)] = -L.cz;
+                }
+            }
+    // Cholesky A = G G^T (lower), then Ainv = G^-T G^-1   ([PETSc] PCLU on level 0: an exact solve)
+    std::vector<double> G(A);
+    for (long long c = 0; c < n; c++) {
+        double d = G[c * n + c];
+        for (long long q = 0; q < c; q++) d -= G[c * n + q] * G[c * n + q];
+        if (!(d > 0)) return fail(61, "coarsest operator is not positive definite");
+        d = sqrt(d);
+        G[c * n + c] = d;
+        for (long long r = c + 1; r < n; r++) {
+            double s = G[r * n + c];
+            for (long long q = 0; q < c; q++) s -= G[r * n + q] * G[c * n + q];
+            G[r * n + c] = s / d;
+        }
+    }
+    std::vector<double> Gi((size_t)n * n, 0.0);   // G^-1, lower triangular
+    for (long long c = 0; c < n; c++) {
+        Gi[c * n + c] = 1.0 / G[c * n + c];
+        for (long long r = c + 1; r < n; r++) {
+            double s = 0;
+            for (long long q = c; q < r; q++) s -= G[r * n + q] * Gi[q * n + c];
+            Gi[r * n + c] = s / G[r * n + r];
+        }
+    }
+    std::vector<double> Ai((size_t)n * n, 0.0);
+    for (long long r = 0; r < n; r++)
+        for (long long c = 0; c <= r; c++) {
+            double s = 0;
+            for (long long q = r; q < n; q++) s += Gi[q * n + r] * Gi[q * n + c];
+            Ai[r * n + c] = s;
+            Ai[c * n + r] = s;
+        }
+    P4B_CUDA(cudaMalloc(&m->Ainv, sizeof(double) * n * n));
+    P4B_CUDA(cudaMemcpy(m->Ainv, Ai.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static void slab_range(int m, int P, int r, int *s, int *c) {
+    const int base = m / P, rem = m % P;
+    *c = base + (r < rem ? 1 : 0);
+    *s = r * base + (r < rem ? r : rem);
+}
+
+extern "C" {
+
+int p4b_version(void) { return P4B_VERSION; }
+const char *p4b_last_error(void) { return g_err.c_str(); }
+const char *p4b_kernel_name(int c) { return (c >= 0 && c < P4B_K_NCLASSES) ? k_names[c] : "?"; }
+
+int p4b_device_count(int *n) {
+    P4B_CUDA(cudaGetDeviceCount(n));
+    return 0;
+}
+
+int p4b_ctx_create(int device, void *stream, p4b_ctx **out) {
+    if (!out) return fail(62, "null ctx pointer");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(70, "no CUDA device available (%s): p4b200 has no CPU fallback", cudaGetErrorString(e));
+    P4B_CUDA(cudaSetDevice(device));
+    p4b_ctx *c = new p4b_ctx();
+    c->device = device;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        P4B_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    c->red.max_blocks = 1 << 20;
+    P4B_CUDA(cudaMalloc(&c->red.partials, sizeof(double) * 4 * (size_t)c->red.max_blocks));
+    P4B_CUDA(cudaMalloc(&c->red.ticket, sizeof(unsigned int)));
+    P4B_CUDA(cudaMemset(c->red.ticket, 0, sizeof(unsigned int)));
+    P4B_CUDA(cudaMalloc(&c->d_scal, sizeof(double) * 16));
+    P4B_CUDA(cudaMemset(c->d_scal, 0, sizeof(double) * 16));
+    P4B_CUDA(cudaMallocHost(&c->h_scal, sizeof(double) * 16));
+    P4B_CUDA(cudaEventCreate(&c->ev0));
+    P4B_CUDA(cudaEventCreate(&c->ev1));
+    *out = c;
+    return 0;
+}
+
+int p4b_ctx_destroy(p4b_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    cudaFree(c->red.partials);
+    cudaFree(c->red.ticket);
+    cudaFree(c->d_scal);
+    cudaFreeHost(c->h_scal);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int p4b_ctx_sync(p4b_ctx *c) {
+    P4B_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int p4b_comm_unique_id(void *id128) {
+    P4B_CHECK(nccl_load());
+    ncclUniqueId id;
+    P4B_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof id);
+    return 0;
+}
+
+int p4b_comm_init(p4b_ctx *c, const void *id128, int rank, int nranks) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(62, "bad rank %d of %d", rank, nranks);
+    c->rank = rank;
+    c->nranks = nranks;
+    if (nranks == 1) return 0;
+    P4B_CHECK(nccl_load());
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    P4B_CUDA(cudaSetDevice(c->device));
+    P4B_NCCL(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    return 0;
+}
+
+int p4b_slab_range(int m, int nranks, int rank, int *start, int *count) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || m < 0) return fail(62, "bad slab arguments");
+    slab_range(m, nranks, rank, start, count);
+    return 0;
+}
+
+int p4b_malloc(p4b_ctx *c, size_t bytes, void **d) {
+    P4B_CUDA(cudaSetDevice(c->device));
+    P4B_CUDA(cudaMalloc(d, bytes ? bytes : 8));
+    return 0;
+}
+int p4b_free(p4b_ctx *c, void *d) {
+    P4B_CUDA(cudaSetDevice(c->device));
+    P4B_CUDA(cudaStreamSynchronize(c->stream));
+    P4B_CUDA(cudaFree(d));
+    return 0;
+}
+int p4b_memcpy_h2d(p4b_ctx *c, void *dst, const void *src, size_t bytes) {
+    P4B_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    P4B_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+int p4b_memcpy_d2h(p4b_ctx *c, void *dst, const void *src, size_t bytes) {
+    P4B_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    P4B_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- single-slab building blocks ------------------------------------------------------------------
+int p4b_stencil_apply(p4b_ctx *c, const p4b_grid *g, const double *u, double *y) {
+    LevelDesc L;
+    P4B_CHECK(make_desc(g, &L));
+    StencilOp op;
+    memset(&op, 0, sizeof op);
+    op.mode = ST_APPLY; op.u = u; op.out = y;
+    return launch_stencil(c->stream, L, op, c->red);
+}
+
+int p4b_stencil_residual(p4b_ctx *c, const p4b_grid *g, const double *b, const double *u, double *r) {
+    LevelDesc L;
+    P4B_CHECK(make_desc(g, &L));
+    StencilOp op;
+    memset(&op, 0, sizeof op);
+    op.mode = ST_LIN; op.u = u; op.b = b; op.out = r; op.cb = 0.0; op.cg = 1.0;
+    return launch_stencil(c->stream, L, op, c->red);
+}
+
+int p4b_lambda_max_jacobi(const p4b_grid *g, double *lam) {
+    LevelDesc L;
+    P4B_CHECK(make_desc(g, &L));
+    *lam = lambda_max(L);
+    return 0;
+}
+
+static void cheb_omegas(double emin, double emax, int its, double *scale, std::vector<double> *omega) {
+    *scale = 2.0 / (emax + emin);
+    const double alpha = 1.0 - (*scale) * emin;
+    const double mu = 1.0 / alpha, omegaprod = 2.0 / alpha;
+    double cm1 = 1.0, ck = mu;
+    omega->clear();
+    for (int i = 1; i < its; i++) {
+        const double cp1 = 2.0 * mu * ck - cm1;
+        omega->push_back(omegaprod * ck / cp1);
+        cm1 = ck;
+        ck = cp1;
+    }
+}
+
+int p4b_cheb_jacobi(p4b_ctx *c, const p4b_grid *g, double emin, double emax, int its, int zero_guess,
+                    const double *b, double *x, double *work) {
+    LevelDesc L;
+    P4B_CHECK(make_desc(g, &L));
+    if (its <= 0) return 0;
+    double scale;
+    std::vector<double> om;
+    cheb_omegas(emin, emax, its, &scale, &om);
+    const double s1 = scale / L.diag;
+    const long long n = L.nlocal();
+    StencilOp op;
+    memset(&op, 0, sizeof op);
+    double *pm1 = x, *pk = work;
+    bool pm1_zero = zero_guess != 0;
+    if (zero_guess) {
+        P4B_CHECK(launch_scale_copy(c->stream, n, s1, b, pk));
+    } else {
+        op.mode = ST_LIN; op.u = pm1; op.b = b; op.out = pk; op.cb = 1.0; op.cg = s1;
+        P4B_CHECK(launch_stencil(c->stream, L, op, c->red));
+    }
+    for (int i = 1; i < its; i++) {
+        const double w = om[i - 1];
+        op.u = pk; op.b = b; op.out = pm1; op.cb = w; op.cg = w * s1;
+        if (pm1_zero) {
+            op.mode = ST_LIN;
+        } else {
+            op.mode = ST_LIN_PM1; op.pm1 = pm1; op.ca = 1.0 - w;
+        }
+        P4B_CHECK(launch_stencil(c->stream, L, op, c->red));
+        std::swap(pm1, pk);
+        pm1_zero = false;
+    }
+    if (pk != x) P4B_CUDA(cudaMemcpyAsync(x, pk, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+int p4b_restrict(p4b_ctx *c, const p4b_grid *gf, const double *rf, double *bc) {
+    if (!can_coarsen(*gf)) return fail(60, "grid cannot be coarsened");
+    p4b_grid gc = coarsen(*gf);
+    LevelDesc F, C;
+    P4B_CHECK(make_desc(gf, &F));
+    P4B_CHECK(make_desc(&gc, &C));
+    return launch_restrict(c->stream, F, C, rf, bc);
+}
+
+int p4b_prolong_add(p4b_ctx *c, const p4b_grid *gf, const double *xc, double *xf) {
+    if (!can_coarsen(*gf)) return fail(60, "grid cannot be coarsened");
+    p4b_grid gc = coarsen(*gf);
+    LevelDesc F, C;
+    P4B_CHECK(make_desc(gf, &F));
+    P4B_CHECK(make_desc(&gc, &C));
+    return launch_prolong_add(c->stream, F, C, xc, xf);
+}
+
+int p4b_residual_restrict(p4b_ctx *c, const p4b_grid *gf, const double *b, const double *x, double *bc) {
+    // unfused composition (scratch vector from the async pool); the fused kernel replaces it inside Mg
+    LevelDesc F;
+    P4B_CHECK(make_desc(gf, &F));
+    double *t = nullptr;
+    P4B_CUDA(cudaMallocAsync((void **)&t, sizeof(double) * F.nlocal(), c->stream));
+    int rc = p4b_stencil_residual(c, gf, b, x, t);
+    if (!rc) rc = p4b_restrict(c, gf, t, bc);
+    cudaFreeAsync(t, c->stream);
+    return rc;
+}
+
+static int fetch_scal(p4b_ctx *c, const double *d, int count, double *h) {
+    P4B_CUDA(cudaMemcpyAsync(c->h_scal, d, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
+    P4B_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < count; i++) h[i] = c->h_scal[i];
+    return 0;
+}
+
+int p4b_vec_dot(p4b_ctx *c, size_t n, const double *x, const double *y, double *res) {
+    P4B_CHECK(launch_dotn(c->stream, (long long)n, x, y, c->d_scal + 8, c->red));
+    P4B_CHECK(ctx_allreduce(c, c->d_scal + 8, 1));
+    return fetch_scal(c, c->d_scal + 8, 1, res);
+}
+int p4b_vec_norm2(p4b_ctx *c, size_t n, const double *x, double *res) {
+    P4B_CHECK(p4b_vec_dot(c, n, x, x, res));
+    *res = sqrt(*res);
+    return 0;
+}
+int p4b_vec_norminf(p4b_ctx *c, size_t n, const double *x, double *res) {
+    P4B_CHECK(launch_absmax(c->stream, (long long)n, x, c->d_scal + 8, c->red));
+    if (c->nranks > 1)
+        P4B_NCCL(g_nccl.AllReduce(c->d_scal + 8, c->d_scal + 8, 1, ncclFloat64, ncclMax, c->comm, c->stream));
+    return fetch_scal(c, c->d_scal + 8, 1, res);
+}
+int p4b_vec_axpy(p4b_ctx *c, size_t n, double a, const double *x, double *y) {
+    return launch_axpy(c->stream, (long long)n, a, x, y);
+}
+int p4b_vec_aypx(p4b_ctx *c, size_t n, double a, const double *x, double *y) {
+    return launch_aypx(c->stream, (long long)n, a, x, y);
+}
+int p4b_vec_set(p4b_ctx *c, size_t n, double a, double *y) { return launch_set(c->stream, (long long)n, a, y); }
+
+// ---- fish problem -----------------------------------------------------------------------------------
+int p4b_fish_sample(p4b_ctx *c, const p4b_grid *g, int problem, double *f, double *gb) {
+    LevelDesc L;
+    P4B_CHECK(make_desc(g, &L));
+    if (problem == P4B_PROBLEM_MANUEXP && (g->cx != 1.0 || g->cy != 1.0 || g->cz != 1.0))
+        return fail(3, "cx=cy=cz=1 required for problem MANUEXP");   // fish.c:191-193
+    return launch_fish_sample(c->stream, L, g->dim, problem, g->cx, g->cy, g->cz, f, gb);
+}
+int p4b_initial_state(p4b_ctx *c, const p4b_grid *g, const double *gb, int gonboundary, double *u) {
+    LevelDesc L;
+    P4B_CHECK(make_desc(g, &L));
+    if (gonboundary && !gb) return fail(62, "gb required when gonboundary is set");
+    return launch_initial_state(c->stream, L, gb, gonboundary, u);
+}
+int p4b_poisson_function(p4b_ctx *c, const p4b_grid *g, const double *u, const double *f, const double *gb,
+                         double *F) {
+    LevelDesc L;
+    P4B_CHECK(make_desc(g, &L));
+    return launch_poisson_function(c->stream, L, g->dim, g->cx, u, f, gb, F);
+}
+
+// ---- PCMG -------------------------------------------------------------------------------------------
+int p4b_mg_default_opts(p4b_mg_opts *o) {
+    memset(o, 0, sizeof *o);
+    o->levels = 0;
+    o->cycle = P4B_CYCLE_V;
+    o->smoother = P4B_SMOOTH_CHEBYSHEV;
+    o->smooth_its = 2;
+    o->emin = 0; o->emax = 0;
+    o->est_lo = 0.1; o->est_hi = 1.1;
+    o->fuse = 1;
+    o->use_graph = 0;
+    return 0;
+}
+
+int p4b_mg_create(p4b_ctx *c, const p4b_grid *g, const p4b_mg_opts *oin, p4b_mg **out) {
+    p4b_mg_opts o;
+    if (oin) o = *oin; else p4b_mg_default_opts(&o);
+    if (o.cycle != P4B_CYCLE_V && o.cycle != P4B_CYCLE_W) return fail(62, "unknown -pc_mg_cycle_type");
+    if (o.smoother != P4B_SMOOTH_CHEBYSHEV && o.smoother != P4B_SMOOTH_RICHARDSON)
+        return fail(62, "smoother must be chebyshev or richardson (Jacobi PC); SOR is sequential and not provided");
+    P4B_CUDA(cudaSetDevice(c->device));
+    p4b_mg *m = new p4b_mg();
+    m->ctx = c;
+    m->o = o;
+    // level grids, finest first
+    std::vector<p4b_grid> gs;
+    gs.push_back(*g);
+    while ((o.levels <= 0 || (int)gs.size() < o.levels) && can_coarsen(gs.back())) gs.push_back(coarsen(gs.back()));
+    if (o.levels > 0 && (int)gs.size() < o.levels) {
+        delete m;
+        return fail(60, "cannot build %d multigrid levels from this grid (got %d)", o.levels, (int)gs.size());
+    }
+    const int nl = (int)gs.size();
+    m->lev.resize(nl);
+    m->top = nl - 1;
+    const int P = c->nranks, R = c->rank;
+    for (int l = 0; l < nl; l++) {
+        Level &L = m->lev[l];
+        L.g = gs[nl - 1 - l];
+        int rc = make_desc(&L.g, &L.d);
+        if (rc) { delete m; return rc; }
+        L.lam = lambda_max(L.d);
+        if (o.emax > 0) { L.emin = o.emin; L.emax = o.emax; }
+        else { L.emin = o.est_lo * L.lam; L.emax = o.est_hi * L.lam; }
+        cheb_omegas(L.emin, L.emax, o.smooth_its, &L.scale, &L.omega);
+    }
+    // slab ownership: finest by p4b_slab_range, coarser by "coarse plane K belongs to the owner of fine 2K"
+    if (P > 1 && g->dim == 1) { delete m; return fail(60, "1-D grids are not distributed"); }
+    for (int l = nl - 1; l >= 0; l--) {
+        Level &L = m->lev[l];
+        L.zs_all.resize(P);
+        L.zm_all.resize(P);
+        for (int r = 0; r < P; r++) {
+            if (l == nl - 1) {
+                slab_range(L.d.nz, P, r, &L.zs_all[r], &L.zm_all[r]);
+            } else {
+                const Level &Fn = m->lev[l + 1];
+                const int fs = Fn.zs_all[r], fe = Fn.zs_all[r] + Fn.zm_all[r];   // [fs, fe)
+                const int ks = (fs + 1) / 2, ke = (fe - 1) / 2;                   // K with fs <= 2K <= fe-1
+                L.zs_all[r] = ks;
+                L.zm_all[r] = (Fn.zm_all[r] > 0 && ke >= ks) ? ke - ks + 1 : 0;
+            }
+        }
+    }
+    // replicate small levels: every rank must own >= 2 planes on a distributed level, and levels at or
+    // below rep_points nodes are cheaper to compute redundantly than to exchange ghosts for
+    const long long rep_points = 70LL * 70 * 70;
+    int lrep = -1;
+    if (P > 1) {
+        lrep = 0;
+        for (int l = 0; l < nl; l++) {
+            int minzm = 1 << 30;
+            for (int r = 0; r < P; r++) minzm = std::min(minzm, m->lev[l].zm_all[r]);
+            if (minzm < 2 || m->lev[l].d.nglobal() <= rep_points) lrep = l;
+        }
+        if (lrep >= nl - 1) lrep = nl - 1;
+    }
+    for (int l = 0; l < nl; l++) {
+        Level &L = m->lev[l];
+        L.own = L.d;
+        L.own.zs = L.zs_all[R];
+        L.own.zm = L.zm_all[R];
+        L.replicated = (P > 1 && l <= lrep);
+        if (P > 1 && !L.replicated) L.d = L.own;
+        if (P == 1) L.replicated = false;
+    }
+    if (P > 1 && m->lev[m->top].replicated) {
+        delete m;
+        return fail(60, "grid too small to distribute over %d ranks", P);
+    }
+    // arena: ghosted vectors x, b, t per level (+ p, w and two scratch vectors on the finest)
+    auto vec_doubles = [](const LevelDesc &d) {
+        size_t n = (size_t)d.plane() * (d.zm + 2) + 8;
+        return (n + 31) & ~(size_t)31;
+    };
+    size_t total = 0;
+    for (int l = 0; l < nl; l++) total += vec_doubles(m->lev[l].d) * (l == nl - 1 ? 7 : 3);
+    m->arena_doubles = total;
+    cudaError_t e = cudaMalloc(&m->arena, sizeof(double) * total);
+    if (e != cudaSuccess) {
+        delete m;
+        return fail(71, "cudaMalloc of %.2f GB for the level hierarchy failed: %s", total * 8e-9, cudaGetErrorString(e));
+    }
+    P4B_CUDA(cudaMemsetAsync(m->arena, 0, sizeof(double) * total, c->stream));
+    size_t off = 0;
+    auto carve = [&](const LevelDesc &d) {
+        // owned start is 16-byte aligned: base is 256-byte aligned, skip (4 or 5) + plane doubles
+        const size_t plane = (size_t)d.plane();
+        const size_t lead = 4 + (plane & 1);
+        double *ptr = m->arena + off + lead + plane;
+        off += vec_doubles(d);
+        return ptr;
+    };
+    for (int l = 0; l < nl; l++) {
+        Level &L = m->lev[l];
+        L.x = carve(L.d);
+        L.b = carve(L.d);
+        L.t = carve(L.d);
+        if (l == nl - 1) {
+            m->p = carve(L.d);
+            m->w = carve(L.d);
+            m->fbuf = carve(L.d);
+            m->gbuf = carve(L.d);
+        }
+    }
+    int rc = build_coarse_inverse(m);
+    if (rc) { cudaFree(m->arena); delete m; return rc; }
+    memset(m->prof.stat, 0, sizeof m->prof.stat);
+    P4B_CUDA(cudaStreamSynchronize(c->stream));
+    *out = m;
+    return 0;
+}
+
+int p4b_mg_destroy(p4b_mg *m) {
+    if (!m) return 0;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    for (auto e : m->prof.pool) cudaEventDestroy(e);
+    if (m->coarse_graph) cudaGraphExecDestroy(m->coarse_graph);
+    cudaFree(m->arena);
+    cudaFree(m->Ainv);
+    delete m;
+    return 0;
+}
+
+int p4b_mg_nlevels(p4b_mg *m, int *n) { *n = (int)m->lev.size(); return 0; }
+
+int p4b_mg_level_info(p4b_mg *m, int l, int *mm, double *eig) {
+    if (l < 0 || l >= (int)m->lev.size()) return fail(62, "level out of range");
+    const Level &L = m->lev[l];
+    if (mm) { mm[0] = L.g.mx; mm[1] = L.g.dim >= 2 ? L.g.my : 1; mm[2] = L.g.dim >= 3 ? L.g.mz : 1; }
+    if (eig) { eig[0] = L.emin; eig[1] = L.emax; }
+    return 0;
+}
+
+int p4b_mg_local_range(p4b_mg *m, int *start, int *count, size_t *nlocal) {
+    const LevelDesc &d = m->lev[m->top].d;
+    if (start) *start = d.zs;
+    if (count) *count = d.zm;
+    if (nlocal) *nlocal = (size_t)d.nlocal();
+    return 0;
+}
+
+int p4b_mg_apply(p4b_mg *m, const double *r, double *z) {
+    Level &T = m->lev[m->top];
+    cudaStream_t st = m->ctx->stream;
+    const size_t bytes = sizeof(double) * (size_t)T.d.nlocal();
+    P4B_CUDA(cudaMemcpyAsync(T.b, r, bytes, cudaMemcpyDeviceToDevice, st));
+    P4B_CHECK(mg_apply_internal(m));
+    P4B_CUDA(cudaMemcpyAsync(z, T.x, bytes, cudaMemcpyDeviceToDevice, st));
+    prof_collect(m);
+    return 0;
+}
+
+// [PETSc] KSPSolve_CG.  r lives in lev[top].b, z in lev[top].x (so PCApply is in place).
+int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol, double abstol, int max_it,
+                 p4b_ksp_result *res) {
+    p4b_ctx *c = m->ctx;
+    cudaStream_t st = c->stream;
+    Level &T = m->lev[m->top];
+    const long long n = T.d.nlocal();
+    const Reducer &red = c->red;
+    double *S = c->d_scal;   // [0,1]=(zz,zr) parity 0 ; [2,3] parity 1 ; [4] = (p,w)
+    p4b_ksp_result R;
+    memset(&R, 0, sizeof R);
+    if (pc_type != P4B_PC_NONE && pc_type != P4B_PC_JACOBI && pc_type != P4B_PC_MG)
+        return fail(62, "unknown pc_type %d (the device path provides none, jacobi, mg)", pc_type);
+    P4B_CUDA(cudaSetDevice(c->device));
+    P4B_CUDA(cudaEventRecord(c->ev0, st));
+    P4B_CUDA(cudaMemcpyAsync(T.b, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    P4B_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n, st));
+    auto precond = [&]() -> int {
+        if (pc_type == P4B_PC_MG) return mg_apply_internal(m);
+        return launch_scale_copy(st, n, pc_type == P4B_PC_JACOBI ? 1.0 / T.d.diag : 1.0, T.b, T.x);
+    };
+    int q = 0;
+    double h[2];
+    P4B_CHECK(precond());
+    {
+        ProfScope ps(m, m->top, P4B_K_DOT2);
+        P4B_CHECK(launch_dot2(st, n, T.x, T.b, S + 2 * q, red));
+    }
+    P4B_CHECK(ctx_allreduce(c, S + 2 * q, 2));
+    P4B_CHECK(fetch_scal(c, S + 2 * q, 2, h));
+    double dp = sqrt(h[0]);
+    R.rnorm0 = dp;
+    R.hist[R.nhist++] = dp;
+    const double ttol = fmax(rtol * dp, abstol);
+    int its = 0;
+    R.reason = 0;
+    if (!(dp == dp)) R.reason = P4B_DIVERGED_NAN;
+    else if (dp <= ttol) R.reason = (dp <= abstol) ? P4B_CONVERGED_ATOL : P4B_CONVERGED_RTOL;
+    while (!R.reason) {
+        if (its >= max_it) { R.reason = P4B_DIVERGED_ITS; break; }
+        {
+            ProfScope ps(m, m->top, P4B_K_AYPX);
+            P4B_CHECK(launch_aypx_dev(st, n, S + 2 * q + 1, S + 2 * (1 - q) + 1, T.x, m->p, its == 0));
+        }
+        P4B_CHECK(halo(m, m->top, m->p));
+        {
+            ProfScope ps(m, m->top, P4B_K_APPLY_DOT);
+            StencilOp op;
+            memset(&op, 0, sizeof op);
+            op.mode = ST_APPLY_DOT; op.u = m->p; op.out = m->w; op.dot_out = S + 4;
+            P4B_CHECK(launch_stencil(st, T.d, op, red));
+        }
+        P4B_CHECK(ctx_allreduce(c, S + 4, 1));
+        {
+            ProfScope ps(m, m->top, P4B_K_AXPY2);
+            P4B_CHECK(launch_axpy2(st, n, S + 2 * q + 1, S + 4, m->p, m->w, x, T.b));
+        }
+        P4B_CHECK(precond());
+        q ^= 1;
+        {
+            ProfScope ps(m, m->top, P4B_K_DOT2);
+            P4B_CHECK(launch_dot2(st, n, T.x, T.b, S + 2 * q, red));
+        }
+        P4B_CHECK(ctx_allreduce(c, S + 2 * q, 2));
+        P4B_CHECK(fetch_scal(c, S + 2 * q, 2, h));
+        dp = sqrt(h[0]);
+        its++;
+        if (R.nhist < P4B_MAX_HIST) R.hist[R.nhist++] = dp;
+        if (!(dp == dp)) R.reason = P4B_DIVERGED_NAN;
+        else if (dp <= ttol) R.reason = (dp <= abstol) ? P4B_CONVERGED_ATOL : P4B_CONVERGED_RTOL;
+    }
+    P4B_CUDA(cudaEventRecord(c->ev1, st));
+    P4B_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0;
+    P4B_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    R.its = its;
+    R.rnorm = dp;
+    R.solve_ms = ms;
+    prof_collect(m);
+    if (res) *res = R;
+    return 0;
+}
+
+int p4b_cg_solve_host(p4b_mg *m, int pc_type, const double *bh, double *xh, double rtol, double abstol, int max_it,
+                      p4b_ksp_result *res) {
+    p4b_ctx *c = m->ctx;
+    Level &T = m->lev[m->top];
+    const size_t bytes = sizeof(double) * (size_t)T.d.nlocal();
+    P4B_CUDA(cudaMemcpyAsync(m->fbuf, bh, bytes, cudaMemcpyHostToDevice, c->stream));
+    P4B_CHECK(p4b_cg_solve(m, pc_type, m->fbuf, m->gbuf, rtol, abstol, max_it, res));
+    P4B_CUDA(cudaMemcpyAsync(xh, m->gbuf, bytes, cudaMemcpyDeviceToHost, c->stream));
+    P4B_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// [PETSc] SNESSolve_KSPONLY: F0 = F(u0); J y = F0; u = u0 - y.
+int p4b_fish_solve_host(p4b_mg *m, const double *fh, const double *gh, double *uh, double rtol, double abstol,
+                        int max_it, p4b_ksp_result *res) {
+    p4b_ctx *c = m->ctx;
+    cudaStream_t st = c->stream;
+    Level &T = m->lev[m->top];
+    const long long n = T.d.nlocal();
+    const size_t bytes = sizeof(double) * (size_t)n;
+    // f -> fbuf, g -> gbuf, u -> w (ghosted; halo for F(u)), F -> p, y -> t... keep x,b,t for the solver
+    P4B_CUDA(cudaMemcpyAsync(m->fbuf, fh, bytes, cudaMemcpyHostToDevice, st));
+    P4B_CUDA(cudaMemcpyAsync(m->gbuf, gh, bytes, cudaMemcpyHostToDevice, st));
+    P4B_CUDA(cudaMemcpyAsync(m->w, uh, bytes, cudaMemcpyHostToDevice, st));
+    P4B_CHECK(halo(m, m->top, m->w));
+    P4B_CHECK(halo(m, m->top, m->gbuf));
+    P4B_CHECK(launch_poisson_function(st, T.d, T.g.dim, T.g.cx, m->w, m->fbuf, m->gbuf, m->p));
+    // F0 must survive the solve (p and w are CG work vectors): move F0 to fbuf, u0 to gbuf
+    P4B_CUDA(cudaMemcpyAsync(m->fbuf, m->p, bytes, cudaMemcpyDeviceToDevice, st));
+    P4B_CUDA(cudaMemcpyAsync(m->gbuf, m->w, bytes, cudaMemcpyDeviceToDevice, st));
+    double *y = nullptr;
+    P4B_CUDA(cudaMallocAsync((void **)&y, bytes, st));
+    int rc = p4b_cg_solve(m, P4B_PC_MG, m->fbuf, y, rtol, abstol, max_it, res);
+    if (!rc) rc = launch_axpy(st, n, -1.0, y, m->gbuf);
+    cudaFreeAsync(y, st);
+    if (rc) return rc;
+    P4B_CUDA(cudaMemcpyAsync(uh, m->gbuf, bytes, cudaMemcpyDeviceToHost, st));
+    P4B_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// b = F(u0) for fish.c's built-in problems on this rank's slab (any of the outputs may be NULL):
+// fish.c:186-187 (function tables), :237-238 (InitialState), SNESComputeFunction at :239.
+int p4b_mg_fish_setup(p4b_mg *m, int problem, int gonboundary, double *b_out, double *u0_out, double *uexact_out) {
+    p4b_ctx *c = m->ctx;
+    cudaStream_t st = c->stream;
+    Level &T = m->lev[m->top];
+    const size_t bytes = sizeof(double) * (size_t)T.d.nlocal();
+    if (problem == P4B_PROBLEM_MANUEXP && (T.g.cx != 1.0 || T.g.cy != 1.0 || T.g.cz != 1.0))
+        return fail(3, "cx=cy=cz=1 required for problem MANUEXP");
+    P4B_CHECK(launch_fish_sample(st, T.d, T.g.dim, problem, T.g.cx, T.g.cy, T.g.cz, m->fbuf, m->gbuf));
+    P4B_CHECK(launch_initial_state(st, T.d, m->gbuf, gonboundary, m->w));
+    P4B_CHECK(halo(m, m->top, m->w));
+    P4B_CHECK(halo(m, m->top, m->gbuf));
+    P4B_CHECK(launch_poisson_function(st, T.d, T.g.dim, T.g.cx, m->w, m->fbuf, m->gbuf, m->p));
+    if (b_out) P4B_CUDA(cudaMemcpyAsync(b_out, m->p, bytes, cudaMemcpyDeviceToDevice, st));
+    if (u0_out) P4B_CUDA(cudaMemcpyAsync(u0_out, m->w, bytes, cudaMemcpyDeviceToDevice, st));
+    if (uexact_out) P4B_CUDA(cudaMemcpyAsync(uexact_out, m->gbuf, bytes, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// ---- profiler -----------------------------------------------------------------------------------------
+int p4b_profile_enable(p4b_mg *m, int on) { m->prof.on = on != 0; return 0; }
+int p4b_profile_reset(p4b_mg *m) {
+    memset(m->prof.stat, 0, sizeof m->prof.stat);
+    return 0;
+}
+int p4b_profile_get(p4b_mg *m, int cls, p4b_kernel_stat *out) {
+    if (cls < 0 || cls >= P4B_K_NCLASSES) return fail(62, "kernel class out of range");
+    *out = m->prof.stat[cls];
+    return 0;
+}
+long long p4b_launch_count(void) { return g_launch_count; }
+
+}  // extern "C"

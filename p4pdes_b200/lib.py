@@ -1,0 +1,152 @@
+"""ctypes bindings of include/p4b200.h (the C ABI of libp4b200.so).
+
+PyTorch supplies device memory (tensors), streams and torch.distributed; every numerical
+operation goes through the C ABI into the hand-written sm_100a kernels.  There is no
+fallback: if the library is missing, or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libp4b200.so")
+
+P4B_MAX_HIST = 256
+CYCLE_V, CYCLE_W = 1, 2
+SMOOTH_CHEBYSHEV, SMOOTH_RICHARDSON = 0, 1
+PC_NONE, PC_JACOBI, PC_MG = 0, 1, 2
+PROBLEMS = {"manupoly": 0, "manuexp": 1, "zero": 2}
+CONVERGED_RTOL, CONVERGED_ATOL, DIVERGED_ITS, DIVERGED_NAN = 2, 3, -3, -9
+REASONS = {2: "CONVERGED_RTOL", 3: "CONVERGED_ATOL", -3: "DIVERGED_ITS", -9: "DIVERGED_NANORINF"}
+KERNEL_CLASSES = ["apply_dot", "residual", "cheb_zero", "cheb_first", "cheb_next", "restrict", "prolong_add",
+                  "axpy2", "dot2", "aypx", "resid_restrict"]
+
+
+class Grid(C.Structure):
+    _fields_ = [("dim", C.c_int), ("mx", C.c_int), ("my", C.c_int), ("mz", C.c_int),
+                ("Lx", C.c_double), ("Ly", C.c_double), ("Lz", C.c_double),
+                ("cx", C.c_double), ("cy", C.c_double), ("cz", C.c_double)]
+
+    @property
+    def n(self):
+        return self.mx * self.my * self.mz
+
+    @property
+    def m(self):
+        return (self.mx, self.my, self.mz)
+
+
+class MGOpts(C.Structure):
+    _fields_ = [("levels", C.c_int), ("cycle", C.c_int), ("smoother", C.c_int), ("smooth_its", C.c_int),
+                ("emin", C.c_double), ("emax", C.c_double), ("est_lo", C.c_double), ("est_hi", C.c_double),
+                ("fuse", C.c_int), ("use_graph", C.c_int)]
+
+
+class KSPResult(C.Structure):
+    _fields_ = [("its", C.c_int), ("reason", C.c_int), ("rnorm0", C.c_double), ("rnorm", C.c_double),
+                ("nhist", C.c_int), ("hist", C.c_double * P4B_MAX_HIST), ("solve_ms", C.c_double)]
+
+    @property
+    def history(self):
+        return [self.hist[i] for i in range(self.nhist)]
+
+
+class KernelStat(C.Structure):
+    _fields_ = [("launches", C.c_longlong), ("ms", C.c_double), ("bytes", C.c_double)]
+
+
+class P4BError(RuntimeError):
+    pass
+
+
+_P = C.c_void_p
+_D = C.c_void_p      # device pointer
+_SIGS = {
+    "p4b_version": (C.c_int, []),
+    "p4b_last_error": (C.c_char_p, []),
+    "p4b_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "p4b_launch_count": (C.c_longlong, []),
+    "p4b_kernel_name": (C.c_char_p, [C.c_int]),
+    "p4b_ctx_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "p4b_ctx_destroy": (C.c_int, [_P]),
+    "p4b_ctx_sync": (C.c_int, [_P]),
+    "p4b_comm_unique_id": (C.c_int, [_P]),
+    "p4b_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "p4b_slab_range": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "p4b_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    "p4b_free": (C.c_int, [_P, _P]),
+    "p4b_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "p4b_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "p4b_stencil_apply": (C.c_int, [_P, C.POINTER(Grid), _D, _D]),
+    "p4b_stencil_residual": (C.c_int, [_P, C.POINTER(Grid), _D, _D, _D]),
+    "p4b_cheb_jacobi": (C.c_int, [_P, C.POINTER(Grid), C.c_double, C.c_double, C.c_int, C.c_int, _D, _D, _D]),
+    "p4b_restrict": (C.c_int, [_P, C.POINTER(Grid), _D, _D]),
+    "p4b_prolong_add": (C.c_int, [_P, C.POINTER(Grid), _D, _D]),
+    "p4b_residual_restrict": (C.c_int, [_P, C.POINTER(Grid), _D, _D, _D]),
+    "p4b_lambda_max_jacobi": (C.c_int, [C.POINTER(Grid), C.POINTER(C.c_double)]),
+    "p4b_vec_dot": (C.c_int, [_P, C.c_size_t, _D, _D, C.POINTER(C.c_double)]),
+    "p4b_vec_norm2": (C.c_int, [_P, C.c_size_t, _D, C.POINTER(C.c_double)]),
+    "p4b_vec_norminf": (C.c_int, [_P, C.c_size_t, _D, C.POINTER(C.c_double)]),
+    "p4b_vec_axpy": (C.c_int, [_P, C.c_size_t, C.c_double, _D, _D]),
+    "p4b_vec_aypx": (C.c_int, [_P, C.c_size_t, C.c_double, _D, _D]),
+    "p4b_vec_set": (C.c_int, [_P, C.c_size_t, C.c_double, _D]),
+    "p4b_fish_sample": (C.c_int, [_P, C.POINTER(Grid), C.c_int, _D, _D]),
+    "p4b_initial_state": (C.c_int, [_P, C.POINTER(Grid), _D, C.c_int, _D]),
+    "p4b_poisson_function": (C.c_int, [_P, C.POINTER(Grid), _D, _D, _D, _D]),
+    "p4b_mg_default_opts": (C.c_int, [C.POINTER(MGOpts)]),
+    "p4b_mg_create": (C.c_int, [_P, C.POINTER(Grid), C.POINTER(MGOpts), C.POINTER(_P)]),
+    "p4b_mg_destroy": (C.c_int, [_P]),
+    "p4b_mg_nlevels": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "p4b_mg_level_info": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "p4b_mg_local_range": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "p4b_mg_apply": (C.c_int, [_P, _D, _D]),
+    "p4b_cg_solve": (C.c_int, [_P, C.c_int, _D, _D, C.c_double, C.c_double, C.c_int, C.POINTER(KSPResult)]),
+    "p4b_cg_solve_host": (C.c_int, [_P, C.c_int, _P, _P, C.c_double, C.c_double, C.c_int, C.POINTER(KSPResult)]),
+    "p4b_fish_solve_host": (C.c_int, [_P, _P, _P, _P, C.c_double, C.c_double, C.c_int, C.POINTER(KSPResult)]),
+    "p4b_mg_fish_setup": (C.c_int, [_P, C.c_int, C.c_int, _D, _D, _D]),
+    "p4b_profile_enable": (C.c_int, [_P, C.c_int]),
+    "p4b_profile_reset": (C.c_int, [_P]),
+    "p4b_profile_get": (C.c_int, [_P, C.c_int, C.POINTER(KernelStat)]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Every symbol include/p4b200.h declares (the tests check the .so exports each one)."""
+    return sorted(_SIGS)
+
+
+def load(path: str | None = None):
+    """dlopen libp4b200.so and attach the signatures.  Raises if it is not built: no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise P4BError("libp4b200.so is not built (%s); run `python -m p4pdes_b200.build`. "
+                       "There is no CPU fallback." % path)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise P4BError("p4b200 error %d: %s" % (rc, load().p4b_last_error().decode()))
+
+
+def make_grid(dim, m, L=(1.0, 1.0, 1.0), c=(1.0, 1.0, 1.0)) -> Grid:
+    m = tuple(m) + (1,) * (3 - len(m))
+    return Grid(dim, m[0], m[1] if dim >= 2 else 1, m[2] if dim >= 3 else 1, L[0], L[1], L[2], c[0], c[1], c[2])
+
+
+def refined_grid(dim, refine, base=3, L=(1.0, 1.0, 1.0), c=(1.0, 1.0, 1.0)) -> Grid:
+    """-da_refine n on the 3^d DMDA of fish.c:199-212: m <- 1 + 2^n (m - 1)."""
+    m = 1 + (2 ** refine) * (base - 1)
+    return make_grid(dim, (m,) * dim, L, c)

@@ -1,0 +1,97 @@
+"""CPU-side checks of the C ABI: the library builds, loads, exports every declared symbol, and the
+host-only entry points behave.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from p4pdes_b200 import build as p4build
+from p4pdes_b200 import lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    p4build.build()
+    return L.load()
+
+
+def test_header_and_bindings_agree(lib):
+    hdr = open(os.path.join(ROOT, "include", "p4b200.h")).read()
+    declared = set(re.findall(r"\b(p4b_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(L.exported_symbols())
+    for name in declared:
+        assert hasattr(lib, name), "libp4b200.so does not export %s" % name
+
+
+def test_version(lib):
+    assert lib.p4b_version() == 100
+
+
+def test_slab_range_matches_dmda_split(lib):
+    # DMDA ownership: first (m % P) ranks get one more (17 -> 9+8, 9 -> 5+4, 5 -> 3+2, 3 -> 2+1)
+    for m, P, want in ((17, 2, [(0, 9), (9, 8)]), (9, 2, [(0, 5), (5, 4)]), (5, 2, [(0, 3), (3, 2)]),
+                       (3, 2, [(0, 2), (2, 1)]), (513, 8, None)):
+        got = []
+        for r in range(P):
+            s, c = C.c_int(), C.c_int()
+            assert lib.p4b_slab_range(m, P, r, C.byref(s), C.byref(c)) == 0
+            got.append((s.value, c.value))
+        if want:
+            assert got == want
+        assert sum(c for _, c in got) == m
+        assert all(got[r][0] + got[r][1] == got[r + 1][0] for r in range(P - 1))
+    s, c = C.c_int(), C.c_int()
+    assert lib.p4b_slab_range(10, 2, 5, C.byref(s), C.byref(c)) != 0
+    assert b"slab" in lib.p4b_last_error()
+
+
+def test_lambda_max_matches_survey_table(lib):
+    # 1.7071 (5), 1.9239 (9), 1.9808 (17), 1.9952 (33)
+    for m, want in ((5, 1.7071), (9, 1.9239), (17, 1.9808), (33, 1.9952)):
+        for dim in (1, 2, 3):
+            g = L.make_grid(dim, (m,) * dim)
+            lam = C.c_double()
+            assert lib.p4b_lambda_max_jacobi(C.byref(g), C.byref(lam)) == 0
+            assert abs(lam.value - want) < 5e-5
+
+
+def test_default_options(lib):
+    o = L.MGOpts()
+    assert lib.p4b_mg_default_opts(C.byref(o)) == 0
+    assert (o.cycle, o.smoother, o.smooth_its, o.est_lo, o.est_hi) == (L.CYCLE_V, L.SMOOTH_CHEBYSHEV, 2, 0.1, 1.1)
+
+
+def test_invalid_grid_is_reported(lib):
+    g = L.make_grid(3, (9, 9, 9), c=(1.0, -1.0, 1.0))
+    lam = C.c_double()
+    assert lib.p4b_lambda_max_jacobi(C.byref(g), C.byref(lam)) == 2          # fish.c:188-190 error code 2
+    assert b"positivity" in lib.p4b_last_error()
+
+
+def test_no_gpu_means_loud_failure(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    rc = lib.p4b_ctx_create(0, None, C.byref(h))
+    assert rc != 0 and b"no CPU fallback" in lib.p4b_last_error()
+    from p4pdes_b200.fish import Context
+    with pytest.raises(L.P4BError):
+        Context()
+
+
+def test_option_parser_mirrors_fish_checks():
+    from p4pdes_b200.fish import parse_options
+    o = parse_options("-fsh_dim 3 -da_refine 7 -pc_mg_levels 6 -pc_type mg -snes_type ksponly -ksp_converged_reason")
+    assert (o.dim, o.da_refine, o.pc_mg_levels, o.ksp_converged_reason) == (3, 7, 6, True)
+    with pytest.raises(L.P4BError, match="MANUEXP"):
+        parse_options("-fsh_cx 2 -pc_type mg")
+    with pytest.raises(L.P4BError, match="positivity"):
+        parse_options("-fsh_problem manupoly -fsh_cy -1 -pc_type mg")
+    with pytest.raises(L.P4BError, match="sequential"):
+        parse_options("-pc_type mg -mg_levels_pc_type sor")
+    with pytest.raises(L.P4BError, match="ILU"):
+        parse_options("-fsh_dim 2")
