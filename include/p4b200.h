@@ -101,8 +101,13 @@ typedef struct {
 int p4b_version(void);
 const char *p4b_last_error(void);
 int p4b_device_count(int *n);
+/* kernel-selection knobs for tests and A/B measurements (never changes results beyond rounding):
+ * "march_enabled" 0|1, "march_min_plane" nodes, "march_P", "march_NT", "march_NS" */
+int p4b_tune(const char *key, long value);
 
 /* ---- context ---- */
+/* stream: the cudaStream_t every kernel, copy and NCCL call of this context is issued on
+ * (NULL = the default stream), so the library's work is ordered with the caller's own. */
 int p4b_ctx_create(int device, void *stream, p4b_ctx **ctx);
 int p4b_ctx_destroy(p4b_ctx *ctx);
 int p4b_ctx_sync(p4b_ctx *ctx);

@@ -32,6 +32,8 @@ int launch_stencil(cudaStream_t st, const LevelDesc &L, const StencilOp &op, con
 // true when the TMA-staged plane-marching kernel handles this level (big 3-D grids)
 bool stencil_fast_eligible(const LevelDesc &L);
 
+int tune_march(const char *key, long v);   // 0 when the key was recognised
+
 // transfer (DMDA Q1, R = P^T)
 int launch_restrict(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *rf, double *bc);
 int launch_prolong_add(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *xc, double *xf);

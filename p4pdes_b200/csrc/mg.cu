@@ -517,6 +517,12 @@ int p4b_version(void) { return P4B_VERSION; }
 const char *p4b_last_error(void) { return g_err.c_str(); }
 const char *p4b_kernel_name(int c) { return (c >= 0 && c < P4B_K_NCLASSES) ? k_names[c] : "?"; }
 
+int p4b_tune(const char *key, long value) {
+    if (!key) return fail(62, "null tuning key");
+    if (tune_march(key, value) == 0) return 0;
+    return fail(62, "unknown tuning key %s", key);
+}
+
 int p4b_device_count(int *n) {
     P4B_CUDA(cudaGetDeviceCount(n));
     return 0;
@@ -531,12 +537,7 @@ int p4b_ctx_create(int device, void *stream, p4b_ctx **out) {
     P4B_CUDA(cudaSetDevice(device));
     p4b_ctx *c = new p4b_ctx();
     c->device = device;
-    if (stream) {
-        c->stream = (cudaStream_t)stream;
-    } else {
-        P4B_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        c->own_stream = true;
-    }
+    c->stream = (cudaStream_t)stream;   // exactly the caller's stream; NULL is the (legacy) default stream
     c->red.max_blocks = 1 << 20;
     P4B_CUDA(cudaMalloc(&c->red.partials, sizeof(double) * 4 * (size_t)c->red.max_blocks));
     P4B_CUDA(cudaMalloc(&c->red.ticket, sizeof(unsigned int)));

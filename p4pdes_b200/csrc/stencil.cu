@@ -79,8 +79,7 @@ static int launch_generic(cudaStream_t st, const LevelDesc &L, const StencilOp &
 
 int launch_stencil_fast(cudaStream_t st, const LevelDesc &L, const StencilOp &op, const Reducer &red);
 
-int launch_stencil(cudaStream_t st, const LevelDesc &L, const StencilOp &op, const Reducer &red) {
-    if (stencil_fast_eligible(L)) return launch_stencil_fast(st, L, op, red);
+int launch_stencil_generic(cudaStream_t st, const LevelDesc &L, const StencilOp &op, const Reducer &red) {
     switch (op.mode) {
         case ST_APPLY: return launch_generic<ST_APPLY>(st, L, op, red);
         case ST_APPLY_DOT: return launch_generic<ST_APPLY_DOT>(st, L, op, red);
@@ -89,6 +88,11 @@ int launch_stencil(cudaStream_t st, const LevelDesc &L, const StencilOp &op, con
         case ST_LIN_BU: return launch_generic<ST_LIN_BU>(st, L, op, red);
     }
     return fail(62, "unknown stencil mode %d", op.mode);
+}
+
+int launch_stencil(cudaStream_t st, const LevelDesc &L, const StencilOp &op, const Reducer &red) {
+    if (stencil_fast_eligible(L)) return launch_stencil_fast(st, L, op, red);
+    return launch_stencil_generic(st, L, op, red);
 }
 
 }  // namespace p4b

@@ -67,6 +67,7 @@ _SIGS = {
     "p4b_last_error": (C.c_char_p, []),
     "p4b_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "p4b_launch_count": (C.c_longlong, []),
+    "p4b_tune": (C.c_int, [C.c_char_p, C.c_long]),
     "p4b_kernel_name": (C.c_char_p, [C.c_int]),
     "p4b_ctx_create": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
     "p4b_ctx_destroy": (C.c_int, [_P]),
@@ -139,6 +140,10 @@ def load(path: str | None = None):
 def check(rc: int):
     if rc != 0:
         raise P4BError("p4b200 error %d: %s" % (rc, load().p4b_last_error().decode()))
+
+
+def tune(key: str, value: int):
+    check(load().p4b_tune(key.encode(), int(value)))
 
 
 def make_grid(dim, m, L=(1.0, 1.0, 1.0), c=(1.0, 1.0, 1.0)) -> Grid:

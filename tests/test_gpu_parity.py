@@ -32,6 +32,16 @@ def ctx():
     return Context()
 
 
+@pytest.fixture(params=["generic", "march"])
+def path(request):
+    """Run a test once on the one-thread-per-node kernels and once with the TMA-staged plane-marching
+    kernel forced on for every 3-D level it can take (normally only planes >= 128^2 use it)."""
+    L.tune("march_enabled", 1)
+    L.tune("march_min_plane", 1 if request.param == "march" else 1 << 30)
+    yield request.param
+    L.tune("march_min_plane", 16384)
+
+
 def ogrid(dim, m, Ls):
     mm = tuple(m) + (1,) * (3 - len(m))
     return fo.Grid(dim, mm, tuple(float(x) for x in Ls))
@@ -48,7 +58,7 @@ def relerr(a, b):
 
 
 @pytest.mark.parametrize("dim,m,Ls,c", GRIDS)
-def test_stencil_apply_and_residual(ctx, dim, m, Ls, c):
+def test_stencil_apply_and_residual(ctx, path, dim, m, Ls, c):
     og = ogrid(dim, m, Ls)
     g = L.make_grid(dim, m, Ls, c)
     A = fo.jacobian(og, c)
@@ -88,7 +98,7 @@ def test_transfer_matches_q1_interpolation(ctx, dim, m, Ls, c):
 
 @pytest.mark.parametrize("dim,m,Ls,c", GRIDS[2:8])
 @pytest.mark.parametrize("its,zero", [(1, True), (2, True), (2, False), (3, False), (4, True)])
-def test_chebyshev_jacobi_smoother(ctx, dim, m, Ls, c, its, zero):
+def test_chebyshev_jacobi_smoother(ctx, path, dim, m, Ls, c, its, zero):
     og = ogrid(dim, m, Ls)
     g = L.make_grid(dim, m, Ls, c)
     A = fo.jacobian(og, c)
@@ -164,7 +174,7 @@ MG_CASES = [
 
 @pytest.mark.parametrize("dim,refine,kw", MG_CASES)
 @pytest.mark.parametrize("fuse", [True, False])
-def test_pcmg_apply(ctx, dim, refine, kw, fuse):
+def test_pcmg_apply(ctx, path, dim, refine, kw, fuse):
     og = fo.refined_grid(dim, refine)
     g = L.refined_grid(dim, refine)
     M = fo.PCMG(og, opts=fo.MGOptions(**kw))
@@ -206,7 +216,7 @@ SOLVE_CASES = [
 
 @pytest.mark.parametrize("opts,okw", SOLVE_CASES)
 @pytest.mark.parametrize("fuse", [True, False])
-def test_fish_solve_matches_oracle(ctx, opts, okw, fuse):
+def test_fish_solve_matches_oracle(ctx, path, opts, okw, fuse):
     okw = dict(okw)
     mgkw = okw.pop("mg", {})
     want = fo.fish(mg=fo.MGOptions(**mgkw), **okw)
