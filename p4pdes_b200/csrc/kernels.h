@@ -16,7 +16,9 @@ struct Reducer {
 //   LIN        out = cb*u + cg*(b - A u)
 //   LIN_PM1    out = ca*pm1 + cb*u + cg*(b - A u)          (out may alias pm1)
 //   LIN_BU     out = cb*u + cg*(u - A u)                   (b == u, loaded once)
-enum StencilMode { ST_APPLY = 0, ST_APPLY_DOT, ST_LIN, ST_LIN_PM1, ST_LIN_BU };
+//   LIN_PM1_DOT2  LIN_PM1 plus (out,out) -> dot_out[0], (out,b) -> dot_out[1]   (the CG scalars of KSPSolve_CG
+//              when `out` is z = M^-1 r and b is r: the last smoother step of the cycle on the finest level)
+enum StencilMode { ST_APPLY = 0, ST_APPLY_DOT, ST_LIN, ST_LIN_PM1, ST_LIN_BU, ST_LIN_PM1_DOT2 };
 
 struct StencilOp {
     int mode;
@@ -25,7 +27,7 @@ struct StencilOp {
     const double *pm1;
     double *out;
     double ca, cb, cg;
-    double *dot_out;      // device scalar for ST_APPLY_DOT
+    double *dot_out;      // device scalar(s) for ST_APPLY_DOT / ST_LIN_PM1_DOT2
 };
 
 int launch_stencil(cudaStream_t st, const LevelDesc &L, const StencilOp &op, const Reducer &red);

@@ -218,6 +218,8 @@ struct p4b_mg {
     int n0 = 0;
     double *p = nullptr, *w = nullptr, *fbuf = nullptr, *gbuf = nullptr;   // CG vectors / fish scratch
     Prof prof;
+    bool dot2_fused = false;     // set by smooth() when the last smoother kernel also produced (z,z), (z,r)
+    double *dot2_target = nullptr;
     cudaGraphExec_t coarse_graph = nullptr;
     int graph_level = -1;
 };
@@ -323,7 +325,7 @@ static int gather_replicated(p4b_mg *m, int l, double *v) {
 }
 
 // ---- smoothers ---------------------------------------------------------------------------------
-static int smooth(p4b_mg *m, int l, bool zero_guess) {
+static int smooth(p4b_mg *m, int l, bool zero_guess, double *dot2_out = nullptr) {
     Level &L = m->lev[l];
     cudaStream_t st = m->ctx->stream;
     const Reducer &red = m->ctx->red;
@@ -382,6 +384,10 @@ static int smooth(p4b_mg *m, int l, bool zero_guess) {
             op.mode = ST_LIN;
         } else {
             op.mode = ST_LIN_PM1; op.pm1 = pm1; op.ca = 1.0 - w;
+            if (dot2_out && i == its - 1) {     // last step of the cycle: also (z,z), (z,r) for KSPSolve_CG
+                op.mode = ST_LIN_PM1_DOT2; op.dot_out = dot2_out;
+                m->dot2_fused = true;
+            }
         }
         P4B_CHECK(launch_stencil(st, L.d, op, red));
         std::swap(pm1, pk);
@@ -430,11 +436,18 @@ static int cycle(p4b_mg *m, int l, bool zero_guess) {
         ProfScope ps(m, l, P4B_K_PROLONG);
         P4B_CHECK(launch_prolong_add(st, L.d, C.d, C.x, L.x));
     }
-    return smooth(m, l, false);
+    return smooth(m, l, false, (l == m->top && m->o.fuse) ? m->dot2_target : nullptr);
 }
 
-// z = M^-1 r with r already in lev[top].b ; result in lev[top].x
-static int mg_apply_internal(p4b_mg *m) { return cycle(m, m->top, true); }
+// z = M^-1 r with r already in lev[top].b ; result in lev[top].x.  With dot2 != NULL (and fused kernels on)
+// the last smoother kernel also leaves (z,z), (z,r) there; m->dot2_fused says whether it did.
+static int mg_apply_internal(p4b_mg *m, double *dot2 = nullptr) {
+    m->dot2_fused = false;
+    m->dot2_target = dot2;
+    int rc = cycle(m, m->top, true);
+    m->dot2_target = nullptr;
+    return rc;
+}
 
 // ------------------------------------------------------------------------------------------------
 // setup
@@ -970,17 +983,20 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
     P4B_CUDA(cudaEventRecord(c->ev0, st));
     P4B_CUDA(cudaMemcpyAsync(T.b, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     P4B_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n, st));
-    auto precond = [&]() -> int {
-        if (pc_type == P4B_PC_MG) return mg_apply_internal(m);
-        return launch_scale_copy(st, n, pc_type == P4B_PC_JACOBI ? 1.0 / T.d.diag : 1.0, T.b, T.x);
+    // z = M^-1 r and the CG scalars (z,z), (z,r) -> dots
+    auto precond = [&](double *dots) -> int {
+        m->dot2_fused = false;
+        if (pc_type == P4B_PC_MG) P4B_CHECK(mg_apply_internal(m, dots));
+        else P4B_CHECK(launch_scale_copy(st, n, pc_type == P4B_PC_JACOBI ? 1.0 / T.d.diag : 1.0, T.b, T.x));
+        if (!m->dot2_fused) {
+            ProfScope ps(m, m->top, P4B_K_DOT2);
+            P4B_CHECK(launch_dot2(st, n, T.x, T.b, dots, red));
+        }
+        return 0;
     };
     int q = 0;
     double h[2];
-    P4B_CHECK(precond());
-    {
-        ProfScope ps(m, m->top, P4B_K_DOT2);
-        P4B_CHECK(launch_dot2(st, n, T.x, T.b, S + 2 * q, red));
-    }
+    P4B_CHECK(precond(S + 2 * q));
     P4B_CHECK(ctx_allreduce(c, S + 2 * q, 2));
     P4B_CHECK(fetch_scal(c, S + 2 * q, 2, h));
     double dp = sqrt(h[0]);
@@ -1010,12 +1026,8 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
             ProfScope ps(m, m->top, P4B_K_AXPY2);
             P4B_CHECK(launch_axpy2(st, n, S + 2 * q + 1, S + 4, m->p, m->w, x, T.b));
         }
-        P4B_CHECK(precond());
         q ^= 1;
-        {
-            ProfScope ps(m, m->top, P4B_K_DOT2);
-            P4B_CHECK(launch_dot2(st, n, T.x, T.b, S + 2 * q, red));
-        }
+        P4B_CHECK(precond(S + 2 * q));
         P4B_CHECK(ctx_allreduce(c, S + 2 * q, 2));
         P4B_CHECK(fetch_scal(c, S + 2 * q, 2, h));
         dp = sqrt(h[0]);

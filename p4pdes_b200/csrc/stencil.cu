@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const LevelDesc L,
                                                                unsigned int *ticket) {
     const long long nloc = L.nlocal();
     const long long n = (long long)blockIdx.x * 256 + threadIdx.x;
-    double dv[1] = {0.0};
+    double dv[2] = {0.0, 0.0};
     if (n < nloc) {
         const int plane = L.nx * L.ny;
         const int kl = (int)(n / plane);
@@ -57,12 +57,18 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const LevelDesc L,
         } else if (MODE == ST_LIN_BU) {
             o = op.cb * uc + op.cg * (uc - Au);
         } else {
-            o = op.cb * uc + op.cg * (op.b[n] - Au);
-            if (MODE == ST_LIN_PM1) o += op.ca * op.pm1[n];
+            const double bv = op.b[n];
+            o = op.cb * uc + op.cg * (bv - Au);
+            if (MODE == ST_LIN_PM1 || MODE == ST_LIN_PM1_DOT2) o += op.ca * op.pm1[n];
+            if (MODE == ST_LIN_PM1_DOT2) { dv[0] = o * o; dv[1] = o * bv; }
         }
         op.out[n] = o;
     }
-    if (MODE == ST_APPLY_DOT) grid_sum_finalize<1, 256>(dv, partials, ticket, op.dot_out);
+    if (MODE == ST_APPLY_DOT) {
+        double d1[1] = {dv[0]};
+        grid_sum_finalize<1, 256>(d1, partials, ticket, op.dot_out);
+    }
+    if (MODE == ST_LIN_PM1_DOT2) grid_sum_finalize<2, 256>(dv, partials, ticket, op.dot_out);
 }
 
 template <int MODE>
@@ -70,7 +76,7 @@ static int launch_generic(cudaStream_t st, const LevelDesc &L, const StencilOp &
     const long long nloc = L.nlocal();
     if (nloc <= 0) return 0;
     const long long nb = (nloc + 255) / 256;
-    if (MODE == ST_APPLY_DOT && nb > red.max_blocks)
+    if ((MODE == ST_APPLY_DOT || MODE == ST_LIN_PM1_DOT2) && nb > red.max_blocks)
         return fail(63, "stencil dot: %lld blocks exceed the reducer scratch (%d)", nb, red.max_blocks);
     stencil_generic_kernel<MODE><<<(unsigned)nb, 256, 0, st>>>(L, op, red.partials, red.ticket);
     P4B_LAUNCH_CHECK();
@@ -86,6 +92,7 @@ int launch_stencil_generic(cudaStream_t st, const LevelDesc &L, const StencilOp 
         case ST_LIN: return launch_generic<ST_LIN>(st, L, op, red);
         case ST_LIN_PM1: return launch_generic<ST_LIN_PM1>(st, L, op, red);
         case ST_LIN_BU: return launch_generic<ST_LIN_BU>(st, L, op, red);
+        case ST_LIN_PM1_DOT2: return launch_generic<ST_LIN_PM1_DOT2>(st, L, op, red);
     }
     return fail(62, "unknown stencil mode %d", op.mode);
 }

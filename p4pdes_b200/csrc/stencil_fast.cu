@@ -63,8 +63,17 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-enum { MK_W = 1, MK_E = 2, MK_S = 4, MK_N = 8, MK_BD = 16, MK_VALID = 32 };
+enum { MK_BD = 1, MK_VALID = 2 };
 
+// Inner-loop design notes (the first version of this kernel was instruction-issue bound at ~200
+// instructions per node, see profiles/r01_march_v1.md):
+//   * Dirichlet masking is applied to the DATA, not the operator: once a plane has landed, the thread
+//     that owns a boundary node reads its true value into a register and then zeroes it in the stage
+//     (halo boundary nodes are zeroed by a few designated threads).  Interior rows then use the plain
+//     7-point formula with no per-neighbour predicates; boundary rows are a final select.
+//   * slot index, mbarrier parity bits, stage parity shift and all global pointers advance
+//     incrementally (no division or 64-bit multiply per plane), invalid tail nodes are clamped and
+//     only their store is predicated off (no divergent control flow).
 template <int MODE, int P, int NT>
 __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, const StencilOp op, const MarchCfg cfg,
                                                            double *partials, unsigned int *ticket) {
@@ -72,7 +81,9 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);              // NS barriers (128 bytes reserved)
     double *stages = reinterpret_cast<double *>(smem_raw + 128);
     constexpr int Q = NT * P;
+    constexpr int HZ = 3;                                                  // halo nodes a thread may have to zero
     const int tid = threadIdx.x;
+    const int nx = L.nx;
     const int plane = L.nx * L.ny;
     const int q0 = blockIdx.x * Q;
     const int k0 = blockIdx.y * cfg.KC;
@@ -80,7 +91,7 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
     const int NS = cfg.NS, H = cfg.H, SD = cfg.stage_doubles;
     const int lo = max(q0 - H, 0), hi = min(q0 + Q + H, plane);            // staged linear range of the plane
     const int cnt = hi - lo;
-    const double *__restrict__ u = op.u;
+    const int podd = plane & 1;
 
     if (tid == 0) {
         for (int s = 0; s < NS; s++) mbar_init(&bars[s], 1);
@@ -90,160 +101,204 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
 
     // plane t of this chunk is local plane kl = k0 - 1 + t, t = 0 .. T-1 (one extra plane on each side)
     const int T = (k1 - k0) + 2;
-    auto plane_valid = [&](int t) {
-        const int kg = L.zs + k0 - 1 + t;
-        return kg >= 0 && kg <= L.nz - 1;
-    };
-    auto plane_adj = [&](int t) {   // parity of the first staged element's offset from u
-        const long long e0 = (long long)(k0 - 1 + t) * plane + lo;
-        return (int)(e0 & 1LL);
-    };
-    auto issue = [&](int t) {       // producer thread only
-        if (t >= T) return;
-        const int s = t % NS;
-        if (!plane_valid(t)) {          // nothing to load: complete the phase so slot parities stay in step
-            mbar_arrive(&bars[s]);
-            return;
+    const int kg0 = L.zs + k0 - 1;                                         // global index of plane t = 0
+    const long long e00 = (long long)(k0 - 1) * plane + lo;                // element offset of plane 0's staged range
+    const int adj0 = (int)(e00 & 1LL);
+
+    // producer state (thread 0): next plane to issue
+    int it = 0, islot = 0;
+    const double *isrc = op.u + e00;                                       // start of plane `it`'s staged range
+    auto issue_next = [&]() {       // producer thread only; issues plane `it` into slot `islot`
+        if (it < T) {
+            const int kg = kg0 + it;
+            if (kg < 0 || kg > L.nz - 1) {
+                mbar_arrive(&bars[islot]);      // nothing to load: complete the phase, slot parities stay in step
+            } else {
+                double *st = stages + (size_t)islot * SD;
+                const int adj = (adj0 + it * podd) & 1;
+                const int total = cnt + adj;              // elements from the aligned start
+                const int even = total & ~1;
+                const double *src = isrc - adj;
+                if (total & 1) st[2 + total - 1] = src[total - 1];   // odd tail by the generic proxy
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&bars[islot], (uint32_t)even * 8u);
+                bulk_g2s(st + 2, src, (uint32_t)even * 8u, &bars[islot]);
+            }
         }
-        double *st = stages + (size_t)s * SD;
-        const long long e0 = (long long)(k0 - 1 + t) * plane + lo;
-        const int adj = (int)(e0 & 1LL);
-        const int total = cnt + adj;              // elements from the aligned start
-        const int even = total & ~1;
-        const double *src = u + (e0 - adj);
-        if (total & 1) st[2 + total - 1] = src[total - 1];   // odd tail by the generic proxy
-        fence_proxy_async();
-        mbar_arrive_expect_tx(&bars[s], (uint32_t)even * 8u);
-        bulk_g2s(st + 2, src, (uint32_t)even * 8u, &bars[s]);
+        it++;
+        isrc += plane;
+        if (++islot == NS) islot = 0;
     };
     if (tid == 0)
-        for (int t = 0; t < NS; t++) issue(t);
+        for (int t = 0; t < NS; t++) issue_next();
 
-    // per-thread nodes: q = q0 + tid + p*NT
+    // per-thread nodes: q = q0 + tid + p*NT ; tail nodes beyond the plane are clamped onto its last node
+    int si[P];          // stage index of the node (before the per-plane parity shift)
+    int gi[P];          // offset of the node from the thread's global base pointer
     int mask[P];
+    const int sb = 2 + (q0 - lo);
 #pragma unroll
     for (int p = 0; p < P; p++) {
-        const int q = q0 + tid + p * NT;
-        int mk = 0;
-        if (q < plane) {
-            const int j = q / L.nx, i = q - j * L.nx;
-            mk = MK_VALID;
-            if (i == 0 || i == L.nx - 1 || (L.ay && (j == 0 || j == L.ny - 1))) mk |= MK_BD;
-            if (i - 1 > 0) mk |= MK_W;
-            if (i + 1 < L.nx - 1) mk |= MK_E;
-            if (L.ay && j - 1 > 0) mk |= MK_S;
-            if (L.ay && j + 1 < L.ny - 1) mk |= MK_N;
-        }
+        int q = q0 + tid + p * NT;
+        int mk = MK_VALID;
+        if (q >= plane) { q = plane - 1; mk = 0; }
+        const int j = q / nx, i = q - j * nx;
+        if (i == 0 || i == nx - 1 || (L.ay && (j == 0 || j == L.ny - 1))) mk |= MK_BD;
         mask[p] = mk;
+        si[p] = sb + (q - q0);
+        gi[p] = q - q0 - tid;
     }
-    const int sbase = 2 + (q0 - lo) + tid;      // stage index of node p=0 before the parity shift
+    // halo nodes (not owned by this CTA) that are boundary nodes and must be zeroed in every stage
+    int hz[HZ];
+    {
+        const int nlo = q0 - lo, nhi = hi - min(q0 + Q, plane);
+#pragma unroll
+        for (int r = 0; r < HZ; r++) {
+            const int hh = tid + r * NT;
+            int q = -1;
+            if (hh < nlo) q = lo + hh;
+            else if (hh < nlo + nhi) q = min(q0 + Q, plane) + (hh - nlo);
+            hz[r] = -1;
+            if (q >= 0) {
+                const int j = q / nx, i = q - j * nx;
+                if (i == 0 || i == nx - 1 || (L.ay && (j == 0 || j == L.ny - 1))) hz[r] = 2 + (q - lo);
+            }
+        }
+    }
 
     double prev[P], cur[P], nxt[P], bq[P], pq[P];
-    double dv[1] = {0.0};
+    double dv[2] = {0.0, 0.0};
 #pragma unroll
     for (int p = 0; p < P; p++) { prev[p] = 0.0; cur[p] = 0.0; nxt[p] = 0.0; bq[p] = 0.0; pq[p] = 0.0; }
 
-    // centre values of plane t = 0
-    if (plane_valid(0)) {
-        mbar_wait(&bars[0], 0);
-        const double *st = stages + plane_adj(0);
+    // take the centre values of a landed plane, then apply the Dirichlet mask to the staged copy
+    auto take_plane = [&](double *st, double (&c)[P]) {
 #pragma unroll
-        for (int p = 0; p < P; p++)
-            if (mask[p] & MK_VALID) cur[p] = st[sbase + p * NT];
+        for (int p = 0; p < P; p++) {
+            c[p] = st[si[p]];
+            if ((mask[p] & (MK_BD | MK_VALID)) == (MK_BD | MK_VALID)) st[si[p]] = 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < HZ; r++)
+            if (hz[r] >= 0) st[hz[r]] = 0.0;
+        fence_proxy_async();          // these generic writes precede the next bulk copy into this slot
+    };
+
+    uint32_t phase = 0;               // bit s = parity to wait for on slot s
+    int slot_c = 0;                   // slot of plane t
+    int adj_c = adj0;                 // parity shift of plane t
+    if (kg0 >= 0) {
+        mbar_wait(&bars[0], 0);
+        take_plane(stages + adj_c, cur);
     }
+    phase ^= 1u;
+
+    // global pointers of plane t (the plane computed in iteration t), advanced by `plane` per step
+    const long long g0 = (long long)(k0 - 1) * plane + q0 + tid;
+    double *outp = op.out + g0;
+    constexpr bool HAS_B = (MODE == ST_LIN || MODE == ST_LIN_PM1 || MODE == ST_LIN_PM1_DOT2);
+    constexpr bool HAS_PM1 = (MODE == ST_LIN_PM1 || MODE == ST_LIN_PM1_DOT2);
+    const double *bp = HAS_B ? op.b + g0 : nullptr;
+    const double *pp = HAS_PM1 ? op.pm1 + g0 : nullptr;
+    const double diag = L.diag, cx = L.cx, cy = L.ay ? L.cy : 0.0, cz = L.cz;
+    const int oy = L.ay ? nx : 0;
+    const double ca = op.ca, cb = op.cb, cg = op.cg;
 
     for (int t = 0; t + 1 < T; t++) {
-        const int kl = k0 - 1 + t;            // plane computed in this iteration (when t >= 1)
-        const int kg = L.zs + kl;
+        const int kg = kg0 + t;               // global plane computed in this iteration (when t >= 1)
+        int slot_n = slot_c + 1;
+        if (slot_n == NS) slot_n = 0;
+        const int adj_n = (adj_c + podd) & 1;
         // prefetch the streamed operands of the next plane to compute (t+1) into registers
         double bn[P], pn[P];
-        if (MODE == ST_LIN || MODE == ST_LIN_PM1) {
-            const bool more = (t + 1 < T - 1);
-            const long long nb = (long long)(kl + 1) * plane + q0 + tid;
+        if (HAS_B) {
+            if (t + 1 < T - 1) {
 #pragma unroll
-            for (int p = 0; p < P; p++) {
-                bn[p] = (more && (mask[p] & MK_VALID)) ? op.b[nb + p * NT] : 0.0;
-                if (MODE == ST_LIN_PM1) pn[p] = (more && (mask[p] & MK_VALID)) ? op.pm1[nb + p * NT] : 0.0;
+                for (int p = 0; p < P; p++) {
+                    bn[p] = bp[plane + gi[p]];
+                    if (HAS_PM1) pn[p] = pp[plane + gi[p]];
+                }
             }
         }
         // centre values of plane t+1
-        {
-            const int tn = t + 1, sn = tn % NS;
-            if (plane_valid(tn)) {
-                mbar_wait(&bars[sn], (uint32_t)((tn / NS) & 1));
-                const double *st = stages + (size_t)sn * SD + plane_adj(tn);
+        if (kg + 1 <= L.nz - 1) {
+            mbar_wait(&bars[slot_n], (phase >> slot_n) & 1u);
+            take_plane(stages + (size_t)slot_n * SD + adj_n, nxt);
+        } else {
 #pragma unroll
-                for (int p = 0; p < P; p++)
-                    if (mask[p] & MK_VALID) nxt[p] = st[sbase + p * NT];
-            } else {
-#pragma unroll
-                for (int p = 0; p < P; p++) nxt[p] = 0.0;
-            }
+            for (int p = 0; p < P; p++) nxt[p] = 0.0;
         }
+        phase ^= (1u << slot_n);
         if (t >= 1) {
-            const double *st = stages + (size_t)(t % NS) * SD + plane_adj(t);
+            const double *st = stages + (size_t)slot_c * SD + adj_c;
             const bool kbd = (kg == 0 || kg == L.nz - 1);
-            const bool dn_ok = (kg - 1 > 0), up_ok = (kg + 1 < L.nz - 1);
-            const long long nb = (long long)kl * plane + q0 + tid;
+            const double czd = (kg - 1 > 0) ? cz : 0.0, czu = (kg + 1 < L.nz - 1) ? cz : 0.0;
 #pragma unroll
             for (int p = 0; p < P; p++) {
-                const int mk = mask[p];
-                if (!(mk & MK_VALID)) continue;
-                const int si = sbase + p * NT;
+                const bool bd = kbd || (mask[p] & MK_BD);
+                const int s0 = si[p];
+                const int dx = bd ? 0 : 1, dy = bd ? 0 : oy;     // boundary rows never leave their own node
                 const double uc = cur[p];
-                double Au = L.diag * uc;
-                if (!kbd && !(mk & MK_BD)) {
-                    const double uw = (mk & MK_W) ? st[si - 1] : 0.0;
-                    const double ue = (mk & MK_E) ? st[si + 1] : 0.0;
-                    Au -= L.cx * (uw + ue);
-                    if (L.ay) {
-                        const double us = (mk & MK_S) ? st[si - L.nx] : 0.0;
-                        const double un = (mk & MK_N) ? st[si + L.nx] : 0.0;
-                        Au -= L.cy * (us + un);
-                    }
-                    const double ud = dn_ok ? prev[p] : 0.0;
-                    const double uu = up_ok ? nxt[p] : 0.0;
-                    Au -= L.cz * (uu + ud);
-                }
+                double Ai = diag * uc - cx * (st[s0 - dx] + st[s0 + dx]);
+                Ai -= cy * (st[s0 - dy] + st[s0 + dy]);
+                Ai -= czu * nxt[p] + czd * prev[p];
+                const double Au = bd ? diag * uc : Ai;
                 double o;
                 if (MODE == ST_APPLY || MODE == ST_APPLY_DOT) {
                     o = Au;
-                    if (MODE == ST_APPLY_DOT) dv[0] += uc * Au;
+                    if (MODE == ST_APPLY_DOT) dv[0] += (mask[p] & MK_VALID) ? uc * Au : 0.0;
                 } else if (MODE == ST_LIN_BU) {
-                    o = op.cb * uc + op.cg * (uc - Au);
+                    o = cb * uc + cg * (uc - Au);
                 } else {
-                    o = op.cb * uc + op.cg * (bq[p] - Au);
-                    if (MODE == ST_LIN_PM1) o += op.ca * pq[p];
+                    o = cb * uc + cg * (bq[p] - Au);
+                    if (HAS_PM1) o += ca * pq[p];
+                    if (MODE == ST_LIN_PM1_DOT2 && (mask[p] & MK_VALID)) {
+                        dv[0] += o * o;
+                        dv[1] += o * bq[p];
+                    }
                 }
-                op.out[nb + p * NT] = o;
+                if (mask[p] & MK_VALID) outp[gi[p]] = o;
             }
         }
-        __syncthreads();                       // everyone is done with stage t%NS (and with plane 0 at t = 0)
-        if (tid == 0) issue(t + NS);
+        __syncthreads();                       // everyone is done with slot_c (and with plane 0 at t = 0)
+        if (tid == 0) issue_next();
+        outp += plane;
+        if (HAS_B) bp += plane;
+        if (HAS_PM1) pp += plane;
+        slot_c = slot_n;
+        adj_c = adj_n;
 #pragma unroll
         for (int p = 0; p < P; p++) {
             prev[p] = cur[p];
             cur[p] = nxt[p];
-            if (MODE == ST_LIN || MODE == ST_LIN_PM1) {
+            if (HAS_B) {
                 bq[p] = bn[p];
-                if (MODE == ST_LIN_PM1) pq[p] = pn[p];
+                if (HAS_PM1) pq[p] = pn[p];
             }
         }
     }
-    if (MODE == ST_APPLY_DOT) {
-        // one partial per CTA, fixed order: block id = blockIdx.y * gridDim.x + blockIdx.x
-        __shared__ double red[NT / 32];
+    if (MODE == ST_APPLY_DOT || MODE == ST_LIN_PM1_DOT2) {
+        // one partial (per value) per CTA, summed in fixed order by the last CTA to finish
+        constexpr int NV = (MODE == ST_LIN_PM1_DOT2) ? 2 : 1;
+        __shared__ double red[2][NT / 32];
         __shared__ bool is_last;
         const int lane = tid & 31, wid = tid >> 5;
-        double s = warp_sum(dv[0]);
-        if (lane == 0) red[wid] = s;
-        __syncthreads();
         const unsigned int nblk = gridDim.x * gridDim.y;
+        const unsigned int bid = blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            const double s = warp_sum(dv[v]);
+            if (lane == 0) red[v][wid] = s;
+        }
+        __syncthreads();
         if (wid == 0) {
-            double t2 = (lane < NT / 32) ? red[lane] : 0.0;
-            t2 = warp_sum(t2);
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                double t2 = (lane < NT / 32) ? red[v][lane] : 0.0;
+                t2 = warp_sum(t2);
+                if (lane == 0) partials[(size_t)v * nblk + bid] = t2;
+            }
             if (lane == 0) {
-                partials[blockIdx.y * gridDim.x + blockIdx.x] = t2;
                 __threadfence();
                 is_last = (atomicAdd(ticket, 1u) == nblk - 1);
             }
@@ -251,17 +306,21 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
         __syncthreads();
         if (is_last) {
             __threadfence();
-            double a = 0.0;
-            for (unsigned int i = tid; i < nblk; i += NT) a += ((volatile double *)partials)[i];
-            a = warp_sum(a);
-            __syncthreads();
-            if (lane == 0) red[wid] = a;
-            __syncthreads();
-            if (wid == 0) {
-                double t3 = (lane < NT / 32) ? red[lane] : 0.0;
-                t3 = warp_sum(t3);
-                if (lane == 0) { op.dot_out[0] = t3; *ticket = 0u; }
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                double a = 0.0;
+                for (unsigned int i = tid; i < nblk; i += NT) a += ((volatile double *)partials)[(size_t)v * nblk + i];
+                a = warp_sum(a);
+                __syncthreads();
+                if (lane == 0) red[v][wid] = a;
+                __syncthreads();
+                if (wid == 0) {
+                    double t3 = (lane < NT / 32) ? red[v][lane] : 0.0;
+                    t3 = warp_sum(t3);
+                    if (lane == 0) op.dot_out[v] = t3;
+                }
             }
+            if (tid == 0) *ticket = 0u;
         }
     }
 }
@@ -273,7 +332,7 @@ struct MarchTune { int P, NT, NS, enabled, min_plane; };
 
 static MarchTune &tune() {
     static MarchTune t = [] {
-        MarchTune x = {4, 512, 4, 1, 16384};
+        MarchTune x = {0, 0, 4, 1, 16384};   // P = 0: per-mode default
         if (const char *e = getenv("P4B_MARCH")) {       // "P,NT,NS" or "0" to disable (tuning / A-B runs)
             int a = 0, b = 0, c = 0;
             const int n = sscanf(e, "%d,%d,%d", &a, &b, &c);
@@ -346,7 +405,8 @@ static int launch_march(cudaStream_t st, const LevelDesc &L, const StencilOp &op
     }
     cfg.KC = (L.zm + best_nc - 1) / best_nc;
     const int nchunks = (L.zm + cfg.KC - 1) / cfg.KC;
-    if (MODE == ST_APPLY_DOT && bands * nchunks > red.max_blocks) return fail(63, "reducer scratch too small");
+    if ((MODE == ST_APPLY_DOT || MODE == ST_LIN_PM1_DOT2) && bands * nchunks > red.max_blocks)
+        return fail(63, "reducer scratch too small");
     dim3 grid(bands, nchunks);
     stencil_march_kernel<MODE, P, NT><<<grid, NT, smem, st>>>(L, op, cfg, red.partials, red.ticket);
     P4B_LAUNCH_CHECK();
@@ -361,6 +421,7 @@ static int launch_march_mode(cudaStream_t st, const LevelDesc &L, const StencilO
         case ST_LIN: return launch_march<ST_LIN, P, NT>(st, L, op, red, NS);
         case ST_LIN_PM1: return launch_march<ST_LIN_PM1, P, NT>(st, L, op, red, NS);
         case ST_LIN_BU: return launch_march<ST_LIN_BU, P, NT>(st, L, op, red, NS);
+        case ST_LIN_PM1_DOT2: return launch_march<ST_LIN_PM1_DOT2, P, NT>(st, L, op, red, NS);
     }
     return fail(62, "unknown stencil mode %d", op.mode);
 }
@@ -370,11 +431,17 @@ int launch_stencil_generic(cudaStream_t st, const LevelDesc &L, const StencilOp 
 int launch_stencil_fast(cudaStream_t st, const LevelDesc &L, const StencilOp &op, const Reducer &red) {
     if (((uintptr_t)op.u & 15) != 0) return launch_stencil_generic(st, L, op, red);   // bulk copies need 16-byte alignment
     const MarchTune &t = tune();
+    if (t.P == 0) {
+        // measured on B200 at 513^3 (profiles/r01_march_tuning.md): the register-heavy three-operand mode
+        // wants 4 nodes/thread x 512 threads, the others 8 nodes/thread x 256 threads (2 CTAs/SM)
+        if (op.mode == ST_LIN_PM1) return launch_march<ST_LIN_PM1, 4, 512>(st, L, op, red, t.NS);
+        if (op.mode == ST_LIN_PM1_DOT2) return launch_march<ST_LIN_PM1_DOT2, 4, 512>(st, L, op, red, t.NS);
+        return launch_march_mode<8, 256>(st, L, op, red, t.NS);
+    }
     if (t.P == 4 && t.NT == 512) return launch_march_mode<4, 512>(st, L, op, red, t.NS);
     if (t.P == 8 && t.NT == 256) return launch_march_mode<8, 256>(st, L, op, red, t.NS);
     if (t.P == 8 && t.NT == 512) return launch_march_mode<8, 512>(st, L, op, red, t.NS);
     if (t.P == 4 && t.NT == 256) return launch_march_mode<4, 256>(st, L, op, red, t.NS);
-    if (t.P == 2 && t.NT == 512) return launch_march_mode<2, 512>(st, L, op, red, t.NS);
     return fail(62, "P4B_MARCH=%d,%d is not instantiated", t.P, t.NT);
 }
 

@@ -80,6 +80,44 @@ __global__ void __launch_bounds__(256) prolong_add_kernel(const LevelDesc F, con
     xf[n] += s;
 }
 
+// 3-D fast path.  One thread per (i, J, K): it interpolates the x direction once per coarse row
+// (a_jk = 1/2 (c[I0] + c[I1]), I1 = I0 for even i, which is exact) and then updates the up-to-four fine
+// nodes (i, 2J+{0,1}, 2K+{0,1}): 8 coarse loads (L1/L2 hits, neighbouring lanes share them) per 4 fine
+// nodes instead of up to 8 per node, fine accesses fully coalesced, one index division per 4 nodes.
+__global__ void __launch_bounds__(256) prolong_add3d_kernel(const LevelDesc F, const LevelDesc C, int Kfirst,
+                                                            const double *__restrict__ xc, double *__restrict__ xf) {
+    const int task = blockIdx.x * 256 + threadIdx.x;       // over nx * cny
+    if (task >= F.nx * C.ny) return;
+    const int J = task / F.nx, i = task - J * F.nx;
+    const int K = Kfirst + blockIdx.y;
+    const int I0 = i >> 1, I1 = I0 + (i & 1);
+    const int J1 = min(J + 1, C.ny - 1), K1 = min(K + 1, C.nz - 1);
+    const long long cplane = (long long)C.nx * C.ny;
+    const double *c00 = xc + ((long long)(K - C.zs) * cplane + (long long)J * C.nx);
+    const double *c10 = xc + ((long long)(K - C.zs) * cplane + (long long)J1 * C.nx);
+    const double *c01 = xc + ((long long)(K1 - C.zs) * cplane + (long long)J * C.nx);
+    const double *c11 = xc + ((long long)(K1 - C.zs) * cplane + (long long)J1 * C.nx);
+    const double a00 = 0.5 * (c00[I0] + c00[I1]);
+    const double a10 = 0.5 * (c10[I0] + c10[I1]);
+    const double a01 = 0.5 * (c01[I0] + c01[I1]);
+    const double a11 = 0.5 * (c11[I0] + c11[I1]);
+    const int j0 = 2 * J, k0 = 2 * K;
+    const bool jok = (j0 + 1 < F.ny);
+    const long long fplane = (long long)F.nx * F.ny;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        const int k = k0 + c;
+        if (k < F.zs || k >= F.zs + F.zm) continue;        // only planes this rank owns (and k <= nz-1)
+        double *row = xf + ((long long)(k - F.zs) * fplane + (long long)j0 * F.nx + i);
+        const double e0 = c ? 0.5 * (a00 + a01) : a00;
+        row[0] += e0;
+        if (jok) {
+            const double e1 = c ? 0.25 * ((a00 + a10) + (a01 + a11)) : 0.5 * (a00 + a10);
+            row[F.nx] += e1;
+        }
+    }
+}
+
 int launch_restrict(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *rf, double *bc) {
     const long long n = C.nlocal();
     if (n <= 0) return 0;
@@ -91,6 +129,13 @@ int launch_restrict(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, con
 int launch_prolong_add(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *xc, double *xf) {
     const long long n = F.nlocal();
     if (n <= 0) return 0;
+    if (F.ax && F.ay && F.az && F.nx >= 64 && (long long)F.nx * C.ny < (1LL << 30)) {
+        const int Kfirst = F.zs / 2, Klast = (F.zs + F.zm - 1) / 2;
+        dim3 grid((unsigned)(((long long)F.nx * C.ny + 255) / 256), (unsigned)(Klast - Kfirst + 1));
+        prolong_add3d_kernel<<<grid, 256, 0, st>>>(F, C, Kfirst, xc, xf);
+        P4B_LAUNCH_CHECK();
+        return 0;
+    }
     prolong_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(F, C, xc, xf);
     P4B_LAUNCH_CHECK();
     return 0;
