@@ -102,7 +102,8 @@ int p4b_version(void);
 const char *p4b_last_error(void);
 int p4b_device_count(int *n);
 /* kernel-selection knobs for tests and A/B measurements (never changes results beyond rounding):
- * "march_enabled" 0|1, "march_min_plane" nodes, "march_P", "march_NT", "march_NS" */
+ * "march_enabled" 0|1, "march_min_plane" nodes, "march_P", "march_NT", "march_NS";
+ * "rep_points": multigrid levels with at most this many nodes are replicated on every rank (default 70^3) */
 int p4b_tune(const char *key, long value);
 
 /* ---- context ---- */
@@ -154,6 +155,12 @@ int p4b_poisson_function(p4b_ctx *ctx, const p4b_grid *g, const double *u, const
 int p4b_mg_default_opts(p4b_mg_opts *o);
 int p4b_mg_create(p4b_ctx *ctx, const p4b_grid *g, const p4b_mg_opts *o, p4b_mg **mg);
 int p4b_mg_destroy(p4b_mg *mg);
+/* Host-only: the level hierarchy and slab ownership p4b_mg_create would use on `nranks` devices.
+ * Level 0 is the coarsest.  m3[3*l..] = node counts, zs/zm[l*nranks + r] = planes of the slowest dimension
+ * rank r owns on level l ("coarse plane K belongs to the owner of fine plane 2K"), replicated[l] = 1 when
+ * the level is computed redundantly on every rank.  Arrays sized for P4B_MAX_LEVELS levels; any may be NULL. */
+int p4b_plan_levels(const p4b_grid *g, const p4b_mg_opts *o, int nranks, int *nlevels, int *m3, int *zs, int *zm,
+                    int *replicated);
 int p4b_mg_nlevels(p4b_mg *mg, int *nlevels);
 /* level 0 = coarsest; m[3], eig[2] = (emin, emax) used by the smoother on that level */
 int p4b_mg_level_info(p4b_mg *mg, int level, int *m, double *eig);

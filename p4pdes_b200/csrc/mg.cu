@@ -524,6 +524,65 @@ static void slab_range(int m, int P, int r, int *s, int *c) {
     *s = r * base + (r < rem ? r : rem);
 }
 
+// ------------------------------------------------------------------------------------------------
+// level + slab planning (host only; shared by p4b_mg_create and p4b_plan_levels)
+// ------------------------------------------------------------------------------------------------
+static long long g_rep_points = 70LL * 70 * 70;   // p4b_tune("rep_points", n)
+
+struct LevelPlan {
+    std::vector<p4b_grid> grids;                 // index 0 = coarsest
+    std::vector<std::vector<int>> zs, zm;        // [level][rank]: planes of the slowest dimension each rank owns
+    int lrep = -1;                               // levels <= lrep are replicated on every rank
+};
+
+static int plan_levels(const p4b_grid *g, const p4b_mg_opts &o, int P, LevelPlan *pl) {
+    LevelDesc probe;
+    P4B_CHECK(make_desc(g, &probe));
+    std::vector<p4b_grid> gs;
+    gs.push_back(*g);
+    while ((o.levels <= 0 || (int)gs.size() < o.levels) && (int)gs.size() < P4B_MAX_LEVELS && can_coarsen(gs.back()))
+        gs.push_back(coarsen(gs.back()));
+    if (o.levels > 0 && (int)gs.size() < o.levels)
+        return fail(60, "cannot build %d multigrid levels from this grid (got %d)", o.levels, (int)gs.size());
+    const int nl = (int)gs.size();
+    pl->grids.assign(gs.rbegin(), gs.rend());
+    pl->zs.assign(nl, std::vector<int>(P, 0));
+    pl->zm.assign(nl, std::vector<int>(P, 0));
+    if (P > 1 && g->dim == 1) return fail(60, "1-D grids are not distributed");
+    // finest by p4b_slab_range; coarser: coarse plane K belongs to the owner of fine plane 2K
+    for (int l = nl - 1; l >= 0; l--) {
+        const p4b_grid &gl = pl->grids[l];
+        const int nz = gl.dim == 3 ? gl.mz : (gl.dim == 2 ? gl.my : 1);
+        for (int r = 0; r < P; r++) {
+            if (l == nl - 1) {
+                slab_range(nz, P, r, &pl->zs[l][r], &pl->zm[l][r]);
+            } else {
+                const int fs = pl->zs[l + 1][r], fe = fs + pl->zm[l + 1][r];     // [fs, fe)
+                const int ks = (fs + 1) / 2, ke = (fe - 1) / 2;                   // K with fs <= 2K <= fe-1
+                pl->zs[l][r] = ks;
+                pl->zm[l][r] = (pl->zm[l + 1][r] > 0 && ke >= ks) ? ke - ks + 1 : 0;
+            }
+        }
+    }
+    // replicate small levels: every rank must own >= 2 planes on a distributed level, and levels at or
+    // below rep_points nodes are cheaper to compute redundantly than to exchange ghosts for
+    const long long rep_points = g_rep_points;
+    pl->lrep = -1;
+    if (P > 1) {
+        pl->lrep = 0;
+        for (int l = 0; l < nl - 1; l++) {
+            int minzm = 1 << 30;
+            for (int r = 0; r < P; r++) minzm = std::min(minzm, pl->zm[l][r]);
+            const p4b_grid &gl = pl->grids[l];
+            if (minzm < 2 || (long long)gl.mx * gl.my * gl.mz <= rep_points) pl->lrep = l;
+        }
+        int minzm = 1 << 30;
+        for (int r = 0; r < P; r++) minzm = std::min(minzm, pl->zm[nl - 1][r]);
+        if (minzm < 2 || nl < 2) return fail(60, "grid too small to distribute over %d ranks", P);
+    }
+    return 0;
+}
+
 extern "C" {
 
 int p4b_version(void) { return P4B_VERSION; }
@@ -533,6 +592,7 @@ const char *p4b_kernel_name(int c) { return (c >= 0 && c < P4B_K_NCLASSES) ? k_n
 int p4b_tune(const char *key, long value) {
     if (!key) return fail(62, "null tuning key");
     if (tune_march(key, value) == 0) return 0;
+    if (std::string(key) == "rep_points") { g_rep_points = value; return 0; }
     return fail(62, "unknown tuning key %s", key);
 }
 
@@ -816,71 +876,31 @@ int p4b_mg_create(p4b_ctx *c, const p4b_grid *g, const p4b_mg_opts *oin, p4b_mg 
     p4b_mg *m = new p4b_mg();
     m->ctx = c;
     m->o = o;
-    // level grids, finest first
-    std::vector<p4b_grid> gs;
-    gs.push_back(*g);
-    while ((o.levels <= 0 || (int)gs.size() < o.levels) && can_coarsen(gs.back())) gs.push_back(coarsen(gs.back()));
-    if (o.levels > 0 && (int)gs.size() < o.levels) {
-        delete m;
-        return fail(60, "cannot build %d multigrid levels from this grid (got %d)", o.levels, (int)gs.size());
+    LevelPlan plan;
+    const int P = c->nranks, R = c->rank;
+    {
+        int rc = plan_levels(g, o, P, &plan);
+        if (rc) { delete m; return rc; }
     }
-    const int nl = (int)gs.size();
+    const int nl = (int)plan.grids.size();
     m->lev.resize(nl);
     m->top = nl - 1;
-    const int P = c->nranks, R = c->rank;
     for (int l = 0; l < nl; l++) {
         Level &L = m->lev[l];
-        L.g = gs[nl - 1 - l];
+        L.g = plan.grids[l];
         int rc = make_desc(&L.g, &L.d);
         if (rc) { delete m; return rc; }
         L.lam = lambda_max(L.d);
         if (o.emax > 0) { L.emin = o.emin; L.emax = o.emax; }
         else { L.emin = o.est_lo * L.lam; L.emax = o.est_hi * L.lam; }
         cheb_omegas(L.emin, L.emax, o.smooth_its, &L.scale, &L.omega);
-    }
-    // slab ownership: finest by p4b_slab_range, coarser by "coarse plane K belongs to the owner of fine 2K"
-    if (P > 1 && g->dim == 1) { delete m; return fail(60, "1-D grids are not distributed"); }
-    for (int l = nl - 1; l >= 0; l--) {
-        Level &L = m->lev[l];
-        L.zs_all.resize(P);
-        L.zm_all.resize(P);
-        for (int r = 0; r < P; r++) {
-            if (l == nl - 1) {
-                slab_range(L.d.nz, P, r, &L.zs_all[r], &L.zm_all[r]);
-            } else {
-                const Level &Fn = m->lev[l + 1];
-                const int fs = Fn.zs_all[r], fe = Fn.zs_all[r] + Fn.zm_all[r];   // [fs, fe)
-                const int ks = (fs + 1) / 2, ke = (fe - 1) / 2;                   // K with fs <= 2K <= fe-1
-                L.zs_all[r] = ks;
-                L.zm_all[r] = (Fn.zm_all[r] > 0 && ke >= ks) ? ke - ks + 1 : 0;
-            }
-        }
-    }
-    // replicate small levels: every rank must own >= 2 planes on a distributed level, and levels at or
-    // below rep_points nodes are cheaper to compute redundantly than to exchange ghosts for
-    const long long rep_points = 70LL * 70 * 70;
-    int lrep = -1;
-    if (P > 1) {
-        lrep = 0;
-        for (int l = 0; l < nl; l++) {
-            int minzm = 1 << 30;
-            for (int r = 0; r < P; r++) minzm = std::min(minzm, m->lev[l].zm_all[r]);
-            if (minzm < 2 || m->lev[l].d.nglobal() <= rep_points) lrep = l;
-        }
-        if (lrep >= nl - 1) lrep = nl - 1;
-    }
-    for (int l = 0; l < nl; l++) {
-        Level &L = m->lev[l];
+        L.zs_all = plan.zs[l];
+        L.zm_all = plan.zm[l];
         L.own = L.d;
         L.own.zs = L.zs_all[R];
         L.own.zm = L.zm_all[R];
-        L.replicated = (P > 1 && l <= lrep);
+        L.replicated = (P > 1 && l <= plan.lrep);
         if (P > 1 && !L.replicated) L.d = L.own;
-        if (P == 1) L.replicated = false;
-    }
-    if (P > 1 && m->lev[m->top].replicated) {
-        delete m;
-        return fail(60, "grid too small to distribute over %d ranks", P);
     }
     // arena: ghosted vectors x, b, t per level (+ p, w and two scratch vectors on the finest)
     auto vec_doubles = [](const LevelDesc &d) {
@@ -922,6 +942,27 @@ int p4b_mg_create(p4b_ctx *c, const p4b_grid *g, const p4b_mg_opts *oin, p4b_mg 
     memset(m->prof.stat, 0, sizeof m->prof.stat);
     P4B_CUDA(cudaStreamSynchronize(c->stream));
     *out = m;
+    return 0;
+}
+
+int p4b_plan_levels(const p4b_grid *g, const p4b_mg_opts *oin, int nranks, int *nlevels, int *m3, int *zs, int *zm,
+                    int *replicated) {
+    p4b_mg_opts o;
+    if (oin) o = *oin; else p4b_mg_default_opts(&o);
+    if (nranks < 1) return fail(62, "bad nranks");
+    LevelPlan pl;
+    P4B_CHECK(plan_levels(g, o, nranks, &pl));
+    const int nl = (int)pl.grids.size();
+    *nlevels = nl;
+    for (int l = 0; l < nl; l++) {
+        const p4b_grid &gl = pl.grids[l];
+        if (m3) { m3[3 * l] = gl.mx; m3[3 * l + 1] = gl.dim >= 2 ? gl.my : 1; m3[3 * l + 2] = gl.dim >= 3 ? gl.mz : 1; }
+        for (int r = 0; r < nranks; r++) {
+            if (zs) zs[l * nranks + r] = pl.zs[l][r];
+            if (zm) zm[l * nranks + r] = pl.zm[l][r];
+        }
+        if (replicated) replicated[l] = (nranks > 1 && l <= pl.lrep) ? 1 : 0;
+    }
     return 0;
 }
 

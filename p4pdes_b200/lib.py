@@ -98,6 +98,8 @@ _SIGS = {
     "p4b_mg_default_opts": (C.c_int, [C.POINTER(MGOpts)]),
     "p4b_mg_create": (C.c_int, [_P, C.POINTER(Grid), C.POINTER(MGOpts), C.POINTER(_P)]),
     "p4b_mg_destroy": (C.c_int, [_P]),
+    "p4b_plan_levels": (C.c_int, [C.POINTER(Grid), C.POINTER(MGOpts), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "p4b_mg_nlevels": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "p4b_mg_level_info": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "p4b_mg_local_range": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
@@ -140,6 +142,23 @@ def load(path: str | None = None):
 def check(rc: int):
     if rc != 0:
         raise P4BError("p4b200 error %d: %s" % (rc, load().p4b_last_error().decode()))
+
+
+def plan_levels(grid: Grid, opts: "MGOpts | None", nranks: int):
+    """Host-only view of the hierarchy and slab ownership (p4b_plan_levels).  Returns a list of dicts,
+    coarsest level first: {"m": (mx,my,mz), "zs": [...per rank], "zm": [...], "replicated": bool}."""
+    lib = load()
+    nl = C.c_int()
+    m3 = (C.c_int * (3 * 16))()
+    zs = (C.c_int * (16 * nranks))()
+    zm = (C.c_int * (16 * nranks))()
+    rep = (C.c_int * 16)()
+    check(lib.p4b_plan_levels(C.byref(grid), C.byref(opts) if opts is not None else None, nranks, C.byref(nl), m3,
+                              zs, zm, rep))
+    return [{"m": (m3[3 * l], m3[3 * l + 1], m3[3 * l + 2]),
+             "zs": [zs[l * nranks + r] for r in range(nranks)],
+             "zm": [zm[l * nranks + r] for r in range(nranks)],
+             "replicated": bool(rep[l])} for l in range(nl.value)]
 
 
 def tune(key: str, value: int):
