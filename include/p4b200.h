@@ -154,6 +154,11 @@ int p4b_poisson_function(p4b_ctx *ctx, const p4b_grid *g, const double *u, const
 /* ---- PCMG + KSPCG ---- */
 int p4b_mg_default_opts(p4b_mg_opts *o);
 int p4b_mg_create(p4b_ctx *ctx, const p4b_grid *g, const p4b_mg_opts *o, p4b_mg **mg);
+/* The Mat-plugin constructor: same as p4b_mg_create, but the constant-coefficient stencil of every level is
+ * given explicitly, coef[4*l + {0,1,2,3}] = (diagonal, |off-diagonal| in x, y, z) for level l, FINEST FIRST,
+ * as read from the values the user's FormJacobianLocal (poissonfunctions.c:117-258) inserted on that level. */
+int p4b_mg_create_stencil(p4b_ctx *ctx, const p4b_grid *g, const p4b_mg_opts *o, const double *coef,
+                          int nlevels_coef, p4b_mg **mg);
 int p4b_mg_destroy(p4b_mg *mg);
 /* Host-only: the level hierarchy and slab ownership p4b_mg_create would use on `nranks` devices.
  * Level 0 is the coarsest.  m3[3*l..] = node counts, zs/zm[l*nranks + r] = planes of the slowest dimension
@@ -166,6 +171,8 @@ int p4b_mg_nlevels(p4b_mg *mg, int *nlevels);
 int p4b_mg_level_info(p4b_mg *mg, int level, int *m, double *eig);
 /* the slab of the finest grid this rank owns: planes [start, start+count) of the slowest dimension */
 int p4b_mg_local_range(p4b_mg *mg, int *start, int *count, size_t *nlocal);
+/* y = A x with the finest level's operator ([PETSc] MatMult); x, y: nlocal doubles on device */
+int p4b_mg_matmult(p4b_mg *mg, const double *x, double *y);
 /* z = M^-1 r (one multigrid cycle from a zero guess); r, z: nlocal doubles on device */
 int p4b_mg_apply(p4b_mg *mg, const double *r, double *z);
 /* solve A x = b from x = 0 with preconditioned CG; b, x: nlocal doubles on device */

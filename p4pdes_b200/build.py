@@ -66,5 +66,52 @@ def build(force=False, verbose=False):
     return LIB
 
 
+SHIM_LIB = os.path.join(LIBDIR, "libpetsc_p4b200.so")
+SHIM_SRC = os.path.join(HERE, "shim", "petscshim.c")
+BINDIR = os.path.join(HERE, "bin")
+REFERENCE = os.environ.get("P4B_REFERENCE", "/root/reference")
+# the reference's unchanged drivers and the files each one is made of (c/ch6/makefile:5-7)
+DRIVERS = {"fish": ["c/ch6/fish.c", "c/ch6/poissonfunctions.c"]}
+
+
+def build_shim(force=False):
+    """libpetsc_p4b200.so: the PETSc-shaped C host layer (include/petsc.h) over libp4b200.so."""
+    build(force=False)
+    deps = [SHIM_SRC, os.path.join(ROOT, "include", "petsc.h"), os.path.join(ROOT, "include", "p4b200.h")]
+    if (not force and os.path.exists(SHIM_LIB)
+            and all(os.path.getmtime(d) < os.path.getmtime(SHIM_LIB) for d in deps)):
+        return SHIM_LIB
+    cmd = ["gcc", "-std=c99", "-O2", "-Wall", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), SHIM_SRC,
+           "-o", SHIM_LIB, "-L", LIBDIR, "-lp4b200", "-Wl,-rpath,$ORIGIN", "-lm"]
+    subprocess.check_call(cmd)
+    return SHIM_LIB
+
+
+def build_drivers(force=False):
+    """Compile the reference's UNCHANGED C drivers from where they lie under /root/reference against the shim.
+    Returns {name: path}; skipped (prebuilt binaries are used) when the reference tree is absent."""
+    out = {}
+    build_shim(force=False)
+    os.makedirs(BINDIR, exist_ok=True)
+    for name, files in DRIVERS.items():
+        exe = os.path.join(BINDIR, name)
+        srcs = [os.path.join(REFERENCE, f) for f in files]
+        if not all(os.path.exists(s) for s in srcs):
+            if os.path.exists(exe):
+                out[name] = exe
+            continue
+        if (not force and os.path.exists(exe) and os.path.getmtime(exe) > os.path.getmtime(SHIM_LIB)
+                and all(os.path.getmtime(exe) > os.path.getmtime(s) for s in srcs)):
+            out[name] = exe
+            continue
+        cmd = ["gcc", "-std=c99", "-pedantic", "-O2", "-I", os.path.join(ROOT, "include")] + srcs + [
+            "-o", exe, "-L", LIBDIR, "-lpetsc_p4b200", "-lp4b200", "-Wl,-rpath,$ORIGIN/../lib", "-lm"]
+        subprocess.check_call(cmd)
+        out[name] = exe
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_shim(force="--force" in sys.argv))
+    print(build_drivers(force="--force" in sys.argv))

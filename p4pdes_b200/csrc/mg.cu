@@ -866,7 +866,24 @@ int p4b_mg_default_opts(p4b_mg_opts *o) {
     return 0;
 }
 
+static int mg_create_impl(p4b_ctx *c, const p4b_grid *g, const p4b_mg_opts *oin, const double *coef, int ncoef,
+                          p4b_mg **out);
+
 int p4b_mg_create(p4b_ctx *c, const p4b_grid *g, const p4b_mg_opts *oin, p4b_mg **out) {
+    return mg_create_impl(c, g, oin, nullptr, 0, out);
+}
+
+// Same hierarchy, but the operator of every level comes from the caller: coef[4*l + {0,1,2,3}] =
+// (diag, off_x, off_y, off_z) magnitudes of level l, FINEST FIRST (l = 0), as a Mat plugin reads them out of
+// the values the user's FormJacobianLocal inserted on that level's DMDA (rediscretisation, fish.c:7).
+int p4b_mg_create_stencil(p4b_ctx *c, const p4b_grid *g, const p4b_mg_opts *oin, const double *coef, int nlevels_coef,
+                          p4b_mg **out) {
+    if (!coef || nlevels_coef < 1) return fail(62, "stencil coefficients required");
+    return mg_create_impl(c, g, oin, coef, nlevels_coef, out);
+}
+
+static int mg_create_impl(p4b_ctx *c, const p4b_grid *g, const p4b_mg_opts *oin, const double *coef, int ncoef,
+                          p4b_mg **out) {
     p4b_mg_opts o;
     if (oin) o = *oin; else p4b_mg_default_opts(&o);
     if (o.cycle != P4B_CYCLE_V && o.cycle != P4B_CYCLE_W) return fail(62, "unknown -pc_mg_cycle_type");
@@ -890,6 +907,16 @@ int p4b_mg_create(p4b_ctx *c, const p4b_grid *g, const p4b_mg_opts *oin, p4b_mg 
         L.g = plan.grids[l];
         int rc = make_desc(&L.g, &L.d);
         if (rc) { delete m; return rc; }
+        if (coef) {
+            const int lc = nl - 1 - l;      // caller's index: finest first
+            if (lc >= ncoef) { delete m; return fail(62, "coefficients for %d levels given, %d needed", ncoef, nl); }
+            const double *q = coef + 4 * lc;
+            if (!(q[0] > 0)) { delete m; return fail(62, "non-positive diagonal on level %d", lc); }
+            L.d.diag = q[0];
+            if (L.g.dim == 1) { L.d.cx = q[1]; }
+            else if (L.g.dim == 2) { L.d.cx = q[1]; L.d.cz = q[2]; }     // 2-D: y lives in slot z
+            else { L.d.cx = q[1]; L.d.cy = q[2]; L.d.cz = q[3]; }
+        }
         L.lam = lambda_max(L.d);
         if (o.emax > 0) { L.emin = o.emin; L.emax = o.emax; }
         else { L.emin = o.est_lo * L.lam; L.emax = o.est_hi * L.lam; }
@@ -993,6 +1020,21 @@ int p4b_mg_local_range(p4b_mg *m, int *start, int *count, size_t *nlocal) {
     if (start) *start = d.zs;
     if (count) *count = d.zm;
     if (nlocal) *nlocal = (size_t)d.nlocal();
+    return 0;
+}
+
+// y = A x on the finest level (MatMult of the level operator, explicit coefficients honoured)
+int p4b_mg_matmult(p4b_mg *m, const double *x, double *y) {
+    Level &T = m->lev[m->top];
+    cudaStream_t st = m->ctx->stream;
+    const size_t bytes = sizeof(double) * (size_t)T.d.nlocal();
+    P4B_CUDA(cudaMemcpyAsync(m->p, x, bytes, cudaMemcpyDeviceToDevice, st));
+    P4B_CHECK(halo(m, m->top, m->p));
+    StencilOp op;
+    memset(&op, 0, sizeof op);
+    op.mode = ST_APPLY; op.u = m->p; op.out = m->w;
+    P4B_CHECK(launch_stencil(st, T.d, op, m->ctx->red));
+    P4B_CUDA(cudaMemcpyAsync(y, m->w, bytes, cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 

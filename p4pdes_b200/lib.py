@@ -97,12 +97,15 @@ _SIGS = {
     "p4b_poisson_function": (C.c_int, [_P, C.POINTER(Grid), _D, _D, _D, _D]),
     "p4b_mg_default_opts": (C.c_int, [C.POINTER(MGOpts)]),
     "p4b_mg_create": (C.c_int, [_P, C.POINTER(Grid), C.POINTER(MGOpts), C.POINTER(_P)]),
+    "p4b_mg_create_stencil": (C.c_int, [_P, C.POINTER(Grid), C.POINTER(MGOpts), C.POINTER(C.c_double), C.c_int,
+                                        C.POINTER(_P)]),
     "p4b_mg_destroy": (C.c_int, [_P]),
     "p4b_plan_levels": (C.c_int, [C.POINTER(Grid), C.POINTER(MGOpts), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "p4b_mg_nlevels": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "p4b_mg_level_info": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "p4b_mg_local_range": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "p4b_mg_matmult": (C.c_int, [_P, _D, _D]),
     "p4b_mg_apply": (C.c_int, [_P, _D, _D]),
     "p4b_cg_solve": (C.c_int, [_P, C.c_int, _D, _D, C.c_double, C.c_double, C.c_int, C.POINTER(KSPResult)]),
     "p4b_cg_solve_host": (C.c_int, [_P, C.c_int, _P, _P, C.c_double, C.c_double, C.c_int, C.POINTER(KSPResult)]),

@@ -1,0 +1,942 @@
+/* petscshim.c -- the PETSc-shaped host layer behind include/petsc.h (C99, NOT PETSc).
+ *
+ * Lets the reference's unchanged drivers (c/ch6/fish.c + c/ch6/poissonfunctions.c) run on a B200:
+ * objects are thin host structs; every numerical operation of the solve goes through the C ABI of
+ * include/p4b200.h into the CUDA kernels.  What runs on the host is what the reference itself runs
+ * on the host: option parsing, the user's FormFunctionLocal / FormJacobianLocal callbacks (called
+ * exactly as PETSc calls them: once per SNES function evaluation, once per multigrid level for the
+ * rediscretised Jacobian, fish.c:7) and the final report.
+ *
+ * Plugin structure (the PETSc idiom): Mat types and PC types are looked up by name in registries
+ * filled through MatRegister()/PCRegister(); the shim registers "stencilcuda" and "mg"/"jacobi"/"none".
+ * There is no CPU solver here: -pc_type ilu/sor/... and friends fail with an explanatory error.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include <petsc.h>
+
+#include <stdarg.h>
+#include <strings.h>
+#include <stdlib.h>
+#include <time.h>
+
+#include "p4b200.h"
+
+/* ------------------------------------------------------------------------------------------------ */
+/* globals: option database, device context, log                                                    */
+/* ------------------------------------------------------------------------------------------------ */
+#define MAXOPT 256
+static struct { char *name; char *value; int used; } g_opt[MAXOPT];
+static int g_nopt = 0;
+static char g_prefix[64] = "";
+static p4b_ctx *g_ctx = NULL;
+static double g_flops = 0.0;
+static double g_t_snes = 0.0, g_t_ksp = 0.0, g_t_ksp_dev_ms = 0.0, g_t_jac = 0.0, g_t_func = 0.0;
+static int g_initialized = 0;
+
+static double wall(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+PetscErrorCode PetscShimError(MPI_Comm comm, int line, const char *func, const char *file, PetscErrorCode code,
+                              const char *msg) {
+    (void)comm;
+    fprintf(stderr, "[0]PETSC ERROR: %s", msg);
+    if (!msg[0] || msg[strlen(msg) - 1] != '\n') fprintf(stderr, "\n");
+    fprintf(stderr, "[0]PETSC ERROR: #1 %s() at %s:%d (p4b200 shim)\n", func, file, line);
+    return code ? code : 1;
+}
+#define SHIM_ERR(code, msg) return PetscShimError(PETSC_COMM_SELF, __LINE__, __func__, __FILE__, code, msg)
+#define P4B(call)                                                                                        \
+    do {                                                                                                 \
+        int rc_ = (call);                                                                                \
+        if (rc_) return PetscShimError(PETSC_COMM_SELF, __LINE__, __func__, __FILE__, rc_, p4b_last_error()); \
+    } while (0)
+
+static PetscErrorCode ensure_ctx(void) {
+    if (!g_ctx) P4B(p4b_ctx_create(0, NULL, &g_ctx));
+    return 0;
+}
+
+/* ---- options ---- */
+static int opt_find(const char *name) {
+    for (int i = 0; i < g_nopt; i++)
+        if (!strcmp(g_opt[i].name, name)) { g_opt[i].used = 1; return i; }
+    return -1;
+}
+static const char *opt_value(const char *name) {
+    int i = opt_find(name);
+    return i < 0 ? NULL : g_opt[i].value;
+}
+static int opt_has(const char *name) { return opt_find(name) >= 0; }
+static int opt_bool(const char *name, int dflt) {
+    int i = opt_find(name);
+    if (i < 0) return dflt;
+    const char *v = g_opt[i].value;
+    if (!v) return 1;
+    return !(v[0] == '0' || v[0] == 'f' || v[0] == 'F' || v[0] == 'n' || v[0] == 'N');
+}
+
+static int is_number(const char *s) {
+    char *e;
+    strtod(s, &e);
+    return e != s;
+}
+
+PetscErrorCode PetscInitialize(int *argc, char ***argv, const char file[], const char help[]) {
+    (void)file;
+    g_nopt = 0;
+    for (int i = 1; argc && i < *argc; i++) {
+        const char *a = (*argv)[i];
+        if (a[0] != '-' || is_number(a)) continue;
+        if (g_nopt >= MAXOPT) break;
+        g_opt[g_nopt].name = strdup(a);
+        g_opt[g_nopt].value = NULL;
+        g_opt[g_nopt].used = 0;
+        if (i + 1 < *argc) {
+            const char *v = (*argv)[i + 1];
+            if (v[0] != '-' || is_number(v)) { g_opt[g_nopt].value = strdup(v); i++; }
+        }
+        g_nopt++;
+    }
+    if (opt_has("-help") && help) printf("%s", help);
+    g_initialized = 1;
+    return 0;
+}
+
+PetscErrorCode PetscFinalize(void) {
+    if (opt_has("-log_view")) {
+        printf("------------------------------------------------------------------ p4b200 shim -log_view\n");
+        printf("Time (sec):  SNESSolve %.6e   KSPSolve %.6e (device %.6e)\n", g_t_snes, g_t_ksp, g_t_ksp_dev_ms * 1e-3);
+        printf("             FunctionEval(host callback) %.6e   JacobianEval(host callback, all levels) %.6e\n",
+               g_t_func, g_t_jac);
+        printf("Flop:  %.6e (user PetscLogFlops only)   kernel launches: %lld\n", g_flops, p4b_launch_count());
+    }
+    if (opt_has("-options_left")) {
+        for (int i = 0; i < g_nopt; i++)
+            if (!g_opt[i].used)
+                printf("WARNING! option %s %s was set but not used\n", g_opt[i].name, g_opt[i].value ? g_opt[i].value : "");
+    }
+    if (g_ctx) { p4b_ctx_destroy(g_ctx); g_ctx = NULL; }
+    for (int i = 0; i < g_nopt; i++) { free(g_opt[i].name); free(g_opt[i].value); }
+    g_nopt = 0;
+    return 0;
+}
+
+PetscErrorCode PetscPrintf(MPI_Comm comm, const char format[], ...) {
+    (void)comm;
+    va_list ap;
+    va_start(ap, format);
+    vprintf(format, ap);
+    va_end(ap);
+    fflush(stdout);
+    return 0;
+}
+
+PetscErrorCode PetscLogFlops(PetscLogDouble f) { g_flops += f; return 0; }
+
+PetscErrorCode PetscShimOptionsBegin(MPI_Comm comm, const char prefix[], const char title[], const char mansec[]) {
+    (void)comm; (void)title; (void)mansec;
+    snprintf(g_prefix, sizeof g_prefix, "%s", prefix ? prefix : "");
+    return 0;
+}
+PetscErrorCode PetscShimOptionsEnd(void) { g_prefix[0] = 0; return 0; }
+
+static void full_name(const char *opt, char *out, size_t n) { snprintf(out, n, "-%s%s", g_prefix, opt + 1); }
+
+PetscErrorCode PetscOptionsReal(const char opt[], const char text[], const char man[], PetscReal cur, PetscReal *value,
+                                PetscBool *set) {
+    (void)text; (void)man;
+    char nm[128];
+    full_name(opt, nm, sizeof nm);
+    const char *v = opt_value(nm);
+    if (set) *set = v ? PETSC_TRUE : PETSC_FALSE;
+    *value = v ? strtod(v, NULL) : cur;
+    return 0;
+}
+PetscErrorCode PetscOptionsInt(const char opt[], const char text[], const char man[], PetscInt cur, PetscInt *value,
+                               PetscBool *set) {
+    (void)text; (void)man;
+    char nm[128];
+    full_name(opt, nm, sizeof nm);
+    const char *v = opt_value(nm);
+    if (set) *set = v ? PETSC_TRUE : PETSC_FALSE;
+    *value = v ? (PetscInt)strtol(v, NULL, 10) : cur;
+    return 0;
+}
+PetscErrorCode PetscOptionsBool(const char opt[], const char text[], const char man[], PetscBool cur, PetscBool *value,
+                                PetscBool *set) {
+    (void)text; (void)man;
+    char nm[128];
+    full_name(opt, nm, sizeof nm);
+    int has = opt_has(nm);
+    if (set) *set = has ? PETSC_TRUE : PETSC_FALSE;
+    *value = has ? (opt_bool(nm, 1) ? PETSC_TRUE : PETSC_FALSE) : cur;
+    return 0;
+}
+PetscErrorCode PetscOptionsEnum(const char opt[], const char text[], const char man[], const char *const *list,
+                                PetscEnum cur, PetscEnum *value, PetscBool *set) {
+    (void)text; (void)man;
+    char nm[128];
+    full_name(opt, nm, sizeof nm);
+    const char *v = opt_value(nm);
+    if (set) *set = v ? PETSC_TRUE : PETSC_FALSE;
+    *value = cur;
+    if (!v) return 0;
+    /* list = names..., "EnumName", "prefix", NULL  (fish.c:109-110) */
+    int n = 0;
+    while (list[n]) n++;
+    n -= 2;
+    for (int i = 0; i < n; i++)
+        if (!strcasecmp(list[i], v)) { *value = (PetscEnum)i; return 0; }
+    {
+        char msg[256];
+        snprintf(msg, sizeof msg, "Unknown option \"%s\" for %s", v, nm);
+        SHIM_ERR(62, msg);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* objects                                                                                          */
+/* ------------------------------------------------------------------------------------------------ */
+struct _p_DM {
+    int dim, M[3], dof, sw, refine, setup, refct;
+    DMBoundaryType b[3];
+    DMDAStencilType st;
+    double cmin[3], cmax[3];
+    void *appctx;
+    DMDASNESFunctionFn *func;
+    void *funcctx;
+    DMDASNESJacobianFn *jac;
+    void *jacctx;
+    Vec pool[8];
+    int pool_busy[8];
+};
+
+enum { LOC_HOST = 1, LOC_DEV = 2 };
+struct _p_Vec {
+    size_t n;
+    DM dm;
+    double *h;          /* host copy */
+    double *d;          /* device copy (lazy) */
+    int valid;          /* LOC_HOST | LOC_DEV */
+    void *tables;       /* pointer tables handed out by DMDAVecGetArray */
+    int pooled;
+};
+
+/* Mat type "stencilcuda": the values inserted by MatSetValuesStencil are checked against the
+ * constant-coefficient Dirichlet stencil of poissonfunctions.h:33-38 and reduced to (diag, cx, cy, cz). */
+struct _p_Mat {
+    DM dm;
+    const char *type;
+    double diag, c[3];
+    int have_diag, have_c[3];
+    long long rows_set;
+    int general;        /* 1: the inserted values are NOT such a stencil */
+    char why[160];
+    int assembled;
+};
+
+struct _p_PC {
+    char type[32];
+    int levels, cycle, smoother, smooth_its, have_eig;
+    double emin, emax, est_lo, est_hi;
+    int fuse;
+    char levels_pc[32];
+};
+struct _p_KSP {
+    char type[32];
+    double rtol, abstol;
+    int max_it, its, reason;
+    int converged_reason_flag, monitor_flag;
+    struct _p_PC pc;
+};
+struct _p_SNES {
+    DM dm;
+    char type[32];
+    struct _p_KSP ksp;
+    Vec sol;
+    int monitor, monitor_short, converged_reason_flag, its;
+};
+
+/* ---- registries ---- */
+#define MAXREG 16
+static struct { char name[32]; PetscErrorCode (*create)(Mat); } g_matreg[MAXREG];
+static struct { char name[32]; PetscErrorCode (*create)(PC); } g_pcreg[MAXREG];
+static int g_nmatreg = 0, g_npcreg = 0;
+
+PetscErrorCode MatRegister(const char name[], PetscErrorCode (*create)(Mat)) {
+    if (g_nmatreg >= MAXREG) SHIM_ERR(62, "Mat registry full");
+    snprintf(g_matreg[g_nmatreg].name, 32, "%s", name);
+    g_matreg[g_nmatreg++].create = create;
+    return 0;
+}
+PetscErrorCode PCRegister(const char name[], PetscErrorCode (*create)(PC)) {
+    if (g_npcreg >= MAXREG) SHIM_ERR(62, "PC registry full");
+    snprintf(g_pcreg[g_npcreg].name, 32, "%s", name);
+    g_pcreg[g_npcreg++].create = create;
+    return 0;
+}
+static PetscErrorCode MatCreate_StencilCUDA(Mat A) { A->type = MATSTENCILCUDA; return 0; }
+static PetscErrorCode PCCreate_MG_P4B(PC pc) { snprintf(pc->type, 32, "%s", PCMG); return 0; }
+static PetscErrorCode PCCreate_Jacobi_P4B(PC pc) { snprintf(pc->type, 32, "%s", PCJACOBI); return 0; }
+static PetscErrorCode PCCreate_None_P4B(PC pc) { snprintf(pc->type, 32, "%s", PCNONE); return 0; }
+static void register_all(void) {
+    static int done = 0;
+    if (done) return;
+    done = 1;
+    MatRegister(MATSTENCILCUDA, MatCreate_StencilCUDA);
+    PCRegister(PCMG, PCCreate_MG_P4B);
+    PCRegister(PCJACOBI, PCCreate_Jacobi_P4B);
+    PCRegister(PCNONE, PCCreate_None_P4B);
+}
+
+PetscErrorCode PCSetType(PC pc, PCType type) {
+    register_all();
+    for (int i = 0; i < g_npcreg; i++)
+        if (!strcmp(g_pcreg[i].name, type)) return g_pcreg[i].create(pc);
+    {
+        char msg[256];
+        snprintf(msg, sizeof msg,
+                 "PC type %s is not provided by the p4b200 device path (registered: mg, jacobi, none); "
+                 "PETSc's ilu/icc/sor/asm/bjacobi are sequential CPU algorithms", type);
+        SHIM_ERR(86, msg);
+    }
+}
+
+/* ---- DMDA ---- */
+static PetscErrorCode da_create(int dim, const DMBoundaryType *b, DMDAStencilType st, const PetscInt *M, PetscInt dof,
+                                PetscInt s, DM *da) {
+    if (!g_initialized) SHIM_ERR(73, "PetscInitialize() must be called first");
+    DM d = (DM)calloc(1, sizeof *d);
+    d->dim = dim;
+    for (int i = 0; i < 3; i++) {
+        d->M[i] = i < dim ? M[i] : 1;
+        d->b[i] = i < dim ? b[i] : DM_BOUNDARY_NONE;
+        d->cmin[i] = 0.0;
+        d->cmax[i] = 1.0;
+        if (d->b[i] != DM_BOUNDARY_NONE) {
+            free(d);
+            SHIM_ERR(56, "only DM_BOUNDARY_NONE grids are provided by the shim so far");
+        }
+    }
+    d->dof = dof; d->sw = s; d->st = st; d->refct = 1;
+    if (dof != 1) { free(d); SHIM_ERR(56, "only dof = 1 grids are provided by the shim so far"); }
+    *da = d;
+    return 0;
+}
+PetscErrorCode DMDACreate1d(MPI_Comm comm, DMBoundaryType bx, PetscInt M, PetscInt dof, PetscInt s, const PetscInt lx[],
+                            DM *da) {
+    (void)comm; (void)lx;
+    DMBoundaryType b[3] = {bx, DM_BOUNDARY_NONE, DM_BOUNDARY_NONE};
+    PetscInt m[3] = {M, 1, 1};
+    return da_create(1, b, DMDA_STENCIL_STAR, m, dof, s, da);
+}
+PetscErrorCode DMDACreate2d(MPI_Comm comm, DMBoundaryType bx, DMBoundaryType by, DMDAStencilType st, PetscInt M, PetscInt N,
+                            PetscInt m, PetscInt n, PetscInt dof, PetscInt s, const PetscInt lx[], const PetscInt ly[],
+                            DM *da) {
+    (void)comm; (void)m; (void)n; (void)lx; (void)ly;
+    DMBoundaryType b[3] = {bx, by, DM_BOUNDARY_NONE};
+    PetscInt mm[3] = {M, N, 1};
+    return da_create(2, b, st, mm, dof, s, da);
+}
+PetscErrorCode DMDACreate3d(MPI_Comm comm, DMBoundaryType bx, DMBoundaryType by, DMBoundaryType bz, DMDAStencilType st,
+                            PetscInt M, PetscInt N, PetscInt P, PetscInt m, PetscInt n, PetscInt p, PetscInt dof,
+                            PetscInt s, const PetscInt lx[], const PetscInt ly[], const PetscInt lz[], DM *da) {
+    (void)comm; (void)m; (void)n; (void)p; (void)lx; (void)ly; (void)lz;
+    DMBoundaryType b[3] = {bx, by, bz};
+    PetscInt mm[3] = {M, N, P};
+    return da_create(3, b, st, mm, dof, s, da);
+}
+PetscErrorCode DMSetApplicationContext(DM dm, void *ctx) { dm->appctx = ctx; return 0; }
+PetscErrorCode DMGetApplicationContext(DM dm, void *ctx) { *(void **)ctx = dm->appctx; return 0; }
+PetscErrorCode DMSetFromOptions(DM dm) {
+    const char *v;
+    const char *names[3] = {"-da_grid_x", "-da_grid_y", "-da_grid_z"};
+    for (int i = 0; i < dm->dim; i++)
+        if ((v = opt_value(names[i]))) dm->M[i] = atoi(v);
+    if ((v = opt_value("-da_refine"))) dm->refine = atoi(v);
+    return 0;
+}
+PetscErrorCode DMSetUp(DM dm) {
+    if (dm->setup) return 0;
+    for (int i = 0; i < dm->dim; i++)       /* -da_refine n, non-periodic: M <- 1 + 2^n (M-1)   */
+        dm->M[i] = 1 + (1 << dm->refine) * (dm->M[i] - 1);
+    dm->setup = 1;
+    return 0;
+}
+PetscErrorCode DMDASetUniformCoordinates(DM da, PetscReal xmin, PetscReal xmax, PetscReal ymin, PetscReal ymax,
+                                         PetscReal zmin, PetscReal zmax) {
+    da->cmin[0] = xmin; da->cmax[0] = xmax;
+    da->cmin[1] = ymin; da->cmax[1] = ymax;
+    da->cmin[2] = zmin; da->cmax[2] = zmax;
+    return 0;
+}
+PetscErrorCode DMGetBoundingBox(DM dm, PetscReal gmin[], PetscReal gmax[]) {
+    for (int i = 0; i < dm->dim; i++) {
+        if (gmin) gmin[i] = dm->cmin[i];
+        if (gmax) gmax[i] = dm->cmax[i];
+    }
+    return 0;
+}
+PetscErrorCode DMDAGetLocalInfo(DM da, DMDALocalInfo *info) {
+    if (!da->setup) SHIM_ERR(73, "DMSetUp() must be called before DMDAGetLocalInfo()");
+    memset(info, 0, sizeof *info);
+    info->da = da; info->dim = da->dim; info->dof = da->dof; info->sw = da->sw;
+    info->mx = da->M[0]; info->my = da->M[1]; info->mz = da->M[2];
+    info->xs = info->ys = info->zs = 0;
+    info->xm = da->M[0]; info->ym = da->M[1]; info->zm = da->M[2];
+    info->gxs = info->gys = info->gzs = 0;        /* one logical rank owns the whole non-periodic grid */
+    info->gxm = da->M[0]; info->gym = da->M[1]; info->gzm = da->M[2];
+    info->bx = da->b[0]; info->by = da->b[1]; info->bz = da->b[2];
+    info->st = da->st;
+    return 0;
+}
+static size_t da_n(DM dm) { return (size_t)dm->M[0] * dm->M[1] * dm->M[2]; }
+
+static PetscErrorCode vec_new(DM dm, Vec *v) {
+    Vec x = (Vec)calloc(1, sizeof *x);
+    x->n = da_n(dm);
+    x->dm = dm;
+    x->h = (double *)calloc(x->n, sizeof(double));
+    if (!x->h) { free(x); SHIM_ERR(55, "out of host memory for a Vec"); }
+    x->valid = LOC_HOST;
+    *v = x;
+    return 0;
+}
+PetscErrorCode DMCreateGlobalVector(DM dm, Vec *g) {
+    if (!dm->setup) SHIM_ERR(73, "DMSetUp() must be called before DMCreateGlobalVector()");
+    return vec_new(dm, g);
+}
+PetscErrorCode DMGetGlobalVector(DM dm, Vec *g) {
+    for (int i = 0; i < 8; i++)
+        if (dm->pool[i] && !dm->pool_busy[i]) { dm->pool_busy[i] = 1; *g = dm->pool[i]; return 0; }
+    for (int i = 0; i < 8; i++)
+        if (!dm->pool[i]) {
+            PetscCall(DMCreateGlobalVector(dm, &dm->pool[i]));
+            dm->pool[i]->pooled = 1;
+            dm->pool_busy[i] = 1;
+            *g = dm->pool[i];
+            return 0;
+        }
+    SHIM_ERR(77, "DMGetGlobalVector pool exhausted");
+}
+PetscErrorCode DMRestoreGlobalVector(DM dm, Vec *g) {
+    for (int i = 0; i < 8; i++)
+        if (dm->pool[i] == *g) { dm->pool_busy[i] = 0; *g = NULL; return 0; }
+    SHIM_ERR(62, "vector was not obtained with DMGetGlobalVector");
+}
+static void vec_free(Vec v) {
+    if (!v) return;
+    if (v->d && g_ctx) p4b_free(g_ctx, v->d);
+    free(v->h);
+    free(v->tables);
+    free(v);
+}
+PetscErrorCode VecDestroy(Vec *v) {
+    if (!v || !*v) return 0;
+    if ((*v)->pooled) SHIM_ERR(62, "cannot VecDestroy a vector owned by DMGetGlobalVector");
+    vec_free(*v);
+    *v = NULL;
+    return 0;
+}
+PetscErrorCode DMDestroy(DM *dm) {
+    if (!dm || !*dm) return 0;
+    if (--(*dm)->refct > 0) { *dm = NULL; return 0; }     /* SNES keeps its own reference (fish.c:245-249) */
+    for (int i = 0; i < 8; i++) vec_free((*dm)->pool[i]);
+    free(*dm);
+    *dm = NULL;
+    return 0;
+}
+
+static PetscErrorCode vec_to_host(Vec v) {
+    if (v->valid & LOC_HOST) return 0;
+    P4B(p4b_memcpy_d2h(g_ctx, v->h, v->d, v->n * sizeof(double)));
+    v->valid |= LOC_HOST;
+    return 0;
+}
+static PetscErrorCode vec_to_dev(Vec v) {
+    PetscCall(ensure_ctx());
+    if (!v->d) P4B(p4b_malloc(g_ctx, v->n * sizeof(double), (void **)&v->d));
+    if (v->valid & LOC_DEV) return 0;
+    P4B(p4b_memcpy_h2d(g_ctx, v->d, v->h, v->n * sizeof(double)));
+    v->valid |= LOC_DEV;
+    return 0;
+}
+
+/* a[k][j][i] views with global indices (one rank owns everything, so no offsets are needed) */
+static void *make_tables(int dim, const int *M, double *base) {
+    if (dim == 1) return NULL;
+    if (dim == 2) {
+        double **rows = (double **)malloc(sizeof(double *) * (size_t)M[1]);
+        for (int j = 0; j < M[1]; j++) rows[j] = base + (size_t)j * M[0];
+        return rows;
+    }
+    size_t np = (size_t)M[2], nr = (size_t)M[2] * M[1];
+    char *blk = (char *)malloc(sizeof(double **) * np + sizeof(double *) * nr);
+    double ***planes = (double ***)blk;
+    double **rows = (double **)(blk + sizeof(double **) * np);
+    for (size_t k = 0; k < np; k++) {
+        planes[k] = rows + k * M[1];
+        for (int j = 0; j < M[1]; j++) planes[k][j] = base + (k * M[1] + j) * (size_t)M[0];
+    }
+    return planes;
+}
+static PetscErrorCode get_array(DM da, Vec vec, void *array, int write) {
+    PetscCall(vec_to_host(vec));
+    if (write) vec->valid = LOC_HOST;
+    free(vec->tables);
+    vec->tables = make_tables(da->dim, da->M, vec->h);
+    *(void **)array = da->dim == 1 ? (void *)vec->h : vec->tables;
+    return 0;
+}
+PetscErrorCode DMDAVecGetArray(DM da, Vec vec, void *array) { return get_array(da, vec, array, 1); }
+PetscErrorCode DMDAVecGetArrayRead(DM da, Vec vec, void *array) { return get_array(da, vec, array, 0); }
+PetscErrorCode DMDAVecRestoreArray(DM da, Vec vec, void *array) {
+    (void)da;
+    free(vec->tables);
+    vec->tables = NULL;
+    *(void **)array = NULL;
+    return 0;
+}
+PetscErrorCode DMDAVecRestoreArrayRead(DM da, Vec vec, void *array) { return DMDAVecRestoreArray(da, vec, array); }
+
+PetscErrorCode DMDASNESSetFunctionLocal(DM dm, InsertMode imode, DMDASNESFunctionFn *func, void *ctx) {
+    (void)imode;
+    dm->func = func; dm->funcctx = ctx;
+    return 0;
+}
+PetscErrorCode DMDASNESSetJacobianLocal(DM dm, DMDASNESJacobianFn *func, void *ctx) {
+    dm->jac = func; dm->jacctx = ctx;
+    return 0;
+}
+
+/* ---- Vec operations: BLAS-1 on the device (p4b_vec_*), trivial fills on the host ---- */
+PetscErrorCode VecSet(Vec x, PetscScalar a) {
+    for (size_t i = 0; i < x->n; i++) x->h[i] = a;
+    x->valid = LOC_HOST;
+    return 0;
+}
+PetscErrorCode PetscRandomCreate(MPI_Comm comm, PetscRandom *r) { (void)comm; *r = NULL; return 0; }
+PetscErrorCode PetscRandomDestroy(PetscRandom *r) { *r = NULL; return 0; }
+PetscErrorCode VecSetRandom(Vec x, PetscRandom r) {
+    (void)x; (void)r;
+    SHIM_ERR(56, "VecSetRandom needs PETSc's rander48 stream, which the shim does not reproduce "
+                 "(-fsh_initial_type random is not provided)");
+}
+PetscErrorCode VecAXPY(Vec y, PetscScalar a, Vec x) {
+    if (x->n != y->n) SHIM_ERR(75, "VecAXPY: incompatible vector sizes");
+    PetscCall(vec_to_dev(x));
+    PetscCall(vec_to_dev(y));
+    P4B(p4b_vec_axpy(g_ctx, y->n, a, x->d, y->d));
+    y->valid = LOC_DEV;
+    return 0;
+}
+PetscErrorCode VecAYPX(Vec y, PetscScalar b, Vec x) {
+    if (x->n != y->n) SHIM_ERR(75, "VecAYPX: incompatible vector sizes");
+    PetscCall(vec_to_dev(x));
+    PetscCall(vec_to_dev(y));
+    P4B(p4b_vec_aypx(g_ctx, y->n, b, x->d, y->d));
+    y->valid = LOC_DEV;
+    return 0;
+}
+PetscErrorCode VecScale(Vec x, PetscScalar a) {
+    PetscCall(vec_to_dev(x));
+    P4B(p4b_vec_aypx(g_ctx, x->n, a - 1.0, x->d, x->d));    /* x = x + (a-1) x */
+    x->valid = LOC_DEV;
+    return 0;
+}
+PetscErrorCode VecCopy(Vec x, Vec y) {
+    PetscCall(vec_to_host(x));
+    memcpy(y->h, x->h, x->n * sizeof(double));
+    y->valid = LOC_HOST;
+    return 0;
+}
+PetscErrorCode VecDot(Vec x, Vec y, PetscScalar *val) {
+    PetscCall(vec_to_dev(x));
+    PetscCall(vec_to_dev(y));
+    P4B(p4b_vec_dot(g_ctx, x->n, x->d, y->d, val));
+    return 0;
+}
+PetscErrorCode VecNorm(Vec x, NormType type, PetscReal *val) {
+    PetscCall(vec_to_dev(x));
+    if (type == NORM_2 || type == NORM_FROBENIUS) P4B(p4b_vec_norm2(g_ctx, x->n, x->d, val));
+    else if (type == NORM_INFINITY) P4B(p4b_vec_norminf(g_ctx, x->n, x->d, val));
+    else SHIM_ERR(56, "VecNorm: only NORM_2 and NORM_INFINITY are provided");
+    return 0;
+}
+PetscErrorCode VecGetSize(Vec x, PetscInt *size) { *size = (PetscInt)x->n; return 0; }
+PetscErrorCode VecDuplicate(Vec v, Vec *newv) { return vec_new(v->dm, newv); }
+
+/* ---- Mat "stencilcuda" ---- */
+static PetscErrorCode mat_new(DM dm, Mat *mat) {
+    register_all();
+    Mat A = (Mat)calloc(1, sizeof *A);
+    A->dm = dm;
+    const char *want = opt_value("-mat_type");
+    if (!want || !strcmp(want, "aij")) want = MATSTENCILCUDA;      /* DMCreateMatrix default -> our structured type */
+    for (int i = 0; i < g_nmatreg; i++)
+        if (!strcmp(g_matreg[i].name, want)) {
+            PetscCall(g_matreg[i].create(A));
+            *mat = A;
+            return 0;
+        }
+    free(A);
+    SHIM_ERR(86, "unknown -mat_type (registered: stencilcuda)");
+}
+PetscErrorCode DMCreateMatrix(DM dm, Mat *mat) { return mat_new(dm, mat); }
+PetscErrorCode MatDestroy(Mat *mat) {
+    if (mat && *mat) { free(*mat); *mat = NULL; }
+    return 0;
+}
+PetscErrorCode MatZeroEntries(Mat A) {
+    A->have_diag = A->have_c[0] = A->have_c[1] = A->have_c[2] = 0;
+    A->rows_set = 0; A->general = 0; A->assembled = 0;
+    return 0;
+}
+static void mat_reject(Mat A, const char *why) {
+    if (!A->general) { A->general = 1; snprintf(A->why, sizeof A->why, "%s", why); }
+}
+static int node_is_bdry(const DM dm, int i, int j, int k) {
+    if (i == 0 || i == dm->M[0] - 1) return 1;
+    if (dm->dim >= 2 && (j == 0 || j == dm->M[1] - 1)) return 1;
+    if (dm->dim >= 3 && (k == 0 || k == dm->M[2] - 1)) return 1;
+    return 0;
+}
+PetscErrorCode MatSetValuesStencil(Mat A, PetscInt m, const MatStencil idxm[], PetscInt n, const MatStencil idxn[],
+                                   const PetscScalar v[], InsertMode addv) {
+    if (addv != INSERT_VALUES) { mat_reject(A, "ADD_VALUES insertion"); return 0; }
+    const DM dm = A->dm;
+    const int dim = dm->dim;
+    for (int r = 0; r < m; r++) {
+        const int ri = idxm[r].i, rj = dim >= 2 ? idxm[r].j : 0, rk = dim >= 3 ? idxm[r].k : 0;
+        const int rb = node_is_bdry(dm, ri, rj, rk);
+        int nb_seen = 0, have_d = 0;
+        for (int c = 0; c < n; c++) {
+            const int ci = idxn[c].i, cj = dim >= 2 ? idxn[c].j : 0, ck = dim >= 3 ? idxn[c].k : 0;
+            const double val = v[r * n + c];
+            const int di = ci - ri, dj = cj - rj, dk = ck - rk;
+            if (!di && !dj && !dk) {
+                if (!A->have_diag) { A->diag = val; A->have_diag = 1; }
+                else if (val != A->diag) mat_reject(A, "diagonal is not constant");
+                have_d = 1;
+                continue;
+            }
+            const int dir = (di && !dj && !dk && (di == 1 || di == -1)) ? 0
+                          : (!di && dj && !dk && (dj == 1 || dj == -1)) ? 1
+                          : (!di && !dj && dk && (dk == 1 || dk == -1)) ? 2 : -1;
+            if (dir < 0) { mat_reject(A, "entry outside the 3/5/7-point star"); continue; }
+            if (rb) { mat_reject(A, "off-diagonal entry in a boundary row"); continue; }
+            if (node_is_bdry(dm, ci, cj, ck)) { mat_reject(A, "column to a boundary node was not dropped"); continue; }
+            if (!A->have_c[dir]) { A->c[dir] = -val; A->have_c[dir] = 1; }
+            else if (-val != A->c[dir]) mat_reject(A, "off-diagonal coefficient is not constant");
+            nb_seen++;
+        }
+        if (!have_d) mat_reject(A, "row without a diagonal entry");
+        if (!rb) {      /* an interior row must couple to every interior neighbour */
+            int expect = 0;
+            if (ri - 1 > 0) expect++;
+            if (ri + 1 < dm->M[0] - 1) expect++;
+            if (dim >= 2) { if (rj - 1 > 0) expect++; if (rj + 1 < dm->M[1] - 1) expect++; }
+            if (dim >= 3) { if (rk - 1 > 0) expect++; if (rk + 1 < dm->M[2] - 1) expect++; }
+            if (nb_seen != expect) mat_reject(A, "interior row does not couple to all interior neighbours");
+        }
+        A->rows_set++;
+    }
+    return 0;
+}
+PetscErrorCode MatAssemblyBegin(Mat A, MatAssemblyType t) { (void)A; (void)t; return 0; }
+PetscErrorCode MatAssemblyEnd(Mat A, MatAssemblyType t) {
+    if (t == MAT_FINAL_ASSEMBLY) A->assembled = 1;
+    return 0;
+}
+static PetscErrorCode mat_to_grid(Mat A, p4b_grid *g) {
+    memset(g, 0, sizeof *g);
+    g->dim = A->dm->dim;
+    g->mx = A->dm->M[0]; g->my = A->dm->M[1]; g->mz = A->dm->M[2];
+    g->Lx = A->dm->cmax[0] - A->dm->cmin[0];
+    g->Ly = A->dm->cmax[1] - A->dm->cmin[1];
+    g->Lz = A->dm->cmax[2] - A->dm->cmin[2];
+    g->cx = g->cy = g->cz = 1.0;        /* the real coefficients travel separately (p4b_mg_create_stencil) */
+    return 0;
+}
+PetscErrorCode MatMult(Mat A, Vec x, Vec y) {
+    /* matrix-free apply of the recognised stencil: y = A x */
+    if (A->general) SHIM_ERR(56, "MatMult: matrix is not a constant-coefficient stencil");
+    p4b_grid g;
+    p4b_mg_opts o;
+    p4b_mg *mg = NULL;
+    PetscCall(mat_to_grid(A, &g));
+    p4b_mg_default_opts(&o);
+    o.levels = 1;
+    double coef[4] = {A->diag, A->c[0], A->c[1], A->c[2]};
+    PetscCall(vec_to_dev(x));
+    PetscCall(vec_to_dev(y));
+    /* a one-level hierarchy gives access to the stencil kernel with explicit coefficients:
+     * residual with b = 0 and a sign flip would cost an extra pass, so use r = 0 - A x then scale */
+    P4B(p4b_mg_create_stencil(g_ctx, &g, &o, coef, 1, &mg));
+    P4B(p4b_mg_matmult(mg, x->d, y->d));
+    P4B(p4b_mg_destroy(mg));
+    y->valid = LOC_DEV;
+    return 0;
+}
+
+/* ---- SNES / KSP ---- */
+PetscErrorCode SNESCreate(MPI_Comm comm, SNES *snes) {
+    (void)comm;
+    register_all();
+    SNES s = (SNES)calloc(1, sizeof *s);
+    snprintf(s->type, 32, "%s", SNESNEWTONLS);
+    snprintf(s->ksp.type, 32, "%s", KSPGMRES);       /* PETSc defaults; fish.c overrides both (:231-233) */
+    s->ksp.rtol = 1e-5; s->ksp.abstol = 1e-50; s->ksp.max_it = 10000;
+    s->ksp.pc.type[0] = 0;
+    s->ksp.pc.levels = 0; s->ksp.pc.cycle = P4B_CYCLE_V; s->ksp.pc.smoother = P4B_SMOOTH_CHEBYSHEV;
+    s->ksp.pc.smooth_its = 2; s->ksp.pc.est_lo = 0.1; s->ksp.pc.est_hi = 1.1; s->ksp.pc.fuse = 1;
+    snprintf(s->ksp.pc.levels_pc, 32, "sor");        /* PETSc's default level smoother PC */
+    *snes = s;
+    return 0;
+}
+PetscErrorCode SNESSetDM(SNES snes, DM dm) { snes->dm = dm; dm->refct++; return 0; }
+PetscErrorCode SNESGetDM(SNES snes, DM *dm) { *dm = snes->dm; return 0; }
+PetscErrorCode SNESSetType(SNES snes, SNESType type) { snprintf(snes->type, 32, "%s", type); return 0; }
+PetscErrorCode SNESGetKSP(SNES snes, KSP *ksp) { *ksp = &snes->ksp; return 0; }
+PetscErrorCode KSPSetType(KSP ksp, KSPType type) { snprintf(ksp->type, 32, "%s", type); return 0; }
+PetscErrorCode KSPGetPC(KSP ksp, PC *pc) { *pc = &ksp->pc; return 0; }
+PetscErrorCode KSPSetTolerances(KSP ksp, PetscReal rtol, PetscReal abstol, PetscReal dtol, PetscInt maxits) {
+    (void)dtol;
+    if (rtol != PETSC_DEFAULT) ksp->rtol = rtol;
+    if (abstol != PETSC_DEFAULT) ksp->abstol = abstol;
+    if (maxits != PETSC_DEFAULT) ksp->max_it = maxits;
+    return 0;
+}
+PetscErrorCode KSPGetIterationNumber(KSP ksp, PetscInt *its) { *its = ksp->its; return 0; }
+PetscErrorCode SNESGetIterationNumber(SNES snes, PetscInt *it) { *it = snes->its; return 0; }
+PetscErrorCode SNESGetSolution(SNES snes, Vec *x) { *x = snes->sol; return 0; }
+
+PetscErrorCode SNESSetFromOptions(SNES snes) {
+    const char *v;
+    KSP ksp = &snes->ksp;
+    PC pc = &ksp->pc;
+    if ((v = opt_value("-snes_type"))) snprintf(snes->type, 32, "%s", v);
+    if ((v = opt_value("-ksp_type"))) snprintf(ksp->type, 32, "%s", v);
+    if ((v = opt_value("-ksp_rtol"))) ksp->rtol = strtod(v, NULL);
+    if ((v = opt_value("-ksp_atol"))) ksp->abstol = strtod(v, NULL);
+    if ((v = opt_value("-ksp_max_it"))) ksp->max_it = atoi(v);
+    if ((v = opt_value("-pc_type"))) PetscCall(PCSetType(pc, v));
+    if ((v = opt_value("-pc_mg_levels"))) pc->levels = atoi(v);
+    if ((v = opt_value("-pc_mg_cycle_type"))) pc->cycle = (v[0] == 'w' || v[0] == 'W') ? P4B_CYCLE_W : P4B_CYCLE_V;
+    if ((v = opt_value("-mg_levels_ksp_type"))) {
+        if (!strcmp(v, "chebyshev")) pc->smoother = P4B_SMOOTH_CHEBYSHEV;
+        else if (!strcmp(v, "richardson")) pc->smoother = P4B_SMOOTH_RICHARDSON;
+        else SHIM_ERR(86, "-mg_levels_ksp_type must be chebyshev or richardson on the device path");
+    }
+    if ((v = opt_value("-mg_levels_ksp_max_it"))) pc->smooth_its = atoi(v);
+    if ((v = opt_value("-mg_levels_pc_type"))) snprintf(pc->levels_pc, 32, "%s", v);
+    if ((v = opt_value("-mg_levels_ksp_chebyshev_eigenvalues"))) {
+        if (sscanf(v, "%lf,%lf", &pc->emin, &pc->emax) != 2) SHIM_ERR(62, "need emin,emax");
+        pc->have_eig = 1;
+    }
+    if ((v = opt_value("-mg_levels_ksp_chebyshev_esteig"))) {
+        double a, b, c, d;
+        if (sscanf(v, "%lf,%lf,%lf,%lf", &a, &b, &c, &d) == 4) { pc->est_lo = b; pc->est_hi = d; }
+    }
+    if (opt_has("-p4b_no_fuse")) pc->fuse = 0;
+    ksp->converged_reason_flag = opt_has("-ksp_converged_reason");
+    ksp->monitor_flag = opt_has("-ksp_monitor");
+    snes->monitor_short = opt_has("-snes_monitor_short");
+    snes->monitor = opt_has("-snes_monitor");
+    snes->converged_reason_flag = opt_has("-snes_converged_reason");
+    if (opt_has("-snes_grid_sequence")) SHIM_ERR(56, "-snes_grid_sequence is not provided by the shim yet");
+    if (opt_has("-snes_fd_color") || opt_has("-snes_mf_operator") || opt_has("-snes_mf"))
+        SHIM_ERR(56, "-snes_fd_color / -snes_mf* are not provided by the shim (analytic Jacobian callback only)");
+    if (opt_has("-pc_mg_galerkin")) SHIM_ERR(56, "-pc_mg_galerkin is not provided (levels are rediscretised, fish.c:7)");
+    return 0;
+}
+
+static void print_snes_norm(SNES snes, int it, double fnorm) {
+    if (snes->monitor_short) {
+        if (fnorm < 1e-11) printf("  %d SNES Function norm < 1.e-11\n", it);
+        else printf("  %d SNES Function norm %g\n", it, fnorm);
+    } else if (snes->monitor) {
+        printf("  %d SNES Function norm %14.12e\n", it, fnorm);
+    }
+}
+
+/* call the user's FormFunctionLocal on the host exactly as PETSc does (ghosted local array == the global
+ * array for one rank on a non-periodic DMDA) */
+static PetscErrorCode compute_function(SNES snes, Vec u, Vec F) {
+    DM dm = snes->dm;
+    DMDALocalInfo info;
+    void *au, *aF;
+    if (!dm->func) SHIM_ERR(73, "no residual callback: call DMDASNESSetFunctionLocal()");
+    const double t0 = wall();
+    PetscCall(DMDAGetLocalInfo(dm, &info));
+    PetscCall(DMDAVecGetArrayRead(dm, u, &au));
+    PetscCall(DMDAVecGetArray(dm, F, &aF));
+    PetscErrorCode rc = dm->func(&info, au, aF, dm->funcctx);
+    PetscCall(DMDAVecRestoreArrayRead(dm, u, &au));
+    PetscCall(DMDAVecRestoreArray(dm, F, &aF));
+    g_t_func += wall() - t0;
+    return rc;
+}
+
+static const char *reason_name(int r) {
+    switch (r) {
+        case P4B_CONVERGED_RTOL: return "CONVERGED_RTOL";
+        case P4B_CONVERGED_ATOL: return "CONVERGED_ATOL";
+        case P4B_DIVERGED_ITS: return "DIVERGED_ITS";
+        default: return "DIVERGED_NANORINF";
+    }
+}
+
+PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
+    if (b) SHIM_ERR(56, "SNESSolve with a right-hand side is not provided");
+    if (strcmp(snes->type, SNESKSPONLY))
+        SHIM_ERR(56, "only -snes_type ksponly is provided by the shim so far (fish.c is linear, fish.c:230-231)");
+    if (strcmp(snes->ksp.type, KSPCG)) SHIM_ERR(56, "only -ksp_type cg is provided on the device path");
+    KSP ksp = &snes->ksp;
+    PC pc = &ksp->pc;
+    if (!pc->type[0])
+        SHIM_ERR(56, "PETSc's default PC (ILU(0) on one rank) is sequential and not provided on the device: "
+                     "pass -pc_type mg (or jacobi, none)");
+    if (!strcmp(pc->type, PCMG) && strcmp(pc->levels_pc, "jacobi"))
+        SHIM_ERR(56, "PCMG's default level smoother PC (SOR) is sequential and not provided on the device: "
+                     "pass -mg_levels_pc_type jacobi");
+    DM dm = snes->dm;
+    if (!dm || !dm->jac) SHIM_ERR(73, "no Jacobian callback: call DMDASNESSetJacobianLocal()");
+    PetscCall(ensure_ctx());
+    const double t_snes0 = wall();
+
+    /* the solution vector is owned by the SNES (fish.c:248) */
+    if (!snes->sol) PetscCall(vec_new(dm, &snes->sol));
+    PetscCall(vec_to_host(x));
+    memcpy(snes->sol->h, x->h, x->n * sizeof(double));
+    snes->sol->valid = LOC_HOST;
+    Vec u = snes->sol, F = NULL, Y = NULL;
+    PetscCall(vec_new(dm, &F));
+    PetscCall(vec_new(dm, &Y));
+
+    /* F0 = F(u0) */
+    PetscCall(compute_function(snes, u, F));
+    double fnorm;
+    PetscCall(VecNorm(F, NORM_2, &fnorm));
+    print_snes_norm(snes, 0, fnorm);
+
+    /* Jacobian on every level by rediscretisation: the user's callback on the coarsened DMDAs (PCSetUp_MG) */
+    const double t_jac0 = wall();
+    int nlev = 1;
+    int Ml[P4B_MAX_LEVELS][3];
+    memcpy(Ml[0], dm->M, sizeof(int) * 3);
+    if (!strcmp(pc->type, PCMG)) {
+        for (;;) {
+            if (pc->levels > 0 && nlev >= pc->levels) break;
+            int ok = 1;
+            for (int d = 0; d < dm->dim; d++)
+                if (Ml[nlev - 1][d] <= 3 || (Ml[nlev - 1][d] - 1) % 2) ok = 0;
+            if (!ok || nlev >= P4B_MAX_LEVELS) break;
+            for (int d = 0; d < 3; d++) Ml[nlev][d] = d < dm->dim ? (Ml[nlev - 1][d] - 1) / 2 + 1 : 1;
+            nlev++;
+        }
+        if (pc->levels > 0 && nlev < pc->levels) SHIM_ERR(62, "cannot coarsen to the requested -pc_mg_levels");
+    }
+    double coef[P4B_MAX_LEVELS * 4];
+    for (int l = 0; l < nlev; l++) {
+        struct _p_DM cd = *dm;                    /* coarsened DMDA: same box, fewer nodes */
+        memcpy(cd.M, Ml[l], sizeof(int) * 3);
+        memset(cd.pool, 0, sizeof cd.pool);
+        DMDALocalInfo info;
+        PetscCall(DMDAGetLocalInfo(&cd, &info));
+        Mat J;
+        PetscCall(mat_new(&cd, &J));
+        Vec ul = NULL;
+        void *au = NULL;
+        if (l == 0) ul = u;
+        else PetscCall(vec_new(&cd, &ul));        /* PETSc hands the callback a state on that level */
+        PetscCall(DMDAVecGetArrayRead(&cd, ul, &au));
+        PetscErrorCode rc = dm->jac(&info, au, J, J, dm->jacctx);
+        PetscCall(DMDAVecRestoreArrayRead(&cd, ul, &au));
+        if (l) vec_free(ul);
+        if (rc) return rc;
+        if (J->general || !J->have_diag || J->rows_set != (long long)da_n(&cd)) {
+            char msg[640];
+            snprintf(msg, sizeof msg,
+                     "Jacobian on level %d is not the constant-coefficient Dirichlet stencil the device Mat type "
+                     "\"stencilcuda\" represents (%s; %lld of %zu rows set); the assembled AIJ device path is not built yet",
+                     l, J->general ? J->why : "incomplete", J->rows_set, da_n(&cd));
+            MatDestroy(&J);
+            SHIM_ERR(56, msg);
+        }
+        coef[4 * l + 0] = J->diag;
+        coef[4 * l + 1] = J->have_c[0] ? J->c[0] : 0.0;
+        coef[4 * l + 2] = J->have_c[1] ? J->c[1] : 0.0;
+        coef[4 * l + 3] = J->have_c[2] ? J->c[2] : 0.0;
+        /* grids with a single interior node per direction never show an off-diagonal: harmless, it is unused */
+        MatDestroy(&J);
+    }
+    g_t_jac += wall() - t_jac0;
+
+    /* KSPSolve: J y = F0 on the device */
+    p4b_grid g;
+    {
+        struct _p_Mat tmp;
+        memset(&tmp, 0, sizeof tmp);
+        tmp.dm = dm;
+        PetscCall(mat_to_grid(&tmp, &g));
+    }
+    p4b_mg_opts o;
+    p4b_mg_default_opts(&o);
+    o.levels = nlev;
+    o.cycle = pc->cycle; o.smoother = pc->smoother; o.smooth_its = pc->smooth_its;
+    if (pc->have_eig) { o.emin = pc->emin; o.emax = pc->emax; }
+    o.est_lo = pc->est_lo; o.est_hi = pc->est_hi; o.fuse = pc->fuse;
+    p4b_mg *mg = NULL;
+    P4B(p4b_mg_create_stencil(g_ctx, &g, &o, coef, nlev, &mg));
+    const int pct = !strcmp(pc->type, PCMG) ? P4B_PC_MG : (!strcmp(pc->type, PCJACOBI) ? P4B_PC_JACOBI : P4B_PC_NONE);
+    PetscCall(vec_to_dev(F));
+    PetscCall(vec_to_dev(Y));
+    p4b_ksp_result res;
+    const double t_ksp0 = wall();
+    P4B(p4b_cg_solve(mg, pct, F->d, Y->d, ksp->rtol, ksp->abstol, ksp->max_it, &res));
+    g_t_ksp += wall() - t_ksp0;
+    g_t_ksp_dev_ms += res.solve_ms;
+    Y->valid = LOC_DEV;
+    ksp->its = res.its;
+    ksp->reason = res.reason;
+    if (ksp->monitor_flag)
+        for (int i = 0; i < res.nhist; i++) printf("    %d KSP Residual norm %14.12e\n", i, res.hist[i]);
+    if (ksp->converged_reason_flag) {
+        if (res.reason > 0) printf("    Linear solve converged due to %s iterations %d\n", reason_name(res.reason), res.its);
+        else printf("    Linear solve did not converge due to %s iterations %d\n", reason_name(res.reason), res.its);
+    }
+    P4B(p4b_mg_destroy(mg));
+
+    /* u = u0 - y ; then the post-solve function norm PETSc's KSPONLY monitor prints */
+    PetscCall(VecAXPY(u, -1.0, Y));
+    snes->its = 1;
+    if (snes->monitor_short || snes->monitor) {
+        PetscCall(compute_function(snes, u, F));
+        PetscCall(VecNorm(F, NORM_2, &fnorm));
+        print_snes_norm(snes, 1, fnorm);
+    }
+    if (snes->converged_reason_flag)
+        printf("Nonlinear solve converged due to CONVERGED_ITS iterations 1\n");
+    vec_free(F);
+    vec_free(Y);
+    /* PETSc's SNESSolve leaves the solution in x as well */
+    PetscCall(vec_to_host(u));
+    memcpy(x->h, u->h, x->n * sizeof(double));
+    x->valid = LOC_HOST;
+    g_t_snes += wall() - t_snes0;
+    fflush(stdout);
+    return 0;
+}
+
+PetscErrorCode SNESDestroy(SNES *snes) {
+    if (!snes || !*snes) return 0;
+    vec_free((*snes)->sol);
+    if ((*snes)->dm) { DM d = (*snes)->dm; DMDestroy(&d); }
+    free(*snes);
+    *snes = NULL;
+    return 0;
+}
