@@ -23,7 +23,9 @@ golden outputs ``c/ch6/output/fish.test1`` (complete), ``fish.test3`` (complete)
 ``fish.test4`` (complete, 2-rank block SSOR + W cycle), ``fish.test5,6,8`` (CG + the default
 ILU(0) PC: iteration count of test6 and all error norms) and the error norms of
 ``fish.test2,7``.  (``fish.test7``'s iteration count needs -pc_mg_galerkin, which is
-off the north-star path and is NOT reproduced: parity unpinned for Galerkin.)  No reference golden uses Chebyshev+Jacobi or a grid larger
+off the north-star path and is NOT reproduced: parity unpinned for Galerkin.)  The discretisation part is
+additionally checked against the reference's OWN compiled code (oracle/_ref/libfishref.so = c/ch6/poissonfunctions.c +
+c/ch6/fish.c built unchanged by oracle/refstub/Makefile; tests/test_oracle_ref.py).  No reference golden uses Chebyshev+Jacobi or a grid larger
 than 17^2 / 9^3, so at BASELINE sizes parity is pinned only transitively
 (oracle validated on goldens -> oracle run at size).
 """
