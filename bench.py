@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fuse", action="store_true")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="multi-GPU transport (A/B)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -152,6 +153,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L.tune("comm_peer", 1 if args.comm == "peer" else 0)
     ctx = Context(local_rank, distributed=world > 1)
     lib = ctx.lib
 
@@ -282,7 +284,7 @@ def main():
         "config": {"workload": "fish.c 3-D Poisson manuexp %d^3 (%d unknowns), CG + V-cycle GMG, Chebyshev(2)/Jacobi, "
                                "rtol 1e-10" % (m, ndof),
                    "options": OPTIONS.format(refine=refine, levels=levels), "levels": mg.nlevels,
-                   "parallelism": "z-slabs x%d" % world, "l2": "inputs (%.2f GB per vector) exceed the 126 MB L2"
+                   "parallelism": "z-slabs x%d" % world, "transport": (args.comm if world > 1 else None), "l2": "inputs (%.2f GB per vector) exceed the 126 MB L2"
                    % (8 * ndof / 1e9), "fused": not args.no_fuse},
         "ksp_its": res.its, "ksp_reason": L.REASONS.get(res.reason), "rnorm0": res.rnorm0, "rnorm": res.rnorm,
         "errinf": errinf, "err2h": err2h,

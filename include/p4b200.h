@@ -103,7 +103,9 @@ const char *p4b_last_error(void);
 int p4b_device_count(int *n);
 /* kernel-selection knobs for tests and A/B measurements (never changes results beyond rounding):
  * "march_enabled" 0|1, "march_min_plane" nodes, "march_P", "march_NT", "march_NS";
- * "rep_points": multigrid levels with at most this many nodes are replicated on every rank (default 70^3) */
+ * "rep_points": multigrid levels with at most this many nodes are replicated on every rank (default 70^3);
+ * "comm_peer" 0|1 (set before p4b_comm_init): 1 = ghost planes / allreduce / gather as peer-memory kernels
+ * over CUDA IPC + NVLink (default), 0 = NCCL send/recv/allreduce/broadcast */
 int p4b_tune(const char *key, long value);
 
 /* ---- context ---- */

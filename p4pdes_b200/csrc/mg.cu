@@ -16,6 +16,9 @@
 
 #include <vector>
 
+#include <array>
+
+#include "comm.h"
 #include "kernels.h"
 
 namespace p4b {
@@ -48,6 +51,7 @@ struct Nccl {
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -73,6 +77,7 @@ static int nccl_load() {
     LD(CommDestroy, "ncclCommDestroy");
     LD(AllReduce, "ncclAllReduce");
     LD(Broadcast, "ncclBroadcast");
+    LD(AllGather, "ncclAllGather");
     LD(Send, "ncclSend");
     LD(Recv, "ncclRecv");
     LD(GroupStart, "ncclGroupStart");
@@ -108,13 +113,68 @@ struct p4b_ctx {
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // peer-memory path (comm.cu): mailboxes of all ranks mapped through CUDA IPC
+    bool peer = false;
+    Mailbox *mbox = nullptr;
+    LocalSync *sync = nullptr;
+    PeerTable peers;
 };
 
-static int ctx_allreduce(p4b_ctx *c, double *d, int count) {
-    if (c->nranks == 1) return 0;
-    P4B_NCCL(g_nccl.AllReduce(d, d, (size_t)count, ncclFloat64, ncclSum, c->comm, c->stream));
+static long long g_comm_peer = 1;      // p4b_tune("comm_peer", 0) keeps everything on NCCL
+
+// all-gather one CUDA IPC handle per rank (over NCCL, as raw bytes)
+static int ipc_allgather(p4b_ctx *c, const cudaIpcMemHandle_t &mine, std::vector<cudaIpcMemHandle_t> *all) {
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    char *d = nullptr;
+    P4B_CUDA(cudaMalloc(&d, hb * c->nranks));
+    P4B_CUDA(cudaMemcpy(d + hb * c->rank, &mine, hb, cudaMemcpyHostToDevice));
+    P4B_NCCL(g_nccl.AllGather(d + hb * c->rank, d, hb, ncclChar, c->comm, c->stream));
+    P4B_CUDA(cudaStreamSynchronize(c->stream));
+    all->resize(c->nranks);
+    P4B_CUDA(cudaMemcpy(all->data(), d, hb * c->nranks, cudaMemcpyDeviceToHost));
+    P4B_CUDA(cudaFree(d));
     return 0;
 }
+
+static int nccl_barrier(p4b_ctx *c) {
+    if (c->nranks == 1) return 0;
+    P4B_NCCL(g_nccl.AllReduce(c->d_scal + 15, c->d_scal + 15, 1, ncclFloat64, ncclSum, c->comm, c->stream));
+    P4B_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int peer_setup(p4b_ctx *c) {
+    if (c->nranks == 1 || c->nranks > MAX_RANKS || !g_comm_peer) return 0;
+    P4B_CUDA(cudaMalloc(&c->mbox, sizeof(Mailbox)));
+    P4B_CUDA(cudaMemset(c->mbox, 0, sizeof(Mailbox)));
+    P4B_CUDA(cudaMalloc(&c->sync, sizeof(LocalSync)));
+    P4B_CUDA(cudaMemset(c->sync, 0, sizeof(LocalSync)));
+    cudaIpcMemHandle_t mine;
+    P4B_CUDA(cudaIpcGetMemHandle(&mine, c->mbox));
+    std::vector<cudaIpcMemHandle_t> all;
+    P4B_CHECK(ipc_allgather(c, mine, &all));
+    c->peers.rank = c->rank;
+    c->peers.nranks = c->nranks;
+    for (int r = 0; r < c->nranks; r++) {
+        if (r == c->rank) { c->peers.mbox[r] = c->mbox; continue; }
+        void *p = nullptr;
+        P4B_CUDA(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
+        c->peers.mbox[r] = (Mailbox *)p;
+    }
+    P4B_CHECK(nccl_barrier(c));
+    c->peer = true;
+    return 0;
+}
+
+static int ctx_allreduce_op(p4b_ctx *c, double *d, int count, int op_max) {
+    if (c->nranks == 1) return 0;
+    if (c->peer) return launch_allreduce(c->stream, d, count, op_max, c->peers, c->sync);
+    P4B_NCCL(g_nccl.AllReduce(d, d, (size_t)count, ncclFloat64, op_max ? ncclMax : ncclSum, c->comm, c->stream));
+    return 0;
+}
+
+static int ctx_allreduce_op(p4b_ctx *c, double *d, int count, int op_max);
+static int ctx_allreduce(p4b_ctx *c, double *d, int count) { return ctx_allreduce_op(c, d, count, 0); }
 
 // ------------------------------------------------------------------------------------------------
 // grid -> level descriptor
@@ -196,6 +256,10 @@ struct Level {
     double scale = 0;            // 2/(emax+emin)
     double *x = nullptr, *b = nullptr, *t = nullptr;   // first owned element of each ghosted vector
     std::vector<int> zs_all, zm_all;                   // ownership of every rank (2K rule) on this level
+    // arena offsets (in doubles) of the first owned element of this level's buffers: here and on the slab neighbours
+    std::array<size_t, 7> off_me{}, off_prev{}, off_next{};
+    int nslots = 3;
+    int zm_prev = 0, zm_next = 0;
 };
 
 struct Prof {
@@ -218,6 +282,10 @@ struct p4b_mg {
     int n0 = 0;
     double *p = nullptr, *w = nullptr, *fbuf = nullptr, *gbuf = nullptr;   // CG vectors / fish scratch
     Prof prof;
+    // peer-memory path: arenas of all ranks mapped through CUDA IPC
+    bool peer = false;
+    GatherTable peer_arena;
+    const double *last_halo = nullptr;
     bool dot2_fused = false;     // set by smooth() when the last smoother kernel also produced (z,z), (z,r)
     double *dot2_target = nullptr;
     cudaGraphExec_t coarse_graph = nullptr;
@@ -295,6 +363,22 @@ static int halo(p4b_mg *m, int l, double *v) {
     if (c->nranks == 1 || L.replicated) return 0;
     const size_t plane = (size_t)L.d.plane();
     const bool lo = L.d.zs > 0, hi = L.d.zs + L.d.zm < L.d.nz;
+    if (m->peer) {
+        // push my boundary planes into the neighbours' ghost planes (comm.cu)
+        int slot = -1;
+        const size_t voff = (size_t)(v - m->arena);
+        for (int q = 0; q < L.nslots; q++)
+            if (L.off_me[q] == voff) slot = q;
+        if (slot < 0) return fail(64, "halo: vector is not one of this level's arena buffers");
+        if (v == m->last_halo) P4B_CHECK(launch_barrier(c->stream, 0, c->peers, c->sync));   // see comm.cu "Hazards"
+        m->last_halo = v;
+        double *lo_dst = lo ? m->peer_arena.base[c->rank - 1] + L.off_prev[slot] + (size_t)L.zm_prev * plane : nullptr;
+        double *hi_dst = hi ? m->peer_arena.base[c->rank + 1] + L.off_next[slot] - plane : nullptr;
+        unsigned long long *fp = lo ? &c->peers.mbox[c->rank - 1]->halo_flag[1] : nullptr;
+        unsigned long long *fn = hi ? &c->peers.mbox[c->rank + 1]->halo_flag[0] : nullptr;
+        return launch_halo_push(c->stream, v, lo_dst, v + (size_t)(L.d.zm - 1) * plane, hi_dst, (long long)plane, fp, fn,
+                                c->mbox->halo_flag, c->sync);
+    }
     P4B_NCCL(g_nccl.GroupStart());
     if (lo) {
         P4B_NCCL(g_nccl.Send(v, plane, ncclFloat64, c->rank - 1, c->comm, c->stream));
@@ -308,12 +392,20 @@ static int halo(p4b_mg *m, int l, double *v) {
     return 0;
 }
 
-// make a replicated level's vector complete on every rank: each rank broadcasts the planes it owns
+// make a replicated level's vector complete on every rank: each rank contributes the planes it owns
 static int gather_replicated(p4b_mg *m, int l, double *v) {
     p4b_ctx *c = m->ctx;
     Level &L = m->lev[l];
     if (c->nranks == 1) return 0;
     const size_t plane = (size_t)L.d.plane();
+    if (m->peer) {
+        // replicated levels are carved first and have the same size everywhere: same arena offset on every rank
+        const long long off = (long long)(v - m->arena) + (long long)L.own.zs * (long long)plane;
+        P4B_CHECK(launch_barrier(c->stream, 1, c->peers, c->sync));     // everyone is done reading the old copy
+        P4B_CHECK(launch_gather_push(c->stream, v + (size_t)L.own.zs * plane, (long long)L.own.zm * (long long)plane, off,
+                                     m->peer_arena, c->rank, c->nranks));
+        return launch_barrier(c->stream, 1, c->peers, c->sync);          // every contribution has landed
+    }
     P4B_NCCL(g_nccl.GroupStart());
     for (int r = 0; r < c->nranks; r++) {
         if (L.zm_all[r] <= 0) continue;
@@ -593,6 +685,7 @@ int p4b_tune(const char *key, long value) {
     if (!key) return fail(62, "null tuning key");
     if (tune_march(key, value) == 0) return 0;
     if (std::string(key) == "rep_points") { g_rep_points = value; return 0; }
+    if (std::string(key) == "comm_peer") { g_comm_peer = value; return 0; }
     return fail(62, "unknown tuning key %s", key);
 }
 
@@ -628,6 +721,14 @@ int p4b_ctx_destroy(p4b_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->peer) {
+        nccl_barrier(c);
+        for (int r = 0; r < c->nranks; r++)
+            if (r != c->rank && c->peers.mbox[r]) cudaIpcCloseMemHandle(c->peers.mbox[r]);
+        nccl_barrier(c);
+        cudaFree(c->mbox);
+        cudaFree(c->sync);
+    }
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     cudaFree(c->red.partials);
     cudaFree(c->red.ticket);
@@ -663,7 +764,7 @@ int p4b_comm_init(p4b_ctx *c, const void *id128, int rank, int nranks) {
     memcpy(&id, id128, sizeof id);
     P4B_CUDA(cudaSetDevice(c->device));
     P4B_NCCL(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
-    return 0;
+    return peer_setup(c);
 }
 
 int p4b_slab_range(int m, int nranks, int rank, int *start, int *count) {
@@ -819,8 +920,7 @@ int p4b_vec_norm2(p4b_ctx *c, size_t n, const double *x, double *res) {
 }
 int p4b_vec_norminf(p4b_ctx *c, size_t n, const double *x, double *res) {
     P4B_CHECK(launch_absmax(c->stream, (long long)n, x, c->d_scal + 8, c->red));
-    if (c->nranks > 1)
-        P4B_NCCL(g_nccl.AllReduce(c->d_scal + 8, c->d_scal + 8, 1, ncclFloat64, ncclMax, c->comm, c->stream));
+    P4B_CHECK(ctx_allreduce_op(c, c->d_scal + 8, 1, 1));
     return fetch_scal(c, c->d_scal + 8, 1, res);
 }
 int p4b_vec_axpy(p4b_ctx *c, size_t n, double a, const double *x, double *y) {
@@ -929,13 +1029,30 @@ static int mg_create_impl(p4b_ctx *c, const p4b_grid *g, const p4b_mg_opts *oin,
         L.replicated = (P > 1 && l <= plan.lrep);
         if (P > 1 && !L.replicated) L.d = L.own;
     }
-    // arena: ghosted vectors x, b, t per level (+ p, w and two scratch vectors on the finest)
-    auto vec_doubles = [](const LevelDesc &d) {
-        size_t n = (size_t)d.plane() * (d.zm + 2) + 8;
-        return (n + 31) & ~(size_t)31;
+    // arena: ghosted vectors x, b, t per level (+ p, w and two scratch vectors on the finest).  The layout is a
+    // pure function of the plan, so a rank can compute where its neighbours keep the same buffers.
+    auto layout = [&](int rank, std::vector<std::array<size_t, 7>> *offs) {
+        size_t off = 0;
+        offs->assign(nl, std::array<size_t, 7>{});
+        for (int l = 0; l < nl; l++) {
+            const Level &L = m->lev[l];
+            const size_t plane = (size_t)L.d.plane();
+            const int zm = (P > 1 && !L.replicated) ? L.zm_all[rank] : L.d.nz;
+            size_t n = plane * (size_t)(zm + 2) + 8;
+            n = (n + 31) & ~(size_t)31;
+            const size_t lead = 4 + (plane & 1);      // owned start 16-byte aligned (arena base is 256-byte aligned)
+            const int ns = (l == nl - 1) ? 7 : 3;
+            for (int q = 0; q < ns; q++) {
+                (*offs)[l][q] = off + lead + plane;
+                off += n;
+            }
+        }
+        return off;
     };
-    size_t total = 0;
-    for (int l = 0; l < nl; l++) total += vec_doubles(m->lev[l].d) * (l == nl - 1 ? 7 : 3);
+    std::vector<std::array<size_t, 7>> offs_me, offs_prev, offs_next;
+    const size_t total = layout(R, &offs_me);
+    if (P > 1 && R > 0) layout(R - 1, &offs_prev);
+    if (P > 1 && R < P - 1) layout(R + 1, &offs_next);
     m->arena_doubles = total;
     cudaError_t e = cudaMalloc(&m->arena, sizeof(double) * total);
     if (e != cudaSuccess) {
@@ -943,29 +1060,40 @@ static int mg_create_impl(p4b_ctx *c, const p4b_grid *g, const p4b_mg_opts *oin,
         return fail(71, "cudaMalloc of %.2f GB for the level hierarchy failed: %s", total * 8e-9, cudaGetErrorString(e));
     }
     P4B_CUDA(cudaMemsetAsync(m->arena, 0, sizeof(double) * total, c->stream));
-    size_t off = 0;
-    auto carve = [&](const LevelDesc &d) {
-        // owned start is 16-byte aligned: base is 256-byte aligned, skip (4 or 5) + plane doubles
-        const size_t plane = (size_t)d.plane();
-        const size_t lead = 4 + (plane & 1);
-        double *ptr = m->arena + off + lead + plane;
-        off += vec_doubles(d);
-        return ptr;
-    };
     for (int l = 0; l < nl; l++) {
         Level &L = m->lev[l];
-        L.x = carve(L.d);
-        L.b = carve(L.d);
-        L.t = carve(L.d);
+        L.nslots = (l == nl - 1) ? 7 : 3;
+        L.off_me = offs_me[l];
+        if (P > 1 && R > 0) { L.off_prev = offs_prev[l]; L.zm_prev = L.zm_all[R - 1]; }
+        if (P > 1 && R < P - 1) { L.off_next = offs_next[l]; L.zm_next = L.zm_all[R + 1]; }
+        L.x = m->arena + L.off_me[0];
+        L.b = m->arena + L.off_me[1];
+        L.t = m->arena + L.off_me[2];
         if (l == nl - 1) {
-            m->p = carve(L.d);
-            m->w = carve(L.d);
-            m->fbuf = carve(L.d);
-            m->gbuf = carve(L.d);
+            m->p = m->arena + L.off_me[3];
+            m->w = m->arena + L.off_me[4];
+            m->fbuf = m->arena + L.off_me[5];
+            m->gbuf = m->arena + L.off_me[6];
         }
     }
+    if (c->peer) {
+        // map every rank's arena (neighbours for ghost planes, everyone for the replicated-level gather)
+        P4B_CUDA(cudaStreamSynchronize(c->stream));
+        cudaIpcMemHandle_t mine;
+        P4B_CUDA(cudaIpcGetMemHandle(&mine, m->arena));
+        std::vector<cudaIpcMemHandle_t> all;
+        P4B_CHECK(ipc_allgather(c, mine, &all));
+        for (int r = 0; r < P; r++) {
+            if (r == R) { m->peer_arena.base[r] = m->arena; continue; }
+            void *pp = nullptr;
+            P4B_CUDA(cudaIpcOpenMemHandle(&pp, all[r], cudaIpcMemLazyEnablePeerAccess));
+            m->peer_arena.base[r] = (double *)pp;
+        }
+        P4B_CHECK(nccl_barrier(c));
+        m->peer = true;
+    }
     int rc = build_coarse_inverse(m);
-    if (rc) { cudaFree(m->arena); delete m; return rc; }
+    if (rc) return rc;
     memset(m->prof.stat, 0, sizeof m->prof.stat);
     P4B_CUDA(cudaStreamSynchronize(c->stream));
     *out = m;
@@ -999,6 +1127,12 @@ int p4b_mg_destroy(p4b_mg *m) {
     cudaStreamSynchronize(m->ctx->stream);
     for (auto e : m->prof.pool) cudaEventDestroy(e);
     if (m->coarse_graph) cudaGraphExecDestroy(m->coarse_graph);
+    if (m->peer) {      // collective: nobody may still be storing into an arena that is about to be freed
+        nccl_barrier(m->ctx);
+        for (int r = 0; r < m->ctx->nranks; r++)
+            if (r != m->ctx->rank && m->peer_arena.base[r]) cudaIpcCloseMemHandle(m->peer_arena.base[r]);
+        nccl_barrier(m->ctx);
+    }
     cudaFree(m->arena);
     cudaFree(m->Ainv);
     delete m;

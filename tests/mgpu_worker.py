@@ -27,12 +27,14 @@ def main():
     ap.add_argument("--cycle", default="v")
     ap.add_argument("--march-min-plane", type=int, default=16384)
     ap.add_argument("--rep-points", type=int, default=0)
+    ap.add_argument("--comm-peer", type=int, default=1)
     ap.add_argument("--no-oracle", action="store_true")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L.tune("comm_peer", a.comm_peer)
     ctx = Context(local, distributed=True)
     L.tune("march_min_plane", a.march_min_plane)
     if a.rep_points:

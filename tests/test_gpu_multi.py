@@ -33,6 +33,8 @@ def ngpu():
     ("--refine", 6, "--rtol", 1e-10, "--levels", 5),                    # 129^3 distributed, coarse 9^3
     ("--refine", 6, "--rtol", 1e-10, "--levels", 5, "--march-min-plane", 1),   # plane-marching kernel on slabs
     ("--refine", 5, "--rtol", 1e-8, "--cycle", "w"),
+    ("--refine", 6, "--rtol", 1e-10, "--levels", 5, "--comm-peer", 0),          # NCCL send/recv/allreduce path
+    ("--refine", 5, "--rtol", 1e-8, "--cycle", "w", "--rep-points", 1, "--comm-peer", 0),
     ("--refine", 5, "--rtol", 1e-10, "--rep-points", 1, "--march-min-plane", 1),   # every level that can be is distributed
 ])
 def test_slab_solve_matches_oracle(nproc, args):
