@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fuse", action="store_true")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="multi-GPU transport (A/B)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the coarse levels kernel by kernel (A/B)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -153,6 +154,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # everything runs on one explicit (capturable) stream: torch ops, the library's kernels, its CUDA graph
+    side = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(side)
     L.tune("comm_peer", 1 if args.comm == "peer" else 0)
     ctx = Context(local_rank, distributed=world > 1)
     lib = ctx.lib
@@ -161,7 +165,7 @@ def main():
     levels = args.levels or max(2, refine - 1)
     g = L.refined_grid(3, refine)
     ndof = g.n
-    mg = Multigrid(ctx, g, mg_options(levels=levels, fuse=not args.no_fuse))
+    mg = Multigrid(ctx, g, mg_options(levels=levels, fuse=not args.no_fuse, use_graph=not args.no_graph))
     nloc = mg.nlocal
     b = ctx.empty(nloc)
     x = ctx.empty(nloc)
@@ -285,7 +289,7 @@ def main():
                                "rtol 1e-10" % (m, ndof),
                    "options": OPTIONS.format(refine=refine, levels=levels), "levels": mg.nlevels,
                    "parallelism": "z-slabs x%d" % world, "transport": (args.comm if world > 1 else None), "l2": "inputs (%.2f GB per vector) exceed the 126 MB L2"
-                   % (8 * ndof / 1e9), "fused": not args.no_fuse},
+                   % (8 * ndof / 1e9), "fused": not args.no_fuse, "cuda_graph_coarse_levels": not args.no_graph},
         "ksp_its": res.its, "ksp_reason": L.REASONS.get(res.reason), "rnorm0": res.rnorm0, "rnorm": res.rnorm,
         "errinf": errinf, "err2h": err2h,
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": table,

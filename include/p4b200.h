@@ -63,7 +63,9 @@ typedef struct {
     double emin, emax;   /* -mg_levels_ksp_chebyshev_eigenvalues; emax <= 0 => estimate */
     double est_lo, est_hi; /* esteig transform applied to the analytic lambda_max (0.1, 1.1) */
     int fuse;            /* 1 = fused kernels (default); 0 = one kernel per PETSc operation */
-    int use_graph;       /* 1 = replay the coarse part of the cycle as a CUDA graph */
+    int use_graph;       /* 1 (default) = replay everything below the finest level as one CUDA graph; needs a
+                            non-default stream, an even smooth_its and (multi-GPU) the peer-memory transport,
+                            otherwise the same kernels are launched one by one */
 } p4b_mg_opts;
 
 typedef struct {

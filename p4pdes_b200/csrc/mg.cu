@@ -288,8 +288,10 @@ struct p4b_mg {
     const double *last_halo = nullptr;
     bool dot2_fused = false;     // set by smooth() when the last smoother kernel also produced (z,z), (z,r)
     double *dot2_target = nullptr;
-    cudaGraphExec_t coarse_graph = nullptr;
-    int graph_level = -1;
+    cudaGraphExec_t coarse_graph = nullptr;   // the whole sub-cycle below the finest level, captured once
+    long long graph_kernels = 0;              // kernel launches one replay stands for
+    const double *graph_last_halo = nullptr;  // host-side exchange tracking as the captured sweep leaves it
+    bool graph_failed = false;
 };
 
 static double alg_bytes(int cls, double N, double Nc) {
@@ -495,6 +497,54 @@ static int coarse_solve(p4b_mg *m) {
     return launch_dense_matvec(m->ctx->stream, m->n0, m->Ainv, L.b, L.x);
 }
 
+static int cycle(p4b_mg *m, int l, bool zero_guess);
+
+// The levels below the finest are launch-latency bound (L2-resident grids, ~6 kernels each), so their whole
+// down-and-up sweep is captured once into a CUDA graph and replayed; the finest-level kernels stay ordinary
+// launches (they are timed individually by the profiler).  Needs a capturable (non-default) stream, no net
+// buffer swaps per smoother call (even -mg_levels_ksp_max_it) and kernel-only communication (peer path).
+static bool graph_usable(const p4b_mg *m) {
+    return m->o.use_graph && !m->graph_failed && m->top >= 2 && m->ctx->stream != nullptr &&
+           m->ctx->stream != cudaStreamLegacy && (m->o.smooth_its % 2 == 0) && (m->ctx->nranks == 1 || m->peer);
+}
+
+static int coarse_cycle_graph(p4b_mg *m) {
+    cudaStream_t st = m->ctx->stream;
+    if (!m->coarse_graph) {
+        const long long before = g_launch_count;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            m->graph_failed = true;
+            return cycle(m, m->top - 1, true);
+        }
+        const int rc = cycle(m, m->top - 1, true);
+        const cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (rc || e != cudaSuccess || !graph) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            m->graph_failed = true;
+            if (rc) return rc;
+            return cycle(m, m->top - 1, true);
+        }
+        m->graph_kernels = g_launch_count - before;
+        g_launch_count = before;
+        m->graph_last_halo = m->last_halo;
+        const cudaError_t e2 = cudaGraphInstantiate(&m->coarse_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e2 != cudaSuccess) {
+            cudaGetLastError();
+            m->coarse_graph = nullptr;
+            m->graph_failed = true;
+            return cycle(m, m->top - 1, true);
+        }
+    }
+    P4B_CUDA(cudaGraphLaunch(m->coarse_graph, st));
+    g_launch_count += m->graph_kernels;
+    m->last_halo = m->graph_last_halo;
+    return 0;
+}
+
 static int cycle(p4b_mg *m, int l, bool zero_guess) {
     if (l == 0) return coarse_solve(m);
     Level &L = m->lev[l];
@@ -522,7 +572,10 @@ static int cycle(p4b_mg *m, int l, bool zero_guess) {
         if (boundary) P4B_CHECK(gather_replicated(m, l - 1, C.b));
     }
     const int cycles = (l == 1 || m->o.cycle == P4B_CYCLE_V) ? 1 : 2;
-    for (int c = 0; c < cycles; c++) P4B_CHECK(cycle(m, l - 1, c == 0));
+    for (int c = 0; c < cycles; c++) {
+        if (l == m->top && c == 0 && graph_usable(m)) P4B_CHECK(coarse_cycle_graph(m));
+        else P4B_CHECK(cycle(m, l - 1, c == 0));
+    }
     P4B_CHECK(halo(m, l - 1, C.x));
     {
         ProfScope ps(m, l, P4B_K_PROLONG);
@@ -962,7 +1015,7 @@ int p4b_mg_default_opts(p4b_mg_opts *o) {
     o->emin = 0; o->emax = 0;
     o->est_lo = 0.1; o->est_hi = 1.1;
     o->fuse = 1;
-    o->use_graph = 0;
+    o->use_graph = 1;
     return 0;
 }
 

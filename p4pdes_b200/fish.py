@@ -127,7 +127,7 @@ class Context:
 
 
 def mg_options(levels=0, cycle="v", smoother="chebyshev", smooth_its=2, eig=None, esteig=(0.1, 1.1), fuse=True,
-               use_graph=False) -> L.MGOpts:
+               use_graph=True) -> L.MGOpts:
     o = L.MGOpts()
     L.load().p4b_mg_default_opts(C.byref(o))
     o.levels = int(levels or 0)

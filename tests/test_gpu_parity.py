@@ -236,6 +236,32 @@ def test_fish_solve_matches_oracle(ctx, path, opts, okw, fuse):
     assert ("    Linear solve converged due to CONVERGED_RTOL iterations %d" % want.its) in rep.lines
 
 
+def test_cuda_graph_replay_of_coarse_levels():
+    # on a capturable (non-default) stream the sub-cycle below the finest level is replayed as a CUDA graph;
+    # results must be the same as the kernel-by-kernel launch sequence (and as the oracle)
+    want = fo.fish(dim=3, refine=5, rtol=1e-10, mg=fo.MGOptions(levels=4))
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        c2 = Context()
+        g = L.refined_grid(3, 5)
+        outs = []
+        for use_graph in (True, False):
+            mg = Multigrid(c2, g, mg_options(levels=4, use_graph=use_graph))
+            b, x = c2.empty(mg.nlocal), c2.empty(mg.nlocal)
+            mg.fish_setup("manuexp", True, b=b)
+            n0 = c2.lib.p4b_launch_count()
+            for _ in range(3):                       # replays, not just the capture pass
+                res = mg.cg_solve(b, x, rtol=1e-10)
+            outs.append((res.its, res.history, x.clone(), c2.lib.p4b_launch_count() - n0))
+            mg.close()
+        side.synchronize()
+    assert outs[0][0] == outs[1][0] == want.its
+    np.testing.assert_allclose(outs[0][1], want.history, rtol=1e-10)
+    assert torch.equal(outs[0][2], outs[1][2])       # same kernels, same order: bitwise equal
+    assert outs[0][3] == outs[1][3]                  # the launch counter accounts for replayed kernels
+    assert relerr(outs[0][2], want.y) < 1e-12
+
+
 def test_cg_with_jacobi_and_no_pc(ctx):
     og = fo.refined_grid(2, 4)
     g = L.refined_grid(2, 4)
