@@ -193,6 +193,29 @@ int p4b_fish_solve_host(p4b_mg *mg, const double *f_host, const double *gb_host,
  * uexact (fish.c:186-187,237-239,248-253).  Outputs are nlocal doubles on device; any may be NULL. */
 int p4b_mg_fish_setup(p4b_mg *mg, int problem, int gonboundary, double *b, double *u0, double *uexact);
 
+/* ---- callbacks of the other two DMDA drivers on the BASELINE path, as device kernels ----
+ *   p4b_minimal_function        c/ch7/minimal.c:210-282  FormFunctionLocal   (u, g, FF: my*mx doubles, i fastest)
+ *   p4b_minimal_sample          c/ch7/minimal.c:27-42    g_bdry_tent (problem 0) / g_bdry_catenoid (problem 1)
+ *   p4b_pattern_initial_state   c/ch5/pattern.c:146-179  InitialState without noise (Y: my*mx*2, (u,v) interleaved)
+ *   p4b_pattern_rhsfunction     c/ch5/pattern.c:185-199  FormRHSFunctionLocal
+ *   p4b_pattern_ifunction       c/ch5/pattern.c:242-267  FormIFunctionLocal   F = Ydot - C L9(Y), periodic
+ *   p4b_pattern_ijacobian_mult  c/ch5/pattern.c:274-318  action of the matrix FormIJacobianLocal assembles
+ *   p4b_sell_*                  [PETSc] MatMult_SeqAIJ for assembled Jacobians: CSR (host) -> SELL-32 (device) */
+int p4b_minimal_sample(p4b_ctx *ctx, int mx, int my, int problem, double tent_H, double catenoid_c, double *g);
+int p4b_minimal_function(p4b_ctx *ctx, int mx, int my, double q, const double *u, const double *g, double *FF);
+int p4b_pattern_initial_state(p4b_ctx *ctx, int mx, int my, double L, double *Y);
+int p4b_pattern_rhsfunction(p4b_ctx *ctx, int mx, int my, double phi, double kappa, const double *Y, double *G);
+int p4b_pattern_ifunction(p4b_ctx *ctx, int mx, int my, double L, double Du, double Dv, const double *Y,
+                          const double *Ydot, double *F);
+int p4b_pattern_ijacobian_mult(p4b_ctx *ctx, int mx, int my, double L, double Du, double Dv, double shift,
+                               const double *X, double *JX);
+typedef struct p4b_sell p4b_sell;
+int p4b_sell_create(p4b_ctx *ctx, int nrows, const int *rowptr_host, const int *colind_host, const double *vals_host,
+                    p4b_sell **A);
+int p4b_sell_spmv(p4b_sell *A, const double *x, double *y);
+int p4b_sell_info(p4b_sell *A, int *nrows, long long *nnz, long long *padded_nnz);
+int p4b_sell_destroy(p4b_sell *A);
+
 /* ---- profiler (CUDA events around finest-level launches on the ctx stream) ---- */
 int p4b_profile_enable(p4b_mg *mg, int on);
 int p4b_profile_reset(p4b_mg *mg);

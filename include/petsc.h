@@ -216,6 +216,77 @@ PetscErrorCode KSPSetTolerances(KSP ksp, PetscReal rtol, PetscReal abstol, Petsc
 PetscErrorCode KSPGetIterationNumber(KSP ksp, PetscInt *its);
 PetscErrorCode PCSetType(PC pc, PCType type);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Declarations for c/ch7/minimal.c and c/ch5/pattern.c ("+ minimal.c", "+ pattern.c").
+ * They let those files compile unchanged (oracle/_ref checks their callbacks against the oracle today);
+ * the shim library does NOT implement the SNES-Newton / TS drivers behind them yet.
+ * ------------------------------------------------------------------------------------------------------ */
+#define PetscCoshReal(a) cosh(a)
+#define PetscAcosReal(a) acos(a)
+#define PetscSinReal(a) sin(a)
+#define PetscCosReal(a) cos(a)
+#define PetscPowReal(a, b) pow(a, b)
+
+typedef struct _p_PetscObject *PetscObject;
+typedef struct _p_PetscViewer *PetscViewer;
+typedef struct _p_TS *TS;
+typedef const char *TSType;
+typedef int MPI_Datatype;
+typedef int MPI_Op;
+#define MPIU_REAL ((MPI_Datatype)1)
+#define MPIU_SUM ((MPI_Op)1)
+#define MPIU_MIN ((MPI_Op)2)
+#define MPIU_MAX ((MPI_Op)3)
+#define TSARKIMEX "arkimex"
+#define TSBEULER "beuler"
+#define TSCN "cn"
+#define TSBDF "bdf"
+typedef enum { TS_LINEAR = 0, TS_NONLINEAR } TSProblemType;
+typedef enum { TS_EXACTFINALTIME_UNSPECIFIED = 0, TS_EXACTFINALTIME_STEPOVER, TS_EXACTFINALTIME_INTERPOLATE,
+               TS_EXACTFINALTIME_MATCHSTEP } TSExactFinalTimeOption;
+typedef struct { PetscScalar x, y; } DMDACoor2d;
+
+PetscViewer PETSC_VIEWER_STDOUT_(MPI_Comm comm);
+#define PETSC_VIEWER_STDOUT_WORLD PETSC_VIEWER_STDOUT_(PETSC_COMM_WORLD)
+int MPI_Allreduce(const void *sendbuf, void *recvbuf, int count, MPI_Datatype datatype, MPI_Op op, MPI_Comm comm);
+PetscErrorCode PetscObjectGetComm(PetscObject obj, MPI_Comm *comm);
+PetscErrorCode PetscObjectGetTabLevel(PetscObject obj, PetscInt *tab);
+PetscErrorCode PetscViewerASCIIAddTab(PetscViewer viewer, PetscInt tabs);
+PetscErrorCode PetscViewerASCIISubtractTab(PetscViewer viewer, PetscInt tabs);
+PetscErrorCode PetscViewerASCIIPrintf(PetscViewer viewer, const char format[], ...);
+PetscErrorCode SNESMonitorSet(SNES snes, PetscErrorCode (*f)(SNES, PetscInt, PetscReal, void *), void *mctx,
+                              PetscErrorCode (*monitordestroy)(void **));
+PetscErrorCode DMGetLocalVector(DM dm, Vec *g);
+PetscErrorCode DMRestoreLocalVector(DM dm, Vec *g);
+PetscErrorCode DMGlobalToLocalBegin(DM dm, Vec g, InsertMode mode, Vec l);
+PetscErrorCode DMGlobalToLocalEnd(DM dm, Vec g, InsertMode mode, Vec l);
+PetscErrorCode DMDASetFieldName(DM da, PetscInt nf, const char name[]);
+PetscErrorCode DMDAGetCoordinateArray(DM da, void *xc);
+PetscErrorCode DMDARestoreCoordinateArray(DM da, void *xc);
+
+/* the TS callback contract (pattern.c:23-30,103-114) */
+typedef PetscErrorCode (*DMDATSRHSFunctionLocal)(DMDALocalInfo *, PetscReal, void *, void *, void *);
+typedef PetscErrorCode (*DMDATSRHSJacobianLocal)(DMDALocalInfo *, PetscReal, void *, Mat, Mat, void *);
+typedef PetscErrorCode (*DMDATSIFunctionLocal)(DMDALocalInfo *, PetscReal, void *, void *, void *, void *);
+typedef PetscErrorCode (*DMDATSIJacobianLocal)(DMDALocalInfo *, PetscReal, void *, void *, PetscReal, Mat, Mat, void *);
+PetscErrorCode DMDATSSetRHSFunctionLocal(DM dm, InsertMode imode, DMDATSRHSFunctionLocal func, void *ctx);
+PetscErrorCode DMDATSSetRHSJacobianLocal(DM dm, DMDATSRHSJacobianLocal func, void *ctx);
+PetscErrorCode DMDATSSetIFunctionLocal(DM dm, InsertMode imode, DMDATSIFunctionLocal func, void *ctx);
+PetscErrorCode DMDATSSetIJacobianLocal(DM dm, DMDATSIJacobianLocal func, void *ctx);
+PetscErrorCode TSCreate(MPI_Comm comm, TS *ts);
+PetscErrorCode TSSetProblemType(TS ts, TSProblemType type);
+PetscErrorCode TSSetDM(TS ts, DM dm);
+PetscErrorCode TSSetApplicationContext(TS ts, void *usrP);
+PetscErrorCode TSSetType(TS ts, TSType type);
+PetscErrorCode TSGetType(TS ts, TSType *type);
+PetscErrorCode TSSetTime(TS ts, PetscReal t);
+PetscErrorCode TSSetMaxTime(TS ts, PetscReal maxtime);
+PetscErrorCode TSSetTimeStep(TS ts, PetscReal time_step);
+PetscErrorCode TSSetExactFinalTime(TS ts, TSExactFinalTimeOption eftopt);
+PetscErrorCode TSSetFromOptions(TS ts);
+PetscErrorCode TSSolve(TS ts, Vec u);
+PetscErrorCode TSDestroy(TS *ts);
+
 #ifdef __cplusplus
 }
 #endif

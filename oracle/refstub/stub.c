@@ -7,7 +7,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
-struct _p_DM { int dim, M[3]; double cmin[3], cmax[3]; };
+struct _p_DM { int dim, M[3], dof; double cmin[3], cmax[3]; };
 struct _p_Vec { size_t n; double *h; DM dm; void *tables; };
 struct _p_Mat { long cap, n; int *row, *col; double *val; DM dm; };
 
@@ -75,6 +75,16 @@ PetscErrorCode MatSetValuesStencil(Mat A, PetscInt m, const MatStencil im[], Pet
             }
             const int rk = dim >= 3 ? im[r].k : 0, rj = dim >= 2 ? im[r].j : 0;
             const int ck = dim >= 3 ? in[c].k : 0, cj = dim >= 2 ? in[c].j : 0;
+            const int dof = A->dm->dof > 1 ? A->dm->dof : 1;
+            if (dof > 1) {      /* multi-component periodic grids (pattern.c): wrap the stencil indices */
+                const int ri = (im[r].i + M[0]) % M[0], rjj = (rj + M[1]) % M[1];
+                const int ci = (in[c].i + M[0]) % M[0], cjj = (cj + M[1]) % M[1];
+                A->row[A->n] = (rjj * M[0] + ri) * dof + im[r].c;
+                A->col[A->n] = (cjj * M[0] + ci) * dof + in[c].c;
+                A->val[A->n] = v[r * n + c];
+                A->n++;
+                continue;
+            }
             A->row[A->n] = (rk * M[1] + rj) * M[0] + im[r].i;
             A->col[A->n] = (ck * M[1] + cj) * M[0] + in[c].i;
             A->val[A->n] = v[r * n + c];
@@ -82,6 +92,9 @@ PetscErrorCode MatSetValuesStencil(Mat A, PetscInt m, const MatStencil im[], Pet
         }
     return 0;
 }
+PetscErrorCode MatZeroEntries(Mat A) { A->n = 0; return 0; }
+PetscErrorCode VecScale(Vec x, PetscScalar a) { for (size_t i = 0; i < x->n; i++) x->h[i] *= a; return 0; }
+void refstub_set_dof(DM dm, int dof) { dm->dof = dof; }
 PetscErrorCode MatAssemblyBegin(Mat A, MatAssemblyType t) { (void)A; (void)t; return 0; }
 PetscErrorCode MatAssemblyEnd(Mat A, MatAssemblyType t) { (void)A; (void)t; return 0; }
 

@@ -67,4 +67,18 @@ int launch_initial_state(cudaStream_t st, const LevelDesc &L, const double *gb, 
 int launch_poisson_function(cudaStream_t st, const LevelDesc &L, int dim, double c0, const double *u, const double *f,
                             const double *gb, double *F);
 
+// minimal.c / pattern.c callbacks and SELL SpMV (mp_kernels.cu)
+int launch_minimal_sample(cudaStream_t st, int mx, int my, int zs, int zm, int problem, double tent_H, double c, double *g);
+int launch_minimal_function(cudaStream_t st, int mx, int my, int zs, int zm, double q, const double *u, const double *g,
+                            double *FF);
+int launch_pattern_init(cudaStream_t st, int mx, int my, double L, double *Y);
+int launch_pattern_rhs(cudaStream_t st, int n, double phi, double kappa, const double *Y, double *G);
+int launch_pattern_ifunction(cudaStream_t st, int mx, int my, double Cu, double Cv, int use_shift, double shift,
+                             const double *Y, const double *Ydot, double *F);
+struct Sell;
+int sell_build(cudaStream_t st, int nrows, const int *rowptr, const int *colind, const double *vals, Sell **out);
+int sell_spmv(cudaStream_t st, const Sell *A, const double *x, double *y);
+void sell_free(Sell *A);
+void sell_info(const Sell *A, int *nrows, long long *nnz, long long *padded);
+
 }  // namespace p4b

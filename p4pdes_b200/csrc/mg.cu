@@ -1379,6 +1379,60 @@ int p4b_mg_fish_setup(p4b_mg *m, int problem, int gonboundary, double *b_out, do
     return 0;
 }
 
+// ---- minimal.c / pattern.c callbacks, assembled SpMV ---------------------------------------------------
+int p4b_minimal_sample(p4b_ctx *c, int mx, int my, int problem, double tent_H, double catenoid_c, double *g) {
+    if (mx < 3 || my < 3) return fail(60, "grid needs at least 3 nodes per dimension");
+    if (problem != 0 && problem != 1) return fail(62, "minimal problem must be 0 (tent) or 1 (catenoid)");
+    if (problem == 1 && catenoid_c < 1.0) return fail(62, "catenoid_c >= 1 required (minimal.c:116)");
+    return launch_minimal_sample(c->stream, mx, my, 0, my, problem, tent_H, catenoid_c, g);
+}
+int p4b_minimal_function(p4b_ctx *c, int mx, int my, double q, const double *u, const double *g, double *FF) {
+    if (mx < 3 || my < 3) return fail(60, "grid needs at least 3 nodes per dimension");
+    return launch_minimal_function(c->stream, mx, my, 0, my, q, u, g, FF);
+}
+int p4b_pattern_initial_state(p4b_ctx *c, int mx, int my, double L, double *Y) {
+    if (mx < 3 || my < 3) return fail(60, "periodic grid needs at least 3 nodes per dimension");
+    return launch_pattern_init(c->stream, mx, my, L, Y);
+}
+int p4b_pattern_rhsfunction(p4b_ctx *c, int mx, int my, double phi, double kappa, const double *Y, double *G) {
+    return launch_pattern_rhs(c->stream, mx * my, phi, kappa, Y, G);
+}
+int p4b_pattern_ifunction(p4b_ctx *c, int mx, int my, double L, double Du, double Dv, const double *Y, const double *Ydot,
+                          double *F) {
+    if (mx < 3 || my < 3) return fail(60, "periodic grid needs at least 3 nodes per dimension");
+    const double h = L / (double)mx;                       // pattern.c:246
+    return launch_pattern_ifunction(c->stream, mx, my, Du / (6.0 * h * h), Dv / (6.0 * h * h), 0, 0.0, Y, Ydot, F);
+}
+int p4b_pattern_ijacobian_mult(p4b_ctx *c, int mx, int my, double L, double Du, double Dv, double shift, const double *X,
+                               double *JX) {
+    if (mx < 3 || my < 3) return fail(60, "periodic grid needs at least 3 nodes per dimension");
+    const double h = L / (double)mx;
+    return launch_pattern_ifunction(c->stream, mx, my, Du / (6.0 * h * h), Dv / (6.0 * h * h), 1, shift, X, nullptr, JX);
+}
+
+struct p4b_sell {
+    p4b_ctx *ctx;
+    Sell *A;
+};
+int p4b_sell_create(p4b_ctx *c, int nrows, const int *rowptr, const int *colind, const double *vals, p4b_sell **out) {
+    Sell *A = nullptr;
+    P4B_CHECK(sell_build(c->stream, nrows, rowptr, colind, vals, &A));
+    *out = new p4b_sell{c, A};
+    return 0;
+}
+int p4b_sell_spmv(p4b_sell *S, const double *x, double *y) { return sell_spmv(S->ctx->stream, S->A, x, y); }
+int p4b_sell_info(p4b_sell *S, int *nrows, long long *nnz, long long *padded) {
+    sell_info(S->A, nrows, nnz, padded);
+    return 0;
+}
+int p4b_sell_destroy(p4b_sell *S) {
+    if (!S) return 0;
+    cudaStreamSynchronize(S->ctx->stream);
+    sell_free(S->A);
+    delete S;
+    return 0;
+}
+
 // ---- profiler -----------------------------------------------------------------------------------------
 int p4b_profile_enable(p4b_mg *m, int on) { m->prof.on = on != 0; return 0; }
 int p4b_profile_reset(p4b_mg *m) {

@@ -111,6 +111,17 @@ _SIGS = {
     "p4b_cg_solve_host": (C.c_int, [_P, C.c_int, _P, _P, C.c_double, C.c_double, C.c_int, C.POINTER(KSPResult)]),
     "p4b_fish_solve_host": (C.c_int, [_P, _P, _P, _P, C.c_double, C.c_double, C.c_int, C.POINTER(KSPResult)]),
     "p4b_mg_fish_setup": (C.c_int, [_P, C.c_int, C.c_int, _D, _D, _D]),
+    "p4b_minimal_sample": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _D]),
+    "p4b_minimal_function": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, _D, _D]),
+    "p4b_pattern_initial_state": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D]),
+    "p4b_pattern_rhsfunction": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, _D, _D]),
+    "p4b_pattern_ifunction": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _D, _D, _D]),
+    "p4b_pattern_ijacobian_mult": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                             _D, _D]),
+    "p4b_sell_create": (C.c_int, [_P, C.c_int, _P, _P, _P, C.POINTER(_P)]),
+    "p4b_sell_spmv": (C.c_int, [_P, _D, _D]),
+    "p4b_sell_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "p4b_sell_destroy": (C.c_int, [_P]),
     "p4b_profile_enable": (C.c_int, [_P, C.c_int]),
     "p4b_profile_reset": (C.c_int, [_P]),
     "p4b_profile_get": (C.c_int, [_P, C.c_int, C.POINTER(KernelStat)]),
