@@ -29,7 +29,7 @@ OPTIONS = ("-fsh_dim 3 -da_refine {refine} -pc_type mg -pc_mg_levels {levels} -m
            "-mg_levels_ksp_max_it 2 -mg_levels_pc_type jacobi -ksp_rtol 1e-10")
 ALG_BYTES = {"apply_dot": "16N", "residual": "24N", "cheb_zero": "16N", "cheb_first": "24N", "cheb_next": "32N",
              "restrict": "8N+8Nc", "prolong_add": "16N+8Nc", "axpy2": "48N", "dot2": "16N", "aypx": "24N",
-             "resid_restrict": "16N+8Nc"}
+             "resid_restrict": "16N+8Nc", "xp_update": "40N", "r_update": "24N"}
 
 
 def peaks():

@@ -90,6 +90,8 @@ enum {
     P4B_K_DOT2,            /* (z,z), (z,r)                         16 N */
     P4B_K_AYPX,            /* p = z + b p                          24 N */
     P4B_K_RESID_RESTRICT,  /* b_c = P^T (b - A x) fused            16 N + 8 N_c */
+    P4B_K_XP_UPDATE,       /* x += a p ; p = z + b p (one pass)    40 N */
+    P4B_K_R_UPDATE,        /* r -= a w                             24 N */
     P4B_K_NCLASSES
 };
 

@@ -50,6 +50,11 @@ int launch_axpy2(cudaStream_t st, long long n, const double *num, const double *
 // p = z + (num/den) p ; first != 0: p = z
 int launch_aypx_dev(cudaStream_t st, long long n, const double *num, const double *den, const double *z, double *p,
                     int first);
+// fused CG updates: (x += a_prev p ; p = z + b p) in one pass, r -= a w, and the final x += a p
+int launch_xp_update(cudaStream_t st, long long n, const double *an, const double *ad, const double *bn, const double *bd,
+                     const double *z, double *p, double *x, int first);
+int launch_r_update(cudaStream_t st, long long n, const double *num, const double *den, const double *w, double *r);
+int launch_x_flush(cudaStream_t st, long long n, const double *num, const double *den, const double *p, double *x);
 int launch_axpy(cudaStream_t st, long long n, double a, const double *x, double *y);
 int launch_aypx(cudaStream_t st, long long n, double a, const double *x, double *y);
 int launch_set(cudaStream_t st, long long n, double a, double *y);

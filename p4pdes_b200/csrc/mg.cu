@@ -307,12 +307,14 @@ static double alg_bytes(int cls, double N, double Nc) {
         case P4B_K_DOT2: return 16 * N;
         case P4B_K_AYPX: return 24 * N;
         case P4B_K_RESID_RESTRICT: return 16 * N + 8 * Nc;
+        case P4B_K_XP_UPDATE: return 40 * N;
+        case P4B_K_R_UPDATE: return 24 * N;
     }
     return 0;
 }
 
 static const char *k_names[P4B_K_NCLASSES] = {"apply_dot", "residual", "cheb_zero", "cheb_first", "cheb_next", "restrict",
-                                              "prolong_add", "axpy2", "dot2", "aypx", "resid_restrict"};
+                                              "prolong_add", "axpy2", "dot2", "aypx", "resid_restrict", "xp_update", "r_update"};
 
 // RAII-free profiling bracket: only finest-level launches are timed
 struct ProfScope {
@@ -1279,7 +1281,12 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
     else if (dp <= ttol) R.reason = (dp <= abstol) ? P4B_CONVERGED_ATOL : P4B_CONVERGED_RTOL;
     while (!R.reason) {
         if (its >= max_it) { R.reason = P4B_DIVERGED_ITS; break; }
-        {
+        if (m->o.fuse) {
+            // x += alpha_{k-1} p (deferred from the previous iteration) and p = z + beta p in one pass over p
+            ProfScope ps(m, m->top, P4B_K_XP_UPDATE);
+            P4B_CHECK(launch_xp_update(st, n, S + 2 * (1 - q) + 1, S + 4, S + 2 * q + 1, S + 2 * (1 - q) + 1, T.x, m->p, x,
+                                       its == 0));
+        } else {
             ProfScope ps(m, m->top, P4B_K_AYPX);
             P4B_CHECK(launch_aypx_dev(st, n, S + 2 * q + 1, S + 2 * (1 - q) + 1, T.x, m->p, its == 0));
         }
@@ -1292,7 +1299,10 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
             P4B_CHECK(launch_stencil(st, T.d, op, red));
         }
         P4B_CHECK(ctx_allreduce(c, S + 4, 1));
-        {
+        if (m->o.fuse) {
+            ProfScope ps(m, m->top, P4B_K_R_UPDATE);
+            P4B_CHECK(launch_r_update(st, n, S + 2 * q + 1, S + 4, m->w, T.b));
+        } else {
             ProfScope ps(m, m->top, P4B_K_AXPY2);
             P4B_CHECK(launch_axpy2(st, n, S + 2 * q + 1, S + 4, m->p, m->w, x, T.b));
         }
@@ -1306,6 +1316,8 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
         if (!(dp == dp)) R.reason = P4B_DIVERGED_NAN;
         else if (dp <= ttol) R.reason = (dp <= abstol) ? P4B_CONVERGED_ATOL : P4B_CONVERGED_RTOL;
     }
+    if (m->o.fuse && its >= 1)      // the last iteration's x += alpha p is still pending
+        P4B_CHECK(launch_x_flush(st, n, S + 2 * (1 - q) + 1, S + 4, m->p, x));
     P4B_CUDA(cudaEventRecord(c->ev1, st));
     P4B_CUDA(cudaEventSynchronize(c->ev1));
     float ms = 0;

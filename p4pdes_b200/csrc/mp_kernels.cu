@@ -29,7 +29,18 @@ __global__ void __launch_bounds__(256) minimal_sample_kernel(int mx, int my, int
     g[n] = v;
 }
 
+// DD(w) = (1+w)^q (minimal.c:46-48).  The reference calls libm pow(); fp64 pow costs ~10x the rest of the
+// residual, so the exponents the drivers actually use are special-cased (q = -1/2: the minimal surface
+// equation, q = 0: Laplace) and the general case is exp(q log(1+w)); all agree with pow() to a few ulp.
+template <int QMODE>
+__device__ __forceinline__ double diffusivity(double w, double q) {
+    if (QMODE == 0) return 1.0;
+    if (QMODE == 1) return rsqrt(1.0 + w);
+    return exp(q * log(1.0 + w));
+}
+
 // u, g: rows [zs-1, zs+zm] readable (ghost rows) when the slab is interior
+template <int QMODE>
 __global__ void __launch_bounds__(256) minimal_function_kernel(int mx, int my, int zs, int zm, double q,
                                                                 const double *__restrict__ u,
                                                                 const double *__restrict__ g,
@@ -42,7 +53,6 @@ __global__ void __launch_bounds__(256) minimal_function_kernel(int mx, int my, i
         FF[n] = uc - g[n];                                   // unscaled boundary rows (:227)
         return;
     }
-    const double hx = 1.0 / (mx - 1), hy = 1.0 / (my - 1);
     const bool be = (i + 1 == mx - 1), bw = (i - 1 == 0), bn = (j + 1 == my - 1), bs = (j - 1 == 0);
     // a neighbour that is a boundary node takes the boundary value g (:230-256)
     const double ue = be ? g[n + 1] : u[n + 1];
@@ -53,16 +63,19 @@ __global__ void __launch_bounds__(256) minimal_function_kernel(int mx, int my, i
     const double unw = (bw || bn) ? g[n + mx - 1] : u[n + mx - 1];
     const double use = (be || bs) ? g[n - mx + 1] : u[n - mx + 1];
     const double usw = (bw || bs) ? g[n - mx - 1] : u[n - mx - 1];
+    // reciprocal spacings instead of the reference's divisions (a few ulp; fp64 division is ~10x a multiply)
+    const double ihx = (double)(mx - 1), ihy = (double)(my - 1), i4hx = 0.25 * ihx, i4hy = 0.25 * ihy;
     double dux, duy;
-    dux = (ue - uc) / hx;  duy = (un + une - us - use) / (4.0 * hy);
-    const double De = pow(1.0 + (dux * dux + duy * duy), q);
-    dux = (uc - uw) / hx;  duy = (unw + un - usw - us) / (4.0 * hy);
-    const double Dw = pow(1.0 + (dux * dux + duy * duy), q);
-    dux = (ue + une - uw - unw) / (4.0 * hx);  duy = (un - uc) / hy;
-    const double Dn = pow(1.0 + (dux * dux + duy * duy), q);
-    dux = (ue + use - uw - usw) / (4.0 * hx);  duy = (uc - us) / hy;
-    const double Ds = pow(1.0 + (dux * dux + duy * duy), q);
-    FF[n] = -(hy / hx) * (De * (ue - uc) - Dw * (uc - uw)) - (hx / hy) * (Dn * (un - uc) - Ds * (uc - us));
+    dux = (ue - uc) * ihx;  duy = (un + une - us - use) * i4hy;
+    const double De = diffusivity<QMODE>(dux * dux + duy * duy, q);
+    dux = (uc - uw) * ihx;  duy = (unw + un - usw - us) * i4hy;
+    const double Dw = diffusivity<QMODE>(dux * dux + duy * duy, q);
+    dux = (ue + une - uw - unw) * i4hx;  duy = (un - uc) * ihy;
+    const double Dn = diffusivity<QMODE>(dux * dux + duy * duy, q);
+    dux = (ue + use - uw - usw) * i4hx;  duy = (uc - us) * ihy;
+    const double Ds = diffusivity<QMODE>(dux * dux + duy * duy, q);
+    const double hyhx = ihx / ihy, hxhy = ihy / ihx;        // hy/hx and hx/hy
+    FF[n] = -hyhx * (De * (ue - uc) - Dw * (uc - uw)) - hxhy * (Dn * (un - uc) - Ds * (uc - us));
 }
 
 int launch_minimal_sample(cudaStream_t st, int mx, int my, int zs, int zm, int problem, double tent_H, double c, double *g) {
@@ -76,7 +89,10 @@ int launch_minimal_function(cudaStream_t st, int mx, int my, int zs, int zm, dou
                             double *FF) {
     const long long n = (long long)mx * zm;
     if (n <= 0) return 0;
-    minimal_function_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mx, my, zs, zm, q, u, g, FF);
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (q == 0.0) minimal_function_kernel<0><<<nb, 256, 0, st>>>(mx, my, zs, zm, q, u, g, FF);
+    else if (q == -0.5) minimal_function_kernel<1><<<nb, 256, 0, st>>>(mx, my, zs, zm, q, u, g, FF);
+    else minimal_function_kernel<2><<<nb, 256, 0, st>>>(mx, my, zs, zm, q, u, g, FF);
     P4B_LAUNCH_CHECK();
     return 0;
 }

@@ -358,8 +358,10 @@ int tune_march(const char *key, long v) {
 
 bool stencil_fast_eligible(const LevelDesc &L) {
     const MarchTune &t = tune();
-    return t.enabled && L.ax && L.az && (long long)L.nx * L.ny >= t.min_plane && L.zm >= 8 &&
-           (long long)L.nx * L.ny * (L.zm + 2) < (1LL << 31);
+    // 3-D grids: planes of at least min_plane nodes; 2-D grids (slots x,z): rows of at least min_plane/16 nodes
+    const long long plane = (long long)L.nx * L.ny;
+    const bool big = L.ay ? plane >= t.min_plane : plane >= t.min_plane / 16;
+    return t.enabled && L.ax && L.az && big && L.zm >= 8 && plane * (L.zm + 2) < (1LL << 31);
 }
 
 template <int MODE, int P, int NT>

@@ -124,6 +124,56 @@ __global__ void __launch_bounds__(VT) aypx_dev_kernel(long long n, const double 
     }
 }
 
+// One pass for the CG direction update AND the previous iteration's solution update:
+//   x += a_prev * p   (a_prev = an/ad, the alpha of the iteration that produced this p; skipped when first)
+//   p  = z + b * p    (b = bn/bd)
+// p is read once for both, which saves the separate 24 N pass x += a p of KSPSolve_CG.
+__global__ void __launch_bounds__(VT) xp_update_kernel(long long n, const double *__restrict__ an,
+                                                        const double *__restrict__ ad, const double *__restrict__ bn,
+                                                        const double *__restrict__ bd, const double *__restrict__ z,
+                                                        double *__restrict__ p, double *__restrict__ x, int first) {
+    const double a = first ? 0.0 : an[0] / ad[0];
+    const double b = first ? 0.0 : bn[0] / bd[0];
+    const long long stride = (long long)gridDim.x * VT * VU;
+    for (long long base = (long long)blockIdx.x * VT * VU + threadIdx.x; base < n; base += stride) {
+        double zv[VU], pv[VU], xv[VU];
+#pragma unroll
+        for (int q = 0; q < VU; q++) {
+            const long long i = base + (long long)q * VT;
+            if (i < n) { zv[q] = z[i]; pv[q] = first ? 0.0 : p[i]; xv[q] = first ? 0.0 : x[i]; }
+        }
+#pragma unroll
+        for (int q = 0; q < VU; q++) {
+            const long long i = base + (long long)q * VT;
+            if (i < n) {
+                if (!first) x[i] = xv[q] + a * pv[q];
+                p[i] = first ? zv[q] : zv[q] + b * pv[q];
+            }
+        }
+    }
+}
+
+// r -= a w  with a = num/den on the device
+__global__ void __launch_bounds__(VT) r_update_kernel(long long n, const double *__restrict__ num,
+                                                       const double *__restrict__ den, const double *__restrict__ w,
+                                                       double *__restrict__ r) {
+    const double a = num[0] / den[0];
+    const long long stride = (long long)gridDim.x * VT * VU;
+    for (long long base = (long long)blockIdx.x * VT * VU + threadIdx.x; base < n; base += stride) {
+        double wv[VU], rv[VU];
+#pragma unroll
+        for (int q = 0; q < VU; q++) {
+            const long long i = base + (long long)q * VT;
+            if (i < n) { wv[q] = w[i]; rv[q] = r[i]; }
+        }
+#pragma unroll
+        for (int q = 0; q < VU; q++) {
+            const long long i = base + (long long)q * VT;
+            if (i < n) r[i] = rv[q] - a * wv[q];
+        }
+    }
+}
+
 // out = a x + b y ; x or y may be null (treated as zero) ; out may alias x or y
 __global__ void __launch_bounds__(VT) axpby_kernel(long long n, double a, const double *x, double b, const double *y,
                                                     double *out) {
@@ -175,6 +225,34 @@ int launch_aypx_dev(cudaStream_t st, long long n, const double *num, const doubl
     P4B_LAUNCH_CHECK();
     return 0;
 }
+int launch_xp_update(cudaStream_t st, long long n, const double *an, const double *ad, const double *bn, const double *bd,
+                     const double *z, double *p, double *x, int first) {
+    if (n <= 0) return 0;
+    xp_update_kernel<<<vec_blocks(n, STREAM_BLOCKS), VT, 0, st>>>(n, an, ad, bn, bd, z, p, x, first);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+int launch_r_update(cudaStream_t st, long long n, const double *num, const double *den, const double *w, double *r) {
+    if (n <= 0) return 0;
+    r_update_kernel<<<vec_blocks(n, STREAM_BLOCKS), VT, 0, st>>>(n, num, den, w, r);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+// x += (num/den) p
+__global__ void __launch_bounds__(VT) x_flush_kernel(long long n, const double *__restrict__ num,
+                                                      const double *__restrict__ den, const double *__restrict__ p,
+                                                      double *__restrict__ x) {
+    const double a = num[0] / den[0];
+    const long long stride = (long long)gridDim.x * VT;
+    for (long long i = (long long)blockIdx.x * VT + threadIdx.x; i < n; i += stride) x[i] += a * p[i];
+}
+int launch_x_flush(cudaStream_t st, long long n, const double *num, const double *den, const double *p, double *x) {
+    if (n <= 0) return 0;
+    x_flush_kernel<<<vec_blocks(n, STREAM_BLOCKS * 4), VT, 0, st>>>(n, num, den, p, x);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+
 static int launch_axpby(cudaStream_t st, long long n, double a, const double *x, double b, const double *y,
                         double *out) {
     if (n <= 0) return 0;

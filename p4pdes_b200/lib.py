@@ -20,7 +20,7 @@ PROBLEMS = {"manupoly": 0, "manuexp": 1, "zero": 2}
 CONVERGED_RTOL, CONVERGED_ATOL, DIVERGED_ITS, DIVERGED_NAN = 2, 3, -3, -9
 REASONS = {2: "CONVERGED_RTOL", 3: "CONVERGED_ATOL", -3: "DIVERGED_ITS", -9: "DIVERGED_NANORINF"}
 KERNEL_CLASSES = ["apply_dot", "residual", "cheb_zero", "cheb_first", "cheb_next", "restrict", "prolong_add",
-                  "axpy2", "dot2", "aypx", "resid_restrict"]
+                  "axpy2", "dot2", "aypx", "resid_restrict", "xp_update", "r_update"]
 
 
 class Grid(C.Structure):

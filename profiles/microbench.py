@@ -1,0 +1,82 @@
+"""Micro-benchmark of the callback / SpMV kernels at the BASELINE config sizes (C4: 2049^2, C5: 2048^2 x 2 dof) and at
+sizes that exceed the 126 MB L2, with CUDA events on the launching stream.  Prints one JSON line per kernel.
+
+    python profiles/microbench.py > profiles/r01_microbench.jsonl
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from p4pdes_b200 import callbacks as cb  # noqa: E402
+from p4pdes_b200 import lib as L  # noqa: E402
+from p4pdes_b200.fish import Context  # noqa: E402
+
+PEAK = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] \
+    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6553.9
+
+
+def timeit(fn, reps=20, warm=5):
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def report(name, size, bytes_alg, ms, note=""):
+    gbs = bytes_alg / ms / 1e6
+    print(json.dumps({"kernel": name, "size": size, "alg_bytes": bytes_alg, "ms": ms, "GBs": gbs,
+                      "frac_of_hbm_peak": gbs / PEAK, "working_set_MB": bytes_alg / 1e6, "note": note}), flush=True)
+
+
+def main():
+    ctx = Context()
+    for m in (2049, 8193):
+        n = m * m
+        g = cb.minimal_g(ctx, m, m, "catenoid", 1.0, 1.1)
+        u = g.clone() * 0.9
+        FF = ctx.empty(n)
+        ms = timeit(lambda: cb.minimal_form_function(ctx, m, m, u, g, -0.5, out=FF))
+        report("minimal_function", "%d^2" % m, 16.0 * n, ms, "L2 resident" if 16 * n < 100e6 else "exceeds L2")
+        del g, u, FF
+    for m in (2048, 6144):
+        n = m * m
+        Y = cb.pattern_initial_state(ctx, m, m)
+        Yd = Y.clone()
+        F = ctx.empty(2 * n)
+        ms = timeit(lambda: cb.pattern_ifunction(ctx, m, m, Y, Yd, out=F))
+        report("pattern_ifunction", "%d^2 x2" % m, 48.0 * n, ms, "L2 resident" if 48 * n < 100e6 else "exceeds L2")
+        ms = timeit(lambda: cb.pattern_rhs_function(ctx, m, m, Y, out=F))
+        report("pattern_rhsfunction", "%d^2 x2" % m, 32.0 * n, ms)
+        ms = timeit(lambda: cb.pattern_ijacobian_mult(ctx, m, m, 0.2, Y, out=F))
+        report("pattern_ijacobian_mult", "%d^2 x2" % m, 32.0 * n, ms)
+        del Y, Yd, F
+    # SELL SpMV on the assembled 5-point fish Jacobian (2049^2) and 7-point (257^3): built with scipy on the host
+    from oracle import fish_oracle as fo
+    for og, label in ((fo.Grid(2, (2049, 2049, 1)), "fish 2-D 2049^2 5-pt"), (fo.Grid(3, (257, 257, 257)), "fish 3-D 257^3 7-pt")):
+        A = fo.jacobian(og)
+        A.sort_indices()
+        S = cb.SellMatrix(ctx, A.indptr, A.indices, A.data)
+        x = torch.randn(og.n, dtype=torch.float64, device="cuda")
+        y = ctx.empty(og.n)
+        ms = timeit(lambda: S.mult(x, y))
+        report("sell_spmv", label, 12.0 * S.padded_nnz + 16.0 * og.n, ms, "nnz %d padded %d" % (S.nnz, S.padded_nnz))
+        # the matrix-free kernel for the same operator
+        g = L.make_grid(og.dim, og.m[:og.dim])
+        ms2 = timeit(lambda: ctx.stencil_apply(g, x, y))
+        report("stencil_apply (matrix-free)", label, 16.0 * og.n, ms2, "same operator, %.1fx faster than SpMV" % (ms / ms2))
+        S.close()
+        del x, y
+
+
+if __name__ == "__main__":
+    main()

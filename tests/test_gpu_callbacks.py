@@ -27,7 +27,7 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("mx,my", [(5, 5), (9, 17), (33, 33), (129, 65), (513, 513)])
-@pytest.mark.parametrize("problem,q", [("catenoid", -0.5), ("tent", -0.5), ("tent", 0.0)])
+@pytest.mark.parametrize("problem,q", [("catenoid", -0.5), ("tent", -0.5), ("tent", 0.0), ("catenoid", -0.3)])
 def test_minimal_form_function(ctx, mx, my, problem, q):
     g = mp.minimal_g(mx, my, problem, 1.0, 1.1)
     dg = cb.minimal_g(ctx, mx, my, problem, 1.0, 1.1)

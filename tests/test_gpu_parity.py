@@ -24,6 +24,7 @@ GRIDS = [
     (3, (17, 9, 33), (1.0, 0.5, 2.0), (1.0, 1.0, 1.0)),
     (3, (33, 33, 33), (1, 1, 1), (1.0, 1.0, 1.0)),
     (3, (65, 65, 65), (1, 1, 1), (1.0, 1.0, 1.0)),
+    (2, (2049, 33), (1, 1, 1), (1.0, 1.0, 1.0)),          # wide 2-D rows: the plane-marching kernel's 2-D path
 ]
 
 
