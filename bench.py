@@ -137,6 +137,8 @@ def main():
     ap.add_argument("--no-fuse", action="store_true")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="multi-GPU transport (A/B)")
     ap.add_argument("--no-graph", action="store_true", help="launch the coarse levels kernel by kernel (A/B)")
+    ap.add_argument("--trace", default="", help="after the timed steps, run one more solve with every launch on every "
+                                                "level bracketed by CUDA events and write the table to this JSON file")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -210,6 +212,18 @@ def main():
     ms_step = ms_total / args.steps
     stats = mg.profile_stats()
     mg.profile(False)
+    exchange = {k: stats.pop(k) for k in L.KERNEL_CLASSES[L.N_ROOFLINE_CLASSES:] if k in stats}
+    if args.trace:
+        mg.profile(2)
+        mg.profile_reset()
+        barrier()
+        tres = mg.cg_solve(b, x, rtol=1e-10)
+        barrier()
+        tr = mg.profile_trace()
+        mg.profile(False)
+        with open("%s.rank%d" % (args.trace, rank) if world > 1 else args.trace, "w") as fh:
+            json.dump({"n_gpus": world, "rank": rank, "solve_ms": tres.solve_ms, "its": tres.its,
+                       "levels": {str(l): v for l, v in tr.items()}}, fh, indent=1)
 
     # correctness of what was timed: error norms of u = u0 - y against the exact solution (fish.c:248-280)
     ctx.axpy(-1.0, x, u0)
@@ -293,6 +307,7 @@ def main():
         "ksp_its": res.its, "ksp_reason": L.REASONS.get(res.reason), "rnorm0": res.rnorm0, "rnorm": res.rnorm,
         "errinf": errinf, "err2h": err2h,
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": table,
+        "exchange_ms_per_step": {k: v["ms"] / args.steps for k, v in exchange.items()},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

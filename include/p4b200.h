@@ -92,6 +92,12 @@ enum {
     P4B_K_RESID_RESTRICT,  /* b_c = P^T (b - A x) fused            16 N + 8 N_c */
     P4B_K_XP_UPDATE,       /* x += a p ; p = z + b p (one pass)    40 N */
     P4B_K_R_UPDATE,        /* r -= a w                             24 N */
+    /* not kernels of the roofline table: exchange / latency items, timed the same way (0 algorithmic bytes) */
+    P4B_K_HALO,            /* ghost-plane exchange (DMGlobalToLocal) */
+    P4B_K_GATHER,          /* completing a replicated level's right-hand side on every rank */
+    P4B_K_ALLREDUCE,       /* Krylov scalars over all ranks */
+    P4B_K_COARSE,          /* dense coarsest-level solve */
+    P4B_K_SUBCYCLE,        /* everything below the finest level as one unit (the CUDA-graph replay) */
     P4B_K_NCLASSES
 };
 
@@ -219,7 +225,11 @@ int p4b_sell_info(p4b_sell *A, int *nrows, long long *nnz, long long *padded_nnz
 int p4b_sell_destroy(p4b_sell *A);
 
 /* ---- profiler (CUDA events around finest-level launches on the ctx stream) ---- */
+/* on = 1: finest-level kernels (+ exchanges and the sub-cycle as one unit); on = 2: trace mode, every launch on
+ * every level is bracketed (the CUDA graph is bypassed so that they are visible) */
 int p4b_profile_enable(p4b_mg *mg, int on);
+/* trace mode: the same statistics per level (0 = coarsest) */
+int p4b_profile_get_level(p4b_mg *mg, int level, int kernel_class, p4b_kernel_stat *out);
 int p4b_profile_reset(p4b_mg *mg);
 int p4b_profile_get(p4b_mg *mg, int kernel_class, p4b_kernel_stat *out);
 /* kernels launched by this library in this process so far (bench.py reports the difference) */

@@ -263,12 +263,13 @@ struct Level {
 };
 
 struct Prof {
-    bool on = false;
-    struct Rec { int cls; cudaEvent_t a, b; double bytes; };
+    int on = 0;                  // 1 = finest level, 2 = trace (every level, no graph)
+    struct Rec { int cls; int level; cudaEvent_t a, b; double bytes; };
     std::vector<Rec> recs;
     std::vector<cudaEvent_t> pool;
     size_t used = 0;
     p4b_kernel_stat stat[P4B_K_NCLASSES];
+    p4b_kernel_stat lstat[P4B_MAX_LEVELS][P4B_K_NCLASSES];
 };
 
 struct p4b_mg {
@@ -314,14 +315,15 @@ static double alg_bytes(int cls, double N, double Nc) {
 }
 
 static const char *k_names[P4B_K_NCLASSES] = {"apply_dot", "residual", "cheb_zero", "cheb_first", "cheb_next", "restrict",
-                                              "prolong_add", "axpy2", "dot2", "aypx", "resid_restrict", "xp_update", "r_update"};
+                                              "prolong_add", "axpy2", "dot2", "aypx", "resid_restrict", "xp_update", "r_update",
+                                              "halo", "gather", "allreduce", "coarse_solve", "subcycle"};
 
 // RAII-free profiling bracket: only finest-level launches are timed
 struct ProfScope {
     p4b_mg *m;
     int idx = -1;
     ProfScope(p4b_mg *mg, int level, int cls) : m(mg) {
-        if (!m->prof.on || level != m->top) return;
+        if (!m->prof.on || (m->prof.on == 1 && level != m->top)) return;
         Prof &P = m->prof;
         while (P.pool.size() < P.used + 2) {
             cudaEvent_t e;
@@ -330,6 +332,7 @@ struct ProfScope {
         }
         Prof::Rec r;
         r.cls = cls;
+        r.level = level;
         r.a = P.pool[P.used++];
         r.b = P.pool[P.used++];
         const Level &L = m->lev[level];
@@ -352,9 +355,15 @@ static void prof_collect(p4b_mg *m) {
     for (auto &r : P.recs) {
         float ms = 0;
         cudaEventElapsedTime(&ms, r.a, r.b);
-        P.stat[r.cls].launches++;
-        P.stat[r.cls].ms += ms;
-        P.stat[r.cls].bytes += r.bytes;
+        if (r.level == m->top) {
+            P.stat[r.cls].launches++;
+            P.stat[r.cls].ms += ms;
+            P.stat[r.cls].bytes += r.bytes;
+        }
+        p4b_kernel_stat &ls = P.lstat[r.level][r.cls];
+        ls.launches++;
+        ls.ms += ms;
+        ls.bytes += r.bytes;
     }
     P.recs.clear();
     P.used = 0;
@@ -367,6 +376,7 @@ static int halo(p4b_mg *m, int l, double *v) {
     if (c->nranks == 1 || L.replicated) return 0;
     const size_t plane = (size_t)L.d.plane();
     const bool lo = L.d.zs > 0, hi = L.d.zs + L.d.zm < L.d.nz;
+    ProfScope ps(m, l, P4B_K_HALO);
     if (m->peer) {
         // push my boundary planes into the neighbours' ghost planes (comm.cu)
         int slot = -1;
@@ -402,6 +412,7 @@ static int gather_replicated(p4b_mg *m, int l, double *v) {
     Level &L = m->lev[l];
     if (c->nranks == 1) return 0;
     const size_t plane = (size_t)L.d.plane();
+    ProfScope ps(m, l, P4B_K_GATHER);
     if (m->peer) {
         // replicated levels are carved first and have the same size everywhere: same arena offset on every rank
         const long long off = (long long)(v - m->arena) + (long long)L.own.zs * (long long)plane;
@@ -496,6 +507,7 @@ static int smooth(p4b_mg *m, int l, bool zero_guess, double *dot2_out = nullptr)
 
 static int coarse_solve(p4b_mg *m) {
     Level &L = m->lev[0];
+    ProfScope ps(m, 0, P4B_K_COARSE);
     return launch_dense_matvec(m->ctx->stream, m->n0, m->Ainv, L.b, L.x);
 }
 
@@ -506,7 +518,7 @@ static int cycle(p4b_mg *m, int l, bool zero_guess);
 // launches (they are timed individually by the profiler).  Needs a capturable (non-default) stream, no net
 // buffer swaps per smoother call (even -mg_levels_ksp_max_it) and kernel-only communication (peer path).
 static bool graph_usable(const p4b_mg *m) {
-    return m->o.use_graph && !m->graph_failed && m->top >= 2 && m->ctx->stream != nullptr &&
+    return m->o.use_graph && m->prof.on != 2 && !m->graph_failed && m->top >= 2 && m->ctx->stream != nullptr &&
            m->ctx->stream != cudaStreamLegacy && (m->o.smooth_its % 2 == 0) && (m->ctx->nranks == 1 || m->peer);
 }
 
@@ -575,8 +587,15 @@ static int cycle(p4b_mg *m, int l, bool zero_guess) {
     }
     const int cycles = (l == 1 || m->o.cycle == P4B_CYCLE_V) ? 1 : 2;
     for (int c = 0; c < cycles; c++) {
-        if (l == m->top && c == 0 && graph_usable(m)) P4B_CHECK(coarse_cycle_graph(m));
-        else P4B_CHECK(cycle(m, l - 1, c == 0));
+        if (l == m->top && c == 0 && graph_usable(m)) {
+            ProfScope ps(m, l, P4B_K_SUBCYCLE);
+            P4B_CHECK(coarse_cycle_graph(m));
+        } else if (l == m->top) {
+            ProfScope ps(m, l, P4B_K_SUBCYCLE);
+            P4B_CHECK(cycle(m, l - 1, c == 0));
+        } else {
+            P4B_CHECK(cycle(m, l - 1, c == 0));
+        }
     }
     P4B_CHECK(halo(m, l - 1, C.x));
     {
@@ -1269,7 +1288,10 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
     int q = 0;
     double h[2];
     P4B_CHECK(precond(S + 2 * q));
-    P4B_CHECK(ctx_allreduce(c, S + 2 * q, 2));
+    {
+        ProfScope ps(m, m->top, P4B_K_ALLREDUCE);
+        P4B_CHECK(ctx_allreduce(c, S + 2 * q, 2));
+    }
     P4B_CHECK(fetch_scal(c, S + 2 * q, 2, h));
     double dp = sqrt(h[0]);
     R.rnorm0 = dp;
@@ -1298,7 +1320,10 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
             op.mode = ST_APPLY_DOT; op.u = m->p; op.out = m->w; op.dot_out = S + 4;
             P4B_CHECK(launch_stencil(st, T.d, op, red));
         }
-        P4B_CHECK(ctx_allreduce(c, S + 4, 1));
+        {
+            ProfScope ps(m, m->top, P4B_K_ALLREDUCE);
+            P4B_CHECK(ctx_allreduce(c, S + 4, 1));
+        }
         if (m->o.fuse) {
             ProfScope ps(m, m->top, P4B_K_R_UPDATE);
             P4B_CHECK(launch_r_update(st, n, S + 2 * q + 1, S + 4, m->w, T.b));
@@ -1308,7 +1333,10 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
         }
         q ^= 1;
         P4B_CHECK(precond(S + 2 * q));
-        P4B_CHECK(ctx_allreduce(c, S + 2 * q, 2));
+        {
+            ProfScope ps(m, m->top, P4B_K_ALLREDUCE);
+            P4B_CHECK(ctx_allreduce(c, S + 2 * q, 2));
+        }
         P4B_CHECK(fetch_scal(c, S + 2 * q, 2, h));
         dp = sqrt(h[0]);
         its++;
@@ -1446,9 +1474,15 @@ int p4b_sell_destroy(p4b_sell *S) {
 }
 
 // ---- profiler -----------------------------------------------------------------------------------------
-int p4b_profile_enable(p4b_mg *m, int on) { m->prof.on = on != 0; return 0; }
+int p4b_profile_enable(p4b_mg *m, int on) { m->prof.on = on < 0 ? 0 : (on > 2 ? 2 : on); return 0; }
+int p4b_profile_get_level(p4b_mg *m, int level, int cls, p4b_kernel_stat *out) {
+    if (cls < 0 || cls >= P4B_K_NCLASSES || level < 0 || level > m->top) return fail(62, "bad level / kernel class");
+    *out = m->prof.lstat[level][cls];
+    return 0;
+}
 int p4b_profile_reset(p4b_mg *m) {
     memset(m->prof.stat, 0, sizeof m->prof.stat);
+    memset(m->prof.lstat, 0, sizeof m->prof.lstat);
     return 0;
 }
 int p4b_profile_get(p4b_mg *m, int cls, p4b_kernel_stat *out) {

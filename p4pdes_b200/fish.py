@@ -196,6 +196,7 @@ class Multigrid:
         L.check(self.lib.p4b_mg_fish_setup(self.h, L.PROBLEMS[problem], int(gonboundary), ptr(b), ptr(u0), ptr(uexact)))
 
     def profile(self, on=True):
+        """1/True: finest-level kernels; 2: trace mode (every level, every exchange, CUDA graph bypassed)."""
         L.check(self.lib.p4b_profile_enable(self.h, int(on)))
 
     def profile_reset(self):
@@ -208,6 +209,17 @@ class Multigrid:
             L.check(self.lib.p4b_profile_get(self.h, i, C.byref(s)))
             if s.launches:
                 out[name] = {"launches": s.launches, "ms": s.ms, "bytes": s.bytes}
+        return out
+
+    def profile_trace(self):
+        """{level: {class: {launches, ms, bytes}}} collected in trace mode (level 0 = coarsest)."""
+        out = {}
+        for l in range(self.nlevels):
+            for i, name in enumerate(L.KERNEL_CLASSES):
+                s = L.KernelStat()
+                L.check(self.lib.p4b_profile_get_level(self.h, l, i, C.byref(s)))
+                if s.launches:
+                    out.setdefault(l, {})[name] = {"launches": s.launches, "ms": s.ms, "bytes": s.bytes}
         return out
 
     def close(self):

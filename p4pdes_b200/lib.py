@@ -20,7 +20,10 @@ PROBLEMS = {"manupoly": 0, "manuexp": 1, "zero": 2}
 CONVERGED_RTOL, CONVERGED_ATOL, DIVERGED_ITS, DIVERGED_NAN = 2, 3, -3, -9
 REASONS = {2: "CONVERGED_RTOL", 3: "CONVERGED_ATOL", -3: "DIVERGED_ITS", -9: "DIVERGED_NANORINF"}
 KERNEL_CLASSES = ["apply_dot", "residual", "cheb_zero", "cheb_first", "cheb_next", "restrict", "prolong_add",
-                  "axpy2", "dot2", "aypx", "resid_restrict", "xp_update", "r_update"]
+                  "axpy2", "dot2", "aypx", "resid_restrict", "xp_update", "r_update",
+                  "halo", "gather", "allreduce", "coarse_solve", "subcycle"]
+# the classes after r_update are exchanges / latency items, not roofline kernels (no algorithmic bytes)
+N_ROOFLINE_CLASSES = 13
 
 
 class Grid(C.Structure):
@@ -125,6 +128,7 @@ _SIGS = {
     "p4b_profile_enable": (C.c_int, [_P, C.c_int]),
     "p4b_profile_reset": (C.c_int, [_P]),
     "p4b_profile_get": (C.c_int, [_P, C.c_int, C.POINTER(KernelStat)]),
+    "p4b_profile_get_level": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(KernelStat)]),
 }
 
 _lib = None

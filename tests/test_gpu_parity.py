@@ -73,7 +73,16 @@ def test_stencil_apply_and_residual(ctx, path, dim, m, Ls, c):
     assert relerr(dy, b - A @ u) < 1e-14
 
 
-@pytest.mark.parametrize("dim,m,Ls,c", GRIDS)
+# grids whose coarse rows are >= 64 wide take the marching restriction / 4-node prolongation kernels; ragged
+# row strips (11 = 2*4 + 3 coarse rows), fewer coarse planes than one chunk, and a chunked z range
+TRANSFER_GRIDS = GRIDS + [
+    (3, (129, 21, 13), (1, 1, 1), (1.0, 1.0, 1.0)),
+    (3, (131, 9, 37), (1.0, 0.5, 2.0), (1.0, 2.0, 0.5)),
+    (3, (257, 17, 9), (1, 1, 1), (1.0, 1.0, 1.0)),
+]
+
+
+@pytest.mark.parametrize("dim,m,Ls,c", TRANSFER_GRIDS)
 def test_transfer_matches_q1_interpolation(ctx, dim, m, Ls, c):
     og = ogrid(dim, m, Ls)
     if any((og.m[d] - 1) % 2 or og.m[d] <= 3 for d in range(dim)):
@@ -91,6 +100,13 @@ def test_transfer_matches_q1_interpolation(ctx, dim, m, Ls, c):
     dxf = dev(xf)
     ctx.prolong_add(g, dev(xc), dxf)
     assert relerr(dxf, xf + P @ xc) < 1e-14
+    # the same through vectors that start on an odd element (8-byte, not 16-byte, aligned)
+    r1 = torch.zeros(og.n + 1, dtype=torch.float64, device="cuda")
+    r1[1:] = dev(r)
+    b1 = torch.zeros(oc.n + 1, dtype=torch.float64, device="cuda")
+    ctx.restrict(g, r1[1:], b1[1:])
+    assert relerr(b1[1:], P.T @ r) < 1e-14
+    assert torch.equal(b1[1:], dbc)                       # and bit-identical to the aligned call
     # fused residual + restriction
     A = fo.jacobian(og, c)
     ctx.residual_restrict(g, dev(r), dev(xf), dbc)
