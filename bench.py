@@ -136,6 +136,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fuse", action="store_true")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="multi-GPU transport (A/B)")
+    ap.add_argument("--no-fused-halo", action="store_true", help="one push kernel per ghost exchange (A/B)")
     ap.add_argument("--no-graph", action="store_true", help="launch the coarse levels kernel by kernel (A/B)")
     ap.add_argument("--trace", default="", help="after the timed steps, run one more solve with every launch on every "
                                                 "level bracketed by CUDA events and write the table to this JSON file")
@@ -160,6 +161,7 @@ def main():
     side = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(side)
     L.tune("comm_peer", 1 if args.comm == "peer" else 0)
+    L.tune("fused_halo", 0 if args.no_fused_halo else 1)
     ctx = Context(local_rank, distributed=world > 1)
     lib = ctx.lib
 
@@ -303,7 +305,8 @@ def main():
                                "rtol 1e-10" % (m, ndof),
                    "options": OPTIONS.format(refine=refine, levels=levels), "levels": mg.nlevels,
                    "parallelism": "z-slabs x%d" % world, "transport": (args.comm if world > 1 else None), "l2": "inputs (%.2f GB per vector) exceed the 126 MB L2"
-                   % (8 * ndof / 1e9), "fused": not args.no_fuse, "cuda_graph_coarse_levels": not args.no_graph},
+                   % (8 * ndof / 1e9), "fused": not args.no_fuse, "cuda_graph_coarse_levels": not args.no_graph,
+                   "fused_halo": (not args.no_fused_halo) if world > 1 and args.comm == "peer" else None},
         "ksp_its": res.its, "ksp_reason": L.REASONS.get(res.reason), "rnorm0": res.rnorm0, "rnorm": res.rnorm,
         "errinf": errinf, "err2h": err2h,
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": table,

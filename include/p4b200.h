@@ -115,7 +115,10 @@ int p4b_device_count(int *n);
  * "march_enabled" 0|1, "march_min_plane" nodes, "march_P", "march_NT", "march_NS";
  * "rep_points": multigrid levels with at most this many nodes are replicated on every rank (default 70^3);
  * "comm_peer" 0|1 (set before p4b_comm_init): 1 = ghost planes / allreduce / gather as peer-memory kernels
- * over CUDA IPC + NVLink (default), 0 = NCCL send/recv/allreduce/broadcast */
+ * over CUDA IPC + NVLink (default), 0 = NCCL send/recv/allreduce/broadcast;
+ * "fused_halo" 0|1: 1 (default) = on the peer path a ghost exchange costs no kernel of its own: the kernel that
+ * writes a vector also stores its boundary planes into the neighbours' ghost planes and the kernel that reads them
+ * waits for the neighbours' flags; 0 = one push kernel per exchange */
 int p4b_tune(const char *key, long value);
 
 /* ---- context ---- */

@@ -51,6 +51,14 @@ __global__ void __launch_bounds__(512) halo_push_kernel(const double *lo_src, do
                                                          unsigned long long *flag_next, const unsigned long long *my_flags,
                                                          LocalSync *sync) {
     const int nb = gridDim.x, half = nb / 2;
+    // every earlier exchange has landed here, i.e. the neighbours have finished the kernels that read the ghost
+    // planes about to be overwritten (same rule as the fused HaloPort exchanges, comm.h)
+    if (threadIdx.x == 0) {
+        const unsigned long long e0 = *(volatile unsigned long long *)&sync->halo_epoch;
+        if (flag_prev) while (ld_acquire_sys(&my_flags[0]) < e0) { }
+        if (flag_next) while (ld_acquire_sys(&my_flags[1]) < e0) { }
+    }
+    __syncthreads();
     // first half of the CTAs serves the lower neighbour, second half the upper one
     if (lo_dst && (int)blockIdx.x < half)
         copy_span(lo_dst, lo_src, plane, blockIdx.x * blockDim.x + threadIdx.x, half * blockDim.x);

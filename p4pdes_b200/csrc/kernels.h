@@ -1,6 +1,7 @@
 // kernels.h -- host-side launchers of the p4b200 CUDA kernels (internal; the C ABI is p4b200.h).
 #pragma once
 #include "common.cuh"
+#include "comm.h"
 
 namespace p4b {
 
@@ -28,6 +29,7 @@ struct StencilOp {
     double *out;
     double ca, cb, cg;
     double *dot_out;      // device scalar(s) for ST_APPLY_DOT / ST_LIN_PM1_DOT2
+    HaloPort port;        // fused ghost exchange of `out` / wait for the ghosts of `u` (comm.h); zero = inactive
 };
 
 int launch_stencil(cudaStream_t st, const LevelDesc &L, const StencilOp &op, const Reducer &red);
@@ -37,8 +39,10 @@ bool stencil_fast_eligible(const LevelDesc &L);
 int tune_march(const char *key, long v);   // 0 when the key was recognised
 
 // transfer (DMDA Q1, R = P^T)
-int launch_restrict(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *rf, double *bc);
-int launch_prolong_add(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *xc, double *xf);
+int launch_restrict(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *rf, double *bc,
+                    const HaloPort &port = HaloPort());
+int launch_prolong_add(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *xc, double *xf,
+                       const HaloPort &port = HaloPort());
 
 // vector kernels (n = local length)
 int launch_dot2(cudaStream_t st, long long n, const double *x, const double *y, double *out2, const Reducer &red);
@@ -52,8 +56,9 @@ int launch_aypx_dev(cudaStream_t st, long long n, const double *num, const doubl
                     int first);
 // fused CG updates: (x += a_prev p ; p = z + b p) in one pass, r -= a w, and the final x += a p
 int launch_xp_update(cudaStream_t st, long long n, const double *an, const double *ad, const double *bn, const double *bd,
-                     const double *z, double *p, double *x, int first);
-int launch_r_update(cudaStream_t st, long long n, const double *num, const double *den, const double *w, double *r);
+                     const double *z, double *p, double *x, int first, const HaloPort &port = HaloPort());
+int launch_r_update(cudaStream_t st, long long n, const double *num, const double *den, const double *w, double *r,
+                    const HaloPort &port = HaloPort());
 int launch_x_flush(cudaStream_t st, long long n, const double *num, const double *den, const double *p, double *x);
 int launch_axpy(cudaStream_t st, long long n, double a, const double *x, double *y);
 int launch_aypx(cudaStream_t st, long long n, double a, const double *x, double *y);

@@ -286,12 +286,14 @@ struct p4b_mg {
     // peer-memory path: arenas of all ranks mapped through CUDA IPC
     bool peer = false;
     GatherTable peer_arena;
-    const double *last_halo = nullptr;
+    const double *last_halo = nullptr;     // the vector exchanged most recently (hazard tracking, comm.cu "Hazards")
+    const double *pushed = nullptr;        // the vector whose ghost planes are current (exchanged, not written since)
     bool dot2_fused = false;     // set by smooth() when the last smoother kernel also produced (z,z), (z,r)
     double *dot2_target = nullptr;
     cudaGraphExec_t coarse_graph = nullptr;   // the whole sub-cycle below the finest level, captured once
     long long graph_kernels = 0;              // kernel launches one replay stands for
     const double *graph_last_halo = nullptr;  // host-side exchange tracking as the captured sweep leaves it
+    const double *graph_pushed = nullptr;
     bool graph_failed = false;
 };
 
@@ -376,6 +378,7 @@ static int halo(p4b_mg *m, int l, double *v) {
     if (c->nranks == 1 || L.replicated) return 0;
     const size_t plane = (size_t)L.d.plane();
     const bool lo = L.d.zs > 0, hi = L.d.zs + L.d.zm < L.d.nz;
+    if (m->peer && v == m->pushed) return 0;      // the producing kernel pushed them; the consumer's port waits
     ProfScope ps(m, l, P4B_K_HALO);
     if (m->peer) {
         // push my boundary planes into the neighbours' ghost planes (comm.cu)
@@ -386,6 +389,7 @@ static int halo(p4b_mg *m, int l, double *v) {
         if (slot < 0) return fail(64, "halo: vector is not one of this level's arena buffers");
         if (v == m->last_halo) P4B_CHECK(launch_barrier(c->stream, 0, c->peers, c->sync));   // see comm.cu "Hazards"
         m->last_halo = v;
+        m->pushed = v;
         double *lo_dst = lo ? m->peer_arena.base[c->rank - 1] + L.off_prev[slot] + (size_t)L.zm_prev * plane : nullptr;
         double *hi_dst = hi ? m->peer_arena.base[c->rank + 1] + L.off_next[slot] - plane : nullptr;
         unsigned long long *fp = lo ? &c->peers.mbox[c->rank - 1]->halo_flag[1] : nullptr;
@@ -403,6 +407,46 @@ static int halo(p4b_mg *m, int l, double *v) {
         P4B_NCCL(g_nccl.Recv(v + (size_t)L.d.zm * plane, plane, ncclFloat64, c->rank + 1, c->comm, c->stream));
     }
     P4B_NCCL(g_nccl.GroupEnd());
+    return 0;
+}
+
+static long long g_fused_halo = 1;     // p4b_tune("fused_halo", 0): every exchange is a kernel of its own again (A/B)
+
+// a kernel wrote `v` without pushing its boundary planes: its ghost copies on the neighbours are stale
+static void wrote(p4b_mg *m, const double *v) {
+    if (m->pushed == v) m->pushed = nullptr;
+}
+
+// The HaloPort (comm.h) of a kernel launched on level l that writes the ghosted vector `out` (nullptr: it only
+// reads ghost planes): wait at its start, push of out's boundary planes, signal at its end.  Inactive (all zero)
+// without the peer-memory transport, on replicated levels and when out is not one of the level's arena vectors --
+// then the caller's halo() before the consumer does the exchange as a kernel of its own.
+static int make_port(p4b_mg *m, int l, double *out, HaloPort *hp) {
+    memset(hp, 0, sizeof *hp);
+    p4b_ctx *c = m->ctx;
+    Level &L = m->lev[l];
+    if (out) wrote(m, out);
+    if (!m->peer || c->nranks == 1 || L.replicated || !g_fused_halo) return 0;
+    const bool lo = L.d.zs > 0, hi = L.d.zs + L.d.zm < L.d.nz;
+    hp->sync = c->sync;
+    hp->my_flags = c->mbox->halo_flag;
+    hp->flag_lo = lo ? &c->peers.mbox[c->rank - 1]->halo_flag[1] : nullptr;
+    hp->flag_hi = hi ? &c->peers.mbox[c->rank + 1]->halo_flag[0] : nullptr;
+    const size_t plane = (size_t)L.d.plane();
+    hp->plane = (long long)plane;
+    hp->hi_start = (long long)(L.d.zm - 1) * (long long)plane;
+    if (!out) return 0;
+    int slot = -1;
+    const size_t voff = (size_t)(out - m->arena);
+    for (int q = 0; q < L.nslots; q++)
+        if (L.off_me[q] == voff) slot = q;
+    if (slot < 0) return 0;
+    if (out == m->last_halo) P4B_CHECK(launch_barrier(c->stream, 0, c->peers, c->sync));   // comm.cu "Hazards"
+    m->last_halo = out;
+    m->pushed = out;
+    hp->push = 1;
+    hp->lo_dst = lo ? m->peer_arena.base[c->rank - 1] + L.off_prev[slot] + (size_t)L.zm_prev * plane : nullptr;
+    hp->hi_dst = hi ? m->peer_arena.base[c->rank + 1] + L.off_next[slot] - plane : nullptr;
     return 0;
 }
 
@@ -432,13 +476,16 @@ static int gather_replicated(p4b_mg *m, int l, double *v) {
 }
 
 // ---- smoothers ---------------------------------------------------------------------------------
-static int smooth(p4b_mg *m, int l, bool zero_guess, double *dot2_out = nullptr) {
+static int smooth(p4b_mg *m, int l, bool zero_guess, double *dot2_out = nullptr, bool result_exchanged = true) {
     Level &L = m->lev[l];
     cudaStream_t st = m->ctx->stream;
     const Reducer &red = m->ctx->red;
     const int its = m->o.smooth_its;
     if (its <= 0) {
-        if (zero_guess) P4B_CHECK(launch_set(st, L.d.nlocal(), 0.0, L.x));
+        if (zero_guess) {
+            wrote(m, L.x);
+            P4B_CHECK(launch_set(st, L.d.nlocal(), 0.0, L.x));
+        }
         return 0;
     }
     StencilOp op;
@@ -449,11 +496,13 @@ static int smooth(p4b_mg *m, int l, bool zero_guess, double *dot2_out = nullptr)
         for (int i = 0; i < its; i++) {
             if (i == 0 && zero_guess) {
                 ProfScope ps(m, l, P4B_K_CHEB_ZERO);
+                wrote(m, L.t);
                 P4B_CHECK(launch_scale_copy(st, L.d.nlocal(), s1, L.b, L.t));
             } else {
                 P4B_CHECK(halo(m, l, L.x));
                 ProfScope ps(m, l, P4B_K_CHEB_FIRST);
                 op.mode = ST_LIN; op.u = L.x; op.b = L.b; op.out = L.t; op.cb = 1.0; op.cg = s1;
+                P4B_CHECK(make_port(m, l, L.t, &op.port));
                 P4B_CHECK(launch_stencil(st, L.d, op, red));
             }
             std::swap(L.x, L.t);
@@ -469,17 +518,20 @@ static int smooth(p4b_mg *m, int l, bool zero_guess, double *dot2_out = nullptr)
         P4B_CHECK(halo(m, l, L.b));
         ProfScope ps(m, l, P4B_K_CHEB_ZERO);
         op.mode = ST_LIN_BU; op.u = L.b; op.out = L.x; op.cb = cb; op.cg = cg;
+        P4B_CHECK(make_port(m, l, L.x, &op.port));
         return launch_stencil(st, L.d, op, red);
     }
     double *pm1 = L.x, *pk = L.t;
     bool pm1_zero = zero_guess;
     if (zero_guess) {
         ProfScope ps(m, l, P4B_K_CHEB_ZERO);
+        wrote(m, pk);
         P4B_CHECK(launch_scale_copy(st, L.d.nlocal(), s1, L.b, pk));
     } else {
         P4B_CHECK(halo(m, l, pm1));
         ProfScope ps(m, l, P4B_K_CHEB_FIRST);
         op.mode = ST_LIN; op.u = pm1; op.b = L.b; op.out = pk; op.cb = 1.0; op.cg = s1;
+        P4B_CHECK(make_port(m, l, pk, &op.port));
         P4B_CHECK(launch_stencil(st, L.d, op, red));
     }
     for (int i = 1; i < its; i++) {
@@ -495,6 +547,13 @@ static int smooth(p4b_mg *m, int l, bool zero_guess, double *dot2_out = nullptr)
                 op.mode = ST_LIN_PM1_DOT2; op.dot_out = dot2_out;
                 m->dot2_fused = true;
             }
+        }
+        // the last iterate's ghost planes are not needed when nothing applies the operator to it next
+        if (i == its - 1 && !result_exchanged) {
+            P4B_CHECK(make_port(m, l, nullptr, &op.port));
+            wrote(m, pm1);
+        } else {
+            P4B_CHECK(make_port(m, l, pm1, &op.port));
         }
         P4B_CHECK(launch_stencil(st, L.d, op, red));
         std::swap(pm1, pk);
@@ -544,6 +603,7 @@ static int coarse_cycle_graph(p4b_mg *m) {
         m->graph_kernels = g_launch_count - before;
         g_launch_count = before;
         m->graph_last_halo = m->last_halo;
+        m->graph_pushed = m->pushed;
         const cudaError_t e2 = cudaGraphInstantiate(&m->coarse_graph, graph, 0);
         cudaGraphDestroy(graph);
         if (e2 != cudaSuccess) {
@@ -556,6 +616,7 @@ static int coarse_cycle_graph(p4b_mg *m) {
     P4B_CUDA(cudaGraphLaunch(m->coarse_graph, st));
     g_launch_count += m->graph_kernels;
     m->last_halo = m->graph_last_halo;
+    m->pushed = m->graph_pushed;
     return 0;
 }
 
@@ -573,6 +634,7 @@ static int cycle(p4b_mg *m, int l, bool zero_guess) {
             StencilOp op;
             memset(&op, 0, sizeof op);
             op.mode = ST_LIN; op.u = L.x; op.b = L.b; op.out = L.t; op.cb = 0.0; op.cg = 1.0;
+            P4B_CHECK(make_port(m, l, L.t, &op.port));
             P4B_CHECK(launch_stencil(st, L.d, op, red));
         }
         P4B_CHECK(halo(m, l, L.t));
@@ -581,7 +643,14 @@ static int cycle(p4b_mg *m, int l, bool zero_guess) {
         double *bc = boundary ? C.b + (size_t)C.own.zs * C.d.plane() : C.b;
         {
             ProfScope ps(m, l, P4B_K_RESTRICT);
-            P4B_CHECK(launch_restrict(st, L.d, Cd, L.t, bc));
+            HaloPort port;
+            if (!L.replicated && !C.replicated) {
+                P4B_CHECK(make_port(m, l - 1, C.b, &port));      // the coarse right-hand side is exchanged next
+            } else {
+                P4B_CHECK(make_port(m, l, nullptr, &port));      // only waits for the ghost planes of t
+                wrote(m, C.b);
+            }
+            P4B_CHECK(launch_restrict(st, L.d, Cd, L.t, bc, port));
         }
         if (boundary) P4B_CHECK(gather_replicated(m, l - 1, C.b));
     }
@@ -600,9 +669,12 @@ static int cycle(p4b_mg *m, int l, bool zero_guess) {
     P4B_CHECK(halo(m, l - 1, C.x));
     {
         ProfScope ps(m, l, P4B_K_PROLONG);
-        P4B_CHECK(launch_prolong_add(st, L.d, C.d, C.x, L.x));
+        HaloPort port;
+        P4B_CHECK(make_port(m, l, L.x, &port));
+        P4B_CHECK(launch_prolong_add(st, L.d, C.d, C.x, L.x, port));
     }
-    return smooth(m, l, false, (l == m->top && m->o.fuse) ? m->dot2_target : nullptr);
+    // z = M^-1 r on the finest level feeds vector updates only: its ghost planes are not exchanged
+    return smooth(m, l, false, (l == m->top && m->o.fuse) ? m->dot2_target : nullptr, l != m->top);
 }
 
 // z = M^-1 r with r already in lev[top].b ; result in lev[top].x.  With dot2 != NULL (and fused kernels on)
@@ -760,6 +832,7 @@ int p4b_tune(const char *key, long value) {
     if (tune_march(key, value) == 0) return 0;
     if (std::string(key) == "rep_points") { g_rep_points = value; return 0; }
     if (std::string(key) == "comm_peer") { g_comm_peer = value; return 0; }
+    if (std::string(key) == "fused_halo") { g_fused_halo = value; return 0; }
     return fail(62, "unknown tuning key %s", key);
 }
 
@@ -1236,6 +1309,7 @@ int p4b_mg_matmult(p4b_mg *m, const double *x, double *y) {
     Level &T = m->lev[m->top];
     cudaStream_t st = m->ctx->stream;
     const size_t bytes = sizeof(double) * (size_t)T.d.nlocal();
+    m->pushed = nullptr;
     P4B_CUDA(cudaMemcpyAsync(m->p, x, bytes, cudaMemcpyDeviceToDevice, st));
     P4B_CHECK(halo(m, m->top, m->p));
     StencilOp op;
@@ -1250,6 +1324,7 @@ int p4b_mg_apply(p4b_mg *m, const double *r, double *z) {
     Level &T = m->lev[m->top];
     cudaStream_t st = m->ctx->stream;
     const size_t bytes = sizeof(double) * (size_t)T.d.nlocal();
+    m->pushed = nullptr;
     P4B_CUDA(cudaMemcpyAsync(T.b, r, bytes, cudaMemcpyDeviceToDevice, st));
     P4B_CHECK(mg_apply_internal(m));
     P4B_CUDA(cudaMemcpyAsync(z, T.x, bytes, cudaMemcpyDeviceToDevice, st));
@@ -1272,6 +1347,7 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
         return fail(62, "unknown pc_type %d (the device path provides none, jacobi, mg)", pc_type);
     P4B_CUDA(cudaSetDevice(c->device));
     P4B_CUDA(cudaEventRecord(c->ev0, st));
+    m->pushed = nullptr;
     P4B_CUDA(cudaMemcpyAsync(T.b, b, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     P4B_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * n, st));
     // z = M^-1 r and the CG scalars (z,z), (z,r) -> dots
@@ -1306,10 +1382,13 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
         if (m->o.fuse) {
             // x += alpha_{k-1} p (deferred from the previous iteration) and p = z + beta p in one pass over p
             ProfScope ps(m, m->top, P4B_K_XP_UPDATE);
+            HaloPort port;
+            P4B_CHECK(make_port(m, m->top, m->p, &port));
             P4B_CHECK(launch_xp_update(st, n, S + 2 * (1 - q) + 1, S + 4, S + 2 * q + 1, S + 2 * (1 - q) + 1, T.x, m->p, x,
-                                       its == 0));
+                                       its == 0, port));
         } else {
             ProfScope ps(m, m->top, P4B_K_AYPX);
+            wrote(m, m->p);
             P4B_CHECK(launch_aypx_dev(st, n, S + 2 * q + 1, S + 2 * (1 - q) + 1, T.x, m->p, its == 0));
         }
         P4B_CHECK(halo(m, m->top, m->p));
@@ -1318,6 +1397,8 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
             StencilOp op;
             memset(&op, 0, sizeof op);
             op.mode = ST_APPLY_DOT; op.u = m->p; op.out = m->w; op.dot_out = S + 4;
+            P4B_CHECK(make_port(m, m->top, nullptr, &op.port));
+            wrote(m, m->w);
             P4B_CHECK(launch_stencil(st, T.d, op, red));
         }
         {
@@ -1326,9 +1407,12 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
         }
         if (m->o.fuse) {
             ProfScope ps(m, m->top, P4B_K_R_UPDATE);
-            P4B_CHECK(launch_r_update(st, n, S + 2 * q + 1, S + 4, m->w, T.b));
+            HaloPort port;
+            P4B_CHECK(make_port(m, m->top, T.b, &port));
+            P4B_CHECK(launch_r_update(st, n, S + 2 * q + 1, S + 4, m->w, T.b, port));
         } else {
             ProfScope ps(m, m->top, P4B_K_AXPY2);
+            wrote(m, T.b);
             P4B_CHECK(launch_axpy2(st, n, S + 2 * q + 1, S + 4, m->p, m->w, x, T.b));
         }
         q ^= 1;
@@ -1382,6 +1466,7 @@ int p4b_fish_solve_host(p4b_mg *m, const double *fh, const double *gh, double *u
     P4B_CUDA(cudaMemcpyAsync(m->fbuf, fh, bytes, cudaMemcpyHostToDevice, st));
     P4B_CUDA(cudaMemcpyAsync(m->gbuf, gh, bytes, cudaMemcpyHostToDevice, st));
     P4B_CUDA(cudaMemcpyAsync(m->w, uh, bytes, cudaMemcpyHostToDevice, st));
+    m->pushed = nullptr;
     P4B_CHECK(halo(m, m->top, m->w));
     P4B_CHECK(halo(m, m->top, m->gbuf));
     P4B_CHECK(launch_poisson_function(st, T.d, T.g.dim, T.g.cx, m->w, m->fbuf, m->gbuf, m->p));
@@ -1410,6 +1495,7 @@ int p4b_mg_fish_setup(p4b_mg *m, int problem, int gonboundary, double *b_out, do
         return fail(3, "cx=cy=cz=1 required for problem MANUEXP");
     P4B_CHECK(launch_fish_sample(st, T.d, T.g.dim, problem, T.g.cx, T.g.cy, T.g.cz, m->fbuf, m->gbuf));
     P4B_CHECK(launch_initial_state(st, T.d, m->gbuf, gonboundary, m->w));
+    m->pushed = nullptr;
     P4B_CHECK(halo(m, m->top, m->w));
     P4B_CHECK(halo(m, m->top, m->gbuf));
     P4B_CHECK(launch_poisson_function(st, T.d, T.g.dim, T.g.cx, m->w, m->fbuf, m->gbuf, m->p));

@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const LevelDesc L,
     const long long nloc = L.nlocal();
     const long long n = (long long)blockIdx.x * 256 + threadIdx.x;
     double dv[2] = {0.0, 0.0};
+    const PortSpan span = port_span_linear(op.port, (long long)L.nx * L.ny, nloc, 256);
+    port_wait(op.port, span.boundary);
     if (n < nloc) {
         const int plane = L.nx * L.ny;
         const int kl = (int)(n / plane);
@@ -63,7 +65,9 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const LevelDesc L,
             if (MODE == ST_LIN_PM1_DOT2) { dv[0] = o * o; dv[1] = o * bv; }
         }
         op.out[n] = o;
+        port_store(op.port, n, o);
     }
+    port_signal(op.port, span.boundary, span.nboundary);
     if (MODE == ST_APPLY_DOT) {
         double d1[1] = {dv[0]};
         grid_sum_finalize<1, 256>(d1, partials, ticket, op.dot_out);

@@ -98,6 +98,10 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // CTAs of the first / last chunk read u's ghost plane and push out's boundary plane
+    const bool port_cta = op.port.sync != nullptr && ((blockIdx.y == 0 && op.port.flag_lo != nullptr) ||
+                                                      (blockIdx.y == gridDim.y - 1 && op.port.flag_hi != nullptr));
+    port_wait(op.port, port_cta);
 
     // plane t of this chunk is local plane kl = k0 - 1 + t, t = 0 .. T-1 (one extra plane on each side)
     const int T = (k1 - k0) + 2;
@@ -232,6 +236,9 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
         if (t >= 1) {
             const double *st = stages + (size_t)slot_c * SD + adj_c;
             const bool kbd = (kg == 0 || kg == L.nz - 1);
+            // first / last owned plane of the slab: the value also goes into the neighbour's ghost plane
+            const bool push_lo = op.port.lo_dst != nullptr && kg == L.zs;
+            const bool push_hi = op.port.hi_dst != nullptr && kg == L.zs + L.zm - 1;
             const double czd = (kg - 1 > 0) ? cz : 0.0, czu = (kg + 1 < L.nz - 1) ? cz : 0.0;
 #pragma unroll
             for (int p = 0; p < P; p++) {
@@ -257,7 +264,11 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
                         dv[1] += o * bq[p];
                     }
                 }
-                if (mask[p] & MK_VALID) outp[gi[p]] = o;
+                if (mask[p] & MK_VALID) {
+                    outp[gi[p]] = o;
+                    if (push_lo) op.port.lo_dst[q0 + tid + gi[p]] = o;
+                    if (push_hi) op.port.hi_dst[q0 + tid + gi[p]] = o;
+                }
             }
         }
         __syncthreads();                       // everyone is done with slot_c (and with plane 0 at t = 0)
@@ -277,6 +288,8 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
             }
         }
     }
+    port_signal(op.port, port_cta,
+                gridDim.x * (gridDim.y == 1 ? 1u : (op.port.flag_lo != nullptr) + (op.port.flag_hi != nullptr)));
     if (MODE == ST_APPLY_DOT || MODE == ST_LIN_PM1_DOT2) {
         // one partial (per value) per CTA, summed in fixed order by the last CTA to finish
         constexpr int NV = (MODE == ST_LIN_PM1_DOT2) ? 2 : 1;

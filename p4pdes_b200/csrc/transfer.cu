@@ -11,9 +11,12 @@ namespace p4b {
 // b_c(I,J,K) = sum_{d in {-1,0,1}^3} w(di) w(dj) w(dk) r(2I+di, 2J+dj, 2K+dk),  w(0)=1, w(+-1)=1/2,
 // fine indices outside the grid skipped; inactive slots contribute offset 0 only.
 __global__ void __launch_bounds__(256) restrict_kernel(const LevelDesc F, const LevelDesc C,
-                                                        const double *__restrict__ rf, double *__restrict__ bc) {
+                                                        const double *__restrict__ rf, double *__restrict__ bc,
+                                                        const HaloPort port) {
     const long long n = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (n >= C.nlocal()) return;
+    const PortSpan span = port_span_linear(port, C.plane(), C.nlocal(), 256);
+    port_wait(port, span.boundary);
+    if (n < C.nlocal()) {
     const int cplane = C.nx * C.ny;
     const int Kl = (int)(n / cplane);
     const int rem = (int)(n - (long long)Kl * cplane);
@@ -46,13 +49,19 @@ __global__ void __launch_bounds__(256) restrict_kernel(const LevelDesc F, const 
         s += wk * sk;
     }
     bc[n] = s;
+    port_store(port, n, s);
+    }
+    port_signal(port, span.boundary, span.nboundary);
 }
 
 // x_f(i,j,k) += sum over the (<= 8) coarse parents of their Q1 weights times x_c.
 __global__ void __launch_bounds__(256) prolong_add_kernel(const LevelDesc F, const LevelDesc C,
-                                                           const double *__restrict__ xc, double *__restrict__ xf) {
+                                                           const double *__restrict__ xc, double *__restrict__ xf,
+                                                           const HaloPort port) {
     const long long n = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (n >= F.nlocal()) return;
+    const PortSpan span = port_span_linear(port, F.plane(), F.nlocal(), 256);
+    port_wait(port, span.boundary);
+    if (n < F.nlocal()) {
     const int fplane = F.nx * F.ny;
     const int kl = (int)(n / fplane);
     const int rem = (int)(n - (long long)kl * fplane);
@@ -77,7 +86,11 @@ __global__ void __launch_bounds__(256) prolong_add_kernel(const LevelDesc F, con
         s += sk;
     }
     if (ok) s *= 0.5;
-    xf[n] += s;
+    const double v = xf[n] + s;
+    xf[n] = v;
+    port_store(port, n, v);
+    }
+    port_signal(port, span.boundary, span.nboundary);
 }
 
 // 3-D fast path.  One thread per (i, J, K): it interpolates the x direction once per coarse row
@@ -85,9 +98,15 @@ __global__ void __launch_bounds__(256) prolong_add_kernel(const LevelDesc F, con
 // nodes (i, 2J+{0,1}, 2K+{0,1}): 8 coarse loads (L1/L2 hits, neighbouring lanes share them) per 4 fine
 // nodes instead of up to 8 per node, fine accesses fully coalesced, one index division per 4 nodes.
 __global__ void __launch_bounds__(256) prolong_add3d_kernel(const LevelDesc F, const LevelDesc C, int Kfirst,
-                                                            const double *__restrict__ xc, double *__restrict__ xf) {
+                                                            const double *__restrict__ xc, double *__restrict__ xf,
+                                                            const HaloPort port) {
     const int task = blockIdx.x * 256 + threadIdx.x;       // over nx * cny
-    if (task >= F.nx * C.ny) return;
+    // the first / last coarse plane of the range are the ones that may be a neighbour's (coarse ghost read) and
+    // hold the first / last owned fine plane (pushed)
+    const bool port_cta = port.sync != nullptr && ((blockIdx.y == 0 && port.flag_lo != nullptr) ||
+                                                   (blockIdx.y == gridDim.y - 1 && port.flag_hi != nullptr));
+    port_wait(port, port_cta);
+    if (task < F.nx * C.ny) {
     const int J = task / F.nx, i = task - J * F.nx;
     const int K = Kfirst + blockIdx.y;
     const int I0 = i >> 1, I1 = I0 + (i & 1);
@@ -120,12 +139,18 @@ __global__ void __launch_bounds__(256) prolong_add3d_kernel(const LevelDesc F, c
     for (int c = 0; c < 2; c++) {
         if (!own[c]) continue;
         const double e0 = c ? 0.5 * (a00 + a01) : a00;
-        row[c][0] = f[c][0] + e0;
+        const double v0 = f[c][0] + e0;
+        row[c][0] = v0;
+        port_store(port, row[c] - xf, v0);
         if (jok) {
             const double e1 = c ? 0.25 * ((a00 + a10) + (a01 + a11)) : 0.5 * (a00 + a10);
-            row[c][F.nx] = f[c][1] + e1;
+            const double v1 = f[c][1] + e1;
+            row[c][F.nx] = v1;
+            port_store(port, row[c] + F.nx - xf, v1);
         }
     }
+    }
+    port_signal(port, port_cta, gridDim.x * (gridDim.y == 1 ? 1u : (port.flag_lo != nullptr) + (port.flag_hi != nullptr)));
 }
 
 // 3-D fast path of the restriction.  One thread per coarse column I and strip of TJ coarse rows; it marches a
@@ -193,13 +218,18 @@ __device__ __forceinline__ void restrict_plane(const LevelDesc &F, const double 
 
 template <int TJ>
 __global__ void __launch_bounds__(128) restrict3d_kernel(const LevelDesc F, const LevelDesc C, int KC,
-                                                          const double *__restrict__ rf, double *__restrict__ bc) {
+                                                          const double *__restrict__ rf, double *__restrict__ bc,
+                                                          const HaloPort port) {
     const int I = blockIdx.x * 128 + threadIdx.x;
+    // the first / last chunk of coarse planes read the fine ghost planes and hold the coarse boundary planes (pushed)
+    const bool port_cta = port.sync != nullptr && ((blockIdx.z == 0 && port.flag_lo != nullptr) ||
+                                                   (blockIdx.z == gridDim.z - 1 && port.flag_hi != nullptr));
+    port_wait(port, port_cta);
     const int J0 = TJ * blockIdx.y;
     const int Kb = C.zs + KC * blockIdx.z;                       // first coarse plane of this chunk
     const int Ke = min(Kb + KC, C.zs + C.zm);
     const int lane = threadIdx.x & 31;
-    if ((I & ~31) >= C.nx) return;                               // whole warp beyond the row
+    const bool warp_live = (I & ~31) < C.nx;                     // false: whole warp beyond the row
     const bool live = I < C.nx;
     const int fi = 2 * I;
     const int vparity = (int)(((uintptr_t)rf >> 3) & 1);
@@ -208,8 +238,8 @@ __global__ void __launch_bounds__(128) restrict3d_kernel(const LevelDesc F, cons
     double Pm[TJ], Pc[TJ], Pp[TJ];
 #pragma unroll
     for (int jj = 0; jj < TJ; jj++) Pm[jj] = 0.0;
-    if (plane_ok(2 * Kb - 1)) restrict_plane<TJ>(F, rf, 2 * Kb - 1, J0, fi, live, lane, vparity, Pm);
-    for (int K = Kb; K < Ke; K++) {
+    if (warp_live && plane_ok(2 * Kb - 1)) restrict_plane<TJ>(F, rf, 2 * Kb - 1, J0, fi, live, lane, vparity, Pm);
+    for (int K = Kb; K < Ke && warp_live; K++) {
         restrict_plane<TJ>(F, rf, 2 * K, J0, fi, live, lane, vparity, Pc);
         if (plane_ok(2 * K + 1)) {
             restrict_plane<TJ>(F, rf, 2 * K + 1, J0, fi, live, lane, vparity, Pp);
@@ -221,40 +251,48 @@ __global__ void __launch_bounds__(128) restrict3d_kernel(const LevelDesc F, cons
             double *out = bc + (long long)(K - C.zs) * cplane + (long long)J0 * C.nx + I;
 #pragma unroll
             for (int jj = 0; jj < TJ; jj++)
-                if (J0 + jj < C.ny) out[(long long)jj * C.nx] = Pc[jj] + 0.5 * (Pm[jj] + Pp[jj]);
+                if (J0 + jj < C.ny) {
+                    const double v = Pc[jj] + 0.5 * (Pm[jj] + Pp[jj]);
+                    out[(long long)jj * C.nx] = v;
+                    port_store(port, (out - bc) + (long long)jj * C.nx, v);
+                }
         }
 #pragma unroll
         for (int jj = 0; jj < TJ; jj++) Pm[jj] = Pp[jj];
     }
+    port_signal(port, port_cta, gridDim.x * gridDim.y *
+                                    (gridDim.z == 1 ? 1u : (port.flag_lo != nullptr) + (port.flag_hi != nullptr)));
 }
 
-int launch_restrict(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *rf, double *bc) {
+int launch_restrict(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *rf, double *bc,
+                    const HaloPort &port) {
     const long long n = C.nlocal();
     if (n <= 0) return 0;
     if (F.ax && F.ay && F.az && C.nx >= 64 && (((uintptr_t)rf) & 7) == 0) {
         constexpr int TJ = 4;
         const int KC = 8;
         dim3 grid((unsigned)((C.nx + 127) / 128), (unsigned)((C.ny + TJ - 1) / TJ), (unsigned)((C.zm + KC - 1) / KC));
-        restrict3d_kernel<TJ><<<grid, 128, 0, st>>>(F, C, KC, rf, bc);
+        restrict3d_kernel<TJ><<<grid, 128, 0, st>>>(F, C, KC, rf, bc, port);
         P4B_LAUNCH_CHECK();
         return 0;
     }
-    restrict_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(F, C, rf, bc);
+    restrict_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(F, C, rf, bc, port);
     P4B_LAUNCH_CHECK();
     return 0;
 }
 
-int launch_prolong_add(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *xc, double *xf) {
+int launch_prolong_add(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *xc, double *xf,
+                       const HaloPort &port) {
     const long long n = F.nlocal();
     if (n <= 0) return 0;
     if (F.ax && F.ay && F.az && F.nx >= 64 && (long long)F.nx * C.ny < (1LL << 30)) {
         const int Kfirst = F.zs / 2, Klast = (F.zs + F.zm - 1) / 2;
         dim3 grid((unsigned)(((long long)F.nx * C.ny + 255) / 256), (unsigned)(Klast - Kfirst + 1));
-        prolong_add3d_kernel<<<grid, 256, 0, st>>>(F, C, Kfirst, xc, xf);
+        prolong_add3d_kernel<<<grid, 256, 0, st>>>(F, C, Kfirst, xc, xf, port);
         P4B_LAUNCH_CHECK();
         return 0;
     }
-    prolong_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(F, C, xc, xf);
+    prolong_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(F, C, xc, xf, port);
     P4B_LAUNCH_CHECK();
     return 0;
 }

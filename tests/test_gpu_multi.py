@@ -46,3 +46,25 @@ def test_slab_solve_matches_oracle(nproc, args):
     assert r["hist_rel"] is not None and r["hist_rel"] < 1e-10
     assert r["sol_rel"] < 1e-12
     assert r["bnorm_rel"] < 1e-13
+
+
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+@pytest.mark.parametrize("args", [
+    ("--refine", 6, "--rtol", 1e-10, "--levels", 5, "--march-min-plane", 1, "--repeat", 3),
+    ("--refine", 5, "--rtol", 1e-10, "--rep-points", 1, "--repeat", 2),      # small distributed levels: generic kernels
+    ("--refine", 5, "--rtol", 1e-8, "--cycle", "w", "--rep-points", 1),
+])
+def test_fused_exchange_is_bit_identical_to_push_kernels(nproc, args):
+    """Ghost planes pushed by the producing kernel and awaited by the consuming kernel (comm.h HaloPort) must give the
+    same bits as one exchange kernel per halo, and as the NCCL send/recv transport."""
+    if ngpu() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
+    fused = run_worker(nproc, *args, "--fused-halo", 1, "--no-oracle")
+    plain = run_worker(nproc, *args, "--fused-halo", 0, "--no-oracle")
+    nccl = run_worker(nproc, *args, "--comm-peer", 0, "--no-oracle")
+    assert fused["its"] == plain["its"] == nccl["its"]
+    assert fused["history"] == plain["history"]
+    assert fused["sol_sha1"] == plain["sol_sha1"]
+    if nproc == 2:       # a two-term sum has one rounding whatever the allreduce algorithm
+        assert fused["history"] == nccl["history"]
+        assert fused["sol_sha1"] == nccl["sol_sha1"]
