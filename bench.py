@@ -15,6 +15,7 @@ the total problem is fixed), ghost planes and dot products go over NCCL.
 --impl reference: the CPU restatement of the same algorithm (oracle/) on the host cores.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -137,6 +138,8 @@ def main():
     ap.add_argument("--no-fuse", action="store_true")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="multi-GPU transport (A/B)")
     ap.add_argument("--no-fused-halo", action="store_true", help="one push kernel per ghost exchange (A/B)")
+    ap.add_argument("--force-mg", type=int, default=0, help="run the multi-GPU kernel variants on one GPU (A/B)")
+    ap.add_argument("--port-opts", type=int, default=0, help="HaloPort experiments (p4b_tune port_opts)")
     ap.add_argument("--no-graph", action="store_true", help="launch the coarse levels kernel by kernel (A/B)")
     ap.add_argument("--trace", default="", help="after the timed steps, run one more solve with every launch on every "
                                                 "level bracketed by CUDA events and write the table to this JSON file")
@@ -162,6 +165,8 @@ def main():
     torch.cuda.set_stream(side)
     L.tune("comm_peer", 1 if args.comm == "peer" else 0)
     L.tune("fused_halo", 0 if args.no_fused_halo else 1)
+    L.tune("port_opts", args.port_opts)
+    L.tune("force_mg", args.force_mg)
     ctx = Context(local_rank, distributed=world > 1)
     lib = ctx.lib
 
@@ -214,6 +219,10 @@ def main():
     ms_step = ms_total / args.steps
     stats = mg.profile_stats()
     mg.profile(False)
+    cs = (C.c_ulonglong * 5)()
+    lib.p4b_comm_stats(ctx.h, C.byref(cs), 1)
+    comm_stats = {"waits": cs[0], "wait_ms": cs[1] / 1e6, "wait_max_us": cs[2] / 1e3, "fences": cs[3],
+                  "fence_ms": cs[4] / 1e6, "note": "sums over boundary CTAs (rank 0), all warm-up + timed steps"}
     exchange = {k: stats.pop(k) for k in L.KERNEL_CLASSES[L.N_ROOFLINE_CLASSES:] if k in stats}
     if args.trace:
         mg.profile(2)
@@ -311,6 +320,7 @@ def main():
         "errinf": errinf, "err2h": err2h,
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": table,
         "exchange_ms_per_step": {k: v["ms"] / args.steps for k, v in exchange.items()},
+        "comm_stats": comm_stats,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

@@ -131,6 +131,10 @@ int p4b_ctx_sync(p4b_ctx *ctx);
  * in this repo), every rank calls p4b_comm_init.  Halo planes and dot products then go over NCCL. */
 int p4b_comm_unique_id(void *id128);
 int p4b_comm_init(p4b_ctx *ctx, const void *id128, int rank, int nranks);
+/* exchange statistics of the fused ghost exchange since the last reset (reset != 0 clears them after reading):
+ * out[0] = boundary-CTA waits, out[1] = their summed spin time (ns), out[2] = the longest single wait (ns),
+ * out[3] = system-scope fences that published peer stores, out[4] = their summed time (ns) */
+int p4b_comm_stats(p4b_ctx *ctx, unsigned long long out[5], int reset);
 /* DMDA-style ownership of the slowest dimension: the first (m % nranks) ranks own one more plane. */
 int p4b_slab_range(int m, int nranks, int rank, int *start, int *count);
 

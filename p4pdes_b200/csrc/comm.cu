@@ -136,6 +136,15 @@ __global__ void __launch_bounds__(512) gather_push_kernel(const double *src, lon
     __threadfence_system();
 }
 
+__global__ void __launch_bounds__(32) port_wait_kernel(const HaloPort port) { port_wait(port, true); }
+
+int launch_port_wait(cudaStream_t st, const HaloPort &port) {
+    if (!port.sync) return 0;
+    port_wait_kernel<<<1, 32, 0, st>>>(port);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_halo_push(cudaStream_t st, const double *lo_src, double *lo_dst, const double *hi_src, double *hi_dst,
                      long long plane, unsigned long long *flag_prev, unsigned long long *flag_next,
                      const unsigned long long *my_flags, LocalSync *sync) {

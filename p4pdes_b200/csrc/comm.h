@@ -23,6 +23,9 @@ struct LocalSync {
     unsigned long long halo_epoch, bar_epoch, red_epoch;
     unsigned int done;
     unsigned int pdone;      // CTAs of the running kernel that have finished their fused push (HaloPort)
+    // exchange statistics (p4b_comm_stats): what the boundary CTAs spent spinning on the neighbours' flags and in the
+    // system-scope fence that publishes their peer stores; sums over CTAs of %globaltimer nanoseconds
+    unsigned long long wait_ns, wait_n, fence_ns, fence_n, wait_max_ns;
 };
 
 struct PeerTable {
@@ -56,9 +59,18 @@ struct HaloPort {
     long long plane;                            // doubles per plane of that vector
     long long hi_start;                         // local index of the first element of its last owned plane
     int push;                                   // 1 = this kernel pushes and advances the exchange count
+    int opts;                                   // experiments (p4b_tune "port_opts"): 1 = keep the natural chunk order
+                                                // and direction, 2 = signal at the end of the boundary CTAs' work
 };
 
 #ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long port_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// release-pattern fence at system scope (lighter than __threadfence_system(), which is fence.sc.sys)
+__device__ __forceinline__ void port_fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ void port_st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -73,10 +85,15 @@ __device__ __forceinline__ unsigned long long port_ld_acquire_sys(const unsigned
 __device__ __forceinline__ void port_wait(const HaloPort &hp, bool boundary) {
     if (!hp.sync || !boundary) return;
     if (threadIdx.x == 0) {
+        const unsigned long long t0 = port_now_ns();
         const unsigned long long e = *(volatile unsigned long long *)&hp.sync->halo_epoch;
         if (hp.flag_lo) while (port_ld_acquire_sys(&hp.my_flags[0]) < e) { }
         if (hp.flag_hi) while (port_ld_acquire_sys(&hp.my_flags[1]) < e) { }
         asm volatile("fence.proxy.async;" ::: "memory");     // ghost planes may be read by bulk (TMA) copies
+        const unsigned long long dt = port_now_ns() - t0;
+        atomicAdd(&hp.sync->wait_ns, dt);
+        atomicAdd(&hp.sync->wait_n, 1ull);
+        atomicMax(&hp.sync->wait_max_ns, dt);
     }
     __syncthreads();
 }
@@ -93,9 +110,15 @@ __device__ __forceinline__ void port_signal(const HaloPort &hp, bool boundary, u
     if (!hp.sync || !hp.push || !boundary) return;
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (stored) __threadfence_system();
+        if (stored) {
+            const unsigned long long t0 = port_now_ns();
+            port_fence_sys();
+            atomicAdd(&hp.sync->fence_ns, port_now_ns() - t0);
+            atomicAdd(&hp.sync->fence_n, 1ull);
+        }
         if (atomicAdd(&hp.sync->pdone, 1u) == nboundary - 1u) {
-            __threadfence_system();
+            // (the release stores below carry the fence that orders the other CTAs' pushes, observed through
+            // the counter, before the flags)
             const unsigned long long e = hp.sync->halo_epoch + 1ull;
             if (hp.flag_lo) port_st_release_sys(hp.flag_lo, e);
             if (hp.flag_hi) port_st_release_sys(hp.flag_hi, e);
@@ -104,6 +127,46 @@ __device__ __forceinline__ void port_signal(const HaloPort &hp, bool boundary, u
             __threadfence();
         }
     }
+}
+// The same for a caller that has just passed a __syncthreads() after its last peer store: `elected` is true in
+// exactly one thread of the CTA.
+__device__ __forceinline__ void port_signal_nosync(const HaloPort &hp, unsigned int nboundary, bool elected) {
+    if (!hp.sync || !hp.push || !elected) return;
+    const unsigned long long t0 = port_now_ns();
+    port_fence_sys();
+    atomicAdd(&hp.sync->fence_ns, port_now_ns() - t0);
+    atomicAdd(&hp.sync->fence_n, 1ull);
+    if (atomicAdd(&hp.sync->pdone, 1u) == nboundary - 1u) {
+        const unsigned long long e = hp.sync->halo_epoch + 1ull;
+        if (hp.flag_lo) port_st_release_sys(hp.flag_lo, e);
+        if (hp.flag_hi) port_st_release_sys(hp.flag_hi, e);
+        hp.sync->halo_epoch = e;
+        hp.sync->pdone = 0u;
+        __threadfence();
+    }
+}
+// Launch-order remap of a block index that runs over planes / chunks of the slab: with an upper neighbour the block
+// that holds the LAST plane is scheduled second, so both boundary planes are produced (and signalled) first.
+__device__ __forceinline__ unsigned int port_remap(const HaloPort &hp, unsigned int b, unsigned int nb) {
+    if (!hp.sync || !hp.flag_hi || nb < 2u || (hp.opts & 1)) return b;
+    return b == 0u ? 0u : (b == 1u ? nb - 1u : b - 1u);
+}
+// Grid-stride elementwise kernels: the slab is cut into segments of W elements and CTA b takes the logical segments
+// b, b + G, b + 2G, ...  Logical segment g is the physical segment seg_phys(g): the segments of the last plane come
+// first, then those of the first plane, then the interior -- so the boundary planes are written in the first pass
+// and can be signalled while the rest of the vector is still being streamed.
+struct SegRot {
+    long long S, H, NB;       // segments, segments of the last plane rotated to the front, boundary segments
+    __device__ __forceinline__ long long phys(long long g) const { return g < H ? S - H + g : g - H; }
+};
+__device__ __forceinline__ SegRot seg_rot(const HaloPort &hp, long long n, long long W) {
+    SegRot r;
+    r.S = (n + W - 1) / W;
+    const bool on = hp.sync != nullptr && hp.push;
+    r.H = (on && hp.flag_hi) ? r.S - hp.hi_start / W : 0;
+    const long long A = (on && hp.flag_lo) ? min((hp.plane + W - 1) / W, r.S) : 0;
+    r.NB = min(r.S, r.H + A);
+    return r;
 }
 // Boundary CTAs of a kernel whose CTA b owns the `per` consecutive elements starting at b * per (one pass, no grid
 // stride) of a slab of n elements: those that touch the first plane (when there is a lower neighbour) or the last.
@@ -121,6 +184,8 @@ __device__ __forceinline__ PortSpan port_span_linear(const HaloPort &hp, long lo
 }
 #endif
 
+// one-thread kernel that only waits for the neighbours' flags (for consumers that do not carry a HaloPort themselves)
+int launch_port_wait(cudaStream_t st, const HaloPort &port);
 int launch_halo_push(cudaStream_t st, const double *lo_src, double *lo_dst, const double *hi_src, double *hi_dst,
                      long long plane, unsigned long long *flag_prev, unsigned long long *flag_next,
                      const unsigned long long *my_flags, LocalSync *sync);

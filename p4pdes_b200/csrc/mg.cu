@@ -19,6 +19,7 @@
 #include <array>
 
 #include "comm.h"
+#include <cstddef>
 #include "kernels.h"
 
 namespace p4b {
@@ -118,6 +119,10 @@ struct p4b_ctx {
     Mailbox *mbox = nullptr;
     LocalSync *sync = nullptr;
     PeerTable peers;
+    // p4b_tune("force_mg"): single-GPU stand-ins for the neighbours (kernel A/B measurements only)
+    double *dummy_planes = nullptr;
+    size_t dummy_plane_cap = 0;
+    unsigned long long *dummy_flags = nullptr;
 };
 
 static long long g_comm_peer = 1;      // p4b_tune("comm_peer", 0) keeps everything on NCCL
@@ -410,6 +415,10 @@ static int halo(p4b_mg *m, int l, double *v) {
     return 0;
 }
 
+static long long g_force_mg = 0;       // p4b_tune("force_mg", 1|2): run the multi-GPU kernel variants on ONE GPU for
+                                       // measurements: 1 = no neighbours, 2 = both "neighbours" are scratch memory
+                                       // on this device (peer stores, fences and flag traffic stay local)
+static long long g_port_opts = 0;      // p4b_tune("port_opts", bits): HaloPort::opts experiments
 static long long g_fused_halo = 1;     // p4b_tune("fused_halo", 0): every exchange is a kernel of its own again (A/B)
 
 // a kernel wrote `v` without pushing its boundary planes: its ghost copies on the neighbours are stale
@@ -426,9 +435,38 @@ static int make_port(p4b_mg *m, int l, double *out, HaloPort *hp) {
     p4b_ctx *c = m->ctx;
     Level &L = m->lev[l];
     if (out) wrote(m, out);
+    if (g_force_mg && c->nranks == 1 && !L.replicated && L.d.az) {
+        const size_t plane = (size_t)L.d.plane();
+        if (!c->sync) {
+            P4B_CUDA(cudaMalloc(&c->sync, sizeof(LocalSync)));
+            P4B_CUDA(cudaMemset(c->sync, 0, sizeof(LocalSync)));
+            P4B_CUDA(cudaMalloc(&c->dummy_flags, 4 * sizeof(unsigned long long)));
+            const unsigned long long init[4] = {1ull << 62, 1ull << 62, 0ull, 0ull};
+            P4B_CUDA(cudaMemcpy(c->dummy_flags, init, sizeof init, cudaMemcpyHostToDevice));
+        }
+        if (plane > c->dummy_plane_cap) {
+            P4B_CUDA(cudaStreamSynchronize(c->stream));
+            if (c->dummy_planes) cudaFree(c->dummy_planes);
+            P4B_CUDA(cudaMalloc(&c->dummy_planes, 2 * plane * sizeof(double)));
+            c->dummy_plane_cap = plane;
+        }
+        hp->sync = c->sync;
+        hp->opts = (int)g_port_opts;
+        hp->my_flags = c->dummy_flags;
+        hp->plane = (long long)plane;
+        hp->hi_start = (long long)(L.d.zm - 1) * (long long)plane;
+        hp->push = out != nullptr;
+        if (g_force_mg >= 2) {
+            hp->flag_lo = c->dummy_flags + 2;
+            hp->flag_hi = c->dummy_flags + 3;
+            if (out) { hp->lo_dst = c->dummy_planes; hp->hi_dst = c->dummy_planes + plane; }
+        }
+        return 0;
+    }
     if (!m->peer || c->nranks == 1 || L.replicated || !g_fused_halo) return 0;
     const bool lo = L.d.zs > 0, hi = L.d.zs + L.d.zm < L.d.nz;
     hp->sync = c->sync;
+    hp->opts = (int)g_port_opts;
     hp->my_flags = c->mbox->halo_flag;
     hp->flag_lo = lo ? &c->peers.mbox[c->rank - 1]->halo_flag[1] : nullptr;
     hp->flag_hi = hi ? &c->peers.mbox[c->rank + 1]->halo_flag[0] : nullptr;
@@ -833,6 +871,8 @@ int p4b_tune(const char *key, long value) {
     if (std::string(key) == "rep_points") { g_rep_points = value; return 0; }
     if (std::string(key) == "comm_peer") { g_comm_peer = value; return 0; }
     if (std::string(key) == "fused_halo") { g_fused_halo = value; return 0; }
+    if (std::string(key) == "port_opts") { g_port_opts = value; return 0; }
+    if (std::string(key) == "force_mg") { g_force_mg = value; return 0; }
     return fail(62, "unknown tuning key %s", key);
 }
 
@@ -875,6 +915,8 @@ int p4b_ctx_destroy(p4b_ctx *c) {
         nccl_barrier(c);
         cudaFree(c->mbox);
         cudaFree(c->sync);
+        cudaFree(c->dummy_planes);
+        cudaFree(c->dummy_flags);
     }
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     cudaFree(c->red.partials);
@@ -912,6 +954,20 @@ int p4b_comm_init(p4b_ctx *c, const void *id128, int rank, int nranks) {
     P4B_CUDA(cudaSetDevice(c->device));
     P4B_NCCL(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
     return peer_setup(c);
+}
+
+int p4b_comm_stats(p4b_ctx *c, unsigned long long out[5], int reset) {
+    for (int i = 0; i < 5; i++) out[i] = 0;
+    if (!c->sync) return 0;
+    LocalSync h;
+    P4B_CUDA(cudaStreamSynchronize(c->stream));
+    P4B_CUDA(cudaMemcpy(&h, c->sync, sizeof h, cudaMemcpyDeviceToHost));
+    out[0] = h.wait_n; out[1] = h.wait_ns; out[2] = h.wait_max_ns; out[3] = h.fence_n; out[4] = h.fence_ns;
+    if (reset) {
+        const size_t off = offsetof(LocalSync, wait_ns);
+        P4B_CUDA(cudaMemset((char *)c->sync + off, 0, sizeof(LocalSync) - off));
+    }
+    return 0;
 }
 
 int p4b_slab_range(int m, int nranks, int rank, int *start, int *count) {

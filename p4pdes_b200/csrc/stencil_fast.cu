@@ -74,8 +74,10 @@ enum { MK_BD = 1, MK_VALID = 2 };
 //   * slot index, mbarrier parity bits, stage parity shift and all global pointers advance
 //     incrementally (no division or 64-bit multiply per plane), invalid tail nodes are clamped and
 //     only their store is predicated off (no divergent control flow).
-template <int MODE, int P, int NT>
-__global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, const StencilOp op, const MarchCfg cfg,
+//   * MG (multi-GPU) = false compiles the slab-exchange code (HaloPort waits / pushes / signals, downward march of
+//     the last chunk) out: the single-GPU kernel carries none of its registers or instructions.
+template <int MODE, int P, int NT, bool MG>
+__global__ void __launch_bounds__(NT, (NT <= 256 && P <= 8) ? 2 : 1) stencil_march_kernel(const LevelDesc L, const StencilOp op, const MarchCfg cfg,
                                                            double *partials, unsigned int *ticket) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);              // NS barriers (128 bytes reserved)
@@ -86,7 +88,14 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
     const int nx = L.nx;
     const int plane = L.nx * L.ny;
     const int q0 = blockIdx.x * Q;
-    const int k0 = blockIdx.y * cfg.KC;
+    // With an upper slab neighbour the LAST chunk is scheduled second and marched downwards, so that both boundary
+    // planes of the slab are the first planes computed: they are pushed to the neighbours and signalled while the
+    // rest of the kernel still runs (comm.h).  Without one, chunks are taken in order, all upwards.
+    const bool hi_nb = MG && op.port.push && !(op.port.opts & 1) && op.port.flag_hi != nullptr && gridDim.y > 1;
+    const int chunk = !hi_nb ? (int)blockIdx.y
+                             : (blockIdx.y == 0 ? 0 : (blockIdx.y == 1 ? (int)gridDim.y - 1 : (int)blockIdx.y - 1));
+    const bool rev = hi_nb && chunk == (int)gridDim.y - 1;
+    const int k0 = chunk * cfg.KC;
     const int k1 = min(k0 + cfg.KC, L.zm);                                 // local planes [k0, k1)
     const int NS = cfg.NS, H = cfg.H, SD = cfg.stage_doubles;
     const int lo = max(q0 - H, 0), hi = min(q0 + Q + H, plane);            // staged linear range of the plane
@@ -99,14 +108,18 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
     }
     __syncthreads();
     // CTAs of the first / last chunk read u's ghost plane and push out's boundary plane
-    const bool port_cta = op.port.sync != nullptr && ((blockIdx.y == 0 && op.port.flag_lo != nullptr) ||
-                                                      (blockIdx.y == gridDim.y - 1 && op.port.flag_hi != nullptr));
-    port_wait(op.port, port_cta);
+    const bool port_cta = MG && op.port.sync != nullptr && ((chunk == 0 && op.port.flag_lo != nullptr) ||
+                                                      (chunk == (int)gridDim.y - 1 && op.port.flag_hi != nullptr));
+    if (MG) port_wait(op.port, port_cta);
 
-    // plane t of this chunk is local plane kl = k0 - 1 + t, t = 0 .. T-1 (one extra plane on each side)
+    // plane t of this chunk, t = 0 .. T-1 (one extra plane on each side), is local plane k0 - 1 + t going up
+    // and k1 - t going down
     const int T = (k1 - k0) + 2;
-    const int kg0 = L.zs + k0 - 1;                                         // global index of plane t = 0
-    const long long e00 = (long long)(k0 - 1) * plane + lo;                // element offset of plane 0's staged range
+    const int dir = (MG && rev) ? -1 : 1;
+    const int kl0 = rev ? k1 : k0 - 1;                                     // local index of plane t = 0
+    const int kg0 = L.zs + kl0;                                            // its global index
+    const long long dstep = (long long)dir * plane;                        // element step from plane t to t + 1
+    const long long e00 = (long long)kl0 * plane + lo;                     // element offset of plane 0's staged range
     const int adj0 = (int)(e00 & 1LL);
 
     // producer state (thread 0): next plane to issue
@@ -114,7 +127,7 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
     const double *isrc = op.u + e00;                                       // start of plane `it`'s staged range
     auto issue_next = [&]() {       // producer thread only; issues plane `it` into slot `islot`
         if (it < T) {
-            const int kg = kg0 + it;
+            const int kg = kg0 + dir * it;
             if (kg < 0 || kg > L.nz - 1) {
                 mbar_arrive(&bars[islot]);      // nothing to load: complete the phase, slot parities stay in step
             } else {
@@ -130,28 +143,41 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
             }
         }
         it++;
-        isrc += plane;
+        isrc += dstep;
         if (++islot == NS) islot = 0;
     };
     if (tid == 0)
         for (int t = 0; t < NS; t++) issue_next();
 
     // per-thread nodes: q = q0 + tid + p*NT ; tail nodes beyond the plane are clamped onto its last node
-    int si[P];          // stage index of the node (before the per-plane parity shift)
-    int gi[P];          // offset of the node from the thread's global base pointer
-    int mask[P];
+    // Per-node indices.  Node p of a thread is `off(p)` elements after its first node, its stage index is sidx(p).
+    // Normally both live in registers (si/gi).  The two-operand mode at 8 nodes/thread does not fit 128 registers
+    // (two CTAs per SM) that way and recomputes them instead (LEAN): off(p) = min(p*NT, lim), lim = the thread's
+    // largest in-plane offset -- which also clamps a tail node beyond the plane onto the plane's last node.  The
+    // one-operand modes are instruction-issue bound and keep the arrays.  Boundary / validity flags: 2 bits per node.
+    constexpr bool LEAN = (MODE == ST_LIN && P >= 8);
+    const int lim = (plane - 1) - (q0 + tid);
     const int sb = 2 + (q0 - lo);
+    const int sbase = sb + tid;
+    int si[P], gi[P];
+    unsigned int mbits = 0u;
+    int mask[P];
 #pragma unroll
     for (int p = 0; p < P; p++) {
         int q = q0 + tid + p * NT;
-        int mk = MK_VALID;
-        if (q >= plane) { q = plane - 1; mk = 0; }
+        unsigned int mk = MK_VALID;
+        if (q >= plane) { q = plane - 1; mk = 0u; }
         const int j = q / nx, i = q - j * nx;
         if (i == 0 || i == nx - 1 || (L.ay && (j == 0 || j == L.ny - 1))) mk |= MK_BD;
-        mask[p] = mk;
+        mbits |= mk << (2 * p);
+        mask[p] = (int)mk;
         si[p] = sb + (q - q0);
         gi[p] = q - q0 - tid;
     }
+    auto off = [&](int p) { return LEAN ? min(p * NT, lim) : gi[p]; };
+    auto sidx = [&](int p) { return LEAN ? sbase + min(p * NT, lim) : si[p]; };
+    auto is_bd = [&](int p) { return LEAN ? (mbits & ((unsigned)MK_BD << (2 * p))) != 0u : (mask[p] & MK_BD) != 0; };
+    auto is_valid = [&](int p) { return LEAN ? (mbits & ((unsigned)MK_VALID << (2 * p))) != 0u : (mask[p] & MK_VALID) != 0; };
     // halo nodes (not owned by this CTA) that are boundary nodes and must be zeroed in every stage
     int hz[HZ];
     {
@@ -179,8 +205,9 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
     auto take_plane = [&](double *st, double (&c)[P]) {
 #pragma unroll
         for (int p = 0; p < P; p++) {
-            c[p] = st[si[p]];
-            if ((mask[p] & (MK_BD | MK_VALID)) == (MK_BD | MK_VALID)) st[si[p]] = 0.0;
+            const int s0 = sidx(p);
+            c[p] = st[s0];
+            if (is_bd(p) && is_valid(p)) st[s0] = 0.0;
         }
 #pragma unroll
         for (int r = 0; r < HZ; r++)
@@ -191,14 +218,14 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
     uint32_t phase = 0;               // bit s = parity to wait for on slot s
     int slot_c = 0;                   // slot of plane t
     int adj_c = adj0;                 // parity shift of plane t
-    if (kg0 >= 0) {
+    if (kg0 >= 0 && kg0 <= L.nz - 1) {
         mbar_wait(&bars[0], 0);
         take_plane(stages + adj_c, cur);
     }
     phase ^= 1u;
 
     // global pointers of plane t (the plane computed in iteration t), advanced by `plane` per step
-    const long long g0 = (long long)(k0 - 1) * plane + q0 + tid;
+    const long long g0 = (long long)kl0 * plane + q0 + tid;
     double *outp = op.out + g0;
     constexpr bool HAS_B = (MODE == ST_LIN || MODE == ST_LIN_PM1 || MODE == ST_LIN_PM1_DOT2);
     constexpr bool HAS_PM1 = (MODE == ST_LIN_PM1 || MODE == ST_LIN_PM1_DOT2);
@@ -208,8 +235,12 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
     const int oy = L.ay ? nx : 0;
     const double ca = op.ca, cb = op.cb, cg = op.cg;
 
+    // the iteration after which both boundary planes of this CTA have been pushed
+    const int t_sig = ((chunk == (int)gridDim.y - 1 && op.port.flag_hi != nullptr && !rev) || (op.port.opts & 2)) ? T - 2 : 1;
+    const unsigned int n_port_ctas =
+        gridDim.x * (gridDim.y == 1 ? 1u : (op.port.flag_lo != nullptr) + (op.port.flag_hi != nullptr));
     for (int t = 0; t + 1 < T; t++) {
-        const int kg = kg0 + t;               // global plane computed in this iteration (when t >= 1)
+        const int kg = kg0 + dir * t;         // global plane computed in this iteration (when t >= 1)
         int slot_n = slot_c + 1;
         if (slot_n == NS) slot_n = 0;
         const int adj_n = (adj_c + podd) & 1;
@@ -217,15 +248,24 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
         double bn[P], pn[P];
         if (HAS_B) {
             if (t + 1 < T - 1) {
+                if (MG) {       // (runtime direction: one pointer bump instead of a 64-bit add per node)
+                    const double *bnx = bp + dstep, *pnx = HAS_PM1 ? pp + dstep : nullptr;
 #pragma unroll
-                for (int p = 0; p < P; p++) {
-                    bn[p] = bp[plane + gi[p]];
-                    if (HAS_PM1) pn[p] = pp[plane + gi[p]];
+                    for (int p = 0; p < P; p++) {
+                        bn[p] = bnx[off(p)];
+                        if (HAS_PM1) pn[p] = pnx[off(p)];
+                    }
+                } else {
+#pragma unroll
+                    for (int p = 0; p < P; p++) {
+                        bn[p] = bp[plane + off(p)];
+                        if (HAS_PM1) pn[p] = pp[plane + off(p)];
+                    }
                 }
             }
         }
         // centre values of plane t+1
-        if (kg + 1 <= L.nz - 1) {
+        if (kg + dir >= 0 && kg + dir <= L.nz - 1) {
             mbar_wait(&bars[slot_n], (phase >> slot_n) & 1u);
             take_plane(stages + (size_t)slot_n * SD + adj_n, nxt);
         } else {
@@ -237,45 +277,61 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
             const double *st = stages + (size_t)slot_c * SD + adj_c;
             const bool kbd = (kg == 0 || kg == L.nz - 1);
             // first / last owned plane of the slab: the value also goes into the neighbour's ghost plane
-            const bool push_lo = op.port.lo_dst != nullptr && kg == L.zs;
-            const bool push_hi = op.port.hi_dst != nullptr && kg == L.zs + L.zm - 1;
+            const bool push_lo = MG && op.port.lo_dst != nullptr && kg == L.zs;
+            const bool push_hi = MG && op.port.hi_dst != nullptr && kg == L.zs + L.zm - 1;
             const double czd = (kg - 1 > 0) ? cz : 0.0, czu = (kg + 1 < L.nz - 1) ? cz : 0.0;
+            // coefficients by march order: `nxt` is the plane above when going up, the plane below when going down
+            const double czn = (MG && rev) ? czd : czu, czp = (MG && rev) ? czu : czd;
 #pragma unroll
             for (int p = 0; p < P; p++) {
-                const bool bd = kbd || (mask[p] & MK_BD);
-                const int s0 = si[p];
+                const bool bd = kbd || is_bd(p);
+                const int s0 = sidx(p);
                 const int dx = bd ? 0 : 1, dy = bd ? 0 : oy;     // boundary rows never leave their own node
                 const double uc = cur[p];
                 double Ai = diag * uc - cx * (st[s0 - dx] + st[s0 + dx]);
                 Ai -= cy * (st[s0 - dy] + st[s0 + dy]);
-                Ai -= czu * nxt[p] + czd * prev[p];
+                // MG: two rounded products, then their (commutative) sum -- the same bits in both march directions
+                if (MG) Ai -= __dadd_rn(__dmul_rn(czn, nxt[p]), __dmul_rn(czp, prev[p]));
+                else Ai -= czu * nxt[p] + czd * prev[p];
                 const double Au = bd ? diag * uc : Ai;
                 double o;
                 if (MODE == ST_APPLY || MODE == ST_APPLY_DOT) {
                     o = Au;
-                    if (MODE == ST_APPLY_DOT) dv[0] += (mask[p] & MK_VALID) ? uc * Au : 0.0;
+                    if (MODE == ST_APPLY_DOT) dv[0] += is_valid(p) ? uc * Au : 0.0;
                 } else if (MODE == ST_LIN_BU) {
                     o = cb * uc + cg * (uc - Au);
                 } else {
                     o = cb * uc + cg * (bq[p] - Au);
                     if (HAS_PM1) o += ca * pq[p];
-                    if (MODE == ST_LIN_PM1_DOT2 && (mask[p] & MK_VALID)) {
+                    if (MODE == ST_LIN_PM1_DOT2 && is_valid(p)) {
                         dv[0] += o * o;
                         dv[1] += o * bq[p];
                     }
                 }
-                if (mask[p] & MK_VALID) {
-                    outp[gi[p]] = o;
-                    if (push_lo) op.port.lo_dst[q0 + tid + gi[p]] = o;
-                    if (push_hi) op.port.hi_dst[q0 + tid + gi[p]] = o;
+                if (is_valid(p)) outp[off(p)] = o;
+            }
+            // first / last owned plane of the slab: the values also go into the neighbour's ghost plane.  Kept out
+            // of the loop above (this happens once per kernel and CTA): the thread reads back what it just stored.
+            if (MG && (push_lo || push_hi)) {
+                double *dst = (push_lo ? op.port.lo_dst : op.port.hi_dst) + q0 + tid;
+                double *dst2 = (push_lo && push_hi) ? op.port.hi_dst + q0 + tid : nullptr;     // one-plane slab
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    if (is_valid(p)) {
+                        const double o = outp[off(p)];
+                        dst[off(p)] = o;
+                        if (dst2) dst2[off(p)] = o;
+                    }
                 }
             }
         }
         __syncthreads();                       // everyone is done with slot_c (and with plane 0 at t = 0)
         if (tid == 0) issue_next();
-        outp += plane;
-        if (HAS_B) bp += plane;
-        if (HAS_PM1) pp += plane;
+        // boundary planes are out: publish them (one thread of another warp than the copy producer's)
+        if (MG && port_cta && t == t_sig) port_signal_nosync(op.port, n_port_ctas, tid == NT - 32);
+        outp += dstep;
+        if (HAS_B) bp += dstep;
+        if (HAS_PM1) pp += dstep;
         slot_c = slot_n;
         adj_c = adj_n;
 #pragma unroll
@@ -288,8 +344,10 @@ __global__ void __launch_bounds__(NT) stencil_march_kernel(const LevelDesc L, co
             }
         }
     }
-    port_signal(op.port, port_cta,
-                gridDim.x * (gridDim.y == 1 ? 1u : (op.port.flag_lo != nullptr) + (op.port.flag_hi != nullptr)));
+    if (MG && port_cta && T - 1 <= t_sig) {          // (a chunk too short to have reached t_sig inside the loop)
+        __syncthreads();
+        port_signal_nosync(op.port, n_port_ctas, tid == NT - 32);
+    }
     if (MODE == ST_APPLY_DOT || MODE == ST_LIN_PM1_DOT2) {
         // one partial (per value) per CTA, summed in fixed order by the last CTA to finish
         constexpr int NV = (MODE == ST_LIN_PM1_DOT2) ? 2 : 1;
@@ -377,8 +435,8 @@ bool stencil_fast_eligible(const LevelDesc &L) {
     return t.enabled && L.ax && L.az && big && L.zm >= 8 && plane * (L.zm + 2) < (1LL << 31);
 }
 
-template <int MODE, int P, int NT>
-static int launch_march(cudaStream_t st, const LevelDesc &L, const StencilOp &op, const Reducer &red, int NS) {
+template <int MODE, int P, int NT, bool MG>
+static int launch_march_mg(cudaStream_t st, const LevelDesc &L, const StencilOp &op, const Reducer &red, int NS) {
     static int sm_count = 0, max_smem = 0;
     if (!sm_count) {
         int dev = 0;
@@ -398,12 +456,12 @@ static int launch_march(cudaStream_t st, const LevelDesc &L, const StencilOp &op
     if (smem + 1024 > (size_t)max_smem) return fail(62, "plane-marching stage does not fit shared memory");
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        P4B_CUDA(cudaFuncSetAttribute(stencil_march_kernel<MODE, P, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        P4B_CUDA(cudaFuncSetAttribute(stencil_march_kernel<MODE, P, NT, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
         attr_smem = smem;
     }
     int occ = 1;
-    P4B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stencil_march_kernel<MODE, P, NT>, NT, smem));
+    P4B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stencil_march_kernel<MODE, P, NT, MG>, NT, smem));
     if (occ < 1) occ = 1;
     const int bands = (plane + Q - 1) / Q;
     const long long slots = (long long)sm_count * occ;
@@ -423,9 +481,18 @@ static int launch_march(cudaStream_t st, const LevelDesc &L, const StencilOp &op
     if ((MODE == ST_APPLY_DOT || MODE == ST_LIN_PM1_DOT2) && bands * nchunks > red.max_blocks)
         return fail(63, "reducer scratch too small");
     dim3 grid(bands, nchunks);
-    stencil_march_kernel<MODE, P, NT><<<grid, NT, smem, st>>>(L, op, cfg, red.partials, red.ticket);
+    stencil_march_kernel<MODE, P, NT, MG><<<grid, NT, smem, st>>>(L, op, cfg, red.partials, red.ticket);
     P4B_LAUNCH_CHECK();
     return 0;
+}
+
+template <int MODE, int P, int NT>
+static int launch_march(cudaStream_t st, const LevelDesc &L, const StencilOp &op, const Reducer &red, int NS) {
+    if (op.port.sync && op.port.push) return launch_march_mg<MODE, P, NT, true>(st, L, op, red, NS);
+    // a kernel that only READS ghost planes keeps the lean single-GPU code: the wait for the neighbours' flags is a
+    // one-thread kernel in front of it (measured: the exchange-capable variant costs the 16 N modes 8-25 %)
+    if (op.port.sync) P4B_CHECK(launch_port_wait(st, op.port));
+    return launch_march_mg<MODE, P, NT, false>(st, L, op, red, NS);
 }
 
 template <int P, int NT>
@@ -451,12 +518,12 @@ int launch_stencil_fast(cudaStream_t st, const LevelDesc &L, const StencilOp &op
         // wants 4 nodes/thread x 512 threads, the others 8 nodes/thread x 256 threads (2 CTAs/SM)
         if (op.mode == ST_LIN_PM1) return launch_march<ST_LIN_PM1, 4, 512>(st, L, op, red, t.NS);
         if (op.mode == ST_LIN_PM1_DOT2) return launch_march<ST_LIN_PM1_DOT2, 4, 512>(st, L, op, red, t.NS);
+        // with the slab-exchange code the two-operand mode no longer fits 128 registers at 8 nodes/thread
+        if (op.mode == ST_LIN && op.port.sync) return launch_march<ST_LIN, 4, 512>(st, L, op, red, t.NS);
         return launch_march_mode<8, 256>(st, L, op, red, t.NS);
     }
     if (t.P == 4 && t.NT == 512) return launch_march_mode<4, 512>(st, L, op, red, t.NS);
     if (t.P == 8 && t.NT == 256) return launch_march_mode<8, 256>(st, L, op, red, t.NS);
-    if (t.P == 8 && t.NT == 512) return launch_march_mode<8, 512>(st, L, op, red, t.NS);
-    if (t.P == 4 && t.NT == 256) return launch_march_mode<4, 256>(st, L, op, red, t.NS);
     return fail(62, "P4B_MARCH=%d,%d is not instantiated", t.P, t.NT);
 }
 

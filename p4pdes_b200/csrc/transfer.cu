@@ -97,18 +97,20 @@ __global__ void __launch_bounds__(256) prolong_add_kernel(const LevelDesc F, con
 // (a_jk = 1/2 (c[I0] + c[I1]), I1 = I0 for even i, which is exact) and then updates the up-to-four fine
 // nodes (i, 2J+{0,1}, 2K+{0,1}): 8 coarse loads (L1/L2 hits, neighbouring lanes share them) per 4 fine
 // nodes instead of up to 8 per node, fine accesses fully coalesced, one index division per 4 nodes.
+template <bool MG>
 __global__ void __launch_bounds__(256) prolong_add3d_kernel(const LevelDesc F, const LevelDesc C, int Kfirst,
                                                             const double *__restrict__ xc, double *__restrict__ xf,
                                                             const HaloPort port) {
     const int task = blockIdx.x * 256 + threadIdx.x;       // over nx * cny
     // the first / last coarse plane of the range are the ones that may be a neighbour's (coarse ghost read) and
     // hold the first / last owned fine plane (pushed)
-    const bool port_cta = port.sync != nullptr && ((blockIdx.y == 0 && port.flag_lo != nullptr) ||
-                                                   (blockIdx.y == gridDim.y - 1 && port.flag_hi != nullptr));
-    port_wait(port, port_cta);
+    const unsigned int by = MG ? port_remap(port, blockIdx.y, gridDim.y) : blockIdx.y;
+    const bool port_cta = MG && port.sync != nullptr && ((by == 0 && port.flag_lo != nullptr) ||
+                                                         (by == gridDim.y - 1 && port.flag_hi != nullptr));
+    if (MG) port_wait(port, port_cta);
     if (task < F.nx * C.ny) {
     const int J = task / F.nx, i = task - J * F.nx;
-    const int K = Kfirst + blockIdx.y;
+    const int K = Kfirst + (int)by;
     const int I0 = i >> 1, I1 = I0 + (i & 1);
     const int J1 = min(J + 1, C.ny - 1), K1 = min(K + 1, C.nz - 1);
     const long long cplane = (long long)C.nx * C.ny;
@@ -141,16 +143,16 @@ __global__ void __launch_bounds__(256) prolong_add3d_kernel(const LevelDesc F, c
         const double e0 = c ? 0.5 * (a00 + a01) : a00;
         const double v0 = f[c][0] + e0;
         row[c][0] = v0;
-        port_store(port, row[c] - xf, v0);
+        if (MG) port_store(port, row[c] - xf, v0);
         if (jok) {
             const double e1 = c ? 0.25 * ((a00 + a10) + (a01 + a11)) : 0.5 * (a00 + a10);
             const double v1 = f[c][1] + e1;
             row[c][F.nx] = v1;
-            port_store(port, row[c] + F.nx - xf, v1);
+            if (MG) port_store(port, row[c] + F.nx - xf, v1);
         }
     }
     }
-    port_signal(port, port_cta, gridDim.x * (gridDim.y == 1 ? 1u : (port.flag_lo != nullptr) + (port.flag_hi != nullptr)));
+    if (MG) port_signal(port, port_cta, gridDim.x * (gridDim.y == 1 ? 1u : (port.flag_lo != nullptr) + (port.flag_hi != nullptr)));
 }
 
 // 3-D fast path of the restriction.  One thread per coarse column I and strip of TJ coarse rows; it marches a
@@ -216,20 +218,22 @@ __device__ __forceinline__ void restrict_plane(const LevelDesc &F, const double 
     for (int jj = 0; jj < TJ; jj++) P[jj] = rx[2 * jj + 1] + 0.5 * (rx[2 * jj] + rx[2 * jj + 2]);
 }
 
-template <int TJ>
+template <int TJ, bool MG>
 __global__ void __launch_bounds__(128) restrict3d_kernel(const LevelDesc F, const LevelDesc C, int KC,
                                                           const double *__restrict__ rf, double *__restrict__ bc,
                                                           const HaloPort port) {
     const int I = blockIdx.x * 128 + threadIdx.x;
     // the first / last chunk of coarse planes read the fine ghost planes and hold the coarse boundary planes (pushed)
-    const bool port_cta = port.sync != nullptr && ((blockIdx.z == 0 && port.flag_lo != nullptr) ||
-                                                   (blockIdx.z == gridDim.z - 1 && port.flag_hi != nullptr));
-    port_wait(port, port_cta);
+    const unsigned int bz = MG ? port_remap(port, blockIdx.z, gridDim.z) : blockIdx.z;
+    const bool port_cta = MG && port.sync != nullptr && ((bz == 0 && port.flag_lo != nullptr) ||
+                                                         (bz == gridDim.z - 1 && port.flag_hi != nullptr));
+    if (MG) port_wait(port, port_cta);
     const int J0 = TJ * blockIdx.y;
-    const int Kb = C.zs + KC * blockIdx.z;                       // first coarse plane of this chunk
+    const int Kb = C.zs + KC * (int)bz;                          // first coarse plane of this chunk
     const int Ke = min(Kb + KC, C.zs + C.zm);
     const int lane = threadIdx.x & 31;
-    const bool warp_live = (I & ~31) < C.nx;                     // false: whole warp beyond the row
+    if (!MG && (I & ~31) >= C.nx) return;                        // whole warp beyond the row
+    const bool warp_live = (I & ~31) < C.nx;                     // (MG: it stays for the barrier in port_signal)
     const bool live = I < C.nx;
     const int fi = 2 * I;
     const int vparity = (int)(((uintptr_t)rf >> 3) & 1);
@@ -254,14 +258,14 @@ __global__ void __launch_bounds__(128) restrict3d_kernel(const LevelDesc F, cons
                 if (J0 + jj < C.ny) {
                     const double v = Pc[jj] + 0.5 * (Pm[jj] + Pp[jj]);
                     out[(long long)jj * C.nx] = v;
-                    port_store(port, (out - bc) + (long long)jj * C.nx, v);
+                    if (MG) port_store(port, (out - bc) + (long long)jj * C.nx, v);
                 }
         }
 #pragma unroll
         for (int jj = 0; jj < TJ; jj++) Pm[jj] = Pp[jj];
     }
-    port_signal(port, port_cta, gridDim.x * gridDim.y *
-                                    (gridDim.z == 1 ? 1u : (port.flag_lo != nullptr) + (port.flag_hi != nullptr)));
+    if (MG) port_signal(port, port_cta, gridDim.x * gridDim.y *
+                                            (gridDim.z == 1 ? 1u : (port.flag_lo != nullptr) + (port.flag_hi != nullptr)));
 }
 
 int launch_restrict(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, const double *rf, double *bc,
@@ -272,7 +276,8 @@ int launch_restrict(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, con
         constexpr int TJ = 4;
         const int KC = 8;
         dim3 grid((unsigned)((C.nx + 127) / 128), (unsigned)((C.ny + TJ - 1) / TJ), (unsigned)((C.zm + KC - 1) / KC));
-        restrict3d_kernel<TJ><<<grid, 128, 0, st>>>(F, C, KC, rf, bc, port);
+        if (port.sync) restrict3d_kernel<TJ, true><<<grid, 128, 0, st>>>(F, C, KC, rf, bc, port);
+        else restrict3d_kernel<TJ, false><<<grid, 128, 0, st>>>(F, C, KC, rf, bc, port);
         P4B_LAUNCH_CHECK();
         return 0;
     }
@@ -288,7 +293,8 @@ int launch_prolong_add(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, 
     if (F.ax && F.ay && F.az && F.nx >= 64 && (long long)F.nx * C.ny < (1LL << 30)) {
         const int Kfirst = F.zs / 2, Klast = (F.zs + F.zm - 1) / 2;
         dim3 grid((unsigned)(((long long)F.nx * C.ny + 255) / 256), (unsigned)(Klast - Kfirst + 1));
-        prolong_add3d_kernel<<<grid, 256, 0, st>>>(F, C, Kfirst, xc, xf, port);
+        if (port.sync) prolong_add3d_kernel<true><<<grid, 256, 0, st>>>(F, C, Kfirst, xc, xf, port);
+        else prolong_add3d_kernel<false><<<grid, 256, 0, st>>>(F, C, Kfirst, xc, xf, port);
         P4B_LAUNCH_CHECK();
         return 0;
     }

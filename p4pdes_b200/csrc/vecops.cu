@@ -124,33 +124,25 @@ __global__ void __launch_bounds__(VT) aypx_dev_kernel(long long n, const double 
     }
 }
 
-// CTA b of a grid-stride kernel owns the VT*VU-element segments starting at b*VT*VU + k*stride: does any of them
-// touch the first plane (when there is a lower neighbour) or the last plane (upper neighbour) of the slab?
-__device__ __forceinline__ bool port_touch_strided(const HaloPort &hp, long long n, long long s0, long long width,
-                                                   long long stride) {
-    if (!hp.sync || s0 >= n) return false;
-    const bool lo = hp.flag_lo != nullptr && s0 < hp.plane;
-    const long long slast = s0 + ((n - 1 - s0) / stride) * stride;       // last segment start below n
-    const bool hi = hp.flag_hi != nullptr && slast + width > hp.hi_start;
-    return lo || hi;
-}
-
 // One pass for the CG direction update AND the previous iteration's solution update:
 //   x += a_prev * p   (a_prev = an/ad, the alpha of the iteration that produced this p; skipped when first)
 //   p  = z + b * p    (b = bn/bd)
 // p is read once for both, which saves the separate 24 N pass x += a p of KSPSolve_CG.
+template <bool MG>
 __global__ void __launch_bounds__(VT) xp_update_kernel(long long n, const double *__restrict__ an,
                                                         const double *__restrict__ ad, const double *__restrict__ bn,
                                                         const double *__restrict__ bd, const double *__restrict__ z,
                                                         double *__restrict__ p, double *__restrict__ x, int first,
                                                         const HaloPort port) {
-    // only CTAs that touch a boundary plane wait and fence; every CTA is counted (the grid is small)
-    const bool touch = port_touch_strided(port, n, (long long)blockIdx.x * VT * VU, VT * VU, (long long)gridDim.x * VT * VU);
-    port_wait(port, touch);
+    // boundary planes of p first (comm.h SegRot): the CTAs that write them wait for the neighbours before, and
+    // signal right after, their last boundary segment
+    const SegRot rot = seg_rot(MG ? port : HaloPort(), n, VT * VU);      // (MG = false: the exchange code compiles out)
+    const bool bcta = MG && (long long)blockIdx.x < rot.NB;
+    if (MG) port_wait(port, bcta);
     const double a = first ? 0.0 : an[0] / ad[0];
     const double b = first ? 0.0 : bn[0] / bd[0];
-    const long long stride = (long long)gridDim.x * VT * VU;
-    for (long long base = (long long)blockIdx.x * VT * VU + threadIdx.x; base < n; base += stride) {
+    for (long long g = blockIdx.x; g < rot.S; g += gridDim.x) {
+        const long long base = rot.phys(g) * (VT * VU) + threadIdx.x;
         double zv[VU], pv[VU], xv[VU];
 #pragma unroll
         for (int q = 0; q < VU; q++) {
@@ -164,22 +156,27 @@ __global__ void __launch_bounds__(VT) xp_update_kernel(long long n, const double
                 if (!first) x[i] = xv[q] + a * pv[q];
                 const double pn = first ? zv[q] : zv[q] + b * pv[q];
                 p[i] = pn;
-                port_store(port, i, pn);
+                if (MG) port_store(port, i, pn);
             }
         }
+        if (MG && bcta && g < rot.NB && g + gridDim.x >= rot.NB) {       // this CTA's last boundary segment
+            __syncthreads();
+            port_signal_nosync(port, (unsigned int)min((long long)gridDim.x, rot.NB), threadIdx.x == 0);
+        }
     }
-    port_signal(port, true, gridDim.x, touch);
 }
 
 // r -= a w  with a = num/den on the device
+template <bool MG>
 __global__ void __launch_bounds__(VT) r_update_kernel(long long n, const double *__restrict__ num,
                                                        const double *__restrict__ den, const double *__restrict__ w,
                                                        double *__restrict__ r, const HaloPort port) {
-    const bool touch = port_touch_strided(port, n, (long long)blockIdx.x * VT * VU, VT * VU, (long long)gridDim.x * VT * VU);
-    port_wait(port, touch);
+    const SegRot rot = seg_rot(MG ? port : HaloPort(), n, VT * VU);      // boundary planes of r first, see xp_update_kernel
+    const bool bcta = MG && (long long)blockIdx.x < rot.NB;
+    if (MG) port_wait(port, bcta);
     const double a = num[0] / den[0];
-    const long long stride = (long long)gridDim.x * VT * VU;
-    for (long long base = (long long)blockIdx.x * VT * VU + threadIdx.x; base < n; base += stride) {
+    for (long long g = blockIdx.x; g < rot.S; g += gridDim.x) {
+        const long long base = rot.phys(g) * (VT * VU) + threadIdx.x;
         double wv[VU], rv[VU];
 #pragma unroll
         for (int q = 0; q < VU; q++) {
@@ -192,11 +189,14 @@ __global__ void __launch_bounds__(VT) r_update_kernel(long long n, const double 
             if (i < n) {
                 const double rn = rv[q] - a * wv[q];
                 r[i] = rn;
-                port_store(port, i, rn);
+                if (MG) port_store(port, i, rn);
             }
         }
+        if (MG && bcta && g < rot.NB && g + gridDim.x >= rot.NB) {
+            __syncthreads();
+            port_signal_nosync(port, (unsigned int)min((long long)gridDim.x, rot.NB), threadIdx.x == 0);
+        }
     }
-    port_signal(port, true, gridDim.x, touch);
 }
 
 // out = a x + b y ; x or y may be null (treated as zero) ; out may alias x or y
@@ -253,14 +253,16 @@ int launch_aypx_dev(cudaStream_t st, long long n, const double *num, const doubl
 int launch_xp_update(cudaStream_t st, long long n, const double *an, const double *ad, const double *bn, const double *bd,
                      const double *z, double *p, double *x, int first, const HaloPort &port) {
     if (n <= 0) return 0;
-    xp_update_kernel<<<vec_blocks(n, STREAM_BLOCKS), VT, 0, st>>>(n, an, ad, bn, bd, z, p, x, first, port);
+    if (port.sync) xp_update_kernel<true><<<vec_blocks(n, STREAM_BLOCKS), VT, 0, st>>>(n, an, ad, bn, bd, z, p, x, first, port);
+    else xp_update_kernel<false><<<vec_blocks(n, STREAM_BLOCKS), VT, 0, st>>>(n, an, ad, bn, bd, z, p, x, first, port);
     P4B_LAUNCH_CHECK();
     return 0;
 }
 int launch_r_update(cudaStream_t st, long long n, const double *num, const double *den, const double *w, double *r,
                     const HaloPort &port) {
     if (n <= 0) return 0;
-    r_update_kernel<<<vec_blocks(n, STREAM_BLOCKS), VT, 0, st>>>(n, num, den, w, r, port);
+    if (port.sync) r_update_kernel<true><<<vec_blocks(n, STREAM_BLOCKS), VT, 0, st>>>(n, num, den, w, r, port);
+    else r_update_kernel<false><<<vec_blocks(n, STREAM_BLOCKS), VT, 0, st>>>(n, num, den, w, r, port);
     P4B_LAUNCH_CHECK();
     return 0;
 }

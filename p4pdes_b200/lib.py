@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libp4b200.so")
+# P4B_LIB: an alternative build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("P4B_LIB") or os.path.join(HERE, "lib", "libp4b200.so")
 
 P4B_MAX_HIST = 256
 CYCLE_V, CYCLE_W = 1, 2
@@ -77,6 +78,7 @@ _SIGS = {
     "p4b_ctx_sync": (C.c_int, [_P]),
     "p4b_comm_unique_id": (C.c_int, [_P]),
     "p4b_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "p4b_comm_stats": (C.c_int, [_P, C.POINTER(C.c_ulonglong * 5), C.c_int]),
     "p4b_slab_range": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "p4b_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "p4b_free": (C.c_int, [_P, _P]),

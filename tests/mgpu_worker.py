@@ -30,6 +30,9 @@ def main():
     ap.add_argument("--comm-peer", type=int, default=1)
     ap.add_argument("--fused-halo", type=int, default=1)
     ap.add_argument("--repeat", type=int, default=1, help="solve this many times (CUDA-graph replay, exchange counters)")
+    ap.add_argument("--compare-fused", action="store_true",
+                    help="also solve with the other setting of fused_halo (same process, fresh hierarchy) and report "
+                         "whether history and solution are bit-identical")
     ap.add_argument("--no-oracle", action="store_true")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -49,6 +52,16 @@ def main():
     mg.fish_setup("manuexp", True, b=b, u0=u0)
     for _ in range(a.repeat):
         res = mg.cg_solve(b, x, rtol=a.rtol)
+    if a.compare_fused:
+        L.tune("fused_halo", 1 - a.fused_halo)
+        mg2 = Multigrid(ctx, g, mg_options(levels=a.levels, cycle=a.cycle))
+        x2 = ctx.empty(n)
+        for _ in range(a.repeat):
+            res2 = mg2.cg_solve(b, x2, rtol=a.rtol)
+        same = torch.tensor([int(torch.equal(x, x2) and res.history == res2.history)], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        fused_equal = bool(same.item())
+        mg2.close()
     ctx.axpy(-1.0, x, u0)          # u = u0 - y
     bnorm = ctx.norm2(b)           # allreduced inside the library
     # gather the slabs on rank 0
@@ -62,6 +75,8 @@ def main():
     dist.all_gather(parts, buf)
     out = {"world": world, "its": res.its, "reason": res.reason, "history": res.history, "bnorm": bnorm,
            "slab": [mg.zs, mg.zm], "nlevels": mg.nlevels}
+    if a.compare_fused:
+        out["fused_equal"] = fused_equal
     if rank == 0:
         u = torch.cat([p[:s] for p, s in zip(parts, sizes)]).cpu().numpy()
         assert u.size == g.n
