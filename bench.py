@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--no-fuse", action="store_true")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="multi-GPU transport (A/B)")
     ap.add_argument("--no-fused-halo", action="store_true", help="one push kernel per ghost exchange (A/B)")
+    ap.add_argument("--rep-points", type=int, default=0, help="replicate levels with at most this many nodes (A/B)")
     ap.add_argument("--force-mg", type=int, default=0, help="run the multi-GPU kernel variants on one GPU (A/B)")
     ap.add_argument("--port-opts", type=int, default=0, help="HaloPort experiments (p4b_tune port_opts)")
     ap.add_argument("--no-graph", action="store_true", help="launch the coarse levels kernel by kernel (A/B)")
@@ -167,6 +168,8 @@ def main():
     L.tune("fused_halo", 0 if args.no_fused_halo else 1)
     L.tune("port_opts", args.port_opts)
     L.tune("force_mg", args.force_mg)
+    if args.rep_points:
+        L.tune("rep_points", args.rep_points)
     ctx = Context(local_rank, distributed=world > 1)
     lib = ctx.lib
 

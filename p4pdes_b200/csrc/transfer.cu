@@ -274,7 +274,7 @@ int launch_restrict(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, con
     if (n <= 0) return 0;
     if (F.ax && F.ay && F.az && C.nx >= 64 && (((uintptr_t)rf) & 7) == 0) {
         constexpr int TJ = 4;
-        const int KC = 8;
+        const int KC = C.zm > 64 ? 8 : 4;      // thin slabs (multi-GPU): more, smaller chunks keep all SMs busy
         dim3 grid((unsigned)((C.nx + 127) / 128), (unsigned)((C.ny + TJ - 1) / TJ), (unsigned)((C.zm + KC - 1) / KC));
         if (port.sync) restrict3d_kernel<TJ, true><<<grid, 128, 0, st>>>(F, C, KC, rf, bc, port);
         else restrict3d_kernel<TJ, false><<<grid, 128, 0, st>>>(F, C, KC, rf, bc, port);
