@@ -224,6 +224,28 @@ int p4b_pattern_ifunction(p4b_ctx *ctx, int mx, int my, double L, double Du, dou
                           const double *Ydot, double *F);
 int p4b_pattern_ijacobian_mult(p4b_ctx *ctx, int mx, int my, double L, double Du, double Dv, double shift,
                                const double *X, double *JX);
+/* ---- assembled Jacobians of the 2-D drivers: finite-difference assembly and the solver kernels on them ----
+ *   p4b_minimal_jacobian_fd  [PETSc] SNESComputeJacobianDefaultColor on c/ch7/minimal.c:210-282 (-snes_fd_color):
+ *                            9 colours (DMDA BOX stencil), MatFDColoring "ds" differencing; F0 = F(u) already computed
+ *   p4b_stencil9_apply       [PETSc] MatMult on that matrix
+ *   p4b_stencil9_lin         [PETSc] KSPSolve_Chebyshev/Richardson step + PCApply_Jacobi on it:
+ *                            out = ca*pm1 + cb*u + cg*B(b - A u), B = diag(A)^-1 (jacobi != 0) or I
+ *                            (pm1 may be NULL or alias out; b may be NULL)
+ *   p4b_dense_matvec         [PETSc] PCApply_LU on the coarsest level (x = Ainv b, Ainv n x n row-major on device)
+ * Matrix layout "stencil9": 9*mx*my doubles, vals[s*mx*my + j*mx + i] = dF(i,j)/du(i+di, j+dj), s = 3(dj+1) + (di+1). */
+int p4b_minimal_jacobian_fd(p4b_ctx *ctx, int mx, int my, double q, const double *u, const double *g, const double *F0,
+                            double *vals9);
+int p4b_stencil9_apply(p4b_ctx *ctx, int mx, int my, const double *vals9, const double *x, double *y);
+int p4b_stencil9_lin(p4b_ctx *ctx, int mx, int my, const double *vals9, const double *u, const double *b,
+                     const double *pm1, double ca, double cb, double cg, int jacobi, double *out);
+int p4b_dense_matvec(p4b_ctx *ctx, int n, const double *Ainv, const double *b, double *x);
+/* max_n sum_s |a_ns| / |a_nn| (Gershgorin bound of lambda_max(D^-1 A), the Chebyshev target); work: mx*my doubles */
+int p4b_stencil9_gershgorin(p4b_ctx *ctx, int mx, int my, const double *vals9, double *work, double *result_host);
+/* [PETSc] DMCreateInjection (DMDA, ratio 2): uc(I,J) = uf(2I,2J); fine grid (2cmx-1) x (2cmy-1) */
+int p4b_inject2d(p4b_ctx *ctx, int cmx, int cmy, const double *ufine, double *ucoarse);
+/* out = a x + b y (x, y may alias out) and a device-to-device copy: [PETSc] VecAXPBY / VecWAXPY / VecCopy */
+int p4b_vec_axpby(p4b_ctx *ctx, size_t n, double a, const double *x, double b, const double *y, double *out);
+int p4b_vec_copy(p4b_ctx *ctx, size_t n, const double *x, double *y);
 typedef struct p4b_sell p4b_sell;
 int p4b_sell_create(p4b_ctx *ctx, int nrows, const int *rowptr_host, const int *colind_host, const double *vals_host,
                     p4b_sell **A);

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libp4b200.so")
-SOURCES = ["mg.cu", "stencil.cu", "stencil_fast.cu", "transfer.cu", "vecops.cu", "fishfn.cu", "comm.cu", "mp_kernels.cu"]
+SOURCES = ["mg.cu", "stencil.cu", "stencil_fast.cu", "transfer.cu", "vecops.cu", "fishfn.cu", "comm.cu", "mp_kernels.cu", "assembled.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "comm.h"),
            os.path.join(ROOT, "include", "p4b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -91,4 +91,13 @@ int sell_spmv(cudaStream_t st, const Sell *A, const double *x, double *y);
 void sell_free(Sell *A);
 void sell_info(const Sell *A, int *nrows, long long *nnz, long long *padded);
 
+// assembled 2-D 9-point Jacobians (assembled.cu): stencil9 layout vals[s*N + n], s = 3(dj+1) + (di+1)
+int fd_jacobian_minimal(cudaStream_t st, int mx, int my, double q, const double *u, const double *g, const double *F0,
+                        double *vals, double *up, double *Fp);
+int launch_stencil9_apply(cudaStream_t st, int mx, int my, const double *vals, const double *x, double *y);
+int launch_stencil9_rowratio(cudaStream_t st, int mx, int my, const double *vals, double *out);
+int launch_inject2d(cudaStream_t st, int cmx, int cmy, int fmx, const double *uf, double *uc);
+int launch_stencil9_lin(cudaStream_t st, int mx, int my, const double *vals, const double *u, const double *b,
+                        const double *pm1, double ca, double cb, double cg, int jacobi, double *out);
+
 }  // namespace p4b

@@ -1592,6 +1592,41 @@ int p4b_pattern_ijacobian_mult(p4b_ctx *c, int mx, int my, double L, double Du, 
     return launch_pattern_ifunction(c->stream, mx, my, Du / (6.0 * h * h), Dv / (6.0 * h * h), 1, shift, X, nullptr, JX);
 }
 
+int p4b_minimal_jacobian_fd(p4b_ctx *c, int mx, int my, double q, const double *u, const double *g, const double *F0,
+                            double *vals9) {
+    if (mx < 3 || my < 3) return fail(60, "minimal Jacobian: grid must be at least 3 x 3");
+    double *tmp = nullptr;
+    const size_t N = (size_t)mx * my;
+    P4B_CUDA(cudaMallocAsync((void **)&tmp, sizeof(double) * 2 * N, c->stream));
+    const int rc = fd_jacobian_minimal(c->stream, mx, my, q, u, g, F0, vals9, tmp, tmp + N);
+    cudaFreeAsync(tmp, c->stream);
+    return rc;
+}
+int p4b_stencil9_apply(p4b_ctx *c, int mx, int my, const double *vals9, const double *x, double *y) {
+    return launch_stencil9_apply(c->stream, mx, my, vals9, x, y);
+}
+int p4b_stencil9_lin(p4b_ctx *c, int mx, int my, const double *vals9, const double *u, const double *b, const double *pm1,
+                     double ca, double cb, double cg, int jacobi, double *out) {
+    return launch_stencil9_lin(c->stream, mx, my, vals9, u, b, pm1, ca, cb, cg, jacobi, out);
+}
+int p4b_dense_matvec(p4b_ctx *c, int n, const double *Ainv, const double *b, double *x) {
+    return launch_dense_matvec(c->stream, n, Ainv, b, x);
+}
+int p4b_stencil9_gershgorin(p4b_ctx *c, int mx, int my, const double *vals9, double *work, double *res) {
+    P4B_CHECK(launch_stencil9_rowratio(c->stream, mx, my, vals9, work));
+    return p4b_vec_norminf(c, (size_t)mx * my, work, res);
+}
+int p4b_inject2d(p4b_ctx *c, int cmx, int cmy, const double *uf, double *uc) {
+    return launch_inject2d(c->stream, cmx, cmy, 2 * cmx - 1, uf, uc);
+}
+int p4b_vec_axpby(p4b_ctx *c, size_t n, double a, const double *x, double b, const double *y, double *out) {
+    return launch_axpby_out(c->stream, (long long)n, a, x, b, y, out);
+}
+int p4b_vec_copy(p4b_ctx *c, size_t n, const double *x, double *y) {
+    P4B_CUDA(cudaMemcpyAsync(y, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
 struct p4b_sell {
     p4b_ctx *ctx;
     Sell *A;

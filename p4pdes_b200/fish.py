@@ -112,6 +112,61 @@ class Context:
     def aypx(self, a, x, y):
         L.check(self.lib.p4b_vec_aypx(self.h, x.numel(), a, x.data_ptr(), y.data_ptr()))
 
+    def axpby(self, a, x, b, y, out):
+        """out = a x + b y; x or y may be None (treated as zero) and may alias out."""
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        L.check(self.lib.p4b_vec_axpby(self.h, out.numel(), a, ptr(x), b, ptr(y), out.data_ptr()))
+
+    def copy(self, x, y):
+        L.check(self.lib.p4b_vec_copy(self.h, x.numel(), x.data_ptr(), y.data_ptr()))
+
+    def set(self, a, y):
+        L.check(self.lib.p4b_vec_set(self.h, y.numel(), a, y.data_ptr()))
+
+    def to_host(self, t):
+        self.sync()
+        return t.detach().cpu().numpy()
+
+    def from_host(self, a):
+        import numpy as np
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64).ravel()).to("cuda:%d" % self.device)
+
+    # ---- 2-D assembled-Jacobian path (minimal.c; include/p4b200.h "assembled Jacobians") ----
+    def grid2d(self, mx, my):
+        return L.make_grid(2, (mx, my), (1.0, 1.0, 1.0), (1.0, 1.0, 1.0))
+
+    def initial_state2d(self, grid, g, u):
+        self.initial_state(grid, g, True, u)
+
+    def minimal_sample(self, mx, my, problem, tent_H, catenoid_c, g):
+        L.check(self.lib.p4b_minimal_sample(self.h, mx, my, problem, tent_H, catenoid_c, g.data_ptr()))
+
+    def minimal_function(self, mx, my, q, u, g, FF):
+        L.check(self.lib.p4b_minimal_function(self.h, mx, my, q, u.data_ptr(), g.data_ptr(), FF.data_ptr()))
+
+    def minimal_jacobian_fd(self, mx, my, q, u, g, F0, vals):
+        L.check(self.lib.p4b_minimal_jacobian_fd(self.h, mx, my, q, u.data_ptr(), g.data_ptr(), F0.data_ptr(),
+                                                 vals.data_ptr()))
+
+    def stencil9_apply(self, mx, my, vals, x, y):
+        L.check(self.lib.p4b_stencil9_apply(self.h, mx, my, vals.data_ptr(), x.data_ptr(), y.data_ptr()))
+
+    def stencil9_lin(self, mx, my, vals, u, b, pm1, ca, cb, cg, jacobi, out):
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        L.check(self.lib.p4b_stencil9_lin(self.h, mx, my, vals.data_ptr(), u.data_ptr(), ptr(b), ptr(pm1), ca, cb, cg,
+                                          int(bool(jacobi)), out.data_ptr()))
+
+    def stencil9_gershgorin(self, mx, my, vals, work):
+        r = C.c_double()
+        L.check(self.lib.p4b_stencil9_gershgorin(self.h, mx, my, vals.data_ptr(), work.data_ptr(), C.byref(r)))
+        return r.value
+
+    def inject2d(self, cmx, cmy, ufine, ucoarse):
+        L.check(self.lib.p4b_inject2d(self.h, cmx, cmy, ufine.data_ptr(), ucoarse.data_ptr()))
+
+    def dense_matvec(self, n, Ainv, b, x):
+        L.check(self.lib.p4b_dense_matvec(self.h, n, Ainv.data_ptr(), b.data_ptr(), x.data_ptr()))
+
     def fish_sample(self, g, problem, f=None, gb=None):
         L.check(self.lib.p4b_fish_sample(self.h, C.byref(g), L.PROBLEMS[problem],
                                          f.data_ptr() if f is not None else None,

@@ -1,0 +1,143 @@
+"""NumPy stand-in for the device Context, so that the control flow of p4pdes_b200/minimal.py (Newton, line search,
+GMRES/CG, the multigrid cycle, grid sequencing) can be exercised on a machine without a GPU.
+
+TEST INFRASTRUCTURE ONLY: the product never imports this file; every operation here is a restatement from oracle/ of
+the C-ABI call of the same name (include/p4b200.h).  GPU tests run the same driver on the real Context."""
+import numpy as np
+import scipy.sparse as sp
+
+from oracle import fish_oracle as fo
+from oracle import minimal_pattern_oracle as mpo
+from oracle import minimal_solver_oracle as mso
+
+
+class Vec:
+    def __init__(self, a):
+        self.a = np.asarray(a, dtype=np.float64).ravel().copy()
+
+    def numel(self):
+        return self.a.size
+
+
+class FakeOps:
+    def __init__(self):
+        self.calls = {}
+
+    def _count(self, name):
+        self.calls[name] = self.calls.get(name, 0) + 1
+
+    # memory
+    def empty(self, n):
+        return Vec(np.full(int(n), np.nan))
+
+    def zeros(self, n):
+        return Vec(np.zeros(int(n)))
+
+    def to_host(self, t):
+        return t.a.copy()
+
+    def from_host(self, a):
+        return Vec(a)
+
+    def sync(self):
+        pass
+
+    # vectors
+    def dot(self, x, y):
+        return float(x.a @ y.a)
+
+    def norm2(self, x):
+        return float(np.linalg.norm(x.a))
+
+    def norminf(self, x):
+        return float(np.max(np.abs(x.a)))
+
+    def axpy(self, a, x, y):
+        y.a += a * x.a
+
+    def aypx(self, a, x, y):
+        y.a[:] = x.a + a * y.a
+
+    def axpby(self, a, x, b, y, out):
+        v = np.zeros(out.a.size)
+        if x is not None:
+            v = a * x.a
+        if y is not None:
+            v = v + b * y.a
+        out.a[:] = v
+
+    def copy(self, x, y):
+        y.a[:] = x.a
+
+    def set(self, a, y):
+        y.a[:] = a
+
+    # grids
+    def grid2d(self, mx, my):
+        return (mx, my)
+
+    def initial_state2d(self, grid, g, u):
+        mx, my = grid
+        gg = g.a.reshape(my, mx)
+        uu = np.zeros((my, mx))
+        uu[0, :], uu[-1, :], uu[:, 0], uu[:, -1] = gg[0, :], gg[-1, :], gg[:, 0], gg[:, -1]
+        u.a[:] = uu.ravel()
+
+    def _P(self, grid):
+        mx, my = grid
+        return sp.kron(fo.interp1d((my - 1) // 2 + 1), fo.interp1d((mx - 1) // 2 + 1), format="csr")
+
+    def restrict(self, grid, rf, bc):
+        self._count("restrict")
+        bc.a[:] = self._P(grid).T @ rf.a
+
+    def prolong_add(self, grid, xc, xf):
+        self._count("prolong_add")
+        xf.a += self._P(grid) @ xc.a
+
+    def inject2d(self, cmx, cmy, uf, uc):
+        uc.a[:] = uf.a.reshape(2 * cmy - 1, 2 * cmx - 1)[::2, ::2].ravel()
+
+    # minimal.c callbacks and assembled Jacobians
+    def minimal_sample(self, mx, my, problem, tent_H, c, g):
+        g.a[:] = mpo.minimal_g(mx, my, "tent" if problem == 0 else "catenoid", tent_H, c).ravel()
+
+    def minimal_function(self, mx, my, q, u, g, FF):
+        self._count("minimal_function")
+        FF.a[:] = mpo.minimal_function(u.a.reshape(my, mx), g.a.reshape(my, mx), q).ravel()
+
+    def minimal_jacobian_fd(self, mx, my, q, u, g, F0, vals):
+        self._count("minimal_jacobian_fd")
+        gg = g.a.reshape(my, mx)
+        A = mso.fd_jacobian(lambda w: mpo.minimal_function(w, gg, q), u.a.reshape(my, mx), F0.a.reshape(my, mx)).tocoo()
+        v = np.zeros((9, my * mx))
+        dj = A.col // mx - A.row // mx
+        di = A.col % mx - A.row % mx
+        v[3 * (dj + 1) + (di + 1), A.row] = A.data
+        vals.a[:] = v.ravel()
+
+    def _csr(self, mx, my, vals):
+        from p4pdes_b200.minimal import stencil9_to_csr
+        rp, ci, d = stencil9_to_csr(vals.a, mx, my)
+        return sp.csr_matrix((d, ci, rp), shape=(mx * my, mx * my))
+
+    def stencil9_apply(self, mx, my, vals, x, y):
+        self._count("stencil9_apply")
+        y.a[:] = self._csr(mx, my, vals) @ x.a
+
+    def stencil9_lin(self, mx, my, vals, u, b, pm1, ca, cb, cg, jacobi, out):
+        self._count("stencil9_lin")
+        A = self._csr(mx, my, vals)
+        r = (b.a if b is not None else 0.0) - A @ u.a
+        if jacobi:
+            r = r / A.diagonal()
+        o = cb * u.a + cg * r
+        if pm1 is not None:
+            o = o + ca * pm1.a
+        out.a[:] = o
+
+    def stencil9_gershgorin(self, mx, my, vals, work):
+        return mso.gershgorin_jacobi(self._csr(mx, my, vals))
+
+    def dense_matvec(self, n, Ainv, b, x):
+        x.a[:] = Ainv.a.reshape(n, n) @ b.a
