@@ -243,6 +243,25 @@ int p4b_dense_matvec(p4b_ctx *ctx, int n, const double *Ainv, const double *b, d
 int p4b_stencil9_gershgorin(p4b_ctx *ctx, int mx, int my, const double *vals9, double *work, double *result_host);
 /* [PETSc] DMCreateInjection (DMDA, ratio 2): uc(I,J) = uf(2I,2J); fine grid (2cmx-1) x (2cmy-1) */
 int p4b_inject2d(p4b_ctx *ctx, int cmx, int cmy, const double *ufine, double *ucoarse);
+/* ---- pattern.c implicit stage equation F(t,Y,(Y-Y0)/dt) = G(t,Y): its Jacobian, matrix-free, on a periodic level ----
+ *   J X = shift*X - C L9(X) - G'(Y) X : FormIJacobianLocal (c/ch5/pattern.c:274-318) minus FormRHSJacobianLocal
+ *   (:202-236) at the iterate Y ([PETSc] TSComputeIJacobian); Y == NULL drops the RHS block (-ptn_no_rhsjacobian).
+ *   p4b_pattern_jac_apply     out = J X                                        [PETSc] MatMult
+ *   p4b_pattern_jac_lin       out = ca*pm1 + cb*X + cg*B(b - J X), B = diag(J)^-1 (jacobi) or I   smoother step / residual
+ *   p4b_pattern_jac_gershgorin max over rows of sum_j |J_nj| / |J_nn|          Chebyshev target
+ *   p4b_pattern_restrict / _prolong_add / _inject   [PETSc] DMCreateInterpolation/Injection on the periodic 2-dof DMDA
+ *                             (fine grid 2Mx x 2My, coarse Mx x My; R = P^T)
+ * All vectors: my*mx*2 doubles, (u,v) interleaved, i fastest. */
+int p4b_pattern_jac_apply(p4b_ctx *ctx, int mx, int my, double L, double Du, double Dv, double phi, double kappa,
+                          double shift, const double *Y, const double *X, double *out);
+int p4b_pattern_jac_lin(p4b_ctx *ctx, int mx, int my, double L, double Du, double Dv, double phi, double kappa,
+                        double shift, const double *Y, const double *X, const double *b, const double *pm1, double ca,
+                        double cb, double cg, int jacobi, double *out);
+int p4b_pattern_jac_gershgorin(p4b_ctx *ctx, int mx, int my, double L, double Du, double Dv, double phi, double kappa,
+                               double shift, const double *Y, double *work, double *result_host);
+int p4b_pattern_restrict(p4b_ctx *ctx, int Mx, int My, const double *rfine, double *bcoarse);
+int p4b_pattern_prolong_add(p4b_ctx *ctx, int Mx, int My, const double *xcoarse, double *xfine);
+int p4b_pattern_inject(p4b_ctx *ctx, int Mx, int My, const double *yfine, double *ycoarse);
 /* out = a x + b y (x, y may alias out) and a device-to-device copy: [PETSc] VecAXPBY / VecWAXPY / VecCopy */
 int p4b_vec_axpby(p4b_ctx *ctx, size_t n, double a, const double *x, double b, const double *y, double *out);
 int p4b_vec_copy(p4b_ctx *ctx, size_t n, const double *x, double *y);

@@ -1,0 +1,143 @@
+"""CPU oracle for the implicit time stepping around c/ch5/pattern.c  (TEST INFRASTRUCTURE ONLY).
+
+pattern.c hands PETSc the split system F(t,Y,Ydot) = G(t,Y) (IFunction / RHSFunction and their Jacobians, restated in
+minimal_pattern_oracle.py) and calls TSSolve (c/ch5/pattern.c:99-125).  This file restates the PETSc pieces of the
+implicit runs the reference uses (c/ch5/makefile:52-53 `-ts_type beuler -pc_type mg`):
+
+  backward Euler   [PETSc] TSTHETA, theta = 1, fixed step (TSAdapt none), TS_EXACTFINALTIME_MATCHSTEP: each step solves
+                   R(Y) = F(t+dt, Y, (Y - Y_n)/dt) - G(t+dt, Y) = 0 from the guess Y = Y_n
+  Jacobian         [PETSc] TSComputeIJacobian: shift dF/dYdot + dF/dY - dG/dY, shift = 1/dt; without FormRHSJacobianLocal
+                   (-ptn_no_rhsjacobian) the dG/dY block is missing and Newton runs with the approximate Jacobian
+  Newton / GMRES   minimal_solver_oracle.newton / gmres (SNESNEWTONLS + bt, KSPGMRES(30) left-preconditioned)
+  PCMG             periodic DMDA Q1 interpolation (ratio 2), R = P^T, level operators rediscretised on every level at
+                   the injected iterate, Chebyshev(2)/Jacobi, dense LU on the base grid
+
+Pinned on c/ch5/output/pattern.test2 (banner, one Newton iteration at -snes_rtol 0.1, TS lines); the golden's KSP count
+(3) belongs to PETSc's Chebyshev/SOR smoother -- Chebyshev/Jacobi has no golden: parity unpinned there.
+ARKIMEX (the reference's default, pattern.test1/4), BDF and CN runs are not restated.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import fish_oracle as fo
+from . import minimal_pattern_oracle as mpo
+from . import minimal_solver_oracle as mso
+
+
+def interp1d_periodic(M):
+    """(2M x M): fine 2I <- coarse I; fine 2I+1 <- (coarse I + coarse (I+1) mod M) / 2."""
+    rows, cols, vals = [], [], []
+    for I in range(M):
+        rows.append(2 * I); cols.append(I); vals.append(1.0)
+        rows += [2 * I + 1, 2 * I + 1]; cols += [I, (I + 1) % M]; vals += [0.5, 0.5]
+    return sp.csr_matrix((vals, (rows, cols)), shape=(2 * M, M))
+
+
+def interpolation(Mx, My):
+    """P: coarse (My, Mx, 2) -> fine (2My, 2Mx, 2), interleaved components."""
+    return sp.csr_matrix(sp.kron(sp.kron(interp1d_periodic(My), interp1d_periodic(Mx)), sp.eye(2), format="csr"))
+
+
+def rhs_jacobian(Y, phi=0.024, kappa=0.06):
+    """FormRHSJacobianLocal, pattern.c:202-236: 2 x 2 pointwise blocks, interleaved ordering."""
+    u, v = Y[..., 0].ravel(), Y[..., 1].ravel()
+    n = u.size
+    uv, v2 = u * v, v * v
+    k = np.arange(n)
+    rows = np.concatenate([2 * k, 2 * k, 2 * k + 1, 2 * k + 1])
+    cols = np.concatenate([2 * k, 2 * k + 1, 2 * k, 2 * k + 1])
+    vals = np.concatenate([-v2 - phi, -2.0 * uv, v2, 2.0 * uv - (phi + kappa)])
+    return sp.csr_matrix((vals, (rows, cols)), shape=(2 * n, 2 * n))
+
+
+def stage_jacobian(Y, shift, rhsjac=True, L=2.5, Du=8.0e-5, Dv=4.0e-5, phi=0.024, kappa=0.06):
+    my, mx, _ = Y.shape
+    J = mpo.pattern_ijacobian(mx, my, shift, L, Du, Dv)
+    if rhsjac:
+        J = J - rhs_jacobian(Y, phi, kappa)
+    return sp.csr_matrix(J)
+
+
+class PatternMG:
+    """V cycle on rediscretised level operators (finest first), Chebyshev(its)/Jacobi, Gershgorin targets."""
+
+    def __init__(self, Y, shift, base, rhsjac, its=2, **par):
+        self.A, self.P = [], []
+        Yl = Y
+        while True:
+            self.A.append(stage_jacobian(Yl, shift, rhsjac, **par))
+            my, mx, _ = Yl.shape
+            if mx <= base or mx % 2 or my % 2:
+                break
+            self.P.append(interpolation(mx // 2, my // 2))
+            Yl = Yl[::2, ::2, :].copy()                       # DMCreateInjection
+        self.eig = [(0.1 * mso.gershgorin_jacobi(a), 1.1 * mso.gershgorin_jacobi(a)) for a in self.A[:-1]]
+        self.dinv = [1.0 / a.diagonal() for a in self.A]
+        self.coarse = np.linalg.inv(self.A[-1].toarray())
+        self.its = its
+
+    def _smooth(self, l, b, x):
+        class _J:
+            def __init__(s, d): s.d = d
+            def apply(s, r): return s.d * r
+        return fo.chebyshev_smooth(self.A[l], _J(self.dinv[l]), b, x, self.eig[l][0], self.eig[l][1], self.its)
+
+    def _cycle(self, l, b, x):
+        if l == len(self.A) - 1:
+            return self.coarse @ b
+        x = self._smooth(l, b, x)
+        r = b - self.A[l] @ x
+        xc = self._cycle(l + 1, self.P[l].T @ r, np.zeros(self.P[l].shape[1]))
+        return self._smooth(l, b, x + self.P[l] @ xc)
+
+    def apply(self, r):
+        return self._cycle(0, r, np.zeros_like(r))
+
+
+@dataclass
+class PatternResult:
+    Y: np.ndarray
+    mx: int
+    steps: list = field(default_factory=list)        # (t_after, dt, NewtonResult)
+    lines: list = field(default_factory=list)
+
+
+def fmt_g(v):
+    """PETSc's %g: an integral value prints with a trailing '.' ("5.", "200.")."""
+    s = "%g" % v
+    return s + "." if s.lstrip("-").isdigit() else s
+
+
+def pattern_beuler(grid=3, refine=0, dt=5.0, tmax=200.0, pc="mg", rhsjac=True, snes_rtol=1.0e-8, ksp_rtol=1.0e-5,
+                   smooth_its=2, max_steps=10000, L=2.5, Du=8.0e-5, Dv=4.0e-5, phi=0.024, kappa=0.06):
+    mx = grid * 2 ** refine
+    par = dict(L=L, Du=Du, Dv=Dv, phi=phi, kappa=kappa)
+    Y = mpo.pattern_initial_state(mx, mx, L)
+    res = PatternResult(Y=Y, mx=mx)
+    res.lines.append("running on %d x %d grid with square cells of side h = %.6f ..." % (mx, mx, L / mx))
+    t, k = 0.0, 0
+    while t < tmax - 1e-14 * max(1.0, abs(tmax)) and k < max_steps:
+        step = min(dt, tmax - t)
+        res.lines.append("%d TS dt %s time %s" % (k, fmt_g(step), fmt_g(t)))
+        Y0 = Y.copy()
+        shift = 1.0 / step
+        R = lambda W: mpo.pattern_ifunction(W, (W - Y0) * shift, L, Du, Dv) - mpo.pattern_rhsfunction(W, phi, kappa)
+        jac = lambda W: stage_jacobian(W, shift, rhsjac, **par)
+
+        def make_pc(J, W):
+            if pc == "none":
+                return lambda r: r
+            if pc == "ilu":
+                return fo.ILU0PC(J).apply
+            return PatternMG(W, shift, grid, rhsjac, smooth_its, **par).apply
+
+        nr = mso.newton(R, Y, make_pc, jac=jac, snes_rtol=snes_rtol, ksp_rtol=ksp_rtol)
+        Y = nr.u
+        t += step
+        k += 1
+        res.steps.append((t, step, nr))
+    res.lines.append("%d TS dt %s time %s" % (k, fmt_g(res.steps[-1][1] if res.steps else dt), fmt_g(t)))
+    res.Y = Y
+    return res

@@ -165,4 +165,128 @@ int launch_inject2d(cudaStream_t st, int cmx, int cmy, int fmx, const double *uf
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// pattern.c: the Jacobian of the implicit stage equation  F(t, Y, (Y - Y0)/dt) = G(t, Y)
+//     J X = shift*X - C L9(X) - G'(Y) X       ([PETSc] TSComputeIJacobian: shift dF/dYdot + dF/dY, minus the RHS Jacobian)
+// with L9 = [1 4 1; 4 -20 4; 1 4 1] periodic (c/ch5/pattern.c:274-318) and the 2 x 2 pointwise blocks of
+// FormRHSJacobianLocal (:202-236) evaluated at the level's iterate Y (Y == nullptr: -ptn_no_rhsjacobian, the block
+// is dropped).  Applied matrix-free: the operator is a constant stencil plus a pointwise block, storing it would
+// only add traffic.  MODE 0: out = J X.   MODE 1: out = ca*pm1 + cb*X + cg*B(b - J X), B = diag(J)^-1 or I.
+// MODE 2: out.x/.y = Gershgorin row ratios sum_j |J_nj| / |J_nn| of the two rows of the node.
+// ---------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) pattern_jac_kernel(int mx, int my, double Cu, double Cv, double shift, double phi,
+                                                           double kappa, const double2 *__restrict__ Y,
+                                                           const double2 *__restrict__ X, const double2 *b,
+                                                           const double2 *pm1, double ca, double cb, double cg,
+                                                           int jacobi, double2 *out) {
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= mx * my) return;
+    const int j = n / mx, i = n - j * mx;
+    // the RHS Jacobian block [[-v^2 - phi, -2uv], [v^2, 2uv - (phi + kappa)]] at this node
+    double g00 = 0.0, g01 = 0.0, g10 = 0.0, g11 = 0.0;
+    if (Y) {
+        const double2 y = Y[n];
+        const double uv = y.x * y.y, v2 = y.y * y.y;
+        g00 = -v2 - phi;  g01 = -2.0 * uv;  g10 = v2;  g11 = 2.0 * uv - (phi + kappa);
+    }
+    const double du = shift + 20.0 * Cu - g00, dv = shift + 20.0 * Cv - g11;      // diagonal of J
+    if (MODE == 2) {
+        out[n] = make_double2((fabs(du) + 20.0 * Cu + fabs(g01)) / fabs(du), (fabs(dv) + 20.0 * Cv + fabs(g10)) / fabs(dv));
+        return;
+    }
+    const int iw = (i == 0) ? mx - 1 : i - 1, ie = (i == mx - 1) ? 0 : i + 1;      // periodic wrap
+    const int js = (j == 0) ? my - 1 : j - 1, jn = (j == my - 1) ? 0 : j + 1;
+    const double2 c = X[n];
+    const double2 nw = X[jn * mx + iw], nn = X[jn * mx + i], ne = X[jn * mx + ie];
+    const double2 ww = X[j * mx + iw], ee = X[j * mx + ie];
+    const double2 sw = X[js * mx + iw], ss = X[js * mx + i], se = X[js * mx + ie];
+    const double lapu = nw.x + 4.0 * nn.x + ne.x + 4.0 * ww.x - 20.0 * c.x + 4.0 * ee.x + sw.x + 4.0 * ss.x + se.x;
+    const double lapv = nw.y + 4.0 * nn.y + ne.y + 4.0 * ww.y - 20.0 * c.y + 4.0 * ee.y + sw.y + 4.0 * ss.y + se.y;
+    const double Ju = shift * c.x - Cu * lapu - (g00 * c.x + g01 * c.y);
+    const double Jv = shift * c.y - Cv * lapv - (g10 * c.x + g11 * c.y);
+    if (MODE == 0) {
+        out[n] = make_double2(Ju, Jv);
+    } else {
+        const double2 bb = b ? b[n] : make_double2(0.0, 0.0);
+        double ru = bb.x - Ju, rv = bb.y - Jv;
+        if (jacobi) { ru /= du; rv /= dv; }
+        double ou = cb * c.x + cg * ru, ov = cb * c.y + cg * rv;
+        if (pm1) { const double2 p = pm1[n]; ou += ca * p.x; ov += ca * p.y; }
+        out[n] = make_double2(ou, ov);
+    }
+}
+
+int launch_pattern_jac(cudaStream_t st, int mode, int mx, int my, double Cu, double Cv, double shift, double phi,
+                       double kappa, const double *Y, const double *X, const double *b, const double *pm1, double ca,
+                       double cb, double cg, int jacobi, double *out) {
+    const int N = mx * my;
+    if (N <= 0) return 0;
+    const unsigned nb = (unsigned)((N + 255) / 256);
+    const double2 *Y2 = reinterpret_cast<const double2 *>(Y), *X2 = reinterpret_cast<const double2 *>(X);
+    const double2 *b2 = reinterpret_cast<const double2 *>(b), *p2 = reinterpret_cast<const double2 *>(pm1);
+    double2 *o2 = reinterpret_cast<double2 *>(out);
+    if (mode == 0) pattern_jac_kernel<0><<<nb, 256, 0, st>>>(mx, my, Cu, Cv, shift, phi, kappa, Y2, X2, b2, p2, ca, cb, cg, jacobi, o2);
+    else if (mode == 1) pattern_jac_kernel<1><<<nb, 256, 0, st>>>(mx, my, Cu, Cv, shift, phi, kappa, Y2, X2, b2, p2, ca, cb, cg, jacobi, o2);
+    else pattern_jac_kernel<2><<<nb, 256, 0, st>>>(mx, my, Cu, Cv, shift, phi, kappa, Y2, X2, b2, p2, ca, cb, cg, jacobi, o2);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+
+// [PETSc] DMCreateInterpolation on a PERIODIC 2-dof DMDA (ratio 2, fine m = 2 M): fine node 2I coincides with coarse I,
+// fine node 2I+1 averages coarse I and (I+1) mod M; tensor product in x and y, the same for both components.
+// mode 0: restriction b_c = P^T r      mode 1: prolongation x_f += P x_c      mode 2: injection y_c(I,J) = y_f(2I,2J)
+__global__ void __launch_bounds__(256) pattern_transfer_kernel(int mode, int Mx, int My, const double2 *__restrict__ src,
+                                                                double2 *__restrict__ dst) {
+    const int fx = 2 * Mx, fy = 2 * My;
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (mode == 1) {
+        if (n >= fx * fy) return;
+        const int j = n / fx, i = n - j * fx;
+        const int I0 = i >> 1, I1 = (i & 1) ? (I0 + 1 == Mx ? 0 : I0 + 1) : I0;
+        const int J0 = j >> 1, J1 = (j & 1) ? (J0 + 1 == My ? 0 : J0 + 1) : J0;
+        const double2 a = src[J0 * Mx + I0], b = src[J0 * Mx + I1], c = src[J1 * Mx + I0], d = src[J1 * Mx + I1];
+        double2 o = dst[n];
+        o.x += 0.25 * ((a.x + b.x) + (c.x + d.x));
+        o.y += 0.25 * ((a.y + b.y) + (c.y + d.y));
+        dst[n] = o;
+        return;
+    }
+    if (n >= Mx * My) return;
+    const int J = n / Mx, I = n - J * Mx;
+    if (mode == 2) {
+        dst[n] = src[(2 * J) * fx + 2 * I];
+        return;
+    }
+    double su = 0.0, sv = 0.0;
+#pragma unroll
+    for (int dj = -1; dj <= 1; dj++) {
+        int jf = 2 * J + dj;
+        jf = jf < 0 ? jf + fy : (jf >= fy ? jf - fy : jf);
+        const double wj = dj ? 0.5 : 1.0;
+        double ru = 0.0, rv = 0.0;
+#pragma unroll
+        for (int di = -1; di <= 1; di++) {
+            int i_f = 2 * I + di;
+            i_f = i_f < 0 ? i_f + fx : (i_f >= fx ? i_f - fx : i_f);
+            const double2 v = src[jf * fx + i_f];
+            const double wi = di ? 0.5 : 1.0;
+            ru += wi * v.x;
+            rv += wi * v.y;
+        }
+        su += wj * ru;
+        sv += wj * rv;
+    }
+    dst[n] = make_double2(su, sv);
+}
+
+int launch_pattern_transfer(cudaStream_t st, int mode, int Mx, int My, const double *src, double *dst) {
+    const int N = (mode == 1) ? 4 * Mx * My : Mx * My;
+    if (N <= 0) return 0;
+    pattern_transfer_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(mode, Mx, My, reinterpret_cast<const double2 *>(src),
+                                                                       reinterpret_cast<double2 *>(dst));
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace p4b

@@ -95,6 +95,10 @@ void sell_info(const Sell *A, int *nrows, long long *nnz, long long *padded);
 int fd_jacobian_minimal(cudaStream_t st, int mx, int my, double q, const double *u, const double *g, const double *F0,
                         double *vals, double *up, double *Fp);
 int launch_stencil9_apply(cudaStream_t st, int mx, int my, const double *vals, const double *x, double *y);
+int launch_pattern_jac(cudaStream_t st, int mode, int mx, int my, double Cu, double Cv, double shift, double phi,
+                       double kappa, const double *Y, const double *X, const double *b, const double *pm1, double ca,
+                       double cb, double cg, int jacobi, double *out);
+int launch_pattern_transfer(cudaStream_t st, int mode, int Mx, int My, const double *src, double *dst);
 int launch_stencil9_rowratio(cudaStream_t st, int mx, int my, const double *vals, double *out);
 int launch_inject2d(cudaStream_t st, int cmx, int cmy, int fmx, const double *uf, double *uc);
 int launch_stencil9_lin(cudaStream_t st, int mx, int my, const double *vals, const double *u, const double *b,

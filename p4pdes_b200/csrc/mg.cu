@@ -1592,6 +1592,43 @@ int p4b_pattern_ijacobian_mult(p4b_ctx *c, int mx, int my, double L, double Du, 
     return launch_pattern_ifunction(c->stream, mx, my, Du / (6.0 * h * h), Dv / (6.0 * h * h), 1, shift, X, nullptr, JX);
 }
 
+static int pattern_coef(int mx, int my, double L, double Du, double Dv, double *Cu, double *Cv) {
+    if (mx < 3 || my < 3) return fail(60, "periodic grid needs at least 3 nodes per dimension");
+    const double h = L / (double)mx;
+    *Cu = Du / (6.0 * h * h);
+    *Cv = Dv / (6.0 * h * h);
+    return 0;
+}
+int p4b_pattern_jac_apply(p4b_ctx *c, int mx, int my, double L, double Du, double Dv, double phi, double kappa,
+                          double shift, const double *Y, const double *X, double *out) {
+    double Cu, Cv;
+    P4B_CHECK(pattern_coef(mx, my, L, Du, Dv, &Cu, &Cv));
+    return launch_pattern_jac(c->stream, 0, mx, my, Cu, Cv, shift, phi, kappa, Y, X, nullptr, nullptr, 0, 0, 0, 0, out);
+}
+int p4b_pattern_jac_lin(p4b_ctx *c, int mx, int my, double L, double Du, double Dv, double phi, double kappa,
+                        double shift, const double *Y, const double *X, const double *b, const double *pm1, double ca,
+                        double cb, double cg, int jacobi, double *out) {
+    double Cu, Cv;
+    P4B_CHECK(pattern_coef(mx, my, L, Du, Dv, &Cu, &Cv));
+    return launch_pattern_jac(c->stream, 1, mx, my, Cu, Cv, shift, phi, kappa, Y, X, b, pm1, ca, cb, cg, jacobi, out);
+}
+int p4b_pattern_jac_gershgorin(p4b_ctx *c, int mx, int my, double L, double Du, double Dv, double phi, double kappa,
+                               double shift, const double *Y, double *work, double *res) {
+    double Cu, Cv;
+    P4B_CHECK(pattern_coef(mx, my, L, Du, Dv, &Cu, &Cv));
+    P4B_CHECK(launch_pattern_jac(c->stream, 2, mx, my, Cu, Cv, shift, phi, kappa, Y, Y, nullptr, nullptr, 0, 0, 0, 0, work));
+    return p4b_vec_norminf(c, (size_t)2 * mx * my, work, res);
+}
+int p4b_pattern_restrict(p4b_ctx *c, int Mx, int My, const double *rf, double *bc) {
+    return launch_pattern_transfer(c->stream, 0, Mx, My, rf, bc);
+}
+int p4b_pattern_prolong_add(p4b_ctx *c, int Mx, int My, const double *xc, double *xf) {
+    return launch_pattern_transfer(c->stream, 1, Mx, My, xc, xf);
+}
+int p4b_pattern_inject(p4b_ctx *c, int Mx, int My, const double *yf, double *yc) {
+    return launch_pattern_transfer(c->stream, 2, Mx, My, yf, yc);
+}
+
 int p4b_minimal_jacobian_fd(p4b_ctx *c, int mx, int my, double q, const double *u, const double *g, const double *F0,
                             double *vals9) {
     if (mx < 3 || my < 3) return fail(60, "minimal Jacobian: grid must be at least 3 x 3");

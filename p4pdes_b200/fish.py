@@ -167,6 +167,40 @@ class Context:
     def dense_matvec(self, n, Ainv, b, x):
         L.check(self.lib.p4b_dense_matvec(self.h, n, Ainv.data_ptr(), b.data_ptr(), x.data_ptr()))
 
+    # ---- pattern.c implicit stage equation (include/p4b200.h "pattern.c implicit stage equation") ----
+    def pattern_initial_state(self, mx, my, Lside, Y):
+        L.check(self.lib.p4b_pattern_initial_state(self.h, mx, my, Lside, Y.data_ptr()))
+
+    def pattern_ifunction(self, mx, my, Lside, Du, Dv, Y, Ydot, F):
+        L.check(self.lib.p4b_pattern_ifunction(self.h, mx, my, Lside, Du, Dv, Y.data_ptr(), Ydot.data_ptr(), F.data_ptr()))
+
+    def pattern_rhsfunction(self, mx, my, phi, kappa, Y, G):
+        L.check(self.lib.p4b_pattern_rhsfunction(self.h, mx, my, phi, kappa, Y.data_ptr(), G.data_ptr()))
+
+    def pattern_jac_apply(self, m, Lside, Du, Dv, phi, kappa, shift, Y, X, out):
+        L.check(self.lib.p4b_pattern_jac_apply(self.h, m, m, Lside, Du, Dv, phi, kappa, shift,
+                                               Y.data_ptr() if Y is not None else None, X.data_ptr(), out.data_ptr()))
+
+    def pattern_jac_lin(self, m, Lside, Du, Dv, phi, kappa, shift, Y, X, b, pm1, ca, cb, cg, jacobi, out):
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        L.check(self.lib.p4b_pattern_jac_lin(self.h, m, m, Lside, Du, Dv, phi, kappa, shift, ptr(Y), X.data_ptr(), ptr(b),
+                                             ptr(pm1), ca, cb, cg, int(bool(jacobi)), out.data_ptr()))
+
+    def pattern_jac_gershgorin(self, m, Lside, Du, Dv, phi, kappa, shift, Y, work):
+        r = C.c_double()
+        L.check(self.lib.p4b_pattern_jac_gershgorin(self.h, m, m, Lside, Du, Dv, phi, kappa, shift,
+                                                    Y.data_ptr() if Y is not None else None, work.data_ptr(), C.byref(r)))
+        return r.value
+
+    def pattern_restrict(self, Mx, My, rf, bc):
+        L.check(self.lib.p4b_pattern_restrict(self.h, Mx, My, rf.data_ptr(), bc.data_ptr()))
+
+    def pattern_prolong_add(self, Mx, My, xc, xf):
+        L.check(self.lib.p4b_pattern_prolong_add(self.h, Mx, My, xc.data_ptr(), xf.data_ptr()))
+
+    def pattern_inject(self, Mx, My, yf, yc):
+        L.check(self.lib.p4b_pattern_inject(self.h, Mx, My, yf.data_ptr(), yc.data_ptr()))
+
     def fish_sample(self, g, problem, f=None, gb=None):
         L.check(self.lib.p4b_fish_sample(self.h, C.byref(g), L.PROBLEMS[problem],
                                          f.data_ptr() if f is not None else None,

@@ -132,6 +132,13 @@ _SIGS = {
     "p4b_inject2d": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
     "p4b_vec_axpby": (C.c_int, [_P, C.c_size_t, C.c_double, _D, C.c_double, _D, _D]),
     "p4b_vec_copy": (C.c_int, [_P, C.c_size_t, _D, _D]),
+    "p4b_pattern_jac_apply": (C.c_int, [_P, C.c_int, C.c_int] + [C.c_double] * 6 + [_D, _D, _D]),
+    "p4b_pattern_jac_lin": (C.c_int, [_P, C.c_int, C.c_int] + [C.c_double] * 6 + [_D, _D, _D, _D, C.c_double, C.c_double,
+                                                                                  C.c_double, C.c_int, _D]),
+    "p4b_pattern_jac_gershgorin": (C.c_int, [_P, C.c_int, C.c_int] + [C.c_double] * 6 + [_D, _D, C.POINTER(C.c_double)]),
+    "p4b_pattern_restrict": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
+    "p4b_pattern_prolong_add": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
+    "p4b_pattern_inject": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
     "p4b_sell_create": (C.c_int, [_P, C.c_int, _P, _P, _P, C.POINTER(_P)]),
     "p4b_sell_spmv": (C.c_int, [_P, _D, _D]),
     "p4b_sell_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

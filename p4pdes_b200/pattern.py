@@ -1,0 +1,332 @@
+"""Host-side mirror of c/ch5/pattern.c for its IMPLICIT runs, on top of the C ABI (include/p4b200.h).
+
+`pattern_main(argv)` takes pattern.c's command line (`-ptn_*`, c/ch5/pattern.c:54-78; `-da_grid_x/_y -da_refine -ts_type
+beuler -ts_dt -ts_max_time -pc_type mg -snes_rtol ...`: c/ch5/makefile:52-53), runs
+pattern.c:main -- periodic 2-dof DMDA, banner, InitialState, TSSolve -- and prints the reference's lines.  Inside TSSolve:
+
+  backward Euler           [PETSc] TSTHETA(theta = 1), fixed step, final step matched to -ts_max_time
+  stage residual           p4b_pattern_ifunction (pattern.c:242-267) with Ydot = (Y - Y_n)/dt, minus p4b_pattern_rhsfunction
+                           (:185-199)
+  stage Jacobian           shift*I - C L9 - G'(Y), matrix-free: p4b_pattern_jac_apply (FormIJacobianLocal :274-318 and
+                           FormRHSJacobianLocal :202-236; `-ptn_no_rhsjacobian` drops G')
+  Newton / GMRES           the device loops of p4pdes_b200/minimal.py (SNESNEWTONLS + bt, KSPGMRES(30))
+  -pc_type mg              V cycle on the rediscretised level operators at the injected iterate: p4b_pattern_jac_lin
+                           (Chebyshev + Jacobi), p4b_pattern_restrict / _prolong_add / _inject (periodic Q1), dense inverse
+                           of the base-grid operator x vector
+
+ARKIMEX (pattern.c's default type), BDF, CN, time-step adaptivity and `-ptn_noisy_init` (PETSc's random stream) are not
+provided: `-ts_type beuler` is required.  No CPU path: `ops` must be a device Context (tests/ substitutes a NumPy
+stand-in to exercise this file's control flow without a GPU).
+"""
+from __future__ import annotations
+
+import math
+import shlex
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .minimal import KSPResult, SNESResult, gmres, linesearch_bt
+
+
+@dataclass
+class PatternOptions:
+    L: float = 2.5
+    Du: float = 8.0e-5
+    Dv: float = 4.0e-5
+    phi: float = 0.024
+    kappa: float = 0.06
+    no_rhsjacobian: bool = False
+    call_back_report: bool = False
+    grid_x: int = 3
+    grid_y: int = 3
+    refine: int = 0
+    ts_type: str = "arkimex"
+    ts_dt: float = 5.0
+    ts_max_time: float = 200.0
+    ts_max_steps: int = 5000
+    ts_monitor: bool = False
+    pc_type: str = "mg"
+    smooth_its: int = 2
+    snes_rtol: float = 1.0e-8
+    snes_stol: float = 1.0e-8
+    snes_atol: float = 1.0e-50
+    snes_max_it: int = 50
+    ksp_rtol: float = 1.0e-5
+    ksp_max_it: int = 10000
+    gmres_restart: int = 30
+    snes_converged_reason: bool = False
+    ksp_converged_reason: bool = False
+    log_view: bool = False
+
+
+def parse_options(argv) -> PatternOptions:
+    if isinstance(argv, str):
+        argv = shlex.split(argv)
+    o = PatternOptions()
+    flags = {"-ptn_no_rhsjacobian": "no_rhsjacobian", "-ptn_call_back_report": "call_back_report",
+             "-ts_monitor": "ts_monitor", "-snes_converged_reason": "snes_converged_reason",
+             "-ksp_converged_reason": "ksp_converged_reason", "-log_view": "log_view"}
+    valued = {"-ptn_L": ("L", float), "-ptn_Du": ("Du", float), "-ptn_Dv": ("Dv", float), "-ptn_phi": ("phi", float),
+              "-ptn_kappa": ("kappa", float), "-da_grid_x": ("grid_x", int), "-da_grid_y": ("grid_y", int),
+              "-da_refine": ("refine", int), "-ts_type": ("ts_type", str), "-ts_dt": ("ts_dt", float),
+              "-ts_max_time": ("ts_max_time", float), "-ts_max_steps": ("ts_max_steps", int), "-pc_type": ("pc_type", str),
+              "-mg_levels_ksp_max_it": ("smooth_its", int), "-snes_rtol": ("snes_rtol", float),
+              "-snes_max_it": ("snes_max_it", int), "-ksp_rtol": ("ksp_rtol", float), "-ksp_max_it": ("ksp_max_it", int),
+              "-ksp_gmres_restart": ("gmres_restart", int)}
+    accepted = {"-mg_levels_ksp_type": ("chebyshev",), "-mg_levels_pc_type": ("jacobi",), "-ksp_type": ("gmres",)}
+    i = 0
+    while i < len(argv):
+        a = argv[i]
+        if a in flags:
+            setattr(o, flags[a], True)
+            i += 1
+        elif a in valued:
+            name, typ = valued[a]
+            setattr(o, name, typ(argv[i + 1]))
+            i += 2
+        elif a in accepted:
+            if argv[i + 1] not in accepted[a]:
+                raise ValueError("%s %s: the device path provides %s only" % (a, argv[i + 1], "|".join(accepted[a])))
+            i += 2
+        elif a in ("-ptn_noisy_init", "-ptn_no_ijacobian"):
+            raise ValueError("%s is not provided by the device path (PETSc random stream / finite-difference IJacobian)" % a)
+        else:
+            raise ValueError("unknown or unsupported option %s" % a)
+    if o.ts_type != "beuler":
+        raise ValueError("-ts_type %s: the device path provides beuler (pattern.c's default arkimex, bdf and cn are not "
+                         "built)" % o.ts_type)
+    if o.pc_type not in ("mg", "none"):
+        raise ValueError("-pc_type %s: the device path provides mg and none (ilu/sor are sequential)" % o.pc_type)
+    return o
+
+
+class Level:
+    def __init__(self, ops, m, opt: PatternOptions):
+        self.ops, self.m, self.n = ops, m, 2 * m * m
+        self.Y = ops.empty(self.n)            # the iterate this level's operator is linearised at
+        self.x, self.b, self.t = ops.empty(self.n), ops.empty(self.n), ops.empty(self.n)
+        self.scale, self.omega = 0.0, []
+
+
+class StageOperator:
+    """J = shift*I - C L9 - G'(Y) on every level of the periodic hierarchy (levels[0] finest), with the V cycle."""
+
+    def __init__(self, ops, levels, opt: PatternOptions):
+        self.ops, self.levels, self.opt = ops, levels, opt
+        self.shift = 0.0
+        self.Ainv = None
+        self.par = (opt.L, opt.Du, opt.Dv, opt.phi, opt.kappa)
+
+    def _Y(self, L):
+        return None if self.opt.no_rhsjacobian else L.Y
+
+    def mult(self, x, y):
+        L = self.levels[0]
+        self.ops.pattern_jac_apply(L.m, *self.par, self.shift, self._Y(L), x, y)
+
+    def setup(self, shift):
+        """Linearise at levels[0].Y: injected iterates, Chebyshev targets, dense base-grid inverse."""
+        ops, opt = self.ops, self.opt
+        self.shift = shift
+        for l, L in enumerate(self.levels):
+            if l > 0:
+                ops.pattern_inject(L.m, L.m, self.levels[l - 1].Y, L.Y)
+            if l < len(self.levels) - 1:
+                lam = ops.pattern_jac_gershgorin(L.m, *self.par, shift, self._Y(L), L.t)
+                emin, emax = 0.1 * lam, 1.1 * lam
+                L.scale = 2.0 / (emax + emin)                      # [PETSc] KSPSolve_Chebyshev
+                alpha = 1.0 - L.scale * emin
+                mu, omegaprod = 1.0 / alpha, 2.0 / alpha
+                cm1, ck = 1.0, mu
+                L.omega = []
+                for _ in range(1, opt.smooth_its):
+                    cp1 = 2.0 * mu * ck - cm1
+                    L.omega.append(omegaprod * ck / cp1)
+                    cm1, ck = ck, cp1
+        C = self.levels[-1]
+        if C.n > 2048:
+            raise ValueError("base grid of the hierarchy has %d unknowns: use a coarser -da_grid_x/_y" % C.n)
+        Yc = None if opt.no_rhsjacobian else ops.to_host(C.Y).reshape(C.m, C.m, 2)
+        self.Ainv = ops.from_host(np.linalg.inv(dense_stage_jacobian(C.m, shift, Yc, *self.par)).ravel())
+
+    def _smooth(self, L, zero_guess):
+        ops, its = self.ops, self.opt.smooth_its
+        Y = self._Y(L)
+        if its <= 0:
+            if zero_guess:
+                ops.set(0.0, L.x)
+            return
+        pm1, pk = L.x, L.t
+        if zero_guess:
+            ops.set(0.0, pm1)
+        ops.pattern_jac_lin(L.m, *self.par, self.shift, Y, pm1, L.b, None, 0.0, 1.0, L.scale, True, pk)
+        for i in range(1, its):
+            w = L.omega[i - 1]
+            ops.pattern_jac_lin(L.m, *self.par, self.shift, Y, pk, L.b, pm1, 1.0 - w, w, w * L.scale, True, pm1)
+            pm1, pk = pk, pm1
+        if pk is not L.x:
+            L.x, L.t = L.t, L.x
+
+    def _cycle(self, l, zero_guess):
+        ops = self.ops
+        L = self.levels[l]
+        if l == len(self.levels) - 1:
+            ops.dense_matvec(L.n, self.Ainv, L.b, L.x)
+            return
+        C = self.levels[l + 1]
+        self._smooth(L, zero_guess)
+        ops.pattern_jac_lin(L.m, *self.par, self.shift, self._Y(L), L.x, L.b, None, 0.0, 0.0, 1.0, False, L.t)   # b - J x
+        ops.pattern_restrict(C.m, C.m, L.t, C.b)
+        self._cycle(l + 1, True)
+        ops.pattern_prolong_add(C.m, C.m, C.x, L.x)
+        self._smooth(L, False)
+
+    def precond(self, r, z):
+        if self.opt.pc_type == "none":
+            self.ops.copy(r, z)
+            return
+        L = self.levels[0]
+        self.ops.copy(r, L.b)
+        self._cycle(0, True)
+        self.ops.copy(L.x, z)
+
+
+def dense_stage_jacobian(m, shift, Y, L, Du, Dv, phi, kappa):
+    """Host copy of the (small) base-grid operator as a dense array ([PETSc] PCLU on the coarsest level)."""
+    h = L / m
+    C = (Du / (6.0 * h * h), Dv / (6.0 * h * h))
+    n = m * m
+    A = np.zeros((2 * n, 2 * n))
+    for j in range(m):
+        for i in range(m):
+            k = j * m + i
+            for c in (0, 1):
+                r = 2 * k + c
+                A[r, r] += shift + 20.0 * C[c]
+                for dj, di, w in ((0, -1, 4.0), (0, 1, 4.0), (-1, 0, 4.0), (1, 0, 4.0), (-1, -1, 1.0), (1, -1, 1.0),
+                                  (-1, 1, 1.0), (1, 1, 1.0)):
+                    A[r, 2 * (((j + dj) % m) * m + (i + di) % m) + c] += -w * C[c]
+            if Y is not None:
+                u, v = Y[j, i, 0], Y[j, i, 1]
+                A[2 * k, 2 * k] -= -v * v - phi
+                A[2 * k, 2 * k + 1] -= -2.0 * u * v
+                A[2 * k + 1, 2 * k] -= v * v
+                A[2 * k + 1, 2 * k + 1] -= 2.0 * u * v - (phi + kappa)
+    return A
+
+
+def fmt_g(v):
+    """PETSc's %g: an integral value prints with a trailing '.' ("5.", "200.")."""
+    s = "%g" % v
+    return s + "." if s.lstrip("-").isdigit() else s
+
+
+@dataclass
+class PatternReport:
+    m: int
+    steps: list
+    Y: object
+    seconds: float
+    lines: list
+
+
+def pattern_main(argv, ops, echo=False) -> PatternReport:
+    opt = parse_options(argv)
+    lines = []
+
+    def out(s):
+        lines.append(s)
+        if echo:
+            print(s)
+
+    mx, my = opt.grid_x * 2 ** opt.refine, opt.grid_y * 2 ** opt.refine     # periodic: -da_refine doubles
+    if mx != my:
+        raise ValueError("pattern.c requires mx == my")                                                  # pattern.c:89
+    m = mx
+    out("running on %d x %d grid with square cells of side h = %.6f ..." % (m, m, opt.L / m))          # :94-96
+    sizes = [m]
+    if opt.pc_type == "mg":
+        while sizes[-1] > opt.grid_x and sizes[-1] % 2 == 0:
+            sizes.append(sizes[-1] // 2)
+    levels = [Level(ops, s, opt) for s in sizes]
+    A = StageOperator(ops, levels, opt)
+    L0 = levels[0]
+    n = L0.n
+    Y, Y0, R, Ydot, G = L0.Y, ops.empty(n), ops.empty(n), ops.empty(n), ops.empty(n)
+    y, Jy, w, gnew = ops.empty(n), ops.empty(n), ops.empty(n), ops.empty(n)
+    work = [ops.empty(n) for _ in range(opt.gmres_restart + 1)]
+    ops.pattern_initial_state(m, m, opt.L, Y)                                                          # :146-179
+    t0 = time.perf_counter()
+    t, k, steps = 0.0, 0, []
+    dt_last = opt.ts_dt
+    while t < opt.ts_max_time - 1e-14 * max(1.0, abs(opt.ts_max_time)) and k < opt.ts_max_steps:
+        dt = min(opt.ts_dt, opt.ts_max_time - t)                   # TS_EXACTFINALTIME_MATCHSTEP (:118)
+        dt_last = dt
+        if opt.ts_monitor:
+            out("%d TS dt %s time %s" % (k, fmt_g(dt), fmt_g(t)))
+        shift = 1.0 / dt
+        ops.copy(Y, Y0)
+
+        def F(W, f):                                               # f = F(W, (W - Y0)/dt) - G(W)
+            ops.axpby(shift, W, -shift, Y0, Ydot)
+            ops.pattern_ifunction(m, m, opt.L, opt.Du, opt.Dv, W, Ydot, f)
+            ops.pattern_rhsfunction(m, m, opt.phi, opt.kappa, W, G)
+            ops.axpy(-1.0, G, f)
+
+        F(Y, R)
+        fnorm = ops.norm2(R)
+        res = SNESResult(fnorms=[fnorm])
+        ttol = opt.snes_rtol * fnorm
+        if fnorm < opt.snes_atol:
+            res.reason = "CONVERGED_FNORM_ABS"
+        while not res.reason:
+            if res.its >= opt.snes_max_it:
+                res.reason = "DIVERGED_MAX_IT"
+                break
+            A.setup(shift)
+            kr = gmres(ops, A.mult, R, y, A.precond, opt.ksp_rtol, restart=opt.gmres_restart, max_it=opt.ksp_max_it,
+                       work=work)
+            res.ksp_its.append(kr.its)
+            if opt.ksp_converged_reason:
+                out("      Linear solve %s due to %s iterations %d" % ("converged" if kr.reason.startswith("CONV")
+                                                                       else "did not converge", kr.reason, kr.its))
+            A.mult(y, Jy)
+            gnorm, lam = linesearch_bt(ops, F, Y, R, fnorm, y, Jy, w, gnew)
+            res.lambdas.append(lam)
+            ops.axpby(1.0, w, -1.0, Y, y)
+            snorm, xnorm = ops.norm2(y), ops.norm2(w)
+            ops.copy(w, Y)
+            ops.copy(gnew, R)
+            fnorm = gnorm
+            res.its += 1
+            res.fnorms.append(fnorm)
+            if not math.isfinite(fnorm):
+                res.reason = "DIVERGED_FNORM_NAN"
+            elif fnorm < opt.snes_atol:
+                res.reason = "CONVERGED_FNORM_ABS"
+            elif fnorm <= ttol:
+                res.reason = "CONVERGED_FNORM_RELATIVE"
+            elif snorm < opt.snes_stol * xnorm:
+                res.reason = "CONVERGED_SNORM_RELATIVE"
+        if opt.snes_converged_reason:
+            out("    Nonlinear solve %s due to %s iterations %d" % ("converged" if res.reason.startswith("CONV")
+                                                                    else "did not converge", res.reason, res.its))
+        if not res.reason.startswith("CONV"):
+            raise RuntimeError("TSSolve: nonlinear solve failed at step %d (%s)" % (k, res.reason))
+        t += dt
+        k += 1
+        steps.append((t, dt, res))
+    if opt.ts_monitor:
+        out("%d TS dt %s time %s" % (k, fmt_g(dt_last), fmt_g(t)))
+    ops.sync()
+    seconds = time.perf_counter() - t0
+    if opt.call_back_report:                                                                           # :127-135
+        out("CALL-BACK REPORT")
+        out("  solver type: %s" % opt.ts_type)
+        out("  IFunction:   1  | IJacobian:   1")
+        out("  RHSFunction: 1  | RHSJacobian: %d" % (0 if opt.no_rhsjacobian else 1))
+    if opt.log_view:
+        out("TSSolve %.6f s" % seconds)
+    return PatternReport(m=m, steps=steps, Y=Y, seconds=seconds, lines=lines)

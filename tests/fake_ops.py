@@ -9,6 +9,7 @@ import scipy.sparse as sp
 from oracle import fish_oracle as fo
 from oracle import minimal_pattern_oracle as mpo
 from oracle import minimal_solver_oracle as mso
+from oracle import pattern_solver_oracle as pso
 
 
 class Vec:
@@ -141,3 +142,46 @@ class FakeOps:
 
     def dense_matvec(self, n, Ainv, b, x):
         x.a[:] = Ainv.a.reshape(n, n) @ b.a
+
+    # pattern.c implicit stage equation
+    def pattern_initial_state(self, mx, my, Lside, Y):
+        Y.a[:] = mpo.pattern_initial_state(mx, my, Lside).ravel()
+
+    def pattern_ifunction(self, mx, my, Lside, Du, Dv, Y, Ydot, F):
+        F.a[:] = mpo.pattern_ifunction(Y.a.reshape(my, mx, 2), Ydot.a.reshape(my, mx, 2), Lside, Du, Dv).ravel()
+
+    def pattern_rhsfunction(self, mx, my, phi, kappa, Y, G):
+        G.a[:] = mpo.pattern_rhsfunction(Y.a.reshape(my, mx, 2), phi, kappa).ravel()
+
+    def _pJ(self, m, Lside, Du, Dv, phi, kappa, shift, Y):
+        J = mpo.pattern_ijacobian(m, m, shift, Lside, Du, Dv)
+        if Y is not None:
+            J = J - pso.rhs_jacobian(Y.a.reshape(m, m, 2), phi, kappa)
+        return sp.csr_matrix(J)
+
+    def pattern_jac_apply(self, m, Lside, Du, Dv, phi, kappa, shift, Y, X, out):
+        self._count("pattern_jac_apply")
+        out.a[:] = self._pJ(m, Lside, Du, Dv, phi, kappa, shift, Y) @ X.a
+
+    def pattern_jac_lin(self, m, Lside, Du, Dv, phi, kappa, shift, Y, X, b, pm1, ca, cb, cg, jacobi, out):
+        self._count("pattern_jac_lin")
+        J = self._pJ(m, Lside, Du, Dv, phi, kappa, shift, Y)
+        r = (b.a if b is not None else 0.0) - J @ X.a
+        if jacobi:
+            r = r / J.diagonal()
+        o = cb * X.a + cg * r
+        if pm1 is not None:
+            o = o + ca * pm1.a
+        out.a[:] = o
+
+    def pattern_jac_gershgorin(self, m, Lside, Du, Dv, phi, kappa, shift, Y, work):
+        return mso.gershgorin_jacobi(self._pJ(m, Lside, Du, Dv, phi, kappa, shift, Y))
+
+    def pattern_restrict(self, Mx, My, rf, bc):
+        bc.a[:] = pso.interpolation(Mx, My).T @ rf.a
+
+    def pattern_prolong_add(self, Mx, My, xc, xf):
+        xf.a += pso.interpolation(Mx, My) @ xc.a
+
+    def pattern_inject(self, Mx, My, yf, yc):
+        yc.a[:] = yf.a.reshape(2 * My, 2 * Mx, 2)[::2, ::2, :].ravel()
