@@ -63,8 +63,10 @@ def stage_jacobian(Y, shift, rhsjac=True, L=2.5, Du=8.0e-5, Dv=4.0e-5, phi=0.024
 class PatternMG:
     """V cycle on rediscretised level operators (finest first), Chebyshev(its)/Jacobi, Gershgorin targets."""
 
-    def __init__(self, Y, shift, base, rhsjac, its=2, **par):
+    def __init__(self, Y, shift, base, rhsjac, its=2, rscale=1.0, **par):
         self.A, self.P = [], []
+        self.rscale = rscale        # 1: [PETSc] R = P^T; 0.25: averaging restriction, consistent with the pointwise
+                                    # (finite-difference) scaling of pattern.c's equations
         Yl = Y
         while True:
             self.A.append(stage_jacobian(Yl, shift, rhsjac, **par))
@@ -89,7 +91,7 @@ class PatternMG:
             return self.coarse @ b
         x = self._smooth(l, b, x)
         r = b - self.A[l] @ x
-        xc = self._cycle(l + 1, self.P[l].T @ r, np.zeros(self.P[l].shape[1]))
+        xc = self._cycle(l + 1, self.rscale * (self.P[l].T @ r), np.zeros(self.P[l].shape[1]))
         return self._smooth(l, b, x + self.P[l] @ xc)
 
     def apply(self, r):
@@ -111,7 +113,7 @@ def fmt_g(v):
 
 
 def pattern_beuler(grid=3, refine=0, dt=5.0, tmax=200.0, pc="mg", rhsjac=True, snes_rtol=1.0e-8, ksp_rtol=1.0e-5,
-                   smooth_its=2, max_steps=10000, L=2.5, Du=8.0e-5, Dv=4.0e-5, phi=0.024, kappa=0.06):
+                   smooth_its=2, max_steps=10000, rscale=1.0, L=2.5, Du=8.0e-5, Dv=4.0e-5, phi=0.024, kappa=0.06):
     mx = grid * 2 ** refine
     par = dict(L=L, Du=Du, Dv=Dv, phi=phi, kappa=kappa)
     Y = mpo.pattern_initial_state(mx, mx, L)
@@ -131,7 +133,7 @@ def pattern_beuler(grid=3, refine=0, dt=5.0, tmax=200.0, pc="mg", rhsjac=True, s
                 return lambda r: r
             if pc == "ilu":
                 return fo.ILU0PC(J).apply
-            return PatternMG(W, shift, grid, rhsjac, smooth_its, **par).apply
+            return PatternMG(W, shift, grid, rhsjac, smooth_its, rscale, **par).apply
 
         nr = mso.newton(R, Y, make_pc, jac=jac, snes_rtol=snes_rtol, ksp_rtol=ksp_rtol)
         Y = nr.u

@@ -49,6 +49,10 @@ class PatternOptions:
     ts_monitor: bool = False
     pc_type: str = "mg"
     smooth_its: int = 2
+    mg_rscale: float = 1.0          # -p4b_mg_rscale: factor on the restricted residual.  1 = [PETSc] R = P^T.  pattern.c's
+                                    # equations are scaled pointwise (no cell-volume factor, unlike fish.c), so P^T over-
+                                    # weights the coarse correction 4x; 0.25 (averaging restriction) restores
+                                    # mesh-independent Krylov counts on fine grids (2048^2: 362 -> single digits)
     snes_rtol: float = 1.0e-8
     snes_stol: float = 1.0e-8
     snes_atol: float = 1.0e-50
@@ -72,7 +76,8 @@ def parse_options(argv) -> PatternOptions:
               "-ptn_kappa": ("kappa", float), "-da_grid_x": ("grid_x", int), "-da_grid_y": ("grid_y", int),
               "-da_refine": ("refine", int), "-ts_type": ("ts_type", str), "-ts_dt": ("ts_dt", float),
               "-ts_max_time": ("ts_max_time", float), "-ts_max_steps": ("ts_max_steps", int), "-pc_type": ("pc_type", str),
-              "-mg_levels_ksp_max_it": ("smooth_its", int), "-snes_rtol": ("snes_rtol", float),
+              "-mg_levels_ksp_max_it": ("smooth_its", int), "-p4b_mg_rscale": ("mg_rscale", float),
+              "-snes_rtol": ("snes_rtol", float),
               "-snes_max_it": ("snes_max_it", int), "-ksp_rtol": ("ksp_rtol", float), "-ksp_max_it": ("ksp_max_it", int),
               "-ksp_gmres_restart": ("gmres_restart", int)}
     accepted = {"-mg_levels_ksp_type": ("chebyshev",), "-mg_levels_pc_type": ("jacobi",), "-ksp_type": ("gmres",)}
@@ -179,6 +184,8 @@ class StageOperator:
         self._smooth(L, zero_guess)
         ops.pattern_jac_lin(L.m, *self.par, self.shift, self._Y(L), L.x, L.b, None, 0.0, 0.0, 1.0, False, L.t)   # b - J x
         ops.pattern_restrict(C.m, C.m, L.t, C.b)
+        if self.opt.mg_rscale != 1.0:
+            ops.axpby(self.opt.mg_rscale, C.b, 0.0, None, C.b)
         self._cycle(l + 1, True)
         ops.pattern_prolong_add(C.m, C.m, C.x, L.x)
         self._smooth(L, False)

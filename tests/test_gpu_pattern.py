@@ -74,6 +74,8 @@ def test_golden_pattern_test2_verbatim_on_device(ctx):
      dict(grid=4, refine=4, dt=5.0, tmax=12.0)),
     ("-da_refine 4 -ts_type beuler -ts_dt 2 -ts_max_time 4 -pc_type mg -ptn_no_rhsjacobian -snes_rtol 1e-6",
      dict(grid=3, refine=4, dt=2.0, tmax=4.0, rhsjac=False, snes_rtol=1e-6)),
+    ("-da_grid_x 4 -da_grid_y 4 -da_refine 5 -ts_type beuler -ts_dt 5 -ts_max_time 10 -pc_type mg -p4b_mg_rscale 0.25",
+     dict(grid=4, refine=5, dt=5.0, tmax=10.0, rscale=0.25)),
 ])
 def test_device_time_stepping_matches_oracle(ctx, argv, okw):
     r = pp.pattern_main(argv, ctx)
@@ -91,10 +93,13 @@ def test_config5_at_full_size(ctx):
     """-da_grid_x 4 -da_grid_y 4 -da_refine 9 (2048 x 2048 x 2 = 8.4 M unknowns, 10 levels),
     backward Euler + Newton-GMRES-MG.  Size-independent properties: every stage solve converges with bounded Krylov
     counts; mass-like invariants stay in range (0 <= v, u <= 1); the pattern has started to grow from the seeded patch."""
-    r = pp.pattern_main("-da_grid_x 4 -da_grid_y 4 -da_refine 9 -ts_type beuler -ts_dt 5 -ts_max_time 10 -pc_type mg", ctx)
+    # -p4b_mg_rscale 0.25: averaging restriction.  With PETSc's R = P^T the pointwise-scaled equations of pattern.c get a
+    # 4x over-weighted coarse correction and GMRES needs hundreds of iterations at this resolution (pattern.py).
+    r = pp.pattern_main("-da_grid_x 4 -da_grid_y 4 -da_refine 9 -ts_type beuler -ts_dt 5 -ts_max_time 10 -pc_type mg "
+                        "-p4b_mg_rscale 0.25", ctx)
     assert r.m == 2048 and len(r.steps) == 2
     assert all(s[2].reason.startswith("CONVERGED") for s in r.steps)
-    assert max(max(s[2].ksp_its) for s in r.steps) <= 20
+    assert max(max(s[2].ksp_its) for s in r.steps) <= 12
     Y = ctx.to_host(r.Y).reshape(2048, 2048, 2)
     assert Y[..., 0].max() <= 1.0 + 1e-9 and Y[..., 1].min() >= -1e-9 and Y[..., 1].max() > 0.1
     print("pattern 2048^2 x 2: %.3f s for 2 steps, Newton its %s, KSP its %s"

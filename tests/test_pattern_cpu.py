@@ -43,6 +43,8 @@ def test_driver_prints_pattern_test2_verbatim():
     ("-da_refine 3 -ts_type beuler -ts_dt 2 -ts_max_time 4 -pc_type mg -ptn_no_rhsjacobian -snes_rtol 1e-6",
      dict(grid=3, refine=3, dt=2.0, tmax=4.0, rhsjac=False, snes_rtol=1e-6)),
     ("-da_refine 2 -ts_type beuler -ts_dt 5 -ts_max_time 5 -pc_type none", dict(grid=3, refine=2, dt=5.0, tmax=5.0, pc="none")),
+    ("-da_grid_x 4 -da_grid_y 4 -da_refine 4 -ts_type beuler -ts_dt 5 -ts_max_time 5 -pc_type mg -p4b_mg_rscale 0.25",
+     dict(grid=4, refine=4, dt=5.0, tmax=5.0, rscale=0.25)),
 ])
 def test_driver_matches_oracle(argv, okw):
     r = pp.pattern_main(argv, FakeOps())
@@ -69,3 +71,11 @@ def test_periodic_interpolation_is_partition_of_unity_and_restriction_its_transp
     assert P.shape == (2 * 12 * 8, 2 * 6 * 4)
     np.testing.assert_allclose(P @ np.ones(P.shape[1]), 1.0)
     np.testing.assert_allclose(P.T @ np.ones(P.shape[0]), 4.0)            # every coarse node collects weight 4 in 2-D
+
+
+def test_averaging_restriction_gives_mesh_independent_krylov_counts():
+    """pattern.c's equations carry no cell-volume factor, so [PETSc]'s R = P^T over-weights the coarse correction 4x and
+    the GMRES count grows with resolution; the averaging restriction (-p4b_mg_rscale 0.25) keeps it flat."""
+    petsc = [max(po.pattern_beuler(grid=4, refine=r, dt=5.0, tmax=5.0).steps[0][2].ksp_its) for r in (5, 6)]
+    avg = [max(po.pattern_beuler(grid=4, refine=r, dt=5.0, tmax=5.0, rscale=0.25).steps[0][2].ksp_its) for r in (5, 6)]
+    assert avg[1] <= avg[0] <= 8 and petsc[1] >= 2 * avg[1]
