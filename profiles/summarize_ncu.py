@@ -16,6 +16,7 @@ CLASS_OF = [
     (r"stencil_march_kernel<(\(int\))?1", "apply_dot"), (r"stencil_march_kernel<(\(int\))?4", "cheb_zero"),
     (r"stencil_march_kernel<(\(int\))?2", "residual|cheb_first"), (r"stencil_march_kernel<(\(int\))?3", "cheb_next"),
     (r"stencil_march_kernel<(\(int\))?5", "cheb_next"), (r"prolong_add3d", "prolong_add"), (r"restrict_kernel", "restrict"),
+    (r"restrict3d_kernel", "restrict"), (r"xp_update_kernel", "xp_update"), (r"r_update_kernel", "r_update"),
     (r"axpy2_kernel", "axpy2"), (r"aypx_dev_kernel", "aypx"), (r"dot2_kernel", "dot2"),
 ]
 
