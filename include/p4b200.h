@@ -21,6 +21,11 @@
  *   p4b_mg_create/apply      [PETSc] PCSetUp_MG / PCApply_MG  (-pc_type mg)
  *   p4b_cg_solve             [PETSc] KSPSolve_CG              (fish.c:233 KSPSetType(ksp,KSPCG))
  *   p4b_fish_solve_host      [PETSc] SNESSolve_KSPONLY        (fish.c:231,239)
+ *   p4b_minimal_* / p4b_stencil9_* / p4b_inject2d / p4b_dense_matvec
+ *                            c/ch7/minimal.c:210-282 + [PETSc] -snes_fd_color, MatMult, Chebyshev/Jacobi, PCLU on the
+ *                            assembled Jacobians of the Newton-Krylov-MG run of c/ch8/cluster.sh:70
+ *   p4b_pattern_*            c/ch5/pattern.c:146-318 callbacks; the stage Jacobian of the implicit TS run
+ *                            (c/ch5/makefile:52-53), matrix-free, and the periodic Q1 transfer
  *
  * There is no CPU fallback behind any of these: without a CUDA device they fail.
  */

@@ -4,7 +4,8 @@ NumPy restatements, each citing the reference lines it follows.  They are checke
 OWN compiled code (oracle/_ref/libfishref.so, built unchanged from c/ch7/minimal.c and c/ch5/pattern.c by
 oracle/refstub/Makefile; tests/test_oracle_ref_mp.py) and against the pure-callback known answers of the goldens
 (c/ch7/output/minimal.test1:1 "0 SNES Function norm 1.08276").  The Newton / TS drivers around these callbacks live
-in PETSc and are not restated yet: parity for whole minimal/pattern runs is unpinned.
+in PETSc; their restatements are minimal_solver_oracle.py and pattern_solver_oracle.py (pinned on
+c/ch7/output/minimal.test1,2,4 and c/ch5/output/pattern.test2).
 """
 import numpy as np
 
