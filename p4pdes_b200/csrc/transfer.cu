@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) prolong_add3d_kernel(const LevelDesc F, c
 //     P(J, kf)  = rx(2J) + (rx(2J-1) + rx(2J+1)) / 2
 //     bc(J, K)  = P(J, 2K) + (P(J, 2K-1) + P(J, 2K+1)) / 2          (missing rows/planes contribute 0)
 // The formula per coarse node does not depend on strips or chunks, so any decomposition gives the same bits.
-// A fine value is fetched (2 TJ + 1) / (2 TJ) x (2 KC + 1) / (2 KC) = 1.2 times through L1/L2 (TJ = 4, KC = 8),
+// A fine value is fetched (2 TJ + 1) / (2 TJ) x (2 KC + 1) / (2 KC) = 1.33 times through L1/L2 (TJ = 2, KC = 8),
 // against 27/8 = 3.4 times with scattered 8-byte accesses for one thread per coarse node.
 template <int TJ>
 __device__ __forceinline__ void restrict_plane(const LevelDesc &F, const double *__restrict__ rf, int kf, int J0, int fi,
@@ -273,7 +273,7 @@ int launch_restrict(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, con
     const long long n = C.nlocal();
     if (n <= 0) return 0;
     if (F.ax && F.ay && F.az && C.nx >= 64 && (((uintptr_t)rf) & 7) == 0) {
-        constexpr int TJ = 4;
+        constexpr int TJ = 2;      // measured (tools/ab_bench.py): 2-row strips, 48 registers, 83 % of HBM peak; 4-row strips 84 registers, 70 %
         const int KC = C.zm > 64 ? 8 : 4;      // thin slabs (multi-GPU): more, smaller chunks keep all SMs busy
         dim3 grid((unsigned)((C.nx + 127) / 128), (unsigned)((C.ny + TJ - 1) / TJ), (unsigned)((C.zm + KC - 1) / KC));
         if (port.sync) restrict3d_kernel<TJ, true><<<grid, 128, 0, st>>>(F, C, KC, rf, bc, port);
