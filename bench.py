@@ -205,19 +205,31 @@ def main():
         res = mg.cg_solve(b, x, rtol=1e-10)
     mg.profile(True)
     mg.profile_reset()
-    sampler = ClockSampler(local_rank)
-    barrier()
+    # a timed region that saw a hardware / thermal slowdown is re-measured once (the recipe's rule); a power cap is
+    # kept and reported
+    BAD = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    remeasured = 0
+    while True:
+        mg.profile_reset()
+        sampler = ClockSampler(local_rank)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        launches0 = lib.p4b_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(ctx.stream)
+        for _ in range(args.steps):
+            res = mg.cg_solve(b, x, rtol=1e-10)
+        ev1.record(ctx.stream)
+        barrier()
+        launches = lib.p4b_launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        again = 1.0 if (rank == 0 and remeasured == 0 and BAD & set(clocks["reasons"])) else 0.0
+        if max_over_ranks(again) == 0.0:
+            break
+        remeasured += 1
     if rank == 0:
-        sampler.start()
-    launches0 = lib.p4b_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(ctx.stream)
-    for _ in range(args.steps):
-        res = mg.cg_solve(b, x, rtol=1e-10)
-    ev1.record(ctx.stream)
-    barrier()
-    launches = lib.p4b_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+        clocks["remeasured"] = remeasured
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_step = ms_total / args.steps
     stats = mg.profile_stats()

@@ -42,8 +42,11 @@ struct GatherTable {
 //   * port_wait   : the CTAs that touch the slab boundary (they read a ghost plane or store into a neighbour's) wait
 //                 until the neighbours' flags have reached this rank's exchange count: every earlier push has landed,
 //                 so ghost planes may be read, and -- because a rank signals only after ALL its boundary CTAs are
-//                 done -- nothing on the neighbours still reads the ghost planes this kernel is about to overwrite
-//                 (mg.cu keeps the one exception, the same vector exchanged twice in a row, apart with a flag barrier);
+//                 done -- nothing on the neighbours still reads the ghost planes this kernel is about to overwrite.
+//                 The one pattern this cannot serve is a kernel that reads the ghosts of the very vector it pushes;
+//                 no kernel does (stencil operand and result are distinct buffers, in-place updates are element-wise
+//                 and read no ghosts).  tests/test_exchange_protocol_model.py checks every interleaving of the
+//                 V-cycle + CG kernel sequence on an abstract 3-rank model;
 //   * port_store  : where the kernel stores an element of its first / last owned plane, the same value goes straight
 //                 into the neighbour's ghost plane over NVLink;
 //   * port_signal : the last boundary CTA to finish bumps the exchange count and releases it to both neighbours.
