@@ -76,6 +76,49 @@ def main():
         report("stencil_apply (matrix-free)", label, 16.0 * og.n, ms2, "same operator, %.1fx faster than SpMV" % (ms / ms2))
         S.close()
         del x, y
+    # ---- assembled 9-point Jacobian of minimal.c (stencil9 layout) and its column-indexed SELL-32 copy ----------------
+    import ctypes as C
+    from p4pdes_b200.minimal import stencil9_to_csr
+    for m in (2049, 4097):
+        n = m * m
+        g = cb.minimal_g(ctx, m, m, "catenoid", 1.0, 1.1)
+        u = g.clone() * 0.9
+        F0, vals = ctx.empty(n), ctx.empty(9 * n)
+        ctx.minimal_function(m, m, -0.5, u, g, F0)
+        ms = timeit(lambda: ctx.minimal_jacobian_fd(m, m, -0.5, u, g, F0, vals), reps=5, warm=2)
+        # per colour: perturb (16 N), residual (16 N + g), extract (reads u, F0, Fp: 24 N, writes N values);
+        # nine colours fill the 9 N coefficients once (72 N) after a 72 N memset
+        report("minimal_jacobian_fd (9 colours x 3 kernels)", "%d^2" % m, (9 * (16 + 24 + 24) + 72 + 72) * float(n), ms,
+               "%.2f ms per assembled Jacobian" % ms)
+        x, b, y = torch.randn(n, dtype=torch.float64, device="cuda"), torch.randn(n, dtype=torch.float64, device="cuda"), ctx.empty(n)
+        ms1 = timeit(lambda: ctx.stencil9_apply(m, m, vals, x, y))
+        report("stencil9_apply (y = A x)", "%d^2" % m, 88.0 * n, ms1)
+        ms2 = timeit(lambda: ctx.stencil9_lin(m, m, vals, x, b, y, 0.3, 0.7, 0.4, True, y))
+        report("stencil9_lin (Chebyshev+Jacobi step)", "%d^2" % m, 104.0 * n, ms2)
+        if m == 2049:
+            rp, ci, d = stencil9_to_csr(ctx.to_host(vals), m, m)
+            S = cb.SellMatrix(ctx, rp, ci, d)
+            ms3 = timeit(lambda: S.mult(x, y))
+            report("sell_spmv (same Jacobian, column-indexed copy)", "%d^2" % m, 12.0 * S.padded_nnz + 16.0 * n, ms3,
+                   "stencil9 layout is %.2fx faster" % (ms3 / ms1))
+            S.close()
+        del g, u, F0, vals, x, b, y
+    # ---- pattern.c stage Jacobian, matrix-free, and the periodic transfer ------------------------------------------------
+    PAR = (2.5, 8.0e-5, 4.0e-5, 0.024, 0.06)
+    for m in (2048, 6144):
+        n = m * m
+        Y = cb.pattern_initial_state(ctx, m, m)
+        X, B, out = torch.randn(2 * n, dtype=torch.float64, device="cuda"), torch.randn(2 * n, dtype=torch.float64, device="cuda"), ctx.empty(2 * n)
+        ms = timeit(lambda: ctx.pattern_jac_apply(m, *PAR, 0.2, Y, X, out))
+        report("pattern_jac_apply (J X, matrix-free)", "%d^2 x2" % m, 48.0 * n, ms)
+        ms = timeit(lambda: ctx.pattern_jac_lin(m, *PAR, 0.2, Y, X, B, out, 0.3, 0.7, 0.4, True, out))
+        report("pattern_jac_lin (Chebyshev+Jacobi step)", "%d^2 x2" % m, 80.0 * n, ms)
+        xc = ctx.empty(n // 2)
+        ms = timeit(lambda: ctx.pattern_restrict(m // 2, m // 2, X, xc))
+        report("pattern_restrict", "%d^2 x2" % m, 16.0 * n + 4.0 * n, ms)
+        ms = timeit(lambda: ctx.pattern_prolong_add(m // 2, m // 2, xc, out))
+        report("pattern_prolong_add", "%d^2 x2" % m, 32.0 * n + 4.0 * n, ms)
+        del Y, X, B, out, xc
 
 
 if __name__ == "__main__":
