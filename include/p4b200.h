@@ -123,7 +123,10 @@ int p4b_device_count(int *n);
  * over CUDA IPC + NVLink (default), 0 = NCCL send/recv/allreduce/broadcast;
  * "fused_halo" 0|1: 1 (default) = on the peer path a ghost exchange costs no kernel of its own: the kernel that
  * writes a vector also stores its boundary planes into the neighbours' ghost planes and the kernel that reads them
- * waits for the neighbours' flags; 0 = one push kernel per exchange */
+ * waits for the neighbours' flags; 0 = one push kernel per exchange;
+ * measurement-only keys: "force_mg" 1|2 (run the multi-GPU kernel variants on ONE GPU: 1 = no neighbours, 2 = scratch
+ * memory on this device stands in for both neighbours) and "port_opts" (bit 0: natural chunk order and march
+ * direction, bit 1: signal at the end of the boundary CTAs' work) -- the A/B switches behind DESIGN.md section 5 */
 int p4b_tune(const char *key, long value);
 
 /* ---- context ---- */
