@@ -16,6 +16,14 @@
 // DRAM traffic is therefore the algorithmic minimum (each vector is read/written once) plus
 // 2H/Q halo re-reads that hit in L2 because neighbouring bands run concurrently.
 //
+// Multi-GPU slabs (template parameter MG, comm.h HaloPort): the CTAs of the first chunk read the lower ghost plane,
+// those of the last chunk the upper one, after waiting for the neighbours' flags; a kernel that writes a ghosted
+// vector stores its first / last owned plane into the neighbours' ghost planes as well.  So that BOTH boundary
+// planes are the first planes computed, the last chunk is scheduled second and marched downwards (the z stencil
+// sum is formed from two rounded products, so the direction does not change the bits), and the push is published
+// (system-scope fence + flags) right after that first plane, while the rest of the chunk is still being marched.
+// MG = false compiles all of this out.
+//
 // Alignment: cp.async.bulk needs 16-byte aligned addresses and sizes, but nx*ny is odd for the
 // 2^k+1 grids, so a plane's band may start on an odd element.  The copy then starts one element
 // early (the stage keeps a per-plane parity `adj`) and an odd trailing element is moved by the
