@@ -166,6 +166,9 @@ int p4b_lambda_max_jacobi(const p4b_grid *g, double *lam);
 
 int p4b_vec_dot(p4b_ctx *ctx, size_t n, const double *x, const double *y, double *result_host);
 int p4b_vec_norm2(p4b_ctx *ctx, size_t n, const double *x, double *result_host);
+/* sum_i ((x_i - y_i) / (atol + rtol max(|x_i|, |y_i|)))^2: [PETSc] TSErrorWeightedNorm2 (TSAdapt's error estimate) */
+int p4b_vec_wrms2(p4b_ctx *ctx, size_t n, const double *x, const double *y, double atol, double rtol,
+                  double *result_host);
 int p4b_vec_norminf(p4b_ctx *ctx, size_t n, const double *x, double *result_host);
 int p4b_vec_axpy(p4b_ctx *ctx, size_t n, double a, const double *x, double *y);      /* y += a x */
 int p4b_vec_aypx(p4b_ctx *ctx, size_t n, double a, const double *x, double *y);      /* y = x + a y */

@@ -12,9 +12,15 @@ implicit runs the reference uses (c/ch5/makefile:52-53 `-ts_type beuler -pc_type
   PCMG             periodic DMDA Q1 interpolation (ratio 2), R = P^T, level operators rediscretised on every level at
                    the injected iterate, Chebyshev(2)/Jacobi, dense LU on the base grid
 
-Pinned on c/ch5/output/pattern.test2 (banner, one Newton iteration at -snes_rtol 0.1, TS lines); the golden's KSP count
-(3) belongs to PETSc's Chebyshev/SOR smoother -- Chebyshev/Jacobi has no golden: parity unpinned there.
-ARKIMEX (the reference's default, pattern.test1/4), BDF and CN runs are not restated.
+  ARKIMEX          [PETSc] TSARKIMEX3 = ARK3(2)4L[2]SA (Kennedy & Carpenter 2003): 4 stages, F implicit (ESDIRK, L-stable),
+                   G explicit, 2nd-order embedded method; TSAdaptBasic (safety 0.9, clip [0.1, 10], exponent -1/3, an extra
+                   factor 1/2 only from the SECOND consecutive rejection on), TSErrorWeightedNorm2 with atol = rtol = 1e-4,
+                   TS_EXACTFINALTIME_MATCHSTEP (last step stretched by <= 1 %, or the last two steps made equal)
+
+Pinned on c/ch5/output/pattern.test2 (backward Euler: all lines verbatim; the golden's KSP count (3) also comes out of the
+Chebyshev/Jacobi multigrid) and on c/ch5/output/pattern.test1 and pattern.test4 (ARKIMEX: every "TS dt ... time ..."
+line of the adaptive runs, 13 and 11 lines, to all printed digits, including the rejected step of test1).
+BDF and CN runs (pattern.test3, test5) are not restated.
 """
 from dataclasses import dataclass, field
 
@@ -142,4 +148,102 @@ def pattern_beuler(grid=3, refine=0, dt=5.0, tmax=200.0, pc="mg", rhsjac=True, s
         res.steps.append((t, step, nr))
     res.lines.append("%d TS dt %s time %s" % (k, fmt_g(res.steps[-1][1] if res.steps else dt), fmt_g(t)))
     res.Y = Y
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ARKIMEX 3 (pattern.c's default TS type: c/ch5/pattern.c:115)
+# ---------------------------------------------------------------------------------------------------------
+from fractions import Fraction as _Fr
+
+_G = _Fr(1767732205903, 4055673282236)
+ARK3_AI = np.array([[0, 0, 0, 0], [_G, _G, 0, 0],
+                    [_Fr(2746238789719, 10658868560708), _Fr(-640167445237, 6845629431997), _G, 0],
+                    [_Fr(1471266399579, 7840856788654), _Fr(-4482444167858, 7529755066697),
+                     _Fr(11266239266428, 11593286722821), _G]], dtype=float)
+ARK3_AE = np.array([[0, 0, 0, 0], [_Fr(1767732205903, 2027836641118), 0, 0, 0],
+                    [_Fr(5535828885825, 10492691773637), _Fr(788022342437, 10882634858940), 0, 0],
+                    [_Fr(6485989280629, 16251701735622), _Fr(-4246266847089, 9704473918619),
+                     _Fr(10755448449292, 10357097424841), 0]], dtype=float)
+ARK3_B = ARK3_AI[3].copy()
+ARK3_BH = np.array([_Fr(2756255671327, 12835298489170), _Fr(-10771552573575, 22201958757719),
+                    _Fr(9247589265047, 10645013368117), _Fr(2193209047091, 5459859503100)], dtype=float)
+ARK3_C = np.array([0.0, float(_Fr(1767732205903, 2027836641118)), 0.6, 1.0])
+
+
+def adapt_basic(h, enorm, prev_accept, order=3, safety=0.9, reject_safety=0.5, clip=(0.1, 10.0)):
+    """[PETSc] TSAdaptChoose_Basic: (accept, next h)."""
+    accept = enorm <= 1.0
+    s = safety * (reject_safety if (not accept and not prev_accept) else 1.0)
+    hfac = s * enorm ** (-1.0 / order) if enorm > 0.0 else np.inf
+    return accept, h * min(max(hfac, clip[0]), clip[1])
+
+
+def match_step(t, hnext, tmax, fac=(0.01, 2.0)):
+    """TS_EXACTFINALTIME_MATCHSTEP in TSAdaptChoose: t = time after the accepted step."""
+    if t >= tmax:
+        return hnext
+    hmax, tend, out = tmax - t, t + hnext, hnext
+    if tend > tmax:
+        out = hmax
+    if tend < tmax and hnext * fac[1] > hmax:
+        out = hmax / 2.0
+    if tend < tmax and hnext * (1.0 + fac[0]) > hmax:
+        out = hmax
+    return out
+
+
+def pattern_arkimex(grid=3, refine=0, dt=5.0, tmax=200.0, atol=1.0e-4, rtol=1.0e-4, solve=None, max_steps=10000, L=2.5,
+                    Du=8.0e-5, Dv=4.0e-5, phi=0.024, kappa=0.06):
+    """pattern.c with its default TS type.  `solve(shift, rhs)` solves (shift I - C L9) y = rhs (default: sparse direct, which
+    is what PETSc's Newton iteration on the linear stage equation converges to)."""
+    import scipy.sparse.linalg as spla
+    m = grid * 2 ** refine
+    Y = mpo.pattern_initial_state(m, m, L)
+    n = Y.size
+    Lap = mpo.pattern_ijacobian(m, m, 0.0, L, Du, Dv)          # F(Y, Ydot) = Ydot + Lap Y   (Lap = -C L9)
+    I = sp.identity(n, format="csr")
+    if solve is None:
+        solve = lambda shift, rhs: spla.spsolve((shift * I + Lap).tocsc(), rhs)
+    res = PatternResult(Y=Y, mx=m)
+    res.lines.append("running on %d x %d grid with square cells of side h = %.6f ..." % (m, m, L / m))
+    t, k, h = 0.0, 0, dt
+    rejected = 0
+    while t < tmax - 1e-12 * max(1.0, abs(tmax)) and k < max_steps:
+        res.lines.append("%d TS dt %s time %s" % (k, fmt_g(h), fmt_g(t)))
+        prev_accept = True
+        while True:
+            y0 = Y.ravel()
+            FI, FE = [], []
+            for i in range(4):
+                Z = y0.copy()
+                for j in range(i):
+                    Z = Z + h * (ARK3_AE[i, j] * FE[j] + ARK3_AI[i, j] * FI[j])
+                if ARK3_AI[i, i] == 0.0:
+                    Yi = Z
+                    fi = -(Lap @ Yi)                               # explicit first stage: YdotI = -F(Y, 0)
+                else:
+                    shift = 1.0 / (h * ARK3_AI[i, i])
+                    Yi = solve(shift, shift * Z)                   # F(Yi, shift (Yi - Z)) = 0
+                    fi = shift * (Yi - Z)
+                FI.append(fi)
+                FE.append(mpo.pattern_rhsfunction(Yi.reshape(m, m, 2), phi, kappa).ravel())
+            ynew = y0 + h * sum(ARK3_B[j] * (FI[j] + FE[j]) for j in range(4))
+            yemb = y0 + h * sum(ARK3_BH[j] * (FI[j] + FE[j]) for j in range(4))
+            tol = atol + rtol * np.maximum(np.abs(ynew), np.abs(yemb))
+            enorm = float(np.sqrt(np.sum(((ynew - yemb) / tol) ** 2) / n))
+            accept, hnext = adapt_basic(h, enorm, prev_accept)
+            if accept:
+                break
+            prev_accept = False
+            rejected += 1
+            h = hnext
+        Y = ynew.reshape(m, m, 2)
+        t += h
+        res.steps.append((t, h, enorm))
+        h = match_step(t, hnext, tmax)
+        k += 1
+    res.lines.append("%d TS dt %s time %s" % (k, fmt_g(h), fmt_g(t)))
+    res.Y = Y
+    res.rejected = rejected
     return res

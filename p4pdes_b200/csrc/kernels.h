@@ -48,6 +48,8 @@ int launch_prolong_add(cudaStream_t st, const LevelDesc &F, const LevelDesc &C, 
 int launch_dot2(cudaStream_t st, long long n, const double *x, const double *y, double *out2, const Reducer &red);
 int launch_dotn(cudaStream_t st, long long n, const double *x, const double *y, double *out1, const Reducer &red);
 int launch_absmax(cudaStream_t st, long long n, const double *x, double *out1, const Reducer &red);
+int launch_wrms(cudaStream_t st, long long n, const double *x, const double *y, double atol, double rtol, double *out1,
+                const Reducer &red);
 // x += a p ; r -= a w   with a = num[0]/den[0] read on device
 int launch_axpy2(cudaStream_t st, long long n, const double *num, const double *den, const double *p,
                  const double *w, double *x, double *r);

@@ -1116,6 +1116,11 @@ int p4b_vec_dot(p4b_ctx *c, size_t n, const double *x, const double *y, double *
     P4B_CHECK(ctx_allreduce(c, c->d_scal + 8, 1));
     return fetch_scal(c, c->d_scal + 8, 1, res);
 }
+int p4b_vec_wrms2(p4b_ctx *c, size_t n, const double *x, const double *y, double atol, double rtol, double *res) {
+    P4B_CHECK(launch_wrms(c->stream, (long long)n, x, y, atol, rtol, c->d_scal + 8, c->red));
+    P4B_CHECK(ctx_allreduce(c, c->d_scal + 8, 1));
+    return fetch_scal(c, c->d_scal + 8, 1, res);
+}
 int p4b_vec_norm2(p4b_ctx *c, size_t n, const double *x, double *res) {
     P4B_CHECK(p4b_vec_dot(c, n, x, x, res));
     *res = sqrt(*res);

@@ -56,6 +56,27 @@ __global__ void __launch_bounds__(VT) dot1_kernel(long long n, const double *__r
     grid_sum_finalize<1, VT>(v, partials, ticket, out1);
 }
 
+// sum_i ((x_i - y_i) / (atol + rtol max(|x_i|, |y_i|)))^2 : the weighted error of [PETSc] TSErrorWeightedNorm2 (the
+// local-truncation-error estimate of the adaptive time steppers); same fixed-order reduction as the dot products
+__global__ void __launch_bounds__(VT) wrms_kernel(long long n, const double *__restrict__ x, const double *__restrict__ y,
+                                                   double atol, double rtol, double *partials, unsigned int *ticket,
+                                                   double *out1) {
+    double v[1] = {0.0};
+    const long long stride = (long long)gridDim.x * VT * VU;
+    for (long long base = (long long)blockIdx.x * VT * VU + threadIdx.x; base < n; base += stride) {
+#pragma unroll
+        for (int q = 0; q < VU; q++) {
+            const long long i = base + (long long)q * VT;
+            if (i < n) {
+                const double a = x[i], b = y[i];
+                const double e = (a - b) / (atol + rtol * fmax(fabs(a), fabs(b)));
+                v[0] += e * e;
+            }
+        }
+    }
+    grid_sum_finalize<1, VT>(v, partials, ticket, out1);
+}
+
 // max |x_i| via the same two-stage scheme (max is order independent, so plain block max + final pass)
 __global__ void __launch_bounds__(VT) absmax_kernel(long long n, const double *__restrict__ x, double *partials,
                                                      unsigned int *ticket, double *out1) {
@@ -226,6 +247,14 @@ int launch_dotn(cudaStream_t st, long long n, const double *x, const double *y, 
     unsigned nb = vec_blocks(n, STREAM_BLOCKS);
     RED_CHECK(nb);
     dot1_kernel<<<nb, VT, 0, st>>>(n, x, y, red.partials, red.ticket, out1);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+int launch_wrms(cudaStream_t st, long long n, const double *x, const double *y, double atol, double rtol, double *out1,
+                const Reducer &red) {
+    unsigned nb = vec_blocks(n, STREAM_BLOCKS);
+    RED_CHECK(nb);
+    wrms_kernel<<<nb, VT, 0, st>>>(n, x, y, atol, rtol, red.partials, red.ticket, out1);
     P4B_LAUNCH_CHECK();
     return 0;
 }

@@ -101,6 +101,12 @@ class Context:
         L.check(self.lib.p4b_vec_norm2(self.h, x.numel(), x.data_ptr(), C.byref(r)))
         return r.value
 
+    def wrms2(self, x, y, atol, rtol):
+        """sum_i ((x_i - y_i) / (atol + rtol max(|x_i|, |y_i|)))^2  ([PETSc] TSErrorWeightedNorm2)."""
+        r = C.c_double()
+        L.check(self.lib.p4b_vec_wrms2(self.h, x.numel(), x.data_ptr(), y.data_ptr(), atol, rtol, C.byref(r)))
+        return r.value
+
     def norminf(self, x):
         r = C.c_double()
         L.check(self.lib.p4b_vec_norminf(self.h, x.numel(), x.data_ptr(), C.byref(r)))

@@ -92,6 +92,7 @@ _SIGS = {
     "p4b_residual_restrict": (C.c_int, [_P, C.POINTER(Grid), _D, _D, _D]),
     "p4b_lambda_max_jacobi": (C.c_int, [C.POINTER(Grid), C.POINTER(C.c_double)]),
     "p4b_vec_dot": (C.c_int, [_P, C.c_size_t, _D, _D, C.POINTER(C.c_double)]),
+    "p4b_vec_wrms2": (C.c_int, [_P, C.c_size_t, _D, _D, C.c_double, C.c_double, C.POINTER(C.c_double)]),
     "p4b_vec_norm2": (C.c_int, [_P, C.c_size_t, _D, C.POINTER(C.c_double)]),
     "p4b_vec_norminf": (C.c_int, [_P, C.c_size_t, _D, C.POINTER(C.c_double)]),
     "p4b_vec_axpy": (C.c_int, [_P, C.c_size_t, C.c_double, _D, _D]),

@@ -14,8 +14,13 @@ pattern.c:main -- periodic 2-dof DMDA, banner, InitialState, TSSolve -- and prin
                            (Chebyshev + Jacobi), p4b_pattern_restrict / _prolong_add / _inject (periodic Q1), dense inverse
                            of the base-grid operator x vector
 
-ARKIMEX (pattern.c's default type), BDF, CN, time-step adaptivity and `-ptn_noisy_init` (PETSc's random stream) are not
-provided: `-ts_type beuler` is required.  No CPU path: `ops` must be a device Context (tests/ substitutes a NumPy
+  -ts_type arkimex (pattern.c's default, :115): [PETSc] TSARKIMEX3 = ARK3(2)4L[2]SA with TSAdaptBasic and
+                           MATCHSTEP.  The diffusion (IFunction) is implicit: each of the three implicit stages solves the
+                           LINEAR system (shift*I - C L9) Y_i = shift*Z with the same GMRES + multigrid machinery (G' never
+                           enters: the reaction is explicit); the embedded 2nd-order solution gives the error estimate,
+                           p4b_vec_wrms2 its weighted norm ([PETSc] TSErrorWeightedNorm2).
+
+BDF, CN and `-ptn_noisy_init` (PETSc's random stream) are not provided.  No CPU path: `ops` must be a device Context (tests/ substitutes a NumPy
 stand-in to exercise this file's control flow without a GPU).
 """
 from __future__ import annotations
@@ -46,6 +51,8 @@ class PatternOptions:
     ts_dt: float = 5.0
     ts_max_time: float = 200.0
     ts_max_steps: int = 5000
+    ts_rtol: float = 1.0e-4
+    ts_atol: float = 1.0e-4
     ts_monitor: bool = False
     pc_type: str = "mg"
     smooth_its: int = 2
@@ -76,11 +83,13 @@ def parse_options(argv) -> PatternOptions:
               "-ptn_kappa": ("kappa", float), "-da_grid_x": ("grid_x", int), "-da_grid_y": ("grid_y", int),
               "-da_refine": ("refine", int), "-ts_type": ("ts_type", str), "-ts_dt": ("ts_dt", float),
               "-ts_max_time": ("ts_max_time", float), "-ts_max_steps": ("ts_max_steps", int), "-pc_type": ("pc_type", str),
+              "-ts_rtol": ("ts_rtol", float), "-ts_atol": ("ts_atol", float),
               "-mg_levels_ksp_max_it": ("smooth_its", int), "-p4b_mg_rscale": ("mg_rscale", float),
               "-snes_rtol": ("snes_rtol", float),
               "-snes_max_it": ("snes_max_it", int), "-ksp_rtol": ("ksp_rtol", float), "-ksp_max_it": ("ksp_max_it", int),
               "-ksp_gmres_restart": ("gmres_restart", int)}
-    accepted = {"-mg_levels_ksp_type": ("chebyshev",), "-mg_levels_pc_type": ("jacobi",), "-ksp_type": ("gmres",)}
+    accepted = {"-mg_levels_ksp_type": ("chebyshev",), "-mg_levels_pc_type": ("jacobi",), "-ksp_type": ("gmres",),
+                "-ts_adapt_type": ("basic",), "-ts_arkimex_type": ("3",)}
     i = 0
     while i < len(argv):
         a = argv[i]
@@ -99,9 +108,9 @@ def parse_options(argv) -> PatternOptions:
             raise ValueError("%s is not provided by the device path (PETSc random stream / finite-difference IJacobian)" % a)
         else:
             raise ValueError("unknown or unsupported option %s" % a)
-    if o.ts_type != "beuler":
-        raise ValueError("-ts_type %s: the device path provides beuler (pattern.c's default arkimex, bdf and cn are not "
-                         "built)" % o.ts_type)
+    if o.ts_type not in ("arkimex", "beuler"):
+        raise ValueError("-ts_type %s: the device path provides arkimex (pattern.c's default) and beuler; bdf and cn are "
+                         "not built" % o.ts_type)
     if o.pc_type not in ("mg", "none"):
         raise ValueError("-pc_type %s: the device path provides mg and none (ilu/sor are sequential)" % o.pc_type)
     return o
@@ -118,14 +127,15 @@ class Level:
 class StageOperator:
     """J = shift*I - C L9 - G'(Y) on every level of the periodic hierarchy (levels[0] finest), with the V cycle."""
 
-    def __init__(self, ops, levels, opt: PatternOptions):
+    def __init__(self, ops, levels, opt: PatternOptions, imex=False):
         self.ops, self.levels, self.opt = ops, levels, opt
         self.shift = 0.0
         self.Ainv = None
         self.par = (opt.L, opt.Du, opt.Dv, opt.phi, opt.kappa)
+        self.no_rhs = opt.no_rhsjacobian or imex          # IMEX: the reaction is explicit, G' never enters the stage matrix
 
     def _Y(self, L):
-        return None if self.opt.no_rhsjacobian else L.Y
+        return None if self.no_rhs else L.Y
 
     def mult(self, x, y):
         L = self.levels[0]
@@ -136,7 +146,7 @@ class StageOperator:
         ops, opt = self.ops, self.opt
         self.shift = shift
         for l, L in enumerate(self.levels):
-            if l > 0:
+            if l > 0 and not self.no_rhs:
                 ops.pattern_inject(L.m, L.m, self.levels[l - 1].Y, L.Y)
             if l < len(self.levels) - 1:
                 lam = ops.pattern_jac_gershgorin(L.m, *self.par, shift, self._Y(L), L.t)
@@ -153,7 +163,7 @@ class StageOperator:
         C = self.levels[-1]
         if C.n > 2048:
             raise ValueError("base grid of the hierarchy has %d unknowns: use a coarser -da_grid_x/_y" % C.n)
-        Yc = None if opt.no_rhsjacobian else ops.to_host(C.Y).reshape(C.m, C.m, 2)
+        Yc = None if self.no_rhs else ops.to_host(C.Y).reshape(C.m, C.m, 2)
         self.Ainv = ops.from_host(np.linalg.inv(dense_stage_jacobian(C.m, shift, Yc, *self.par)).ravel())
 
     def _smooth(self, L, zero_guess):
@@ -258,6 +268,8 @@ def pattern_main(argv, ops, echo=False) -> PatternReport:
         while sizes[-1] > opt.grid_x and sizes[-1] % 2 == 0:
             sizes.append(sizes[-1] // 2)
     levels = [Level(ops, s, opt) for s in sizes]
+    if opt.ts_type == "arkimex":
+        return _arkimex(ops, opt, levels, m, out, lines)
     A = StageOperator(ops, levels, opt)
     L0 = levels[0]
     n = L0.n
@@ -337,3 +349,135 @@ def pattern_main(argv, ops, echo=False) -> PatternReport:
     if opt.log_view:
         out("TSSolve %.6f s" % seconds)
     return PatternReport(m=m, steps=steps, Y=Y, seconds=seconds, lines=lines)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# -ts_type arkimex: [PETSc] TSARKIMEX3 = ARK3(2)4L[2]SA (Kennedy & Carpenter 2003) + TSAdaptBasic + MATCHSTEP
+# ---------------------------------------------------------------------------------------------------------
+def _fr(a, b):
+    return a / b
+
+
+_G = _fr(1767732205903, 4055673282236)
+ARK3_AI = ((0.0, 0.0, 0.0, 0.0), (_G, _G, 0.0, 0.0),
+           (_fr(2746238789719, 10658868560708), _fr(-640167445237, 6845629431997), _G, 0.0),
+           (_fr(1471266399579, 7840856788654), _fr(-4482444167858, 7529755066697), _fr(11266239266428, 11593286722821), _G))
+ARK3_AE = ((0.0, 0.0, 0.0, 0.0), (_fr(1767732205903, 2027836641118), 0.0, 0.0, 0.0),
+           (_fr(5535828885825, 10492691773637), _fr(788022342437, 10882634858940), 0.0, 0.0),
+           (_fr(6485989280629, 16251701735622), _fr(-4246266847089, 9704473918619), _fr(10755448449292, 10357097424841), 0.0))
+ARK3_B = ARK3_AI[3]
+ARK3_BH = (_fr(2756255671327, 12835298489170), _fr(-10771552573575, 22201958757719), _fr(9247589265047, 10645013368117),
+           _fr(2193209047091, 5459859503100))
+
+
+def adapt_basic(h, enorm, prev_accept, order=3, safety=0.9, reject_safety=0.5, clip=(0.1, 10.0)):
+    """[PETSc] TSAdaptChoose_Basic -> (accept, next h): the extra factor 1/2 only from the second consecutive rejection."""
+    accept = enorm <= 1.0
+    s = safety * (reject_safety if (not accept and not prev_accept) else 1.0)
+    hfac = s * enorm ** (-1.0 / order) if enorm > 0.0 else float("inf")
+    return accept, h * min(max(hfac, clip[0]), clip[1])
+
+
+def match_step(t, hnext, tmax, fac=(0.01, 2.0)):
+    """TS_EXACTFINALTIME_MATCHSTEP (pattern.c:118) as TSAdaptChoose applies it; t = time after the accepted step."""
+    if t >= tmax:
+        return hnext
+    hmax, tend, out = tmax - t, t + hnext, hnext
+    if tend > tmax:
+        out = hmax
+    if tend < tmax and hnext * fac[1] > hmax:
+        out = hmax / 2.0
+    if tend < tmax and hnext * (1.0 + fac[0]) > hmax:
+        out = hmax
+    return out
+
+
+def _arkimex(ops, opt: PatternOptions, levels, m, out, lines) -> PatternReport:
+    A = StageOperator(ops, levels, opt, imex=True)
+    n = levels[0].n
+    Y = levels[0].Y
+    Z, R, d, Ynew, Yemb, zero = (ops.empty(n) for _ in range(6))
+    Ys = [ops.empty(n) for _ in range(4)]
+    FI = [ops.empty(n) for _ in range(4)]
+    FE = [ops.empty(n) for _ in range(4)]
+    work = [ops.empty(n) for _ in range(opt.gmres_restart + 1)]
+    ops.set(0.0, zero)
+    ops.pattern_initial_state(m, m, opt.L, Y)
+    t0 = time.perf_counter()
+    t, k, h, steps, rejected, ksp_total = 0.0, 0, opt.ts_dt, [], 0, 0
+    tmax = opt.ts_max_time
+    while t < tmax - 1e-12 * max(1.0, abs(tmax)) and k < opt.ts_max_steps:
+        if opt.ts_monitor:
+            out("%d TS dt %s time %s" % (k, fmt_g(h), fmt_g(t)))
+        prev_accept = True
+        while True:
+            for i in range(4):
+                ops.copy(Y, Z)
+                for j in range(i):
+                    if ARK3_AE[i][j] != 0.0:
+                        ops.axpy(h * ARK3_AE[i][j], FE[j], Z)
+                    if ARK3_AI[i][j] != 0.0:
+                        ops.axpy(h * ARK3_AI[i][j], FI[j], Z)
+                if ARK3_AI[i][i] == 0.0:                           # explicit first stage: Y_1 = Z, YdotI = -F(Y_1, 0)
+                    ops.copy(Z, Ys[i])
+                    ops.pattern_ifunction(m, m, opt.L, opt.Du, opt.Dv, Ys[i], zero, FI[i])
+                    ops.axpby(-1.0, FI[i], 0.0, None, FI[i])
+                else:
+                    # F(Y_i, shift (Y_i - Z)) = 0 with shift = 1/(h a_ii): linear; [PETSc] runs Newton on it (rtol 1e-8)
+                    shift = 1.0 / (h * ARK3_AI[i][i])
+                    if A.shift != shift or A.Ainv is None:
+                        A.setup(shift)                             # the same shift for the three implicit stages
+                    ops.copy(Ys[i - 1], Ys[i])                     # initial guess: the previous stage
+
+                    def resid(W, f):
+                        ops.axpby(shift, W, -shift, Z, d)
+                        ops.pattern_ifunction(m, m, opt.L, opt.Du, opt.Dv, W, d, f)
+
+                    resid(Ys[i], R)
+                    r0 = rn = ops.norm2(R)
+                    its = 0
+                    while rn > opt.snes_rtol * r0 and rn > opt.snes_atol and its < opt.snes_max_it:
+                        kr = gmres(ops, A.mult, R, d, A.precond, opt.ksp_rtol, restart=opt.gmres_restart,
+                                   max_it=opt.ksp_max_it, work=work)
+                        ksp_total += kr.its
+                        ops.axpy(-1.0, d, Ys[i])
+                        resid(Ys[i], R)
+                        rn = ops.norm2(R)
+                        its += 1
+                    if not math.isfinite(rn) or rn > opt.snes_rtol * r0 and rn > opt.snes_atol:
+                        raise RuntimeError("TSSolve: stage solve failed at step %d" % k)
+                    ops.axpby(shift, Ys[i], -shift, Z, FI[i])      # YdotI = shift (Y_i - Z)
+                ops.pattern_rhsfunction(m, m, opt.phi, opt.kappa, Ys[i], FE[i])
+            ops.copy(Y, Ynew)
+            ops.copy(Y, Yemb)
+            for j in range(4):
+                ops.axpy(h * ARK3_B[j], FI[j], Ynew)
+                ops.axpy(h * ARK3_B[j], FE[j], Ynew)
+                ops.axpy(h * ARK3_BH[j], FI[j], Yemb)
+                ops.axpy(h * ARK3_BH[j], FE[j], Yemb)
+            enorm = math.sqrt(ops.wrms2(Ynew, Yemb, opt.ts_atol, opt.ts_rtol) / n)     # TSErrorWeightedNorm2
+            accept, hnext = adapt_basic(h, enorm, prev_accept)
+            if accept:
+                break
+            prev_accept = False
+            rejected += 1
+            h = hnext
+        ops.copy(Ynew, Y)
+        t += h
+        steps.append((t, h, enorm))
+        h = match_step(t, hnext, tmax)
+        k += 1
+    if opt.ts_monitor:
+        out("%d TS dt %s time %s" % (k, fmt_g(h), fmt_g(t)))
+    ops.sync()
+    seconds = time.perf_counter() - t0
+    if opt.call_back_report:                                                                           # pattern.c:127-135
+        out("CALL-BACK REPORT")
+        out("  solver type: arkimex")
+        out("  IFunction:   1  | IJacobian:   1")
+        out("  RHSFunction: 1  | RHSJacobian: 0")              # IMEX: the reaction Jacobian is never needed
+    if opt.log_view:
+        out("TSSolve %.6f s (%d steps, %d rejected, %d GMRES iterations)" % (seconds, k, rejected, ksp_total))
+    rep = PatternReport(m=m, steps=steps, Y=Y, seconds=seconds, lines=lines)
+    rep.rejected = rejected
+    return rep

@@ -53,6 +53,9 @@ class FakeOps:
     def norminf(self, x):
         return float(np.max(np.abs(x.a)))
 
+    def wrms2(self, x, y, atol, rtol):
+        return float(np.sum(((x.a - y.a) / (atol + rtol * np.maximum(np.abs(x.a), np.abs(y.a)))) ** 2))
+
     def axpy(self, a, x, y):
         y.a += a * x.a
 

@@ -56,7 +56,7 @@ def test_driver_matches_oracle(argv, okw):
 
 
 @pytest.mark.parametrize("argv,msg", [
-    ("-da_refine 2", "beuler"),                                           # the reference's default is arkimex: not built
+    ("-da_refine 2 -ts_type bdf", "arkimex"),                             # bdf / cn are not built
     ("-ts_type beuler -pc_type ilu", "sequential"),
     ("-ts_type beuler -ptn_noisy_init 0.2", "not provided"),
     ("-ts_type beuler -da_grid_x 4 -da_grid_y 6", "requires mx == my"),   # pattern.c:89
@@ -79,3 +79,84 @@ def test_averaging_restriction_gives_mesh_independent_krylov_counts():
     petsc = [max(po.pattern_beuler(grid=4, refine=r, dt=5.0, tmax=5.0).steps[0][2].ksp_its) for r in (5, 6)]
     avg = [max(po.pattern_beuler(grid=4, refine=r, dt=5.0, tmax=5.0, rscale=0.25).steps[0][2].ksp_its) for r in (5, 6)]
     assert avg[1] <= avg[0] <= 8 and petsc[1] >= 2 * avg[1]
+
+
+# ---- ARKIMEX (pattern.c's default TS type): goldens c/ch5/output/pattern.test1, pattern.test4 -------------------------
+GOLDEN_TEST1 = """running on 16 x 16 grid with square cells of side h = 0.156250 ...
+0 TS dt 5. time 0.
+1 TS dt 10.0587 time 5.
+2 TS dt 9.52508 time 15.0587
+3 TS dt 11.0962 time 24.5838
+4 TS dt 12.5472 time 35.68
+5 TS dt 15.0847 time 48.2272
+6 TS dt 19.2147 time 63.3119
+7 TS dt 27.8378 time 82.5266
+8 TS dt 36.8439 time 110.364
+9 TS dt 26.3958 time 147.208
+10 TS dt 16.1864 time 167.627
+11 TS dt 16.1864 time 183.814
+12 TS dt 35.668 time 200.""".split("\n")
+GOLDEN_TEST4 = """running on 24 x 24 grid with square cells of side h = 0.104167 ...
+0 TS dt 5. time 0.
+1 TS dt 7.32225 time 5.
+2 TS dt 9.34935 time 12.3223
+3 TS dt 12.4736 time 21.6716
+4 TS dt 17.0057 time 34.1452
+5 TS dt 25.5789 time 51.1509
+6 TS dt 28.718 time 76.7298
+7 TS dt 26.7656 time 105.448
+8 TS dt 33.8933 time 132.213
+9 TS dt 33.8933 time 166.107
+10 TS dt 83.5115 time 200.
+CALL-BACK REPORT
+  solver type: arkimex
+  IFunction:   1  | IJacobian:   1
+  RHSFunction: 1  | RHSJacobian: 0""".split("\n")
+TEST1 = "-da_grid_x 4 -da_grid_y 4 -da_refine 2 -ts_monitor"                  # c/ch5/makefile:50
+TEST4 = "-da_refine 3 -ptn_call_back_report -ts_monitor"                      # c/ch5/makefile:59
+
+
+def test_arkimex_golden_files_are_what_we_pin():
+    for name, want in (("pattern.test1", GOLDEN_TEST1), ("pattern.test4", GOLDEN_TEST4)):
+        ref = "/root/reference/c/ch5/output/" + name
+        if not os.path.exists(ref):
+            pytest.skip("reference tree not present")
+        assert open(ref).read().rstrip("\n").split("\n") == want
+
+
+def test_ark3_tableau_satisfies_its_order_conditions():
+    AI, AE, b, bh, c = po.ARK3_AI, po.ARK3_AE, po.ARK3_B, po.ARK3_BH, po.ARK3_C
+    np.testing.assert_allclose(AI.sum(1), c, atol=1e-15)
+    np.testing.assert_allclose(AE.sum(1), c, atol=1e-15)
+    for A in (AI, AE):                                     # third order, including the coupling conditions
+        assert abs(b.sum() - 1) < 1e-15 and abs(b @ c - 0.5) < 1e-15 and abs(b @ c ** 2 - 1 / 3) < 1e-15
+        assert abs(b @ A @ c - 1 / 6) < 1e-15
+    assert abs(bh.sum() - 1) < 1e-15 and abs(bh @ c - 0.5) < 1e-15 and abs(bh @ c ** 2 - 1 / 3) > 1e-3    # embedded: order 2
+    assert np.allclose(np.array(pp.ARK3_AI), AI) and np.allclose(np.array(pp.ARK3_AE), AE)
+    assert np.allclose(pp.ARK3_BH, bh)
+
+
+def test_oracle_reproduces_the_adaptive_arkimex_goldens_verbatim():
+    r = po.pattern_arkimex(grid=4, refine=2)
+    assert r.lines == GOLDEN_TEST1 and r.rejected == 1          # the step proposed at t = 147.208 is rejected once
+    r = po.pattern_arkimex(grid=3, refine=3)
+    assert r.lines == GOLDEN_TEST4[:12] and r.rejected == 0
+
+
+def test_driver_prints_the_arkimex_goldens_verbatim():
+    assert pp.pattern_main(TEST1, FakeOps()).lines == GOLDEN_TEST1
+    assert pp.pattern_main(TEST4, FakeOps()).lines == GOLDEN_TEST4
+
+
+def test_step_size_controller_rules():
+    # accepted step: h * 0.9 * enorm^(-1/3), clipped to [0.1, 10]
+    assert pp.adapt_basic(2.0, 0.001, True) == (True, 2.0 * 0.9 * 0.001 ** (-1 / 3))
+    assert pp.adapt_basic(2.0, 1e-9, True) == (True, 20.0)
+    # first rejection keeps the safety factor, the second consecutive one halves it
+    assert pp.adapt_basic(2.0, 8.0, True) == (False, 2.0 * 0.9 * 0.5)
+    assert pp.adapt_basic(2.0, 8.0, False) == (False, 2.0 * 0.45 * 0.5)
+    # MATCHSTEP: overshoot -> land exactly; within 1 % -> stretch; less than two steps left -> two equal steps
+    assert pp.match_step(190.0, 20.0, 200.0) == 10.0
+    assert pp.match_step(190.0, 9.95, 200.0) == 10.0
+    assert pp.match_step(180.0, 15.0, 200.0) == 10.0
+    assert pp.match_step(100.0, 15.0, 200.0) == 15.0
