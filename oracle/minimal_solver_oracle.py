@@ -338,3 +338,32 @@ def minimal(mx=3, my=3, refine=0, grid_sequence=0, problem="catenoid", q=-0.5, c
     if problem == "catenoid" and q == -0.5:
         errinf = float(np.max(np.abs(u - g)))          # minimal.c:169-179 (g is the exact solution everywhere)
     return MinimalResult(u=u, stages=stages, errinf=errinf, mx=mx, my=my)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# MSEMonitor (c/ch7/minimal.c:284-360, -ms_monitor): surface area and diffusivity bounds by tensor Gauss-Legendre
+# quadrature of the Q1 interpolant (c/interlude/quadrature.h:14-25)
+# ---------------------------------------------------------------------------------------------------------
+GAUSS_LEGENDRE = {1: ((0.0,), (2.0,)),
+                  2: ((-0.577350269189626, 0.577350269189626), (1.0, 1.0)),
+                  3: ((-0.774596669241483, 0.0, 0.774596669241483), (0.555555555555556, 0.888888888888889, 0.555555555555556))}
+
+
+def mse_monitor(u, q=-0.5, quaddegree=3):
+    """(area, Dmin, Dmax) of the iterate u ((my, mx) array on the unit square)."""
+    my, mx = u.shape
+    hx, hy = 1.0 / (mx - 1), 1.0 / (my - 1)
+    xi, w = GAUSS_LEGENDRE[quaddegree]
+    a11, a10, a01, a00 = u[1:, 1:], u[1:, :-1], u[:-1, 1:], u[:-1, :-1]      # au[j][i], au[j][i-1], au[j-1][i], au[j-1][i-1]
+    area, Dmin, Dmax = 0.0, np.inf, 0.0
+    for r, wr in zip(xi, w):
+        dx = hx * 0.5 * (r + 1.0)                       # x - (x_i - hx)
+        for s_, ws in zip(xi, w):
+            dy = hy * 0.5 * (s_ + 1.0)                  # y - (y_j - hy)
+            ux = ((a11 - a10) * dy + (a01 - a00) * (hy - dy)) / (hx * hy)
+            uy = ((a11 - a01) * dx + (a10 - a00) * (hx - dx)) / (hx * hy)
+            W = ux * ux + uy * uy
+            D = np.power(1.0 + W, q)
+            Dmin, Dmax = min(Dmin, float(D.min())), max(Dmax, float(D.max()))
+            area += wr * ws * float(np.sum(np.sqrt(1.0 + W)))
+    return area * hx * hy / 4.0, Dmin, Dmax

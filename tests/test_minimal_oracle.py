@@ -80,3 +80,33 @@ def test_multigrid_preconditioned_newton_is_mesh_independent():
         its.append(max(r.stages[-1].ksp_its))
         assert r.stages[-1].reason == "CONVERGED_FNORM_RELATIVE"
     assert max(its) - min(its) <= 2 and max(its) <= 10
+
+
+def test_golden_minimal_test3_path_independent_lines():
+    """c/ch7/output/minimal.test3 (-snes_mf_operator -pc_type mg -snes_grid_sequence 2 -ms_monitor -ms_quaddegree 2, 2 ranks):
+    MSEMonitor (minimal.c:284-360) prints area and diffusivity bounds of every Newton iterate.  The Newton path of that run
+    (matrix-free operator, Poisson preconditioner) is not restated, but the lines of the INITIAL iterate, of each
+    CONVERGED stage and of each INTERPOLATED stage start do not depend on it: they pin the quadrature monitor, the
+    discretisation, and the DMDA Q1 interpolation -snes_grid_sequence uses."""
+    from oracle import fish_oracle as fo
+    fmt = lambda t: "area = %.8f; %.4f <= D <= %.4f" % t
+    g = mo.mpo.minimal_g(3, 3, "catenoid", 1.0, 1.1)
+    u = np.zeros((3, 3))
+    u[[0, -1], :] = g[[0, -1], :]
+    u[:, [0, -1]] = g[:, [0, -1]]
+    got = [fmt(mo.mse_monitor(u, -0.5, 2))]
+    for stage in range(3):
+        if stage:
+            u = mo.interpolate(u)
+            got.append(fmt(mo.mse_monitor(u, -0.5, 2)))
+        gg = mo.mpo.minimal_g(u.shape[1], u.shape[0], "catenoid", 1.0, 1.1)
+        u = mo.newton(lambda w, gg=gg: mo.mpo.minimal_function(w, gg, -0.5), u, lambda J, uu: fo.ILU0PC(J).apply,
+                      snes_rtol=1e-12).u
+        got.append(fmt(mo.mse_monitor(u, -0.5, 2)))
+    assert got == ["area = 2.14201032; 0.2985 <= D <= 0.8826",        # minimal.test3:1
+                   "area = 1.32217567; 0.6158 <= D <= 0.9510",        # :5-6   (3 x 3 converged)
+                   "area = 1.32217583; 0.6035 <= D <= 0.9518",        # :8     (interpolated to 5 x 5)
+                   "area = 1.33230217; 0.5755 <= D <= 0.9872",        # :11
+                   "area = 1.33230220; 0.5684 <= D <= 0.9872",        # :13    (interpolated to 9 x 9)
+                   "area = 1.33475385; 0.5156 <= D <= 0.9968"]        # :15-16
+    assert "%.5e" % float(np.max(np.abs(u - gg))) == "6.79501e-04"    # :18
