@@ -119,7 +119,10 @@ def fmt_g(v):
 
 
 def pattern_beuler(grid=3, refine=0, dt=5.0, tmax=200.0, pc="mg", rhsjac=True, snes_rtol=1.0e-8, ksp_rtol=1.0e-5,
-                   smooth_its=2, max_steps=10000, rscale=1.0, L=2.5, Du=8.0e-5, Dv=4.0e-5, phi=0.024, kappa=0.06):
+                   smooth_its=2, max_steps=10000, rscale=1.0, theta=1.0, L=2.5, Du=8.0e-5, Dv=4.0e-5, phi=0.024,
+                   kappa=0.06):
+    """[PETSc] TSTHETA with fixed steps: theta = 1 backward Euler (TSBEULER), theta = 1/2 with the endpoint form =
+    Crank-Nicolson (TSCN): solve  F(t+dt, Y, (Y - Y_n)/(theta dt)) - G(Y) + (1-theta)/theta [F(t, Y_n, 0) - G(Y_n)] = 0."""
     mx = grid * 2 ** refine
     par = dict(L=L, Du=Du, Dv=Dv, phi=phi, kappa=kappa)
     Y = mpo.pattern_initial_state(mx, mx, L)
@@ -130,8 +133,11 @@ def pattern_beuler(grid=3, refine=0, dt=5.0, tmax=200.0, pc="mg", rhsjac=True, s
         step = min(dt, tmax - t)
         res.lines.append("%d TS dt %s time %s" % (k, fmt_g(step), fmt_g(t)))
         Y0 = Y.copy()
-        shift = 1.0 / step
-        R = lambda W: mpo.pattern_ifunction(W, (W - Y0) * shift, L, Du, Dv) - mpo.pattern_rhsfunction(W, phi, kappa)
+        shift = 1.0 / (theta * step)
+        aff = 0.0
+        if theta != 1.0:
+            aff = ((1.0 - theta) / theta) * (mpo.pattern_ifunction(Y0, 0.0 * Y0, L, Du, Dv) - mpo.pattern_rhsfunction(Y0, phi, kappa))
+        R = lambda W: (mpo.pattern_ifunction(W, (W - Y0) * shift, L, Du, Dv) - mpo.pattern_rhsfunction(W, phi, kappa)) + aff
         jac = lambda W: stage_jacobian(W, shift, rhsjac, **par)
 
         def make_pc(J, W):

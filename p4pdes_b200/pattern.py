@@ -14,13 +14,14 @@ pattern.c:main -- periodic 2-dof DMDA, banner, InitialState, TSSolve -- and prin
                            (Chebyshev + Jacobi), p4b_pattern_restrict / _prolong_add / _inject (periodic Q1), dense inverse
                            of the base-grid operator x vector
 
+  -ts_type cn              [PETSc] TSCN: the theta = 1/2 endpoint form of the same stage equation (c/ch5/makefile:56)
   -ts_type arkimex (pattern.c's default, :115): [PETSc] TSARKIMEX3 = ARK3(2)4L[2]SA with TSAdaptBasic and
                            MATCHSTEP.  The diffusion (IFunction) is implicit: each of the three implicit stages solves the
                            LINEAR system (shift*I - C L9) Y_i = shift*Z with the same GMRES + multigrid machinery (G' never
                            enters: the reaction is explicit); the embedded 2nd-order solution gives the error estimate,
                            p4b_vec_wrms2 its weighted norm ([PETSc] TSErrorWeightedNorm2).
 
-BDF, CN and `-ptn_noisy_init` (PETSc's random stream) are not provided.  No CPU path: `ops` must be a device Context (tests/ substitutes a NumPy
+BDF and `-ptn_noisy_init` (PETSc's random stream) are not provided.  No CPU path: `ops` must be a device Context (tests/ substitutes a NumPy
 stand-in to exercise this file's control flow without a GPU).
 """
 from __future__ import annotations
@@ -108,8 +109,8 @@ def parse_options(argv) -> PatternOptions:
             raise ValueError("%s is not provided by the device path (PETSc random stream / finite-difference IJacobian)" % a)
         else:
             raise ValueError("unknown or unsupported option %s" % a)
-    if o.ts_type not in ("arkimex", "beuler"):
-        raise ValueError("-ts_type %s: the device path provides arkimex (pattern.c's default) and beuler; bdf and cn are "
+    if o.ts_type not in ("arkimex", "beuler", "cn"):
+        raise ValueError("-ts_type %s: the device path provides arkimex (pattern.c's default), beuler and cn; bdf is "
                          "not built" % o.ts_type)
     if o.pc_type not in ("mg", "none"):
         raise ValueError("-pc_type %s: the device path provides mg and none (ilu/sor are sequential)" % o.pc_type)
@@ -274,6 +275,8 @@ def pattern_main(argv, ops, echo=False) -> PatternReport:
     L0 = levels[0]
     n = L0.n
     Y, Y0, R, Ydot, G = L0.Y, ops.empty(n), ops.empty(n), ops.empty(n), ops.empty(n)
+    theta = 0.5 if opt.ts_type == "cn" else 1.0
+    affine = ops.empty(n) if theta != 1.0 else None
     y, Jy, w, gnew = ops.empty(n), ops.empty(n), ops.empty(n), ops.empty(n)
     work = [ops.empty(n) for _ in range(opt.gmres_restart + 1)]
     ops.pattern_initial_state(m, m, opt.L, Y)                                                          # :146-179
@@ -285,14 +288,23 @@ def pattern_main(argv, ops, echo=False) -> PatternReport:
         dt_last = dt
         if opt.ts_monitor:
             out("%d TS dt %s time %s" % (k, fmt_g(dt), fmt_g(t)))
-        shift = 1.0 / dt
+        # [PETSc] TSTHETA: theta = 1 backward Euler; theta = 1/2 in endpoint form = Crank-Nicolson (TSCN):
+        #   F(W, (W - Y0)/(theta dt)) - G(W) + (1 - theta)/theta [F(Y0, 0) - G(Y0)] = 0
+        shift = 1.0 / (theta * dt)
         ops.copy(Y, Y0)
+        if theta != 1.0:
+            ops.set(0.0, Ydot)
+            ops.pattern_ifunction(m, m, opt.L, opt.Du, opt.Dv, Y0, Ydot, affine)
+            ops.pattern_rhsfunction(m, m, opt.phi, opt.kappa, Y0, G)
+            ops.axpy(-1.0, G, affine)
 
-        def F(W, f):                                               # f = F(W, (W - Y0)/dt) - G(W)
+        def F(W, f):
             ops.axpby(shift, W, -shift, Y0, Ydot)
             ops.pattern_ifunction(m, m, opt.L, opt.Du, opt.Dv, W, Ydot, f)
             ops.pattern_rhsfunction(m, m, opt.phi, opt.kappa, W, G)
             ops.axpy(-1.0, G, f)
+            if theta != 1.0:
+                ops.axpy((1.0 - theta) / theta, affine, f)
 
         F(Y, R)
         fnorm = ops.norm2(R)

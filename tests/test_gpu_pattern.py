@@ -8,7 +8,8 @@ from oracle import minimal_solver_oracle as mso
 from oracle import pattern_solver_oracle as po
 from p4pdes_b200 import pattern as pp
 from p4pdes_b200.fish import Context
-from tests.test_pattern_cpu import GOLDEN_TEST1, GOLDEN_TEST2, GOLDEN_TEST4, TEST1, TEST2, TEST4
+from tests.test_pattern_cpu import (GOLDEN_TEST1, GOLDEN_TEST2, GOLDEN_TEST3, GOLDEN_TEST4, TEST1, TEST2, TEST3,
+                                    TEST4)
 
 pytestmark = pytest.mark.gpu
 PAR = (2.5, 8.0e-5, 4.0e-5, 0.024, 0.06)
@@ -130,3 +131,7 @@ def test_arkimex_goldens_on_device(ctx, argv, golden):
     assert [l for l in r.lines if " TS " not in l] == [l for l in golden if " TS " not in l]
     if r.lines != golden:
         print("printed digits differ:", [(a, b) for a, b in zip(r.lines, golden) if a != b])
+
+
+def test_golden_pattern_test3_crank_nicolson_on_device(ctx):
+    assert pp.pattern_main(TEST3, ctx).lines == GOLDEN_TEST3                 # c/ch5/output/pattern.test3

@@ -160,3 +160,36 @@ def test_step_size_controller_rules():
     assert pp.match_step(190.0, 9.95, 200.0) == 10.0
     assert pp.match_step(180.0, 15.0, 200.0) == 10.0
     assert pp.match_step(100.0, 15.0, 200.0) == 15.0
+
+
+GOLDEN_TEST3 = """running on 12 x 12 grid with square cells of side h = 0.208333 ...
+0 TS dt 5. time 0.
+    Nonlinear solve converged due to CONVERGED_FNORM_RELATIVE iterations 3
+1 TS dt 5. time 5.
+    Nonlinear solve converged due to CONVERGED_FNORM_RELATIVE iterations 3
+2 TS dt 5. time 10.""".split("\n")
+# c/ch5/makefile:56 runs `-ts_type cn -snes_fd_color` on 2 ranks (default PC); the device path uses the analytic
+# Jacobian and multigrid: the printed lines (step sequence, 3 Newton iterations per step) are the same
+TEST3 = "-da_refine 2 -ts_monitor -ts_type cn -ts_max_time 10 -snes_converged_reason -pc_type mg"
+
+
+def test_crank_nicolson_golden_pattern_test3():
+    ref = "/root/reference/c/ch5/output/pattern.test3"
+    if os.path.exists(ref):
+        assert open(ref).read().rstrip("\n").split("\n") == GOLDEN_TEST3
+    for pc in ("ilu", "mg"):
+        r = po.pattern_beuler(grid=3, refine=2, dt=5.0, tmax=10.0, theta=0.5, pc=pc)
+        assert [s[2].its for s in r.steps] == [3, 3]
+        assert r.lines == [GOLDEN_TEST3[0], GOLDEN_TEST3[1], GOLDEN_TEST3[3], GOLDEN_TEST3[5]]
+    assert pp.pattern_main(TEST3, FakeOps()).lines == GOLDEN_TEST3
+
+
+def test_crank_nicolson_is_second_order_and_backward_euler_first_order():
+    # temporal convergence against a fine-step reference on a small grid
+    ref = po.pattern_beuler(grid=3, refine=2, dt=0.125, tmax=8.0, theta=0.5, pc="ilu").Y
+    err = {}
+    for theta in (1.0, 0.5):
+        err[theta] = [np.max(np.abs(po.pattern_beuler(grid=3, refine=2, dt=dt, tmax=8.0, theta=theta, pc="ilu").Y - ref))
+                      for dt in (2.0, 1.0)]
+    assert 1.7 < err[1.0][0] / err[1.0][1] < 2.3          # O(dt)
+    assert 3.3 < err[0.5][0] / err[0.5][1] < 4.8          # O(dt^2)
