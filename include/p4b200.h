@@ -276,6 +276,43 @@ int p4b_pattern_inject(p4b_ctx *ctx, int Mx, int My, const double *yfine, double
 /* out = a x + b y (x, y may alias out) and a device-to-device copy: [PETSc] VecAXPBY / VecWAXPY / VecCopy */
 int p4b_vec_axpby(p4b_ctx *ctx, size_t n, double a, const double *x, double b, const double *y, double *out);
 int p4b_vec_copy(p4b_ctx *ctx, size_t n, const double *x, double *y);
+/* ---- the whole minimal.c run in one call: [PETSc] SNESSolve for `./minimal -snes_fd_color -pc_type mg|none
+ * [-snes_grid_sequence k]` (c/ch7/minimal.c:128-181, c/ch8/cluster.sh:70) -- Newton + cubic bt line search, GMRES(30) or CG,
+ * V cycle on FD-coloured level Jacobians at the injected iterate, grid sequencing; host logic csrc/nk_solver.hpp, every
+ * vector operation one of the kernels above.  Field-for-field the options of minimal.c:69-103 and of PETSc. ---- */
+typedef struct {
+    int problem;                 /* 0 tent, 1 catenoid            -ms_problem */
+    double q, catenoid_c, tent_H;/*                               -ms_q -ms_catenoid_c -ms_tent_H */
+    int exact_init;              /*                               -ms_exact_init */
+    int grid_x, grid_y, refine, grid_sequence;   /*               -da_grid_x -da_grid_y -da_refine -snes_grid_sequence */
+    int ksp_type;                /* 0 gmres, 1 cg                 -ksp_type */
+    double ksp_rtol;
+    int ksp_max_it, gmres_restart;
+    int pc_type;                 /* 0 none, 1 mg                  -pc_type */
+    int mg_levels, smooth_its;   /*                               -pc_mg_levels -mg_levels_ksp_max_it */
+    double snes_rtol, snes_stol, snes_atol;
+    int snes_max_it;
+    int snes_monitor;            /* 0 off, 1 -snes_monitor, 2 -snes_monitor_short */
+    int snes_converged_reason, ksp_converged_reason;
+} p4b_minimal_opts;
+typedef struct {
+    int mx, my, its, reason, nksp;   /* reason: 2 FNORM_ABS, 3 FNORM_RELATIVE, 4 SNORM_RELATIVE, < 0 diverged ([PETSc] numbering) */
+    int ksp_its[64];
+    double lambda[64];               /* accepted line-search step of every Newton iteration */
+    double fnorm[65];                /* ||F|| before the first and after every iteration */
+} p4b_minimal_stage;
+typedef struct {
+    int mx, my, nstages;             /* final grid; grid-sequence stages, coarsest first */
+    p4b_minimal_stage stage[16];
+    double errinf;                   /* |u - uexact|_inf (catenoid, q = -1/2), else -1 */
+    int error;
+    char errmsg[256];
+} p4b_minimal_result;
+typedef void (*p4b_line_fn)(const char *line, void *ctx);    /* receives the lines minimal.c / PETSc would print */
+int p4b_minimal_default_opts(p4b_minimal_opts *o);
+/* u_out (device, may be NULL): the final iterate, u_capacity doubles available */
+int p4b_minimal_solve(p4b_ctx *ctx, const p4b_minimal_opts *opts, p4b_line_fn line, void *line_ctx, double *u_out,
+                      size_t u_capacity, p4b_minimal_result *result);
 typedef struct p4b_sell p4b_sell;
 int p4b_sell_create(p4b_ctx *ctx, int nrows, const int *rowptr_host, const int *colind_host, const double *vals_host,
                     p4b_sell **A);

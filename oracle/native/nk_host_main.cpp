@@ -1,0 +1,61 @@
+// nk_host_main.cpp -- runs p4pdes_b200/csrc/nk_solver.hpp on HostOps (TEST INFRASTRUCTURE ONLY; see host_ops.hpp).
+//   nk_host_test [-ms_problem tent|catenoid] [-ms_q q] [-ms_catenoid_c c] [-da_grid_x n] [-da_grid_y n] [-da_refine r]
+//                [-snes_grid_sequence k] [-ksp_type gmres|cg] [-pc_type mg|none] [-pc_mg_levels n] [-monitor]
+// prints the solver's lines, then one JSON line with the per-stage results and a checksum of the solution.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+
+#include "host_ops.hpp"
+#include "nk_solver.hpp"
+
+static void print_line(const char *s, void *) { printf("%s\n", s); }
+
+int main(int argc, char **argv) {
+    using namespace p4b::nk;
+    MinimalOpts o;
+    default_opts(&o);
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
+        if (a == "-ms_problem") o.problem = std::string(next()) == "tent" ? 0 : 1;
+        else if (a == "-ms_q") o.q = atof(next());
+        else if (a == "-ms_catenoid_c") o.catenoid_c = atof(next());
+        else if (a == "-ms_tent_H") o.tent_H = atof(next());
+        else if (a == "-da_grid_x") o.grid_x = atoi(next());
+        else if (a == "-da_grid_y") o.grid_y = atoi(next());
+        else if (a == "-da_refine") o.refine = atoi(next());
+        else if (a == "-snes_grid_sequence") o.grid_sequence = atoi(next());
+        else if (a == "-ksp_type") o.ksp_type = std::string(next()) == "cg" ? KSP_CG : KSP_GMRES;
+        else if (a == "-pc_type") o.pc_type = std::string(next()) == "mg" ? PC_MG : PC_NONE;
+        else if (a == "-pc_mg_levels") o.mg_levels = atoi(next());
+        else if (a == "-snes_fd_color") { }
+        else if (a == "-monitor") { o.snes_monitor = 2; o.snes_converged_reason = 1; o.ksp_converged_reason = 1; }
+        else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
+    }
+    HostOps ops;
+    MinimalResult R;
+    double *u = nullptr;
+    Printer pr{print_line, nullptr};
+    const int rc = minimal_solve(&ops, o, pr, &u, &R);
+    if (rc) { fprintf(stderr, "minimal_solve failed: %d\n", rc); return 1; }
+    double sum = 0.0, sum2 = 0.0;
+    for (int n = 0; n < R.mx * R.my; n++) { sum += u[n]; sum2 += u[n] * u[n] * (1 + n % 7); }
+    printf("{\"mx\": %d, \"my\": %d, \"errinf\": %.17g, \"sum\": %.17g, \"wsum2\": %.17g, \"allocs\": %lld, \"frees\": %lld, \"stages\": [",
+           R.mx, R.my, R.errinf, sum, sum2, ops.allocs, ops.frees + 1);
+    for (int s = 0; s < R.nstages; s++) {
+        const StageResult &S = R.stage[s];
+        printf("%s{\"mx\": %d, \"its\": %d, \"reason\": \"%s\", \"ksp_its\": [", s ? ", " : "", S.mx, S.its, snes_reason_name(S.reason));
+        for (int k = 0; k < S.its; k++) printf("%s%d", k ? ", " : "", S.ksp_its[k]);
+        printf("], \"lambda\": [");
+        for (int k = 0; k < S.its; k++) printf("%s%.17g", k ? ", " : "", S.lambda[k]);
+        printf("], \"fnorm\": [");
+        for (int k = 0; k <= S.its; k++) printf("%s%.17g", k ? ", " : "", S.fnorm[k]);
+        printf("]}");
+    }
+    printf("]}\n");
+    ops.release(u);
+    return 0;
+}

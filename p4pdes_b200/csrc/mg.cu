@@ -859,6 +859,10 @@ static int plan_levels(const p4b_grid *g, const p4b_mg_opts &o, int P, LevelPlan
     return 0;
 }
 
+namespace p4b {
+cudaStream_t ctx_stream(p4b_ctx *c) { return c->stream; }     // for the other translation units (nk_device.cu)
+}  // namespace p4b
+
 extern "C" {
 
 int p4b_version(void) { return P4B_VERSION; }

@@ -1,0 +1,117 @@
+// nk_device.cu -- p4b_minimal_solve: the Newton-Krylov-multigrid host logic of nk_solver.hpp with every vector
+// operation a CUDA kernel of this library (vectors in HBM, scalars on the host).
+//
+// Replaces, for `./minimal -snes_fd_color -pc_type mg [-snes_grid_sequence k]` (c/ch8/cluster.sh:70), what the reference
+// gets from [PETSc] SNESSolve: see nk_solver.hpp.  The Python host p4pdes_b200/minimal.py runs the same algorithm
+// through the individual C-ABI calls; this entry point is the native form of it (one call, no interpreter between
+// the kernels) and what a C host such as the PETSc-shaped shim binds.
+#include <math.h>
+
+#include "kernels.h"
+#include "nk_solver.hpp"
+
+namespace p4b {
+
+// defined in mg.cu (the context owns the stream and the reduction scratch)
+cudaStream_t ctx_stream(p4b_ctx *c);
+
+struct DeviceOps {
+    p4b_ctx *c;
+    cudaStream_t st;
+    int err = 0;
+    int error() const { return err; }
+    void chk(int rc) { if (rc && !err) err = rc; }
+    void cu(cudaError_t e) { if (e != cudaSuccess && !err) err = 70 + (int)e % 20; }
+
+    double *alloc(size_t n) {
+        double *p = nullptr;
+        cu(cudaMallocAsync((void **)&p, sizeof(double) * (n ? n : 1), st));
+        return p;
+    }
+    void release(double *p) { if (p) cu(cudaFreeAsync(p, st)); }
+    void to_host(const double *s, double *d, size_t n) {
+        cu(cudaMemcpyAsync(d, s, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        cu(cudaStreamSynchronize(st));
+    }
+    void from_host(const double *s, double *d, size_t n) {
+        cu(cudaMemcpyAsync(d, s, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+        cu(cudaStreamSynchronize(st));          // the host buffer may go away right after
+    }
+    double dot(size_t n, const double *x, const double *y) { double r = NAN; chk(p4b_vec_dot(c, n, x, y, &r)); return r; }
+    double norm2(size_t n, const double *x) { double r = NAN; chk(p4b_vec_norm2(c, n, x, &r)); return r; }
+    double norminf(size_t n, const double *x) { double r = NAN; chk(p4b_vec_norminf(c, n, x, &r)); return r; }
+    void axpy(size_t n, double a, const double *x, double *y) { chk(p4b_vec_axpy(c, n, a, x, y)); }
+    void aypx(size_t n, double a, const double *x, double *y) { chk(p4b_vec_aypx(c, n, a, x, y)); }
+    void axpby(size_t n, double a, const double *x, double b, const double *y, double *out) { chk(p4b_vec_axpby(c, n, a, x, b, y, out)); }
+    void copy(size_t n, const double *x, double *y) { chk(p4b_vec_copy(c, n, x, y)); }
+    void set(size_t n, double a, double *y) { chk(p4b_vec_set(c, n, a, y)); }
+    void minimal_sample(int mx, int my, int problem, double H, double cc, double *g) { chk(p4b_minimal_sample(c, mx, my, problem, H, cc, g)); }
+    void minimal_function(int mx, int my, double q, const double *u, const double *g, double *F) { chk(p4b_minimal_function(c, mx, my, q, u, g, F)); }
+    void minimal_jacobian_fd(int mx, int my, double q, const double *u, const double *g, const double *F0, double *vals) {
+        chk(p4b_minimal_jacobian_fd(c, mx, my, q, u, g, F0, vals));
+    }
+    void stencil9_apply(int mx, int my, const double *vals, const double *x, double *y) { chk(p4b_stencil9_apply(c, mx, my, vals, x, y)); }
+    void stencil9_lin(int mx, int my, const double *vals, const double *u, const double *b, const double *pm1, double ca, double cb,
+                      double cg, int jacobi, double *out) {
+        chk(p4b_stencil9_lin(c, mx, my, vals, u, b, pm1, ca, cb, cg, jacobi, out));
+    }
+    double stencil9_gershgorin(int mx, int my, const double *vals, double *work) {
+        double r = NAN;
+        chk(p4b_stencil9_gershgorin(c, mx, my, vals, work, &r));
+        return r;
+    }
+    void inject2d(int cmx, int cmy, const double *uf, double *uc) { chk(p4b_inject2d(c, cmx, cmy, uf, uc)); }
+    static p4b_grid grid2d(int mx, int my) {
+        p4b_grid g;
+        g.dim = 2; g.mx = mx; g.my = my; g.mz = 1;
+        g.Lx = g.Ly = g.Lz = 1.0;
+        g.cx = g.cy = g.cz = 1.0;
+        return g;
+    }
+    void restrict2d(int fmx, int fmy, const double *rf, double *bc) { p4b_grid g = grid2d(fmx, fmy); chk(p4b_restrict(c, &g, rf, bc)); }
+    void prolong_add2d(int fmx, int fmy, const double *xc, double *xf) { p4b_grid g = grid2d(fmx, fmy); chk(p4b_prolong_add(c, &g, xc, xf)); }
+    void initial_state2d(int mx, int my, const double *g, double *u) { p4b_grid gr = grid2d(mx, my); chk(p4b_initial_state(c, &gr, g, 1, u)); }
+    void dense_matvec(int n, const double *Ainv, const double *b, double *x) { chk(p4b_dense_matvec(c, n, Ainv, b, x)); }
+};
+
+}  // namespace p4b
+
+using namespace p4b;
+
+extern "C" int p4b_minimal_default_opts(p4b_minimal_opts *o) {
+    if (!o) return fail(62, "null options");
+    static_assert(sizeof(p4b_minimal_opts) == sizeof(nk::MinimalOpts), "p4b_minimal_opts and nk::MinimalOpts must agree");
+    nk::default_opts(reinterpret_cast<nk::MinimalOpts *>(o));
+    return 0;
+}
+
+extern "C" int p4b_minimal_solve(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_line_fn line, void *line_ctx, double *u_out,
+                                 size_t u_capacity, p4b_minimal_result *result) {
+    static_assert(sizeof(p4b_minimal_result) == sizeof(nk::MinimalResult), "p4b_minimal_result and nk::MinimalResult must agree");
+    static_assert(sizeof(p4b_minimal_stage) == sizeof(nk::StageResult), "p4b_minimal_stage and nk::StageResult must agree");
+    if (!c || !opts || !result) return fail(62, "p4b_minimal_solve: null argument");
+    const nk::MinimalOpts &o = *reinterpret_cast<const nk::MinimalOpts *>(opts);
+    if (o.problem != 0 && o.problem != 1) return fail(5, "unknown problem type");                                   // minimal.c:127
+    if (o.problem == 0 && o.exact_init) return fail(2, "initialization with exact solution only possible for -mse_problem catenoid");
+    if (o.problem == 1 && o.catenoid_c < 1.0) return fail(3, "catenoid exact solution only valid if c >= 1");       // :116
+    if (o.exact_init && o.q != -0.5) return fail(4, "initialization with catenoid exact solution only possible if q=-0.5");
+    if (o.grid_x < 3 || o.grid_y < 3) return fail(60, "grid needs at least 3 nodes per dimension");
+    DeviceOps ops{c, ctx_stream(c)};
+    nk::Printer pr{line, line_ctx};
+    double *u = nullptr;
+    nk::MinimalResult &R = *reinterpret_cast<nk::MinimalResult *>(result);
+    int rc = nk::minimal_solve(&ops, o, pr, u_out ? &u : nullptr, &R);
+    if (!rc && ops.error()) rc = ops.error();
+    if (!rc && u_out) {
+        const size_t n = (size_t)R.mx * R.my;
+        if (u_capacity < n) rc = 63;
+        else if (cudaMemcpyAsync(u_out, u, sizeof(double) * n, cudaMemcpyDeviceToDevice, ops.st) != cudaSuccess) rc = 70;
+    }
+    if (u) cudaFreeAsync(u, ops.st);
+    cudaStreamSynchronize(ops.st);
+    if (rc == 61) return fail(61, "base grid of the multigrid hierarchy is larger than 65 x 65: use a coarser -da_grid_x/_y");
+    if (rc == 62) return fail(62, "base-grid Jacobian is singular");
+    if (rc == 63) return fail(63, "u_out holds %zu doubles, the final grid needs %d x %d", u_capacity, R.mx, R.my);
+    if (rc) return fail(rc, "p4b_minimal_solve failed (%s)", p4b_last_error());
+    return 0;
+}

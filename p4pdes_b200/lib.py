@@ -56,6 +56,29 @@ class KSPResult(C.Structure):
         return [self.hist[i] for i in range(self.nhist)]
 
 
+class MinimalOpts(C.Structure):
+    """p4b_minimal_opts (include/p4b200.h)."""
+    _fields_ = [("problem", C.c_int), ("q", C.c_double), ("catenoid_c", C.c_double), ("tent_H", C.c_double),
+                ("exact_init", C.c_int), ("grid_x", C.c_int), ("grid_y", C.c_int), ("refine", C.c_int),
+                ("grid_sequence", C.c_int), ("ksp_type", C.c_int), ("ksp_rtol", C.c_double), ("ksp_max_it", C.c_int),
+                ("gmres_restart", C.c_int), ("pc_type", C.c_int), ("mg_levels", C.c_int), ("smooth_its", C.c_int),
+                ("snes_rtol", C.c_double), ("snes_stol", C.c_double), ("snes_atol", C.c_double), ("snes_max_it", C.c_int),
+                ("snes_monitor", C.c_int), ("snes_converged_reason", C.c_int), ("ksp_converged_reason", C.c_int)]
+
+
+class MinimalStage(C.Structure):
+    _fields_ = [("mx", C.c_int), ("my", C.c_int), ("its", C.c_int), ("reason", C.c_int), ("nksp", C.c_int),
+                ("ksp_its", C.c_int * 64), ("lam", C.c_double * 64), ("fnorm", C.c_double * 65)]
+
+
+class MinimalResult(C.Structure):
+    _fields_ = [("mx", C.c_int), ("my", C.c_int), ("nstages", C.c_int), ("stage", MinimalStage * 16),
+                ("errinf", C.c_double), ("error", C.c_int), ("errmsg", C.c_char * 256)]
+
+
+LINE_FN = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)
+
+
 class KernelStat(C.Structure):
     _fields_ = [("launches", C.c_longlong), ("ms", C.c_double), ("bytes", C.c_double)]
 
@@ -140,6 +163,8 @@ _SIGS = {
     "p4b_pattern_restrict": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
     "p4b_pattern_prolong_add": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
     "p4b_pattern_inject": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
+    "p4b_minimal_default_opts": (C.c_int, [C.POINTER(MinimalOpts)]),
+    "p4b_minimal_solve": (C.c_int, [_P, C.POINTER(MinimalOpts), LINE_FN, _P, _D, C.c_size_t, C.POINTER(MinimalResult)]),
     "p4b_sell_create": (C.c_int, [_P, C.c_int, _P, _P, _P, C.POINTER(_P)]),
     "p4b_sell_spmv": (C.c_int, [_P, _D, _D]),
     "p4b_sell_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

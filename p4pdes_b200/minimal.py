@@ -510,7 +510,51 @@ class MinimalReport:
     lines: list
 
 
-def minimal_main(argv, ops, echo=False, keep_solution=True) -> MinimalReport:
+SNES_REASONS = {2: "CONVERGED_FNORM_ABS", 3: "CONVERGED_FNORM_RELATIVE", 4: "CONVERGED_SNORM_RELATIVE",
+                -5: "DIVERGED_MAX_IT", -6: "DIVERGED_LINE_SEARCH", -4: "DIVERGED_FNORM_NAN"}
+
+
+def _minimal_native(opt: MinimalOptions, ctx, out, keep_solution) -> MinimalReport:
+    """The same run through ONE C-ABI call, p4b_minimal_solve (csrc/nk_device.cu + nk_solver.hpp): the host logic in C++
+    inside the library, no interpreter between the kernels."""
+    import ctypes as C
+
+    from . import lib as L
+    o = L.MinimalOpts()
+    L.check(ctx.lib.p4b_minimal_default_opts(C.byref(o)))
+    o.problem, o.q, o.catenoid_c, o.tent_H = PROBLEMS[opt.problem], opt.q, opt.catenoid_c, opt.tent_H
+    o.exact_init, o.grid_x, o.grid_y, o.refine = int(opt.exact_init), opt.grid_x, opt.grid_y, opt.refine
+    o.grid_sequence, o.ksp_type, o.ksp_rtol = opt.grid_sequence, {"gmres": 0, "cg": 1}[opt.ksp_type], opt.ksp_rtol
+    o.ksp_max_it, o.gmres_restart, o.pc_type = opt.ksp_max_it, opt.gmres_restart, {"none": 0, "mg": 1}[opt.pc_type]
+    o.mg_levels, o.smooth_its = opt.mg_levels, opt.smooth_its
+    o.snes_rtol, o.snes_stol, o.snes_atol, o.snes_max_it = opt.snes_rtol, opt.snes_stol, opt.snes_atol, opt.snes_max_it
+    o.snes_monitor = 2 if opt.snes_monitor_short else (1 if opt.snes_monitor else 0)
+    o.snes_converged_reason, o.ksp_converged_reason = int(opt.snes_converged_reason), int(opt.ksp_converged_reason)
+    mx, my = opt.grid_x, opt.grid_y
+    for _ in range(opt.refine + opt.grid_sequence):
+        mx, my = 2 * mx - 1, 2 * my - 1
+    u = ctx.empty(mx * my) if keep_solution else None
+    res = L.MinimalResult()
+    cb = L.LINE_FN(lambda line, _ctx: out(line.decode()))
+    t0 = time.perf_counter()
+    L.check(ctx.lib.p4b_minimal_solve(ctx.h, C.byref(o), cb, None, u.data_ptr() if u is not None else None, mx * my,
+                                      C.byref(res)))
+    seconds = time.perf_counter() - t0
+    stages = []
+    for s in range(res.nstages):
+        st = res.stage[s]
+        stages.append(SNESResult(its=st.its, reason=SNES_REASONS.get(st.reason, str(st.reason)),
+                                 fnorms=[st.fnorm[k] for k in range(st.its + 1)],
+                                 ksp_its=[st.ksp_its[k] for k in range(st.its)], lambdas=[st.lam[k] for k in range(st.its)]))
+    if opt.log_view:
+        out("SNESSolve (all grid-sequence stages) %.6f s" % seconds)
+    return MinimalReport(mx=res.mx, my=res.my, stages=stages, errinf=res.errinf if res.errinf >= 0 else None, u=u,
+                         seconds=seconds, lines=None)
+
+
+def minimal_main(argv, ops, echo=False, keep_solution=True, native=False) -> MinimalReport:
+    """native=True: the whole run is one call of p4b_minimal_solve (host logic in C++ inside the library) instead of this
+    file's loops over the individual C-ABI calls; same options, same lines, same report."""
     opt = parse_options(argv)
     lines = []
 
@@ -518,6 +562,11 @@ def minimal_main(argv, ops, echo=False, keep_solution=True) -> MinimalReport:
         lines.append(s)
         if echo:
             print(s)
+
+    if native:
+        rep = _minimal_native(opt, ops, out, keep_solution)
+        rep.lines = lines
+        return rep
 
     mx, my = opt.grid_x, opt.grid_y
     for _ in range(opt.refine):

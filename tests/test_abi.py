@@ -95,3 +95,26 @@ def test_option_parser_mirrors_fish_checks():
         parse_options("-pc_type mg -mg_levels_pc_type sor")
     with pytest.raises(L.P4BError, match="ILU"):
         parse_options("-fsh_dim 2")
+
+
+def test_minimal_solve_structs_match_the_header(lib, tmp_path):
+    """ctypes mirrors of p4b_minimal_opts / p4b_minimal_result against the C header: defaults written by the library
+    arrive in the right fields, and the sizes agree with what a C compiler makes of include/p4b200.h."""
+    import subprocess
+    o = L.MinimalOpts()
+    assert lib.p4b_minimal_default_opts(C.byref(o)) == 0
+    assert (o.problem, o.q, o.catenoid_c, o.tent_H, o.exact_init) == (1, -0.5, 1.1, 1.0, 0)
+    assert (o.grid_x, o.grid_y, o.refine, o.grid_sequence) == (3, 3, 0, 0)
+    assert (o.ksp_type, o.ksp_rtol, o.ksp_max_it, o.gmres_restart) == (0, 1.0e-5, 10000, 30)
+    assert (o.pc_type, o.mg_levels, o.smooth_its) == (1, 0, 2)
+    assert (o.snes_rtol, o.snes_stol, o.snes_atol, o.snes_max_it) == (1.0e-8, 1.0e-8, 1.0e-50, 50)
+    assert (o.snes_monitor, o.snes_converged_reason, o.ksp_converged_reason) == (0, 0, 0)
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "p4b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n",'
+                   'sizeof(p4b_minimal_opts),sizeof(p4b_minimal_stage),sizeof(p4b_minimal_result),'
+                   'offsetof(p4b_minimal_result,errinf),offsetof(p4b_minimal_stage,fnorm));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    assert got == [C.sizeof(L.MinimalOpts), C.sizeof(L.MinimalStage), C.sizeof(L.MinimalResult),
+                   L.MinimalResult.errinf.offset, L.MinimalStage.fnorm.offset]

@@ -1,0 +1,84 @@
+"""The C++ Newton-Krylov-multigrid host logic (p4pdes_b200/csrc/nk_solver.hpp -- what p4b_minimal_solve runs on the
+device) exercised WITHOUT a GPU: oracle/Makefile instantiates the same template with plain C++ loops
+(oracle/native/host_ops.hpp, test infrastructure) and this test compares the runs with the independent Python oracle."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import minimal_solver_oracle as mo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "oracle", "nk_host_test")
+
+
+@pytest.fixture(scope="module")
+def exe():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "nk_host_test"])
+    return EXE
+
+
+def run(exe, *args):
+    p = subprocess.run([exe, *map(str, args)], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    lines = p.stdout.rstrip("\n").split("\n")
+    return lines[:-1], json.loads(lines[-1])
+
+
+@pytest.mark.parametrize("argv,okw", [
+    (("-snes_grid_sequence", 3, "-ms_problem", "tent", "-pc_type", "mg"), dict(grid_sequence=3, problem="tent", pc="mg")),
+    (("-da_refine", 3, "-pc_type", "mg", "-ksp_type", "cg", "-ms_q", 0.0, "-ms_problem", "tent"),
+     dict(refine=3, problem="tent", q=0.0, pc="mg", ksp="cg")),
+    (("-da_grid_x", 5, "-da_grid_y", 9, "-snes_grid_sequence", 2, "-pc_type", "mg", "-ms_problem", "tent"),
+     dict(mx=5, my=9, grid_sequence=2, pc="mg", problem="tent")),
+    (("-da_refine", 2, "-pc_type", "none", "-ms_problem", "tent"), dict(refine=2, problem="tent", pc="none")),
+    (("-da_refine", 4, "-pc_type", "mg", "-pc_mg_levels", 3, "-ms_problem", "tent"),
+     dict(refine=4, pc="mg", mg_levels=3, problem="tent")),
+])
+def test_native_solver_matches_python_oracle(exe, argv, okw):
+    _, d = run(exe, "-snes_fd_color", *argv)
+    o = mo.minimal(**okw)
+    assert (d["mx"], d["my"]) == (o.mx, o.my)
+    assert [s["its"] for s in d["stages"]] == [s.its for s in o.stages]
+    assert [s["ksp_its"] for s in d["stages"]] == [s.ksp_its for s in o.stages]
+    assert all(s["reason"] == t.reason for s, t in zip(d["stages"], o.stages))
+    for k, (s, t) in enumerate(zip(d["stages"], o.stages)):
+        # (the first grid starts at u = 0, where the FD Jacobian carries ~1 % rounding noise: pow vs numpy power)
+        np.testing.assert_allclose(s["fnorm"], t.fnorms, rtol=5e-2 if k == 0 else 1e-2, atol=1e-10 * t.fnorms[0])
+        np.testing.assert_allclose(s["lambda"], t.lambdas, rtol=1e-6)
+    assert abs(d["sum"] - float(o.u.sum())) <= 1e-9 * abs(float(o.u.sum()))
+    if o.errinf is not None:
+        assert abs(d["errinf"] - o.errinf) <= 1e-10
+    assert d["allocs"] == d["frees"]                      # every vector the solver took from Ops went back
+
+
+def test_native_solver_on_the_catenoid_cold_start(exe):
+    """The catenoid runs start at u = 0, where the first finite-difference Jacobian is rounding-noise limited
+    (tests/test_minimal_oracle.py): libm pow vs numpy power take different Newton paths on the first grid.  Everything
+    path-independent agrees: convergence, the later (grid-sequenced) stages, the solution and its error."""
+    _, d = run(exe, "-snes_fd_color", "-da_grid_x", 5, "-da_grid_y", 9, "-snes_grid_sequence", 2, "-pc_type", "mg",
+               "-ms_catenoid_c", 1.5)
+    o = mo.minimal(mx=5, my=9, grid_sequence=2, pc="mg", catenoid_c=1.5)
+    assert all(s["reason"] == "CONVERGED_FNORM_RELATIVE" for s in d["stages"])
+    assert [s["its"] for s in d["stages"][1:]] == [s.its for s in o.stages[1:]]
+    assert abs(d["errinf"] - o.errinf) <= 1e-8 and abs(d["sum"] - float(o.u.sum())) <= 1e-7 * abs(float(o.u.sum()))
+
+
+def test_native_solver_prints_the_reference_lines(exe):
+    lines, d = run(exe, "-snes_fd_color", "-ms_problem", "catenoid", "-ms_catenoid_c", 2.0, "-da_refine", 1, "-monitor")
+    assert lines[0] == "  0 SNES Function norm 1.08276"                                            # minimal.test1:1
+    assert lines[-1] == "done on 5 x 5 grid and problem catenoid:  error |u-uexact|_inf = 1.10603e-04"   # :8
+    assert lines[-2].startswith("Nonlinear solve converged due to CONVERGED_FNORM_RELATIVE iterations ")
+    assert abs(d["stages"][0]["its"] - 5) <= 1
+
+
+def test_banded_inverse_agrees_with_lapack(exe):
+    # the base-grid solve of the native path (banded LU + n solves) against numpy on the Python driver's dense copy:
+    # same Newton / Krylov counts with a 17 x 17 base grid (289 unknowns, bandwidth 18)
+    _, d = run(exe, "-snes_fd_color", "-da_grid_x", 17, "-da_grid_y", 17, "-snes_grid_sequence", 1, "-pc_type", "mg",
+               "-ms_problem", "tent")
+    o = mo.minimal(mx=17, my=17, grid_sequence=1, pc="mg", problem="tent")
+    assert [s["ksp_its"] for s in d["stages"]] == [s.ksp_its for s in o.stages]
+    assert abs(d["sum"] - float(o.u.sum())) <= 1e-9 * abs(float(o.u.sum()))
