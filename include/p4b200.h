@@ -313,6 +313,39 @@ int p4b_minimal_default_opts(p4b_minimal_opts *o);
 /* u_out (device, may be NULL): the final iterate, u_capacity doubles available */
 int p4b_minimal_solve(p4b_ctx *ctx, const p4b_minimal_opts *opts, p4b_line_fn line, void *line_ctx, double *u_out,
                       size_t u_capacity, p4b_minimal_result *result);
+/* ---- the whole pattern.c run in one call: [PETSc] TSSolve for `./pattern [-ts_type arkimex|beuler|cn] -pc_type mg|none`
+ * (c/ch5/pattern.c:99-125, c/ch5/makefile:49-62): TSARKIMEX3 + TSAdaptBasic + MATCHSTEP, or TSTHETA with Newton + bt;
+ * stage solves GMRES(30) + V cycle on the matrix-free stage operator; host logic csrc/ts_solver.hpp. ---- */
+typedef struct {
+    double L, Du, Dv, phi, kappa;          /* -ptn_L -ptn_Du -ptn_Dv -ptn_phi -ptn_kappa (pattern.c:47-52) */
+    int no_rhsjacobian, call_back_report;  /* -ptn_no_rhsjacobian -ptn_call_back_report */
+    int grid_x, grid_y, refine;            /* -da_grid_x -da_grid_y -da_refine (periodic: refine doubles) */
+    int ts_type;                           /* 0 arkimex (pattern.c's default), 1 beuler, 2 cn */
+    double ts_dt, ts_max_time;
+    int ts_max_steps;
+    double ts_rtol, ts_atol;
+    int ts_monitor;
+    int pc_type;                           /* 0 none, 1 mg */
+    int smooth_its;
+    double mg_rscale;                      /* -p4b_mg_rscale: 1 = [PETSc] R = P^T, 0.25 = averaging restriction */
+    double snes_rtol, snes_stol, snes_atol;
+    int snes_max_it;
+    double ksp_rtol;
+    int ksp_max_it, gmres_restart;
+    int snes_converged_reason, ksp_converged_reason;
+} p4b_pattern_opts;
+typedef struct {
+    int m, nsteps, rejected;               /* grid m x m x 2; accepted steps; rejected step attempts (arkimex) */
+    long long ksp_its_total, newton_its_total;
+    double t_final, dt_last;
+    double step_t[512], step_dt[512];      /* the first 512 steps: time after the step, step taken */
+    int step_newton[512];                  /* Newton iterations of the step (summed over the stages for arkimex) */
+    int error;
+} p4b_pattern_result;
+int p4b_pattern_default_opts(p4b_pattern_opts *o);
+/* Y_out (device, may be NULL): the final state, 2*m*m doubles, (u,v) interleaved */
+int p4b_pattern_solve(p4b_ctx *ctx, const p4b_pattern_opts *opts, p4b_line_fn line, void *line_ctx, double *Y_out,
+                      size_t Y_capacity, p4b_pattern_result *result);
 typedef struct p4b_sell p4b_sell;
 int p4b_sell_create(p4b_ctx *ctx, int nrows, const int *rowptr_host, const int *colind_host, const double *vals_host,
                     p4b_sell **A);

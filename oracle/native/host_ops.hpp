@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <vector>
 
+#include "ts_solver.hpp"      // p4b::nk::PatternOpts (the options struct the pattern operations take)
+
 struct HostOps {
     int err = 0;
     long long allocs = 0, frees = 0;
@@ -183,6 +185,150 @@ struct HostOps {
                 xf[j * fmx + i] += s * (oi ? 0.5 : 1.0) * (oj ? 0.5 : 1.0);
             }
     }
+    // ---- c/ch5/pattern.c ----------------------------------------------------------------------------------
+    typedef p4b::nk::PatternOpts PO;
+    // [PETSc] TSErrorWeightedNorm2 (sum of squares; the caller divides by n and takes the root)
+    double wrms2(size_t n, const double *x, const double *y, double atol, double rtol) {
+        double s = 0.0;
+        for (size_t i = 0; i < n; i++) {
+            const double e = (x[i] - y[i]) / (atol + rtol * std::max(fabs(x[i]), fabs(y[i])));
+            s += e * e;
+        }
+        return s;
+    }
+    // pattern.c:146-179  InitialState without noise
+    void pattern_initial_state(int mx, int my, double L, double *Y) {
+        const double PI = 3.14159265358979323846264338327950288, ledge = (L - 0.5) / 2.0, redge = L - ledge;
+        for (int j = 0; j < my; j++)
+            for (int i = 0; i < mx; i++) {
+                const double x = i * (L / mx), y = j * (L / my);
+                double v = 0.0;
+                if (x >= ledge && x <= redge && y >= ledge && y <= redge) {
+                    const double sx = sin(4.0 * PI * x), sy = sin(4.0 * PI * y);
+                    v = 0.5 * sx * sx * sy * sy;
+                }
+                Y[2 * (j * mx + i)] = 1.0 - 2.0 * v;
+                Y[2 * (j * mx + i) + 1] = v;
+            }
+    }
+    static void lap9(int m, const double *Y, int i, int j, double *lu, double *lv) {
+        auto at = [&](int ii, int jj, int c) { return Y[2 * (((jj + m) % m) * m + (ii + m) % m) + c]; };
+        double l[2];
+        for (int c = 0; c < 2; c++)
+            l[c] = at(i - 1, j + 1, c) + 4.0 * at(i, j + 1, c) + at(i + 1, j + 1, c) + 4.0 * at(i - 1, j, c) - 20.0 * at(i, j, c) +
+                   4.0 * at(i + 1, j, c) + at(i - 1, j - 1, c) + 4.0 * at(i, j - 1, c) + at(i + 1, j - 1, c);
+        *lu = l[0];
+        *lv = l[1];
+    }
+    // pattern.c:242-267  FormIFunctionLocal
+    void pattern_ifunction(int m, const PO &o, const double *Y, const double *Ydot, double *F) {
+        const double h = o.L / m, Cu = o.Du / (6.0 * h * h), Cv = o.Dv / (6.0 * h * h);
+        std::vector<double> out((size_t)2 * m * m);
+        for (int j = 0; j < m; j++)
+            for (int i = 0; i < m; i++) {
+                double lu, lv;
+                lap9(m, Y, i, j, &lu, &lv);
+                const int k = 2 * (j * m + i);
+                out[k] = Ydot[k] - Cu * lu;
+                out[k + 1] = Ydot[k + 1] - Cv * lv;
+            }
+        memcpy(F, out.data(), sizeof(double) * out.size());
+    }
+    // pattern.c:185-199  FormRHSFunctionLocal
+    void pattern_rhsfunction(int m, const PO &o, const double *Y, double *G) {
+        for (int k = 0; k < m * m; k++) {
+            const double u = Y[2 * k], v = Y[2 * k + 1], uv2 = u * v * v;
+            G[2 * k] = -uv2 + o.phi * (1.0 - u);
+            G[2 * k + 1] = uv2 - (o.phi + o.kappa) * v;
+        }
+    }
+    // J X = shift X - C L9 X - G'(Y) X   (pattern.c:274-318 minus :202-236; Y == nullptr drops G')
+    void jac_rows(int m, const PO &o, double shift, const double *Y, const double *X, int i, int j, double *Ju, double *Jv, double *du,
+                  double *dv, double *g01, double *g10) const {
+        const double h = o.L / m, Cu = o.Du / (6.0 * h * h), Cv = o.Dv / (6.0 * h * h);
+        const int k = 2 * (j * m + i);
+        double a00 = 0, a01 = 0, a10 = 0, a11 = 0;
+        if (Y) {
+            const double u = Y[k], v = Y[k + 1];
+            a00 = -v * v - o.phi; a01 = -2.0 * u * v; a10 = v * v; a11 = 2.0 * u * v - (o.phi + o.kappa);
+        }
+        *du = shift + 20.0 * Cu - a00;
+        *dv = shift + 20.0 * Cv - a11;
+        *g01 = a01;
+        *g10 = a10;
+        if (X) {
+            double lu, lv;
+            lap9(m, X, i, j, &lu, &lv);
+            *Ju = shift * X[k] - Cu * lu - (a00 * X[k] + a01 * X[k + 1]);
+            *Jv = shift * X[k + 1] - Cv * lv - (a10 * X[k] + a11 * X[k + 1]);
+        }
+    }
+    void pattern_jac_apply(int m, const PO &o, double shift, const double *Y, const double *X, double *out) {
+        std::vector<double> r((size_t)2 * m * m);
+        for (int j = 0; j < m; j++)
+            for (int i = 0; i < m; i++) {
+                double du, dv, g01, g10;
+                jac_rows(m, o, shift, Y, X, i, j, &r[2 * (j * m + i)], &r[2 * (j * m + i) + 1], &du, &dv, &g01, &g10);
+            }
+        memcpy(out, r.data(), sizeof(double) * r.size());
+    }
+    void pattern_jac_lin(int m, const PO &o, double shift, const double *Y, const double *X, const double *b, const double *pm1,
+                         double ca, double cb, double cg, int jacobi, double *out) {
+        std::vector<double> r((size_t)2 * m * m);
+        for (int j = 0; j < m; j++)
+            for (int i = 0; i < m; i++) {
+                const int k = 2 * (j * m + i);
+                double Ju = 0.0, Jv = 0.0, du, dv, g01, g10;
+                jac_rows(m, o, shift, Y, X, i, j, &Ju, &Jv, &du, &dv, &g01, &g10);
+                double ru = (b ? b[k] : 0.0) - Ju, rv = (b ? b[k + 1] : 0.0) - Jv;
+                if (jacobi) { ru /= du; rv /= dv; }
+                r[k] = cb * X[k] + cg * ru + (pm1 ? ca * pm1[k] : 0.0);
+                r[k + 1] = cb * X[k + 1] + cg * rv + (pm1 ? ca * pm1[k + 1] : 0.0);
+            }
+        memcpy(out, r.data(), sizeof(double) * r.size());
+    }
+    double pattern_jac_gershgorin(int m, const PO &o, double shift, const double *Y, double *) {
+        const double h = o.L / m, Cu = o.Du / (6.0 * h * h), Cv = o.Dv / (6.0 * h * h);
+        double best = 0.0;
+        for (int j = 0; j < m; j++)
+            for (int i = 0; i < m; i++) {
+                double Ju = 0.0, Jv = 0.0, du, dv, g01, g10;
+                jac_rows(m, o, shift, Y, nullptr, i, j, &Ju, &Jv, &du, &dv, &g01, &g10);
+                best = std::max(best, (fabs(du) + 20.0 * Cu + fabs(g01)) / fabs(du));
+                best = std::max(best, (fabs(dv) + 20.0 * Cv + fabs(g10)) / fabs(dv));
+            }
+        return best;
+    }
+    // [PETSc] periodic DMDA Q1 interpolation (ratio 2), its transpose, injection; (u, v) interleaved
+    void pattern_restrict(int Mx, int My, const double *rf, double *bc) {
+        const int fx = 2 * Mx, fy = 2 * My;
+        for (int J = 0; J < My; J++)
+            for (int I = 0; I < Mx; I++)
+                for (int c = 0; c < 2; c++) {
+                    double s = 0.0;
+                    for (int dj = -1; dj <= 1; dj++)
+                        for (int di = -1; di <= 1; di++)
+                            s += (di ? 0.5 : 1.0) * (dj ? 0.5 : 1.0) * rf[2 * (((2 * J + dj + fy) % fy) * fx + (2 * I + di + fx) % fx) + c];
+                    bc[2 * (J * Mx + I) + c] = s;
+                }
+    }
+    void pattern_prolong_add(int Mx, int My, const double *xc, double *xf) {
+        const int fx = 2 * Mx, fy = 2 * My;
+        for (int j = 0; j < fy; j++)
+            for (int i = 0; i < fx; i++)
+                for (int c = 0; c < 2; c++) {
+                    const int I0 = i / 2, J0 = j / 2, I1 = (i & 1) ? (I0 + 1) % Mx : I0, J1 = (j & 1) ? (J0 + 1) % My : J0;
+                    xf[2 * (j * fx + i) + c] += 0.25 * ((xc[2 * (J0 * Mx + I0) + c] + xc[2 * (J0 * Mx + I1) + c]) +
+                                                        (xc[2 * (J1 * Mx + I0) + c] + xc[2 * (J1 * Mx + I1) + c]));
+                }
+    }
+    void pattern_inject(int Mx, int My, const double *yf, double *yc) {
+        const int fx = 2 * Mx;
+        for (int J = 0; J < My; J++)
+            for (int I = 0; I < Mx; I++)
+                for (int c = 0; c < 2; c++) yc[2 * (J * Mx + I) + c] = yf[2 * ((2 * J) * fx + 2 * I) + c];
+    }
+
     void dense_matvec(int n, const double *Ainv, const double *b, double *x) {
         std::vector<double> o(n);
         for (int r = 0; r < n; r++) {

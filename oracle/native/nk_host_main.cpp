@@ -8,13 +8,58 @@
 
 #include <string>
 
-#include "host_ops.hpp"
 #include "nk_solver.hpp"
+#include "ts_solver.hpp"
+#include "host_ops.hpp"
 
 static void print_line(const char *s, void *) { printf("%s\n", s); }
 
+// nk_host_test -pattern [-da_grid_x n] [-da_grid_y n] [-da_refine r] [-ts_type arkimex|beuler|cn] [-ts_dt h] [-ts_max_time T]
+//              [-pc_type mg|none] [-snes_rtol r] [-ptn_no_rhsjacobian] [-ptn_call_back_report] [-p4b_mg_rscale s]
+//              [-ts_monitor] [-snes_converged_reason] [-ksp_converged_reason]
+static int pattern_main(int argc, char **argv) {
+    using namespace p4b::nk;
+    PatternOpts o;
+    default_opts(&o);
+    for (int i = 2; i < argc; i++) {
+        const std::string a = argv[i];
+        auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
+        if (a == "-da_grid_x") o.grid_x = atoi(next());
+        else if (a == "-da_grid_y") o.grid_y = atoi(next());
+        else if (a == "-da_refine") o.refine = atoi(next());
+        else if (a == "-ts_type") { const std::string v = next(); o.ts_type = v == "beuler" ? TS_BEULER : (v == "cn" ? TS_CN : TS_ARKIMEX); }
+        else if (a == "-ts_dt") o.ts_dt = atof(next());
+        else if (a == "-ts_max_time") o.ts_max_time = atof(next());
+        else if (a == "-pc_type") o.pc_type = std::string(next()) == "mg" ? PC_MG : PC_NONE;
+        else if (a == "-snes_rtol") o.snes_rtol = atof(next());
+        else if (a == "-p4b_mg_rscale") o.mg_rscale = atof(next());
+        else if (a == "-ptn_no_rhsjacobian") o.no_rhsjacobian = 1;
+        else if (a == "-ptn_call_back_report") o.call_back_report = 1;
+        else if (a == "-ts_monitor") o.ts_monitor = 1;
+        else if (a == "-snes_converged_reason") o.snes_converged_reason = 1;
+        else if (a == "-ksp_converged_reason") o.ksp_converged_reason = 1;
+        else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
+    }
+    HostOps ops;
+    PatternResult R;
+    double *Y = nullptr;
+    Printer pr{print_line, nullptr};
+    const int rc = pattern_solve(&ops, o, pr, &Y, &R);
+    if (rc) { fprintf(stderr, "pattern_solve failed: %d\n", rc); return 1; }
+    double sum = 0.0, vmax = 0.0;
+    for (int k = 0; k < R.m * R.m; k++) { sum += Y[2 * k] + 3.0 * Y[2 * k + 1]; vmax = std::max(vmax, Y[2 * k + 1]); }
+    printf("{\"m\": %d, \"nsteps\": %d, \"rejected\": %d, \"ksp_its_total\": %lld, \"newton_its_total\": %lld, \"t_final\": %.17g, "
+           "\"sum\": %.17g, \"vmax\": %.17g, \"allocs\": %lld, \"frees\": %lld, \"step_newton\": [",
+           R.m, R.nsteps, R.rejected, R.ksp_its_total, R.newton_its_total, R.t_final, sum, vmax, ops.allocs, ops.frees + 1);
+    for (int k = 0; k < R.nsteps && k < MAX_TS_STEPS_KEPT; k++) printf("%s%d", k ? ", " : "", R.step_newton[k]);
+    printf("]}\n");
+    ops.release(Y);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     using namespace p4b::nk;
+    if (argc > 1 && std::string(argv[1]) == "-pattern") return pattern_main(argc, argv);
     MinimalOpts o;
     default_opts(&o);
     for (int i = 1; i < argc; i++) {

@@ -16,7 +16,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libp4b200.so")
 SOURCES = ["mg.cu", "stencil.cu", "stencil_fast.cu", "transfer.cu", "vecops.cu", "fishfn.cu", "comm.cu", "mp_kernels.cu", "assembled.cu", "nk_device.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "comm.h"),
-           os.path.join(CSRC, "nk_solver.hpp"),
+           os.path.join(CSRC, "nk_solver.hpp"), os.path.join(CSRC, "ts_solver.hpp"),
            os.path.join(ROOT, "include", "p4b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", CSRC]

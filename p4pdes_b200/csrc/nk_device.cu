@@ -9,6 +9,7 @@
 
 #include "kernels.h"
 #include "nk_solver.hpp"
+#include "ts_solver.hpp"
 
 namespace p4b {
 
@@ -72,6 +73,33 @@ struct DeviceOps {
     void prolong_add2d(int fmx, int fmy, const double *xc, double *xf) { p4b_grid g = grid2d(fmx, fmy); chk(p4b_prolong_add(c, &g, xc, xf)); }
     void initial_state2d(int mx, int my, const double *g, double *u) { p4b_grid gr = grid2d(mx, my); chk(p4b_initial_state(c, &gr, g, 1, u)); }
     void dense_matvec(int n, const double *Ainv, const double *b, double *x) { chk(p4b_dense_matvec(c, n, Ainv, b, x)); }
+    // pattern.c
+    typedef nk::PatternOpts PO;
+    double wrms2(size_t n, const double *x, const double *y, double atol, double rtol) {
+        double r = NAN;
+        chk(p4b_vec_wrms2(c, n, x, y, atol, rtol, &r));
+        return r;
+    }
+    void pattern_initial_state(int mx, int my, double L, double *Y) { chk(p4b_pattern_initial_state(c, mx, my, L, Y)); }
+    void pattern_ifunction(int m, const PO &o, const double *Y, const double *Ydot, double *F) {
+        chk(p4b_pattern_ifunction(c, m, m, o.L, o.Du, o.Dv, Y, Ydot, F));
+    }
+    void pattern_rhsfunction(int m, const PO &o, const double *Y, double *G) { chk(p4b_pattern_rhsfunction(c, m, m, o.phi, o.kappa, Y, G)); }
+    void pattern_jac_apply(int m, const PO &o, double shift, const double *Y, const double *X, double *out) {
+        chk(p4b_pattern_jac_apply(c, m, m, o.L, o.Du, o.Dv, o.phi, o.kappa, shift, Y, X, out));
+    }
+    void pattern_jac_lin(int m, const PO &o, double shift, const double *Y, const double *X, const double *b, const double *pm1,
+                         double ca, double cb, double cg, int jacobi, double *out) {
+        chk(p4b_pattern_jac_lin(c, m, m, o.L, o.Du, o.Dv, o.phi, o.kappa, shift, Y, X, b, pm1, ca, cb, cg, jacobi, out));
+    }
+    double pattern_jac_gershgorin(int m, const PO &o, double shift, const double *Y, double *work) {
+        double r = NAN;
+        chk(p4b_pattern_jac_gershgorin(c, m, m, o.L, o.Du, o.Dv, o.phi, o.kappa, shift, Y, work, &r));
+        return r;
+    }
+    void pattern_restrict(int Mx, int My, const double *rf, double *bc) { chk(p4b_pattern_restrict(c, Mx, My, rf, bc)); }
+    void pattern_prolong_add(int Mx, int My, const double *xc, double *xf) { chk(p4b_pattern_prolong_add(c, Mx, My, xc, xf)); }
+    void pattern_inject(int Mx, int My, const double *yf, double *yc) { chk(p4b_pattern_inject(c, Mx, My, yf, yc)); }
 };
 
 }  // namespace p4b
@@ -113,5 +141,41 @@ extern "C" int p4b_minimal_solve(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_l
     if (rc == 62) return fail(62, "base-grid Jacobian is singular");
     if (rc == 63) return fail(63, "u_out holds %zu doubles, the final grid needs %d x %d", u_capacity, R.mx, R.my);
     if (rc) return fail(rc, "p4b_minimal_solve failed (%s)", p4b_last_error());
+    return 0;
+}
+
+extern "C" int p4b_pattern_default_opts(p4b_pattern_opts *o) {
+    if (!o) return fail(62, "null options");
+    static_assert(sizeof(p4b_pattern_opts) == sizeof(nk::PatternOpts), "p4b_pattern_opts and nk::PatternOpts must agree");
+    nk::default_opts(reinterpret_cast<nk::PatternOpts *>(o));
+    return 0;
+}
+
+extern "C" int p4b_pattern_solve(p4b_ctx *c, const p4b_pattern_opts *opts, p4b_line_fn line, void *line_ctx, double *Y_out,
+                                 size_t Y_capacity, p4b_pattern_result *result) {
+    static_assert(sizeof(p4b_pattern_result) == sizeof(nk::PatternResult), "p4b_pattern_result and nk::PatternResult must agree");
+    if (!c || !opts || !result) return fail(62, "p4b_pattern_solve: null argument");
+    const nk::PatternOpts &o = *reinterpret_cast<const nk::PatternOpts *>(opts);
+    if (o.grid_x < 3 || o.grid_y < 3) return fail(60, "periodic grid needs at least 3 nodes per dimension");
+    if ((o.grid_x << o.refine) != (o.grid_y << o.refine)) return fail(1, "pattern.c requires mx == my");            // pattern.c:89
+    if (o.ts_type < nk::TS_ARKIMEX || o.ts_type > nk::TS_CN) return fail(62, "ts_type: arkimex (0), beuler (1), cn (2)");
+    DeviceOps ops{c, ctx_stream(c)};
+    nk::Printer pr{line, line_ctx};
+    double *Y = nullptr;
+    nk::PatternResult &R = *reinterpret_cast<nk::PatternResult *>(result);
+    int rc = nk::pattern_solve(&ops, o, pr, Y_out ? &Y : nullptr, &R);
+    if (!rc && ops.error()) rc = ops.error();
+    if (!rc && Y_out) {
+        const size_t n = (size_t)2 * R.m * R.m;
+        if (Y_capacity < n) rc = 63;
+        else if (cudaMemcpyAsync(Y_out, Y, sizeof(double) * n, cudaMemcpyDeviceToDevice, ops.st) != cudaSuccess) rc = 70;
+    }
+    if (Y) cudaFreeAsync(Y, ops.st);
+    cudaStreamSynchronize(ops.st);
+    if (rc == 61) return fail(61, "base grid of the periodic hierarchy has more than 512 unknowns: use a coarser -da_grid_x/_y");
+    if (rc == 62) return fail(62, "base-grid stage Jacobian is singular");
+    if (rc == 63) return fail(63, "Y_out holds %zu doubles, the grid needs 2 x %d x %d", Y_capacity, R.m, R.m);
+    if (rc == 64) return fail(64, "TSSolve: a nonlinear (stage) solve did not converge");
+    if (rc) return fail(rc, "p4b_pattern_solve failed (%s)", p4b_last_error());
     return 0;
 }

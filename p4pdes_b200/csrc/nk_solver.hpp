@@ -300,12 +300,12 @@ struct Precond {
 struct KSPInfo { int its; bool converged; };
 
 // [PETSc] KSPGMRES: left-preconditioned, restarted, x0 = 0, convergence on the preconditioned residual norm
-template <class Ops>
-KSPInfo gmres(Ops *ops, Level<Ops> &A, const double *b, double *x, Precond<Ops> &M, double rtol, double abstol, int restart,
+// (mult(in, out): out = A in;  prec(r, z): z = M^-1 r)
+template <class Ops, class Mult, class Prec>
+KSPInfo gmres(Ops *ops, size_t n, Mult mult, const double *b, double *x, Prec prec, double rtol, double abstol, int restart,
               int max_it, std::vector<double *> &V, double *w, double *t) {
-    const size_t n = A.n;
     ops->set(n, 0.0, x);
-    M.apply(b, V[0]);
+    prec(b, V[0]);
     double beta = ops->norm2(n, V[0]);
     const double ttol = std::max(rtol * beta, abstol);
     int its = 0;
@@ -319,8 +319,8 @@ KSPInfo gmres(Ops *ops, Level<Ops> &A, const double *b, double *x, Precond<Ops> 
         ops->axpby(n, 1.0 / beta, V[0], 0.0, nullptr, V[0]);
         int k = 0;
         while (k < restart && its < max_it) {
-            A.mult(V[k], t);
-            M.apply(t, w);
+            mult(V[k], t);
+            prec(t, w);
             for (int i = 0; i <= k; i++) {                     // modified Gram-Schmidt
                 h(i, k) = ops->dot(n, w, V[i]);
                 ops->axpy(n, -h(i, k), V[i], w);
@@ -351,33 +351,32 @@ KSPInfo gmres(Ops *ops, Level<Ops> &A, const double *b, double *x, Precond<Ops> 
         }
         for (int i = 0; i < k; i++) ops->axpy(n, y[i], V[i], x);
         if (beta <= ttol) break;
-        A.mult(x, t);                                          // restart: r = M^-1 (b - A x)
+        mult(x, t);                                            // restart: r = M^-1 (b - A x)
         ops->axpby(n, 1.0, b, -1.0, t, t);
-        M.apply(t, V[0]);
+        prec(t, V[0]);
         beta = ops->norm2(n, V[0]);
     }
     return {its, beta <= ttol};
 }
 
 // [PETSc] KSPCG, preconditioned norm
-template <class Ops>
-KSPInfo cg(Ops *ops, Level<Ops> &A, const double *b, double *x, Precond<Ops> &M, double rtol, double abstol, int max_it,
+template <class Ops, class Mult, class Prec>
+KSPInfo cg(Ops *ops, size_t n, Mult mult, const double *b, double *x, Prec prec, double rtol, double abstol, int max_it,
            double *r, double *z, double *p, double *w) {
-    const size_t n = A.n;
     ops->set(n, 0.0, x);
     ops->copy(n, b, r);
-    M.apply(r, z);
+    prec(r, z);
     double beta = ops->dot(n, z, r), dp = ops->norm2(n, z), beta_old = 0.0;
     const double ttol = std::max(rtol * dp, abstol);
     int its = 0;
     while (dp > ttol && its < max_it) {
         if (its == 0) ops->copy(n, z, p);
         else ops->aypx(n, beta / beta_old, z, p);
-        A.mult(p, w);
+        mult(p, w);
         const double a = beta / ops->dot(n, p, w);
         ops->axpy(n, a, p, x);
         ops->axpy(n, -a, w, r);
-        M.apply(r, z);
+        prec(r, z);
         beta_old = beta;
         beta = ops->dot(n, z, r);
         dp = ops->norm2(n, z);
@@ -494,8 +493,10 @@ int newton(Ops *ops, std::vector<Level<Ops>> &lev, const MinimalOpts &opt, const
             }
         }
         KSPInfo k;
-        if (opt.ksp_type == KSP_GMRES) k = gmres(ops, L, L.F, y, M, opt.ksp_rtol, 1.0e-50, opt.gmres_restart, opt.ksp_max_it, V, w, t);
-        else k = cg(ops, L, L.F, y, M, opt.ksp_rtol, 1.0e-50, opt.ksp_max_it, kr, kz, kp, w);
+        auto mult = [&](const double *in, double *out) { L.mult(in, out); };
+        auto prec = [&](const double *r, double *z) { M.apply(r, z); };
+        if (opt.ksp_type == KSP_GMRES) k = gmres(ops, n, mult, L.F, y, prec, opt.ksp_rtol, 1.0e-50, opt.gmres_restart, opt.ksp_max_it, V, w, t);
+        else k = cg(ops, n, mult, L.F, y, prec, opt.ksp_rtol, 1.0e-50, opt.ksp_max_it, kr, kz, kp, w);
         res->ksp_its[it] = k.its;
         if (opt.ksp_converged_reason)
             pr.out("%s  Linear solve %s due to %s iterations %d", pad.c_str(), k.converged ? "converged" : "did not converge",

@@ -76,6 +76,25 @@ class MinimalResult(C.Structure):
                 ("errinf", C.c_double), ("error", C.c_int), ("errmsg", C.c_char * 256)]
 
 
+class PatternOpts(C.Structure):
+    """p4b_pattern_opts (include/p4b200.h)."""
+    _fields_ = [("L", C.c_double), ("Du", C.c_double), ("Dv", C.c_double), ("phi", C.c_double), ("kappa", C.c_double),
+                ("no_rhsjacobian", C.c_int), ("call_back_report", C.c_int), ("grid_x", C.c_int), ("grid_y", C.c_int),
+                ("refine", C.c_int), ("ts_type", C.c_int), ("ts_dt", C.c_double), ("ts_max_time", C.c_double),
+                ("ts_max_steps", C.c_int), ("ts_rtol", C.c_double), ("ts_atol", C.c_double), ("ts_monitor", C.c_int),
+                ("pc_type", C.c_int), ("smooth_its", C.c_int), ("mg_rscale", C.c_double), ("snes_rtol", C.c_double),
+                ("snes_stol", C.c_double), ("snes_atol", C.c_double), ("snes_max_it", C.c_int), ("ksp_rtol", C.c_double),
+                ("ksp_max_it", C.c_int), ("gmres_restart", C.c_int), ("snes_converged_reason", C.c_int),
+                ("ksp_converged_reason", C.c_int)]
+
+
+class PatternResult(C.Structure):
+    _fields_ = [("m", C.c_int), ("nsteps", C.c_int), ("rejected", C.c_int), ("ksp_its_total", C.c_longlong),
+                ("newton_its_total", C.c_longlong), ("t_final", C.c_double), ("dt_last", C.c_double),
+                ("step_t", C.c_double * 512), ("step_dt", C.c_double * 512), ("step_newton", C.c_int * 512),
+                ("error", C.c_int)]
+
+
 LINE_FN = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)
 
 
@@ -165,6 +184,8 @@ _SIGS = {
     "p4b_pattern_inject": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
     "p4b_minimal_default_opts": (C.c_int, [C.POINTER(MinimalOpts)]),
     "p4b_minimal_solve": (C.c_int, [_P, C.POINTER(MinimalOpts), LINE_FN, _P, _D, C.c_size_t, C.POINTER(MinimalResult)]),
+    "p4b_pattern_default_opts": (C.c_int, [C.POINTER(PatternOpts)]),
+    "p4b_pattern_solve": (C.c_int, [_P, C.POINTER(PatternOpts), LINE_FN, _P, _D, C.c_size_t, C.POINTER(PatternResult)]),
     "p4b_sell_create": (C.c_int, [_P, C.c_int, _P, _P, _P, C.POINTER(_P)]),
     "p4b_sell_spmv": (C.c_int, [_P, _D, _D]),
     "p4b_sell_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

@@ -250,7 +250,41 @@ class PatternReport:
     lines: list
 
 
-def pattern_main(argv, ops, echo=False) -> PatternReport:
+def _pattern_native(opt: PatternOptions, ctx, out) -> PatternReport:
+    """The same run through ONE C-ABI call, p4b_pattern_solve (csrc/nk_device.cu + ts_solver.hpp)."""
+    import ctypes as C
+
+    from . import lib as L
+    o = L.PatternOpts()
+    L.check(ctx.lib.p4b_pattern_default_opts(C.byref(o)))
+    o.L, o.Du, o.Dv, o.phi, o.kappa = opt.L, opt.Du, opt.Dv, opt.phi, opt.kappa
+    o.no_rhsjacobian, o.call_back_report = int(opt.no_rhsjacobian), int(opt.call_back_report)
+    o.grid_x, o.grid_y, o.refine = opt.grid_x, opt.grid_y, opt.refine
+    o.ts_type = {"arkimex": 0, "beuler": 1, "cn": 2}[opt.ts_type]
+    o.ts_dt, o.ts_max_time, o.ts_max_steps = opt.ts_dt, opt.ts_max_time, opt.ts_max_steps
+    o.ts_rtol, o.ts_atol, o.ts_monitor = opt.ts_rtol, opt.ts_atol, int(opt.ts_monitor)
+    o.pc_type, o.smooth_its, o.mg_rscale = {"none": 0, "mg": 1}[opt.pc_type], opt.smooth_its, opt.mg_rscale
+    o.snes_rtol, o.snes_stol, o.snes_atol, o.snes_max_it = opt.snes_rtol, opt.snes_stol, opt.snes_atol, opt.snes_max_it
+    o.ksp_rtol, o.ksp_max_it, o.gmres_restart = opt.ksp_rtol, opt.ksp_max_it, opt.gmres_restart
+    o.snes_converged_reason, o.ksp_converged_reason = int(opt.snes_converged_reason), int(opt.ksp_converged_reason)
+    m = opt.grid_x * 2 ** opt.refine
+    Y = ctx.empty(2 * m * m)
+    res = L.PatternResult()
+    cb = L.LINE_FN(lambda line, _ctx: out(line.decode()))
+    t0 = time.perf_counter()
+    L.check(ctx.lib.p4b_pattern_solve(ctx.h, C.byref(o), cb, None, Y.data_ptr(), Y.numel(), C.byref(res)))
+    seconds = time.perf_counter() - t0
+    steps = [(res.step_t[k], res.step_dt[k], res.step_newton[k]) for k in range(min(res.nsteps, 512))]
+    if opt.log_view:
+        out("TSSolve %.6f s (%d steps, %d rejected, %d GMRES iterations)" % (seconds, res.nsteps, res.rejected,
+                                                                           res.ksp_its_total))
+    rep = PatternReport(m=res.m, steps=steps, Y=Y, seconds=seconds, lines=None)
+    rep.rejected = res.rejected
+    return rep
+
+
+def pattern_main(argv, ops, echo=False, native=False) -> PatternReport:
+    """native=True: the whole run is one call of p4b_pattern_solve (host logic in C++ inside the library)."""
     opt = parse_options(argv)
     lines = []
 
@@ -258,6 +292,11 @@ def pattern_main(argv, ops, echo=False) -> PatternReport:
         lines.append(s)
         if echo:
             print(s)
+
+    if native:
+        rep = _pattern_native(opt, ops, out)
+        rep.lines = lines
+        return rep
 
     mx, my = opt.grid_x * 2 ** opt.refine, opt.grid_y * 2 ** opt.refine     # periodic: -da_refine doubles
     if mx != my:

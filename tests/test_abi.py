@@ -118,3 +118,24 @@ def test_minimal_solve_structs_match_the_header(lib, tmp_path):
     got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     assert got == [C.sizeof(L.MinimalOpts), C.sizeof(L.MinimalStage), C.sizeof(L.MinimalResult),
                    L.MinimalResult.errinf.offset, L.MinimalStage.fnorm.offset]
+
+
+def test_pattern_solve_structs_match_the_header(lib, tmp_path):
+    import subprocess
+    o = L.PatternOpts()
+    assert lib.p4b_pattern_default_opts(C.byref(o)) == 0
+    assert (o.L, o.Du, o.Dv, o.phi, o.kappa) == (2.5, 8.0e-5, 4.0e-5, 0.024, 0.06)                  # pattern.c:47-52
+    assert (o.no_rhsjacobian, o.call_back_report, o.grid_x, o.grid_y, o.refine) == (0, 0, 3, 3, 0)
+    assert (o.ts_type, o.ts_dt, o.ts_max_time, o.ts_max_steps) == (0, 5.0, 200.0, 5000)            # pattern.c:115-117
+    assert (o.ts_rtol, o.ts_atol, o.ts_monitor, o.pc_type, o.smooth_its, o.mg_rscale) == (1e-4, 1e-4, 0, 1, 2, 1.0)
+    assert (o.snes_rtol, o.snes_stol, o.snes_atol, o.snes_max_it) == (1e-8, 1e-8, 1e-50, 50)
+    assert (o.ksp_rtol, o.ksp_max_it, o.gmres_restart, o.snes_converged_reason, o.ksp_converged_reason) == (1e-5, 10000, 30, 0, 0)
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "p4b200.h"\nint main(void){printf("%zu %zu %zu %zu\\n",'
+                   'sizeof(p4b_pattern_opts),sizeof(p4b_pattern_result),offsetof(p4b_pattern_result,step_newton),'
+                   'offsetof(p4b_pattern_result,error));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    assert got == [C.sizeof(L.PatternOpts), C.sizeof(L.PatternResult), L.PatternResult.step_newton.offset,
+                   L.PatternResult.error.offset]

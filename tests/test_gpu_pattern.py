@@ -135,3 +135,23 @@ def test_arkimex_goldens_on_device(ctx, argv, golden):
 
 def test_golden_pattern_test3_crank_nicolson_on_device(ctx):
     assert pp.pattern_main(TEST3, ctx).lines == GOLDEN_TEST3                 # c/ch5/output/pattern.test3
+
+
+@pytest.mark.parametrize("argv,golden", [(TEST1, GOLDEN_TEST1), (TEST2, GOLDEN_TEST2), (TEST3, GOLDEN_TEST3),
+                                         (TEST4, GOLDEN_TEST4)])
+def test_native_time_stepper_on_device(ctx, argv, golden):
+    """p4b_pattern_solve (host logic in C++ inside the library, csrc/ts_solver.hpp; CPU-checked against the same goldens
+    in tests/test_native_nk_cpu.py) on the device: step sizes as numbers, everything else verbatim."""
+    r = pp.pattern_main(argv, ctx, native=True)
+    assert len(r.lines) == len(golden)
+    np.testing.assert_allclose(_ts_numbers(r.lines), _ts_numbers(golden), rtol=3e-6)
+    assert [l for l in r.lines if " TS " not in l] == [l for l in golden if " TS " not in l]
+
+
+def test_native_time_stepper_equals_the_python_host(ctx):
+    argv = "-da_grid_x 4 -da_grid_y 4 -da_refine 5 -ts_type beuler -ts_dt 5 -ts_max_time 10 -pc_type mg -p4b_mg_rscale 0.25"
+    a = pp.pattern_main(argv, ctx)
+    b = pp.pattern_main(argv, ctx, native=True)
+    assert [(t, dt) for t, dt, _ in a.steps] == [(t, dt) for t, dt, _ in b.steps]
+    assert [s[2].its for s in a.steps] == [s[2] for s in b.steps]
+    assert float((a.Y - b.Y).abs().max()) <= 1e-10

@@ -82,3 +82,33 @@ def test_banded_inverse_agrees_with_lapack(exe):
     o = mo.minimal(mx=17, my=17, grid_sequence=1, pc="mg", problem="tent")
     assert [s["ksp_its"] for s in d["stages"]] == [s.ksp_its for s in o.stages]
     assert abs(d["sum"] - float(o.u.sum())) <= 1e-9 * abs(float(o.u.sum()))
+
+
+# ---- pattern.c: the native time-stepping host (csrc/ts_solver.hpp) against the reference's goldens --------------------
+from tests.test_pattern_cpu import (GOLDEN_TEST1, GOLDEN_TEST2, GOLDEN_TEST3, GOLDEN_TEST4, TEST1, TEST2, TEST3,  # noqa: E402
+                                    TEST4)
+
+
+@pytest.mark.parametrize("argv,golden", [(TEST1, GOLDEN_TEST1), (TEST2, GOLDEN_TEST2), (TEST3, GOLDEN_TEST3),
+                                         (TEST4, GOLDEN_TEST4)])
+def test_native_time_stepper_prints_the_pattern_goldens_verbatim(exe, argv, golden):
+    """c/ch5/output/pattern.test1-4: adaptive ARKIMEX3 (incl. the rejected step), backward Euler, Crank-Nicolson."""
+    lines, d = run(exe, "-pattern", *argv.split())
+    assert lines == golden
+    assert d["allocs"] == d["frees"]
+
+
+def test_native_time_stepper_matches_python_oracle(exe):
+    from oracle import pattern_solver_oracle as po
+    _, d = run(exe, "-pattern", "-da_grid_x", 4, "-da_grid_y", 4, "-da_refine", 3, "-ts_type", "beuler", "-ts_dt", 5,
+               "-ts_max_time", 12, "-pc_type", "mg")
+    o = po.pattern_beuler(grid=4, refine=3, dt=5.0, tmax=12.0)
+    assert d["nsteps"] == len(o.steps) and d["step_newton"] == [s[2].its for s in o.steps]
+    assert d["ksp_its_total"] == sum(sum(s[2].ksp_its) for s in o.steps)
+    want = float(np.sum(o.Y[..., 0] + 3.0 * o.Y[..., 1]))
+    assert abs(d["sum"] - want) <= 1e-10 * abs(want)
+    _, d = run(exe, "-pattern", "-da_grid_x", 4, "-da_grid_y", 4, "-da_refine", 2, "-ts_max_time", 60)
+    o = po.pattern_arkimex(grid=4, refine=2, tmax=60.0)
+    assert d["nsteps"] == len(o.steps) and d["rejected"] == o.rejected
+    want = float(np.sum(o.Y[..., 0] + 3.0 * o.Y[..., 1]))
+    assert abs(d["sum"] - want) <= 1e-7 * abs(want)           # stage solves: Newton rtol 1e-8 vs the oracle's direct solves
