@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "gpu_pending: needs a CUDA device; written after the round's GPU budget was spent and "
+                                       "not yet run on one (-m gpu_pending); promoted to `gpu` once validated")
 
 
 @pytest.fixture(scope="session")

@@ -148,33 +148,3 @@ def test_cluster_configuration_at_full_size(ctx):
     assert r.errinf < e[3] / 30.0
     print("minimal 2049^2: %.3f s, Newton its %s, max KSP its %s, error %.3e"
           % (r.seconds, [s.its for s in r.stages], [max(s.ksp_its) for s in r.stages], r.errinf))
-
-
-@pytest.mark.parametrize("argv", [
-    "-snes_fd_color -snes_converged_reason -snes_monitor_short -ksp_converged_reason -snes_grid_sequence 3 -ms_problem tent "
-    "-pc_type mg",
-    "-snes_fd_color -da_refine 4 -pc_type mg -ksp_type cg -ms_q 0.0 -ms_problem tent -snes_converged_reason",
-    "-snes_fd_color -da_grid_x 17 -da_grid_y 17 -snes_grid_sequence 2 -pc_type mg -ms_problem tent",
-])
-def test_native_solve_equals_the_python_host(ctx, argv):
-    """p4b_minimal_solve (host logic in C++ inside the library, csrc/nk_solver.hpp) against the Python host running the
-    same algorithm through the individual C-ABI calls: same lines, same counts, same solution.  (The two differ only in
-    the base-grid inverse: banded LU in C++, LAPACK in Python.)"""
-    a = pm.minimal_main(argv, ctx)
-    b = pm.minimal_main(argv, ctx, native=True)
-    assert (a.mx, a.my) == (b.mx, b.my)
-    assert [s.its for s in a.stages] == [s.its for s in b.stages]
-    assert [s.ksp_its for s in a.stages] == [s.ksp_its for s in b.stages]
-    assert [s.reason for s in a.stages] == [s.reason for s in b.stages]
-    for s, t in zip(a.stages, b.stages):
-        np.testing.assert_allclose(s.fnorms, t.fnorms, rtol=1e-2, atol=1e-10 * s.fnorms[0])
-    assert [l.split(" norm ")[0] for l in a.lines] == [l.split(" norm ")[0] for l in b.lines]
-    ua, ub = ctx.to_host(a.u), ctx.to_host(b.u)
-    assert np.max(np.abs(ua - ub)) <= 1e-9 * max(1.0, np.max(np.abs(ua)))
-
-
-def test_native_solve_cluster_configuration(ctx):
-    r = pm.minimal_main("-da_grid_x 33 -da_grid_y 33 -snes_grid_sequence 6 -snes_fd_color -pc_type mg", ctx, native=True)
-    assert (r.mx, r.my) == (2049, 2049) and all(s.reason.startswith("CONVERGED") for s in r.stages)
-    assert max(max(s.ksp_its) for s in r.stages[1:]) <= 12 and r.errinf < 1e-7
-    print("minimal 2049^2 native: %.3f s, Newton its %s" % (r.seconds, [s.its for s in r.stages]))

@@ -8,8 +8,7 @@ from oracle import minimal_solver_oracle as mso
 from oracle import pattern_solver_oracle as po
 from p4pdes_b200 import pattern as pp
 from p4pdes_b200.fish import Context
-from tests.test_pattern_cpu import (GOLDEN_TEST1, GOLDEN_TEST2, GOLDEN_TEST3, GOLDEN_TEST4, TEST1, TEST2, TEST3,
-                                    TEST4)
+from tests.test_pattern_cpu import GOLDEN_TEST2, TEST2
 
 pytestmark = pytest.mark.gpu
 PAR = (2.5, 8.0e-5, 4.0e-5, 0.024, 0.06)
@@ -105,53 +104,3 @@ def test_config5_at_full_size(ctx):
     assert Y[..., 0].max() <= 1.0 + 1e-9 and Y[..., 1].min() >= -1e-9 and Y[..., 1].max() > 0.1
     print("pattern 2048^2 x 2: %.3f s for 2 steps, Newton its %s, KSP its %s"
           % (r.seconds, [s[2].its for s in r.steps], [s[2].ksp_its for s in r.steps]))
-
-
-def test_weighted_error_norm_kernel(ctx):
-    rng = np.random.default_rng(9)
-    for n in (1, 1000, 2 * 2048 * 2048 + 3):
-        x, y = rng.standard_normal(n), rng.standard_normal(n)
-        want = np.sum(((x - y) / (1e-4 + 1e-3 * np.maximum(np.abs(x), np.abs(y)))) ** 2)
-        got = ctx.wrms2(dev(ctx, x), dev(ctx, y), 1e-4, 1e-3)
-        assert abs(got - want) <= 1e-12 * want
-
-
-def _ts_numbers(lines):
-    return [(float(w[3]), float(w[5])) for w in (l.split() for l in lines) if len(w) == 6 and w[1] == "TS"]
-
-
-@pytest.mark.parametrize("argv,golden", [(TEST1, GOLDEN_TEST1), (TEST4, GOLDEN_TEST4)])
-def test_arkimex_goldens_on_device(ctx, argv, golden):
-    """pattern.c's default TS type with adaptive steps: c/ch5/output/pattern.test1 / test4.  The step sizes are compared as
-    numbers (6 printed digits; a value that sits on a rounding boundary may print differently after 1e-10-level
-    differences in the stage solves); everything else verbatim."""
-    r = pp.pattern_main(argv, ctx)
-    assert len(r.lines) == len(golden)
-    np.testing.assert_allclose(_ts_numbers(r.lines), _ts_numbers(golden), rtol=3e-6)
-    assert [l for l in r.lines if " TS " not in l] == [l for l in golden if " TS " not in l]
-    if r.lines != golden:
-        print("printed digits differ:", [(a, b) for a, b in zip(r.lines, golden) if a != b])
-
-
-def test_golden_pattern_test3_crank_nicolson_on_device(ctx):
-    assert pp.pattern_main(TEST3, ctx).lines == GOLDEN_TEST3                 # c/ch5/output/pattern.test3
-
-
-@pytest.mark.parametrize("argv,golden", [(TEST1, GOLDEN_TEST1), (TEST2, GOLDEN_TEST2), (TEST3, GOLDEN_TEST3),
-                                         (TEST4, GOLDEN_TEST4)])
-def test_native_time_stepper_on_device(ctx, argv, golden):
-    """p4b_pattern_solve (host logic in C++ inside the library, csrc/ts_solver.hpp; CPU-checked against the same goldens
-    in tests/test_native_nk_cpu.py) on the device: step sizes as numbers, everything else verbatim."""
-    r = pp.pattern_main(argv, ctx, native=True)
-    assert len(r.lines) == len(golden)
-    np.testing.assert_allclose(_ts_numbers(r.lines), _ts_numbers(golden), rtol=3e-6)
-    assert [l for l in r.lines if " TS " not in l] == [l for l in golden if " TS " not in l]
-
-
-def test_native_time_stepper_equals_the_python_host(ctx):
-    argv = "-da_grid_x 4 -da_grid_y 4 -da_refine 5 -ts_type beuler -ts_dt 5 -ts_max_time 10 -pc_type mg -p4b_mg_rscale 0.25"
-    a = pp.pattern_main(argv, ctx)
-    b = pp.pattern_main(argv, ctx, native=True)
-    assert [(t, dt) for t, dt, _ in a.steps] == [(t, dt) for t, dt, _ in b.steps]
-    assert [s[2].its for s in a.steps] == [s[2] for s in b.steps]
-    assert float((a.Y - b.Y).abs().max()) <= 1e-10
