@@ -112,7 +112,27 @@ def build_drivers(force=False):
     return out
 
 
+EXAMPLES = {"minimal_native": "examples/minimal_native.c", "pattern_native": "examples/pattern_native.c"}
+
+
+def build_examples(force=False):
+    """The C hosts of examples/ (one C-ABI call per driver run) -> p4pdes_b200/bin/.  C99 -pedantic: the header is what a
+    C maintainer includes."""
+    build(force=False)
+    os.makedirs(BINDIR, exist_ok=True)
+    out = {}
+    for name, rel in EXAMPLES.items():
+        src, exe = os.path.join(ROOT, rel), os.path.join(BINDIR, name)
+        if (force or not os.path.exists(exe) or os.path.getmtime(exe) < os.path.getmtime(src)
+                or os.path.getmtime(exe) < os.path.getmtime(LIB)):
+            subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-O2", "-I", os.path.join(ROOT, "include"), src,
+                                   "-o", exe, "-L", LIBDIR, "-lp4b200", "-Wl,-rpath,$ORIGIN/../lib", "-lm"])
+        out[name] = exe
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_shim(force="--force" in sys.argv))
     print(build_drivers(force="--force" in sys.argv))
+    print(build_examples(force="--force" in sys.argv))

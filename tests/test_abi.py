@@ -139,3 +139,18 @@ def test_pattern_solve_structs_match_the_header(lib, tmp_path):
     got = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
     assert got == [C.sizeof(L.PatternOpts), C.sizeof(L.PatternResult), L.PatternResult.step_newton.offset,
                    L.PatternResult.error.offset]
+
+
+def test_c_example_hosts_build_as_c99_and_refuse_to_run_without_a_device():
+    """examples/*.c are what INTEGRATION.md shows a C maintainer: they must compile as pedantic C99 against the header and
+    link against the library; without a CUDA device they fail loudly (no CPU fallback behind the C ABI)."""
+    import subprocess
+    import torch
+    exes = p4build.build_examples()
+    assert set(exes) == {"minimal_native", "pattern_native"}
+    if torch.cuda.is_available():
+        pytest.skip("a device is present: the run itself is covered by the gpu_pending tests")
+    for exe in exes.values():
+        p = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        assert p.returncode == 1 and "no CPU fallback" in p.stderr
+        assert subprocess.run([exe, "-bogus"], capture_output=True).returncode == 2

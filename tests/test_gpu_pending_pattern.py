@@ -73,3 +73,22 @@ def test_native_time_stepper_equals_the_python_host(ctx):
     assert [(t, dt) for t, dt, _ in a.steps] == [(t, dt) for t, dt, _ in b.steps]
     assert [s[2].its for s in a.steps] == [s[2] for s in b.steps]
     assert float((a.Y - b.Y).abs().max()) <= 1e-10
+
+
+def test_c_example_hosts_print_the_goldens():
+    """examples/pattern_native.c / minimal_native.c: a C program, one C-ABI call per run."""
+    import subprocess
+    from p4pdes_b200 import build as p4build
+    exes = p4build.build_examples()
+    for argv, golden in ((TEST1, GOLDEN_TEST1), (TEST2, GOLDEN_TEST2), (TEST3, GOLDEN_TEST3), (TEST4, GOLDEN_TEST4)):
+        out = subprocess.run([exes["pattern_native"], *argv.split()], capture_output=True, text=True, timeout=300, check=True)
+        lines = out.stdout.rstrip("\n").split("\n")
+        assert len(lines) == len(golden)
+        np.testing.assert_allclose(_ts_numbers(lines), _ts_numbers(golden), rtol=3e-6)
+        assert [l for l in lines if " TS " not in l] == [l for l in golden if " TS " not in l]
+    out = subprocess.run([exes["minimal_native"], "-snes_fd_color", "-snes_converged_reason", "-snes_monitor_short",
+                          "-ms_problem", "catenoid", "-ms_catenoid_c", "2.0", "-da_refine", "1"], capture_output=True,
+                         text=True, timeout=300, check=True)
+    lines = out.stdout.rstrip("\n").split("\n")
+    assert lines[0] == "  0 SNES Function norm 1.08276"                                                  # minimal.test1:1
+    assert lines[-1] == "done on 5 x 5 grid and problem catenoid:  error |u-uexact|_inf = 1.10603e-04"  # :8
