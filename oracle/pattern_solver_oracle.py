@@ -20,7 +20,7 @@ implicit runs the reference uses (c/ch5/makefile:52-53 `-ts_type beuler -pc_type
 Pinned on c/ch5/output/pattern.test2 (backward Euler: all lines verbatim; the golden's KSP count (3) also comes out of the
 Chebyshev/Jacobi multigrid) and on c/ch5/output/pattern.test1 and pattern.test4 (ARKIMEX: every "TS dt ... time ..."
 line of the adaptive runs, 13 and 11 lines, to all printed digits, including the rejected step of test1).
-BDF and CN runs (pattern.test3, test5) are not restated.
+Crank-Nicolson: pattern.test3 verbatim.  BDF: only the restart step of pattern.test5 (see pattern_bdf_first_step).
 """
 from dataclasses import dataclass, field
 
@@ -253,3 +253,52 @@ def pattern_arkimex(grid=3, refine=0, dt=5.0, tmax=200.0, atol=1.0e-4, rtol=1.0e
     res.Y = Y
     res.rejected = rejected
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BDF2, first step only (pattern.test5).  [PETSc] TSBDF restarts with a backward-Euler HALF step (t0 -> t0 + dt/2), then
+# takes the BDF2 step over the nodes {t0 + dt, t0, t0 + dt/2} (variable-step weights = derivatives of the Lagrange basis
+# at the new time); the local truncation error is the difference between the 2-node and 3-node derivative formulas,
+# alpha = (a - b)/a_0, applied to the history (TSBDF_VecLTE, order k + 1 = 2), fed to TSAdaptBasic.  Later steps (order-2
+# LTE over four nodes, history rotation) have no golden and are not restated; the device path does not offer bdf.
+# ---------------------------------------------------------------------------------------------------------
+def lagrange_basis_ders(t, T):
+    """d/dt of the Lagrange basis polynomials over the nodes T, at t."""
+    n = len(T)
+    d = np.zeros(n)
+    for k in range(n):
+        for j in range(n):
+            if j == k:
+                continue
+            p = 1.0 / (T[k] - T[j])
+            for l in range(n):
+                if l not in (k, j):
+                    p *= (t - T[l]) / (T[k] - T[l])
+            d[k] += p
+    return d
+
+
+def pattern_bdf_first_step(grid=3, refine=4, dt=1.0, atol=1.0e-4, rtol=1.0e-4, L=2.5, Du=8.0e-5, Dv=4.0e-5, phi=0.024,
+                           kappa=0.06):
+    """Returns (Newton iterations of the two solves, proposed next step, state after the step)."""
+    m = grid * 2 ** refine
+    par = dict(L=L, Du=Du, Dv=Dv, phi=phi, kappa=kappa)
+    Y0 = mpo.pattern_initial_state(m, m, L)
+
+    def stage(times, hist, guess):
+        a = lagrange_basis_ders(times[0], times)
+        aff = sum(a[i] * hist[i - 1] for i in range(1, len(times)))
+        R = lambda W: mpo.pattern_ifunction(W, a[0] * W + aff, L, Du, Dv) - mpo.pattern_rhsfunction(W, phi, kappa)
+        return mso.newton(R, guess, lambda J, W: fo.ILU0PC(J).apply, jac=lambda W: stage_jacobian(W, a[0], True, **par))
+
+    half = stage([0.5 * dt, 0.0], [Y0], Y0)
+    full = stage([dt, 0.0, 0.5 * dt], [Y0, half.u], half.u)
+    T = [dt, 0.0, 0.5 * dt]
+    a = np.append(lagrange_basis_ders(dt, T[:2]), 0.0)
+    b = lagrange_basis_ders(dt, T)
+    alpha = (a - b) / a[0]
+    lte = alpha[0] * full.u + alpha[1] * Y0 + alpha[2] * half.u
+    tol = atol + rtol * np.maximum(np.abs(full.u), np.abs(full.u + lte))
+    enorm = float(np.sqrt(np.mean((lte / tol) ** 2)))
+    _, hnext = adapt_basic(dt, enorm, True, order=2)
+    return (half.its, full.its), hnext, full.u

@@ -193,3 +193,11 @@ def test_crank_nicolson_is_second_order_and_backward_euler_first_order():
                       for dt in (2.0, 1.0)]
     assert 1.7 < err[1.0][0] / err[1.0][1] < 2.3          # O(dt)
     assert 3.3 < err[0.5][0] / err[0.5][1] < 4.8          # O(dt^2)
+
+
+def test_bdf_restart_step_golden_pattern_test5():
+    """c/ch5/output/pattern.test5 (-da_refine 4 -ts_type bdf -ts_max_time 1): the two nonlinear solves of the restart
+    (3 and 2 Newton iterations) and the step the controller proposes next (1.10972)."""
+    (n1, n2), hnext, _ = po.pattern_bdf_first_step(grid=3, refine=4, dt=1.0)
+    assert (n1, n2) == (3, 2)                               # pattern.test5:3-4
+    assert po.fmt_g(float("%.6g" % hnext)) == "1.10972"     # pattern.test5:5  "1 TS dt 1.10972 time 1."
