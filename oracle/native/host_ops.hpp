@@ -339,3 +339,42 @@ struct HostOps {
         memcpy(x, o.data(), sizeof(double) * n);
     }
 };
+
+// The residual supplied as a host callback (the FormFunctionLocal contract; include/p4b200.h p4b_residual2d_fn): the CPU
+// counterpart of CallbackOps in p4pdes_b200/csrc/nk_device.cu.
+struct HostCallbackOps : HostOps {
+    int (*fn)(void *user, int mx, int my, const double *u, double *F) = nullptr;
+    void *user = nullptr;
+    long long callbacks = 0;
+    void minimal_sample(int, int, int, double, double, double *) {}
+    void minimal_function(int mx, int my, double, const double *u, const double *, double *F) {
+        callbacks++;
+        std::vector<double> uu(u, u + (size_t)mx * my), ff((size_t)mx * my);
+        if (fn(user, mx, my, uu.data(), ff.data()) && !err) err = 65;
+        memcpy(F, ff.data(), sizeof(double) * ff.size());
+    }
+    void minimal_jacobian_fd(int mx, int my, double q, const double *u, const double *g, const double *F0, double *vals) {
+        const int N = mx * my;
+        std::vector<double> up(N), Fp(N);
+        memset(vals, 0, sizeof(double) * 9 * (size_t)N);
+        for (int cj = 0; cj < 3; cj++)
+            for (int ci = 0; ci < 3; ci++) {
+                for (int n = 0; n < N; n++) {
+                    const int j = n / mx, i = n - j * mx;
+                    up[n] = (i % 3 == ci && j % 3 == cj) ? u[n] + fd_dx(u[n]) : u[n];
+                }
+                minimal_function(mx, my, q, up.data(), g, Fp.data());
+                for (int n = 0; n < N; n++) {
+                    const int j = n / mx, i = n - j * mx;
+                    int di = ci - i % 3, dj = cj - j % 3;
+                    if (di > 1) di -= 3;
+                    if (di < -1) di += 3;
+                    if (dj > 1) dj -= 3;
+                    if (dj < -1) dj += 3;
+                    const int ii = i + di, jj = j + dj;
+                    if (ii < 0 || ii >= mx || jj < 0 || jj >= my) continue;
+                    vals[(size_t)(3 * (dj + 1) + (di + 1)) * N + n] = (Fp[n] - F0[n]) * (1.0 / fd_dx(u[jj * mx + ii]));
+                }
+            }
+    }
+};

@@ -2,6 +2,7 @@
 //   nk_host_test [-ms_problem tent|catenoid] [-ms_q q] [-ms_catenoid_c c] [-da_grid_x n] [-da_grid_y n] [-da_refine r]
 //                [-snes_grid_sequence k] [-ksp_type gmres|cg] [-pc_type mg|none] [-pc_mg_levels n] [-monitor]
 // prints the solver's lines, then one JSON line with the per-stage results and a checksum of the solution.
+#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -57,11 +58,25 @@ static int pattern_main(int argc, char **argv) {
     return 0;
 }
 
+// -callback <libfishref.so>: the residual is the REFERENCE's own FormFunctionLocal (c/ch7/minimal.c:210-282, compiled
+// unchanged by oracle/refstub into oracle/_ref/libfishref.so), reached through the p4b_residual2d_fn contract
+typedef int (*ref_minimal_fn)(const int *M, int problem, double q, double tent_H, double catenoid_c, double *u, double *FF);
+struct RefUser { ref_minimal_fn f; int problem; double q, H, c; };
+static int ref_residual(void *user, int mx, int my, const double *u, double *F) {
+    RefUser *r = (RefUser *)user;
+    const int M[3] = {mx, my, 1};
+    return r->f(M, r->problem, r->q, r->H, r->c, const_cast<double *>(u), F);
+}
+
 int main(int argc, char **argv) {
     using namespace p4b::nk;
     if (argc > 1 && std::string(argv[1]) == "-pattern") return pattern_main(argc, argv);
     MinimalOpts o;
     default_opts(&o);
+    const char *cb_lib = nullptr;
+    for (int i = 1; i < argc; i++) {
+        if (std::string(argv[i]) == "-callback" && i + 1 < argc) { cb_lib = argv[i + 1]; for (int k = i; k + 2 < argc; k++) argv[k] = argv[k + 2]; argc -= 2; break; }
+    }
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
@@ -80,10 +95,43 @@ int main(int argc, char **argv) {
         else if (a == "-monitor") { o.snes_monitor = 2; o.snes_converged_reason = 1; o.ksp_converged_reason = 1; }
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
-    HostOps ops;
     MinimalResult R;
     double *u = nullptr;
     Printer pr{print_line, nullptr};
+    if (cb_lib) {
+        void *h = dlopen(cb_lib, RTLD_NOW);
+        if (!h) { fprintf(stderr, "%s\n", dlerror()); return 3; }
+        RefUser ru{(ref_minimal_fn)dlsym(h, "ref_minimal_function"), o.problem, o.q, o.tent_H, o.catenoid_c};
+        if (!ru.f) { fprintf(stderr, "ref_minimal_function not found\n"); return 3; }
+        // the caller's part of minimal.c:main: the grid and the initial iterate (InitialState: g on the boundary, 0 inside)
+        int mx = o.grid_x, my = o.grid_y;
+        for (int r = 0; r < o.refine; r++) { mx = 2 * mx - 1; my = 2 * my - 1; }
+        HostOps tmp;
+        std::vector<double> g((size_t)mx * my), u0((size_t)mx * my);
+        tmp.minimal_sample(mx, my, o.problem, o.tent_H, o.catenoid_c, g.data());
+        tmp.initial_state2d(mx, my, g.data(), u0.data());
+        HostCallbackOps cops;
+        cops.fn = ref_residual;
+        cops.user = &ru;
+        const int rc = minimal_solve(&cops, o, pr, &u, &R, u0.data(), false);
+        if (rc) { fprintf(stderr, "minimal_solve (callback) failed: %d\n", rc); return 1; }
+        // the caller's error report (minimal.c:166-181)
+        std::vector<double> gf((size_t)R.mx * R.my);
+        tmp.minimal_sample(R.mx, R.my, o.problem, o.tent_H, o.catenoid_c, gf.data());
+        double e = 0.0, sum = 0.0;
+        for (int n = 0; n < R.mx * R.my; n++) { e = std::max(e, fabs(u[n] - gf[n])); sum += u[n]; }
+        printf("{\"mx\": %d, \"my\": %d, \"errinf\": %.17g, \"sum\": %.17g, \"callbacks\": %lld, \"stages\": [", R.mx, R.my, e, sum, cops.callbacks);
+        for (int s = 0; s < R.nstages; s++) {
+            const StageResult &S = R.stage[s];
+            printf("%s{\"mx\": %d, \"its\": %d, \"reason\": \"%s\", \"ksp_its\": [", s ? ", " : "", S.mx, S.its, snes_reason_name(S.reason));
+            for (int k = 0; k < S.its; k++) printf("%s%d", k ? ", " : "", S.ksp_its[k]);
+            printf("]}");
+        }
+        printf("]}\n");
+        cops.release(u);
+        return 0;
+    }
+    HostOps ops;
     const int rc = minimal_solve(&ops, o, pr, &u, &R);
     if (rc) { fprintf(stderr, "minimal_solve failed: %d\n", rc); return 1; }
     double sum = 0.0, sum2 = 0.0;

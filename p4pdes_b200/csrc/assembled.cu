@@ -57,6 +57,19 @@ __global__ void __launch_bounds__(256) fd_extract_kernel(int mx, int my, int ci,
     vals[(size_t)(3 * (dj + 1) + (di + 1)) * N + n] = (Fp[n] - F0[n]) * vscale;
 }
 
+// the two device halves of one colour, for callers whose residual is not a kernel of this library (host callbacks)
+int launch_fd_perturb(cudaStream_t st, int mx, int my, int ci, int cj, const double *u, double *up) {
+    fd_perturb_kernel<<<(unsigned)((mx * my + 255) / 256), 256, 0, st>>>(mx, my, ci, cj, u, up);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+int launch_fd_extract(cudaStream_t st, int mx, int my, int ci, int cj, const double *u, const double *F0, const double *Fp,
+                      double *vals) {
+    fd_extract_kernel<<<(unsigned)((mx * my + 255) / 256), 256, 0, st>>>(mx, my, ci, cj, u, F0, Fp, vals);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+
 int fd_jacobian_minimal(cudaStream_t st, int mx, int my, double q, const double *u, const double *g, const double *F0,
                         double *vals, double *up, double *Fp) {
     const int N = mx * my;

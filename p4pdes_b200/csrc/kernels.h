@@ -96,6 +96,9 @@ void sell_info(const Sell *A, int *nrows, long long *nnz, long long *padded);
 // assembled 2-D 9-point Jacobians (assembled.cu): stencil9 layout vals[s*N + n], s = 3(dj+1) + (di+1)
 int fd_jacobian_minimal(cudaStream_t st, int mx, int my, double q, const double *u, const double *g, const double *F0,
                         double *vals, double *up, double *Fp);
+int launch_fd_perturb(cudaStream_t st, int mx, int my, int ci, int cj, const double *u, double *up);
+int launch_fd_extract(cudaStream_t st, int mx, int my, int ci, int cj, const double *u, const double *F0, const double *Fp,
+                      double *vals);
 int launch_stencil9_apply(cudaStream_t st, int mx, int my, const double *vals, const double *x, double *y);
 int launch_pattern_jac(cudaStream_t st, int mode, int mx, int my, double Cu, double Cv, double shift, double phi,
                        double kappa, const double *Y, const double *X, const double *b, const double *pm1, double ca,

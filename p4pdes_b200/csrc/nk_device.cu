@@ -102,6 +102,43 @@ struct DeviceOps {
     void pattern_inject(int Mx, int My, const double *yf, double *yc) { chk(p4b_pattern_inject(c, Mx, My, yf, yc)); }
 };
 
+// The same operations with the RESIDUAL supplied by the caller as a host callback -- the FormFunctionLocal contract of
+// the reference's drivers (c/ch7/minimal.c:210-282 is registered with DMDASNESSetFunctionLocal, :138-140): the iterate
+// is brought to the host, the callback fills F on the host exactly as PETSc would have it called (whole grid, natural
+// ordering), F goes back.  Everything else (Jacobian differencing, Krylov, multigrid, line search algebra) stays on
+// the device; the coloured finite-difference Jacobian costs nine callback evaluations per level.
+struct CallbackOps : DeviceOps {
+    p4b_residual2d_fn fn = nullptr;
+    void *user = nullptr;
+    std::vector<double> hu, hF;
+    CallbackOps(p4b_ctx *c_, cudaStream_t st_, p4b_residual2d_fn f, void *u) : DeviceOps{c_, st_}, fn(f), user(u) {}
+    void minimal_sample(int, int, int, double, double, double *) {}
+    void minimal_function(int mx, int my, double, const double *u, const double *, double *F) {
+        const size_t n = (size_t)mx * my;
+        hu.resize(n);
+        hF.resize(n);
+        to_host(u, hu.data(), n);
+        if (!err) {
+            const int rc = fn(user, mx, my, hu.data(), hF.data());
+            if (rc && !err) err = 65;
+        }
+        from_host(hF.data(), F, n);
+    }
+    void minimal_jacobian_fd(int mx, int my, double q, const double *u, const double *g, const double *F0, double *vals) {
+        const size_t n = (size_t)mx * my;
+        double *up = alloc(n), *Fp = alloc(n);
+        cu(cudaMemsetAsync(vals, 0, sizeof(double) * 9 * n, st));
+        for (int cj = 0; cj < 3; cj++)
+            for (int ci = 0; ci < 3; ci++) {
+                chk(launch_fd_perturb(st, mx, my, ci, cj, u, up));
+                minimal_function(mx, my, q, up, g, Fp);
+                chk(launch_fd_extract(st, mx, my, ci, cj, u, F0, Fp, vals));
+            }
+        release(up);
+        release(Fp);
+    }
+};
+
 }  // namespace p4b
 
 using namespace p4b;
@@ -141,6 +178,33 @@ extern "C" int p4b_minimal_solve(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_l
     if (rc == 62) return fail(62, "base-grid Jacobian is singular");
     if (rc == 63) return fail(63, "u_out holds %zu doubles, the final grid needs %d x %d", u_capacity, R.mx, R.my);
     if (rc) return fail(rc, "p4b_minimal_solve failed (%s)", p4b_last_error());
+    return 0;
+}
+
+extern "C" int p4b_snes2d_solve(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_residual2d_fn residual, void *user,
+                                const double *u0_host, p4b_line_fn line, void *line_ctx, double *u_out_host,
+                                size_t u_capacity, p4b_minimal_result *result) {
+    if (!c || !opts || !residual || !u0_host || !result) return fail(62, "p4b_snes2d_solve: null argument");
+    const nk::MinimalOpts &o = *reinterpret_cast<const nk::MinimalOpts *>(opts);
+    if (o.grid_x < 3 || o.grid_y < 3) return fail(60, "grid needs at least 3 nodes per dimension");
+    CallbackOps ops(c, ctx_stream(c), residual, user);
+    nk::Printer pr{line, line_ctx};
+    double *u = nullptr;
+    nk::MinimalResult &R = *reinterpret_cast<nk::MinimalResult *>(result);
+    int rc = nk::minimal_solve(&ops, o, pr, u_out_host ? &u : nullptr, &R, u0_host, false);
+    if (!rc && ops.error()) rc = ops.error();
+    if (!rc && u_out_host) {
+        const size_t n = (size_t)R.mx * R.my;
+        if (u_capacity < n) rc = 63;
+        else ops.to_host(u, u_out_host, n);
+    }
+    if (u) cudaFreeAsync(u, ops.st);
+    cudaStreamSynchronize(ops.st);
+    if (rc == 61) return fail(61, "base grid of the multigrid hierarchy is larger than 65 x 65: use a coarser base grid");
+    if (rc == 62) return fail(62, "base-grid Jacobian is singular");
+    if (rc == 63) return fail(63, "u_out holds %zu doubles, the final grid needs %d x %d", u_capacity, R.mx, R.my);
+    if (rc == 65) return fail(65, "the residual callback returned an error");
+    if (rc) return fail(rc, "p4b_snes2d_solve failed (%s)", p4b_last_error());
     return 0;
 }
 

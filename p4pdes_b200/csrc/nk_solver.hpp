@@ -538,8 +538,12 @@ int newton(Ops *ops, std::vector<Level<Ops>> &lev, const MinimalOpts &opt, const
 // minimal.c:main from DMDACreate2d to the error report (c/ch7/minimal.c:128-181)
 // u_out: the final iterate (mx*my doubles in Ops memory, nullptr = not wanted; mx, my are in the result)
 // ---------------------------------------------------------------------------------------------------------
+// u0_host (optional): the caller's initial iterate on the first grid (host, mx*my doubles) -- then the problem is the
+// caller's (its residual comes through Ops as a callback), nothing is known about an exact solution, and the final
+// report is the caller's business (report = false).
 template <class Ops>
-int minimal_solve(Ops *ops, const MinimalOpts &opt, const Printer &pr, double **u_out, MinimalResult *R) {
+int minimal_solve(Ops *ops, const MinimalOpts &opt, const Printer &pr, double **u_out, MinimalResult *R,
+                  const double *u0_host = nullptr, bool report = true) {
     memset(R, 0, sizeof *R);
     R->errinf = -1.0;
     if (opt.grid_sequence + 1 > MAX_STAGES) return 60;
@@ -565,7 +569,8 @@ int minimal_solve(Ops *ops, const MinimalOpts &opt, const Printer &pr, double **
         for (size_t l = 0; l < shapes.size(); l++) next[l].create(ops, shapes[l].first, shapes[l].second, opt);
         Level<Ops> &L = next[0];
         if (stage == 0) {
-            if (opt.exact_init) ops->copy(L.n, L.g, L.u);                      // FormExactFromG (minimal.c:191-208)
+            if (u0_host) ops->from_host(u0_host, L.u, L.n);                    // the caller's u_initial (minimal.c:150-158)
+            else if (opt.exact_init) ops->copy(L.n, L.g, L.u);                 // FormExactFromG (minimal.c:191-208)
             else ops->initial_state2d(L.mx, L.my, L.g, L.u);                   // InitialState(ZEROS, gonboundary) (:157)
         } else {
             ops->set(L.n, 0.0, L.u);
@@ -583,11 +588,11 @@ int minimal_solve(Ops *ops, const MinimalOpts &opt, const Printer &pr, double **
         R->mx = L.mx;
         R->my = L.my;
         const char *pname = opt.problem == 0 ? "tent" : "catenoid";
-        if (opt.problem == 1 && opt.q == -0.5) {
+        if (report && opt.problem == 1 && opt.q == -0.5) {
             ops->axpby(L.n, 1.0, L.u, -1.0, L.g, L.t);
             R->errinf = ops->norminf(L.n, L.t);
             pr.out("done on %d x %d grid and problem %s:  error |u-uexact|_inf = %.5e", L.mx, L.my, pname, R->errinf);   // :177
-        } else {
+        } else if (report) {
             pr.out("done on %d x %d grid and problem %s ...", L.mx, L.my, pname);                                       // :180
         }
         if (u_out) {

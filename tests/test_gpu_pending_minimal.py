@@ -44,3 +44,40 @@ def test_native_solve_cluster_configuration(ctx):
     assert (r.mx, r.my) == (2049, 2049) and all(s.reason.startswith("CONVERGED") for s in r.stages)
     assert max(max(s.ksp_its) for s in r.stages[1:]) <= 12 and r.errinf < 1e-7
     print("minimal 2049^2 native: %.3f s, Newton its %s" % (r.seconds, [s.its for s in r.stages]))
+
+
+def test_callback_contract_on_device(ctx):
+    """p4b_snes2d_solve: the residual is a HOST callback (here the NumPy restatement of minimal.c's FormFunctionLocal plays
+    the user's callback), the algebra runs on the device.  Must agree with the run whose residual is the device kernel."""
+    import ctypes as C
+    from oracle import minimal_pattern_oracle as mpo
+    from p4pdes_b200 import lib as L
+    calls = [0]
+    gcache = {}
+
+    def residual(_user, mx, my, u_ptr, F_ptr):
+        calls[0] += 1
+        if (mx, my) not in gcache:
+            gcache[(mx, my)] = mpo.minimal_g(mx, my, "tent", 1.0, 1.1)
+        u = np.ctypeslib.as_array(u_ptr, shape=(my, mx))
+        np.ctypeslib.as_array(F_ptr, shape=(my, mx))[:] = mpo.minimal_function(u, gcache[(mx, my)], -0.5)
+        return 0
+
+    o = L.MinimalOpts()
+    L.check(ctx.lib.p4b_minimal_default_opts(C.byref(o)))
+    o.grid_x = o.grid_y = 3
+    o.grid_sequence = 3
+    g0 = mpo.minimal_g(3, 3, "tent", 1.0, 1.1)
+    u0 = np.zeros((3, 3))
+    u0[[0, -1], :] = g0[[0, -1], :]
+    u0[:, [0, -1]] = g0[:, [0, -1]]
+    out = np.zeros(17 * 17)
+    res = L.MinimalResult()
+    cb, line = L.RESIDUAL2D_FN(residual), L.LINE_FN(lambda s, c: None)
+    L.check(ctx.lib.p4b_snes2d_solve(ctx.h, C.byref(o), cb, None, u0.ctypes.data_as(C.c_void_p), line, None,
+                                     out.ctypes.data_as(C.c_void_p), out.size, C.byref(res)))
+    ref = pm.minimal_main("-snes_fd_color -snes_grid_sequence 3 -ms_problem tent -pc_type mg", ctx)
+    assert (res.mx, res.my, res.nstages) == (17, 17, 4)
+    assert [res.stage[s].its for s in range(4)] == [s.its for s in ref.stages]
+    assert calls[0] > 9 * sum(s.its for s in ref.stages)
+    assert np.max(np.abs(out - ctx.to_host(ref.u))) <= 1e-8

@@ -112,3 +112,23 @@ def test_native_time_stepper_matches_python_oracle(exe):
     assert d["nsteps"] == len(o.steps) and d["rejected"] == o.rejected
     want = float(np.sum(o.Y[..., 0] + 3.0 * o.Y[..., 1]))
     assert abs(d["sum"] - want) <= 1e-7 * abs(want)           # stage solves: Newton rtol 1e-8 vs the oracle's direct solves
+
+
+# ---- the callback contract: the REFERENCE's own compiled FormFunctionLocal drives the native solver ---------------------
+REFLIB = os.path.join(ROOT, "oracle", "_ref", "libfishref.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REFLIB), reason="oracle/_ref/libfishref.so not built (no /root/reference)")
+def test_reference_callback_drives_the_native_solver(exe):
+    """p4b_residual2d_fn (include/p4b200.h) is the FormFunctionLocal contract.  Here the callback is c/ch7/minimal.c's own
+    FormFunctionLocal, compiled unchanged (oracle/refstub), and the solver is the product's host logic on plain-C++
+    vector operations: golden error of minimal.test1, golden Newton counts of minimal.test4 (with multigrid instead of the
+    sequential ILU), and agreement with the run whose residual is the restated kernel formula."""
+    _, d = run(exe, "-callback", REFLIB, "-snes_fd_color", "-ms_problem", "catenoid", "-ms_catenoid_c", 2.0, "-da_refine", 1)
+    assert "%.5e" % d["errinf"] == "1.10603e-04"                                     # minimal.test1:8
+    assert abs(d["stages"][0]["its"] - 5) <= 1 and d["callbacks"] > 9 * d["stages"][0]["its"]
+    _, d = run(exe, "-callback", REFLIB, "-snes_fd_color", "-ms_problem", "tent", "-snes_grid_sequence", 2, "-pc_type", "mg")
+    assert [s["its"] for s in d["stages"]] == [3, 5, 5]                              # minimal.test4:1-3
+    _, own = run(exe, "-snes_fd_color", "-ms_problem", "tent", "-snes_grid_sequence", 2, "-pc_type", "mg")
+    assert [s["ksp_its"] for s in d["stages"]] == [s["ksp_its"] for s in own["stages"]]
+    assert abs(d["sum"] - own["sum"]) <= 1e-9 * abs(own["sum"])
