@@ -318,8 +318,8 @@ int p4b_minimal_solve(p4b_ctx *ctx, const p4b_minimal_opts *opts, p4b_line_fn li
  * callback is invoked on the host with the whole mx x my grid (one logical rank: xs = 0, xm = mx, ...), arrays in DMDA
  * natural ordering (a binding wraps DMDALocalInfo and a[j][i] pointer tables around them), on every grid of the
  * hierarchy and of the grid sequence; Jacobians by coloured finite differences of it; the algebra stays on the device.
- * opts: the solver fields of p4b_minimal_opts (grid_x/grid_y/refine = the grid u0 lives on, grid_sequence, ksp_*, pc_*,
- * mg_*, snes_*); the -ms_* fields are ignored.  u0_host: initial iterate; u_out_host: the solution on the final grid. ---- */
+ * opts: the solver fields of the options struct above -- grid_x/grid_y/refine = the grid u0 lives on, grid_sequence, ksp_*, pc_*,
+ * mg_*, snes_* -- the -ms_* fields are ignored.  u0_host: initial iterate; u_out_host: the solution on the final grid. ---- */
 typedef int (*p4b_residual2d_fn)(void *user, int mx, int my, const double *u_host, double *F_host);
 int p4b_snes2d_solve(p4b_ctx *ctx, const p4b_minimal_opts *opts, p4b_residual2d_fn residual, void *user,
                      const double *u0_host, p4b_line_fn line, void *line_ctx, double *u_out_host, size_t u_capacity,
