@@ -237,7 +237,8 @@ int p4b_pattern_ijacobian_mult(p4b_ctx *ctx, int mx, int my, double L, double Du
                                const double *X, double *JX);
 /* ---- assembled Jacobians of the 2-D drivers: finite-difference assembly and the solver kernels on them ----
  *   p4b_minimal_jacobian_fd  [PETSc] SNESComputeJacobianDefaultColor on c/ch7/minimal.c:210-282 (-snes_fd_color):
- *                            9 colours (DMDA BOX stencil), MatFDColoring "ds" differencing; F0 = F(u) already computed
+ *                            9 colours (DMDA BOX stencil), MatFDColoring's default "wp" differencing (one step
+ *                            h = sqrt(eps) sqrt(1 + ||u||_2) for every column); F0 = F(u) already computed
  *   p4b_stencil9_apply       [PETSc] MatMult on that matrix
  *   p4b_stencil9_lin         [PETSc] KSPSolve_Chebyshev/Richardson step + PCApply_Jacobi on it:
  *                            out = ca*pm1 + cb*u + cg*B(b - A u), B = diag(A)^-1 (jacobi != 0) or I
@@ -324,6 +325,14 @@ typedef int (*p4b_residual2d_fn)(void *user, int mx, int my, const double *u_hos
 int p4b_snes2d_solve(p4b_ctx *ctx, const p4b_minimal_opts *opts, p4b_residual2d_fn residual, void *user,
                      const double *u0_host, p4b_line_fn line, void *line_ctx, double *u_out_host, size_t u_capacity,
                      p4b_minimal_result *result);
+/* the same with a caller's monitor ([PETSc] SNESMonitorSet, c/ch7/minimal.c:144-146 registers MSEMonitor :286-345): called
+ * on the host before the first and after every Newton iteration of every grid-sequence stage, ahead of the -snes_monitor
+ * line, with the current iterate on that stage's grid; tablevel = the stages still to come ([PETSc] PetscObjectGetTabLevel
+ * of the SNES under -snes_grid_sequence).  A non-zero return aborts the solve (error 66).  monitor may be NULL. */
+typedef int (*p4b_monitor2d_fn)(void *user, int mx, int my, int its, double fnorm, int tablevel, const double *u_host);
+int p4b_snes2d_solve_monitored(p4b_ctx *ctx, const p4b_minimal_opts *opts, p4b_residual2d_fn residual,
+                               p4b_monitor2d_fn monitor, void *user, const double *u0_host, p4b_line_fn line, void *line_ctx,
+                               double *u_out_host, size_t u_capacity, p4b_minimal_result *result);
 /* ---- the whole pattern.c run in one call: [PETSc] TSSolve for `./pattern [-ts_type arkimex|beuler|cn] -pc_type mg|none`
  * (c/ch5/pattern.c:99-125, c/ch5/makefile:49-62): TSARKIMEX3 + TSAdaptBasic + MATCHSTEP, or TSTHETA with Newton + bt;
  * stage solves GMRES(30) + V cycle on the matrix-free stage operator; host logic csrc/ts_solver.hpp. ---- */

@@ -4,8 +4,12 @@ minimal.c hands PETSc a residual callback (FormFunctionLocal, restated in minima
 `SNESSolve` do the rest (c/ch7/minimal.c:138-161).  This file restates, in NumPy/SciPy, the PETSc pieces the
 reference's own runs use (c/ch7/makefile:15-25, c/ch8/cluster.sh:70), following SURVEY.md Appendix A10:
 
-  fd_jacobian      [PETSc] SNESComputeJacobianDefaultColor / MatFDColoringApply ("ds"): 9 colours of the DMDA BOX
-                   stencil, dx = eps*x (|x| >= umin) or eps*umin*sign(x), eps = sqrt(DBL_EPSILON), umin = 1e-6
+  fd_jacobian      [PETSc] SNESComputeJacobianDefaultColor / MatFDColoringApply with the default differencing "wp"
+                   (Walker-Pernice): 9 colours of the DMDA BOX stencil, ONE step for every column,
+                   h = sqrt(DBL_EPSILON) * sqrt(1 + ||u||_2).  Pinned by minimal.test1: with this h every printed digit
+                   of its six residual norms is reproduced; the per-entry "ds" rule (h_m = eps*u_m, eps*umin at
+                   u_m = 0) takes a visibly different Newton path from the zero interior (first FD Jacobian with ~1 %
+                   rounding noise), and h = eps*(1 + ||u||) misses the last printed digit of three of the norms
   gmres            [PETSc] KSPGMRES(30), left preconditioning, preconditioned-residual norm, x0 = 0
   linesearch_bt    [PETSc] SNESLineSearchApply_BT, cubic backtracking, alpha = 1e-4, steptol 1e-12
   newton           [PETSc] SNESSolve_NEWTONLS + SNESConvergedDefault (rtol 1e-8, stol 1e-8, Jacobian every iteration)
@@ -13,8 +17,8 @@ reference's own runs use (c/ch7/makefile:15-25, c/ch8/cluster.sh:70), following 
                    iterate, R = P^T (DMDA Q1), Chebyshev(2)/Jacobi smoothing, dense LU on the coarsest grid
   minimal          minimal.c:main incl. -snes_grid_sequence (DMRefine + Q1 interpolation of the iterate)
 
-Pinned on the reference's goldens (tests/test_minimal_oracle.py): c/ch7/output/minimal.test1 (Newton norms,
-iteration count, error), minimal.test2 (CG+ILU iteration counts 5, 6), minimal.test4 (grid-sequenced Newton
+Pinned on the reference's goldens (tests/test_minimal_oracle.py): c/ch7/output/minimal.test1 (every Newton norm to
+the printed precision, iteration count, error), minimal.test2 (CG+ILU iteration counts 5, 6), minimal.test4 (grid-sequenced Newton
 iteration counts 3, 5, 5).  The Chebyshev/Jacobi MG variant has no golden (PETSc's default smoother PC is the
 sequential SOR): parity unpinned there, as for fish.  Eigenvalue target: PETSc estimates lambda_max
 with GMRES on a random right-hand side; the oracle and the device path both use the Gershgorin bound
@@ -29,12 +33,11 @@ from . import fish_oracle as fo
 from . import minimal_pattern_oracle as mpo
 
 EPS_FD = 1.4901161193847656e-08      # PETSC_SQRT_MACHINE_EPSILON
-UMIN_FD = 1.0e-6
 
 
-def fd_dx(x):
-    d = np.where(np.abs(x) < UMIN_FD, np.where(x < 0.0, -1.0, 1.0) * UMIN_FD, x)
-    return d * EPS_FD
+def fd_step(u):
+    """[PETSc] MatFDColoringApply, htype "wp": the differencing step, the same for every column."""
+    return EPS_FD * float(np.sqrt(1.0 + np.sqrt(np.sum(np.asarray(u, dtype=np.float64) ** 2))))
 
 
 def fd_jacobian(F, u, F0=None):
@@ -44,14 +47,15 @@ def fd_jacobian(F, u, F0=None):
     N = mx * my
     if F0 is None:
         F0 = F(u)
-    dx = fd_dx(u)
+    h = fd_step(u)
+    vscale = 1.0 / h
     jj, ii = np.meshgrid(np.arange(my), np.arange(mx), indexing="ij")
     rows, cols, vals = [], [], []
     n = (jj * mx + ii)
     for cj in range(3):
         for ci in range(3):
             mask = (ii % 3 == ci) & (jj % 3 == cj)
-            Fp = F(u + np.where(mask, dx, 0.0))
+            Fp = F(u + np.where(mask, h, 0.0))
             dF = Fp - F0
             # row (i, j) meets the column (i+di, j+dj) of this colour
             di = ci - ii % 3
@@ -63,7 +67,7 @@ def fd_jacobian(F, u, F0=None):
             m = (j2 * mx + i2)[ok]
             rows.append(n[ok])
             cols.append(m)
-            vals.append(dF[ok] * (1.0 / dx.ravel()[m]))
+            vals.append(dF[ok] * vscale)
     A = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(N, N))
     A.sort_indices()
     return A

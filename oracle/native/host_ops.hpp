@@ -35,6 +35,7 @@ struct HostOps {
     }
     void copy(size_t n, const double *x, double *y) { memmove(y, x, sizeof(double) * n); }
     void set(size_t n, double a, double *y) { for (size_t i = 0; i < n; i++) y[i] = a; }
+    void user_monitor(int, int, int, double, int, const double *) {}
 
     // c/ch7/minimal.c:27-42  g_bdry_tent / g_bdry_catenoid at every node of the unit square
     void minimal_sample(int mx, int my, int problem, double H, double c, double *g) {
@@ -79,22 +80,20 @@ struct HostOps {
                 FF[n] = -hyhx * (De * (ue - uc) - Dw * (uc - uw)) - hxhy * (Dn * (un - uc) - Ds * (uc - us));
             }
     }
-    // [PETSc] MatFDColoringApply ("ds"), 9 colours of the DMDA BOX stencil; vals in the stencil9 layout
-    static double fd_dx(double x) {
-        const double eps = 1.4901161193847656e-08, umin = 1.0e-6;
-        double dx = x;
-        if (fabs(dx) < umin) dx = (dx < 0.0 ? -1.0 : 1.0) * umin;
-        return dx * eps;
-    }
+    // [PETSc] MatFDColoringApply, default differencing "wp": 9 colours of the DMDA BOX stencil, ONE step for every
+    // column, h = sqrt(DBL_EPSILON) sqrt(1 + ||u||_2) (pinned by minimal.test1, oracle/minimal_solver_oracle.py);
+    // vals in the stencil9 layout
+    double fd_step(size_t n, const double *u) { return 1.4901161193847656e-08 * sqrt(1.0 + norm2(n, u)); }
     void minimal_jacobian_fd(int mx, int my, double q, const double *u, const double *g, const double *F0, double *vals) {
         const int N = mx * my;
         std::vector<double> up(N), Fp(N);
+        const double h = fd_step((size_t)N, u), vscale = 1.0 / h;
         memset(vals, 0, sizeof(double) * 9 * (size_t)N);
         for (int cj = 0; cj < 3; cj++)
             for (int ci = 0; ci < 3; ci++) {
                 for (int n = 0; n < N; n++) {
                     const int j = n / mx, i = n - j * mx;
-                    up[n] = (i % 3 == ci && j % 3 == cj) ? u[n] + fd_dx(u[n]) : u[n];
+                    up[n] = (i % 3 == ci && j % 3 == cj) ? u[n] + h : u[n];
                 }
                 minimal_function(mx, my, q, up.data(), g, Fp.data());
                 for (int n = 0; n < N; n++) {
@@ -106,7 +105,7 @@ struct HostOps {
                     if (dj < -1) dj += 3;
                     const int ii = i + di, jj = j + dj;
                     if (ii < 0 || ii >= mx || jj < 0 || jj >= my) continue;
-                    vals[(size_t)(3 * (dj + 1) + (di + 1)) * N + n] = (Fp[n] - F0[n]) * (1.0 / fd_dx(u[jj * mx + ii]));
+                    vals[(size_t)(3 * (dj + 1) + (di + 1)) * N + n] = (Fp[n] - F0[n]) * vscale;
                 }
             }
     }
@@ -345,7 +344,13 @@ struct HostOps {
 struct HostCallbackOps : HostOps {
     int (*fn)(void *user, int mx, int my, const double *u, double *F) = nullptr;
     void *user = nullptr;
+    int (*mon)(void *user, int mx, int my, int its, double fnorm, int tablevel, const double *u) = nullptr;
     long long callbacks = 0;
+    void user_monitor(int mx, int my, int its, double fnorm, int tablevel, const double *u) {
+        if (!mon || err) return;
+        std::vector<double> uu(u, u + (size_t)mx * my);
+        if (mon(user, mx, my, its, fnorm, tablevel, uu.data())) err = 66;
+    }
     void minimal_sample(int, int, int, double, double, double *) {}
     void minimal_function(int mx, int my, double, const double *u, const double *, double *F) {
         callbacks++;
@@ -356,12 +361,13 @@ struct HostCallbackOps : HostOps {
     void minimal_jacobian_fd(int mx, int my, double q, const double *u, const double *g, const double *F0, double *vals) {
         const int N = mx * my;
         std::vector<double> up(N), Fp(N);
+        const double h = fd_step((size_t)N, u), vscale = 1.0 / h;
         memset(vals, 0, sizeof(double) * 9 * (size_t)N);
         for (int cj = 0; cj < 3; cj++)
             for (int ci = 0; ci < 3; ci++) {
                 for (int n = 0; n < N; n++) {
                     const int j = n / mx, i = n - j * mx;
-                    up[n] = (i % 3 == ci && j % 3 == cj) ? u[n] + fd_dx(u[n]) : u[n];
+                    up[n] = (i % 3 == ci && j % 3 == cj) ? u[n] + h : u[n];
                 }
                 minimal_function(mx, my, q, up.data(), g, Fp.data());
                 for (int n = 0; n < N; n++) {
@@ -373,7 +379,7 @@ struct HostCallbackOps : HostOps {
                     if (dj < -1) dj += 3;
                     const int ii = i + di, jj = j + dj;
                     if (ii < 0 || ii >= mx || jj < 0 || jj >= my) continue;
-                    vals[(size_t)(3 * (dj + 1) + (di + 1)) * N + n] = (Fp[n] - F0[n]) * (1.0 / fd_dx(u[jj * mx + ii]));
+                    vals[(size_t)(3 * (dj + 1) + (di + 1)) * N + n] = (Fp[n] - F0[n]) * vscale;
                 }
             }
     }

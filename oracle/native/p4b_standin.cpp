@@ -1,0 +1,97 @@
+// p4b_standin.cpp -- HOST stand-in for the few C-ABI entry points the PETSc-shaped shim calls on the SNESNEWTONLS path
+// (TEST INFRASTRUCTURE ONLY: never compiled into libp4b200.so, never loaded by the product).
+//
+// p4pdes_b200/shim/petscshim.c runs the reference's unchanged c/ch7/minimal.c by handing its FormFunctionLocal to
+// p4b_snes2d_solve_monitored (include/p4b200.h).  On a machine without a GPU the shim's host logic -- option parsing,
+// DMDALocalInfo and a[j][i] views around the callback, SNESMonitorSet monitors with the stage's DM and iterate, DM
+// replacement under -snes_grid_sequence, the final report -- can still be exercised end to end if those entry points
+// exist.  This file provides them over host memory: "device" pointers are malloc'ed, the Vec operations are loops, and
+// the solve is the SAME template (p4pdes_b200/csrc/nk_solver.hpp) instantiated with HostCallbackOps of host_ops.hpp.
+// oracle/Makefile links it with the shim source and the reference's minimal.c into oracle/_ref/minimal_shim_host, which
+// tests/test_shim_minimal_cpu.py compares with the reference's golden outputs (c/ch7/output/minimal.test*).
+// The linear fish.c path (p4b_mg_* / p4b_cg_solve) is NOT restated here: those calls fail with an explanatory error.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/p4b200.h"
+#include "host_ops.hpp"
+#include "nk_solver.hpp"
+
+using namespace p4b;
+
+static char g_err[512] = "";
+static int fail(int code, const char *msg) {
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return code;
+}
+
+struct p4b_ctx { int unused; };
+
+extern "C" {
+
+const char *p4b_last_error(void) { return g_err; }
+long long p4b_launch_count(void) { return 0; }
+int p4b_ctx_create(int, void *, p4b_ctx **ctx) { *ctx = new p4b_ctx{0}; return 0; }
+int p4b_ctx_destroy(p4b_ctx *ctx) { delete ctx; return 0; }
+int p4b_malloc(p4b_ctx *, size_t bytes, void **dptr) { *dptr = malloc(bytes ? bytes : 1); return *dptr ? 0 : 55; }
+int p4b_free(p4b_ctx *, void *dptr) { free(dptr); return 0; }
+int p4b_memcpy_h2d(p4b_ctx *, void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
+int p4b_memcpy_d2h(p4b_ctx *, void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
+
+int p4b_vec_dot(p4b_ctx *, size_t n, const double *x, const double *y, double *r) { HostOps o; *r = o.dot(n, x, y); return 0; }
+int p4b_vec_norm2(p4b_ctx *, size_t n, const double *x, double *r) { HostOps o; *r = o.norm2(n, x); return 0; }
+int p4b_vec_norminf(p4b_ctx *, size_t n, const double *x, double *r) { HostOps o; *r = o.norminf(n, x); return 0; }
+int p4b_vec_axpy(p4b_ctx *, size_t n, double a, const double *x, double *y) { HostOps o; o.axpy(n, a, x, y); return 0; }
+int p4b_vec_aypx(p4b_ctx *, size_t n, double a, const double *x, double *y) { HostOps o; o.aypx(n, a, x, y); return 0; }
+
+int p4b_minimal_default_opts(p4b_minimal_opts *o) {
+    static_assert(sizeof(p4b_minimal_opts) == sizeof(nk::MinimalOpts), "p4b_minimal_opts and nk::MinimalOpts must agree");
+    nk::default_opts(reinterpret_cast<nk::MinimalOpts *>(o));
+    return 0;
+}
+
+int p4b_snes2d_solve_monitored(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_residual2d_fn residual, p4b_monitor2d_fn monitor,
+                               void *user, const double *u0_host, p4b_line_fn line, void *line_ctx, double *u_out_host,
+                               size_t u_capacity, p4b_minimal_result *result) {
+    static_assert(sizeof(p4b_minimal_result) == sizeof(nk::MinimalResult), "p4b_minimal_result and nk::MinimalResult must agree");
+    if (!c || !opts || !residual || !u0_host || !result) return fail(62, "p4b_snes2d_solve: null argument");
+    const nk::MinimalOpts &o = *reinterpret_cast<const nk::MinimalOpts *>(opts);
+    if (o.grid_x < 3 || o.grid_y < 3) return fail(60, "grid needs at least 3 nodes per dimension");
+    HostCallbackOps ops;
+    ops.fn = residual;
+    ops.mon = monitor;
+    ops.user = user;
+    nk::Printer pr{line, line_ctx};
+    double *u = nullptr;
+    nk::MinimalResult &R = *reinterpret_cast<nk::MinimalResult *>(result);
+    int rc = nk::minimal_solve(&ops, o, pr, u_out_host ? &u : nullptr, &R, u0_host, false);
+    if (!rc && ops.error()) rc = ops.error();
+    if (!rc && u_out_host) {
+        const size_t n = (size_t)R.mx * R.my;
+        if (u_capacity < n) rc = 63;
+        else memcpy(u_out_host, u, sizeof(double) * n);
+    }
+    if (u) ops.release(u);
+    if (rc == 61) return fail(61, "base grid of the multigrid hierarchy is larger than 65 x 65: use a coarser base grid");
+    if (rc == 62) return fail(62, "base-grid Jacobian is singular");
+    if (rc == 63) return fail(63, "u_out is too small for the final grid");
+    if (rc == 65) return fail(65, "the residual callback returned an error");
+    if (rc == 66) return fail(66, "the monitor callback returned an error");
+    if (rc) return fail(rc, "p4b_snes2d_solve failed");
+    return 0;
+}
+
+// ---- the linear (fish.c) path is not restated on the host ----
+int p4b_mg_default_opts(p4b_mg_opts *o) { memset(o, 0, sizeof *o); return 0; }
+int p4b_mg_create_stencil(p4b_ctx *, const p4b_grid *, const p4b_mg_opts *, const double *, int, p4b_mg **) {
+    return fail(56, "host stand-in: the fish.c multigrid path needs the CUDA library");
+}
+int p4b_mg_destroy(p4b_mg *) { return 0; }
+int p4b_mg_matmult(p4b_mg *, const double *, double *) { return fail(56, "host stand-in: no MatMult"); }
+int p4b_cg_solve(p4b_mg *, int, const double *, double *, double, double, int, p4b_ksp_result *) {
+    return fail(56, "host stand-in: no KSPSolve");
+}
+
+}  // extern "C"

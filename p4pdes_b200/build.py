@@ -72,7 +72,8 @@ SHIM_SRC = os.path.join(HERE, "shim", "petscshim.c")
 BINDIR = os.path.join(HERE, "bin")
 REFERENCE = os.environ.get("P4B_REFERENCE", "/root/reference")
 # the reference's unchanged drivers and the files each one is made of (c/ch6/makefile:5-7)
-DRIVERS = {"fish": ["c/ch6/fish.c", "c/ch6/poissonfunctions.c"]}
+DRIVERS = {"fish": ["c/ch6/fish.c", "c/ch6/poissonfunctions.c"],
+           "minimal": ["c/ch7/minimal.c", "c/ch6/poissonfunctions.c"]}
 
 
 def build_shim(force=False):

@@ -4,8 +4,8 @@
 // Jacobian of FormFunctionLocal (c/ch7/minimal.c:210-282) column group by column group: the DMDA BOX stencil of width
 // 1 is coloured with 3 x 3 = 9 colours, colour(i,j) = (i mod 3) + 3 (j mod 3), no row of the matrix meets two columns
 // of one colour, so ONE residual evaluation with every node of a colour perturbed yields all those columns:
-//     dx_m   = eps * x_m            if |x_m| >= umin,   eps * umin * sign(x_m) otherwise   (eps = sqrt(DBL_EPSILON),
-//     J_nm   = (F(x + dx e_colour)_n - F(x)_n) / dx_m                                       umin = 1e-6: MatFDColoring "ds")
+//     h      = sqrt(DBL_EPSILON) * sqrt(1 + ||x||_2)        (MatFDColoring's default differencing "wp": one step for
+//     J_nm   = (F(x + h e_colour)_n - F(x)_n) * (1 / h)      every column; pinned by c/ch7/output/minimal.test1, see below)
 // Here that is nine launches of the device residual plus a perturb and an extract kernel each; nothing leaves HBM.
 //
 // The matrix is kept in the layout a structured-grid Jacobian has on a GPU ("stencil9"): nine coefficient planes
@@ -21,24 +21,23 @@
 
 namespace p4b {
 
-__device__ __forceinline__ double fd_dx(double x) {
-    const double eps = 1.4901161193847656e-08, umin = 1.0e-6;      // sqrt(DBL_EPSILON), MatFDColoring defaults
-    double dx = x;
-    if (fabs(dx) < umin) dx = (dx < 0.0 ? -1.0 : 1.0) * umin;
-    return dx * eps;
-}
+// [PETSc] MatFDColoringApply with its default differencing "wp" (Walker-Pernice): ONE step for every column,
+// h = sqrt(DBL_EPSILON) * sqrt(1 + ||u||_2), entries scaled by vscale = 1/h.  (Pinned by c/ch7/output/minimal.test1:
+// every printed digit of its six residual norms is reproduced with this step and with no other candidate; see
+// oracle/minimal_solver_oracle.py.)  ||u||_2 is a reduction: the caller takes it with the library's norm and passes h.
+double fd_step_wp(double unorm) { return 1.4901161193847656e-08 * sqrt(1.0 + unorm); }
 
-__global__ void __launch_bounds__(256) fd_perturb_kernel(int mx, int my, int ci, int cj, const double *__restrict__ u,
+__global__ void __launch_bounds__(256) fd_perturb_kernel(int mx, int my, int ci, int cj, double h, const double *__restrict__ u,
                                                           double *__restrict__ up) {
     const int n = blockIdx.x * 256 + threadIdx.x;
     if (n >= mx * my) return;
     const int j = n / mx, i = n - j * mx;
     const double x = u[n];
-    up[n] = (i % 3 == ci && j % 3 == cj) ? x + fd_dx(x) : x;
+    up[n] = (i % 3 == ci && j % 3 == cj) ? x + h : x;
 }
 
 // the column of colour (ci, cj) that row n meets is its neighbour (i + di, j + dj) with (i+di) mod 3 = ci, ...
-__global__ void __launch_bounds__(256) fd_extract_kernel(int mx, int my, int ci, int cj, const double *__restrict__ u,
+__global__ void __launch_bounds__(256) fd_extract_kernel(int mx, int my, int ci, int cj, double vscale,
                                                           const double *__restrict__ F0, const double *__restrict__ Fp,
                                                           double *__restrict__ vals) {
     const int n = blockIdx.x * 256 + threadIdx.x;
@@ -52,35 +51,34 @@ __global__ void __launch_bounds__(256) fd_extract_kernel(int mx, int my, int ci,
     if (dj < -1) dj += 3;
     const int ii = i + di, jj = j + dj;
     if (ii < 0 || ii >= mx || jj < 0 || jj >= my) return;
-    const int m = jj * mx + ii;
-    const double vscale = 1.0 / fd_dx(u[m]);
     vals[(size_t)(3 * (dj + 1) + (di + 1)) * N + n] = (Fp[n] - F0[n]) * vscale;
 }
 
 // the two device halves of one colour, for callers whose residual is not a kernel of this library (host callbacks)
-int launch_fd_perturb(cudaStream_t st, int mx, int my, int ci, int cj, const double *u, double *up) {
-    fd_perturb_kernel<<<(unsigned)((mx * my + 255) / 256), 256, 0, st>>>(mx, my, ci, cj, u, up);
+int launch_fd_perturb(cudaStream_t st, int mx, int my, int ci, int cj, double h, const double *u, double *up) {
+    fd_perturb_kernel<<<(unsigned)((mx * my + 255) / 256), 256, 0, st>>>(mx, my, ci, cj, h, u, up);
     P4B_LAUNCH_CHECK();
     return 0;
 }
-int launch_fd_extract(cudaStream_t st, int mx, int my, int ci, int cj, const double *u, const double *F0, const double *Fp,
+int launch_fd_extract(cudaStream_t st, int mx, int my, int ci, int cj, double h, const double *F0, const double *Fp,
                       double *vals) {
-    fd_extract_kernel<<<(unsigned)((mx * my + 255) / 256), 256, 0, st>>>(mx, my, ci, cj, u, F0, Fp, vals);
+    fd_extract_kernel<<<(unsigned)((mx * my + 255) / 256), 256, 0, st>>>(mx, my, ci, cj, 1.0 / h, F0, Fp, vals);
     P4B_LAUNCH_CHECK();
     return 0;
 }
 
-int fd_jacobian_minimal(cudaStream_t st, int mx, int my, double q, const double *u, const double *g, const double *F0,
-                        double *vals, double *up, double *Fp) {
+int fd_jacobian_minimal(cudaStream_t st, int mx, int my, double q, double unorm, const double *u, const double *g,
+                        const double *F0, double *vals, double *up, double *Fp) {
     const int N = mx * my;
     const unsigned nb = (unsigned)((N + 255) / 256);
+    const double h = fd_step_wp(unorm), vscale = 1.0 / h;
     P4B_CUDA(cudaMemsetAsync(vals, 0, sizeof(double) * 9 * (size_t)N, st));
     for (int cj = 0; cj < 3; cj++)
         for (int ci = 0; ci < 3; ci++) {
-            fd_perturb_kernel<<<nb, 256, 0, st>>>(mx, my, ci, cj, u, up);
+            fd_perturb_kernel<<<nb, 256, 0, st>>>(mx, my, ci, cj, h, u, up);
             P4B_LAUNCH_CHECK();
             P4B_CHECK(launch_minimal_function(st, mx, my, 0, my, q, up, g, Fp));
-            fd_extract_kernel<<<nb, 256, 0, st>>>(mx, my, ci, cj, u, F0, Fp, vals);
+            fd_extract_kernel<<<nb, 256, 0, st>>>(mx, my, ci, cj, vscale, F0, Fp, vals);
             P4B_LAUNCH_CHECK();
         }
     return 0;

@@ -94,10 +94,12 @@ void sell_free(Sell *A);
 void sell_info(const Sell *A, int *nrows, long long *nnz, long long *padded);
 
 // assembled 2-D 9-point Jacobians (assembled.cu): stencil9 layout vals[s*N + n], s = 3(dj+1) + (di+1)
-int fd_jacobian_minimal(cudaStream_t st, int mx, int my, double q, const double *u, const double *g, const double *F0,
-                        double *vals, double *up, double *Fp);
-int launch_fd_perturb(cudaStream_t st, int mx, int my, int ci, int cj, const double *u, double *up);
-int launch_fd_extract(cudaStream_t st, int mx, int my, int ci, int cj, const double *u, const double *F0, const double *Fp,
+// differencing step h = fd_step_wp(||u||_2), the same for every column ([PETSc] MatFDColoring "wp")
+double fd_step_wp(double unorm);
+int fd_jacobian_minimal(cudaStream_t st, int mx, int my, double q, double unorm, const double *u, const double *g,
+                        const double *F0, double *vals, double *up, double *Fp);
+int launch_fd_perturb(cudaStream_t st, int mx, int my, int ci, int cj, double h, const double *u, double *up);
+int launch_fd_extract(cudaStream_t st, int mx, int my, int ci, int cj, double h, const double *F0, const double *Fp,
                       double *vals);
 int launch_stencil9_apply(cudaStream_t st, int mx, int my, const double *vals, const double *x, double *y);
 int launch_pattern_jac(cudaStream_t st, int mode, int mx, int my, double Cu, double Cv, double shift, double phi,

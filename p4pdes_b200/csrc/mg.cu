@@ -1641,10 +1641,11 @@ int p4b_pattern_inject(p4b_ctx *c, int Mx, int My, const double *yf, double *yc)
 int p4b_minimal_jacobian_fd(p4b_ctx *c, int mx, int my, double q, const double *u, const double *g, const double *F0,
                             double *vals9) {
     if (mx < 3 || my < 3) return fail(60, "minimal Jacobian: grid must be at least 3 x 3");
-    double *tmp = nullptr;
+    double *tmp = nullptr, unorm = 0.0;
     const size_t N = (size_t)mx * my;
+    P4B_CHECK(p4b_vec_norm2(c, N, u, &unorm));                 // the "wp" differencing step depends on ||u||_2
     P4B_CUDA(cudaMallocAsync((void **)&tmp, sizeof(double) * 2 * N, c->stream));
-    const int rc = fd_jacobian_minimal(c->stream, mx, my, q, u, g, F0, vals9, tmp, tmp + N);
+    const int rc = fd_jacobian_minimal(c->stream, mx, my, q, unorm, u, g, F0, vals9, tmp, tmp + N);
     cudaFreeAsync(tmp, c->stream);
     return rc;
 }

@@ -62,6 +62,7 @@ struct DeviceOps {
         return r;
     }
     void inject2d(int cmx, int cmy, const double *uf, double *uc) { chk(p4b_inject2d(c, cmx, cmy, uf, uc)); }
+    void user_monitor(int, int, int, double, int, const double *) {}      // only the callback form has one (CallbackOps)
     static p4b_grid grid2d(int mx, int my) {
         p4b_grid g;
         g.dim = 2; g.mx = mx; g.my = my; g.mz = 1;
@@ -110,8 +111,18 @@ struct DeviceOps {
 struct CallbackOps : DeviceOps {
     p4b_residual2d_fn fn = nullptr;
     void *user = nullptr;
+    p4b_monitor2d_fn mon = nullptr;
     std::vector<double> hu, hF;
-    CallbackOps(p4b_ctx *c_, cudaStream_t st_, p4b_residual2d_fn f, void *u) : DeviceOps{c_, st_}, fn(f), user(u) {}
+    CallbackOps(p4b_ctx *c_, cudaStream_t st_, p4b_residual2d_fn f, p4b_monitor2d_fn m, void *u)
+        : DeviceOps{c_, st_}, fn(f), user(u), mon(m) {}
+    // [PETSc] SNESMonitorSet (c/ch7/minimal.c:144-146): the caller's monitor sees the current iterate on the host
+    void user_monitor(int mx, int my, int its, double fnorm, int tablevel, const double *u) {
+        if (!mon || err) return;
+        const size_t n = (size_t)mx * my;
+        hu.resize(n);
+        to_host(u, hu.data(), n);
+        if (!err && mon(user, mx, my, its, fnorm, tablevel, hu.data())) err = 66;
+    }
     void minimal_sample(int, int, int, double, double, double *) {}
     void minimal_function(int mx, int my, double, const double *u, const double *, double *F) {
         const size_t n = (size_t)mx * my;
@@ -127,12 +138,13 @@ struct CallbackOps : DeviceOps {
     void minimal_jacobian_fd(int mx, int my, double q, const double *u, const double *g, const double *F0, double *vals) {
         const size_t n = (size_t)mx * my;
         double *up = alloc(n), *Fp = alloc(n);
+        const double h = fd_step_wp(norm2(n, u));              // [PETSc] MatFDColoring "wp": one step for every column
         cu(cudaMemsetAsync(vals, 0, sizeof(double) * 9 * n, st));
         for (int cj = 0; cj < 3; cj++)
             for (int ci = 0; ci < 3; ci++) {
-                chk(launch_fd_perturb(st, mx, my, ci, cj, u, up));
+                chk(launch_fd_perturb(st, mx, my, ci, cj, h, u, up));
                 minimal_function(mx, my, q, up, g, Fp);
-                chk(launch_fd_extract(st, mx, my, ci, cj, u, F0, Fp, vals));
+                chk(launch_fd_extract(st, mx, my, ci, cj, h, F0, Fp, vals));
             }
         release(up);
         release(Fp);
@@ -184,10 +196,16 @@ extern "C" int p4b_minimal_solve(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_l
 extern "C" int p4b_snes2d_solve(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_residual2d_fn residual, void *user,
                                 const double *u0_host, p4b_line_fn line, void *line_ctx, double *u_out_host,
                                 size_t u_capacity, p4b_minimal_result *result) {
+    return p4b_snes2d_solve_monitored(c, opts, residual, nullptr, user, u0_host, line, line_ctx, u_out_host, u_capacity, result);
+}
+
+extern "C" int p4b_snes2d_solve_monitored(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_residual2d_fn residual,
+                                          p4b_monitor2d_fn monitor, void *user, const double *u0_host, p4b_line_fn line,
+                                          void *line_ctx, double *u_out_host, size_t u_capacity, p4b_minimal_result *result) {
     if (!c || !opts || !residual || !u0_host || !result) return fail(62, "p4b_snes2d_solve: null argument");
     const nk::MinimalOpts &o = *reinterpret_cast<const nk::MinimalOpts *>(opts);
     if (o.grid_x < 3 || o.grid_y < 3) return fail(60, "grid needs at least 3 nodes per dimension");
-    CallbackOps ops(c, ctx_stream(c), residual, user);
+    CallbackOps ops(c, ctx_stream(c), residual, monitor, user);
     nk::Printer pr{line, line_ctx};
     double *u = nullptr;
     nk::MinimalResult &R = *reinterpret_cast<nk::MinimalResult *>(result);
@@ -204,6 +222,7 @@ extern "C" int p4b_snes2d_solve(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_re
     if (rc == 62) return fail(62, "base-grid Jacobian is singular");
     if (rc == 63) return fail(63, "u_out holds %zu doubles, the final grid needs %d x %d", u_capacity, R.mx, R.my);
     if (rc == 65) return fail(65, "the residual callback returned an error");
+    if (rc == 66) return fail(66, "the monitor callback returned an error");
     if (rc) return fail(rc, "p4b_snes2d_solve failed (%s)", p4b_last_error());
     return 0;
 }

@@ -101,12 +101,14 @@ inline const char *snes_reason_name(int r) {
     return "?";
 }
 
-// printf("%g") of the value rounded to 6 significant digits: how -snes_monitor_short prints norms
+// how -snes_monitor_short prints norms ([PETSc] SNESMonitorDefaultShort): %g above 1e-9, %5.3e down to 1e-11, then
+// "< 1.e-11"  (c/ch7/output/minimal.test1:6 "1.772e-10")
 inline std::string g6(double v) {
-    char a[64], b[64];
-    snprintf(a, sizeof a, "%.6g", v);
-    snprintf(b, sizeof b, "%g", atof(a));
-    return b;
+    char a[64];
+    if (v > 1.0e-9) snprintf(a, sizeof a, "%g", v);
+    else if (v > 1.0e-11) snprintf(a, sizeof a, "%5.3e", v);
+    else snprintf(a, sizeof a, "< 1.e-11");
+    return a;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -467,6 +469,7 @@ int newton(Ops *ops, std::vector<Level<Ops>> &lev, const MinimalOpts &opt, const
         if (opt.snes_monitor == 2) pr.out("%s%3d SNES Function norm %s", pad.c_str(), it, g6(v).c_str());
         else if (opt.snes_monitor == 1) pr.out("%s%3d SNES Function norm %.12e", pad.c_str(), it, v);
     };
+    ops->user_monitor(L.mx, L.my, 0, fnorm, indent, L.u);      // [PETSc] SNESMonitorSet monitors run before -snes_monitor's
     monitor(0, fnorm);
     int reason = 0;
     if (fnorm < opt.snes_atol) reason = SNES_CONVERGED_FNORM_ABS;
@@ -499,7 +502,7 @@ int newton(Ops *ops, std::vector<Level<Ops>> &lev, const MinimalOpts &opt, const
         else k = cg(ops, n, mult, L.F, y, prec, opt.ksp_rtol, 1.0e-50, opt.ksp_max_it, kr, kz, kp, w);
         res->ksp_its[it] = k.its;
         if (opt.ksp_converged_reason)
-            pr.out("%s  Linear solve %s due to %s iterations %d", pad.c_str(), k.converged ? "converged" : "did not converge",
+            pr.out("%s    Linear solve %s due to %s iterations %d", pad.c_str(), k.converged ? "converged" : "did not converge",
                    k.converged ? "CONVERGED_RTOL" : "DIVERGED_ITS", k.its);
         L.mult(y, Jy);
         double gnorm = 0.0, lam = 0.0;
@@ -512,6 +515,7 @@ int newton(Ops *ops, std::vector<Level<Ops>> &lev, const MinimalOpts &opt, const
         fnorm = gnorm;
         it++;
         res->fnorm[it] = fnorm;
+        ops->user_monitor(L.mx, L.my, it, fnorm, indent, L.u);
         monitor(it, fnorm);
         if (fnorm != fnorm) reason = SNES_DIVERGED_FNORM_NAN;
         else if (fnorm < opt.snes_atol) reason = SNES_CONVERGED_FNORM_ABS;
@@ -523,7 +527,7 @@ int newton(Ops *ops, std::vector<Level<Ops>> &lev, const MinimalOpts &opt, const
     res->nksp = it;
     res->reason = reason;
     if (!rc && opt.snes_converged_reason)
-        pr.out("%sNonlinear solve %s due to %s iterations %d", pad.c_str(), reason > 0 ? "converged" : "did not converge",
+        pr.out("%s  Nonlinear solve %s due to %s iterations %d", pad.c_str(), reason > 0 ? "converged" : "did not converge",
                snes_reason_name(reason), it);
     mg.destroy();
     if (dense) ops->release(dense);

@@ -465,10 +465,13 @@ class FishReport:
 
 
 def _snes_short(x):
-    """PETSc's -snes_monitor_short number format: %g with 6 significant digits, '< 1.e-11' below that."""
-    if x < 1e-11:
-        return "< 1.e-11"
-    return "%g" % float("%.6g" % x)
+    """PETSc's -snes_monitor_short number format ([PETSc] SNESMonitorDefaultShort): %g above 1e-9, %5.3e down to
+    1e-11, '< 1.e-11' below that."""
+    if x > 1e-9:
+        return "%g" % x
+    if x > 1e-11:
+        return "%5.3e" % x
+    return "< 1.e-11"
 
 
 def grid_string(g: L.Grid):

@@ -97,6 +97,7 @@ class PatternResult(C.Structure):
 
 LINE_FN = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)
 RESIDUAL2D_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double))
+MONITOR2D_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double))
 
 
 class KernelStat(C.Structure):
@@ -187,6 +188,8 @@ _SIGS = {
     "p4b_minimal_solve": (C.c_int, [_P, C.POINTER(MinimalOpts), LINE_FN, _P, _D, C.c_size_t, C.POINTER(MinimalResult)]),
     "p4b_snes2d_solve": (C.c_int, [_P, C.POINTER(MinimalOpts), RESIDUAL2D_FN, _P, _P, LINE_FN, _P, _P, C.c_size_t,
                                   C.POINTER(MinimalResult)]),
+    "p4b_snes2d_solve_monitored": (C.c_int, [_P, C.POINTER(MinimalOpts), RESIDUAL2D_FN, MONITOR2D_FN, _P, _P, LINE_FN, _P, _P,
+                                            C.c_size_t, C.POINTER(MinimalResult)]),
     "p4b_pattern_default_opts": (C.c_int, [C.POINTER(PatternOpts)]),
     "p4b_pattern_solve": (C.c_int, [_P, C.POINTER(PatternOpts), LINE_FN, _P, _D, C.c_size_t, C.POINTER(PatternResult)]),
     "p4b_sell_create": (C.c_int, [_P, C.c_int, _P, _P, _P, C.POINTER(_P)]),

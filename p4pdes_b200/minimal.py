@@ -462,8 +462,8 @@ def newton(ops, levels, opt: MinimalOptions, out, indent=0) -> SNESResult:
             k = cg(ops, L.mult, L.F, y, precond, opt.ksp_rtol, max_it=opt.ksp_max_it)
         res.ksp_its.append(k.its)
         if opt.ksp_converged_reason:
-            out("%s  Linear solve %s due to %s iterations %d" % (pad, "converged" if k.reason.startswith("CONV")
-                                                                   else "did not converge", k.reason, k.its))
+            out("%s    Linear solve %s due to %s iterations %d" % (pad, "converged" if k.reason.startswith("CONV")
+                                                                     else "did not converge", k.reason, k.its))
         L.mult(y, Jy)
         gnorm, lam = linesearch_bt(ops, F, L.u, L.F, fnorm, y, Jy, w, gnew)
         res.lambdas.append(lam)
@@ -486,14 +486,19 @@ def newton(ops, levels, opt: MinimalOptions, out, indent=0) -> SNESResult:
         elif snorm < opt.snes_stol * xnorm:
             res.reason = "CONVERGED_SNORM_RELATIVE"
     if opt.snes_converged_reason:
-        out("%sNonlinear solve %s due to %s iterations %d" % (pad, "converged" if res.reason.startswith("CONV")
-                                                               else "did not converge", res.reason, res.its))
+        out("%s  Nonlinear solve %s due to %s iterations %d" % (pad, "converged" if res.reason.startswith("CONV")
+                                                                 else "did not converge", res.reason, res.its))
     return res
 
 
 def _g6(v):
-    """printf %g with 6 significant digits, the way -snes_monitor_short prints norms."""
-    return "%g" % float("%.6g" % v)
+    """How -snes_monitor_short prints norms ([PETSc] SNESMonitorDefaultShort): %g above 1e-9, %5.3e down to 1e-11, then
+    '< 1.e-11' (c/ch7/output/minimal.test1:6 "1.772e-10")."""
+    if v > 1.0e-9:
+        return "%g" % v
+    if v > 1.0e-11:
+        return "%5.3e" % v
+    return "< 1.e-11"
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -1,6 +1,6 @@
 /* petscshim.c -- the PETSc-shaped host layer behind include/petsc.h (C99, NOT PETSc).
  *
- * Lets the reference's unchanged drivers (c/ch6/fish.c + c/ch6/poissonfunctions.c) run on a B200:
+ * Lets the reference's unchanged drivers (c/ch6/fish.c, c/ch7/minimal.c + c/ch6/poissonfunctions.c) run on a B200:
  * objects are thin host structs; every numerical operation of the solve goes through the C ABI of
  * include/p4b200.h into the CUDA kernels.  What runs on the host is what the reference itself runs
  * on the host: option parsing, the user's FormFunctionLocal / FormJacobianLocal callbacks (called
@@ -201,7 +201,7 @@ PetscErrorCode PetscOptionsEnum(const char opt[], const char text[], const char 
 /* objects                                                                                          */
 /* ------------------------------------------------------------------------------------------------ */
 struct _p_DM {
-    int dim, M[3], dof, sw, refine, setup, refct;
+    int dim, M[3], M0[3], dof, sw, refine, setup, refct;   /* M0: the grid before -da_refine (the multigrid base) */
     DMBoundaryType b[3];
     DMDAStencilType st;
     double cmin[3], cmax[3];
@@ -258,6 +258,15 @@ struct _p_SNES {
     struct _p_KSP ksp;
     Vec sol;
     int monitor, monitor_short, converged_reason_flag, its;
+    /* newtonls (minimal.c): tolerances, Jacobian source, grid sequencing, SNESMonitorSet monitors */
+    double rtol, atol, stol;
+    int max_it, fd_color, grid_sequence, gmres_restart, tablevel, reason;
+    struct {
+        PetscErrorCode (*f)(SNES, PetscInt, PetscReal, void *);
+        void *ctx;
+        PetscErrorCode (*destroy)(void **);
+    } mon[5];
+    int nmon;
 };
 
 /* ---- registries ---- */
@@ -361,6 +370,7 @@ PetscErrorCode DMSetFromOptions(DM dm) {
 }
 PetscErrorCode DMSetUp(DM dm) {
     if (dm->setup) return 0;
+    memcpy(dm->M0, dm->M, sizeof dm->M0);
     for (int i = 0; i < dm->dim; i++)       /* -da_refine n, non-periodic: M <- 1 + 2^n (M-1)   */
         dm->M[i] = 1 + (1 << dm->refine) * (dm->M[i] - 1);
     dm->setup = 1;
@@ -427,6 +437,26 @@ PetscErrorCode DMRestoreGlobalVector(DM dm, Vec *g) {
         if (dm->pool[i] == *g) { dm->pool_busy[i] = 0; *g = NULL; return 0; }
     SHIM_ERR(62, "vector was not obtained with DMGetGlobalVector");
 }
+/* one logical rank on a non-periodic DMDA: the ghosted local vector IS the global one */
+PetscErrorCode DMGetLocalVector(DM dm, Vec *l) { return vec_new(dm, l); }
+static void vec_free(Vec v);
+PetscErrorCode DMRestoreLocalVector(DM dm, Vec *l) {
+    (void)dm;
+    if (l && *l) { vec_free(*l); *l = NULL; }
+    return 0;
+}
+static PetscErrorCode vec_to_host(Vec v);
+PetscErrorCode DMGlobalToLocalBegin(DM dm, Vec g, InsertMode mode, Vec l) {
+    (void)dm;
+    if (mode != INSERT_VALUES) SHIM_ERR(56, "DMGlobalToLocal: INSERT_VALUES only");
+    if (g->n != l->n) SHIM_ERR(75, "DMGlobalToLocal: incompatible vector sizes");
+    PetscCall(vec_to_host(g));
+    memcpy(l->h, g->h, g->n * sizeof(double));
+    l->valid = LOC_HOST;
+    return 0;
+}
+PetscErrorCode DMGlobalToLocalEnd(DM dm, Vec g, InsertMode mode, Vec l) { (void)dm; (void)g; (void)mode; (void)l; return 0; }
+
 static void vec_free(Vec v) {
     if (!v) return;
     if (v->d && g_ctx) p4b_free(g_ctx, v->d);
@@ -694,6 +724,7 @@ PetscErrorCode SNESCreate(MPI_Comm comm, SNES *snes) {
     s->ksp.pc.levels = 0; s->ksp.pc.cycle = P4B_CYCLE_V; s->ksp.pc.smoother = P4B_SMOOTH_CHEBYSHEV;
     s->ksp.pc.smooth_its = 2; s->ksp.pc.est_lo = 0.1; s->ksp.pc.est_hi = 1.1; s->ksp.pc.fuse = 1;
     snprintf(s->ksp.pc.levels_pc, 32, "sor");        /* PETSc's default level smoother PC */
+    s->rtol = 1e-8; s->atol = 1e-50; s->stol = 1e-8; s->max_it = 50; s->gmres_restart = 30;   /* [PETSc] SNES defaults */
     *snes = s;
     return 0;
 }
@@ -747,17 +778,27 @@ PetscErrorCode SNESSetFromOptions(SNES snes) {
     snes->monitor_short = opt_has("-snes_monitor_short");
     snes->monitor = opt_has("-snes_monitor");
     snes->converged_reason_flag = opt_has("-snes_converged_reason");
-    if (opt_has("-snes_grid_sequence")) SHIM_ERR(56, "-snes_grid_sequence is not provided by the shim yet");
-    if (opt_has("-snes_fd_color") || opt_has("-snes_mf_operator") || opt_has("-snes_mf"))
-        SHIM_ERR(56, "-snes_fd_color / -snes_mf* are not provided by the shim (analytic Jacobian callback only)");
+    if ((v = opt_value("-snes_rtol"))) snes->rtol = strtod(v, NULL);
+    if ((v = opt_value("-snes_atol"))) snes->atol = strtod(v, NULL);
+    if ((v = opt_value("-snes_stol"))) snes->stol = strtod(v, NULL);
+    if ((v = opt_value("-snes_max_it"))) snes->max_it = atoi(v);
+    if ((v = opt_value("-ksp_gmres_restart"))) snes->gmres_restart = atoi(v);
+    if ((v = opt_value("-snes_grid_sequence"))) snes->grid_sequence = atoi(v);
+    snes->fd_color = opt_bool("-snes_fd_color", 0);
+    if (opt_has("-snes_mf_operator") || opt_has("-snes_mf"))
+        SHIM_ERR(56, "-snes_mf_operator / -snes_mf are not provided by the shim (Jacobians: the analytic callback for "
+                     "ksponly, -snes_fd_color for newtonls)");
+    if (!strcmp(snes->type, SNESKSPONLY) && (snes->fd_color || snes->grid_sequence))
+        SHIM_ERR(56, "-snes_fd_color / -snes_grid_sequence are provided for -snes_type newtonls only");
     if (opt_has("-pc_mg_galerkin")) SHIM_ERR(56, "-pc_mg_galerkin is not provided (levels are rediscretised, fish.c:7)");
     return 0;
 }
 
 static void print_snes_norm(SNES snes, int it, double fnorm) {
     if (snes->monitor_short) {
-        if (fnorm < 1e-11) printf("  %d SNES Function norm < 1.e-11\n", it);
-        else printf("  %d SNES Function norm %g\n", it, fnorm);
+        if (fnorm > 1e-9) printf("  %d SNES Function norm %g\n", it, fnorm);              /* SNESMonitorDefaultShort */
+        else if (fnorm > 1e-11) printf("  %d SNES Function norm %5.3e\n", it, fnorm);
+        else printf("  %d SNES Function norm < 1.e-11\n", it);
     } else if (snes->monitor) {
         printf("  %d SNES Function norm %14.12e\n", it, fnorm);
     }
@@ -790,10 +831,188 @@ static const char *reason_name(int r) {
     }
 }
 
+/* ---- SNESNEWTONLS: the callback-contract solve of the C ABI (p4b_snes2d_solve_monitored) --------------------------
+ * What c/ch7/minimal.c:134-162 sets up -- a 2-D DMDA, FormFunctionLocal registered with DMDASNESSetFunctionLocal,
+ * optionally a monitor -- becomes one library call: Newton + bt line search, GMRES/CG, multigrid on finite-difference
+ * coloured Jacobians of the user's residual, -snes_grid_sequence; vectors and algebra on the device, the user's
+ * callbacks on the host, called as PETSc calls them (whole grid of one logical rank, a[j][i] views). */
+static SNES g_mon_snes = NULL;            /* the SNES whose monitors are running (PetscObjectGetTabLevel) */
+
+static int newton_residual(void *user, int mx, int my, const double *u, double *F) {
+    SNES snes = (SNES)user;
+    DM dm = snes->dm;
+    struct _p_DM cd = *dm;                /* the DMDA of this level / grid-sequence stage: same box, mx x my nodes */
+    cd.M[0] = mx; cd.M[1] = my; cd.M[2] = 1;
+    memset(cd.pool, 0, sizeof cd.pool);
+    memset(cd.pool_busy, 0, sizeof cd.pool_busy);
+    DMDALocalInfo info;
+    const double t0 = wall();
+    if (DMDAGetLocalInfo(&cd, &info)) return 1;
+    void *au = make_tables(2, cd.M, (double *)u), *aF = make_tables(2, cd.M, F);
+    PetscErrorCode rc = dm->func(&info, au, aF, dm->funcctx);
+    free(au);
+    free(aF);
+    g_t_func += wall() - t0;
+    return (int)rc;
+}
+
+static int newton_monitor(void *user, int mx, int my, int its, double fnorm, int tablevel, const double *u) {
+    SNES snes = (SNES)user;
+    if (!snes->nmon) return 0;
+    /* SNESGetDM / SNESGetSolution inside a monitor give the current stage's grid and iterate (minimal.c:300-309) */
+    struct _p_DM cd = *snes->dm;
+    cd.M[0] = mx; cd.M[1] = my; cd.M[2] = 1;
+    memset(cd.pool, 0, sizeof cd.pool);
+    memset(cd.pool_busy, 0, sizeof cd.pool_busy);
+    struct _p_Vec v;
+    memset(&v, 0, sizeof v);
+    v.n = (size_t)mx * my; v.dm = &cd; v.h = (double *)u; v.valid = LOC_HOST;
+    DM save_dm = snes->dm;
+    Vec save_sol = snes->sol;
+    const int save_its = snes->its;
+    snes->dm = &cd; snes->sol = &v; snes->its = its; snes->tablevel = tablevel;
+    g_mon_snes = snes;
+    PetscErrorCode rc = 0;
+    for (int i = 0; i < snes->nmon && !rc; i++) rc = snes->mon[i].f(snes, its, fnorm, snes->mon[i].ctx);
+    g_mon_snes = NULL;
+    snes->dm = save_dm; snes->sol = save_sol; snes->its = save_its; snes->tablevel = 0;
+    free(v.tables);
+    for (int i = 0; i < 8; i++) vec_free(cd.pool[i]);
+    fflush(stdout);
+    return (int)rc;
+}
+
+static void newton_line(const char *line, void *ctx) { (void)ctx; puts(line); }
+
+static PetscErrorCode snes_solve_newtonls(SNES snes, Vec x) {
+    KSP ksp = &snes->ksp;
+    PC pc = &ksp->pc;
+    DM dm = snes->dm;
+    if (!dm || !dm->func) SHIM_ERR(73, "no residual callback: call DMDASNESSetFunctionLocal()");
+    if (dm->dim != 2 || dm->dof != 1)
+        SHIM_ERR(56, "-snes_type newtonls is provided for 2-D DMDAs with one degree of freedom (minimal.c); "
+                     "fish.c is linear: -snes_type ksponly (fish.c:230-231)");
+    if (!snes->fd_color)
+        SHIM_ERR(56, "newtonls needs the Jacobian of the registered residual: pass -snes_fd_color (minimal.c:141-142: the "
+                     "Jacobian callback registered there is Poisson's, 'thus ONLY APPROXIMATE')");
+    p4b_minimal_opts o;
+    P4B(p4b_minimal_default_opts(&o));
+    if (!strcmp(ksp->type, KSPGMRES)) o.ksp_type = 0;
+    else if (!strcmp(ksp->type, KSPCG)) o.ksp_type = 1;
+    else SHIM_ERR(56, "-ksp_type: gmres and cg are provided on the device path");
+    if (!pc->type[0])
+        SHIM_ERR(56, "PETSc's default PC (ILU(0) on one rank) is sequential and not provided on the device: "
+                     "pass -pc_type mg or -pc_type none");
+    if (!strcmp(pc->type, PCMG)) o.pc_type = 1;
+    else if (!strcmp(pc->type, PCNONE)) o.pc_type = 0;
+    else SHIM_ERR(56, "newtonls: -pc_type mg and -pc_type none are provided");
+    if (o.pc_type == 1) {
+        if (strcmp(pc->levels_pc, "jacobi"))
+            SHIM_ERR(56, "PCMG's default level smoother PC (SOR) is sequential and not provided on the device: "
+                         "pass -mg_levels_pc_type jacobi");
+        if (pc->smoother != P4B_SMOOTH_CHEBYSHEV) SHIM_ERR(56, "newtonls: the level smoother is chebyshev + jacobi");
+        if (pc->cycle != P4B_CYCLE_V) SHIM_ERR(56, "newtonls: -pc_mg_cycle_type v only");
+    }
+    o.grid_x = dm->M0[0]; o.grid_y = dm->M0[1]; o.refine = dm->refine;
+    o.grid_sequence = snes->grid_sequence;
+    o.ksp_rtol = ksp->rtol; o.ksp_max_it = ksp->max_it; o.gmres_restart = snes->gmres_restart;
+    o.mg_levels = pc->levels; o.smooth_its = pc->smooth_its;
+    o.snes_rtol = snes->rtol; o.snes_stol = snes->stol; o.snes_atol = snes->atol; o.snes_max_it = snes->max_it;
+    o.snes_monitor = snes->monitor_short ? 2 : (snes->monitor ? 1 : 0);
+    o.snes_converged_reason = snes->converged_reason_flag;
+    o.ksp_converged_reason = ksp->converged_reason_flag;
+    PetscCall(ensure_ctx());
+    const double t0 = wall();
+    PetscCall(vec_to_host(x));
+    int fx = dm->M[0], fy = dm->M[1];
+    for (int k = 0; k < snes->grid_sequence; k++) { fx = 2 * fx - 1; fy = 2 * fy - 1; }
+    const size_t nf = (size_t)fx * fy;
+    double *uf = (double *)malloc(sizeof(double) * nf);
+    if (!uf) SHIM_ERR(55, "out of host memory for the solution");
+    p4b_minimal_result *R = (p4b_minimal_result *)calloc(1, sizeof *R);
+    fflush(stdout);
+    int rc = p4b_snes2d_solve_monitored(g_ctx, &o, newton_residual, snes->nmon ? newton_monitor : NULL, snes, x->h,
+                                        newton_line, NULL, uf, nf, R);
+    fflush(stdout);
+    g_t_snes += wall() - t0;
+    if (rc) {
+        free(uf);
+        free(R);
+        return PetscShimError(PETSC_COMM_SELF, __LINE__, __func__, __FILE__, rc, p4b_last_error());
+    }
+    snes->its = R->stage[R->nstages - 1].its;
+    snes->reason = R->stage[R->nstages - 1].reason;
+    ksp->its = snes->its ? R->stage[R->nstages - 1].ksp_its[snes->its - 1] : 0;
+    /* under -snes_grid_sequence the SNES ends up with the refined DM and a solution on it: the caller fetches both
+     * with SNESGetDM / SNESGetSolution (minimal.c:161-165) */
+    if (R->mx != dm->M[0] || R->my != dm->M[1]) {
+        DM fine = (DM)malloc(sizeof *fine);
+        *fine = *dm;
+        fine->M[0] = R->mx; fine->M[1] = R->my;
+        fine->refine = dm->refine + snes->grid_sequence;
+        fine->refct = 1;
+        memset(fine->pool, 0, sizeof fine->pool);
+        memset(fine->pool_busy, 0, sizeof fine->pool_busy);
+        vec_free(snes->sol);
+        snes->sol = NULL;
+        DM old = dm;
+        DMDestroy(&old);                      /* the SNES's reference; the caller still holds (and destroys) its own */
+        snes->dm = dm = fine;
+    }
+    if (snes->sol && snes->sol->n != nf) { vec_free(snes->sol); snes->sol = NULL; }
+    if (!snes->sol) PetscCall(vec_new(dm, &snes->sol));
+    memcpy(snes->sol->h, uf, sizeof(double) * nf);
+    snes->sol->valid = LOC_HOST;
+    if (x->n == nf) {                         /* PETSc's SNESSolve leaves the solution in x as well */
+        memcpy(x->h, uf, sizeof(double) * nf);
+        x->valid = LOC_HOST;
+    }
+    free(uf);
+    free(R);
+    return 0;
+}
+
+PetscErrorCode SNESMonitorSet(SNES snes, PetscErrorCode (*f)(SNES, PetscInt, PetscReal, void *), void *mctx,
+                              PetscErrorCode (*monitordestroy)(void **)) {
+    if (snes->nmon >= 5) SHIM_ERR(63, "too many monitors set");
+    snes->mon[snes->nmon].f = f;
+    snes->mon[snes->nmon].ctx = mctx;
+    snes->mon[snes->nmon].destroy = monitordestroy;
+    snes->nmon++;
+    return 0;
+}
+
+/* ---- what a monitor uses to print (minimal.c:333-343): one rank, stdout ---- */
+struct _p_PetscViewer { int tab; };
+static struct _p_PetscViewer g_stdout_viewer = {0};
+PetscViewer PETSC_VIEWER_STDOUT_(MPI_Comm comm) { (void)comm; return &g_stdout_viewer; }
+PetscErrorCode PetscViewerASCIIAddTab(PetscViewer viewer, PetscInt tabs) { viewer->tab += tabs; return 0; }
+PetscErrorCode PetscViewerASCIISubtractTab(PetscViewer viewer, PetscInt tabs) { viewer->tab -= tabs; return 0; }
+PetscErrorCode PetscViewerASCIIPrintf(PetscViewer viewer, const char format[], ...) {
+    va_list ap;
+    for (int i = 0; i < viewer->tab; i++) fputs("  ", stdout);
+    va_start(ap, format);
+    vprintf(format, ap);
+    va_end(ap);
+    return 0;
+}
+PetscErrorCode PetscObjectGetComm(PetscObject obj, MPI_Comm *comm) { (void)obj; *comm = PETSC_COMM_WORLD; return 0; }
+PetscErrorCode PetscObjectGetTabLevel(PetscObject obj, PetscInt *tab) {
+    *tab = (g_mon_snes && (void *)obj == (void *)g_mon_snes) ? g_mon_snes->tablevel : 0;
+    return 0;
+}
+int MPI_Allreduce(const void *sendbuf, void *recvbuf, int count, MPI_Datatype datatype, MPI_Op op, MPI_Comm comm) {
+    (void)op; (void)comm;
+    if (datatype != MPIU_REAL) return 1;
+    memcpy(recvbuf, sendbuf, sizeof(PetscReal) * (size_t)count);     /* one rank: every reduction is the identity */
+    return 0;
+}
+
 PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
     if (b) SHIM_ERR(56, "SNESSolve with a right-hand side is not provided");
+    if (!strcmp(snes->type, SNESNEWTONLS)) return snes_solve_newtonls(snes, x);
     if (strcmp(snes->type, SNESKSPONLY))
-        SHIM_ERR(56, "only -snes_type ksponly is provided by the shim so far (fish.c is linear, fish.c:230-231)");
+        SHIM_ERR(56, "-snes_type: ksponly (fish.c:230-231) and newtonls (minimal.c) are provided by the shim");
     if (strcmp(snes->ksp.type, KSPCG)) SHIM_ERR(56, "only -ksp_type cg is provided on the device path");
     KSP ksp = &snes->ksp;
     PC pc = &ksp->pc;
@@ -934,6 +1153,8 @@ PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
 
 PetscErrorCode SNESDestroy(SNES *snes) {
     if (!snes || !*snes) return 0;
+    for (int i = 0; i < (*snes)->nmon; i++)
+        if ((*snes)->mon[i].destroy) (*snes)->mon[i].destroy(&(*snes)->mon[i].ctx);
     vec_free((*snes)->sol);
     if ((*snes)->dm) { DM d = (*snes)->dm; DMDestroy(&d); }
     free(*snes);

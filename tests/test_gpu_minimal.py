@@ -30,8 +30,8 @@ def dev(ctx, a):
 def test_fd_jacobian_and_stencil9_kernels(ctx, mx, my, problem, q):
     rng = np.random.default_rng(5)
     g = mpo.minimal_g(mx, my, problem, 1.0, 1.1)
-    # entries bounded away from zero: the differencing step is eps*|u_m|, and the rounding noise of F divided by it
-    # is what separates two implementations of the same finite-difference formula
+    # the differencing step is h = sqrt(eps) sqrt(1 + ||u||_2) for every column ("wp"); the rounding noise of F divided
+    # by it is what separates two implementations of the same finite-difference formula
     u = 1.0 + 0.3 * rng.random((my, mx))
     F = lambda w: mpo.minimal_function(w, g, q)
     du, dg, dF = dev(ctx, u), dev(ctx, g), ctx.empty(mx * my)
@@ -42,7 +42,7 @@ def test_fd_jacobian_and_stencil9_kernels(ctx, mx, my, problem, q):
     rp, ci, d = pm.stencil9_to_csr(ctx.to_host(vals), mx, my)
     J = sp.csr_matrix((d, ci, rp), shape=(mx * my, mx * my))
     Jo = mo.fd_jacobian(F, u)
-    # same differencing, same colours: the two differ by the rounding of F (1e-16 relative) divided by dx ~ 1e-8 |u|
+    # same differencing, same colours: the two differ by the rounding of F (1e-16 relative) divided by h ~ 1e-7
     assert abs(J - Jo).max() <= 2e-6 * abs(Jo).max()
     # structure: identity boundary rows, no coupling of interior rows to boundary columns
     bd = np.ones((my, mx), bool)
@@ -117,10 +117,10 @@ def test_device_solve_matches_oracle(ctx, argv, okw):
     r = pm.minimal_main(argv, ctx)
     o = mo.minimal(**okw)
     assert (r.mx, r.my) == (o.mx, o.my)
-    # Newton paths start from a noisy first FD Jacobian (tests/test_minimal_oracle.py): counts within +-1
+    # device and NumPy residuals differ in rounding (rsqrt vs power), the linear solves stop at rtol 1e-5: counts within +-1
     for a, b in zip(r.stages, o.stages):
         assert a.reason == b.reason == "CONVERGED_FNORM_RELATIVE"
-        # (a long globalisation phase -- a cold start on a fine grid takes ~10 damped steps -- amplifies the noise)
+        # (a long globalisation phase -- a cold start on a fine grid takes ~10 damped steps -- amplifies the difference)
         assert abs(a.its - b.its) <= max(1, b.its // 6)
         assert abs(max(a.ksp_its) - max(b.ksp_its)) <= 1
         assert a.fnorms[-1] <= 1e-8 * a.fnorms[0]

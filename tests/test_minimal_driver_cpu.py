@@ -37,9 +37,15 @@ def test_driver_reproduces_golden_lines_of_minimal_test1():
     r = pm.minimal_main("-snes_fd_color -snes_converged_reason -snes_monitor_short -ms_problem catenoid "
                         "-ms_catenoid_c 2.0 -da_refine 1", ops)
     assert r.lines[0] == "  0 SNES Function norm 1.08276"                                   # minimal.test1:1
-    assert r.lines[-2].startswith("Nonlinear solve converged due to CONVERGED_FNORM_RELATIVE iterations ")
+    assert r.lines[-2] == "  Nonlinear solve converged due to CONVERGED_FNORM_RELATIVE iterations 5"   # :7
     assert r.lines[-1] == "done on 5 x 5 grid and problem catenoid:  error |u-uexact|_inf = 1.10603e-04"   # :8
-    assert abs(r.stages[0].its - 5) <= 1
+    # :2-6 -- the golden ran GMRES + ILU(0) to rtol 1e-5; the inexactness of THAT linear solve is visible in the 4th
+    # digit of the norms (exact Newton steps give 0.69662, 0.170628, ...), so another preconditioner agrees to ~5e-3
+    golden = [1.08276, 0.69656, 0.170569, 0.00995652, 2.20675e-05, 1.772e-10]
+    got = [float(l.split()[-1]) for l in r.lines[:6]]
+    assert len(r.lines) == 8
+    np.testing.assert_allclose(got[:5], golden[:5], rtol=1e-2)
+    assert 5.0e-11 < got[5] < 1.0e-9                          # (dominated by the last linear solve's own tolerance)
 
 
 @pytest.mark.parametrize("argv,okw", [

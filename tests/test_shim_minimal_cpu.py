@@ -1,0 +1,111 @@
+"""The reference's UNCHANGED c/ch7/minimal.c through the PETSc-shaped shim (p4pdes_b200/shim/petscshim.c), on the CPU.
+
+oracle/Makefile compiles minimal.c + poissonfunctions.c from where they lie under /root/reference against
+include/petsc.h and links them with the shim source and -- in place of libp4b200.so -- the host stand-in
+oracle/native/p4b_standin.cpp (the SAME solver template over plain loops; test infrastructure).  What is checked is the
+shim's host logic: option handling, the DMDALocalInfo / a[j][i] views it builds around FormFunctionLocal on every level
+and stage, SNESMonitorSet monitors seeing the stage's DM and iterate, the DM / solution replacement under
+-snes_grid_sequence, error behaviour -- against the reference's goldens (tests/golden/minimal_goldens.json).
+The device instantiation of the same binary (p4pdes_b200/bin/minimal) is tests/test_gpu_pending_shim_minimal.py."""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "minimal_goldens.json")))
+EXTRA = " -pc_type mg -mg_levels_pc_type jacobi"      # the device path has no ILU / SOR: name the preconditioner
+
+
+@pytest.fixture(scope="module")
+def exe():
+    path = os.path.join(ROOT, "oracle", "_ref", "minimal_shim_host")
+    if os.path.exists("/root/reference/c/ch7/minimal.c"):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "_ref/minimal_shim_host"])
+    if not os.path.exists(path):
+        pytest.skip("needs the reference tree to compile minimal.c")
+    return path
+
+
+def run(exe, argv, check=True):
+    p = subprocess.run([exe] + argv.split(), capture_output=True, text=True, timeout=120)
+    if check:
+        assert p.returncode == 0, p.stderr
+    return p.stdout.splitlines(), p
+
+
+def test_golden_test4_verbatim(exe):
+    """-snes_fd_color -snes_converged_reason -snes_grid_sequence 2 -ms_problem tent: three stages, tab levels 2, 1, 0."""
+    g = GOLD["minimal.test4"]
+    for extra in (" -pc_type none", EXTRA):
+        lines, _ = run(exe, g["options"] + extra)
+        assert lines == g["lines"]
+
+
+def test_golden_test1(exe):
+    g = GOLD["minimal.test1"]
+    lines, _ = run(exe, g["options"] + " -pc_type none")
+    assert len(lines) == len(g["lines"]) and lines[0] == g["lines"][0] and lines[-2:] == g["lines"][-2:]
+    # the norms in between carry the golden's own ILU(0)/rtol-1e-5 linear solves in the 4th digit (test_minimal_driver_cpu.py)
+    got = [float(l.split()[-1]) for l in lines[1:5]]
+    want = [float(l.split()[-1]) for l in g["lines"][1:5]]
+    np.testing.assert_allclose(got, want, rtol=1e-2)
+    assert re.fullmatch(r"  5 SNES Function norm \d\.\d{3}e-10", lines[5])          # the %5.3e branch of the short monitor
+
+
+def test_golden_test2_structure(exe):
+    g = GOLD["minimal.test2"]
+    lines, _ = run(exe, g["options"] + " -pc_type none")
+    want = [l for l in g["lines"] if not l.startswith("Matrix is symmetric")]      # -mat_is_symmetric is not provided
+    assert len(lines) == len(want) == 3 and lines[-1] == want[-1]
+    assert all(re.fullmatch(r"    Linear solve converged due to CONVERGED_RTOL iterations \d+", l) for l in lines[:2])
+
+
+def test_golden_test3_monitor_lines(exe):
+    """-ms_monitor (SNESMonitorSet(MSEMonitor), minimal.c:144-146,286-345) under -snes_grid_sequence 2 -pc_type mg: the
+    golden ran -snes_mf_operator on 2 ranks; with -snes_fd_color the Newton path is the same to ~1e-7 in the printed
+    areas, and every other character -- tab levels, iteration counts, the lines of the initial, interpolated and
+    converged iterates, the final error -- is identical."""
+    g = GOLD["minimal.test3"]
+    opts = g["options"].replace("-snes_mf_operator", "-snes_fd_color") + " -mg_levels_pc_type jacobi"
+    lines, _ = run(exe, opts)
+    assert len(lines) == len(g["lines"])
+    nexact = 0
+    for a, b in zip(lines, g["lines"]):
+        if "area" in b:
+            fa, fb = [float(x) for x in re.findall(r"[0-9.]+", a)], [float(x) for x in re.findall(r"[0-9.]+", b)]
+            assert a[:a.index("area")] == b[:b.index("area")]                      # PetscViewerASCIIAddTab(tab level)
+            np.testing.assert_allclose(fa, fb, rtol=0, atol=2e-7)
+            nexact += a == b
+        else:
+            assert a == b
+    assert nexact >= 10        # all but the mid-stage iterates, which depend on how the linear systems were solved
+
+
+def test_solution_and_dm_after_grid_sequencing(exe):
+    """minimal.c:161-177 fetches the refined DM and the solution from the SNES: the reported grid and error prove both."""
+    lines, _ = run(exe, "-snes_fd_color -snes_grid_sequence 3 -da_grid_x 5 -da_grid_y 4" + EXTRA)
+    m = re.fullmatch(r"done on (\d+) x (\d+) grid and problem catenoid:  error \|u-uexact\|_inf = (\S+)", lines[-1])
+    assert m and (int(m.group(1)), int(m.group(2))) == (33, 25) and float(m.group(3)) < 2e-4
+    # -da_refine and -snes_grid_sequence reach the same grid and the same discrete solution
+    l2, _ = run(exe, "-snes_fd_color -da_refine 3 -da_grid_x 5 -da_grid_y 4 -snes_rtol 1e-12" + EXTRA)
+    assert abs(float(l2[-1].split()[-1]) - float(m.group(3))) <= 1e-9
+
+
+@pytest.mark.parametrize("argv,code,msg", [
+    ("-pc_type mg -mg_levels_pc_type jacobi", 56, "pass -snes_fd_color"),
+    ("-snes_fd_color", 56, "ILU"),
+    ("-snes_fd_color -pc_type mg", 56, "SOR"),
+    ("-snes_fd_color -pc_type jacobi", 56, "-pc_type mg and -pc_type none"),
+    ("-snes_fd_color -pc_type none -ksp_type bcgs", 56, "gmres and cg"),
+    ("-snes_mf_operator -pc_type none", 56, "not provided"),
+    ("-snes_fd_color -pc_type none -ms_problem tent -ms_exact_init", 2, "only possible for -mse_problem catenoid"),
+    ("-snes_fd_color -pc_type none -ms_catenoid_c 0.5", 3, "c >= 1"),
+    ("-snes_fd_color -pc_type mg -mg_levels_pc_type jacobi -da_grid_x 129 -da_grid_y 129", 61, "65 x 65"),
+])
+def test_error_paths(exe, argv, code, msg):
+    _, p = run(exe, argv, check=False)
+    assert p.returncode == code and msg in p.stderr and "PETSC ERROR" in p.stderr
