@@ -366,6 +366,11 @@ int p4b_pattern_default_opts(p4b_pattern_opts *o);
 /* Y_out (device, may be NULL): the final state, 2*m*m doubles, (u,v) interleaved */
 int p4b_pattern_solve(p4b_ctx *ctx, const p4b_pattern_opts *opts, p4b_line_fn line, void *line_ctx, double *Y_out,
                       size_t Y_capacity, p4b_pattern_result *result);
+/* the same from the CALLER's initial state Y0 (device, 2*m*m doubles; Y_out may alias it): what TSSolve(ts, x) of the
+ * PETSc-shaped shim binds (c/ch5/pattern.c:121-123).  Only the solver's own lines are reported (no banner, no call-back
+ * report: the caller prints those, pattern.c:94-96,127-135).  Y0 = NULL is p4b_pattern_solve. */
+int p4b_pattern_solve_from(p4b_ctx *ctx, const p4b_pattern_opts *opts, const double *Y0, p4b_line_fn line, void *line_ctx,
+                           double *Y_out, size_t Y_capacity, p4b_pattern_result *result);
 typedef struct p4b_sell p4b_sell;
 int p4b_sell_create(p4b_ctx *ctx, int nrows, const int *rowptr_host, const int *colind_host, const double *vals_host,
                     p4b_sell **A);

@@ -1,4 +1,4 @@
-// p4b_standin.cpp -- HOST stand-in for the few C-ABI entry points the PETSc-shaped shim calls on the SNESNEWTONLS path
+// p4b_standin.cpp -- HOST stand-in for the few C-ABI entry points the PETSc-shaped shim calls on the SNESNEWTONLS / TS paths
 // (TEST INFRASTRUCTURE ONLY: never compiled into libp4b200.so, never loaded by the product).
 //
 // p4pdes_b200/shim/petscshim.c runs the reference's unchanged c/ch7/minimal.c by handing its FormFunctionLocal to
@@ -7,8 +7,9 @@
 // replacement under -snes_grid_sequence, the final report -- can still be exercised end to end if those entry points
 // exist.  This file provides them over host memory: "device" pointers are malloc'ed, the Vec operations are loops, and
 // the solve is the SAME template (p4pdes_b200/csrc/nk_solver.hpp) instantiated with HostCallbackOps of host_ops.hpp.
-// oracle/Makefile links it with the shim source and the reference's minimal.c into oracle/_ref/minimal_shim_host, which
-// tests/test_shim_minimal_cpu.py compares with the reference's golden outputs (c/ch7/output/minimal.test*).
+// oracle/Makefile links it with the shim source and the reference's minimal.c / pattern.c into
+// oracle/_ref/{minimal,pattern}_shim_host, which tests/test_shim_minimal_cpu.py / test_shim_pattern_cpu.py compare with
+// the reference's golden outputs (c/ch7/output/minimal.test*, c/ch5/output/pattern.test*).
 // The linear fish.c path (p4b_mg_* / p4b_cg_solve) is NOT restated here: those calls fail with an explanatory error.
 #include <math.h>
 #include <stdio.h>
@@ -18,6 +19,7 @@
 #include "../../include/p4b200.h"
 #include "host_ops.hpp"
 #include "nk_solver.hpp"
+#include "ts_solver.hpp"
 
 using namespace p4b;
 
@@ -80,6 +82,59 @@ int p4b_snes2d_solve_monitored(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_res
     if (rc == 65) return fail(65, "the residual callback returned an error");
     if (rc == 66) return fail(66, "the monitor callback returned an error");
     if (rc) return fail(rc, "p4b_snes2d_solve failed");
+    return 0;
+}
+
+// ---- pattern.c: TSSolve of the shim (identify + verify against these two, then the solve) ----
+int p4b_pattern_ifunction(p4b_ctx *, int mx, int my, double L, double Du, double Dv, const double *Y, const double *Ydot,
+                          double *F) {
+    if (mx != my) return fail(1, "pattern.c requires mx == my");
+    HostOps o;
+    nk::PatternOpts po;
+    nk::default_opts(&po);
+    po.L = L; po.Du = Du; po.Dv = Dv;
+    o.pattern_ifunction(mx, po, Y, Ydot, F);
+    return 0;
+}
+int p4b_pattern_rhsfunction(p4b_ctx *, int mx, int my, double phi, double kappa, const double *Y, double *G) {
+    if (mx != my) return fail(1, "pattern.c requires mx == my");
+    HostOps o;
+    nk::PatternOpts po;
+    nk::default_opts(&po);
+    po.phi = phi; po.kappa = kappa;
+    o.pattern_rhsfunction(mx, po, Y, G);
+    return 0;
+}
+int p4b_pattern_default_opts(p4b_pattern_opts *o) {
+    static_assert(sizeof(p4b_pattern_opts) == sizeof(nk::PatternOpts), "p4b_pattern_opts and nk::PatternOpts must agree");
+    nk::default_opts(reinterpret_cast<nk::PatternOpts *>(o));
+    return 0;
+}
+int p4b_pattern_solve_from(p4b_ctx *c, const p4b_pattern_opts *opts, const double *Y0, p4b_line_fn line, void *line_ctx,
+                           double *Y_out, size_t Y_capacity, p4b_pattern_result *result) {
+    static_assert(sizeof(p4b_pattern_result) == sizeof(nk::PatternResult), "p4b_pattern_result and nk::PatternResult must agree");
+    if (!c || !opts || !result) return fail(62, "p4b_pattern_solve: null argument");
+    const nk::PatternOpts &o = *reinterpret_cast<const nk::PatternOpts *>(opts);
+    if (o.grid_x < 3 || o.grid_y < 3) return fail(60, "periodic grid needs at least 3 nodes per dimension");
+    if ((o.grid_x << o.refine) != (o.grid_y << o.refine)) return fail(1, "pattern.c requires mx == my");
+    if (o.ts_type < nk::TS_ARKIMEX || o.ts_type > nk::TS_CN) return fail(62, "ts_type: arkimex (0), beuler (1), cn (2)");
+    HostOps ops;
+    nk::Printer pr{line, line_ctx};
+    double *Y = nullptr;
+    nk::PatternResult &R = *reinterpret_cast<nk::PatternResult *>(result);
+    int rc = nk::pattern_solve(&ops, o, pr, Y_out ? &Y : nullptr, &R, Y0);
+    if (!rc && ops.error()) rc = ops.error();
+    if (!rc && Y_out) {
+        const size_t n = (size_t)2 * R.m * R.m;
+        if (Y_capacity < n) rc = 63;
+        else memcpy(Y_out, Y, sizeof(double) * n);
+    }
+    if (Y) ops.release(Y);
+    if (rc == 61) return fail(61, "base grid of the periodic hierarchy has more than 512 unknowns: use a coarser -da_grid_x/_y");
+    if (rc == 62) return fail(62, "base-grid stage Jacobian is singular");
+    if (rc == 63) return fail(63, "Y_out is too small for the grid");
+    if (rc == 64) return fail(64, "TSSolve: a nonlinear (stage) solve did not converge");
+    if (rc) return fail(rc, "p4b_pattern_solve failed");
     return 0;
 }
 

@@ -73,7 +73,8 @@ BINDIR = os.path.join(HERE, "bin")
 REFERENCE = os.environ.get("P4B_REFERENCE", "/root/reference")
 # the reference's unchanged drivers and the files each one is made of (c/ch6/makefile:5-7)
 DRIVERS = {"fish": ["c/ch6/fish.c", "c/ch6/poissonfunctions.c"],
-           "minimal": ["c/ch7/minimal.c", "c/ch6/poissonfunctions.c"]}
+           "minimal": ["c/ch7/minimal.c", "c/ch6/poissonfunctions.c"],
+           "pattern": ["c/ch5/pattern.c"]}
 
 
 def build_shim(force=False):

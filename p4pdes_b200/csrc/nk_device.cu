@@ -236,6 +236,11 @@ extern "C" int p4b_pattern_default_opts(p4b_pattern_opts *o) {
 
 extern "C" int p4b_pattern_solve(p4b_ctx *c, const p4b_pattern_opts *opts, p4b_line_fn line, void *line_ctx, double *Y_out,
                                  size_t Y_capacity, p4b_pattern_result *result) {
+    return p4b_pattern_solve_from(c, opts, nullptr, line, line_ctx, Y_out, Y_capacity, result);
+}
+
+extern "C" int p4b_pattern_solve_from(p4b_ctx *c, const p4b_pattern_opts *opts, const double *Y0, p4b_line_fn line,
+                                      void *line_ctx, double *Y_out, size_t Y_capacity, p4b_pattern_result *result) {
     static_assert(sizeof(p4b_pattern_result) == sizeof(nk::PatternResult), "p4b_pattern_result and nk::PatternResult must agree");
     if (!c || !opts || !result) return fail(62, "p4b_pattern_solve: null argument");
     const nk::PatternOpts &o = *reinterpret_cast<const nk::PatternOpts *>(opts);
@@ -246,7 +251,7 @@ extern "C" int p4b_pattern_solve(p4b_ctx *c, const p4b_pattern_opts *opts, p4b_l
     nk::Printer pr{line, line_ctx};
     double *Y = nullptr;
     nk::PatternResult &R = *reinterpret_cast<nk::PatternResult *>(result);
-    int rc = nk::pattern_solve(&ops, o, pr, Y_out ? &Y : nullptr, &R);
+    int rc = nk::pattern_solve(&ops, o, pr, Y_out ? &Y : nullptr, &R, Y0);
     if (!rc && ops.error()) rc = ops.error();
     if (!rc && Y_out) {
         const size_t n = (size_t)2 * R.m * R.m;

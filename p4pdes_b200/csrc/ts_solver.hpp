@@ -265,14 +265,17 @@ inline double match_step(double t, double hnext, double tmax) {
     return out;
 }
 
+// Y0 (optional, Ops memory, 2*m*m doubles): the caller's initial state -- then the run is the caller's (pattern.c under the
+// PETSc-shaped shim prints its own banner and call-back report): only the solver's lines are printed.
 template <class Ops>
-int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **Y_out, PatternResult *R) {
+int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **Y_out, PatternResult *R,
+                  const double *Y0 = nullptr) {
     memset(R, 0, sizeof *R);
     const int mx = opt.grid_x << opt.refine, my = opt.grid_y << opt.refine;      // periodic: -da_refine doubles
     if (mx != my) return 1;                                                      // pattern.c:89
     const int m = mx;
     R->m = m;
-    pr.out("running on %d x %d grid with square cells of side h = %.6f ...", m, m, opt.L / m);      // :94-96
+    if (!Y0) pr.out("running on %d x %d grid with square cells of side h = %.6f ...", m, m, opt.L / m);      // :94-96
     StageOperator<Ops> A;
     A.create(ops, &opt, m, opt.ts_type == TS_ARKIMEX);
     const size_t n = A.lev[0].n;
@@ -282,7 +285,8 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
     double *w = ops->alloc(n), *t1 = ops->alloc(n), *Rv = ops->alloc(n), *d = ops->alloc(n), *Z = ops->alloc(n);
     std::vector<double *> extra;
     auto take = [&]() { double *p = ops->alloc(n); extra.push_back(p); return p; };
-    ops->pattern_initial_state(m, m, opt.L, Y);                                 // :146-179
+    if (Y0) ops->copy(n, Y0, Y);
+    else ops->pattern_initial_state(m, m, opt.L, Y);                            // :146-179
     auto mult = [&](const double *in, double *out) { A.mult(in, out); };
     auto prec = [&](const double *r, double *z) { A.precond(r, z); };
     const double tmax = opt.ts_max_time;
@@ -433,7 +437,7 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
     }
     R->nsteps = k;
     R->t_final = t;
-    if (!rc && opt.call_back_report) {                                          // pattern.c:127-135
+    if (!rc && opt.call_back_report && !Y0) {                                   // pattern.c:127-135
         const char *name = opt.ts_type == TS_ARKIMEX ? "arkimex" : (opt.ts_type == TS_CN ? "cn" : "beuler");
         pr.out("CALL-BACK REPORT");
         pr.out("  solver type: %s", name);

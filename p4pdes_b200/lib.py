@@ -192,6 +192,8 @@ _SIGS = {
                                             C.c_size_t, C.POINTER(MinimalResult)]),
     "p4b_pattern_default_opts": (C.c_int, [C.POINTER(PatternOpts)]),
     "p4b_pattern_solve": (C.c_int, [_P, C.POINTER(PatternOpts), LINE_FN, _P, _D, C.c_size_t, C.POINTER(PatternResult)]),
+    "p4b_pattern_solve_from": (C.c_int, [_P, C.POINTER(PatternOpts), _D, LINE_FN, _P, _D, C.c_size_t,
+                                        C.POINTER(PatternResult)]),
     "p4b_sell_create": (C.c_int, [_P, C.c_int, _P, _P, _P, C.POINTER(_P)]),
     "p4b_sell_spmv": (C.c_int, [_P, _D, _D]),
     "p4b_sell_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

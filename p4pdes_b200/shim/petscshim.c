@@ -210,6 +210,11 @@ struct _p_DM {
     void *funcctx;
     DMDASNESJacobianFn *jac;
     void *jacctx;
+    DMDATSIFunctionLocal ifunc;        /* the TS callback contract (pattern.c:103-114) */
+    DMDATSRHSFunctionLocal rhsfunc;
+    DMDATSIJacobianLocal ijac;
+    DMDATSRHSJacobianLocal rhsjac;
+    void *ifuncctx, *rhsfuncctx, *ijacctx, *rhsjacctx;
     Vec pool[8];
     int pool_busy[8];
 };
@@ -236,6 +241,22 @@ struct _p_Mat {
     int general;        /* 1: the inserted values are NOT such a stencil */
     char why[160];
     int assembled;
+    struct rd_check *rd; /* non-NULL: a TS Jacobian of a 2-component periodic DMDA is being checked (TSSolve) */
+};
+
+/* TS Jacobians (pattern.c:202-318): the rows inserted by the user's FormIJacobianLocal / FormRHSJacobianLocal are
+ * compared, as they arrive, with the stage matrix the device path applies matrix-free,
+ *   IJacobian:    shift I - C_c L9  (diag shift + 20 C_c, edges -4 C_c, corners -C_c, component c couples to c only)
+ *   RHSJacobian:  the pointwise 2 x 2 block dG/d(u,v) of G = (-u v^2 + phi (1-u), u v^2 - (phi+kappa) v)
+ * -- the same idea as the "stencilcuda" check above, for the two-species reaction-diffusion system. */
+struct rd_check {
+    int mode;           /* 1 IJacobian, 2 RHSJacobian */
+    int m;
+    double shift, C[2], phi, kappa;
+    const double *Y;    /* host state, (u,v) interleaved */
+    double maxdev, scale;
+    long long rows;
+    int bad_structure;
 };
 
 struct _p_PC {
@@ -325,13 +346,20 @@ static PetscErrorCode da_create(int dim, const DMBoundaryType *b, DMDAStencilTyp
         d->b[i] = i < dim ? b[i] : DM_BOUNDARY_NONE;
         d->cmin[i] = 0.0;
         d->cmax[i] = 1.0;
-        if (d->b[i] != DM_BOUNDARY_NONE) {
+        if (d->b[i] != DM_BOUNDARY_NONE && d->b[i] != DM_BOUNDARY_PERIODIC) {
             free(d);
-            SHIM_ERR(56, "only DM_BOUNDARY_NONE grids are provided by the shim so far");
+            SHIM_ERR(56, "DM_BOUNDARY_NONE and DM_BOUNDARY_PERIODIC grids are provided by the shim");
         }
     }
+    if (dim == 2 ? (d->b[0] != d->b[1]) : (d->b[0] == DM_BOUNDARY_PERIODIC)) {
+        free(d);
+        SHIM_ERR(56, "periodic DMDAs are provided in 2-D, periodic in both directions (pattern.c:79-84)");
+    }
+    if (dof < 1 || (dof > 1 && d->b[0] != DM_BOUNDARY_PERIODIC)) {
+        free(d);
+        SHIM_ERR(56, "dof > 1 is provided on the periodic 2-D DMDA only");
+    }
     d->dof = dof; d->sw = s; d->st = st; d->refct = 1;
-    if (dof != 1) { free(d); SHIM_ERR(56, "only dof = 1 grids are provided by the shim so far"); }
     *da = d;
     return 0;
 }
@@ -371,8 +399,8 @@ PetscErrorCode DMSetFromOptions(DM dm) {
 PetscErrorCode DMSetUp(DM dm) {
     if (dm->setup) return 0;
     memcpy(dm->M0, dm->M, sizeof dm->M0);
-    for (int i = 0; i < dm->dim; i++)       /* -da_refine n, non-periodic: M <- 1 + 2^n (M-1)   */
-        dm->M[i] = 1 + (1 << dm->refine) * (dm->M[i] - 1);
+    for (int i = 0; i < dm->dim; i++)       /* -da_refine n: M <- 1 + 2^n (M-1), periodic M <- 2^n M   */
+        dm->M[i] = dm->b[i] == DM_BOUNDARY_PERIODIC ? (dm->M[i] << dm->refine) : 1 + (1 << dm->refine) * (dm->M[i] - 1);
     dm->setup = 1;
     return 0;
 }
@@ -397,13 +425,15 @@ PetscErrorCode DMDAGetLocalInfo(DM da, DMDALocalInfo *info) {
     info->mx = da->M[0]; info->my = da->M[1]; info->mz = da->M[2];
     info->xs = info->ys = info->zs = 0;
     info->xm = da->M[0]; info->ym = da->M[1]; info->zm = da->M[2];
-    info->gxs = info->gys = info->gzs = 0;        /* one logical rank owns the whole non-periodic grid */
+    info->gxs = info->gys = info->gzs = 0;        /* one logical rank owns the whole grid */
     info->gxm = da->M[0]; info->gym = da->M[1]; info->gzm = da->M[2];
+    if (da->b[0] == DM_BOUNDARY_PERIODIC) { info->gxs = -da->sw; info->gxm += 2 * da->sw; }   /* periodic ghosts */
+    if (da->b[1] == DM_BOUNDARY_PERIODIC) { info->gys = -da->sw; info->gym += 2 * da->sw; }
     info->bx = da->b[0]; info->by = da->b[1]; info->bz = da->b[2];
     info->st = da->st;
     return 0;
 }
-static size_t da_n(DM dm) { return (size_t)dm->M[0] * dm->M[1] * dm->M[2]; }
+static size_t da_n(DM dm) { return (size_t)dm->M[0] * dm->M[1] * dm->M[2] * (size_t)dm->dof; }
 
 static PetscErrorCode vec_new(DM dm, Vec *v) {
     Vec x = (Vec)calloc(1, sizeof *x);
@@ -496,13 +526,17 @@ static PetscErrorCode vec_to_dev(Vec v) {
 }
 
 /* a[k][j][i] views with global indices (one rank owns everything, so no offsets are needed) */
-static void *make_tables(int dim, const int *M, double *base) {
-    if (dim == 1) return NULL;
-    if (dim == 2) {
+static void *make_tables_dof(int dim, const int *M, int dof, double *base) {
+    if (dim == 2) {         /* a[j][i] with i counting nodes of dof doubles each (pattern.c: Field **aY) */
         double **rows = (double **)malloc(sizeof(double *) * (size_t)M[1]);
-        for (int j = 0; j < M[1]; j++) rows[j] = base + (size_t)j * M[0];
+        for (int j = 0; j < M[1]; j++) rows[j] = base + (size_t)j * M[0] * dof;
         return rows;
     }
+    return NULL;
+}
+static void *make_tables(int dim, const int *M, double *base) {
+    if (dim == 1) return NULL;
+    if (dim == 2) return make_tables_dof(dim, M, 1, base);
     size_t np = (size_t)M[2], nr = (size_t)M[2] * M[1];
     char *blk = (char *)malloc(sizeof(double **) * np + sizeof(double *) * nr);
     double ***planes = (double ***)blk;
@@ -517,7 +551,7 @@ static PetscErrorCode get_array(DM da, Vec vec, void *array, int write) {
     PetscCall(vec_to_host(vec));
     if (write) vec->valid = LOC_HOST;
     free(vec->tables);
-    vec->tables = make_tables(da->dim, da->M, vec->h);
+    vec->tables = da->dof > 1 ? make_tables_dof(da->dim, da->M, da->dof, vec->h) : make_tables(da->dim, da->M, vec->h);
     *(void **)array = da->dim == 1 ? (void *)vec->h : vec->tables;
     return 0;
 }
@@ -625,6 +659,36 @@ PetscErrorCode MatZeroEntries(Mat A) {
     A->rows_set = 0; A->general = 0; A->assembled = 0;
     return 0;
 }
+static PetscErrorCode rd_check_rows(struct rd_check *k, PetscInt m, const MatStencil idxm[], PetscInt n,
+                                    const MatStencil idxn[], const PetscScalar v[]) {
+    for (int r = 0; r < m; r++) {
+        const int ri = idxm[r].i, rj = idxm[r].j, rc = idxm[r].c;
+        if (rc < 0 || rc > 1 || ri < 0 || ri >= k->m || rj < 0 || rj >= k->m) { k->bad_structure = 1; continue; }
+        if (k->mode == 1) {
+            if (n != 9) k->bad_structure = 1;
+            for (int c = 0; c < n; c++) {
+                const int di = idxn[c].i - ri, dj = idxn[c].j - rj;       /* ghost indices -1, m are legal (periodic) */
+                if (idxn[c].c != rc || di < -1 || di > 1 || dj < -1 || dj > 1) { k->bad_structure = 1; continue; }
+                const double want = (!di && !dj) ? k->shift + 20.0 * k->C[rc] : ((!di || !dj) ? -4.0 * k->C[rc] : -k->C[rc]);
+                const double dev = fabs(v[r * n + c] - want);
+                if (dev > k->maxdev) k->maxdev = dev;
+            }
+        } else {
+            const double u = k->Y[2 * ((size_t)rj * k->m + ri)], w = k->Y[2 * ((size_t)rj * k->m + ri) + 1];
+            if (n != 2) k->bad_structure = 1;
+            for (int c = 0; c < n; c++) {
+                if (idxn[c].i != ri || idxn[c].j != rj || idxn[c].c < 0 || idxn[c].c > 1) { k->bad_structure = 1; continue; }
+                const int cc = idxn[c].c;
+                const double want = rc == 0 ? (cc == 0 ? -w * w - k->phi : -2.0 * u * w)
+                                            : (cc == 0 ? w * w : 2.0 * u * w - (k->phi + k->kappa));
+                const double dev = fabs(v[r * n + c] - want);
+                if (dev > k->maxdev) k->maxdev = dev;
+            }
+        }
+        k->rows++;
+    }
+    return 0;
+}
 static void mat_reject(Mat A, const char *why) {
     if (!A->general) { A->general = 1; snprintf(A->why, sizeof A->why, "%s", why); }
 }
@@ -639,6 +703,7 @@ PetscErrorCode MatSetValuesStencil(Mat A, PetscInt m, const MatStencil idxm[], P
     if (addv != INSERT_VALUES) { mat_reject(A, "ADD_VALUES insertion"); return 0; }
     const DM dm = A->dm;
     const int dim = dm->dim;
+    if (A->rd) return rd_check_rows(A->rd, m, idxm, n, idxn, v);
     for (int r = 0; r < m; r++) {
         const int ri = idxm[r].i, rj = dim >= 2 ? idxm[r].j : 0, rk = dim >= 3 ? idxm[r].k : 0;
         const int rb = node_is_bdry(dm, ri, rj, rk);
@@ -1159,5 +1224,340 @@ PetscErrorCode SNESDestroy(SNES *snes) {
     if ((*snes)->dm) { DM d = (*snes)->dm; DMDestroy(&d); }
     free(*snes);
     *snes = NULL;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* TS: the unchanged c/ch5/pattern.c                                                                 */
+/* ------------------------------------------------------------------------------------------------ */
+/* pattern.c registers four host callbacks on a periodic 2-D DMDA with two components (pattern.c:103-114) and calls
+ * TSSolve.  The device path for this system is p4b_pattern_solve_from (include/p4b200.h): TSARKIMEX3 / TSTHETA with the
+ * residuals and the matrix-free stage Jacobian as CUDA kernels of the two-species reaction-diffusion model
+ *     F(Y, Ydot) = Ydot - D_c L9 Y / (6 h^2),    G(Y) = (-u v^2 + phi (1 - u),  u v^2 - (phi + kappa) v).
+ * TSSolve therefore (1) IDENTIFIES the model's five numbers from the registered callbacks (three probe evaluations on
+ * the host: the box side from the DMDA, phi and kappa from G at constant states, D_u and D_v from F of a unit pulse),
+ * (2) VERIFIES that the callbacks ARE that model: F and G evaluated by the user's functions on the host and by the
+ * device kernels at a generic state must agree to rounding, and every row the user's Jacobian callbacks insert is
+ * compared with the stage matrix the device applies (rd_check_rows above) -- the same recognise-or-refuse contract as
+ * the "stencilcuda" Mat type of fish.c, and (3) runs the solve on the device from the caller's initial state.
+ * Callbacks that are anything else are refused with the measured deviation: there is no general assembled
+ * block-stencil TS path (and no CPU fallback).  Only the callbacks PETSc itself would call for the chosen -ts_type
+ * are invoked (RHSJacobian is never called for the IMEX default), so a driver's own call-back report (pattern.c:127-135)
+ * prints what it prints under PETSc. */
+struct _p_TS {
+    DM dm;
+    char type[32];
+    void *appctx;
+    double t0, max_time, dt, rtol, atol;
+    int max_steps, monitor, eft;
+    SNES snes;               /* holds the KSP / PC / SNES options of the stage solves */
+};
+
+PetscErrorCode DMDASetFieldName(DM da, PetscInt nf, const char name[]) { (void)da; (void)nf; (void)name; return 0; }
+PetscErrorCode DMDAGetCoordinateArray(DM da, void *xc) {
+    if (da->dim != 2) SHIM_ERR(56, "DMDAGetCoordinateArray: 2-D DMDAs only");
+    const int mx = da->M[0], my = da->M[1];
+    /* [PETSc] DMDASetUniformCoordinates: periodic directions have mx cells, the others mx - 1 */
+    const double hx = (da->cmax[0] - da->cmin[0]) / (da->b[0] == DM_BOUNDARY_PERIODIC ? mx : mx - 1);
+    const double hy = (da->cmax[1] - da->cmin[1]) / (da->b[1] == DM_BOUNDARY_PERIODIC ? my : my - 1);
+    char *blk = (char *)malloc(sizeof(DMDACoor2d *) * (size_t)my + sizeof(DMDACoor2d) * (size_t)mx * my);
+    if (!blk) SHIM_ERR(55, "out of host memory for the coordinate array");
+    DMDACoor2d **rows = (DMDACoor2d **)blk;
+    DMDACoor2d *c = (DMDACoor2d *)(blk + sizeof(DMDACoor2d *) * (size_t)my);
+    for (int j = 0; j < my; j++) {
+        rows[j] = c + (size_t)j * mx;
+        for (int i = 0; i < mx; i++) { rows[j][i].x = da->cmin[0] + i * hx; rows[j][i].y = da->cmin[1] + j * hy; }
+    }
+    *(void **)xc = rows;
+    return 0;
+}
+PetscErrorCode DMDARestoreCoordinateArray(DM da, void *xc) {
+    (void)da;
+    free(*(void **)xc);
+    *(void **)xc = NULL;
+    return 0;
+}
+PetscErrorCode DMDATSSetRHSFunctionLocal(DM dm, InsertMode imode, DMDATSRHSFunctionLocal func, void *ctx) {
+    (void)imode; dm->rhsfunc = func; dm->rhsfuncctx = ctx; return 0;
+}
+PetscErrorCode DMDATSSetRHSJacobianLocal(DM dm, DMDATSRHSJacobianLocal func, void *ctx) {
+    dm->rhsjac = func; dm->rhsjacctx = ctx; return 0;
+}
+PetscErrorCode DMDATSSetIFunctionLocal(DM dm, InsertMode imode, DMDATSIFunctionLocal func, void *ctx) {
+    (void)imode; dm->ifunc = func; dm->ifuncctx = ctx; return 0;
+}
+PetscErrorCode DMDATSSetIJacobianLocal(DM dm, DMDATSIJacobianLocal func, void *ctx) {
+    dm->ijac = func; dm->ijacctx = ctx; return 0;
+}
+
+PetscErrorCode TSCreate(MPI_Comm comm, TS *ts) {
+    TS t = (TS)calloc(1, sizeof *t);
+    snprintf(t->type, 32, "%s", TSBEULER);                  /* [PETSc] the default TS type is backward Euler */
+    t->max_time = 5.0; t->dt = 0.1; t->max_steps = 5000; t->rtol = t->atol = 1.0e-4;     /* [PETSc] TS defaults */
+    t->eft = TS_EXACTFINALTIME_UNSPECIFIED;
+    PetscCall(SNESCreate(comm, &t->snes));
+    *ts = t;
+    return 0;
+}
+PetscErrorCode TSSetProblemType(TS ts, TSProblemType type) { (void)ts; (void)type; return 0; }
+PetscErrorCode TSSetDM(TS ts, DM dm) { ts->dm = dm; dm->refct++; return 0; }
+PetscErrorCode TSSetApplicationContext(TS ts, void *usrP) { ts->appctx = usrP; return 0; }
+PetscErrorCode TSSetType(TS ts, TSType type) { snprintf(ts->type, 32, "%s", type); return 0; }
+PetscErrorCode TSGetType(TS ts, TSType *type) { *type = ts->type; return 0; }
+PetscErrorCode TSSetTime(TS ts, PetscReal t) { ts->t0 = t; return 0; }
+PetscErrorCode TSSetMaxTime(TS ts, PetscReal maxtime) { ts->max_time = maxtime; return 0; }
+PetscErrorCode TSSetTimeStep(TS ts, PetscReal time_step) { ts->dt = time_step; return 0; }
+PetscErrorCode TSSetExactFinalTime(TS ts, TSExactFinalTimeOption eftopt) { ts->eft = (int)eftopt; return 0; }
+PetscErrorCode TSSetFromOptions(TS ts) {
+    const char *v;
+    if ((v = opt_value("-ts_type"))) snprintf(ts->type, 32, "%s", v);
+    if ((v = opt_value("-ts_dt"))) ts->dt = strtod(v, NULL);
+    if ((v = opt_value("-ts_max_time"))) ts->max_time = strtod(v, NULL);
+    if ((v = opt_value("-ts_max_steps"))) ts->max_steps = atoi(v);
+    if ((v = opt_value("-ts_rtol"))) ts->rtol = strtod(v, NULL);
+    if ((v = opt_value("-ts_atol"))) ts->atol = strtod(v, NULL);
+    if ((v = opt_value("-ts_exact_final_time"))) {
+        if (!strcmp(v, "matchstep")) ts->eft = TS_EXACTFINALTIME_MATCHSTEP;
+        else if (!strcmp(v, "stepover")) ts->eft = TS_EXACTFINALTIME_STEPOVER;
+        else if (!strcmp(v, "interpolate")) ts->eft = TS_EXACTFINALTIME_INTERPOLATE;
+        else SHIM_ERR(62, "-ts_exact_final_time: stepover, interpolate or matchstep");
+    }
+    ts->monitor = opt_has("-ts_monitor");
+    /* KSP / PC / SNES options of the stage solves.  -snes_fd_color (pattern.test3) asks PETSc to difference the residual
+     * instead of calling the Jacobian callbacks: the device stage operator IS the analytic Jacobian those differences
+     * approximate, so the option only means that the Jacobian callbacks are not called (nor checked) */
+    return SNESSetFromOptions(ts->snes);
+}
+PetscErrorCode TSDestroy(TS *ts) {
+    if (!ts || !*ts) return 0;
+    if ((*ts)->dm) { DM d = (*ts)->dm; DMDestroy(&d); }
+    SNESDestroy(&(*ts)->snes);
+    free(*ts);
+    *ts = NULL;
+    return 0;
+}
+
+/* ghosted (width 1, periodic in both directions) host copy of a field with dof components and a[j][i] views of it
+ * that are valid for j, i in [-1, m]: what DMGlobalToLocal + DMDAVecGetArray hand a periodic callback */
+struct ghosted { double *buf; double **rows; void *a; };
+static int ghosted_make(const double *Y, int mx, int my, int dof, struct ghosted *g) {
+    const int gx = mx + 2, gy = my + 2;
+    g->buf = (double *)malloc(sizeof(double) * (size_t)gx * gy * dof);
+    g->rows = (double **)malloc(sizeof(double *) * (size_t)gy);
+    if (!g->buf || !g->rows) return 1;
+    for (int jj = 0; jj < gy; jj++) {
+        const int j = (jj - 1 + my) % my;
+        double *row = g->buf + (size_t)jj * gx * dof;
+        memcpy(row + dof, Y + (size_t)j * mx * dof, sizeof(double) * (size_t)mx * dof);
+        memcpy(row, Y + ((size_t)j * mx + (mx - 1)) * dof, sizeof(double) * dof);
+        memcpy(row + (size_t)(mx + 1) * dof, Y + (size_t)j * mx * dof, sizeof(double) * dof);
+        g->rows[jj] = row + dof;                     /* a[j][0] is the first owned node; a[j][-1] the left ghost */
+    }
+    g->a = g->rows + 1;                              /* a[-1] is the lower ghost row */
+    return 0;
+}
+static void ghosted_free(struct ghosted *g) { free(g->buf); free(g->rows); g->buf = NULL; g->rows = NULL; }
+
+/* the user's G(t, Y) and F(t, Y, Ydot) on host arrays of the whole grid */
+static PetscErrorCode ts_eval_rhs(DM dm, double t, const double *Y, double *G) {
+    DMDALocalInfo info;
+    struct ghosted gY;
+    PetscCall(DMDAGetLocalInfo(dm, &info));
+    if (ghosted_make(Y, dm->M[0], dm->M[1], dm->dof, &gY)) SHIM_ERR(55, "out of host memory");
+    void *aG = make_tables_dof(2, dm->M, dm->dof, G);
+    const double t0 = wall();
+    PetscErrorCode rc = dm->rhsfunc(&info, t, gY.a, aG, dm->rhsfuncctx);
+    g_t_func += wall() - t0;
+    free(aG);
+    ghosted_free(&gY);
+    return rc;
+}
+static PetscErrorCode ts_eval_ifunc(DM dm, double t, const double *Y, const double *Ydot, double *F) {
+    DMDALocalInfo info;
+    struct ghosted gY, gD;
+    PetscCall(DMDAGetLocalInfo(dm, &info));
+    if (ghosted_make(Y, dm->M[0], dm->M[1], dm->dof, &gY)) SHIM_ERR(55, "out of host memory");
+    if (ghosted_make(Ydot, dm->M[0], dm->M[1], dm->dof, &gD)) SHIM_ERR(55, "out of host memory");
+    void *aF = make_tables_dof(2, dm->M, dm->dof, F);
+    const double t0 = wall();
+    PetscErrorCode rc = dm->ifunc(&info, t, gY.a, gD.a, aF, dm->ifuncctx);
+    g_t_func += wall() - t0;
+    free(aF);
+    ghosted_free(&gY);
+    ghosted_free(&gD);
+    return rc;
+}
+
+static double maxabs_diff(const double *a, const double *b, size_t n, double *scale) {
+    double d = 0.0, s = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        const double e = fabs(a[i] - b[i]);
+        if (!(e <= d)) d = e;                        /* NaN propagates into the deviation */
+        if (fabs(b[i]) > s) s = fabs(b[i]);
+    }
+    *scale = s;
+    return d;
+}
+
+PetscErrorCode TSSolve(TS ts, Vec x) {
+    DM dm = ts->dm;
+    KSP ksp = &ts->snes->ksp;
+    PC pc = &ksp->pc;
+    char msg[512];
+    if (!dm) SHIM_ERR(73, "TSSolve: call TSSetDM() first");
+    if (dm->dim != 2 || dm->dof != 2 || dm->b[0] != DM_BOUNDARY_PERIODIC || dm->b[1] != DM_BOUNDARY_PERIODIC)
+        SHIM_ERR(56, "TSSolve is provided for the periodic 2-D DMDA with two components (pattern.c:79-84)");
+    if (dm->M[0] != dm->M[1]) SHIM_ERR(56, "TSSolve: the device path needs mx == my (pattern.c:89)");
+    if (!dm->ifunc || !dm->rhsfunc) SHIM_ERR(73, "TSSolve: call DMDATSSetIFunctionLocal() and DMDATSSetRHSFunctionLocal()");
+    if (!dm->ijac && !ts->snes->fd_color)
+        SHIM_ERR(56, "TSSolve: no IJacobian callback registered (-ptn_no_ijacobian): the device path checks its stage matrix "
+                     "against the registered callback; pass -snes_fd_color to say that differencing the residual is meant");
+    p4b_pattern_opts o;
+    P4B(p4b_pattern_default_opts(&o));
+    if (!strcmp(ts->type, TSARKIMEX)) o.ts_type = 0;
+    else if (!strcmp(ts->type, TSBEULER)) o.ts_type = 1;
+    else if (!strcmp(ts->type, TSCN)) o.ts_type = 2;
+    else {
+        snprintf(msg, sizeof msg, "-ts_type %s is not provided on the device path (arkimex, beuler, cn are)", ts->type);
+        SHIM_ERR(56, msg);
+    }
+    if (ts->t0 != 0.0) SHIM_ERR(56, "TSSolve: the device path starts at t = 0 (pattern.c:116)");
+    if (ts->eft != TS_EXACTFINALTIME_MATCHSTEP)
+        SHIM_ERR(56, "TSSolve: TS_EXACTFINALTIME_MATCHSTEP is what the device path provides (pattern.c:119)");
+    if (!pc->type[0])
+        SHIM_ERR(56, "PETSc's default PC (ILU(0) on one rank) is sequential and not provided on the device: "
+                     "pass -pc_type mg or -pc_type none");
+    if (!strcmp(pc->type, PCMG)) o.pc_type = 1;
+    else if (!strcmp(pc->type, PCNONE)) o.pc_type = 0;
+    else SHIM_ERR(56, "TSSolve: -pc_type mg and -pc_type none are provided");
+    if (o.pc_type == 1 && strcmp(pc->levels_pc, "jacobi"))
+        SHIM_ERR(56, "PCMG's default level smoother PC (SOR) is sequential and not provided on the device: "
+                     "pass -mg_levels_pc_type jacobi");
+    if (strcmp(ksp->type, KSPGMRES)) SHIM_ERR(56, "TSSolve: the stage solves are GMRES ([PETSc] default)");
+    PetscCall(ensure_ctx());
+    const double t_start = wall();
+
+    const int m = dm->M[0];
+    const size_t n = x->n;
+    const double Lbox = dm->cmax[0] - dm->cmin[0];
+    if (fabs((dm->cmax[1] - dm->cmin[1]) - Lbox) > 1e-14 * fabs(Lbox) || !(Lbox > 0.0))
+        SHIM_ERR(56, "TSSolve: the device path needs a square box (DMDASetUniformCoordinates, pattern.c:92)");
+    const double h = Lbox / m;
+    PetscCall(vec_to_host(x));
+    double *Y = (double *)calloc(n, sizeof(double)), *D = (double *)calloc(n, sizeof(double));
+    double *Fu = (double *)malloc(sizeof(double) * n), *Fd = (double *)malloc(sizeof(double) * n);
+    if (!Y || !D || !Fu || !Fd) SHIM_ERR(55, "out of host memory");
+
+    /* (1) identify: G at (u,v) = (0,0) is (phi, 0), at (0,1) it is (phi, -(phi+kappa)); F of unit pulses with Ydot = 0
+     *     is 20 C_c at the pulse, C_c = D_c / (6 h^2) */
+    Y[2 * 1 + 1] = 1.0;                                          /* node 1: (u, v) = (0, 1); every other node (0, 0) */
+    PetscCall(ts_eval_rhs(dm, 0.0, Y, Fu));
+    o.phi = Fu[0];
+    o.kappa = -Fu[2 * 1 + 1] - o.phi;
+    Y[2 * 1 + 1] = 0.0;
+    const size_t pn = (size_t)1 * m + 1;                         /* node (1, 1) */
+    Y[2 * pn] = 1.0; Y[2 * pn + 1] = 1.0;
+    PetscCall(ts_eval_ifunc(dm, 0.0, Y, D, Fu));
+    o.Du = Fu[2 * pn] / 20.0 * 6.0 * h * h;
+    o.Dv = Fu[2 * pn + 1] / 20.0 * 6.0 * h * h;
+    o.L = Lbox;
+
+    /* (2) verify at a generic state: the caller's initial state plus a fixed pseudo-random perturbation */
+    unsigned long long lcg = 0x9E3779B97F4A7C15ULL;
+    for (size_t i = 0; i < n; i++) {
+        lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
+        Y[i] = x->h[i] + 0.05 * ((double)(lcg >> 11) / 9007199254740992.0 - 0.5);
+        lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
+        D[i] = (double)(lcg >> 11) / 9007199254740992.0 - 0.5;
+    }
+    double *dY = NULL, *dD = NULL, *dF = NULL;
+    P4B(p4b_malloc(g_ctx, n * sizeof(double), (void **)&dY));
+    P4B(p4b_malloc(g_ctx, n * sizeof(double), (void **)&dD));
+    P4B(p4b_malloc(g_ctx, n * sizeof(double), (void **)&dF));
+    P4B(p4b_memcpy_h2d(g_ctx, dY, Y, n * sizeof(double)));
+    P4B(p4b_memcpy_h2d(g_ctx, dD, D, n * sizeof(double)));
+    double dev, scale;
+    PetscCall(ts_eval_ifunc(dm, 0.0, Y, D, Fu));
+    P4B(p4b_pattern_ifunction(g_ctx, m, m, o.L, o.Du, o.Dv, dY, dD, dF));
+    P4B(p4b_memcpy_d2h(g_ctx, Fd, dF, n * sizeof(double)));
+    dev = maxabs_diff(Fu, Fd, n, &scale);
+    if (!(dev <= 1.0e-11 * (scale > 1.0 ? scale : 1.0))) {
+        snprintf(msg, sizeof msg, "TSSolve: the registered IFunction is not F = Ydot - D L9 Y / (6 h^2) with the identified "
+                 "D_u = %g, D_v = %g (max deviation %.3e): not the reaction-diffusion model the device path implements", o.Du,
+                 o.Dv, dev);
+        SHIM_ERR(56, msg);
+    }
+    PetscCall(ts_eval_rhs(dm, 0.0, Y, Fu));
+    P4B(p4b_pattern_rhsfunction(g_ctx, m, m, o.phi, o.kappa, dY, dF));
+    P4B(p4b_memcpy_d2h(g_ctx, Fd, dF, n * sizeof(double)));
+    dev = maxabs_diff(Fu, Fd, n, &scale);
+    if (!(dev <= 1.0e-11 * (scale > 1.0 ? scale : 1.0))) {
+        snprintf(msg, sizeof msg, "TSSolve: the registered RHSFunction is not G = (-u v^2 + phi (1-u), u v^2 - (phi+kappa) v) "
+                 "with the identified phi = %g, kappa = %g (max deviation %.3e): not the model the device path implements",
+                 o.phi, o.kappa, dev);
+        SHIM_ERR(56, msg);
+    }
+    P4B(p4b_free(g_ctx, dY));
+    P4B(p4b_free(g_ctx, dD));
+    P4B(p4b_free(g_ctx, dF));
+    /* the Jacobian callbacks PETSc would call for this type: IJacobian always, RHSJacobian for the fully implicit types */
+    {
+        DMDALocalInfo info;
+        struct ghosted gY, gD;
+        struct rd_check chk;
+        struct _p_Mat P;
+        const double t_jac0 = wall();
+        PetscCall(DMDAGetLocalInfo(dm, &info));
+        if (ghosted_make(Y, m, m, 2, &gY) || ghosted_make(D, m, m, 2, &gD)) SHIM_ERR(55, "out of host memory");
+        memset(&chk, 0, sizeof chk);
+        chk.m = m; chk.shift = 1.0 / ts->dt; chk.C[0] = o.Du / (6.0 * h * h); chk.C[1] = o.Dv / (6.0 * h * h);
+        chk.phi = o.phi; chk.kappa = o.kappa; chk.Y = Y;
+        memset(&P, 0, sizeof P);
+        P.dm = dm; P.type = MATSTENCILCUDA; P.rd = &chk;
+        for (int mode = 1; mode <= 2; mode++) {
+            if (ts->snes->fd_color) break;                       /* PETSc would not call them either */
+            if (mode == 2 && (!dm->rhsjac || o.ts_type == 0)) break;
+            chk.mode = mode; chk.maxdev = 0.0; chk.rows = 0; chk.bad_structure = 0;
+            PetscErrorCode rc = mode == 1 ? dm->ijac(&info, 0.0, gY.a, gD.a, chk.shift, &P, &P, dm->ijacctx)
+                                          : dm->rhsjac(&info, 0.0, gY.a, &P, &P, dm->rhsjacctx);
+            if (rc) return rc;
+            const double tol = 1.0e-11 * (fabs(chk.shift) + 20.0 * chk.C[0] + 20.0 * chk.C[1] + 1.0);
+            if (chk.bad_structure || chk.rows != (long long)n || !(chk.maxdev <= tol)) {
+                snprintf(msg, sizeof msg, "TSSolve: the registered %s does not insert the stage matrix the device path applies "
+                         "(%lld of %zu rows, max deviation %.3e%s)", mode == 1 ? "IJacobian" : "RHSJacobian", chk.rows, n,
+                         chk.maxdev, chk.bad_structure ? ", entries outside the expected pattern" : "");
+                SHIM_ERR(56, msg);
+            }
+        }
+        ghosted_free(&gY);
+        ghosted_free(&gD);
+        g_t_jac += wall() - t_jac0;
+    }
+    free(Y); free(D); free(Fu); free(Fd);
+
+    /* (3) the solve, on the device, from the caller's state */
+    o.no_rhsjacobian = dm->rhsjac ? 0 : 1;
+    o.call_back_report = 0;
+    o.grid_x = dm->M0[0]; o.grid_y = dm->M0[1]; o.refine = dm->refine;
+    o.ts_dt = ts->dt; o.ts_max_time = ts->max_time; o.ts_max_steps = ts->max_steps;
+    o.ts_rtol = ts->rtol; o.ts_atol = ts->atol; o.ts_monitor = ts->monitor;
+    o.smooth_its = pc->smooth_its;
+    {
+        const char *v = opt_value("-p4b_mg_rscale");
+        if (v) o.mg_rscale = strtod(v, NULL);
+    }
+    o.snes_rtol = ts->snes->rtol; o.snes_stol = ts->snes->stol; o.snes_atol = ts->snes->atol; o.snes_max_it = ts->snes->max_it;
+    o.ksp_rtol = ksp->rtol; o.ksp_max_it = ksp->max_it; o.gmres_restart = ts->snes->gmres_restart;
+    o.snes_converged_reason = ts->snes->converged_reason_flag;
+    o.ksp_converged_reason = ksp->converged_reason_flag;
+    PetscCall(vec_to_dev(x));
+    p4b_pattern_result *R = (p4b_pattern_result *)calloc(1, sizeof *R);
+    fflush(stdout);
+    int rc = p4b_pattern_solve_from(g_ctx, &o, x->d, newton_line, NULL, x->d, n, R);
+    fflush(stdout);
+    free(R);
+    if (rc) return PetscShimError(PETSC_COMM_SELF, __LINE__, __func__, __FILE__, rc, p4b_last_error());
+    x->valid = LOC_DEV;
+    g_t_snes += wall() - t_start;
     return 0;
 }
