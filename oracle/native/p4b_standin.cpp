@@ -10,7 +10,8 @@
 // oracle/Makefile links it with the shim source and the reference's minimal.c / pattern.c into
 // oracle/_ref/{minimal,pattern}_shim_host, which tests/test_shim_minimal_cpu.py / test_shim_pattern_cpu.py compare with
 // the reference's golden outputs (c/ch7/output/minimal.test*, c/ch5/output/pattern.test*).
-// The linear fish.c path (p4b_mg_* / p4b_cg_solve) is NOT restated here: those calls fail with an explanatory error.
+// For fish.c the recognised finest-level operator is solved by Jacobi-preconditioned CG (no multigrid: iteration counts
+// are not the device path's; the shim's work around the solve is what a CPU test can see).
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -30,6 +31,7 @@ static int fail(int code, const char *msg) {
 }
 
 struct p4b_ctx { int unused; };
+struct p4b_mg { p4b_grid g; double diag, c[3]; };
 
 extern "C" {
 
@@ -138,15 +140,77 @@ int p4b_pattern_solve_from(p4b_ctx *c, const p4b_pattern_opts *opts, const doubl
     return 0;
 }
 
-// ---- the linear (fish.c) path is not restated on the host ----
-int p4b_mg_default_opts(p4b_mg_opts *o) { memset(o, 0, sizeof *o); return 0; }
-int p4b_mg_create_stencil(p4b_ctx *, const p4b_grid *, const p4b_mg_opts *, const double *, int, p4b_mg **) {
-    return fail(56, "host stand-in: the fish.c multigrid path needs the CUDA library");
+// ---- fish.c: the operator the shim's Mat type recognised (finest level) and a Jacobi-preconditioned CG on it.  There is
+// NO multigrid here: iteration counts are not the device path's; what the stand-in lets a CPU test see is everything
+// the shim does around the solve (callbacks, Mat recognition, Vec bookkeeping, the reference's own report lines). ----
+int p4b_mg_default_opts(p4b_mg_opts *o) { memset(o, 0, sizeof *o); o->smooth_its = 2; o->cycle = P4B_CYCLE_V; return 0; }
+int p4b_mg_create_stencil(p4b_ctx *, const p4b_grid *g, const p4b_mg_opts *, const double *coef, int nlev, p4b_mg **mg) {
+    if (nlev < 1) return fail(62, "need the stencil of the finest level");
+    p4b_mg *m = new p4b_mg;
+    m->g = *g;
+    m->diag = coef[0];
+    for (int d = 0; d < 3; d++) m->c[d] = coef[1 + d];
+    *mg = m;
+    return 0;
 }
-int p4b_mg_destroy(p4b_mg *) { return 0; }
-int p4b_mg_matmult(p4b_mg *, const double *, double *) { return fail(56, "host stand-in: no MatMult"); }
-int p4b_cg_solve(p4b_mg *, int, const double *, double *, double, double, int, p4b_ksp_result *) {
-    return fail(56, "host stand-in: no KSPSolve");
+int p4b_mg_destroy(p4b_mg *mg) { delete mg; return 0; }
+int p4b_mg_matmult(p4b_mg *mg, const double *x, double *y) {
+    // poissonfunctions.c:117-258: boundary rows are diag-only, interior rows couple to interior neighbours only
+    const int M[3] = {mg->g.mx, mg->g.dim >= 2 ? mg->g.my : 1, mg->g.dim >= 3 ? mg->g.mz : 1};
+    const long st[3] = {1, M[0], (long)M[0] * M[1]};
+    auto bd = [&](const int *p) {
+        for (int d = 0; d < mg->g.dim; d++)
+            if (p[d] == 0 || p[d] == M[d] - 1) return true;
+        return false;
+    };
+    for (int k = 0; k < M[2]; k++)
+        for (int j = 0; j < M[1]; j++)
+            for (int i = 0; i < M[0]; i++) {
+                const int p[3] = {i, j, k};
+                const long n = i + st[1] * j + st[2] * k;
+                double v = mg->diag * x[n];
+                if (!bd(p))
+                    for (int d = 0; d < mg->g.dim; d++)
+                        for (int sgn = -1; sgn <= 1; sgn += 2) {
+                            int q[3] = {i, j, k};
+                            q[d] += sgn;
+                            if (!bd(q)) v -= mg->c[d] * x[n + sgn * st[d]];
+                        }
+                y[n] = v;
+            }
+    return 0;
+}
+int p4b_cg_solve(p4b_mg *mg, int, const double *b, double *x, double rtol, double abstol, int max_it, p4b_ksp_result *res) {
+    const size_t n = (size_t)mg->g.mx * (mg->g.dim >= 2 ? mg->g.my : 1) * (mg->g.dim >= 3 ? mg->g.mz : 1);
+    std::vector<double> r(b, b + n), z(n), p(n), w(n);
+    HostOps o;
+    memset(res, 0, sizeof *res);
+    memset(x, 0, sizeof(double) * n);
+    const double idiag = 1.0 / mg->diag;
+    for (size_t i = 0; i < n; i++) z[i] = idiag * r[i];
+    double znorm = o.norm2(n, z.data()), beta = o.dot(n, r.data(), z.data());
+    res->rnorm0 = znorm;
+    res->hist[res->nhist++] = znorm;
+    const double ttol = std::max(rtol * znorm, abstol);
+    p = z;
+    res->reason = P4B_DIVERGED_ITS;
+    if (znorm <= ttol) res->reason = P4B_CONVERGED_ATOL;
+    while (res->reason == P4B_DIVERGED_ITS && res->its < max_it) {
+        p4b_mg_matmult(mg, p.data(), w.data());
+        const double a = beta / o.dot(n, p.data(), w.data());
+        o.axpy(n, a, p.data(), x);
+        o.axpy(n, -a, w.data(), r.data());
+        for (size_t i = 0; i < n; i++) z[i] = idiag * r[i];
+        znorm = o.norm2(n, z.data());
+        res->its++;
+        if (res->nhist < P4B_MAX_HIST) res->hist[res->nhist++] = znorm;
+        if (znorm <= ttol) { res->reason = znorm <= abstol ? P4B_CONVERGED_ATOL : P4B_CONVERGED_RTOL; break; }
+        const double bnew = o.dot(n, r.data(), z.data());
+        o.aypx(n, bnew / beta, z.data(), p.data());
+        beta = bnew;
+    }
+    res->rnorm = znorm;
+    return 0;
 }
 
 }  // extern "C"

@@ -1,0 +1,65 @@
+"""The reference's UNCHANGED c/ch6/fish.c through the PETSc-shaped shim, on the CPU: the shim's work around the solve --
+callbacks on the host, recognition of the Jacobian callback's values on every level ("stencilcuda"), Vec bookkeeping,
+the reference's own report -- with the library replaced by the host stand-in (oracle/native/p4b_standin.cpp: the
+recognised operator + Jacobi-CG, NO multigrid, so iteration counts are not the device path's and are not asserted).
+The device run of the same driver is tests/test_gpu_fish_driver.py (validated on a B200)."""
+import json
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "fish_goldens.json")))
+JAC = " -mg_levels_pc_type jacobi"
+
+
+@pytest.fixture(scope="module")
+def exe():
+    path = os.path.join(ROOT, "oracle", "_ref", "fish_shim_host")
+    if os.path.exists("/root/reference/c/ch6/fish.c"):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "_ref/fish_shim_host"])
+    if not os.path.exists(path):
+        pytest.skip("needs the reference tree to compile fish.c")
+    return path
+
+
+def fish(exe, opts, expect_rc=0):
+    p = subprocess.run([exe] + opts.split(), capture_output=True, text=True, timeout=300)
+    assert p.returncode == expect_rc, (p.returncode, p.stdout, p.stderr)
+    return p.stdout.splitlines(), p.stderr
+
+
+def test_golden_test1_lines(exe):
+    g = GOLD["fish.test1"]
+    lines, _ = fish(exe, g["options"] + JAC)
+    assert lines[0] == "  0 SNES Function norm %s" % g["snes_fnorm0"]
+    assert lines[1].startswith("    Linear solve converged due to CONVERGED_RTOL iterations ")
+    assert lines[2] == "  1 SNES Function norm < 1.e-11"
+    assert lines[3:] == ["problem %s on %s grid:" % (g["problem"], g["gridstr"]),
+                         "  error |u-uexact|_inf = %s, |u-uexact|_h = %s" % (g["errinf"], g["err2h"])]
+
+
+@pytest.mark.parametrize("name,opts", [      # (the goldens' own -snes_fd_color / -pc_mg_galerkin are not on the device path)
+    ("fish.test6", "-fsh_dim 3 -da_refine 2 -fsh_problem manupoly -ksp_converged_reason -fsh_cx 0.01 -fsh_cy 2 -fsh_cz 100"),
+    ("fish.test7", "-fsh_dim 3 -fsh_problem manupoly -ksp_converged_reason -da_refine 2"),
+    ("fish.test2", "-fsh_dim 1 -fsh_problem manupoly -da_refine 1"),
+])
+def test_golden_error_lines(exe, name, opts):
+    g = GOLD[name]
+    lines, _ = fish(exe, opts + " -pc_type mg -ksp_rtol 1.0e-12" + JAC)
+    assert lines[-2:] == ["problem %s on %s grid:" % (g["problem"], g["gridstr"]),
+                          "  error |u-uexact|_inf = %s, |u-uexact|_h = %s" % (g["errinf"], g["err2h"])]
+
+
+def test_reference_error_paths(exe):
+    _, err = fish(exe, "-fsh_cx -1 -fsh_problem manupoly -pc_type mg" + JAC, expect_rc=2)
+    assert "positivity required" in err
+    _, err = fish(exe, "-fsh_dim 4 -pc_type mg" + JAC, expect_rc=1)
+    assert "invalid dim" in err
+    _, err = fish(exe, "-fsh_dim 2 -da_refine 2", expect_rc=56)
+    assert "ILU" in err
+    _, err = fish(exe, "-fsh_dim 2 -da_refine 2 -pc_type mg", expect_rc=56)
+    assert "SOR" in err
+    _, err = fish(exe, "-fsh_dim 2 -da_refine 2 -pc_type mg -snes_grid_sequence 1" + JAC, expect_rc=56)
+    assert "newtonls only" in err
