@@ -23,7 +23,7 @@ int main(int argc, char **argv) {
         if (!strcmp(a, "-da_grid_x")) { o.grid_x = atoi(v); i++; }
         else if (!strcmp(a, "-da_grid_y")) { o.grid_y = atoi(v); i++; }
         else if (!strcmp(a, "-da_refine")) { o.refine = atoi(v); i++; }
-        else if (!strcmp(a, "-ts_type")) { o.ts_type = !strcmp(v, "beuler") ? 1 : (!strcmp(v, "cn") ? 2 : 0); i++; }
+        else if (!strcmp(a, "-ts_type")) { o.ts_type = !strcmp(v, "beuler") ? 1 : (!strcmp(v, "cn") ? 2 : (!strcmp(v, "bdf") ? 3 : 0)); i++; }
         else if (!strcmp(a, "-ts_dt")) { o.ts_dt = atof(v); i++; }
         else if (!strcmp(a, "-ts_max_time")) { o.ts_max_time = atof(v); i++; }
         else if (!strcmp(a, "-pc_type")) { o.pc_type = strcmp(v, "mg") ? 0 : 1; i++; }

@@ -334,13 +334,13 @@ int p4b_snes2d_solve_monitored(p4b_ctx *ctx, const p4b_minimal_opts *opts, p4b_r
                                p4b_monitor2d_fn monitor, void *user, const double *u0_host, p4b_line_fn line, void *line_ctx,
                                double *u_out_host, size_t u_capacity, p4b_minimal_result *result);
 /* ---- the whole pattern.c run in one call: [PETSc] TSSolve for `./pattern [-ts_type arkimex|beuler|cn] -pc_type mg|none`
- * (c/ch5/pattern.c:99-125, c/ch5/makefile:49-62): TSARKIMEX3 + TSAdaptBasic + MATCHSTEP, or TSTHETA with Newton + bt;
+ * (c/ch5/pattern.c:99-125, c/ch5/makefile:49-62): TSARKIMEX3 + TSAdaptBasic + MATCHSTEP, TSTHETA, or TSBDF(2), Newton + bt;
  * stage solves GMRES(30) + V cycle on the matrix-free stage operator; host logic csrc/ts_solver.hpp. ---- */
 typedef struct {
     double L, Du, Dv, phi, kappa;          /* -ptn_L -ptn_Du -ptn_Dv -ptn_phi -ptn_kappa (pattern.c:47-52) */
     int no_rhsjacobian, call_back_report;  /* -ptn_no_rhsjacobian -ptn_call_back_report */
     int grid_x, grid_y, refine;            /* -da_grid_x -da_grid_y -da_refine (periodic: refine doubles) */
-    int ts_type;                           /* 0 arkimex (pattern.c's default), 1 beuler, 2 cn */
+    int ts_type;                           /* 0 arkimex (pattern.c's default), 1 beuler, 2 cn, 3 bdf (order 2) */
     double ts_dt, ts_max_time;
     int ts_max_steps;
     double ts_rtol, ts_atol;

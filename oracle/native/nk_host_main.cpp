@@ -28,11 +28,12 @@ static int pattern_main(int argc, char **argv) {
         if (a == "-da_grid_x") o.grid_x = atoi(next());
         else if (a == "-da_grid_y") o.grid_y = atoi(next());
         else if (a == "-da_refine") o.refine = atoi(next());
-        else if (a == "-ts_type") { const std::string v = next(); o.ts_type = v == "beuler" ? TS_BEULER : (v == "cn" ? TS_CN : TS_ARKIMEX); }
+        else if (a == "-ts_type") { const std::string v = next(); o.ts_type = v == "beuler" ? TS_BEULER : (v == "cn" ? TS_CN : (v == "bdf" ? TS_BDF : TS_ARKIMEX)); }
         else if (a == "-ts_dt") o.ts_dt = atof(next());
         else if (a == "-ts_max_time") o.ts_max_time = atof(next());
         else if (a == "-pc_type") o.pc_type = std::string(next()) == "mg" ? PC_MG : PC_NONE;
         else if (a == "-snes_rtol") o.snes_rtol = atof(next());
+        else if (a == "-ksp_rtol") o.ksp_rtol = atof(next());
         else if (a == "-p4b_mg_rscale") o.mg_rscale = atof(next());
         else if (a == "-ptn_no_rhsjacobian") o.no_rhsjacobian = 1;
         else if (a == "-ptn_call_back_report") o.call_back_report = 1;

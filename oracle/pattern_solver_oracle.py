@@ -302,3 +302,99 @@ def pattern_bdf_first_step(grid=3, refine=4, dt=1.0, atol=1.0e-4, rtol=1.0e-4, L
     enorm = float(np.sqrt(np.mean((lte / tol) ** 2)))
     _, hnext = adapt_basic(dt, enorm, True, order=2)
     return (half.its, full.its), hnext, full.u
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BDF2, every step.  [PETSc] TSStep_BDF with the default order 2 (restated from the algorithm of src/ts/impls/bdf/bdf.c as
+# described above; pattern.test5 pins the restart step -- Newton counts 3 and 2 and the proposed next step 1.10972 -- and
+# nothing later: the steps after the first are checked by their order of accuracy only, "parity unpinned" there).
+#   history  time[0] = new time, time[1..] = accepted states, newest first; after a restart time[2] = the half-step state
+#   stage    Ydot = sum_i dL_i(time[0]) work[i] over the nodes time[0..k]  (Lagrange-basis derivatives; shift = dL_0)
+#   guess    Lagrange extrapolation over min(k + 1, n) history states (k one lower after a rejection)
+#   LTE      order kl = min(k, n - 1): alpha = (a - b)/a_0, a = derivative weights over kl + 1 nodes, b over kl + 2;
+#            error estimate sum_i alpha_i work[i], weighted norm as TSErrorWeightedNorm, TSAdaptBasic with order kl + 1
+# ---------------------------------------------------------------------------------------------------------
+def lagrange_basis_vals(t, T):
+    n = len(T)
+    v = np.ones(n)
+    for k in range(n):
+        for j in range(n):
+            if j != k:
+                v[k] *= (t - T[j]) / (T[k] - T[j])
+    return v
+
+
+def pattern_bdf(grid=3, refine=0, dt=5.0, tmax=200.0, atol=1.0e-4, rtol=1.0e-4, snes_rtol=1.0e-8, max_steps=10000, L=2.5,
+                Du=8.0e-5, Dv=4.0e-5, phi=0.024, kappa=0.06, order=2, adapt=True):
+    m = grid * 2 ** refine
+    par = dict(L=L, Du=Du, Dv=Dv, phi=phi, kappa=kappa)
+    Y = mpo.pattern_initial_state(m, m, L)
+    res = PatternResult(Y=Y, mx=m)
+    res.lines.append("running on %d x %d grid with square cells of side h = %.6f ..." % (m, m, L / m))
+    time, work = [0.0] * 8, [None] * 8
+    state = dict(k=0, n=0)
+    newton_counts = []
+
+    def advance(t, X):
+        for i in range(7, 1, -1):
+            time[i], work[i] = time[i - 1], work[i - 1]
+        state["n"] = min(state["n"] + 1, 7)
+        time[1], work[1] = t, X.copy()
+
+    def solve(guess):
+        nn = max(state["k"], 1) + 1
+        a = lagrange_basis_ders(time[0], time[:nn])
+        aff = sum(a[i] * work[i] for i in range(1, nn))
+        R = lambda W: mpo.pattern_ifunction(W, a[0] * W + aff, L, Du, Dv) - mpo.pattern_rhsfunction(W, phi, kappa)
+        r = mso.newton(R, guess, lambda J, W: fo.ILU0PC(J).apply, jac=lambda W: stage_jacobian(W, a[0], True, **par),
+                       snes_rtol=snes_rtol)
+        newton_counts.append(r.its)
+        res.lines.append("    Nonlinear solve converged due to %s iterations %d" % (r.reason, r.its))
+        return r.u
+
+    t, k, h = 0.0, 0, min(dt, tmax)
+    restart, rejected = True, 0
+    while t < tmax - 1e-12 * max(1.0, abs(tmax)) and k < max_steps:
+        res.lines.append("%d TS dt %s time %s" % (k, fmt_g(h), fmt_g(t)))
+        if not restart:
+            state["k"] = min(state["k"] + 1, order)
+            advance(t, Y)
+        accept = True
+        while True:
+            if restart:
+                state["k"], state["n"] = 1, 0
+                advance(t, Y)
+                time[0] = t + h / 2.0
+                work[0] = solve(work[1])
+                state["k"] = min(2, order)
+                state["n"] += 1
+                work[2], time[2] = work[0].copy(), time[0]
+            time[0] = t + h
+            ne = min(state["k"] - (0 if accept else 1) + 1, state["n"])
+            c = lagrange_basis_vals(time[0], time[1:1 + ne])
+            work[0] = solve(sum(c[i] * work[1 + i] for i in range(ne)))
+            kl = min(state["k"], state["n"] - 1)
+            a = np.append(lagrange_basis_ders(time[0], time[:kl + 1]), 0.0)
+            b = lagrange_basis_ders(time[0], time[:kl + 2])
+            alpha = (a - b) / a[0]
+            lte = sum(alpha[i] * work[i] for i in range(kl + 2))
+            tol = atol + rtol * np.maximum(np.abs(work[0]), np.abs(work[0] + lte))
+            enorm = float(np.sqrt(np.mean((lte / tol) ** 2)))
+            if adapt:
+                ok, hnext = adapt_basic(h, enorm, accept, order=kl + 1)
+            else:
+                ok, hnext = True, h
+            if ok:
+                break
+            accept = False
+            rejected += 1
+            h = hnext
+        Y = work[0]
+        t += h
+        res.steps.append((t, h, enorm))
+        h = match_step(t, hnext, tmax)
+        restart = False
+        k += 1
+    res.lines.append("%d TS dt %s time %s" % (k, fmt_g(h), fmt_g(t)))
+    res.Y, res.rejected, res.newton_counts = Y, rejected, newton_counts
+    return res

@@ -246,7 +246,7 @@ extern "C" int p4b_pattern_solve_from(p4b_ctx *c, const p4b_pattern_opts *opts, 
     const nk::PatternOpts &o = *reinterpret_cast<const nk::PatternOpts *>(opts);
     if (o.grid_x < 3 || o.grid_y < 3) return fail(60, "periodic grid needs at least 3 nodes per dimension");
     if ((o.grid_x << o.refine) != (o.grid_y << o.refine)) return fail(1, "pattern.c requires mx == my");            // pattern.c:89
-    if (o.ts_type < nk::TS_ARKIMEX || o.ts_type > nk::TS_CN) return fail(62, "ts_type: arkimex (0), beuler (1), cn (2)");
+    if (o.ts_type < nk::TS_ARKIMEX || o.ts_type > nk::TS_BDF) return fail(62, "ts_type: arkimex (0), beuler (1), cn (2), bdf (3)");
     DeviceOps ops{c, ctx_stream(c)};
     nk::Printer pr{line, line_ctx};
     double *Y = nullptr;

@@ -4,21 +4,27 @@
 // goldens c/ch5/output/pattern.test1-4 verbatim:
 //   -ts_type arkimex   [PETSc] TSARKIMEX3 = ARK3(2)4L[2]SA (Kennedy & Carpenter 2003) + TSAdaptBasic + MATCHSTEP
 //   -ts_type beuler|cn [PETSc] TSTHETA (theta = 1 | 1/2 endpoint), fixed steps, Newton + bt on every step
+//   -ts_type bdf       [PETSc] TSBDF, order 2: backward-Euler half-step restart, variable-step weights from Lagrange-basis
+//                      derivatives, extrapolated initial guess, LTE from the next-higher difference, TSAdaptBasic.
+//                      c/ch5/output/pattern.test5 pins the restart step (Newton counts 3, 2; next step 1.10972); later
+//                      steps have no golden (checked for second-order accuracy against the oracle): parity unpinned there
 //   stage solves       GMRES(30) preconditioned by a V cycle on the rediscretised, matrix-free stage operator
 //                      J = shift*I - C L9 - G'(Y) (FormIJacobianLocal / FormRHSJacobianLocal, pattern.c:202-318)
 #pragma once
+#include <functional>
+
 #include "nk_solver.hpp"
 
 namespace p4b {
 namespace nk {
 
-enum { TS_ARKIMEX = 0, TS_BEULER = 1, TS_CN = 2 };
+enum { TS_ARKIMEX = 0, TS_BEULER = 1, TS_CN = 2, TS_BDF = 3 };
 
 struct PatternOpts {
     double L, Du, Dv, phi, kappa;          // -ptn_L -ptn_Du -ptn_Dv -ptn_phi -ptn_kappa (pattern.c:47-52)
     int no_rhsjacobian, call_back_report;  // -ptn_no_rhsjacobian -ptn_call_back_report
     int grid_x, grid_y, refine;
-    int ts_type;                           // TS_ARKIMEX | TS_BEULER | TS_CN
+    int ts_type;                           // TS_ARKIMEX | TS_BEULER | TS_CN | TS_BDF
     double ts_dt, ts_max_time;
     int ts_max_steps;
     double ts_rtol, ts_atol;
@@ -245,11 +251,12 @@ static const double ARK3_AE[4][4] = {{0, 0, 0, 0}, {1767732205903.0 / 2027836641
 static const double ARK3_BH[4] = {2756255671327.0 / 12835298489170.0, -10771552573575.0 / 22201958757719.0,
                                   9247589265047.0 / 10645013368117.0, 2193209047091.0 / 5459859503100.0};
 
-// [PETSc] TSAdaptChoose_Basic: the extra factor 1/2 only from the second consecutive rejection on
-inline bool adapt_basic(double h, double enorm, bool prev_accept, double *hnext) {
+// [PETSc] TSAdaptChoose_Basic: the extra factor 1/2 only from the second consecutive rejection on; order = the order the
+// error estimate was taken at (3 for ARK3(2)4L, k + 1 for BDF)
+inline bool adapt_basic(double h, double enorm, bool prev_accept, double *hnext, int order = 3) {
     const bool accept = enorm <= 1.0;
     const double s = 0.9 * ((!accept && !prev_accept) ? 0.5 : 1.0);
-    double hfac = enorm > 0.0 ? s * pow(enorm, -1.0 / 3.0) : INFINITY;
+    double hfac = enorm > 0.0 ? s * pow(enorm, -1.0 / (double)order) : INFINITY;
     hfac = std::min(std::max(hfac, 0.1), 10.0);
     *hnext = h * hfac;
     return accept;
@@ -263,6 +270,27 @@ inline double match_step(double t, double hnext, double tmax) {
     if (tend < tmax && hnext * 2.0 > hmax) out = hmax / 2.0;
     if (tend < tmax && hnext * 1.01 > hmax) out = hmax;
     return out;
+}
+
+// [PETSc] LagrangeBasisVals / LagrangeBasisDers (bdf.c): values and first derivatives at t of the Lagrange basis over T[0..n)
+inline void lagrange_vals(int n, double t, const double *T, double *L) {
+    for (int k = 0; k < n; k++) {
+        L[k] = 1.0;
+        for (int j = 0; j < n; j++)
+            if (j != k) L[k] *= (t - T[j]) / (T[k] - T[j]);
+    }
+}
+inline void lagrange_ders(int n, double t, const double *T, double *dL) {
+    for (int k = 0; k < n; k++) {
+        dL[k] = 0.0;
+        for (int j = 0; j < n; j++) {
+            if (j == k) continue;
+            double p = 1.0 / (T[k] - T[j]);
+            for (int l = 0; l < n; l++)
+                if (l != k && l != j) p *= (t - T[l]) / (T[k] - T[l]);
+            dL[k] += p;
+        }
+    }
 }
 
 // Y0 (optional, Ops memory, 2*m*m doubles): the caller's initial state -- then the run is the caller's (pattern.c under the
@@ -371,35 +399,16 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
         }
         if (!rc && opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(h).c_str(), fmt_g(t).c_str());
     } else {
-        const double theta = opt.ts_type == TS_CN ? 0.5 : 1.0;
-        double *Y0 = take(), *Ydot = take(), *G = take(), *affine = take(), *y = take(), *Jy = take(), *wv = take(), *gnew = take();
-        double dt_last = opt.ts_dt;
-        while (t < tmax - 1e-14 * std::max(1.0, fabs(tmax)) && k < opt.ts_max_steps && !rc) {
-            const double dt = std::min(opt.ts_dt, tmax - t);     // TS_EXACTFINALTIME_MATCHSTEP (:118)
-            dt_last = dt;
-            if (opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(dt).c_str(), fmt_g(t).c_str());
-            const double shift = 1.0 / (theta * dt);
-            ops->copy(n, Y, Y0);
-            if (theta != 1.0) {
-                ops->set(n, 0.0, Ydot);
-                ops->pattern_ifunction(m, opt, Y0, Ydot, affine);
-                ops->pattern_rhsfunction(m, opt, Y0, G);
-                ops->axpy(n, -1.0, G, affine);
-            }
-            // F(W, (W - Y0)/(theta dt)) - G(W) + (1 - theta)/theta [F(Y0, 0) - G(Y0)]
-            auto F = [&](const double *W, double *f) {
-                ops->axpby(n, shift, W, -shift, Y0, Ydot);
-                ops->pattern_ifunction(m, opt, W, Ydot, f);
-                ops->pattern_rhsfunction(m, opt, W, G);
-                ops->axpy(n, -1.0, G, f);
-                if (theta != 1.0) ops->axpy(n, (1.0 - theta) / theta, affine, f);
-            };
-            F(Y, Rv);
+        double *Yprev = take(), *Ydot = take(), *G = take(), *affine = take(), *y = take(), *Jy = take(), *wv = take(), *gnew = take();
+        // [PETSc] SNESSolve_NEWTONLS on F(W) = 0 from the guess X (in place), stage matrix shift*I - C L9 - G'(W)
+        auto newton_solve = [&](const std::function<void(const double *, double *)> &F, double shift, double *X, int *its_out) {
+            F(X, Rv);
             double fnorm = ops->norm2(n, Rv);
             const double ttol = opt.snes_rtol * fnorm;
             int reason = fnorm < opt.snes_atol ? SNES_CONVERGED_FNORM_ABS : 0, its = 0;
             while (!reason && !rc) {
                 if (its >= opt.snes_max_it) { reason = SNES_DIVERGED_MAX_IT; break; }
+                if (X != Y) ops->copy(n, X, Y);                  // the stage operator linearises about lev[0].Y
                 rc = A.setup(shift);
                 if (rc) break;
                 KSPInfo ki = gmres(ops, n, mult, Rv, y, prec, opt.ksp_rtol, 1.0e-50, opt.gmres_restart, opt.ksp_max_it, V, w, t1);
@@ -409,10 +418,10 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
                            ki.converged ? "CONVERGED_RTOL" : "DIVERGED_ITS", ki.its);
                 A.mult(y, Jy);
                 double gnorm = 0.0, lam = 0.0;
-                if (!linesearch_bt(ops, n, F, Y, Rv, fnorm, y, Jy, wv, gnew, &gnorm, &lam)) { reason = SNES_DIVERGED_LINE_SEARCH; break; }
-                ops->axpby(n, 1.0, wv, -1.0, Y, y);
+                if (!linesearch_bt(ops, n, F, X, Rv, fnorm, y, Jy, wv, gnew, &gnorm, &lam)) { reason = SNES_DIVERGED_LINE_SEARCH; break; }
+                ops->axpby(n, 1.0, wv, -1.0, X, y);
                 const double snorm = ops->norm2(n, y), xnorm = ops->norm2(n, wv);
-                ops->copy(n, wv, Y);
+                ops->copy(n, wv, X);
                 ops->copy(n, gnew, Rv);
                 fnorm = gnorm;
                 its++;
@@ -421,24 +430,144 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
                 else if (fnorm <= ttol) reason = SNES_CONVERGED_FNORM_RELATIVE;
                 else if (snorm < opt.snes_stol * xnorm) reason = SNES_CONVERGED_SNORM_RELATIVE;
             }
-            if (rc) break;
-            if (opt.snes_converged_reason)
+            if (!rc && opt.snes_converged_reason)
                 pr.out("    Nonlinear solve %s due to %s iterations %d", reason > 0 ? "converged" : "did not converge",
                        snes_reason_name(reason), its);
-            if (reason <= 0) { rc = 64; break; }
-            t += dt;
-            R->newton_its_total += its;
-            record(dt, its);
-            R->dt_last = dt;
-            k++;
-            if (ops->error()) rc = ops->error();
+            *its_out = its;
+            return reason;
+        };
+        if (opt.ts_type == TS_BDF) {
+            // [PETSc] TSStep_BDF, order 2 (see the header of this file)
+            const int order = 2;
+            double tm[8] = {0, 0, 0, 0, 0, 0, 0, 0}, *wk[8];
+            for (int i = 0; i < 8; i++) wk[i] = take();
+            double *V0 = take(), *lte = take();
+            int kord = 0, nh = 0;
+            bool restart = true;
+            auto advance = [&](double tt, const double *X) {                          // TSBDF_Advance
+                double *tail = wk[7];
+                for (int i = 7; i >= 2; i--) { tm[i] = tm[i - 1]; wk[i] = wk[i - 1]; }
+                nh = std::min(nh + 1, 7);
+                tm[1] = tt;
+                wk[1] = tail;
+                ops->copy(n, X, tail);
+            };
+            auto stage = [&](double *X, int *its) {                                    // TSBDF_PreSolve + SNESSolve
+                const int nn = std::max(kord, 1) + 1;
+                double a[8];
+                lagrange_ders(nn, tm[0], tm, a);
+                ops->set(n, 0.0, V0);
+                for (int i = 1; i < nn; i++) ops->axpy(n, a[i], wk[i], V0);
+                const double shift = a[0];
+                std::function<void(const double *, double *)> F = [&, shift](const double *W, double *f) {
+                    ops->axpby(n, shift, W, 1.0, V0, Ydot);                           // Ydot = shift W + V0
+                    ops->pattern_ifunction(m, opt, W, Ydot, f);
+                    ops->pattern_rhsfunction(m, opt, W, G);
+                    ops->axpy(n, -1.0, G, f);
+                };
+                return newton_solve(F, shift, X, its);
+            };
+            h = std::min(h, tmax - t);                                                // [PETSc] TSSolve: MATCHSTEP clips the first step
+            double dt_next = h;
+            while (t < tmax - 1e-12 * std::max(1.0, fabs(tmax)) && k < opt.ts_max_steps && !rc) {
+                if (opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(h).c_str(), fmt_g(t).c_str());
+                ops->copy(n, Y, Yprev);                              // lev[0].Y is the linearisation point from here on
+                if (!restart) { kord = std::min(kord + 1, order); advance(t, Yprev); }
+                bool accept = true;
+                int newton_step = 0, its = 0;
+                double hnext = h;
+                while (!rc) {
+                    if (restart) {                                                     // TSBDF_Restart
+                        kord = 1; nh = 0;
+                        advance(t, Yprev);
+                        tm[0] = t + h / 2.0;
+                        ops->copy(n, wk[1], wk[0]);
+                        if (stage(wk[0], &its) <= 0 && !rc) rc = 64;
+                        if (rc) break;
+                        newton_step += its;
+                        kord = std::min(2, order);
+                        nh++;
+                        ops->copy(n, wk[0], wk[2]);
+                        tm[2] = tm[0];
+                    }
+                    tm[0] = t + h;
+                    {                                                                  // TSBDF_Extrapolate
+                        const int ne = std::min(kord - (accept ? 0 : 1) + 1, nh);
+                        double c[8];
+                        lagrange_vals(ne, tm[0], tm + 1, c);
+                        ops->set(n, 0.0, wk[0]);
+                        for (int i = 0; i < ne; i++) ops->axpy(n, c[i], wk[1 + i], wk[0]);
+                    }
+                    if (stage(wk[0], &its) <= 0 && !rc) rc = 64;
+                    if (rc) break;
+                    newton_step += its;
+                    const int kl = std::min(kord, nh - 1);                             // TSEvaluateWLTE_BDF / TSBDF_VecLTE
+                    double a[8], b[8];
+                    lagrange_ders(kl + 1, tm[0], tm, a);
+                    a[kl + 1] = 0.0;
+                    lagrange_ders(kl + 2, tm[0], tm, b);
+                    ops->copy(n, wk[0], lte);
+                    for (int i = 0; i < kl + 2; i++) ops->axpy(n, (a[i] - b[i]) / a[0], wk[i], lte);
+                    const double enorm = sqrt(ops->wrms2(n, wk[0], lte, opt.ts_atol, opt.ts_rtol) / (double)n);
+                    if (adapt_basic(h, enorm, accept, &hnext, kl + 1)) break;
+                    accept = false;
+                    R->rejected++;
+                    h = hnext;
+                }
+                if (rc) break;
+                ops->copy(n, wk[0], Y);
+                t += h;
+                R->newton_its_total += newton_step;
+                record(h, newton_step);
+                R->dt_last = h;
+                h = match_step(t, hnext, tmax);
+                dt_next = h;
+                restart = false;
+                k++;
+                if (ops->error()) rc = ops->error();
+            }
+            if (!rc && opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(dt_next).c_str(), fmt_g(t).c_str());
+        } else {
+            const double theta = opt.ts_type == TS_CN ? 0.5 : 1.0;
+            double dt_last = opt.ts_dt;
+            while (t < tmax - 1e-14 * std::max(1.0, fabs(tmax)) && k < opt.ts_max_steps && !rc) {
+                const double dt = std::min(opt.ts_dt, tmax - t);     // TS_EXACTFINALTIME_MATCHSTEP (:118)
+                dt_last = dt;
+                if (opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(dt).c_str(), fmt_g(t).c_str());
+                const double shift = 1.0 / (theta * dt);
+                ops->copy(n, Y, Yprev);
+                if (theta != 1.0) {
+                    ops->set(n, 0.0, Ydot);
+                    ops->pattern_ifunction(m, opt, Yprev, Ydot, affine);
+                    ops->pattern_rhsfunction(m, opt, Yprev, G);
+                    ops->axpy(n, -1.0, G, affine);
+                }
+                // F(W, (W - Yprev)/(theta dt)) - G(W) + (1 - theta)/theta [F(Yprev, 0) - G(Yprev)]
+                std::function<void(const double *, double *)> F = [&](const double *W, double *f) {
+                    ops->axpby(n, shift, W, -shift, Yprev, Ydot);
+                    ops->pattern_ifunction(m, opt, W, Ydot, f);
+                    ops->pattern_rhsfunction(m, opt, W, G);
+                    ops->axpy(n, -1.0, G, f);
+                    if (theta != 1.0) ops->axpy(n, (1.0 - theta) / theta, affine, f);
+                };
+                int its = 0;
+                const int reason = newton_solve(F, shift, Y, &its);
+                if (rc) break;
+                if (reason <= 0) { rc = 64; break; }
+                t += dt;
+                R->newton_its_total += its;
+                record(dt, its);
+                R->dt_last = dt;
+                k++;
+                if (ops->error()) rc = ops->error();
+            }
+            if (!rc && opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(dt_last).c_str(), fmt_g(t).c_str());
         }
-        if (!rc && opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(dt_last).c_str(), fmt_g(t).c_str());
     }
     R->nsteps = k;
     R->t_final = t;
     if (!rc && opt.call_back_report && !Y0) {                                   // pattern.c:127-135
-        const char *name = opt.ts_type == TS_ARKIMEX ? "arkimex" : (opt.ts_type == TS_CN ? "cn" : "beuler");
+        const char *name = opt.ts_type == TS_ARKIMEX ? "arkimex" : (opt.ts_type == TS_CN ? "cn" : (opt.ts_type == TS_BDF ? "bdf" : "beuler"));
         pr.out("CALL-BACK REPORT");
         pr.out("  solver type: %s", name);
         pr.out("  IFunction:   1  | IJacobian:   1");

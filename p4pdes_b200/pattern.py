@@ -109,9 +109,8 @@ def parse_options(argv) -> PatternOptions:
             raise ValueError("%s is not provided by the device path (PETSc random stream / finite-difference IJacobian)" % a)
         else:
             raise ValueError("unknown or unsupported option %s" % a)
-    if o.ts_type not in ("arkimex", "beuler", "cn"):
-        raise ValueError("-ts_type %s: the device path provides arkimex (pattern.c's default), beuler and cn; bdf is "
-                         "not built" % o.ts_type)
+    if o.ts_type not in ("arkimex", "beuler", "cn", "bdf"):
+        raise ValueError("-ts_type %s: the device path provides arkimex (pattern.c's default), beuler, cn and bdf" % o.ts_type)
     if o.pc_type not in ("mg", "none"):
         raise ValueError("-pc_type %s: the device path provides mg and none (ilu/sor are sequential)" % o.pc_type)
     return o
@@ -260,7 +259,7 @@ def _pattern_native(opt: PatternOptions, ctx, out) -> PatternReport:
     o.L, o.Du, o.Dv, o.phi, o.kappa = opt.L, opt.Du, opt.Dv, opt.phi, opt.kappa
     o.no_rhsjacobian, o.call_back_report = int(opt.no_rhsjacobian), int(opt.call_back_report)
     o.grid_x, o.grid_y, o.refine = opt.grid_x, opt.grid_y, opt.refine
-    o.ts_type = {"arkimex": 0, "beuler": 1, "cn": 2}[opt.ts_type]
+    o.ts_type = {"arkimex": 0, "beuler": 1, "cn": 2, "bdf": 3}[opt.ts_type]
     o.ts_dt, o.ts_max_time, o.ts_max_steps = opt.ts_dt, opt.ts_max_time, opt.ts_max_steps
     o.ts_rtol, o.ts_atol, o.ts_monitor = opt.ts_rtol, opt.ts_atol, int(opt.ts_monitor)
     o.pc_type, o.smooth_its, o.mg_rscale = {"none": 0, "mg": 1}[opt.pc_type], opt.smooth_its, opt.mg_rscale
@@ -297,6 +296,8 @@ def pattern_main(argv, ops, echo=False, native=False) -> PatternReport:
         rep = _pattern_native(opt, ops, out)
         rep.lines = lines
         return rep
+    if opt.ts_type == "bdf":
+        raise ValueError("-ts_type bdf is provided by the native host (csrc/ts_solver.hpp): pass native=True")
 
     mx, my = opt.grid_x * 2 ** opt.refine, opt.grid_y * 2 ** opt.refine     # periodic: -da_refine doubles
     if mx != my:

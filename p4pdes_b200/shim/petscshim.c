@@ -1417,8 +1417,9 @@ PetscErrorCode TSSolve(TS ts, Vec x) {
     if (!strcmp(ts->type, TSARKIMEX)) o.ts_type = 0;
     else if (!strcmp(ts->type, TSBEULER)) o.ts_type = 1;
     else if (!strcmp(ts->type, TSCN)) o.ts_type = 2;
+    else if (!strcmp(ts->type, TSBDF)) o.ts_type = 3;
     else {
-        snprintf(msg, sizeof msg, "-ts_type %s is not provided on the device path (arkimex, beuler, cn are)", ts->type);
+        snprintf(msg, sizeof msg, "-ts_type %s is not provided on the device path (arkimex, beuler, cn, bdf are)", ts->type);
         SHIM_ERR(56, msg);
     }
     if (ts->t0 != 0.0) SHIM_ERR(56, "TSSolve: the device path starts at t = 0 (pattern.c:116)");

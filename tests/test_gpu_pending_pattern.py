@@ -10,8 +10,8 @@ import torch
 
 from p4pdes_b200 import pattern as pp
 from p4pdes_b200.fish import Context
-from tests.test_pattern_cpu import (GOLDEN_TEST1, GOLDEN_TEST2, GOLDEN_TEST3, GOLDEN_TEST4, TEST1, TEST2, TEST3,
-                                    TEST4)
+from tests.test_pattern_cpu import (GOLDEN_TEST1, GOLDEN_TEST2, GOLDEN_TEST3, GOLDEN_TEST4, GOLDEN_TEST5, TEST1, TEST2,
+                                    TEST3, TEST4, TEST5)
 
 pytestmark = [pytest.mark.gpu_pending, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
 
@@ -56,7 +56,7 @@ def test_golden_pattern_test3_crank_nicolson_on_device(ctx):
 
 
 @pytest.mark.parametrize("argv,golden", [(TEST1, GOLDEN_TEST1), (TEST2, GOLDEN_TEST2), (TEST3, GOLDEN_TEST3),
-                                         (TEST4, GOLDEN_TEST4)])
+                                         (TEST4, GOLDEN_TEST4), (TEST5 + " -pc_type mg", GOLDEN_TEST5)])
 def test_native_time_stepper_on_device(ctx, argv, golden):
     """p4b_pattern_solve (host logic in C++ inside the library, csrc/ts_solver.hpp; CPU-checked against the same goldens
     in tests/test_native_nk_cpu.py) on the device: step sizes as numbers, everything else verbatim."""

@@ -26,7 +26,7 @@ def run(argv):
 
 @pytest.mark.parametrize("name,extra", [("pattern.test1", " -pc_type none"), ("pattern.test1", MG),
                                         ("pattern.test2", " -mg_levels_pc_type jacobi"), ("pattern.test3", " -pc_type none"),
-                                        ("pattern.test4", MG)])
+                                        ("pattern.test4", MG), ("pattern.test5", MG)])
 def test_goldens_verbatim_on_device(name, extra):
     g = GOLD[name]
     assert run(g["options"] + extra) == g["lines"]

@@ -89,14 +89,15 @@ def test_banded_inverse_agrees_with_lapack(exe):
 
 
 # ---- pattern.c: the native time-stepping host (csrc/ts_solver.hpp) against the reference's goldens --------------------
-from tests.test_pattern_cpu import (GOLDEN_TEST1, GOLDEN_TEST2, GOLDEN_TEST3, GOLDEN_TEST4, TEST1, TEST2, TEST3,  # noqa: E402
-                                    TEST4)
+from tests.test_pattern_cpu import (GOLDEN_TEST1, GOLDEN_TEST2, GOLDEN_TEST3, GOLDEN_TEST4, GOLDEN_TEST5, TEST1,  # noqa: E402
+                                    TEST2, TEST3, TEST4, TEST5)
 
 
 @pytest.mark.parametrize("argv,golden", [(TEST1, GOLDEN_TEST1), (TEST2, GOLDEN_TEST2), (TEST3, GOLDEN_TEST3),
-                                         (TEST4, GOLDEN_TEST4)])
+                                         (TEST4, GOLDEN_TEST4), (TEST5 + " -pc_type none", GOLDEN_TEST5),
+                                         (TEST5 + " -pc_type mg", GOLDEN_TEST5)])
 def test_native_time_stepper_prints_the_pattern_goldens_verbatim(exe, argv, golden):
-    """c/ch5/output/pattern.test1-4: adaptive ARKIMEX3 (incl. the rejected step), backward Euler, Crank-Nicolson."""
+    """c/ch5/output/pattern.test1-5: adaptive ARKIMEX3 (incl. the rejected step), backward Euler, Crank-Nicolson, BDF2."""
     lines, d = run(exe, "-pattern", *argv.split())
     assert lines == golden
     assert d["allocs"] == d["frees"]
@@ -136,3 +137,16 @@ def test_reference_callback_drives_the_native_solver(exe):
     _, own = run(exe, "-snes_fd_color", "-ms_problem", "tent", "-snes_grid_sequence", 2, "-pc_type", "mg")
     assert [s["ksp_its"] for s in d["stages"]] == [s["ksp_its"] for s in own["stages"]]
     assert abs(d["sum"] - own["sum"]) <= 1e-9 * abs(own["sum"])
+
+
+def test_native_bdf_matches_the_oracle_on_an_adaptive_run(exe):
+    """Nothing pins BDF beyond the restart step (pattern.test5): the C++ host and the NumPy oracle, two statements of the
+    same algorithm, print the same 25 adaptive steps (5 rejections) to every digit."""
+    from oracle import pattern_solver_oracle as po
+    for extra in (("-pc_type", "none", "-ksp_rtol", "1e-10"), ("-pc_type", "mg")):
+        lines, d = run(exe, "-pattern", "-da_grid_x", 4, "-da_grid_y", 4, "-da_refine", 2, "-ts_type", "bdf", "-ts_monitor", *extra)
+        o = po.pattern_bdf(grid=4, refine=2, dt=5.0, tmax=200.0)
+        assert [l for l in lines if " TS dt " in l] == [l for l in o.lines if " TS dt " in l]
+        assert (d["nsteps"], d["rejected"]) == (len(o.steps), o.rejected) and o.rejected == 5
+        want = float((o.Y[..., 0] + 3.0 * o.Y[..., 1]).sum())
+        assert abs(d["sum"] - want) <= 1e-8 * abs(want)

@@ -56,7 +56,8 @@ def test_driver_matches_oracle(argv, okw):
 
 
 @pytest.mark.parametrize("argv,msg", [
-    ("-da_refine 2 -ts_type bdf", "arkimex"),                             # bdf / cn are not built
+    ("-da_refine 2 -ts_type rk", "arkimex"),
+    ("-da_refine 2 -ts_type bdf -pc_type none", "native=True"),           # bdf lives in the native host only
     ("-ts_type beuler -pc_type ilu", "sequential"),
     ("-ts_type beuler -ptn_noisy_init 0.2", "not provided"),
     ("-ts_type beuler -da_grid_x 4 -da_grid_y 6", "requires mx == my"),   # pattern.c:89
@@ -201,3 +202,33 @@ def test_bdf_restart_step_golden_pattern_test5():
     (n1, n2), hnext, _ = po.pattern_bdf_first_step(grid=3, refine=4, dt=1.0)
     assert (n1, n2) == (3, 2)                               # pattern.test5:3-4
     assert po.fmt_g(float("%.6g" % hnext)) == "1.10972"     # pattern.test5:5  "1 TS dt 1.10972 time 1."
+
+
+GOLDEN_TEST5 = """running on 48 x 48 grid with square cells of side h = 0.052083 ...
+0 TS dt 1. time 0.
+    Nonlinear solve converged due to CONVERGED_FNORM_RELATIVE iterations 3
+    Nonlinear solve converged due to CONVERGED_FNORM_RELATIVE iterations 2
+1 TS dt 1.10972 time 1.
+CALL-BACK REPORT
+  solver type: bdf
+  IFunction:   1  | IJacobian:   1
+  RHSFunction: 1  | RHSJacobian: 1""".split("\n")
+TEST5 = "-da_refine 4 -ptn_call_back_report -ts_type bdf -ts_max_time 1 -snes_converged_reason -ts_monitor"   # c/ch5/makefile:62
+
+
+def test_bdf_oracle_every_step():
+    """The full BDF2 stepping of the oracle: pattern.test5's solver lines verbatim (the restart step is all the golden
+    holds), and -- since nothing pins the later steps -- their order of accuracy with fixed steps: error ratios ~4."""
+    ref = "/root/reference/c/ch5/output/pattern.test5"
+    if os.path.exists(ref):
+        assert open(ref).read().rstrip("\n").split("\n") == GOLDEN_TEST5
+    r = po.pattern_bdf(grid=3, refine=4, dt=5.0, tmax=1.0)
+    assert r.lines == GOLDEN_TEST5[:5] and r.newton_counts == [3, 2]
+    fine = po.pattern_bdf(grid=3, refine=2, dt=0.125, tmax=8.0, adapt=False, snes_rtol=1e-12).Y
+    err = [np.abs(po.pattern_bdf(grid=3, refine=2, dt=dt, tmax=8.0, adapt=False, snes_rtol=1e-12).Y - fine).max()
+           for dt in (2.0, 1.0, 0.5)]
+    assert 3.5 < err[0] / err[1] < 4.5 and 3.5 < err[1] / err[2] < 4.7
+    # adaptive: rejections happen, the final time is matched, and the answer agrees with ARKIMEX to the controller's tolerance
+    a = po.pattern_bdf(grid=4, refine=2, dt=5.0, tmax=200.0)
+    b = po.pattern_arkimex(grid=4, refine=2, dt=5.0, tmax=200.0)
+    assert a.rejected > 0 and a.steps[-1][0] == 200.0 and np.abs(a.Y - b.Y).max() < 5e-2

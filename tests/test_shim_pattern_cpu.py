@@ -55,6 +55,8 @@ def run(exe, argv, check=True):
     ("pattern.test3", " -pc_type none"),       # Crank-Nicolson, -snes_fd_color
     ("pattern.test4", MG),                     # incl. the rejected step and pattern.c's own CALL-BACK REPORT
     ("pattern.test4", " -pc_type none"),
+    ("pattern.test5", " -pc_type none"),       # BDF2: the restart step; all four callbacks are called (and checked)
+    ("pattern.test5", MG),
 ])
 def test_goldens_verbatim(exe, name, extra):
     g = GOLD[name]
@@ -90,7 +92,7 @@ def test_model_parameters_are_identified_from_the_callbacks(exe):
 @pytest.mark.parametrize("argv,code,msg", [
     ("-da_refine 2", 56, "ILU"),
     ("-da_refine 2 -pc_type mg", 56, "SOR"),
-    ("-da_refine 2 -pc_type none -ts_type bdf", 56, "-ts_type bdf is not provided"),
+    ("-da_refine 2 -pc_type none -ts_type rk", 56, "-ts_type rk is not provided"),
     ("-da_refine 2 -pc_type none -ptn_no_ijacobian", 56, "no IJacobian callback registered"),
     ("-da_refine 2 -pc_type none -ptn_noisy_init 0.2", 56, "VecSetRandom"),
     ("-da_grid_x 4 -da_refine 2 -pc_type none", 1, "pattern.c requires mx == my"),
