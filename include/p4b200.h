@@ -126,7 +126,9 @@ int p4b_device_count(int *n);
  * waits for the neighbours' flags; 0 = one push kernel per exchange;
  * measurement-only keys: "force_mg" 1|2 (run the multi-GPU kernel variants on ONE GPU: 1 = no neighbours, 2 = scratch
  * memory on this device stands in for both neighbours) and "port_opts" (bit 0: natural chunk order and march
- * direction, bit 1: signal at the end of the boundary CTAs' work) -- the A/B switches behind DESIGN.md section 5 */
+ * direction, bit 1: signal at the end of the boundary CTAs' work) -- the A/B switches behind DESIGN.md section 5;
+ * "recognise_residual" 0|1 (p4b_snes2d_solve): 1 (default) = probe the caller's residual callback and keep the residual on
+ * the device when it is the model the library has as a kernel, 0 = evaluate the callback on the host every time */
 int p4b_tune(const char *key, long value);
 
 /* ---- context ---- */
@@ -329,7 +331,13 @@ int p4b_snes2d_solve(p4b_ctx *ctx, const p4b_minimal_opts *opts, p4b_residual2d_
  * on the host before the first and after every Newton iteration of every grid-sequence stage, ahead of the -snes_monitor
  * line, with the current iterate on that stage's grid; tablevel = the stages still to come ([PETSc] PetscObjectGetTabLevel
  * of the SNES under -snes_grid_sequence).  A non-zero return aborts the solve (error 66).  monitor may be NULL. */
+/* Recognition: before the solve the residual callback is probed on every grid the solve will touch (F(0) gives the
+ * Dirichlet data, a generic iterate the exponent q, a second one the check; 2 evaluations per grid + 1).  If it IS
+ * c/ch7/minimal.c:210-282 -- the unchanged minimal.c under the shim -- to rounding, the solve keeps the residual on the
+ * device (minimal_function_kernel) and calls the callback no more; otherwise every evaluation is a host callback (nine per
+ * level Jacobian).  p4b_snes2d_last_route(): 1 = device residual after recognition, 0 = host callbacks. */
 typedef int (*p4b_monitor2d_fn)(void *user, int mx, int my, int its, double fnorm, int tablevel, const double *u_host);
+int p4b_snes2d_last_route(void);
 int p4b_snes2d_solve_monitored(p4b_ctx *ctx, const p4b_minimal_opts *opts, p4b_residual2d_fn residual,
                                p4b_monitor2d_fn monitor, void *user, const double *u0_host, p4b_line_fn line, void *line_ctx,
                                double *u_out_host, size_t u_capacity, p4b_minimal_result *result);

@@ -31,11 +31,18 @@ static int fail(int code, const char *msg) {
 }
 
 struct p4b_ctx { int unused; };
+static int g_route = 0, g_recognise = 1;
+static long long g_callbacks = 0;
 struct p4b_mg { p4b_grid g; double diag, c[3]; };
 
 extern "C" {
 
 const char *p4b_last_error(void) { return g_err; }
+int p4b_snes2d_last_route(void) { return g_route; }
+int p4b_tune(const char *key, long value) {
+    if (!strcmp(key, "recognise_residual")) { g_recognise = (int)value; return 0; }
+    return fail(62, "stand-in: unknown tuning key");
+}
 long long p4b_launch_count(void) { return 0; }
 int p4b_ctx_create(int, void *, p4b_ctx **ctx) { *ctx = new p4b_ctx{0}; return 0; }
 int p4b_ctx_destroy(p4b_ctx *ctx) { delete ctx; return 0; }
@@ -63,21 +70,50 @@ int p4b_snes2d_solve_monitored(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_res
     if (!c || !opts || !residual || !u0_host || !result) return fail(62, "p4b_snes2d_solve: null argument");
     const nk::MinimalOpts &o = *reinterpret_cast<const nk::MinimalOpts *>(opts);
     if (o.grid_x < 3 || o.grid_y < 3) return fail(60, "grid needs at least 3 nodes per dimension");
-    HostCallbackOps ops;
-    ops.fn = residual;
-    ops.mon = monitor;
-    ops.user = user;
     nk::Printer pr{line, line_ctx};
     double *u = nullptr;
     nk::MinimalResult &R = *reinterpret_cast<nk::MinimalResult *>(result);
-    int rc = nk::minimal_solve(&ops, o, pr, u_out_host ? &u : nullptr, &R, u0_host, false);
-    if (!rc && ops.error()) rc = ops.error();
-    if (!rc && u_out_host) {
-        const size_t n = (size_t)R.mx * R.my;
-        if (u_capacity < n) rc = 63;
-        else memcpy(u_out_host, u, sizeof(double) * n);
+    int rc = 0;
+    g_route = 0;
+    g_callbacks = 0;
+    HostOps base;
+    nk::ProbedModel model;
+    auto resid = [&](int mx, int my, const double *uh, double *Fh) { g_callbacks++; return residual(user, mx, my, uh, Fh); };
+    if (g_recognise && nk::probe_minimal_model(&base, resid, o, &model)) {            // as nk_device.cu does
+        nk::ModelOps<HostOps> ops(base);
+        ops.model = &model;
+        if (monitor)
+            ops.monitor = [&](int mx, int my, int its, double fnorm, int tab, const double *uh) {
+                return monitor(user, mx, my, its, fnorm, tab, uh);
+            };
+        nk::MinimalOpts o2 = o;
+        o2.q = model.q;
+        g_route = 1;
+        rc = nk::minimal_solve(&ops, o2, pr, u_out_host ? &u : nullptr, &R, u0_host, false);
+        if (!rc && ops.error()) rc = ops.error();
+        if (!rc && u_out_host) {
+            const size_t n = (size_t)R.mx * R.my;
+            if (u_capacity < n) rc = 63;
+            else memcpy(u_out_host, u, sizeof(double) * n);
+        }
+        if (u) ops.release(u);
+    } else {
+        HostCallbackOps ops;
+        ops.fn = residual;
+        ops.mon = monitor;
+        ops.user = user;
+        rc = nk::minimal_solve(&ops, o, pr, u_out_host ? &u : nullptr, &R, u0_host, false);
+        if (!rc && ops.error()) rc = ops.error();
+        if (!rc && u_out_host) {
+            const size_t n = (size_t)R.mx * R.my;
+            if (u_capacity < n) rc = 63;
+            else memcpy(u_out_host, u, sizeof(double) * n);
+        }
+        if (u) ops.release(u);
+        g_callbacks += ops.callbacks;
     }
-    if (u) ops.release(u);
+    if (getenv("P4B_STANDIN_REPORT"))
+        fprintf(stderr, "standin: route %d, q %.17g, residual callbacks %lld\n", g_route, model.q, g_callbacks);
     if (rc == 61) return fail(61, "base grid of the multigrid hierarchy is larger than 65 x 65: use a coarser base grid");
     if (rc == 62) return fail(62, "base-grid Jacobian is singular");
     if (rc == 63) return fail(63, "u_out is too small for the final grid");

@@ -861,6 +861,7 @@ static int plan_levels(const p4b_grid *g, const p4b_mg_opts &o, int P, LevelPlan
 
 namespace p4b {
 cudaStream_t ctx_stream(p4b_ctx *c) { return c->stream; }     // for the other translation units (nk_device.cu)
+extern long long g_recognise_residual;                        // defined in nk_device.cu
 }  // namespace p4b
 
 extern "C" {
@@ -877,6 +878,7 @@ int p4b_tune(const char *key, long value) {
     if (std::string(key) == "fused_halo") { g_fused_halo = value; return 0; }
     if (std::string(key) == "port_opts") { g_port_opts = value; return 0; }
     if (std::string(key) == "force_mg") { g_force_mg = value; return 0; }
+    if (std::string(key) == "recognise_residual") { g_recognise_residual = value; return 0; }
     return fail(62, "unknown tuning key %s", key);
 }
 

@@ -199,25 +199,60 @@ extern "C" int p4b_snes2d_solve(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_re
     return p4b_snes2d_solve_monitored(c, opts, residual, nullptr, user, u0_host, line, line_ctx, u_out_host, u_capacity, result);
 }
 
+namespace p4b {
+long long g_recognise_residual = 1;     // p4b_tune("recognise_residual", 0): always evaluate the caller's residual on the host
+}
+static int g_snes2d_route = 0;
+
+extern "C" int p4b_snes2d_last_route(void) { return g_snes2d_route; }
+
 extern "C" int p4b_snes2d_solve_monitored(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_residual2d_fn residual,
                                           p4b_monitor2d_fn monitor, void *user, const double *u0_host, p4b_line_fn line,
                                           void *line_ctx, double *u_out_host, size_t u_capacity, p4b_minimal_result *result) {
     if (!c || !opts || !residual || !u0_host || !result) return fail(62, "p4b_snes2d_solve: null argument");
     const nk::MinimalOpts &o = *reinterpret_cast<const nk::MinimalOpts *>(opts);
     if (o.grid_x < 3 || o.grid_y < 3) return fail(60, "grid needs at least 3 nodes per dimension");
-    CallbackOps ops(c, ctx_stream(c), residual, monitor, user);
     nk::Printer pr{line, line_ctx};
     double *u = nullptr;
     nk::MinimalResult &R = *reinterpret_cast<nk::MinimalResult *>(result);
-    int rc = nk::minimal_solve(&ops, o, pr, u_out_host ? &u : nullptr, &R, u0_host, false);
-    if (!rc && ops.error()) rc = ops.error();
-    if (!rc && u_out_host) {
-        const size_t n = (size_t)R.mx * R.my;
-        if (u_capacity < n) rc = 63;
-        else ops.to_host(u, u_out_host, n);
+    cudaStream_t st = ctx_stream(c);
+    int rc = 0;
+    g_snes2d_route = 0;
+    // is the caller's residual the one this library has as a kernel (c/ch7/minimal.c:210-282)?  nk_solver.hpp, "Recognising
+    // the caller's residual": probe it on every grid of the solve; on agreement the residual stays on the device
+    DeviceOps base{c, st};
+    nk::ProbedModel model;
+    auto resid = [&](int mx, int my, const double *uh, double *Fh) { return residual(user, mx, my, uh, Fh); };
+    if (g_recognise_residual && nk::probe_minimal_model(&base, resid, o, &model) && !base.error()) {
+        nk::ModelOps<DeviceOps> ops(base);
+        ops.model = &model;
+        if (monitor)
+            ops.monitor = [&](int mx, int my, int its, double fnorm, int tab, const double *uh) {
+                return monitor(user, mx, my, its, fnorm, tab, uh);
+            };
+        nk::MinimalOpts o2 = o;
+        o2.q = model.q;
+        g_snes2d_route = 1;
+        rc = nk::minimal_solve(&ops, o2, pr, u_out_host ? &u : nullptr, &R, u0_host, false);
+        if (!rc && ops.error()) rc = ops.error();
+        if (!rc && u_out_host) {
+            const size_t n = (size_t)R.mx * R.my;
+            if (u_capacity < n) rc = 63;
+            else ops.to_host(u, u_out_host, n);
+        }
+    } else {
+        if (base.error()) return fail(base.error(), "p4b_snes2d_solve: probing the residual failed (%s)", p4b_last_error());
+        CallbackOps ops(c, st, residual, monitor, user);
+        rc = nk::minimal_solve(&ops, o, pr, u_out_host ? &u : nullptr, &R, u0_host, false);
+        if (!rc && ops.error()) rc = ops.error();
+        if (!rc && u_out_host) {
+            const size_t n = (size_t)R.mx * R.my;
+            if (u_capacity < n) rc = 63;
+            else ops.to_host(u, u_out_host, n);
+        }
     }
-    if (u) cudaFreeAsync(u, ops.st);
-    cudaStreamSynchronize(ops.st);
+    if (u) cudaFreeAsync(u, st);
+    cudaStreamSynchronize(st);
     if (rc == 61) return fail(61, "base grid of the multigrid hierarchy is larger than 65 x 65: use a coarser base grid");
     if (rc == 62) return fail(62, "base-grid Jacobian is singular");
     if (rc == 63) return fail(63, "u_out holds %zu doubles, the final grid needs %d x %d", u_capacity, R.mx, R.my);

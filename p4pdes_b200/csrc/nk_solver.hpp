@@ -17,9 +17,11 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -538,6 +540,32 @@ int newton(Ops *ops, std::vector<Level<Ops>> &lev, const MinimalOpts &opt, const
     return rc;
 }
 
+// the grids of one grid-sequence stage, finest first: [PETSc] PCMG coarsens the DMDA down to the -da_grid_x/_y base grid
+// (or -pc_mg_levels); -pc_type none has the one grid
+inline std::vector<std::pair<int, int>> level_shapes(const MinimalOpts &opt, int fx, int fy) {
+    std::vector<std::pair<int, int>> s{{fx, fy}};
+    if (opt.pc_type != PC_MG) return s;
+    while (opt.mg_levels ? (int)s.size() < opt.mg_levels : true) {
+        const int cx = s.back().first, cy = s.back().second;
+        if (cx <= 3 || cy <= 3 || (cx - 1) % 2 || (cy - 1) % 2) break;
+        if (!opt.mg_levels && cx == opt.grid_x && cy == opt.grid_y) break;
+        s.push_back({(cx - 1) / 2 + 1, (cy - 1) / 2 + 1});
+    }
+    return s;
+}
+// every grid a solve will touch (all stages of the grid sequence, all levels)
+inline std::vector<std::pair<int, int>> all_shapes(const MinimalOpts &opt) {
+    std::vector<std::pair<int, int>> out;
+    int mx = opt.grid_x, my = opt.grid_y;
+    for (int r = 0; r < opt.refine; r++) { mx = 2 * mx - 1; my = 2 * my - 1; }
+    for (int stage = 0; stage <= opt.grid_sequence; stage++) {
+        if (stage > 0) { mx = 2 * mx - 1; my = 2 * my - 1; }
+        for (auto &p : level_shapes(opt, mx, my))
+            if (std::find(out.begin(), out.end(), p) == out.end()) out.push_back(p);
+    }
+    return out;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // minimal.c:main from DMDACreate2d to the error report (c/ch7/minimal.c:128-181)
 // u_out: the final iterate (mx*my doubles in Ops memory, nullptr = not wanted; mx, my are in the result)
@@ -553,22 +581,12 @@ int minimal_solve(Ops *ops, const MinimalOpts &opt, const Printer &pr, double **
     if (opt.grid_sequence + 1 > MAX_STAGES) return 60;
     int mx = opt.grid_x, my = opt.grid_y;
     for (int r = 0; r < opt.refine; r++) { mx = 2 * mx - 1; my = 2 * my - 1; }
-    auto hierarchy = [&](int fx, int fy) {
-        std::vector<std::pair<int, int>> s{{fx, fy}};
-        while (opt.mg_levels ? (int)s.size() < opt.mg_levels : true) {
-            const int cx = s.back().first, cy = s.back().second;
-            if (cx <= 3 || cy <= 3 || (cx - 1) % 2 || (cy - 1) % 2) break;
-            if (!opt.mg_levels && cx == opt.grid_x && cy == opt.grid_y) break;
-            s.push_back({(cx - 1) / 2 + 1, (cy - 1) / 2 + 1});
-        }
-        return s;
-    };
     double *u_prev = nullptr;
     int rc = 0;
     std::vector<Level<Ops>> lev;
     for (int stage = 0; stage <= opt.grid_sequence && !rc; stage++) {
         if (stage > 0) { mx = 2 * mx - 1; my = 2 * my - 1; }
-        std::vector<std::pair<int, int>> shapes = (opt.pc_type == PC_MG) ? hierarchy(mx, my) : std::vector<std::pair<int, int>>{{mx, my}};
+        std::vector<std::pair<int, int>> shapes = level_shapes(opt, mx, my);
         std::vector<Level<Ops>> next(shapes.size());
         for (size_t l = 0; l < shapes.size(); l++) next[l].create(ops, shapes[l].first, shapes[l].second, opt);
         Level<Ops> &L = next[0];
@@ -608,6 +626,149 @@ int minimal_solve(Ops *ops, const MinimalOpts &opt, const Printer &pr, double **
     R->error = rc;
     return rc;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Recognising the caller's residual.  p4b_snes2d_solve takes the residual as a HOST callback (the FormFunctionLocal
+// contract).  When that callback is c/ch7/minimal.c:210-282 itself -- the unchanged minimal.c under the PETSc-shaped shim --
+// the library holds the same function as a kernel, and nine host evaluations per level Jacobian are nine too many.  So,
+// before the solve, the callback is probed on every grid the solve will touch:
+//   g      F(0) on the boundary rows is -g (minimal.c:227): the Dirichlet data of that grid, whatever g_bdry the caller uses
+//   q      the one number of the model: the value for which the kernel reproduces the callback at a generic iterate
+//          (-1/2 is tried first; otherwise a secant iteration on a fixed functional of F_kernel(q) - F_callback)
+//   check  at a second generic iterate, on EVERY grid, kernel and callback must agree to rounding
+// If all of that holds the solve runs with the residual on the device (ModelOps below: minimal_sample hands out the probed
+// g); if anything does not, the caller's residual is not that model and the solve evaluates the callback on the host
+// every time (CallbackOps).  Monitors are host callbacks either way.
+// ---------------------------------------------------------------------------------------------------------
+struct ProbedModel {
+    bool ok = false;
+    double q = 0.0;
+    int callbacks = 0;
+    std::vector<std::pair<std::pair<int, int>, std::vector<double>>> g;     // per grid: Dirichlet data (interior entries 0)
+    const std::vector<double> *find(int mx, int my) const {
+        for (auto &e : g)
+            if (e.first.first == mx && e.first.second == my) return &e.second;
+        return nullptr;
+    }
+};
+
+// resid(mx, my, u_host, F_host) -> 0 on success: the caller's callback
+template <class Ops, class Resid>
+bool probe_minimal_model(Ops *ops, Resid resid, const MinimalOpts &opt, ProbedModel *M) {
+    M->ok = false;
+    unsigned long long lcg = 0x2545F4914F6CDD1DULL;
+    auto rnd = [&]() { lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL; return (double)(lcg >> 11) / 9007199254740992.0; };
+    bool first = true;
+    for (auto &shape : all_shapes(opt)) {
+        const int mx = shape.first, my = shape.second;
+        const size_t n = (size_t)mx * my;
+        std::vector<double> u(n, 0.0), Fu(n), Fd(n), g(n, 0.0);
+        auto bd = [&](size_t k) { const int j = (int)(k / mx), i = (int)(k - (size_t)j * mx); return i == 0 || j == 0 || i == mx - 1 || j == my - 1; };
+        if (resid(mx, my, u.data(), Fu.data())) return false;                       // F(0): boundary rows are 0 - g
+        M->callbacks++;
+        for (size_t k = 0; k < n; k++) {
+            if (Fu[k] != Fu[k]) return false;
+            if (bd(k)) g[k] = -Fu[k];
+        }
+        double *dg = ops->alloc(n), *du = ops->alloc(n), *dF = ops->alloc(n);
+        ops->from_host(g.data(), dg, n);
+        auto kernel = [&](double q, std::vector<double> *out) {
+            ops->minimal_function(mx, my, q, du, dg, dF);
+            ops->to_host(dF, out->data(), n);
+        };
+        auto generic = [&]() {                                                     // g on the boundary, O(1) slopes inside
+            for (size_t k = 0; k < n; k++) u[k] = bd(k) ? g[k] + 0.1 * (rnd() - 0.5) : 0.5 * rnd();
+            ops->from_host(u.data(), du, n);
+        };
+        auto maxdiff = [&](const std::vector<double> &a, const std::vector<double> &b, double *scale) {
+            double d = 0.0, sc = 1.0;
+            for (size_t k = 0; k < n; k++) {
+                const double e = fabs(a[k] - b[k]);
+                if (!(e <= d)) d = e;
+                sc = std::max(sc, fabs(b[k]));
+            }
+            *scale = sc;
+            return d;
+        };
+        bool good = true;
+        double sc = 1.0;
+        if (first) {                                                                // identify q on the first grid
+            generic();
+            good = !resid(mx, my, u.data(), Fu.data());
+            M->callbacks++;
+            if (good) {
+                kernel(-0.5, &Fd);
+                if (maxdiff(Fd, Fu, &sc) <= 1.0e-11 * sc) M->q = -0.5;
+                else {
+                    std::vector<double> F0(n), F1(n), w(n);
+                    double q0 = -0.5, q1 = 0.0;
+                    F0 = Fd;
+                    kernel(q1, &F1);
+                    for (size_t k = 0; k < n; k++) w[k] = F1[k] - F0[k];
+                    auto phi = [&](const std::vector<double> &F) { double s2 = 0.0; for (size_t k = 0; k < n; k++) s2 += w[k] * (F[k] - Fu[k]); return s2; };
+                    double p0 = phi(F0), p1 = phi(F1);
+                    for (int it = 0; it < 40 && p1 != p0 && p1 != 0.0; it++) {
+                        const double q2 = q1 - p1 * (q1 - q0) / (p1 - p0);
+                        if (!(fabs(q2) < 50.0)) { good = false; break; }
+                        q0 = q1; p0 = p1; q1 = q2;
+                        kernel(q1, &F1);
+                        p1 = phi(F1);
+                        if (fabs(q1 - q0) <= 1.0e-15 * std::max(1.0, fabs(q1))) break;
+                    }
+                    char txt[64];                                                   // an option typed as "-0.3" is strtod("-0.3")
+                    snprintf(txt, sizeof txt, "%.12g", q1);
+                    const double snapped = atof(txt);
+                    kernel(snapped, &Fd);
+                    if (good && maxdiff(Fd, Fu, &sc) <= 1.0e-11 * sc) M->q = snapped;
+                    else {
+                        kernel(q1, &Fd);
+                        if (good && maxdiff(Fd, Fu, &sc) <= 1.0e-11 * sc) M->q = q1;
+                        else good = false;
+                    }
+                }
+            }
+            first = false;
+        }
+        if (good) {                                                                 // verify on this grid
+            generic();
+            good = !resid(mx, my, u.data(), Fu.data());
+            M->callbacks++;
+            if (good) {
+                kernel(M->q, &Fd);
+                good = maxdiff(Fd, Fu, &sc) <= 1.0e-11 * sc;
+            }
+        }
+        ops->release(dg);
+        ops->release(du);
+        ops->release(dF);
+        if (!good || ops->error()) return false;
+        M->g.push_back({shape, std::move(g)});
+    }
+    M->ok = true;
+    return true;
+}
+
+// Base (DeviceOps in the library, HostOps in the CPU harness) with the probed Dirichlet data behind minimal_sample and
+// the caller's monitor behind user_monitor
+template <class Base>
+struct ModelOps : Base {
+    const ProbedModel *model = nullptr;
+    std::function<int(int, int, int, double, int, const double *)> monitor;
+    std::vector<double> hu;
+    explicit ModelOps(const Base &b) : Base(b) {}
+    void minimal_sample(int mx, int my, int, double, double, double *g) {
+        const std::vector<double> *h = model->find(mx, my);
+        if (!h) { if (!this->err) this->err = 67; return; }
+        this->from_host(h->data(), g, h->size());
+    }
+    void user_monitor(int mx, int my, int its, double fnorm, int tablevel, const double *u) {
+        if (!monitor || this->err) return;
+        const size_t n = (size_t)mx * my;
+        hu.resize(n);
+        this->to_host(u, hu.data(), n);
+        if (!this->err && monitor(mx, my, its, fnorm, tablevel, hu.data())) this->err = 66;
+    }
+};
 
 }  // namespace nk
 }  // namespace p4b

@@ -32,6 +32,7 @@ static p4b_ctx *g_ctx = NULL;
 static double g_flops = 0.0;
 static double g_t_snes = 0.0, g_t_ksp = 0.0, g_t_ksp_dev_ms = 0.0, g_t_jac = 0.0, g_t_func = 0.0;
 static int g_initialized = 0;
+static int g_newton_solves = 0;
 
 static double wall(void) {
     struct timespec ts;
@@ -112,6 +113,9 @@ PetscErrorCode PetscFinalize(void) {
         printf("             FunctionEval(host callback) %.6e   JacobianEval(host callback, all levels) %.6e\n",
                g_t_func, g_t_jac);
         printf("Flop:  %.6e (user PetscLogFlops only)   kernel launches: %lld\n", g_flops, p4b_launch_count());
+        if (g_newton_solves)
+            printf("SNES newtonls: residual %s\n", p4b_snes2d_last_route()
+                   ? "recognised as the library's kernel: evaluated on the device" : "evaluated by the host callback");
     }
     if (opt_has("-options_left")) {
         for (int i = 0; i < g_nopt; i++)
@@ -987,6 +991,11 @@ static PetscErrorCode snes_solve_newtonls(SNES snes, Vec x) {
     o.snes_converged_reason = snes->converged_reason_flag;
     o.ksp_converged_reason = ksp->converged_reason_flag;
     PetscCall(ensure_ctx());
+    {   /* -p4b_recognise_residual 0: evaluate the registered FormFunctionLocal on the host every time, also when it is the
+         * residual the library has as a kernel (p4b200.h, "Recognition") */
+        const char *v = opt_value("-p4b_recognise_residual");
+        P4B(p4b_tune("recognise_residual", v ? atol(v) : 1));
+    }
     const double t0 = wall();
     PetscCall(vec_to_host(x));
     int fx = dm->M[0], fy = dm->M[1];
@@ -1005,6 +1014,7 @@ static PetscErrorCode snes_solve_newtonls(SNES snes, Vec x) {
         free(R);
         return PetscShimError(PETSC_COMM_SELF, __LINE__, __func__, __FILE__, rc, p4b_last_error());
     }
+    g_newton_solves++;
     snes->its = R->stage[R->nstages - 1].its;
     snes->reason = R->stage[R->nstages - 1].reason;
     ksp->its = snes->its ? R->stage[R->nstages - 1].ksp_its[snes->its - 1] : 0;

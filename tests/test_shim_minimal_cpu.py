@@ -109,3 +109,70 @@ def test_solution_and_dm_after_grid_sequencing(exe):
 def test_error_paths(exe, argv, code, msg):
     _, p = run(exe, argv, check=False)
     assert p.returncode == code and msg in p.stderr and "PETSC ERROR" in p.stderr
+
+
+# ---- recognition of the registered residual (include/p4b200.h "Recognition"; csrc/nk_solver.hpp probe_minimal_model) ----
+def _route(p):
+    m = re.search(r"standin: route (\d), q (\S+), residual callbacks (\d+)", p.stderr)
+    return int(m.group(1)), float(m.group(2).rstrip(",")), int(m.group(3))
+
+
+def run_report(exe, argv):
+    p = subprocess.run([exe] + argv.split(), capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, P4B_STANDIN_REPORT="1"))
+    assert p.returncode == 0, p.stderr
+    return p.stdout.splitlines(), _route(p)
+
+
+def test_minimal_c_is_recognised_and_both_routes_print_the_same(exe):
+    """The unchanged minimal.c's FormFunctionLocal IS the residual the library has as a kernel: after 2 probes per grid + 1
+    the solve calls it no more.  With recognition switched off every evaluation is the host callback (hundreds); the
+    two routes print the same lines."""
+    g = GOLD["minimal.test4"]
+    a, (route, q, ncb) = run_report(exe, g["options"] + EXTRA)
+    assert a == g["lines"] and route == 1 and q == -0.5 and ncb == 2 * 3 + 1            # grids 3x3, 5x5, 9x9
+    b, (route0, _, ncb0) = run_report(exe, g["options"] + EXTRA + " -p4b_recognise_residual 0")
+    assert b == g["lines"] and route0 == 0 and ncb0 > 200
+    # another exponent and boundary problem, with the monitor: identified exactly as the option was parsed
+    argv = "-snes_fd_color -snes_converged_reason -da_refine 3 -ms_q -0.3 -ms_catenoid_c 1.3 -ms_monitor" + EXTRA
+    c, (route, q, _) = run_report(exe, argv)
+    d, (route0, _, _) = run_report(exe, argv + " -p4b_recognise_residual 0")
+    assert route == 1 and q == float("-0.3") and route0 == 0 and c == d
+
+
+@pytest.fixture(scope="module")
+def snes_variants(exe, tmp_path_factory):
+    d = tmp_path_factory.mktemp("sv")
+    obj, out = str(d / "sv.o"), str(d / "sv")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-c",
+                           os.path.join(ROOT, "tests", "shim_cases", "snes_variants.c"), "-o", obj])
+    o = os.path.join(ROOT, "oracle", "_ref", "obj")
+    subprocess.check_call(["g++", obj, os.path.join(o, "petscshim.o"), os.path.join(o, "p4b_standin.o"), "-o", out, "-lm"])
+    return out
+
+
+def test_a_residual_that_is_not_the_model_stays_a_host_callback(snes_variants):
+    """tests/shim_cases/snes_variants.c: the model written differently, with its own Dirichlet data and exponent, is
+    recognised; the model plus a reaction term is not, is solved through host callbacks, and its answer is the one an
+    independent NumPy Newton solve of the same equations gives."""
+    from oracle import fish_oracle as fo
+    from oracle import minimal_pattern_oracle as mpo
+    from oracle import minimal_solver_oracle as mo
+    argv = "-snes_fd_color -da_refine 2 -snes_rtol 1e-12" + EXTRA
+    a, (route, q, ncb) = run_report(snes_variants, "-variant 0 " + argv)
+    b, (route0, _, _) = run_report(snes_variants, "-variant 0 -p4b_recognise_residual 0 " + argv)
+    assert route == 1 and q == float("-0.35") and ncb == 2 * 3 + 1 and route0 == 0 and a == b
+    c, (route1, _, ncb1) = run_report(snes_variants, "-variant 1 " + argv)
+    assert route1 == 0 and ncb1 > 100 and c != a
+    m = 17
+    x = np.linspace(0.0, 1.0, m)
+    X, Y = np.meshgrid(x, x)
+    g = 0.4 * np.sin(3.0 * X + 1.0) * np.cos(2.0 * Y) + 0.2 * X * Y
+    h = 1.0 / (m - 1)
+    inner = np.zeros((m, m), bool)
+    inner[1:-1, 1:-1] = True
+    for variant, lines in ((0, a), (1, c)):
+        F = lambda u, v=variant: mpo.minimal_function(u, g, -0.35) + (5.0 * h * h * u ** 3 * inner if v else 0.0)
+        r = mo.newton(F, np.full((m, m), 0.1), lambda J, uu: fo.ILU0PC(J).apply, snes_rtol=1e-12)
+        got = re.fullmatch(r"done on 17 x 17 grid: sum (\S+) max (\S+)", lines[-1])
+        assert abs(float(got.group(1)) - r.u.sum()) <= 1e-8 * abs(r.u.sum()) and abs(float(got.group(2)) - r.u.max()) <= 1e-9
