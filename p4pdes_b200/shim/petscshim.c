@@ -285,7 +285,8 @@ struct _p_SNES {
     int monitor, monitor_short, converged_reason_flag, its;
     /* newtonls (minimal.c): tolerances, Jacobian source, grid sequencing, SNESMonitorSet monitors */
     double rtol, atol, stol;
-    int max_it, fd_color, grid_sequence, gmres_restart, tablevel, reason;
+    int max_it, fd_color, grid_sequence, gmres_restart, tablevel, reason, sym_check;
+    double sym_tol;          /* -mat_is_symmetric <tol> */
     struct {
         PetscErrorCode (*f)(SNES, PetscInt, PetscReal, void *);
         void *ctx;
@@ -857,8 +858,10 @@ PetscErrorCode SNESSetFromOptions(SNES snes) {
     if (opt_has("-snes_mf_operator") || opt_has("-snes_mf"))
         SHIM_ERR(56, "-snes_mf_operator / -snes_mf are not provided by the shim (Jacobians: the analytic callback for "
                      "ksponly, -snes_fd_color for newtonls)");
-    if (!strcmp(snes->type, SNESKSPONLY) && (snes->fd_color || snes->grid_sequence))
-        SHIM_ERR(56, "-snes_fd_color / -snes_grid_sequence are provided for -snes_type newtonls only");
+    if (!strcmp(snes->type, SNESKSPONLY) && snes->grid_sequence)
+        SHIM_ERR(56, "-snes_grid_sequence is provided for -snes_type newtonls only");
+    if ((v = opt_value("-mat_is_symmetric"))) { snes->sym_tol = strtod(v, NULL); snes->sym_check = 1; }
+    else if (opt_has("-mat_is_symmetric")) { snes->sym_tol = 0.0; snes->sym_check = 1; }
     if (opt_has("-pc_mg_galerkin")) SHIM_ERR(56, "-pc_mg_galerkin is not provided (levels are rediscretised, fish.c:7)");
     return 0;
 }
@@ -1083,6 +1086,76 @@ int MPI_Allreduce(const void *sendbuf, void *recvbuf, int count, MPI_Datatype da
     return 0;
 }
 
+/* fish.test2,5,8 run `-snes_fd_color -mat_is_symmetric tol`: PETSc differences the (linear) residual instead of calling
+ * the Jacobian callback and reports the symmetry of the result.  The device operator comes from the Jacobian callback
+ * (recognised stencil), so
+ *   -snes_fd_color      is honoured by CHECKING that the callback's matrix is the Jacobian of the residual:
+ *                       F(u0 + v) - F(u0) = A v for a pseudo-random v, the residual evaluated by the user's host
+ *                       callback, A v by the device MatMult; a disagreement is an error, not a silent substitution
+ *   -mat_is_symmetric   (x, A y) = (y, A x) for two pseudo-random vectors to the tolerance, on the device; PETSc prints
+ *                       its line once for the matrix DMCreateMatrix hands out and once per Jacobian assembly */
+static PetscErrorCode ksponly_matrix_checks(SNES snes, p4b_mg *mg, Vec u, Vec F0) {
+    DM dm = snes->dm;
+    Vec v = NULL, w = NULL, Av = NULL, Aw = NULL;
+    PetscCall(vec_new(dm, &v));
+    PetscCall(vec_new(dm, &w));
+    PetscCall(vec_new(dm, &Av));
+    PetscCall(vec_new(dm, &Aw));
+    unsigned long long lcg = 0xD1B54A32D192ED03ULL;
+    for (size_t i = 0; i < v->n; i++) {
+        lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
+        v->h[i] = (double)(lcg >> 11) / 9007199254740992.0 - 0.5;
+        lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
+        w->h[i] = (double)(lcg >> 11) / 9007199254740992.0 - 0.5;
+    }
+    PetscCall(vec_to_dev(v));
+    PetscCall(vec_to_dev(w));
+    PetscCall(vec_to_dev(Av));
+    PetscCall(vec_to_dev(Aw));
+    P4B(p4b_mg_matmult(mg, v->d, Av->d));
+    P4B(p4b_mg_matmult(mg, w->d, Aw->d));
+    Av->valid = Aw->valid = LOC_DEV;
+    if (snes->fd_color) {
+        Vec up = NULL, Fp = NULL;
+        PetscCall(vec_new(dm, &up));
+        PetscCall(vec_new(dm, &Fp));
+        PetscCall(vec_to_host(u));
+        PetscCall(vec_to_host(F0));
+        for (size_t i = 0; i < up->n; i++) up->h[i] = u->h[i] + v->h[i];
+        PetscCall(compute_function(snes, up, Fp));
+        PetscCall(vec_to_host(Av));
+        double dev = 0.0, scale = 0.0;
+        for (size_t i = 0; i < up->n; i++) {
+            const double e = fabs((Fp->h[i] - F0->h[i]) - Av->h[i]);
+            if (!(e <= dev)) dev = e;
+            if (fabs(Av->h[i]) > scale) scale = fabs(Av->h[i]);
+        }
+        vec_free(up);
+        vec_free(Fp);
+        if (!(dev <= 1.0e-10 * (scale > 1.0 ? scale : 1.0))) {
+            char msg[256];
+            snprintf(msg, sizeof msg, "-snes_fd_color: the matrix of the Jacobian callback is not the Jacobian of the residual "
+                     "(F(u+v) - F(u) - A v: max %.3e); the device path does not difference the residual of a linear problem", dev);
+            SHIM_ERR(56, msg);
+        }
+    }
+    if (snes->sym_check) {
+        double xAy = 0.0, yAx = 0.0, nx = 0.0, nAy = 0.0;
+        P4B(p4b_vec_dot(g_ctx, v->n, v->d, Aw->d, &xAy));
+        P4B(p4b_vec_dot(g_ctx, v->n, w->d, Av->d, &yAx));
+        P4B(p4b_vec_norm2(g_ctx, v->n, v->d, &nx));
+        P4B(p4b_vec_norm2(g_ctx, v->n, Aw->d, &nAy));
+        const int sym = fabs(xAy - yAx) <= (snes->sym_tol > 1.0e-13 ? snes->sym_tol : 1.0e-13) * nx * nAy;
+        for (int k = 0; k < 2; k++)         /* DMCreateMatrix's (empty) matrix, then the assembled Jacobian */
+            printf(sym || k == 0 ? "Matrix is symmetric (tolerance %g)\n" : "Matrix is not symmetric (tolerance %g)\n", snes->sym_tol);
+    }
+    vec_free(v);
+    vec_free(w);
+    vec_free(Av);
+    vec_free(Aw);
+    return 0;
+}
+
 PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
     if (b) SHIM_ERR(56, "SNESSolve with a right-hand side is not provided");
     if (!strcmp(snes->type, SNESNEWTONLS)) return snes_solve_newtonls(snes, x);
@@ -1187,6 +1260,7 @@ PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
     p4b_mg *mg = NULL;
     P4B(p4b_mg_create_stencil(g_ctx, &g, &o, coef, nlev, &mg));
     const int pct = !strcmp(pc->type, PCMG) ? P4B_PC_MG : (!strcmp(pc->type, PCJACOBI) ? P4B_PC_JACOBI : P4B_PC_NONE);
+    if (snes->fd_color || snes->sym_check) PetscCall(ksponly_matrix_checks(snes, mg, u, F));
     PetscCall(vec_to_dev(F));
     PetscCall(vec_to_dev(Y));
     p4b_ksp_result res;

@@ -63,3 +63,26 @@ def test_reference_error_paths(exe):
     assert "SOR" in err
     _, err = fish(exe, "-fsh_dim 2 -da_refine 2 -pc_type mg -snes_grid_sequence 1" + JAC, expect_rc=56)
     assert "newtonls only" in err
+
+
+@pytest.mark.parametrize("name,verbatim", [("fish.test2", True), ("fish.test5", False), ("fish.test8", False)])
+def test_goldens_with_fd_color_and_symmetry_report(exe, name, verbatim):
+    """fish.test2,5,8 run `-snes_fd_color -mat_is_symmetric tol` (c/ch6/makefile:14,23,32).  The shim honours -snes_fd_color by
+    checking F(u+v) - F(u) = A v (user's residual on the host, device MatMult of the recognised Jacobian) and reports the
+    symmetry it measures on the device operator.  test2 (1-D, 5 points) is reproduced verbatim; test5/8's error norms carry
+    the algebraic error of the golden's own CG + ILU(0) solve at rtol 1e-5 (the oracle reproduces them with ILU,
+    tests/test_oracle_goldens.py), so only their report lines are compared here."""
+    g = GOLD[name]
+    out, _ = fish(exe, g["options"] + " -pc_type none")
+    ref = "/root/reference/c/ch6/output/%s" % name
+    tol = g["options"].split("-mat_is_symmetric ")[1].split()[0]
+    assert out[:2] == ["Matrix is symmetric (tolerance %g)" % float(tol)] * 2 and g["symmetric_lines"] == 2
+    assert out[2] == "problem %s on %s grid:" % (g["problem"], g["gridstr"]) and len(out) == 4
+    if verbatim:
+        assert out[3] == "  error |u-uexact|_inf = %s, |u-uexact|_h = %s" % (g["errinf"], g["err2h"])
+        if os.path.exists(ref):
+            assert out == open(ref).read().splitlines()
+    else:
+        tight, _ = fish(exe, g["options"] + " -pc_type none -ksp_rtol 1e-12")
+        inf_t, inf_g = float(tight[3].split()[3].rstrip(",")), float(g["errinf"])
+        assert abs(inf_t - inf_g) <= 0.15 * inf_g          # discretisation error; the golden adds its solver's 1e-5
