@@ -1483,7 +1483,27 @@ static double maxabs_diff(const double *a, const double *b, size_t n, double *sc
     return d;
 }
 
-PetscErrorCode TSSolve(TS ts, Vec x) {
+/* everything TSSolve allocates for its probes, so that one release covers every exit */
+struct ts_work {
+    double *Y, *D, *Fu, *Fd;                     /* host: probe state, probe Ydot, user's result, device result */
+    double *dY, *dD, *dF;                        /* device copies */
+    struct ghosted gY, gD;
+    p4b_pattern_result *R;
+};
+static void ts_work_release(struct ts_work *W) {
+    free(W->Y); free(W->D); free(W->Fu); free(W->Fd);
+    if (g_ctx) {
+        if (W->dY) p4b_free(g_ctx, W->dY);
+        if (W->dD) p4b_free(g_ctx, W->dD);
+        if (W->dF) p4b_free(g_ctx, W->dF);
+    }
+    ghosted_free(&W->gY);
+    ghosted_free(&W->gD);
+    free(W->R);
+    memset(W, 0, sizeof *W);
+}
+
+static PetscErrorCode ts_solve(TS ts, Vec x, struct ts_work *W) {
     DM dm = ts->dm;
     KSP ksp = &ts->snes->ksp;
     PC pc = &ksp->pc;
@@ -1529,8 +1549,8 @@ PetscErrorCode TSSolve(TS ts, Vec x) {
         SHIM_ERR(56, "TSSolve: the device path needs a square box (DMDASetUniformCoordinates, pattern.c:92)");
     const double h = Lbox / m;
     PetscCall(vec_to_host(x));
-    double *Y = (double *)calloc(n, sizeof(double)), *D = (double *)calloc(n, sizeof(double));
-    double *Fu = (double *)malloc(sizeof(double) * n), *Fd = (double *)malloc(sizeof(double) * n);
+    double *Y = W->Y = (double *)calloc(n, sizeof(double)), *D = W->D = (double *)calloc(n, sizeof(double));
+    double *Fu = W->Fu = (double *)malloc(sizeof(double) * n), *Fd = W->Fd = (double *)malloc(sizeof(double) * n);
     if (!Y || !D || !Fu || !Fd) SHIM_ERR(55, "out of host memory");
 
     /* (1) identify: G at (u,v) = (0,0) is (phi, 0), at (0,1) it is (phi, -(phi+kappa)); F of unit pulses with Ydot = 0
@@ -1555,10 +1575,10 @@ PetscErrorCode TSSolve(TS ts, Vec x) {
         lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
         D[i] = (double)(lcg >> 11) / 9007199254740992.0 - 0.5;
     }
-    double *dY = NULL, *dD = NULL, *dF = NULL;
-    P4B(p4b_malloc(g_ctx, n * sizeof(double), (void **)&dY));
-    P4B(p4b_malloc(g_ctx, n * sizeof(double), (void **)&dD));
-    P4B(p4b_malloc(g_ctx, n * sizeof(double), (void **)&dF));
+    P4B(p4b_malloc(g_ctx, n * sizeof(double), (void **)&W->dY));
+    P4B(p4b_malloc(g_ctx, n * sizeof(double), (void **)&W->dD));
+    P4B(p4b_malloc(g_ctx, n * sizeof(double), (void **)&W->dF));
+    double *dY = W->dY, *dD = W->dD, *dF = W->dF;
     P4B(p4b_memcpy_h2d(g_ctx, dY, Y, n * sizeof(double)));
     P4B(p4b_memcpy_h2d(g_ctx, dD, D, n * sizeof(double)));
     double dev, scale;
@@ -1582,18 +1602,14 @@ PetscErrorCode TSSolve(TS ts, Vec x) {
                  o.phi, o.kappa, dev);
         SHIM_ERR(56, msg);
     }
-    P4B(p4b_free(g_ctx, dY));
-    P4B(p4b_free(g_ctx, dD));
-    P4B(p4b_free(g_ctx, dF));
     /* the Jacobian callbacks PETSc would call for this type: IJacobian always, RHSJacobian for the fully implicit types */
     {
         DMDALocalInfo info;
-        struct ghosted gY, gD;
         struct rd_check chk;
         struct _p_Mat P;
         const double t_jac0 = wall();
         PetscCall(DMDAGetLocalInfo(dm, &info));
-        if (ghosted_make(Y, m, m, 2, &gY) || ghosted_make(D, m, m, 2, &gD)) SHIM_ERR(55, "out of host memory");
+        if (ghosted_make(Y, m, m, 2, &W->gY) || ghosted_make(D, m, m, 2, &W->gD)) SHIM_ERR(55, "out of host memory");
         memset(&chk, 0, sizeof chk);
         chk.m = m; chk.shift = 1.0 / ts->dt; chk.C[0] = o.Du / (6.0 * h * h); chk.C[1] = o.Dv / (6.0 * h * h);
         chk.phi = o.phi; chk.kappa = o.kappa; chk.Y = Y;
@@ -1603,8 +1619,8 @@ PetscErrorCode TSSolve(TS ts, Vec x) {
             if (ts->snes->fd_color) break;                       /* PETSc would not call them either */
             if (mode == 2 && (!dm->rhsjac || o.ts_type == 0)) break;
             chk.mode = mode; chk.maxdev = 0.0; chk.rows = 0; chk.bad_structure = 0;
-            PetscErrorCode rc = mode == 1 ? dm->ijac(&info, 0.0, gY.a, gD.a, chk.shift, &P, &P, dm->ijacctx)
-                                          : dm->rhsjac(&info, 0.0, gY.a, &P, &P, dm->rhsjacctx);
+            PetscErrorCode rc = mode == 1 ? dm->ijac(&info, 0.0, W->gY.a, W->gD.a, chk.shift, &P, &P, dm->ijacctx)
+                                          : dm->rhsjac(&info, 0.0, W->gY.a, &P, &P, dm->rhsjacctx);
             if (rc) return rc;
             const double tol = 1.0e-11 * (fabs(chk.shift) + 20.0 * chk.C[0] + 20.0 * chk.C[1] + 1.0);
             if (chk.bad_structure || chk.rows != (long long)n || !(chk.maxdev <= tol)) {
@@ -1614,11 +1630,8 @@ PetscErrorCode TSSolve(TS ts, Vec x) {
                 SHIM_ERR(56, msg);
             }
         }
-        ghosted_free(&gY);
-        ghosted_free(&gD);
         g_t_jac += wall() - t_jac0;
     }
-    free(Y); free(D); free(Fu); free(Fd);
 
     /* (3) the solve, on the device, from the caller's state */
     o.no_rhsjacobian = dm->rhsjac ? 0 : 1;
@@ -1636,13 +1649,22 @@ PetscErrorCode TSSolve(TS ts, Vec x) {
     o.snes_converged_reason = ts->snes->converged_reason_flag;
     o.ksp_converged_reason = ksp->converged_reason_flag;
     PetscCall(vec_to_dev(x));
-    p4b_pattern_result *R = (p4b_pattern_result *)calloc(1, sizeof *R);
+    ts_work_release(W);                          /* the probes are done: give their buffers back before the solve */
+    p4b_pattern_result *R = W->R = (p4b_pattern_result *)calloc(1, sizeof *R);
+    if (!R) SHIM_ERR(55, "out of host memory");
     fflush(stdout);
     int rc = p4b_pattern_solve_from(g_ctx, &o, x->d, newton_line, NULL, x->d, n, R);
     fflush(stdout);
-    free(R);
     if (rc) return PetscShimError(PETSC_COMM_SELF, __LINE__, __func__, __FILE__, rc, p4b_last_error());
     x->valid = LOC_DEV;
     g_t_snes += wall() - t_start;
     return 0;
+}
+
+PetscErrorCode TSSolve(TS ts, Vec x) {
+    struct ts_work W;
+    memset(&W, 0, sizeof W);
+    PetscErrorCode rc = ts_solve(ts, x, &W);
+    ts_work_release(&W);                         /* also on every error return of ts_solve */
+    return rc;
 }
