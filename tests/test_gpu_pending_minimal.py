@@ -74,10 +74,24 @@ def test_callback_contract_on_device(ctx):
     out = np.zeros(17 * 17)
     res = L.MinimalResult()
     cb, line = L.RESIDUAL2D_FN(residual), L.LINE_FN(lambda s, c: None)
-    L.check(ctx.lib.p4b_snes2d_solve(ctx.h, C.byref(o), cb, None, u0.ctypes.data_as(C.c_void_p), line, None,
-                                     out.ctypes.data_as(C.c_void_p), out.size, C.byref(res)))
     ref = pm.minimal_main("-snes_fd_color -snes_grid_sequence 3 -ms_problem tent -pc_type mg", ctx)
+    # route 0: recognition off, every evaluation is the host callback (nine per level Jacobian)
+    L.check(ctx.lib.p4b_tune(b"recognise_residual", 0))
+    try:
+        L.check(ctx.lib.p4b_snes2d_solve(ctx.h, C.byref(o), cb, None, u0.ctypes.data_as(C.c_void_p), line, None,
+                                         out.ctypes.data_as(C.c_void_p), out.size, C.byref(res)))
+    finally:
+        L.check(ctx.lib.p4b_tune(b"recognise_residual", 1))
+    assert ctx.lib.p4b_snes2d_last_route() == 0
     assert (res.mx, res.my, res.nstages) == (17, 17, 4)
     assert [res.stage[s].its for s in range(4)] == [s.its for s in ref.stages]
     assert calls[0] > 9 * sum(s.its for s in ref.stages)
     assert np.max(np.abs(out - ctx.to_host(ref.u))) <= 1e-8
+    # route 1 (default): the callback is recognised as the library's kernel after 2 probes per grid + 1 (grids 3, 5, 9, 17)
+    calls[0] = 0
+    out2 = np.zeros(17 * 17)
+    L.check(ctx.lib.p4b_snes2d_solve(ctx.h, C.byref(o), cb, None, u0.ctypes.data_as(C.c_void_p), line, None,
+                                     out2.ctypes.data_as(C.c_void_p), out2.size, C.byref(res)))
+    assert ctx.lib.p4b_snes2d_last_route() == 1 and calls[0] == 2 * 4 + 1
+    assert [res.stage[s].its for s in range(4)] == [s.its for s in ref.stages]
+    assert np.max(np.abs(out2 - ctx.to_host(ref.u))) <= 1e-8
