@@ -297,6 +297,8 @@ typedef struct {
     int snes_max_it;
     int snes_monitor;            /* 0 off, 1 -snes_monitor, 2 -snes_monitor_short */
     int snes_converged_reason, ksp_converged_reason;
+    int mf_operator;             /* -snes_mf_operator: J v by differencing the residual ([PETSc] MatMFFD "wp"); the
+                                    FD-coloured Jacobian then only builds the preconditioner */
 } p4b_minimal_opts;
 typedef struct {
     int mx, my, its, reason, nksp;   /* reason: 2 FNORM_ABS, 3 FNORM_RELATIVE, 4 SNORM_RELATIVE, < 0 diverged ([PETSc] numbering) */

@@ -93,6 +93,7 @@ int main(int argc, char **argv) {
         else if (a == "-pc_type") o.pc_type = std::string(next()) == "mg" ? PC_MG : PC_NONE;
         else if (a == "-pc_mg_levels") o.mg_levels = atoi(next());
         else if (a == "-snes_fd_color") { }
+        else if (a == "-snes_mf_operator") o.mf_operator = 1;
         else if (a == "-monitor") { o.snes_monitor = 2; o.snes_converged_reason = 1; o.ksp_converged_reason = 1; }
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }

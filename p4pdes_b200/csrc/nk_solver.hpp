@@ -49,6 +49,8 @@ struct MinimalOpts {
     int snes_max_it;
     int snes_monitor;            // 0 off, 1 full precision, 2 short
     int snes_converged_reason, ksp_converged_reason;
+    int mf_operator;             // -snes_mf_operator: J v by differencing the residual ([PETSc] MatMFFD "wp"); the assembled
+                                 // (FD-coloured) Jacobian is the preconditioner's matrix only
 };
 
 inline void default_opts(MinimalOpts *o) {
@@ -449,6 +451,7 @@ int newton(Ops *ops, std::vector<Level<Ops>> &lev, const MinimalOpts &opt, const
     std::string pad((size_t)(2 * indent), ' ');
     auto F = [&](const double *u, double *f) { ops->minimal_function(L.mx, L.my, q, u, L.g, f); };
     double *y = ops->alloc(n), *Jy = ops->alloc(n), *w = ops->alloc(n), *gnew = ops->alloc(n), *t = ops->alloc(n);
+    double *mfw = opt.mf_operator ? ops->alloc(n) : nullptr;
     double *kr = ops->alloc(n), *kz = nullptr, *kp = nullptr;
     std::vector<double *> V;
     if (opt.ksp_type == KSP_GMRES) {
@@ -485,7 +488,7 @@ int newton(Ops *ops, std::vector<Level<Ops>> &lev, const MinimalOpts &opt, const
             rc = mg.setup(q);
             if (rc) break;
             M.mg = &mg;
-        } else {
+        } else if (!(opt.mf_operator && opt.pc_type == PC_NONE)) {        // (matrix-free and unpreconditioned: no matrix at all)
             L.assemble(q, true);
             if (opt.pc_type == PC_MG) {                        // a single level: the "multigrid" is the direct solve
                 if (n > 4225) { rc = 61; break; }
@@ -498,7 +501,18 @@ int newton(Ops *ops, std::vector<Level<Ops>> &lev, const MinimalOpts &opt, const
             }
         }
         KSPInfo k;
-        auto mult = [&](const double *in, double *out) { L.mult(in, out); };
+        // -snes_mf_operator: [PETSc] MatMFFD, "wp": J v = (F(u + h v) - F(u)) / h, h = sqrt(eps) sqrt(1 + ||u||) / ||v||
+        // (c/ch7/output/minimal.test3: its first stage, one unknown, is reproduced digit for digit with this h)
+        const double unorm = opt.mf_operator ? ops->norm2(n, L.u) : 0.0;
+        auto mult = [&](const double *in, double *out) {
+            if (!opt.mf_operator) { L.mult(in, out); return; }
+            const double vn = ops->norm2(n, in);
+            if (vn == 0.0) { ops->set(n, 0.0, out); return; }
+            const double h = 1.4901161193847656e-08 * sqrt(1.0 + unorm) / vn;
+            ops->axpby(n, 1.0, L.u, h, in, mfw);
+            F(mfw, out);
+            ops->axpby(n, 1.0 / h, out, -1.0 / h, L.F, out);
+        };
         auto prec = [&](const double *r, double *z) { M.apply(r, z); };
         if (opt.ksp_type == KSP_GMRES) k = gmres(ops, n, mult, L.F, y, prec, opt.ksp_rtol, 1.0e-50, opt.gmres_restart, opt.ksp_max_it, V, w, t);
         else k = cg(ops, n, mult, L.F, y, prec, opt.ksp_rtol, 1.0e-50, opt.ksp_max_it, kr, kz, kp, w);
@@ -506,7 +520,7 @@ int newton(Ops *ops, std::vector<Level<Ops>> &lev, const MinimalOpts &opt, const
         if (opt.ksp_converged_reason)
             pr.out("%s    Linear solve %s due to %s iterations %d", pad.c_str(), k.converged ? "converged" : "did not converge",
                    k.converged ? "CONVERGED_RTOL" : "DIVERGED_ITS", k.its);
-        L.mult(y, Jy);
+        mult(y, Jy);
         double gnorm = 0.0, lam = 0.0;
         if (!linesearch_bt(ops, n, F, L.u, L.F, fnorm, y, Jy, w, gnew, &gnorm, &lam)) { reason = SNES_DIVERGED_LINE_SEARCH; break; }
         res->lambda[it] = lam;
@@ -534,6 +548,7 @@ int newton(Ops *ops, std::vector<Level<Ops>> &lev, const MinimalOpts &opt, const
     mg.destroy();
     if (dense) ops->release(dense);
     for (double *p : {y, Jy, w, gnew, t, kr}) ops->release(p);
+    if (mfw) ops->release(mfw);
     if (kz) ops->release(kz);
     if (kp) ops->release(kp);
     for (double *p : V) ops->release(p);

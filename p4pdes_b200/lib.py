@@ -63,7 +63,8 @@ class MinimalOpts(C.Structure):
                 ("grid_sequence", C.c_int), ("ksp_type", C.c_int), ("ksp_rtol", C.c_double), ("ksp_max_it", C.c_int),
                 ("gmres_restart", C.c_int), ("pc_type", C.c_int), ("mg_levels", C.c_int), ("smooth_its", C.c_int),
                 ("snes_rtol", C.c_double), ("snes_stol", C.c_double), ("snes_atol", C.c_double), ("snes_max_it", C.c_int),
-                ("snes_monitor", C.c_int), ("snes_converged_reason", C.c_int), ("ksp_converged_reason", C.c_int)]
+                ("snes_monitor", C.c_int), ("snes_converged_reason", C.c_int), ("ksp_converged_reason", C.c_int),
+                ("mf_operator", C.c_int)]
 
 
 class MinimalStage(C.Structure):

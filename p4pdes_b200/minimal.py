@@ -47,6 +47,7 @@ class MinimalOptions:
     refine: int = 0
     grid_sequence: int = 0
     fd_color: bool = False
+    mf_operator: bool = False
     ksp_type: str = "gmres"
     ksp_rtol: float = 1.0e-5
     ksp_max_it: int = 10000
@@ -69,7 +70,8 @@ def parse_options(argv) -> MinimalOptions:
     if isinstance(argv, str):
         argv = shlex.split(argv)
     o = MinimalOptions()
-    flags = {"-ms_exact_init": "exact_init", "-snes_fd_color": "fd_color", "-snes_monitor": "snes_monitor",
+    flags = {"-ms_exact_init": "exact_init", "-snes_fd_color": "fd_color", "-snes_mf_operator": "mf_operator",
+             "-snes_monitor": "snes_monitor",
              "-snes_monitor_short": "snes_monitor_short", "-snes_converged_reason": "snes_converged_reason",
              "-ksp_converged_reason": "ksp_converged_reason", "-log_view": "log_view"}
     valued = {"-ms_problem": ("problem", str), "-ms_q": ("q", float), "-ms_catenoid_c": ("catenoid_c", float),
@@ -110,9 +112,10 @@ def parse_options(argv) -> MinimalOptions:
         raise ValueError("-ksp_type %s: the device path provides gmres and cg" % o.ksp_type)
     if o.pc_type not in ("mg", "none"):
         raise ValueError("-pc_type %s: the device path provides mg and none (ilu/sor/icc are sequential)" % o.pc_type)
-    if not o.fd_color:
-        raise ValueError("the device path assembles the Jacobian by coloured finite differences: pass -snes_fd_color "
-                         "(minimal.c:142-145 registers only the approximate Poisson Jacobian otherwise)")
+    if not (o.fd_color or o.mf_operator):
+        raise ValueError("the device path takes the Jacobian from the residual: pass -snes_fd_color (coloured finite "
+                         "differences) or -snes_mf_operator (matrix-free action, FD-coloured preconditioner matrix); "
+                         "minimal.c:142-145 registers only the approximate Poisson Jacobian otherwise")
     return o
 
 
@@ -424,6 +427,7 @@ def newton(ops, levels, opt: MinimalOptions, out, indent=0) -> SNESResult:
     pad = "  " * indent
     F = lambda u, f: ops.minimal_function(L.mx, L.my, q, u, L.g, f)
     y, Jy, w, gnew = ops.empty(n), ops.empty(n), ops.empty(n), ops.empty(n)
+    mfw = ops.empty(n) if opt.mf_operator else None
     mg = AssembledMG(ops, levels, opt) if opt.pc_type == "mg" and len(levels) > 1 else None
     work = [ops.empty(n) for _ in range(opt.gmres_restart + 1)] if opt.ksp_type == "gmres" else None
     F(L.u, L.F)
@@ -448,6 +452,8 @@ def newton(ops, levels, opt: MinimalOptions, out, indent=0) -> SNESResult:
         if mg is not None:
             mg.setup(q)
             precond = mg.apply
+        elif opt.mf_operator and opt.pc_type == "none":
+            precond = lambda r, z: ops.copy(r, z)     # matrix-free and unpreconditioned: no matrix at all
         else:
             L.assemble(q, F_known=True)
             if opt.pc_type == "mg":                   # a single level: the "multigrid" is the direct base-grid solve
@@ -455,16 +461,31 @@ def newton(ops, levels, opt: MinimalOptions, out, indent=0) -> SNESResult:
                 precond = lambda r, z: ops.dense_matvec(n, Ainv, r, z)
             else:
                 precond = lambda r, z: ops.copy(r, z)
+        mult = L.mult
+        if opt.mf_operator:
+            # [PETSc] MatMFFD, "wp": J v = (F(u + h v) - F(u)) / h, h = sqrt(eps) sqrt(1 + ||u||) / ||v||  (pinned by
+            # c/ch7/output/minimal.test3, tests/test_minimal_oracle.py)
+            unorm = ops.norm2(L.u)
+
+            def mult(v, outv, unorm=unorm):
+                vn = ops.norm2(v)
+                if vn == 0.0:
+                    ops.set(0.0, outv)
+                    return
+                h = 1.4901161193847656e-08 * math.sqrt(1.0 + unorm) / vn
+                ops.axpby(1.0, L.u, h, v, mfw)
+                F(mfw, outv)
+                ops.axpby(1.0 / h, outv, -1.0 / h, L.F, outv)
         if opt.ksp_type == "gmres":
-            k = gmres(ops, L.mult, L.F, y, precond, opt.ksp_rtol, restart=opt.gmres_restart, max_it=opt.ksp_max_it,
+            k = gmres(ops, mult, L.F, y, precond, opt.ksp_rtol, restart=opt.gmres_restart, max_it=opt.ksp_max_it,
                       work=work)
         else:
-            k = cg(ops, L.mult, L.F, y, precond, opt.ksp_rtol, max_it=opt.ksp_max_it)
+            k = cg(ops, mult, L.F, y, precond, opt.ksp_rtol, max_it=opt.ksp_max_it)
         res.ksp_its.append(k.its)
         if opt.ksp_converged_reason:
             out("%s    Linear solve %s due to %s iterations %d" % (pad, "converged" if k.reason.startswith("CONV")
                                                                      else "did not converge", k.reason, k.its))
-        L.mult(y, Jy)
+        mult(y, Jy)
         gnorm, lam = linesearch_bt(ops, F, L.u, L.F, fnorm, y, Jy, w, gnew)
         res.lambdas.append(lam)
         ops.axpby(1.0, w, -1.0, L.u, y)               # step actually taken (y is free now)
@@ -535,6 +556,7 @@ def _minimal_native(opt: MinimalOptions, ctx, out, keep_solution) -> MinimalRepo
     o.snes_rtol, o.snes_stol, o.snes_atol, o.snes_max_it = opt.snes_rtol, opt.snes_stol, opt.snes_atol, opt.snes_max_it
     o.snes_monitor = 2 if opt.snes_monitor_short else (1 if opt.snes_monitor else 0)
     o.snes_converged_reason, o.ksp_converged_reason = int(opt.snes_converged_reason), int(opt.ksp_converged_reason)
+    o.mf_operator = int(opt.mf_operator)
     mx, my = opt.grid_x, opt.grid_y
     for _ in range(opt.refine + opt.grid_sequence):
         mx, my = 2 * mx - 1, 2 * my - 1

@@ -285,7 +285,7 @@ struct _p_SNES {
     int monitor, monitor_short, converged_reason_flag, its;
     /* newtonls (minimal.c): tolerances, Jacobian source, grid sequencing, SNESMonitorSet monitors */
     double rtol, atol, stol;
-    int max_it, fd_color, grid_sequence, gmres_restart, tablevel, reason, sym_check;
+    int max_it, fd_color, mf_operator, grid_sequence, gmres_restart, tablevel, reason, sym_check;
     double sym_tol;          /* -mat_is_symmetric <tol> */
     struct {
         PetscErrorCode (*f)(SNES, PetscInt, PetscReal, void *);
@@ -855,9 +855,11 @@ PetscErrorCode SNESSetFromOptions(SNES snes) {
     if ((v = opt_value("-ksp_gmres_restart"))) snes->gmres_restart = atoi(v);
     if ((v = opt_value("-snes_grid_sequence"))) snes->grid_sequence = atoi(v);
     snes->fd_color = opt_bool("-snes_fd_color", 0);
-    if (opt_has("-snes_mf_operator") || opt_has("-snes_mf"))
-        SHIM_ERR(56, "-snes_mf_operator / -snes_mf are not provided by the shim (Jacobians: the analytic callback for "
-                     "ksponly, -snes_fd_color for newtonls)");
+    snes->mf_operator = opt_bool("-snes_mf_operator", 0);
+    if (opt_has("-snes_mf"))
+        SHIM_ERR(56, "-snes_mf is not provided by the shim (-snes_fd_color or -snes_mf_operator for newtonls)");
+    if (snes->mf_operator && !strcmp(snes->type, SNESKSPONLY))
+        SHIM_ERR(56, "-snes_mf_operator is provided for -snes_type newtonls only");
     if (!strcmp(snes->type, SNESKSPONLY) && snes->grid_sequence)
         SHIM_ERR(56, "-snes_grid_sequence is provided for -snes_type newtonls only");
     if ((v = opt_value("-mat_is_symmetric"))) { snes->sym_tol = strtod(v, NULL); snes->sym_check = 1; }
@@ -964,9 +966,9 @@ static PetscErrorCode snes_solve_newtonls(SNES snes, Vec x) {
     if (dm->dim != 2 || dm->dof != 1)
         SHIM_ERR(56, "-snes_type newtonls is provided for 2-D DMDAs with one degree of freedom (minimal.c); "
                      "fish.c is linear: -snes_type ksponly (fish.c:230-231)");
-    if (!snes->fd_color)
-        SHIM_ERR(56, "newtonls needs the Jacobian of the registered residual: pass -snes_fd_color (minimal.c:141-142: the "
-                     "Jacobian callback registered there is Poisson's, 'thus ONLY APPROXIMATE')");
+    if (!snes->fd_color && !snes->mf_operator)
+        SHIM_ERR(56, "newtonls needs the Jacobian of the registered residual: pass -snes_fd_color or -snes_mf_operator "
+                     "(minimal.c:141-142: the Jacobian callback registered there is Poisson's, 'thus ONLY APPROXIMATE')");
     p4b_minimal_opts o;
     P4B(p4b_minimal_default_opts(&o));
     if (!strcmp(ksp->type, KSPGMRES)) o.ksp_type = 0;
@@ -993,6 +995,10 @@ static PetscErrorCode snes_solve_newtonls(SNES snes, Vec x) {
     o.snes_monitor = snes->monitor_short ? 2 : (snes->monitor ? 1 : 0);
     o.snes_converged_reason = snes->converged_reason_flag;
     o.ksp_converged_reason = ksp->converged_reason_flag;
+    /* -snes_mf_operator: the Krylov operator is the differenced residual ([PETSc] MatMFFD); PETSc would build the
+     * preconditioner from the registered (Poisson) Jacobian callback, here it is built from the FD-coloured Jacobian of the
+     * residual -- the better matrix; Newton iterates depend on it only through the inexactness of the linear solves */
+    o.mf_operator = snes->mf_operator && !snes->fd_color;
     PetscCall(ensure_ctx());
     {   /* -p4b_recognise_residual 0: evaluate the registered FormFunctionLocal on the host every time, also when it is the
          * residual the library has as a kernel (p4b200.h, "Recognition") */

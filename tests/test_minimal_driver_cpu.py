@@ -56,6 +56,8 @@ def test_driver_reproduces_golden_lines_of_minimal_test1():
      dict(mx=5, my=9, grid_sequence=2, pc="mg", catenoid_c=1.5)),
     ("-snes_fd_color -da_refine 2 -pc_type none -ms_problem tent", dict(refine=2, problem="tent", pc="none")),
     ("-snes_fd_color -da_refine 4 -pc_type mg -pc_mg_levels 3", dict(refine=4, pc="mg", mg_levels=3)),
+    ("-snes_mf_operator -snes_grid_sequence 2 -pc_type mg", dict(grid_sequence=2, pc="mg", mf_operator=True)),
+    ("-snes_mf_operator -da_refine 2 -pc_type none -ms_problem tent", dict(refine=2, problem="tent", pc="none", mf_operator=True)),
 ])
 def test_driver_matches_oracle(argv, okw):
     ops = FakeOps()

@@ -108,3 +108,31 @@ def test_golden_minimal_test3_path_independent_lines():
                    "area = 1.33230220; 0.5684 <= D <= 0.9872",        # :13    (interpolated to 9 x 9)
                    "area = 1.33475385; 0.5156 <= D <= 0.9968"]        # :15-16
     assert "%.5e" % float(np.max(np.abs(u - gg))) == "6.79501e-04"    # :18
+
+
+def test_golden_minimal_test3_matrix_free_operator():
+    """minimal.test3 ran -snes_mf_operator: the Krylov operator is [PETSc] MatMFFD, J v = (F(u + h v) - F(u)) / h with the
+    default "wp" step h = sqrt(eps) sqrt(1 + ||u||) / ||v||.  On the first grid (3 x 3: ONE unknown, so the linear solve is
+    exact whatever preconditioner the golden used) every printed digit of the monitor lines is reproduced with that
+    operator -- and not with the FD-coloured matrix, which differs in the 8th digit; the later stages inherit the golden's
+    inexact multigrid solves (2 ranks, Chebyshev/SOR) in the last digits of two lines."""
+    fmt = lambda t: "area = %.8f; %.4f <= D <= %.4f" % t
+    got = {True: [], False: []}
+    for mf in (True, False):
+        mo.minimal(grid_sequence=2, pc="ilu", mf_operator=mf, monitor=lambda st, it, u, mf=mf: got[mf].append(fmt(mo.mse_monitor(u, -0.5, 2))))
+    ref = "/root/reference/c/ch7/output/minimal.test3"
+    golden = ["area = 2.14201032; 0.2985 <= D <= 0.8826", "area = 1.60235989; 0.4166 <= D <= 0.9873",
+              "area = 1.39125969; 0.5789 <= D <= 0.9362", "area = 1.32285324; 0.6106 <= D <= 0.9561",
+              "area = 1.32217567; 0.6158 <= D <= 0.9510", "area = 1.32217567; 0.6158 <= D <= 0.9510",
+              "area = 1.32217583; 0.6035 <= D <= 0.9518", "area = 1.33231935; 0.5757 <= D <= 0.9872",
+              "area = 1.33230219; 0.5755 <= D <= 0.9872", "area = 1.33230217; 0.5755 <= D <= 0.9872",
+              "area = 1.33230220; 0.5684 <= D <= 0.9872", "area = 1.33475595; 0.5153 <= D <= 0.9968",
+              "area = 1.33475385; 0.5156 <= D <= 0.9968", "area = 1.33475385; 0.5156 <= D <= 0.9968"]
+    import os
+    if os.path.exists(ref):
+        assert [l.strip() for l in open(ref) if "area" in l] == golden
+    assert got[True][:7] == golden[:7]                       # minimal.test3:1-6,8: the whole first stage + the interpolated iterate
+    assert got[False][1:4] != golden[1:4]                    # the assembled FD-coloured operator does not give these digits
+    area = lambda l: float(l.split()[2].rstrip(";"))
+    assert len(got[True]) == 14 and max(abs(area(a) - area(b)) for a, b in zip(got[True], golden)) <= 6e-8
+    assert [l.split(";")[1] for l in got[True]] == [l.split(";")[1] for l in golden]

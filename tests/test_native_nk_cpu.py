@@ -36,6 +36,9 @@ def run(exe, *args):
     (("-da_refine", 2, "-pc_type", "none", "-ms_problem", "tent"), dict(refine=2, problem="tent", pc="none")),
     (("-da_refine", 4, "-pc_type", "mg", "-pc_mg_levels", 3, "-ms_problem", "tent"),
      dict(refine=4, pc="mg", mg_levels=3, problem="tent")),
+    (("-snes_mf_operator", "-snes_grid_sequence", 2, "-pc_type", "mg", "-ms_problem", "tent"),
+     dict(grid_sequence=2, pc="mg", problem="tent", mf_operator=True)),
+    (("-snes_mf_operator", "-da_refine", 2, "-pc_type", "none"), dict(refine=2, pc="none", mf_operator=True)),
 ])
 def test_native_solver_matches_python_oracle(exe, argv, okw):
     _, d = run(exe, "-snes_fd_color", *argv)
