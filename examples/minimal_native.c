@@ -39,7 +39,8 @@ int main(int argc, char **argv) {
         else if (!strcmp(a, "-snes_monitor")) o.snes_monitor = 1;
         else if (!strcmp(a, "-snes_converged_reason")) o.snes_converged_reason = 1;
         else if (!strcmp(a, "-ksp_converged_reason")) o.ksp_converged_reason = 1;
-        else if (!strcmp(a, "-snes_fd_color")) { /* the only Jacobian this path has */ }
+        else if (!strcmp(a, "-snes_fd_color")) { /* the assembled (FD-coloured) Jacobian: the default */ }
+        else if (!strcmp(a, "-snes_mf_operator")) o.mf_operator = 1;
         else { fprintf(stderr, "unknown option %s\n", a); return 2; }
     }
     if (p4b_ctx_create(0, NULL, &ctx)) { fprintf(stderr, "%s\n", p4b_last_error()); return 1; }
