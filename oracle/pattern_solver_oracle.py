@@ -213,7 +213,7 @@ def pattern_arkimex(grid=3, refine=0, dt=5.0, tmax=200.0, atol=1.0e-4, rtol=1.0e
         solve = lambda shift, rhs: spla.spsolve((shift * I + Lap).tocsc(), rhs)
     res = PatternResult(Y=Y, mx=m)
     res.lines.append("running on %d x %d grid with square cells of side h = %.6f ..." % (m, m, L / m))
-    t, k, h = 0.0, 0, dt
+    t, k, h = 0.0, 0, min(dt, tmax)                 # [PETSc] TSSolve: MATCHSTEP clips the first step to the final time
     rejected = 0
     while t < tmax - 1e-12 * max(1.0, abs(tmax)) and k < max_steps:
         res.lines.append("%d TS dt %s time %s" % (k, fmt_g(h), fmt_g(t)))

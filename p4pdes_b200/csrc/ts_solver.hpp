@@ -318,7 +318,7 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
     auto mult = [&](const double *in, double *out) { A.mult(in, out); };
     auto prec = [&](const double *r, double *z) { A.precond(r, z); };
     const double tmax = opt.ts_max_time;
-    double t = 0.0, h = opt.ts_dt;
+    double t = 0.0, h = std::min(opt.ts_dt, opt.ts_max_time);   // [PETSc] TSSolve: MATCHSTEP clips the first step to the final time
     int k = 0, rc = 0;
     auto record = [&](double dt_taken, int newton) {
         if (k < MAX_TS_STEPS_KEPT) { R->step_t[k] = t; R->step_dt[k] = dt_taken; R->step_newton[k] = newton; }
@@ -467,7 +467,6 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
                 };
                 return newton_solve(F, shift, X, its);
             };
-            h = std::min(h, tmax - t);                                                // [PETSc] TSSolve: MATCHSTEP clips the first step
             double dt_next = h;
             while (t < tmax - 1e-12 * std::max(1.0, fabs(tmax)) && k < opt.ts_max_steps && !rc) {
                 if (opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(h).c_str(), fmt_g(t).c_str());

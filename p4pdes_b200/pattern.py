@@ -456,7 +456,8 @@ def _arkimex(ops, opt: PatternOptions, levels, m, out, lines) -> PatternReport:
     ops.set(0.0, zero)
     ops.pattern_initial_state(m, m, opt.L, Y)
     t0 = time.perf_counter()
-    t, k, h, steps, rejected, ksp_total = 0.0, 0, opt.ts_dt, [], 0, 0
+    # ([PETSc] TSSolve: TS_EXACTFINALTIME_MATCHSTEP clips the first step to the final time)
+    t, k, h, steps, rejected, ksp_total = 0.0, 0, min(opt.ts_dt, opt.ts_max_time), [], 0, 0
     tmax = opt.ts_max_time
     while t < tmax - 1e-12 * max(1.0, abs(tmax)) and k < opt.ts_max_steps:
         if opt.ts_monitor:
