@@ -381,6 +381,17 @@ int p4b_pattern_solve(p4b_ctx *ctx, const p4b_pattern_opts *opts, p4b_line_fn li
  * report: the caller prints those, pattern.c:94-96,127-135).  Y0 = NULL is p4b_pattern_solve. */
 int p4b_pattern_solve_from(p4b_ctx *ctx, const p4b_pattern_opts *opts, const double *Y0, p4b_line_fn line, void *line_ctx,
                            double *Y_out, size_t Y_capacity, p4b_pattern_result *result);
+/* ---- the same time steppers for ANY two-component system on the periodic m x m DMDA given by HOST callbacks and no
+ * Jacobian: F(t, Y, Ydot) and G(t, Y) of the DMDATSSet{IFunction,RHSFunction}Local contract (c/ch5/pattern.c:103-114,
+ * 185-199, 242-267; arrays whole-grid, (u,v) interleaved, natural ordering).  The stage operator is the differenced residual
+ * ([PETSc] MatMFFD "wp"), so there is no multigrid: opts->pc_type must be 0 (none).  F must be M Ydot + f(Y) with a constant
+ * M (the caller checks; every method-of-lines system is); the callbacks are called with t = 0 (autonomous systems).  The
+ * model fields of opts (L, Du, ...) are ignored.  Y_inout_host: initial state in, final state out. ---- */
+typedef int (*p4b_ifunction2d_fn)(void *user, int m, double t, const double *Y_host, const double *Ydot_host, double *F_host);
+typedef int (*p4b_rhsfunction2d_fn)(void *user, int m, double t, const double *Y_host, double *G_host);
+int p4b_ts2d_solve(p4b_ctx *ctx, const p4b_pattern_opts *opts, p4b_ifunction2d_fn ifunction, p4b_rhsfunction2d_fn rhsfunction,
+                   void *user, double *Y_inout_host, size_t Y_capacity, p4b_line_fn line, void *line_ctx,
+                   p4b_pattern_result *result);
 typedef struct p4b_sell p4b_sell;
 int p4b_sell_create(p4b_ctx *ctx, int nrows, const int *rowptr_host, const int *colind_host, const double *vals_host,
                     p4b_sell **A);

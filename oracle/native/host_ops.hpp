@@ -36,6 +36,7 @@ struct HostOps {
     void copy(size_t n, const double *x, double *y) { memmove(y, x, sizeof(double) * n); }
     void set(size_t n, double a, double *y) { for (size_t i = 0; i < n; i++) y[i] = a; }
     void user_monitor(int, int, int, double, int, const double *) {}
+    void set_linearisation(const double *) {}
 
     // c/ch7/minimal.c:27-42  g_bdry_tent / g_bdry_catenoid at every node of the unit square
     void minimal_sample(int mx, int my, int problem, double H, double c, double *g) {
@@ -382,5 +383,57 @@ struct HostCallbackOps : HostOps {
                     vals[(size_t)(3 * (dj + 1) + (di + 1)) * N + n] = (Fp[n] - F0[n]) * vscale;
                 }
             }
+    }
+};
+
+// F(t, Y, Ydot) and G(t, Y) supplied as host callbacks, no Jacobian (include/p4b200.h p4b_ts2d_solve): the CPU counterpart of
+// CallbackPatternOps in p4pdes_b200/csrc/nk_device.cu -- the stage operator is the differenced residual ([PETSc] MatMFFD "wp").
+struct HostCallbackPatternOps : HostOps {
+    int (*ifn)(void *user, int m, double t, const double *Y, const double *Ydot, double *F) = nullptr;
+    int (*gfn)(void *user, int m, double t, const double *Y, double *G) = nullptr;
+    void *user = nullptr;
+    const double *lin = nullptr, *r0_for = nullptr;
+    double r0_shift = 0.0;
+    bool r0_rhs = false;
+    std::vector<double> wY, wD, wF, wR0;
+    long long callbacks = 0;
+    void pattern_ifunction(int m, const PO &, const double *Y, const double *Ydot, double *F) {
+        const size_t n = (size_t)2 * m * m;
+        std::vector<double> y(Y, Y + n), d(Ydot, Ydot + n), f(n);
+        callbacks++;
+        if (ifn(user, m, 0.0, y.data(), d.data(), f.data()) && !err) err = 65;
+        memcpy(F, f.data(), sizeof(double) * n);
+    }
+    void pattern_rhsfunction(int m, const PO &, const double *Y, double *G) {
+        const size_t n = (size_t)2 * m * m;
+        std::vector<double> y(Y, Y + n), g(n);
+        callbacks++;
+        if (gfn(user, m, 0.0, y.data(), g.data()) && !err) err = 65;
+        memcpy(G, g.data(), sizeof(double) * n);
+    }
+    void set_linearisation(const double *Y) { lin = Y; r0_for = nullptr; }
+    void resid(int m, const PO &o, double shift, bool rhs, const double *W, double *out) {
+        const size_t n = (size_t)2 * m * m;
+        wD.resize(n);
+        for (size_t i = 0; i < n; i++) wD[i] = shift * W[i];
+        pattern_ifunction(m, o, W, wD.data(), out);
+        if (rhs) { wF.resize(n); pattern_rhsfunction(m, o, W, wF.data()); axpy(n, -1.0, wF.data(), out); }
+    }
+    void pattern_jac_apply(int m, const PO &o, double shift, const double *Y, const double *X, double *out) {
+        const size_t n = (size_t)2 * m * m;
+        const bool rhs = Y != nullptr;
+        if (!lin) { if (!err) err = 68; return; }
+        if (r0_for != lin || r0_shift != shift || r0_rhs != rhs) {
+            wR0.resize(n);
+            resid(m, o, shift, rhs, lin, wR0.data());
+            r0_for = lin; r0_shift = shift; r0_rhs = rhs;
+        }
+        const double xn = norm2(n, X);
+        if (xn == 0.0) { set(n, 0.0, out); return; }
+        const double h = 1.4901161193847656e-08 * sqrt(1.0 + norm2(n, lin)) / xn;
+        wY.resize(n);
+        axpby(n, 1.0, lin, h, X, wY.data());
+        resid(m, o, shift, rhs, wY.data(), out);
+        axpby(n, 1.0 / h, out, -1.0 / h, wR0.data(), out);
     }
 };

@@ -176,6 +176,35 @@ int p4b_pattern_solve_from(p4b_ctx *c, const p4b_pattern_opts *opts, const doubl
     return 0;
 }
 
+int p4b_ts2d_solve(p4b_ctx *c, const p4b_pattern_opts *opts, p4b_ifunction2d_fn ifunction, p4b_rhsfunction2d_fn rhsfunction,
+                   void *user, double *Y_inout_host, size_t Y_capacity, p4b_line_fn line, void *line_ctx,
+                   p4b_pattern_result *result) {
+    if (!c || !opts || !ifunction || !rhsfunction || !Y_inout_host || !result) return fail(62, "p4b_ts2d_solve: null argument");
+    const nk::PatternOpts &o = *reinterpret_cast<const nk::PatternOpts *>(opts);
+    if ((o.grid_x << o.refine) != (o.grid_y << o.refine)) return fail(1, "the device path needs mx == my");
+    if (o.pc_type != nk::PC_NONE) return fail(56, "p4b_ts2d_solve: -pc_type none only");
+    const int m = o.grid_x << o.refine;
+    const size_t n = (size_t)2 * m * m;
+    if (Y_capacity < n) return fail(63, "Y is too small for the grid");
+    HostCallbackPatternOps ops;
+    ops.ifn = ifunction;
+    ops.gfn = rhsfunction;
+    ops.user = user;
+    nk::Printer pr{line, line_ctx};
+    double *Y = nullptr;
+    std::vector<double> Y0(Y_inout_host, Y_inout_host + n);
+    nk::PatternResult &R = *reinterpret_cast<nk::PatternResult *>(result);
+    int rc = nk::pattern_solve(&ops, o, pr, &Y, &R, Y0.data());
+    if (!rc && ops.error()) rc = ops.error();
+    if (!rc) memcpy(Y_inout_host, Y, sizeof(double) * n);
+    if (Y) ops.release(Y);
+    if (getenv("P4B_STANDIN_REPORT")) fprintf(stderr, "standin: ts2d callbacks %lld\n", ops.callbacks);
+    if (rc == 64) return fail(64, "TSSolve: a nonlinear (stage) solve did not converge");
+    if (rc == 65) return fail(65, "a callback returned an error");
+    if (rc) return fail(rc, "p4b_ts2d_solve failed");
+    return 0;
+}
+
 // ---- fish.c: the operator the shim's Mat type recognised (finest level) and a Jacobi-preconditioned CG on it.  There is
 // NO multigrid here: iteration counts are not the device path's; what the stand-in lets a CPU test see is everything
 // the shim does around the solve (callbacks, Mat recognition, Vec bookkeeping, the reference's own report lines). ----

@@ -101,6 +101,7 @@ struct DeviceOps {
     void pattern_restrict(int Mx, int My, const double *rf, double *bc) { chk(p4b_pattern_restrict(c, Mx, My, rf, bc)); }
     void pattern_prolong_add(int Mx, int My, const double *xc, double *xf) { chk(p4b_pattern_prolong_add(c, Mx, My, xc, xf)); }
     void pattern_inject(int Mx, int My, const double *yf, double *yc) { chk(p4b_pattern_inject(c, Mx, My, yf, yc)); }
+    void set_linearisation(const double *) {}             // the kernels take the state as an argument
 };
 
 // The same operations with the RESIDUAL supplied by the caller as a host callback -- the FormFunctionLocal contract of
@@ -148,6 +149,69 @@ struct CallbackOps : DeviceOps {
             }
         release(up);
         release(Fp);
+    }
+};
+
+// The time-stepping operations with F(t, Y, Ydot) and G(t, Y) supplied by the caller as HOST callbacks (the
+// DMDATSSetIFunctionLocal / DMDATSSetRHSFunctionLocal contract, c/ch5/pattern.c:103-114) and NO Jacobian: the stage operator
+// is the differenced residual ([PETSc] MatMFFD "wp", as -snes_mf does),
+//     J X = d/de [ F(Y + e X, shift (Y + e X)) - G(Y + e X) ]   (F = M Ydot + f(Y) with a constant M: the caller checks that)
+// with the vectors and the Krylov / Newton / controller algebra on the device.  No assembled matrix means no multigrid:
+// -pc_type none only.
+struct CallbackPatternOps : DeviceOps {
+    p4b_ifunction2d_fn ifn = nullptr;
+    p4b_rhsfunction2d_fn gfn = nullptr;
+    void *user = nullptr;
+    const double *lin = nullptr;                           // linearisation point of the next operator products
+    std::vector<double> hY, hD, hF;
+    double *wY = nullptr, *wD = nullptr, *wF = nullptr, *wR0 = nullptr;
+    const double *r0_for = nullptr;
+    double r0_shift = 0.0;
+    bool r0_rhs = false;
+    long long callbacks = 0;
+    CallbackPatternOps(p4b_ctx *c_, cudaStream_t st_, p4b_ifunction2d_fn f, p4b_rhsfunction2d_fn g, void *u)
+        : DeviceOps{c_, st_}, ifn(f), gfn(g), user(u) {}
+    void free_work() { for (double *p : {wY, wD, wF, wR0}) release(p); wY = wD = wF = wR0 = nullptr; }
+    void pattern_ifunction(int m, const PO &, const double *Y, const double *Ydot, double *F) {
+        const size_t n = (size_t)2 * m * m;
+        hY.resize(n); hD.resize(n); hF.resize(n);
+        to_host(Y, hY.data(), n);
+        to_host(Ydot, hD.data(), n);
+        callbacks++;
+        if (!err && ifn(user, m, 0.0, hY.data(), hD.data(), hF.data())) err = 65;
+        from_host(hF.data(), F, n);
+    }
+    void pattern_rhsfunction(int m, const PO &, const double *Y, double *G) {
+        const size_t n = (size_t)2 * m * m;
+        hY.resize(n); hF.resize(n);
+        to_host(Y, hY.data(), n);
+        callbacks++;
+        if (!err && gfn(user, m, 0.0, hY.data(), hF.data())) err = 65;
+        from_host(hF.data(), G, n);
+    }
+    void set_linearisation(const double *Y) { lin = Y; r0_for = nullptr; }
+    // R(W) = F(W, shift W) - [rhs ? G(W) : 0]
+    void resid(int m, const PO &o, double shift, bool rhs, const double *W, double *out) {
+        const size_t n = (size_t)2 * m * m;
+        axpby(n, shift, W, 0.0, nullptr, wD);
+        pattern_ifunction(m, o, W, wD, out);
+        if (rhs) { pattern_rhsfunction(m, o, W, wF); axpy(n, -1.0, wF, out); }
+    }
+    void pattern_jac_apply(int m, const PO &o, double shift, const double *Y, const double *X, double *out) {
+        const size_t n = (size_t)2 * m * m;
+        const bool rhs = Y != nullptr;                     // (nullptr: IMEX or -ptn_no_rhsjacobian, G' stays out)
+        if (!lin) { if (!err) err = 68; return; }
+        if (!wY) { wY = alloc(n); wD = alloc(n); wF = alloc(n); wR0 = alloc(n); }
+        if (r0_for != lin || r0_shift != shift || r0_rhs != rhs) {          // R(Y): once per linearisation point
+            resid(m, o, shift, rhs, lin, wR0);
+            r0_for = lin; r0_shift = shift; r0_rhs = rhs;
+        }
+        const double xn = norm2(n, X);
+        if (xn == 0.0) { set(n, 0.0, out); return; }
+        const double h = 1.4901161193847656e-08 * sqrt(1.0 + norm2(n, lin)) / xn;
+        axpby(n, 1.0, lin, h, X, wY);
+        resid(m, o, shift, rhs, wY, out);
+        axpby(n, 1.0 / h, out, -1.0 / h, wR0, out);
     }
 };
 
@@ -259,6 +323,38 @@ extern "C" int p4b_snes2d_solve_monitored(p4b_ctx *c, const p4b_minimal_opts *op
     if (rc == 65) return fail(65, "the residual callback returned an error");
     if (rc == 66) return fail(66, "the monitor callback returned an error");
     if (rc) return fail(rc, "p4b_snes2d_solve failed (%s)", p4b_last_error());
+    return 0;
+}
+
+extern "C" int p4b_ts2d_solve(p4b_ctx *c, const p4b_pattern_opts *opts, p4b_ifunction2d_fn ifunction,
+                              p4b_rhsfunction2d_fn rhsfunction, void *user, double *Y_inout_host, size_t Y_capacity,
+                              p4b_line_fn line, void *line_ctx, p4b_pattern_result *result) {
+    if (!c || !opts || !ifunction || !rhsfunction || !Y_inout_host || !result) return fail(62, "p4b_ts2d_solve: null argument");
+    const nk::PatternOpts &o = *reinterpret_cast<const nk::PatternOpts *>(opts);
+    if (o.grid_x < 3 || o.grid_y < 3) return fail(60, "periodic grid needs at least 3 nodes per dimension");
+    if ((o.grid_x << o.refine) != (o.grid_y << o.refine)) return fail(1, "the device path needs mx == my");
+    if (o.ts_type < nk::TS_ARKIMEX || o.ts_type > nk::TS_BDF) return fail(62, "ts_type: arkimex (0), beuler (1), cn (2), bdf (3)");
+    if (o.pc_type != nk::PC_NONE)
+        return fail(56, "p4b_ts2d_solve: callbacks without a Jacobian give a matrix-free stage operator; no matrix, no multigrid: "
+                        "-pc_type none only");
+    const int m = o.grid_x << o.refine;
+    const size_t n = (size_t)2 * m * m;
+    if (Y_capacity < n) return fail(63, "Y holds %zu doubles, the grid needs 2 x %d x %d", Y_capacity, m, m);
+    CallbackPatternOps ops(c, ctx_stream(c), ifunction, rhsfunction, user);
+    nk::Printer pr{line, line_ctx};
+    double *Y = nullptr, *Y0 = ops.alloc(n);
+    ops.from_host(Y_inout_host, Y0, n);
+    nk::PatternResult &R = *reinterpret_cast<nk::PatternResult *>(result);
+    int rc = nk::pattern_solve(&ops, o, pr, &Y, &R, Y0);
+    if (!rc && ops.error()) rc = ops.error();
+    if (!rc) ops.to_host(Y, Y_inout_host, n);
+    ops.release(Y0);
+    if (Y) ops.release(Y);
+    ops.free_work();
+    cudaStreamSynchronize(ops.st);
+    if (rc == 64) return fail(64, "TSSolve: a nonlinear (stage) solve did not converge");
+    if (rc == 65) return fail(65, "a callback returned an error");
+    if (rc) return fail(rc, "p4b_ts2d_solve failed (%s)", p4b_last_error());
     return 0;
 }
 

@@ -358,6 +358,7 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
                         double rn = r0;
                         int its = 0;
                         while (rn > opt.snes_rtol * r0 && rn > opt.snes_atol && its < opt.snes_max_it) {
+                            ops->set_linearisation(Ys[i]);      // (only a callback-defined operator needs it: F is linear here)
                             KSPInfo ki = gmres(ops, n, mult, Rv, d, prec, opt.ksp_rtol, 1.0e-50, opt.gmres_restart,
                                                opt.ksp_max_it, V, w, t1);
                             R->ksp_its_total += ki.its;
@@ -411,6 +412,7 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
                 if (X != Y) ops->copy(n, X, Y);                  // the stage operator linearises about lev[0].Y
                 rc = A.setup(shift);
                 if (rc) break;
+                ops->set_linearisation(X);
                 KSPInfo ki = gmres(ops, n, mult, Rv, y, prec, opt.ksp_rtol, 1.0e-50, opt.gmres_restart, opt.ksp_max_it, V, w, t1);
                 R->ksp_its_total += ki.its;
                 if (opt.ksp_converged_reason)

@@ -98,6 +98,9 @@ class PatternResult(C.Structure):
 
 LINE_FN = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)
 RESIDUAL2D_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double))
+IFUNCTION2D_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                             C.POINTER(C.c_double))
+RHSFUNCTION2D_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double))
 MONITOR2D_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double))
 
 
@@ -196,6 +199,8 @@ _SIGS = {
     "p4b_pattern_solve": (C.c_int, [_P, C.POINTER(PatternOpts), LINE_FN, _P, _D, C.c_size_t, C.POINTER(PatternResult)]),
     "p4b_pattern_solve_from": (C.c_int, [_P, C.POINTER(PatternOpts), _D, LINE_FN, _P, _D, C.c_size_t,
                                         C.POINTER(PatternResult)]),
+    "p4b_ts2d_solve": (C.c_int, [_P, C.POINTER(PatternOpts), IFUNCTION2D_FN, RHSFUNCTION2D_FN, _P, _P, C.c_size_t, LINE_FN,
+                                _P, C.POINTER(PatternResult)]),
     "p4b_sell_create": (C.c_int, [_P, C.c_int, _P, _P, _P, C.POINTER(_P)]),
     "p4b_sell_spmv": (C.c_int, [_P, _D, _D]),
     "p4b_sell_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

@@ -32,7 +32,7 @@ static p4b_ctx *g_ctx = NULL;
 static double g_flops = 0.0;
 static double g_t_snes = 0.0, g_t_ksp = 0.0, g_t_ksp_dev_ms = 0.0, g_t_jac = 0.0, g_t_func = 0.0;
 static int g_initialized = 0;
-static int g_newton_solves = 0;
+static int g_newton_solves = 0, g_ts_general = 0;
 
 static double wall(void) {
     struct timespec ts;
@@ -113,6 +113,7 @@ PetscErrorCode PetscFinalize(void) {
         printf("             FunctionEval(host callback) %.6e   JacobianEval(host callback, all levels) %.6e\n",
                g_t_func, g_t_jac);
         printf("Flop:  %.6e (user PetscLogFlops only)   kernel launches: %lld\n", g_flops, p4b_launch_count());
+        if (g_ts_general) printf("TS: callbacks evaluated on the host, matrix-free stage operator (not the library's model)\n");
         if (g_newton_solves)
             printf("SNES newtonls: residual %s\n", p4b_snes2d_last_route()
                    ? "recognised as the library's kernel: evaluated on the device" : "evaluated by the host callback");
@@ -1509,6 +1510,87 @@ static void ts_work_release(struct ts_work *W) {
     memset(W, 0, sizeof *W);
 }
 
+/* TSSolve for callbacks that are NOT the model the library has as kernels: p4b_ts2d_solve -- the same time steppers with
+ * F and G evaluated by the user's host callbacks and the stage operator the differenced residual ([PETSc] MatMFFD), vectors
+ * and algebra on the device.  No Jacobian matrix means no multigrid (-pc_type none), and the differencing assumes
+ * F = M Ydot + f(Y) with a constant M, which is checked here on the callbacks (five evaluations). */
+static int ts_ifn(void *user, int m, double t, const double *Y, const double *Ydot, double *F) {
+    TS ts = (TS)user;
+    (void)m;
+    return ts_eval_ifunc(ts->dm, t, Y, Ydot, F) != 0;
+}
+static int ts_gfn(void *user, int m, double t, const double *Y, double *G) {
+    TS ts = (TS)user;
+    (void)m;
+    return ts_eval_rhs(ts->dm, t, Y, G) != 0;
+}
+static PetscErrorCode ts_solve_general(TS ts, Vec x, struct ts_work *W, p4b_pattern_opts *o, const char *why) {
+    DM dm = ts->dm;
+    KSP ksp = &ts->snes->ksp;
+    const size_t n = x->n;
+    char msg[768];
+    if (o->pc_type != 0) {
+        snprintf(msg, sizeof msg, "%s.  Arbitrary callbacks run through the matrix-free route (stage operator = differenced "
+                 "residual, no Jacobian matrix, hence no multigrid): pass -pc_type none", why);
+        SHIM_ERR(56, msg);
+    }
+    /* F(Y, a D) - F(Y, 0) must be a (F(Y, D) - F(Y, 0)) and must not depend on Y */
+    double *Y = W->Y, *D = W->D, *F0 = W->Fu, *F1 = W->Fd;
+    double *F2 = (double *)malloc(sizeof(double) * n), *T = (double *)malloc(sizeof(double) * n);
+    if (!F2 || !T) { free(F2); free(T); SHIM_ERR(55, "out of host memory"); }
+    PetscErrorCode rc = 0;
+    double worst = 0.0, scale = 1.0;
+    do {
+        memset(T, 0, sizeof(double) * n);
+        if ((rc = ts_eval_ifunc(dm, 0.0, Y, T, F0))) break;
+        if ((rc = ts_eval_ifunc(dm, 0.0, Y, D, F1))) break;
+        for (size_t i = 0; i < n; i++) T[i] = 2.0 * D[i];
+        if ((rc = ts_eval_ifunc(dm, 0.0, Y, T, F2))) break;
+        for (size_t i = 0; i < n; i++) {
+            const double e = fabs((F2[i] - F0[i]) - 2.0 * (F1[i] - F0[i]));
+            if (!(e <= worst)) worst = e;
+            if (fabs(F1[i] - F0[i]) > scale) scale = fabs(F1[i] - F0[i]);
+            F1[i] -= F0[i];                                           /* F1 := M D at Y */
+        }
+        for (size_t i = 0; i < n; i++) T[i] = Y[i] + 0.1 * D[i];
+        memset(F2, 0, sizeof(double) * n);
+        if ((rc = ts_eval_ifunc(dm, 0.0, T, F2, F0))) break;           /* F(Yb, 0) */
+        if ((rc = ts_eval_ifunc(dm, 0.0, T, D, F2))) break;            /* F(Yb, D) */
+        for (size_t i = 0; i < n; i++) {
+            const double e = fabs((F2[i] - F0[i]) - F1[i]);
+            if (!(e <= worst)) worst = e;
+        }
+    } while (0);
+    free(F2);
+    free(T);
+    if (rc) return rc;
+    if (!(worst <= 1.0e-10 * scale)) {
+        snprintf(msg, sizeof msg, "TSSolve: the registered IFunction is not of the form M Ydot + f(Y) with a constant M "
+                 "(deviation %.3e): the matrix-free route cannot difference it", worst);
+        SHIM_ERR(56, msg);
+    }
+    ts_work_release(W);
+    o->call_back_report = 0;
+    o->no_rhsjacobian = 0;
+    o->grid_x = dm->M0[0]; o->grid_y = dm->M0[1]; o->refine = dm->refine;
+    o->ts_dt = ts->dt; o->ts_max_time = ts->max_time; o->ts_max_steps = ts->max_steps;
+    o->ts_rtol = ts->rtol; o->ts_atol = ts->atol; o->ts_monitor = ts->monitor;
+    o->snes_rtol = ts->snes->rtol; o->snes_stol = ts->snes->stol; o->snes_atol = ts->snes->atol; o->snes_max_it = ts->snes->max_it;
+    o->ksp_rtol = ksp->rtol; o->ksp_max_it = ksp->max_it; o->gmres_restart = ts->snes->gmres_restart;
+    o->snes_converged_reason = ts->snes->converged_reason_flag;
+    o->ksp_converged_reason = ksp->converged_reason_flag;
+    PetscCall(vec_to_host(x));
+    p4b_pattern_result *R = W->R = (p4b_pattern_result *)calloc(1, sizeof *R);
+    if (!R) SHIM_ERR(55, "out of host memory");
+    fflush(stdout);
+    int prc = p4b_ts2d_solve(g_ctx, o, ts_ifn, ts_gfn, ts, x->h, n, newton_line, NULL, R);
+    fflush(stdout);
+    if (prc) return PetscShimError(PETSC_COMM_SELF, __LINE__, __func__, __FILE__, prc, p4b_last_error());
+    x->valid = LOC_HOST;
+    g_ts_general++;
+    return 0;
+}
+
 static PetscErrorCode ts_solve(TS ts, Vec x, struct ts_work *W) {
     DM dm = ts->dm;
     KSP ksp = &ts->snes->ksp;
@@ -1591,23 +1673,31 @@ static PetscErrorCode ts_solve(TS ts, Vec x, struct ts_work *W) {
     PetscCall(ts_eval_ifunc(dm, 0.0, Y, D, Fu));
     P4B(p4b_pattern_ifunction(g_ctx, m, m, o.L, o.Du, o.Dv, dY, dD, dF));
     P4B(p4b_memcpy_d2h(g_ctx, Fd, dF, n * sizeof(double)));
+    int is_model = 1;
     dev = maxabs_diff(Fu, Fd, n, &scale);
     if (!(dev <= 1.0e-11 * (scale > 1.0 ? scale : 1.0))) {
+        is_model = 0;
         snprintf(msg, sizeof msg, "TSSolve: the registered IFunction is not F = Ydot - D L9 Y / (6 h^2) with the identified "
-                 "D_u = %g, D_v = %g (max deviation %.3e): not the reaction-diffusion model the device path implements", o.Du,
+                 "D_u = %g, D_v = %g (max deviation %.3e): not the reaction-diffusion model the device path has as kernels", o.Du,
                  o.Dv, dev);
-        SHIM_ERR(56, msg);
     }
-    PetscCall(ts_eval_rhs(dm, 0.0, Y, Fu));
-    P4B(p4b_pattern_rhsfunction(g_ctx, m, m, o.phi, o.kappa, dY, dF));
-    P4B(p4b_memcpy_d2h(g_ctx, Fd, dF, n * sizeof(double)));
-    dev = maxabs_diff(Fu, Fd, n, &scale);
-    if (!(dev <= 1.0e-11 * (scale > 1.0 ? scale : 1.0))) {
-        snprintf(msg, sizeof msg, "TSSolve: the registered RHSFunction is not G = (-u v^2 + phi (1-u), u v^2 - (phi+kappa) v) "
-                 "with the identified phi = %g, kappa = %g (max deviation %.3e): not the model the device path implements",
-                 o.phi, o.kappa, dev);
-        SHIM_ERR(56, msg);
+    if (is_model) {
+        PetscCall(ts_eval_rhs(dm, 0.0, Y, Fu));
+        P4B(p4b_pattern_rhsfunction(g_ctx, m, m, o.phi, o.kappa, dY, dF));
+        P4B(p4b_memcpy_d2h(g_ctx, Fd, dF, n * sizeof(double)));
+        dev = maxabs_diff(Fu, Fd, n, &scale);
+        if (!(dev <= 1.0e-11 * (scale > 1.0 ? scale : 1.0))) {
+            is_model = 0;
+            snprintf(msg, sizeof msg, "TSSolve: the registered RHSFunction is not G = (-u v^2 + phi (1-u), u v^2 - (phi+kappa) v) "
+                     "with the identified phi = %g, kappa = %g (max deviation %.3e): not the model the device path has as kernels",
+                     o.phi, o.kappa, dev);
+        }
     }
+    if (is_model && opt_value("-p4b_recognise_residual") && !atol(opt_value("-p4b_recognise_residual"))) {
+        is_model = 0;                  /* A/B: run the model through the general route as well */
+        snprintf(msg, sizeof msg, "TSSolve: -p4b_recognise_residual 0");
+    }
+    if (!is_model) return ts_solve_general(ts, x, W, &o, msg);
     /* the Jacobian callbacks PETSc would call for this type: IJacobian always, RHSJacobian for the fully implicit types */
     {
         DMDALocalInfo info;

@@ -103,14 +103,66 @@ def test_error_paths(exe, argv, code, msg):
     assert p.returncode == code and msg in p.stderr and "PETSC ERROR" in p.stderr
 
 
-def test_other_parameter_values_run_and_other_models_are_refused(variants):
+def test_other_parameter_values_run_and_other_models_take_the_general_route(variants):
     ok, _ = run(variants, "-variant 0 -da_refine 2 -ts_monitor" + MG)
     assert ok[-1].startswith("done: |Y|_2 = ") and ok[-2].endswith("time 20.")
-    for v, what in ((1, "RHSFunction is not G"), (2, "IFunction is not F"), (3, "IJacobian does not insert")):
+    # callbacks that are not the model: with multigrid asked for, a refusal that names the way out ...
+    for v, what in ((1, "RHSFunction is not G"), (2, "IFunction is not F")):
         _, p = run(variants, "-variant %d -da_refine 2" % v + MG, check=False)
-        assert p.returncode == 56 and what in p.stderr and "max deviation" in p.stderr
+        assert p.returncode == 56 and what in p.stderr and "max deviation" in p.stderr and "pass -pc_type none" in p.stderr
+    # ... a Jacobian callback that contradicts its own (model) functions is refused outright
+    _, p = run(variants, "-variant 3 -da_refine 2" + MG, check=False)
+    assert p.returncode == 56 and "IJacobian does not insert" in p.stderr
     # a wrong RHS Jacobian is only seen where PETSc would call it: the IMEX default never does
     ok4, _ = run(variants, "-variant 4 -da_refine 2 -ts_monitor" + MG)
     assert ok4 == ok
     _, p = run(variants, "-variant 4 -da_refine 2 -ts_type beuler" + MG, check=False)
     assert p.returncode == 56 and "RHSJacobian does not insert" in p.stderr
+
+
+def test_general_matrix_free_route(exe, variants):
+    """p4b_ts2d_solve under the shim: F and G are the user's host callbacks, the stage operator the differenced residual.
+    (1) The model itself through this route (recognition switched off) gives what the kernel route gives -- the unchanged
+    pattern.c prints pattern.test4's adaptive steps verbatim (its own report then says the Jacobian callback was never
+    called); (2) a system the library has no kernels for (extra cubic reaction term) agrees with an independent NumPy
+    backward-Euler solve of the same equations."""
+    g = GOLD["pattern.test4"]
+    lines, _ = run(exe, g["options"] + " -pc_type none -p4b_recognise_residual 0 -log_view")
+    assert lines[:len(g["lines"]) - 2] == g["lines"][:-2] and lines[len(g["lines"]) - 2] == "  IFunction:   1  | IJacobian:   0"
+    assert "TS: callbacks evaluated on the host, matrix-free stage operator (not the library's model)" in lines
+    argv = "-da_refine 2 -pc_type none -ts_type beuler -ts_dt 2 -ts_max_time 6 -snes_rtol 1e-10"
+    a, _ = run(variants, "-variant 0 " + argv)
+    b, _ = run(variants, "-variant 0 -p4b_recognise_residual 0 " + argv)
+    assert a == b
+    c, _ = run(variants, "-variant 1 " + argv)
+    # the same three steps in NumPy: Newton on F(W, (W - Y)/dt) - G(W) with the analytic Jacobian
+    import numpy as np
+    import scipy.sparse as sp
+    from oracle import fish_oracle as fo
+    from oracle import minimal_pattern_oracle as mpo
+    from oracle import minimal_solver_oracle as mso
+    from oracle import pattern_solver_oracle as po
+    m, par = 16, dict(L=2.0, Du=6.0e-5, Dv=3.5e-5, phi=0.03, kappa=0.055)
+    sx = np.sin(2.0 * np.pi * np.arange(m) / m)
+    Y = np.zeros((m, m, 2))
+    Y[..., 1] = 0.25 * (sx[None, :] ** 2) * (sx[:, None] ** 2)
+    Y[..., 0] = 1.0 - 2.0 * Y[..., 1]
+    dt = 2.0
+
+    def G(W):
+        out = mpo.pattern_rhsfunction(W, par["phi"], par["kappa"])
+        out[..., 0] += 1.0e-3 * W[..., 0] ** 3
+        return out
+
+    for _ in range(3):
+        Y0 = Y.copy()
+        R = lambda W: mpo.pattern_ifunction(W, (W - Y0) / dt, par["L"], par["Du"], par["Dv"]) - G(W)
+
+        def jac(W):
+            d = np.zeros_like(W)
+            d[..., 0] = 3.0e-3 * W[..., 0] ** 2
+            return (po.stage_jacobian(W, 1.0 / dt, True, **par) - sp.diags(d.ravel())).tocsr()
+
+        Y = mso.newton(R, Y0, lambda J, W: fo.ILU0PC(J).apply, jac=jac, snes_rtol=1e-12).u
+    got = float(c[-1].split()[-1])
+    assert abs(got - np.linalg.norm(Y)) <= 1e-8 * np.linalg.norm(Y) and c != a

@@ -16,7 +16,7 @@ PY
 timeout 900 python -m pytest tests -x -q -m gpu > "$out/gpu.log" 2>&1; echo "gpu suite rc=$?" | tee -a "$out/summary.txt"
 # 2. the pending device tests
 timeout 1200 python -m pytest tests -q -m gpu_pending -rA > "$out/gpu_pending.log" 2>&1; echo "gpu_pending rc=$?" | tee -a "$out/summary.txt"
-tail -5 "$out/gpu_pending.log" | tee -a "$out/summary.txt"
+tail -8 "$out/gpu_pending.log" | tee -a "$out/summary.txt"
 # 3. the unchanged drivers at the BASELINE sizes
 MG="-pc_type mg -mg_levels_pc_type jacobi"
 C4="-da_grid_x 33 -da_grid_y 33 -snes_grid_sequence 6 -snes_fd_color -snes_converged_reason -log_view $MG"
