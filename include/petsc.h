@@ -86,6 +86,7 @@ typedef const char *MatType;
 #define PCJACOBI "jacobi"
 #define PCNONE "none"
 #define MATSTENCILCUDA "stencilcuda"
+#define MATSELLCUDA "sellcuda"
 
 typedef enum { DM_BOUNDARY_NONE = 0, DM_BOUNDARY_GHOSTED, DM_BOUNDARY_MIRROR, DM_BOUNDARY_PERIODIC } DMBoundaryType;
 typedef enum { DMDA_STENCIL_STAR = 0, DMDA_STENCIL_BOX } DMDAStencilType;

@@ -34,6 +34,7 @@ struct p4b_ctx { int unused; };
 static int g_route = 0, g_recognise = 1;
 static long long g_callbacks = 0;
 struct p4b_mg { p4b_grid g; double diag, c[3]; };
+struct p4b_sell { int n; std::vector<int> rp, ci; std::vector<double> v; };
 
 extern "C" {
 
@@ -245,13 +246,13 @@ int p4b_mg_matmult(p4b_mg *mg, const double *x, double *y) {
             }
     return 0;
 }
-int p4b_cg_solve(p4b_mg *mg, int, const double *b, double *x, double rtol, double abstol, int max_it, p4b_ksp_result *res) {
+int p4b_cg_solve(p4b_mg *mg, int pc_type, const double *b, double *x, double rtol, double abstol, int max_it, p4b_ksp_result *res) {
     const size_t n = (size_t)mg->g.mx * (mg->g.dim >= 2 ? mg->g.my : 1) * (mg->g.dim >= 3 ? mg->g.mz : 1);
     std::vector<double> r(b, b + n), z(n), p(n), w(n);
     HostOps o;
     memset(res, 0, sizeof *res);
     memset(x, 0, sizeof(double) * n);
-    const double idiag = 1.0 / mg->diag;
+    const double idiag = pc_type == P4B_PC_NONE ? 1.0 : 1.0 / mg->diag;       // (mg: Jacobi stands in, see above)
     for (size_t i = 0; i < n; i++) z[i] = idiag * r[i];
     double znorm = o.norm2(n, z.data()), beta = o.dot(n, r.data(), z.data());
     res->rnorm0 = znorm;
@@ -277,5 +278,25 @@ int p4b_cg_solve(p4b_mg *mg, int, const double *b, double *x, double rtol, doubl
     res->rnorm = znorm;
     return 0;
 }
+
+// ---- assembled matrices: CSR kept as given (the device library converts to SELL-32; the product of y = A x is the same) ----
+int p4b_sell_create(p4b_ctx *, int nrows, const int *rowptr, const int *colind, const double *vals, p4b_sell **A) {
+    p4b_sell *S = new p4b_sell;
+    S->n = nrows;
+    S->rp.assign(rowptr, rowptr + nrows + 1);
+    S->ci.assign(colind, colind + rowptr[nrows]);
+    S->v.assign(vals, vals + rowptr[nrows]);
+    *A = S;
+    return 0;
+}
+int p4b_sell_spmv(p4b_sell *A, const double *x, double *y) {
+    for (int r = 0; r < A->n; r++) {
+        double s2 = 0.0;
+        for (int k = A->rp[r]; k < A->rp[r + 1]; k++) s2 += A->v[k] * x[A->ci[k]];
+        y[r] = s2;
+    }
+    return 0;
+}
+int p4b_sell_destroy(p4b_sell *A) { delete A; return 0; }
 
 }  // extern "C"

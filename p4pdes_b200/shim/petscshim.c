@@ -247,6 +247,11 @@ struct _p_Mat {
     char why[160];
     int assembled;
     struct rd_check *rd; /* non-NULL: a TS Jacobian of a 2-component periodic DMDA is being checked (TSSolve) */
+    /* Mat type "sellcuda": the inserted values are KEPT (any coefficients), row by row, and go to the device as a SELL-32
+     * matrix ([PETSc] MATSELL / AIJ) for the SpMV kernel */
+    int width;           /* slots per row: 3^dim (every stencil the DMDA can hold) */
+    int *ccol, *ccnt;    /* column indices (natural ordering) and fill count per row */
+    double *cval;
 };
 
 /* TS Jacobians (pattern.c:202-318): the rows inserted by the user's FormIJacobianLocal / FormRHSJacobianLocal are
@@ -315,6 +320,17 @@ PetscErrorCode PCRegister(const char name[], PetscErrorCode (*create)(PC)) {
     return 0;
 }
 static PetscErrorCode MatCreate_StencilCUDA(Mat A) { A->type = MATSTENCILCUDA; return 0; }
+static PetscErrorCode MatCreate_SellCUDA(Mat A) {
+    const size_t nrows = (size_t)A->dm->M[0] * A->dm->M[1] * A->dm->M[2];
+    if (A->dm->dof != 1) SHIM_ERR(56, "Mat type sellcuda: one degree of freedom per node");
+    A->type = MATSELLCUDA;
+    A->width = A->dm->dim == 1 ? 3 : (A->dm->dim == 2 ? 9 : 27);
+    A->ccol = (int *)malloc(sizeof(int) * nrows * A->width);
+    A->cval = (double *)malloc(sizeof(double) * nrows * A->width);
+    A->ccnt = (int *)calloc(nrows, sizeof(int));
+    if (!A->ccol || !A->cval || !A->ccnt) SHIM_ERR(55, "out of host memory for the assembled matrix");
+    return 0;
+}
 static PetscErrorCode PCCreate_MG_P4B(PC pc) { snprintf(pc->type, 32, "%s", PCMG); return 0; }
 static PetscErrorCode PCCreate_Jacobi_P4B(PC pc) { snprintf(pc->type, 32, "%s", PCJACOBI); return 0; }
 static PetscErrorCode PCCreate_None_P4B(PC pc) { snprintf(pc->type, 32, "%s", PCNONE); return 0; }
@@ -323,6 +339,7 @@ static void register_all(void) {
     if (done) return;
     done = 1;
     MatRegister(MATSTENCILCUDA, MatCreate_StencilCUDA);
+    MatRegister(MATSELLCUDA, MatCreate_SellCUDA);
     PCRegister(PCMG, PCCreate_MG_P4B);
     PCRegister(PCJACOBI, PCCreate_Jacobi_P4B);
     PCRegister(PCNONE, PCCreate_None_P4B);
@@ -653,14 +670,18 @@ static PetscErrorCode mat_new(DM dm, Mat *mat) {
             return 0;
         }
     free(A);
-    SHIM_ERR(86, "unknown -mat_type (registered: stencilcuda)");
+    SHIM_ERR(86, "unknown -mat_type (registered: stencilcuda, sellcuda)");
 }
 PetscErrorCode DMCreateMatrix(DM dm, Mat *mat) { return mat_new(dm, mat); }
 PetscErrorCode MatDestroy(Mat *mat) {
-    if (mat && *mat) { free(*mat); *mat = NULL; }
+    if (mat && *mat) { free((*mat)->ccol); free((*mat)->cval); free((*mat)->ccnt); free(*mat); *mat = NULL; }
     return 0;
 }
 PetscErrorCode MatZeroEntries(Mat A) {
+    if (A->ccnt) {
+        const size_t nrows = (size_t)A->dm->M[0] * A->dm->M[1] * A->dm->M[2];
+        for (size_t r = 0; r < nrows * (size_t)A->width; r++) A->cval[r] = 0.0;      /* keeps the nonzero pattern, as PETSc does */
+    }
     A->have_diag = A->have_c[0] = A->have_c[1] = A->have_c[2] = 0;
     A->rows_set = 0; A->general = 0; A->assembled = 0;
     return 0;
@@ -695,6 +716,35 @@ static PetscErrorCode rd_check_rows(struct rd_check *k, PetscInt m, const MatSte
     }
     return 0;
 }
+/* Mat type "sellcuda": INSERT_VALUES of one or more rows */
+static PetscErrorCode sell_set_rows(Mat A, PetscInt m, const MatStencil idxm[], PetscInt n, const MatStencil idxn[],
+                                    const PetscScalar v[]) {
+    const DM dm = A->dm;
+    const int dim = dm->dim, W = A->width;
+    for (int r = 0; r < m; r++) {
+        const int ri = idxm[r].i, rj = dim >= 2 ? idxm[r].j : 0, rk = dim >= 3 ? idxm[r].k : 0;
+        if (ri < 0 || ri >= dm->M[0] || rj < 0 || rj >= dm->M[1] || rk < 0 || rk >= dm->M[2])
+            SHIM_ERR(63, "MatSetValuesStencil: row outside the grid");
+        const size_t row = ((size_t)rk * dm->M[1] + rj) * dm->M[0] + ri;
+        for (int c = 0; c < n; c++) {
+            const int ci = idxn[c].i, cj = dim >= 2 ? idxn[c].j : 0, ck = dim >= 3 ? idxn[c].k : 0;
+            if (ci < 0 || ci >= dm->M[0] || cj < 0 || cj >= dm->M[1] || ck < 0 || ck >= dm->M[2])
+                SHIM_ERR(63, "MatSetValuesStencil: column outside the (non-periodic) grid");
+            const int col = (int)(((size_t)ck * dm->M[1] + cj) * dm->M[0] + ci);
+            int slot = -1;
+            for (int k = 0; k < A->ccnt[row]; k++)
+                if (A->ccol[row * W + k] == col) { slot = k; break; }
+            if (slot < 0) {
+                if (A->ccnt[row] >= W) SHIM_ERR(63, "MatSetValuesStencil: more entries in a row than the DMDA stencil holds");
+                slot = A->ccnt[row]++;
+                A->ccol[row * W + slot] = col;
+            }
+            A->cval[row * W + slot] = v[r * n + c];
+        }
+        A->rows_set++;
+    }
+    return 0;
+}
 static void mat_reject(Mat A, const char *why) {
     if (!A->general) { A->general = 1; snprintf(A->why, sizeof A->why, "%s", why); }
 }
@@ -710,6 +760,7 @@ PetscErrorCode MatSetValuesStencil(Mat A, PetscInt m, const MatStencil idxm[], P
     const DM dm = A->dm;
     const int dim = dm->dim;
     if (A->rd) return rd_check_rows(A->rd, m, idxm, n, idxn, v);
+    if (A->ccnt) return sell_set_rows(A, m, idxm, n, idxn, v);
     for (int r = 0; r < m; r++) {
         const int ri = idxm[r].i, rj = dim >= 2 ? idxm[r].j : 0, rk = dim >= 3 ? idxm[r].k : 0;
         const int rb = node_is_bdry(dm, ri, rj, rk);
@@ -1163,6 +1214,127 @@ static PetscErrorCode ksponly_matrix_checks(SNES snes, p4b_mg *mg, Vec u, Vec F0
     return 0;
 }
 
+/* KSPONLY with -mat_type sellcuda: the Jacobian callback's values are kept as inserted (any coefficients), converted to
+ * CSR on the host and to SELL-32 on the device (p4b_sell_create); KSPCG runs here as a host loop over the library's
+ * SpMV and Vec kernels ([PETSc] KSPSolve_CG, preconditioned norm).  Preconditioners: none, or jacobi when the
+ * diagonal is constant (the library has no pointwise Vec product); PCMG needs the structured type (-mat_type stencilcuda):
+ * its coarse operators are rediscretised stencils, not assembled matrices. */
+static int cmp_int(const void *a, const void *b) { return *(const int *)a - *(const int *)b; }
+static PetscErrorCode ksponly_solve_assembled(SNES snes, Vec u, Vec F, Vec Y, double fnorm0) {
+    DM dm = snes->dm;
+    KSP ksp = &snes->ksp;
+    PC pc = &ksp->pc;
+    (void)fnorm0;
+    if (strcmp(pc->type, PCNONE) && strcmp(pc->type, PCJACOBI))
+        SHIM_ERR(56, "-mat_type sellcuda: -pc_type none or jacobi (PCMG coarsens the structured type: -mat_type stencilcuda)");
+    Mat J = NULL;
+    PetscCall(mat_new(dm, &J));
+    DMDALocalInfo info;
+    void *au = NULL;
+    const double t_jac0 = wall();
+    PetscCall(DMDAGetLocalInfo(dm, &info));
+    PetscCall(DMDAVecGetArrayRead(dm, u, &au));
+    PetscErrorCode rc = dm->jac(&info, au, J, J, dm->jacctx);
+    PetscCall(DMDAVecRestoreArrayRead(dm, u, &au));
+    if (rc) { MatDestroy(&J); return rc; }
+    const size_t n = u->n;
+    const int W = J->width;
+    if (J->rows_set < (long long)n) { MatDestroy(&J); SHIM_ERR(73, "-mat_type sellcuda: the Jacobian callback did not set every row"); }
+    /* CSR with sorted columns; the diagonal for Jacobi */
+    int *rowptr = (int *)malloc(sizeof(int) * (n + 1)), *colind = (int *)malloc(sizeof(int) * n * W);
+    double *vals = (double *)malloc(sizeof(double) * n * W);
+    if (!rowptr || !colind || !vals) SHIM_ERR(55, "out of host memory for the CSR copy");
+    double dmin = 1e300, dmax = -1e300;
+    size_t nnz = 0;
+    for (size_t r = 0; r < n; r++) {
+        rowptr[r] = (int)nnz;
+        const int cnt = J->ccnt[r];
+        int order[27];
+        for (int k = 0; k < cnt; k++) order[k] = J->ccol[r * W + k];
+        qsort(order, (size_t)cnt, sizeof(int), cmp_int);
+        for (int k = 0; k < cnt; k++) {
+            double val = 0.0;
+            for (int q = 0; q < cnt; q++)
+                if (J->ccol[r * W + q] == order[k]) val = J->cval[r * W + q];
+            colind[nnz] = order[k];
+            vals[nnz] = val;
+            if ((size_t)order[k] == r) { if (val < dmin) dmin = val; if (val > dmax) dmax = val; }
+            nnz++;
+        }
+    }
+    rowptr[n] = (int)nnz;
+    MatDestroy(&J);
+    g_t_jac += wall() - t_jac0;
+    const int jacobi = !strcmp(pc->type, PCJACOBI);
+    if (jacobi && !(dmax - dmin <= 1e-14 * fabs(dmax) && dmin > 0.0)) {
+        free(rowptr); free(colind); free(vals);
+        SHIM_ERR(56, "-mat_type sellcuda -pc_type jacobi: provided for a constant positive diagonal (the library has no pointwise "
+                     "Vec product); use -pc_type none");
+    }
+    const double dinv = jacobi ? 1.0 / dmax : 1.0;
+    p4b_sell *A = NULL;
+    int prc = p4b_sell_create(g_ctx, (int)n, rowptr, colind, vals, &A);
+    free(rowptr); free(colind); free(vals);
+    if (prc) return PetscShimError(PETSC_COMM_SELF, __LINE__, __func__, __FILE__, prc, p4b_last_error());
+    /* [PETSc] KSPSolve_CG on A y = F0 from y = 0 */
+    Vec R = NULL, Z = NULL, P = NULL, Wv = NULL;
+    PetscCall(vec_new(dm, &R)); PetscCall(vec_new(dm, &Z)); PetscCall(vec_new(dm, &P)); PetscCall(vec_new(dm, &Wv));
+    PetscCall(vec_to_dev(F)); PetscCall(vec_to_dev(Y)); PetscCall(vec_to_dev(R)); PetscCall(vec_to_dev(Z));
+    PetscCall(vec_to_dev(P)); PetscCall(vec_to_dev(Wv));
+    const double t_ksp0 = wall();
+    P4B(p4b_vec_aypx(g_ctx, n, 0.0, F->d, R->d));                    /* r = b */
+    P4B(p4b_vec_aypx(g_ctx, n, -1.0, Y->d, Y->d));                   /* y = y - y = 0 */
+    P4B(p4b_vec_aypx(g_ctx, n, 0.0, R->d, Z->d));                    /* z = M^-1 r */
+    if (jacobi) P4B(p4b_vec_aypx(g_ctx, n, dinv - 1.0, Z->d, Z->d));
+    P4B(p4b_vec_aypx(g_ctx, n, 0.0, Z->d, P->d));
+    double beta = 0.0, dp = 0.0;
+    P4B(p4b_vec_dot(g_ctx, n, Z->d, R->d, &beta));
+    P4B(p4b_vec_norm2(g_ctx, n, Z->d, &dp));
+    const double ttol = ksp->rtol * dp > ksp->abstol ? ksp->rtol * dp : ksp->abstol;
+    int its = 0, reason = P4B_DIVERGED_ITS;
+    if (ksp->monitor_flag) printf("    %d KSP Residual norm %14.12e\n", 0, dp);
+    if (dp <= ttol) reason = P4B_CONVERGED_ATOL;
+    while (reason == P4B_DIVERGED_ITS && its < ksp->max_it) {
+        double pw = 0.0, bnew = 0.0;
+        P4B(p4b_sell_spmv(A, P->d, Wv->d));
+        P4B(p4b_vec_dot(g_ctx, n, P->d, Wv->d, &pw));
+        const double a = beta / pw;
+        P4B(p4b_vec_axpy(g_ctx, n, a, P->d, Y->d));
+        P4B(p4b_vec_axpy(g_ctx, n, -a, Wv->d, R->d));
+        P4B(p4b_vec_aypx(g_ctx, n, 0.0, R->d, Z->d));
+        if (jacobi) P4B(p4b_vec_aypx(g_ctx, n, dinv - 1.0, Z->d, Z->d));
+        P4B(p4b_vec_norm2(g_ctx, n, Z->d, &dp));
+        its++;
+        if (ksp->monitor_flag) printf("    %d KSP Residual norm %14.12e\n", its, dp);
+        if (!(dp == dp)) { reason = P4B_DIVERGED_NAN; break; }
+        if (dp <= ttol) { reason = dp <= ksp->abstol ? P4B_CONVERGED_ATOL : P4B_CONVERGED_RTOL; break; }
+        P4B(p4b_vec_dot(g_ctx, n, Z->d, R->d, &bnew));
+        P4B(p4b_vec_aypx(g_ctx, n, bnew / beta, Z->d, P->d));          /* p = z + (beta_new / beta) p */
+        beta = bnew;
+    }
+    g_t_ksp += wall() - t_ksp0;
+    Y->valid = LOC_DEV;
+    ksp->its = its;
+    ksp->reason = reason;
+    if (ksp->converged_reason_flag) {
+        if (reason > 0) printf("    Linear solve converged due to %s iterations %d\n", reason_name(reason), its);
+        else printf("    Linear solve did not converge due to %s iterations %d\n", reason_name(reason), its);
+    }
+    p4b_sell_destroy(A);
+    vec_free(R); vec_free(Z); vec_free(P); vec_free(Wv);
+    /* u = u0 - y, the post-solve norm, the reason line: as the structured path */
+    PetscCall(VecAXPY(u, -1.0, Y));
+    snes->its = 1;
+    if (snes->monitor_short || snes->monitor) {
+        double fnorm;
+        PetscCall(compute_function(snes, u, F));
+        PetscCall(VecNorm(F, NORM_2, &fnorm));
+        print_snes_norm(snes, 1, fnorm);
+    }
+    if (snes->converged_reason_flag) printf("Nonlinear solve converged due to CONVERGED_ITS iterations 1\n");
+    return 0;
+}
+
 PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
     if (b) SHIM_ERR(56, "SNESSolve with a right-hand side is not provided");
     if (!strcmp(snes->type, SNESNEWTONLS)) return snes_solve_newtonls(snes, x);
@@ -1197,6 +1369,21 @@ PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
     PetscCall(VecNorm(F, NORM_2, &fnorm));
     print_snes_norm(snes, 0, fnorm);
 
+    {
+        const char *mt = opt_value("-mat_type");
+        if (mt && !strcmp(mt, MATSELLCUDA)) {
+            PetscErrorCode rcs = ksponly_solve_assembled(snes, u, F, Y, fnorm);
+            vec_free(F);
+            vec_free(Y);
+            if (rcs) return rcs;
+            PetscCall(vec_to_host(u));
+            memcpy(x->h, u->h, x->n * sizeof(double));
+            x->valid = LOC_HOST;
+            g_t_snes += wall() - t_snes0;
+            fflush(stdout);
+            return 0;
+        }
+    }
     /* Jacobian on every level by rediscretisation: the user's callback on the coarsened DMDAs (PCSetUp_MG) */
     const double t_jac0 = wall();
     int nlev = 1;
@@ -1236,7 +1423,7 @@ PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
             char msg[640];
             snprintf(msg, sizeof msg,
                      "Jacobian on level %d is not the constant-coefficient Dirichlet stencil the device Mat type "
-                     "\"stencilcuda\" represents (%s; %lld of %zu rows set); the assembled AIJ device path is not built yet",
+                     "\"stencilcuda\" represents (%s; %lld of %zu rows set); pass -mat_type sellcuda for the assembled device path",
                      l, J->general ? J->why : "incomplete", J->rows_set, da_n(&cd));
             MatDestroy(&J);
             SHIM_ERR(56, msg);

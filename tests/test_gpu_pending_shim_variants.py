@@ -21,7 +21,7 @@ pytestmark = [pytest.mark.gpu_pending, pytest.mark.skipif(not torch.cuda.is_avai
 def drivers(tmp_path_factory):
     d = tmp_path_factory.mktemp("variants")
     out = {}
-    for name in ("snes_variants", "ts_variants"):
+    for name in ("snes_variants", "ts_variants", "ksponly_varcoef"):
         exe = str(d / name)
         subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-O2", "-I", os.path.join(ROOT, "include"),
                                os.path.join(ROOT, "tests", "shim_cases", name + ".c"), "-o", exe, "-L", LIB, "-lpetsc_p4b200",
@@ -59,3 +59,18 @@ def test_ts_routes(drivers):
     assert abs(norm(c) - 1.4210174635e+01) <= 1e-8 * 14.0
     p = subprocess.run([drivers["ts_variants"]] + ("-variant 1 -da_refine 2" + MG).split(), capture_output=True, text=True)
     assert p.returncode == 56 and "pass -pc_type none" in p.stderr
+
+
+def test_assembled_mat_type(drivers):
+    """-mat_type sellcuda: the Jacobian callback's values as inserted -> CSR -> SELL-32 on the device, KSPCG over p4b_sell_spmv.
+    (1) the unchanged fish.c gives the structured type's iteration counts and report; (2) a variable-coefficient problem the
+    structured type refuses is solved, with the sums an independent NumPy solve gives (tests/test_shim_fish_cpu.py)."""
+    fishexe = os.path.join(ROOT, "p4pdes_b200", "bin", "fish")
+    if os.path.exists(fishexe):
+        common = "-fsh_dim 3 -fsh_problem manupoly -da_refine 3 -ksp_rtol 1.0e-12 -pc_type none -ksp_converged_reason -snes_monitor_short"
+        assert run(fishexe, common) == run(fishexe, common + " -mat_type sellcuda")
+    p = subprocess.run([drivers["ksponly_varcoef"]] + "-da_refine 3 -pc_type none".split(), capture_output=True, text=True)
+    assert p.returncode == 56 and "-mat_type sellcuda" in p.stderr
+    lines = run(drivers["ksponly_varcoef"], "-da_refine 3 -pc_type none -ksp_rtol 1e-13 -mat_type sellcuda")
+    got = lines[-1].split()
+    assert abs(float(got[7]) - 8.938150776637e+02) <= 1e-8 * 893.8 and abs(float(got[9]) - 7.822558518301e-01) <= 1e-9

@@ -86,3 +86,66 @@ def test_goldens_with_fd_color_and_symmetry_report(exe, name, verbatim):
         tight, _ = fish(exe, g["options"] + " -pc_type none -ksp_rtol 1e-12")
         inf_t, inf_g = float(tight[3].split()[3].rstrip(",")), float(g["errinf"])
         assert abs(inf_t - inf_g) <= 0.15 * inf_g          # discretisation error; the golden adds its solver's 1e-5
+
+
+# ---- the assembled Mat type: -mat_type sellcuda (values kept as inserted -> CSR -> SELL-32 SpMV; KSPCG as a host loop) ----
+def test_assembled_type_gives_the_structured_type_s_answer(exe):
+    """The unchanged fish.c with -mat_type sellcuda: same iteration counts, same residual history (to 1e-10 relative),
+    same report as the matrix-free structured type (here both over the host stand-in: two independent CG loops)."""
+    for opts in ("-fsh_dim 3 -fsh_problem manupoly -da_refine 2 -ksp_rtol 1.0e-12 -fsh_cx 0.01 -fsh_cy 2 -fsh_cz 100 -pc_type none",
+                 "-fsh_dim 2 -da_refine 4 -pc_type jacobi", "-fsh_dim 1 -da_refine 5 -pc_type none -ksp_rtol 1e-10"):
+        common = opts + " -ksp_converged_reason -ksp_monitor -snes_monitor_short"
+        a, _ = fish(exe, common)
+        b, _ = fish(exe, common + " -mat_type sellcuda")
+        assert len(a) == len(b) and any("KSP Residual norm" in l for l in a)
+        for la, lb in zip(a, b):
+            if "KSP Residual norm" in la:            # 13 printed digits: the two loops round differently in the last one
+                assert la.split()[0] == lb.split()[0] and abs(float(la.split()[-1]) - float(lb.split()[-1])) <= 1e-10 * float(la.split()[-1])
+            else:
+                assert la == lb
+    _, err = fish(exe, "-fsh_dim 2 -da_refine 3 -pc_type mg -mg_levels_pc_type jacobi -mat_type sellcuda", expect_rc=56)
+    assert "-mat_type stencilcuda" in err
+    _, err = fish(exe, "-fsh_dim 2 -da_refine 3 -pc_type none -mat_type dense", expect_rc=86)
+    assert "registered: stencilcuda, sellcuda" in err
+
+
+def test_variable_coefficients_need_and_get_the_assembled_type(exe, tmp_path):
+    """tests/shim_cases/ksponly_varcoef.c: -div(a grad u) + c u = f with a varying: the structured type refuses the Jacobian
+    callback's values and names the way out; the assembled type solves, and the answer is NumPy's for the same discretisation."""
+    import numpy as np
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    obj, out = str(tmp_path / "vc.o"), str(tmp_path / "vc")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-c",
+                           os.path.join(ROOT, "tests", "shim_cases", "ksponly_varcoef.c"), "-o", obj])
+    o = os.path.join(ROOT, "oracle", "_ref", "obj")
+    subprocess.check_call(["g++", obj, os.path.join(o, "petscshim.o"), os.path.join(o, "p4b_standin.o"), "-o", out, "-lm"])
+    _, err = fish(out, "-da_refine 3 -pc_type none", expect_rc=56)
+    assert "diagonal is not constant" in err and "-mat_type sellcuda" in err
+    lines, _ = fish(out, "-da_refine 3 -pc_type none -ksp_rtol 1e-13 -mat_type sellcuda -ksp_converged_reason")
+    m = 33
+    h = 1.0 / (m - 1)
+    coef = lambda x, y: 1.0 + 0.5 * np.sin(3.0 * x) * np.cos(2.0 * y)
+    g = lambda x, y: np.sin(x) + y * y
+    idx = lambda i, j: j * m + i
+    A = sp.lil_matrix((m * m, m * m))
+    b = np.zeros(m * m)
+    for j in range(m):
+        for i in range(m):
+            x, y, r = i * h, j * h, idx(i, j)
+            if i in (0, m - 1) or j in (0, m - 1):
+                A[r, r], b[r] = 1.0, g(x, y)
+                continue
+            nb = [(i + 1, j, coef(x + 0.5 * h, y)), (i - 1, j, coef(x - 0.5 * h, y)), (i, j + 1, coef(x, y + 0.5 * h)),
+                  (i, j - 1, coef(x, y - 0.5 * h))]
+            A[r, r] = sum(a for _, _, a in nb) + h * h * 2.0
+            b[r] = h * h * (1.0 + x * y)
+            for ii, jj, a in nb:
+                if ii in (0, m - 1) or jj in (0, m - 1):
+                    b[r] += a * g(ii * h, jj * h)
+                else:
+                    A[r, idx(ii, jj)] = -a
+    u = spla.spsolve(A.tocsc(), b)
+    got = lines[-1].split()
+    assert lines[-1].startswith("done on 33 x 33 grid: sum ")
+    assert abs(float(got[7]) - u.sum()) <= 1e-9 * abs(u.sum()) and abs(float(got[9]) - u[idx(m // 2, m // 2)]) <= 1e-10
