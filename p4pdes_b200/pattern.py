@@ -160,6 +160,8 @@ class StageOperator:
                     cp1 = 2.0 * mu * ck - cm1
                     L.omega.append(omegaprod * ck / cp1)
                     cm1, ck = ck, cp1
+        if opt.pc_type != "mg":                                    # unpreconditioned: no base-grid solve to set up
+            return
         C = self.levels[-1]
         if C.n > 2048:
             raise ValueError("base grid of the hierarchy has %d unknowns: use a coarser -da_grid_x/_y" % C.n)
@@ -296,8 +298,6 @@ def pattern_main(argv, ops, echo=False, native=False) -> PatternReport:
         rep = _pattern_native(opt, ops, out)
         rep.lines = lines
         return rep
-    if opt.ts_type == "bdf":
-        raise ValueError("-ts_type bdf is provided by the native host (csrc/ts_solver.hpp): pass native=True")
 
     mx, my = opt.grid_x * 2 ** opt.refine, opt.grid_y * 2 ** opt.refine     # periodic: -da_refine doubles
     if mx != my:
@@ -311,6 +311,8 @@ def pattern_main(argv, ops, echo=False, native=False) -> PatternReport:
     levels = [Level(ops, s, opt) for s in sizes]
     if opt.ts_type == "arkimex":
         return _arkimex(ops, opt, levels, m, out, lines)
+    if opt.ts_type == "bdf":
+        return _bdf(ops, opt, levels, m, out, lines)
     A = StageOperator(ops, levels, opt)
     L0 = levels[0]
     n = L0.n
@@ -401,6 +403,176 @@ def pattern_main(argv, ops, echo=False, native=False) -> PatternReport:
     if opt.log_view:
         out("TSSolve %.6f s" % seconds)
     return PatternReport(m=m, steps=steps, Y=Y, seconds=seconds, lines=lines)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# -ts_type bdf: [PETSc] TSBDF, order 2 (the statement of csrc/ts_solver.hpp and oracle/pattern_solver_oracle.py:pattern_bdf):
+# backward-Euler half-step restart, stage derivative from the Lagrange basis over the history, extrapolated initial guess,
+# LTE from the next-higher difference into TSAdaptBasic, MATCHSTEP.  c/ch5/output/pattern.test5 pins the restart step.
+# ---------------------------------------------------------------------------------------------------------
+def _lagrange_vals(t, T):
+    v = [1.0] * len(T)
+    for k in range(len(T)):
+        for j in range(len(T)):
+            if j != k:
+                v[k] *= (t - T[j]) / (T[k] - T[j])
+    return v
+
+
+def _lagrange_ders(t, T):
+    n = len(T)
+    d = [0.0] * n
+    for k in range(n):
+        for j in range(n):
+            if j == k:
+                continue
+            p = 1.0 / (T[k] - T[j])
+            for l in range(n):
+                if l not in (k, j):
+                    p *= (t - T[l]) / (T[k] - T[l])
+            d[k] += p
+    return d
+
+
+def _bdf(ops, opt: PatternOptions, levels, m, out, lines, order=2) -> PatternReport:
+    A = StageOperator(ops, levels, opt)
+    n = levels[0].n
+    Y = levels[0].Y                                  # the stage operator linearises about this vector
+    Yacc, R, Ydot, G, V0, lte = (ops.empty(n) for _ in range(6))
+    y, Jy, w, gnew = (ops.empty(n) for _ in range(4))
+    gwork = [ops.empty(n) for _ in range(opt.gmres_restart + 1)]
+    tm, wk = [0.0] * 8, [ops.empty(n) for _ in range(8)]
+    st = dict(k=0, n=0)
+    ops.pattern_initial_state(m, m, opt.L, Yacc)
+    t0 = time.perf_counter()
+    tmax = opt.ts_max_time
+    t, k, h, steps, rejected = 0.0, 0, min(opt.ts_dt, tmax), [], 0
+
+    def advance(tt, X):                              # TSBDF_Advance
+        tail = wk[7]
+        for i in range(7, 1, -1):
+            tm[i], wk[i] = tm[i - 1], wk[i - 1]
+        st["n"] = min(st["n"] + 1, 7)
+        tm[1], wk[1] = tt, tail
+        ops.copy(X, tail)
+
+    def stage(X):                                    # TSBDF_PreSolve + SNESSolve_NEWTONLS on X (in place)
+        nn = max(st["k"], 1) + 1
+        a = _lagrange_ders(tm[0], tm[:nn])
+        ops.set(0.0, V0)
+        for i in range(1, nn):
+            ops.axpy(a[i], wk[i], V0)
+        shift = a[0]
+
+        def F(W, f):
+            ops.axpby(shift, W, 1.0, V0, Ydot)
+            ops.pattern_ifunction(m, m, opt.L, opt.Du, opt.Dv, W, Ydot, f)
+            ops.pattern_rhsfunction(m, m, opt.phi, opt.kappa, W, G)
+            ops.axpy(-1.0, G, f)
+
+        F(X, R)
+        fnorm = ops.norm2(R)
+        res = SNESResult(fnorms=[fnorm])
+        ttol = opt.snes_rtol * fnorm
+        if fnorm < opt.snes_atol:
+            res.reason = "CONVERGED_FNORM_ABS"
+        while not res.reason:
+            if res.its >= opt.snes_max_it:
+                res.reason = "DIVERGED_MAX_IT"
+                break
+            ops.copy(X, Y)
+            A.setup(shift)
+            kr = gmres(ops, A.mult, R, y, A.precond, opt.ksp_rtol, restart=opt.gmres_restart, max_it=opt.ksp_max_it,
+                       work=gwork)
+            res.ksp_its.append(kr.its)
+            if opt.ksp_converged_reason:
+                out("      Linear solve %s due to %s iterations %d" % ("converged" if kr.reason.startswith("CONV")
+                                                                       else "did not converge", kr.reason, kr.its))
+            A.mult(y, Jy)
+            gnorm, lam = linesearch_bt(ops, F, X, R, fnorm, y, Jy, w, gnew)
+            ops.axpby(1.0, w, -1.0, X, y)
+            snorm, xnorm = ops.norm2(y), ops.norm2(w)
+            ops.copy(w, X)
+            ops.copy(gnew, R)
+            fnorm = gnorm
+            res.its += 1
+            res.fnorms.append(fnorm)
+            if not math.isfinite(fnorm):
+                res.reason = "DIVERGED_FNORM_NAN"
+            elif fnorm < opt.snes_atol:
+                res.reason = "CONVERGED_FNORM_ABS"
+            elif fnorm <= ttol:
+                res.reason = "CONVERGED_FNORM_RELATIVE"
+            elif snorm < opt.snes_stol * xnorm:
+                res.reason = "CONVERGED_SNORM_RELATIVE"
+        if opt.snes_converged_reason:
+            out("    Nonlinear solve %s due to %s iterations %d" % ("converged" if res.reason.startswith("CONV")
+                                                                    else "did not converge", res.reason, res.its))
+        if not res.reason.startswith("CONV"):
+            raise RuntimeError("TSSolve: nonlinear solve failed at step %d (%s)" % (k, res.reason))
+        return res
+
+    restart = True
+    hnext = h
+    while t < tmax - 1e-12 * max(1.0, abs(tmax)) and k < opt.ts_max_steps:
+        if opt.ts_monitor:
+            out("%d TS dt %s time %s" % (k, fmt_g(h), fmt_g(t)))
+        if not restart:
+            st["k"] = min(st["k"] + 1, order)
+            advance(t, Yacc)
+        accept, newton = True, []
+        while True:
+            if restart:                              # TSBDF_Restart
+                st["k"], st["n"] = 1, 0
+                advance(t, Yacc)
+                tm[0] = t + h / 2.0
+                ops.copy(wk[1], wk[0])
+                newton.append(stage(wk[0]))
+                st["k"] = min(2, order)
+                st["n"] += 1
+                ops.copy(wk[0], wk[2])
+                tm[2] = tm[0]
+            tm[0] = t + h
+            ne = min(st["k"] - (0 if accept else 1) + 1, st["n"])                      # TSBDF_Extrapolate
+            c = _lagrange_vals(tm[0], tm[1:1 + ne])
+            ops.set(0.0, wk[0])
+            for i in range(ne):
+                ops.axpy(c[i], wk[1 + i], wk[0])
+            newton.append(stage(wk[0]))
+            kl = min(st["k"], st["n"] - 1)                                             # TSBDF_VecLTE
+            a = _lagrange_ders(tm[0], tm[:kl + 1]) + [0.0]
+            b = _lagrange_ders(tm[0], tm[:kl + 2])
+            ops.copy(wk[0], lte)
+            for i in range(kl + 2):
+                ops.axpy((a[i] - b[i]) / a[0], wk[i], lte)
+            enorm = math.sqrt(ops.wrms2(wk[0], lte, opt.ts_atol, opt.ts_rtol) / n)
+            ok, hnext = adapt_basic(h, enorm, accept, order=kl + 1)
+            if ok:
+                break
+            accept = False
+            rejected += 1
+            h = hnext
+        ops.copy(wk[0], Yacc)
+        t += h
+        steps.append((t, h, newton))
+        h = match_step(t, hnext, tmax)
+        restart = False
+        k += 1
+    if opt.ts_monitor:
+        out("%d TS dt %s time %s" % (k, fmt_g(h), fmt_g(t)))
+    ops.copy(Yacc, Y)
+    ops.sync()
+    seconds = time.perf_counter() - t0
+    if opt.call_back_report:                                                           # pattern.c:127-135
+        out("CALL-BACK REPORT")
+        out("  solver type: bdf")
+        out("  IFunction:   1  | IJacobian:   1")
+        out("  RHSFunction: 1  | RHSJacobian: %d" % (0 if opt.no_rhsjacobian else 1))
+    if opt.log_view:
+        out("TSSolve %.6f s (%d steps, %d rejected)" % (seconds, k, rejected))
+    rep = PatternReport(m=m, steps=steps, Y=Y, seconds=seconds, lines=lines)
+    rep.rejected = rejected
+    return rep
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -92,3 +92,14 @@ def test_c_example_hosts_print_the_goldens():
     lines = out.stdout.rstrip("\n").split("\n")
     assert lines[0] == "  0 SNES Function norm 1.08276"                                                  # minimal.test1:1
     assert lines[-1] == "done on 5 x 5 grid and problem catenoid:  error |u-uexact|_inf = 1.10603e-04"  # :8
+
+
+def test_python_host_bdf_on_device(ctx):
+    """-ts_type bdf through the Python host (p4pdes_b200/pattern.py:_bdf): pattern.test5 and the native host's steps."""
+    r = pp.pattern_main(TEST5 + " -pc_type mg", ctx)
+    assert len(r.lines) == len(GOLDEN_TEST5)
+    np.testing.assert_allclose(_ts_numbers(r.lines), _ts_numbers(GOLDEN_TEST5), rtol=3e-6)
+    assert [l for l in r.lines if " TS " not in l] == [l for l in GOLDEN_TEST5 if " TS " not in l]
+    argv = "-da_grid_x 4 -da_grid_y 4 -da_refine 3 -ts_type bdf -ts_monitor -ts_max_time 60 -pc_type mg"
+    a, b = pp.pattern_main(argv, ctx), pp.pattern_main(argv, ctx, native=True)
+    np.testing.assert_allclose(_ts_numbers(a.lines), _ts_numbers(b.lines), rtol=1e-6)

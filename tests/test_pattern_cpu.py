@@ -57,7 +57,6 @@ def test_driver_matches_oracle(argv, okw):
 
 @pytest.mark.parametrize("argv,msg", [
     ("-da_refine 2 -ts_type rk", "arkimex"),
-    ("-da_refine 2 -ts_type bdf -pc_type none", "native=True"),           # bdf lives in the native host only
     ("-ts_type beuler -pc_type ilu", "sequential"),
     ("-ts_type beuler -ptn_noisy_init 0.2", "not provided"),
     ("-ts_type beuler -da_grid_x 4 -da_grid_y 6", "requires mx == my"),   # pattern.c:89
@@ -232,3 +231,15 @@ def test_bdf_oracle_every_step():
     a = po.pattern_bdf(grid=4, refine=2, dt=5.0, tmax=200.0)
     b = po.pattern_arkimex(grid=4, refine=2, dt=5.0, tmax=200.0)
     assert a.rejected > 0 and a.steps[-1][0] == 200.0 and np.abs(a.Y - b.Y).max() < 5e-2
+
+
+@pytest.mark.parametrize("pc", ["none", "mg"])
+def test_driver_prints_pattern_test5_verbatim(pc):
+    assert pp.pattern_main(TEST5 + " -pc_type " + pc, FakeOps()).lines == GOLDEN_TEST5
+
+
+def test_driver_bdf_matches_the_oracle_on_an_adaptive_run():
+    r = pp.pattern_main("-da_grid_x 4 -da_grid_y 4 -da_refine 2 -ts_type bdf -ts_monitor -pc_type none -ksp_rtol 1e-10", FakeOps())
+    o = po.pattern_bdf(grid=4, refine=2, dt=5.0, tmax=200.0)
+    assert [l for l in r.lines if " TS dt " in l] == [l for l in o.lines if " TS dt " in l]
+    assert r.rejected == o.rejected == 5 and np.abs(r.Y.a.reshape(o.Y.shape) - o.Y).max() <= 1e-9
