@@ -127,6 +127,9 @@ int p4b_device_count(int *n);
  * measurement-only keys: "force_mg" 1|2 (run the multi-GPU kernel variants on ONE GPU: 1 = no neighbours, 2 = scratch
  * memory on this device stands in for both neighbours) and "port_opts" (bit 0: natural chunk order and march
  * direction, bit 1: signal at the end of the boundary CTAs' work) -- the A/B switches behind DESIGN.md section 5;
+ * "gmres_cgs" 0|1 (the GMRES of p4b_minimal_solve / p4b_snes2d_solve / p4b_pattern_solve / p4b_ts2d_solve): 0 (default) =
+ * modified Gram-Schmidt, one dot and one read-back per basis vector; 1 = classical Gram-Schmidt ([PETSc]'s default
+ * orthogonalisation), the dots of a step through p4b_vec_mdot with one read-back -- same iterates up to rounding;
  * "recognise_residual" 0|1 (p4b_snes2d_solve): 1 (default) = probe the caller's residual callback and keep the residual on
  * the device when it is the model the library has as a kernel, 0 = evaluate the callback on the host every time */
 int p4b_tune(const char *key, long value);
@@ -172,6 +175,8 @@ int p4b_vec_norm2(p4b_ctx *ctx, size_t n, const double *x, double *result_host);
 int p4b_vec_wrms2(p4b_ctx *ctx, size_t n, const double *x, const double *y, double atol, double rtol,
                   double *result_host);
 int p4b_vec_norminf(p4b_ctx *ctx, size_t n, const double *x, double *result_host);
+/* k dot products (X[i], y), i < k <= 64, with one read-back ([PETSc] VecMDot): X is a HOST array of k device pointers */
+int p4b_vec_mdot(p4b_ctx *ctx, size_t n, int k, const double *const *X, const double *y, double *results_host);
 int p4b_vec_axpy(p4b_ctx *ctx, size_t n, double a, const double *x, double *y);      /* y += a x */
 int p4b_vec_aypx(p4b_ctx *ctx, size_t n, double a, const double *x, double *y);      /* y = x + a y */
 int p4b_vec_set(p4b_ctx *ctx, size_t n, double a, double *y);

@@ -27,6 +27,9 @@ struct HostOps {
     // [PETSc] Vec operations
     double dot(size_t n, const double *x, const double *y) { double s = 0; for (size_t i = 0; i < n; i++) s += x[i] * y[i]; return s; }
     double norm2(size_t n, const double *x) { return sqrt(dot(n, x, x)); }
+    bool cgs = false;                                           // -gmres_cgs of the harness (p4b_tune("gmres_cgs") in the library)
+    bool gmres_cgs() const { return cgs; }
+    void mdot(size_t n, int k, const double *const *X, const double *y, double *res) { for (int i = 0; i < k; i++) res[i] = dot(n, X[i], y); }
     double norminf(size_t n, const double *x) { double m = 0; for (size_t i = 0; i < n; i++) m = std::max(m, fabs(x[i])); return m; }
     void axpy(size_t n, double a, const double *x, double *y) { for (size_t i = 0; i < n; i++) y[i] += a * x[i]; }
     void aypx(size_t n, double a, const double *x, double *y) { for (size_t i = 0; i < n; i++) y[i] = x[i] + a * y[i]; }

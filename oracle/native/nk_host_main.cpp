@@ -22,6 +22,7 @@ static int pattern_main(int argc, char **argv) {
     using namespace p4b::nk;
     PatternOpts o;
     default_opts(&o);
+    bool cgs = false;
     for (int i = 2; i < argc; i++) {
         const std::string a = argv[i];
         auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
@@ -34,6 +35,7 @@ static int pattern_main(int argc, char **argv) {
         else if (a == "-pc_type") o.pc_type = std::string(next()) == "mg" ? PC_MG : PC_NONE;
         else if (a == "-snes_rtol") o.snes_rtol = atof(next());
         else if (a == "-ksp_rtol") o.ksp_rtol = atof(next());
+        else if (a == "-gmres_cgs") cgs = true;
         else if (a == "-p4b_mg_rscale") o.mg_rscale = atof(next());
         else if (a == "-ptn_no_rhsjacobian") o.no_rhsjacobian = 1;
         else if (a == "-ptn_call_back_report") o.call_back_report = 1;
@@ -43,6 +45,7 @@ static int pattern_main(int argc, char **argv) {
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     HostOps ops;
+    ops.cgs = cgs;
     PatternResult R;
     double *Y = nullptr;
     Printer pr{print_line, nullptr};
@@ -75,6 +78,7 @@ int main(int argc, char **argv) {
     MinimalOpts o;
     default_opts(&o);
     const char *cb_lib = nullptr;
+    bool cgs = false;
     for (int i = 1; i < argc; i++) {
         if (std::string(argv[i]) == "-callback" && i + 1 < argc) { cb_lib = argv[i + 1]; for (int k = i; k + 2 < argc; k++) argv[k] = argv[k + 2]; argc -= 2; break; }
     }
@@ -94,6 +98,7 @@ int main(int argc, char **argv) {
         else if (a == "-pc_mg_levels") o.mg_levels = atoi(next());
         else if (a == "-snes_fd_color") { }
         else if (a == "-snes_mf_operator") o.mf_operator = 1;
+        else if (a == "-gmres_cgs") cgs = true;
         else if (a == "-monitor") { o.snes_monitor = 2; o.snes_converged_reason = 1; o.ksp_converged_reason = 1; }
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
@@ -113,6 +118,7 @@ int main(int argc, char **argv) {
         tmp.minimal_sample(mx, my, o.problem, o.tent_H, o.catenoid_c, g.data());
         tmp.initial_state2d(mx, my, g.data(), u0.data());
         HostCallbackOps cops;
+        cops.cgs = cgs;
         cops.fn = ref_residual;
         cops.user = &ru;
         const int rc = minimal_solve(&cops, o, pr, &u, &R, u0.data(), false);
@@ -134,6 +140,7 @@ int main(int argc, char **argv) {
         return 0;
     }
     HostOps ops;
+    ops.cgs = cgs;
     const int rc = minimal_solve(&ops, o, pr, &u, &R);
     if (rc) { fprintf(stderr, "minimal_solve failed: %d\n", rc); return 1; }
     double sum = 0.0, sum2 = 0.0;

@@ -31,7 +31,7 @@ static int fail(int code, const char *msg) {
 }
 
 struct p4b_ctx { int unused; };
-static int g_route = 0, g_recognise = 1;
+static int g_route = 0, g_recognise = 1, g_cgs = 0;
 static long long g_callbacks = 0;
 struct p4b_mg { p4b_grid g; double diag, c[3]; };
 struct p4b_sell { int n; std::vector<int> rp, ci; std::vector<double> v; };
@@ -42,6 +42,7 @@ const char *p4b_last_error(void) { return g_err; }
 int p4b_snes2d_last_route(void) { return g_route; }
 int p4b_tune(const char *key, long value) {
     if (!strcmp(key, "recognise_residual")) { g_recognise = (int)value; return 0; }
+    if (!strcmp(key, "gmres_cgs")) { g_cgs = (int)value; return 0; }
     return fail(62, "stand-in: unknown tuning key");
 }
 long long p4b_launch_count(void) { return 0; }
@@ -78,6 +79,7 @@ int p4b_snes2d_solve_monitored(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_res
     g_route = 0;
     g_callbacks = 0;
     HostOps base;
+    base.cgs = g_cgs != 0;
     nk::ProbedModel model;
     auto resid = [&](int mx, int my, const double *uh, double *Fh) { g_callbacks++; return residual(user, mx, my, uh, Fh); };
     if (g_recognise && nk::probe_minimal_model(&base, resid, o, &model)) {            // as nk_device.cu does
@@ -100,6 +102,7 @@ int p4b_snes2d_solve_monitored(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_res
         if (u) ops.release(u);
     } else {
         HostCallbackOps ops;
+        ops.cgs = g_cgs != 0;
         ops.fn = residual;
         ops.mon = monitor;
         ops.user = user;
@@ -158,6 +161,7 @@ int p4b_pattern_solve_from(p4b_ctx *c, const p4b_pattern_opts *opts, const doubl
     if ((o.grid_x << o.refine) != (o.grid_y << o.refine)) return fail(1, "pattern.c requires mx == my");
     if (o.ts_type < nk::TS_ARKIMEX || o.ts_type > nk::TS_BDF) return fail(62, "ts_type: arkimex (0), beuler (1), cn (2), bdf (3)");
     HostOps ops;
+    ops.cgs = g_cgs != 0;
     nk::Printer pr{line, line_ctx};
     double *Y = nullptr;
     nk::PatternResult &R = *reinterpret_cast<nk::PatternResult *>(result);
@@ -188,6 +192,7 @@ int p4b_ts2d_solve(p4b_ctx *c, const p4b_pattern_opts *opts, p4b_ifunction2d_fn 
     const size_t n = (size_t)2 * m * m;
     if (Y_capacity < n) return fail(63, "Y is too small for the grid");
     HostCallbackPatternOps ops;
+    ops.cgs = g_cgs != 0;
     ops.ifn = ifunction;
     ops.gfn = rhsfunction;
     ops.user = user;

@@ -111,6 +111,7 @@ struct p4b_ctx {
     Reducer red;
     double *d_scal = nullptr;      // 16 device doubles: CG scalars
     double *h_scal = nullptr;      // 16 pinned host doubles
+    double *d_mdot = nullptr, *h_mdot = nullptr;      // 64 doubles each, on first use (p4b_vec_mdot)
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -861,7 +862,7 @@ static int plan_levels(const p4b_grid *g, const p4b_mg_opts &o, int P, LevelPlan
 
 namespace p4b {
 cudaStream_t ctx_stream(p4b_ctx *c) { return c->stream; }     // for the other translation units (nk_device.cu)
-extern long long g_recognise_residual;                        // defined in nk_device.cu
+extern long long g_recognise_residual, g_gmres_cgs;           // defined in nk_device.cu
 }  // namespace p4b
 
 extern "C" {
@@ -879,6 +880,7 @@ int p4b_tune(const char *key, long value) {
     if (std::string(key) == "port_opts") { g_port_opts = value; return 0; }
     if (std::string(key) == "force_mg") { g_force_mg = value; return 0; }
     if (std::string(key) == "recognise_residual") { g_recognise_residual = value; return 0; }
+    if (std::string(key) == "gmres_cgs") { g_gmres_cgs = value; return 0; }
     return fail(62, "unknown tuning key %s", key);
 }
 
@@ -929,6 +931,8 @@ int p4b_ctx_destroy(p4b_ctx *c) {
     cudaFree(c->red.ticket);
     cudaFree(c->d_scal);
     cudaFreeHost(c->h_scal);
+    if (c->d_mdot) cudaFree(c->d_mdot);
+    if (c->h_mdot) cudaFreeHost(c->h_mdot);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1121,6 +1125,22 @@ int p4b_vec_dot(p4b_ctx *c, size_t n, const double *x, const double *y, double *
     P4B_CHECK(launch_dotn(c->stream, (long long)n, x, y, c->d_scal + 8, c->red));
     P4B_CHECK(ctx_allreduce(c, c->d_scal + 8, 1));
     return fetch_scal(c, c->d_scal + 8, 1, res);
+}
+// k dot products (X[i], y) with ONE read-back: the launches of the single dot, one after the other on the stream, each
+// into its own slot ([PETSc] VecMDot; the orthogonalisation of one GMRES step with classical Gram-Schmidt)
+int p4b_vec_mdot(p4b_ctx *c, size_t n, int k, const double *const *X, const double *y, double *res) {
+    if (k <= 0) return 0;
+    if (k > 64) return fail(62, "p4b_vec_mdot: at most 64 vectors");
+    if (!c->d_mdot) {
+        P4B_CUDA(cudaMalloc(&c->d_mdot, sizeof(double) * 64));
+        P4B_CUDA(cudaMallocHost(&c->h_mdot, sizeof(double) * 64));
+    }
+    for (int i = 0; i < k; i++) P4B_CHECK(launch_dotn(c->stream, (long long)n, X[i], y, c->d_mdot + i, c->red));
+    P4B_CHECK(ctx_allreduce(c, c->d_mdot, k));
+    P4B_CUDA(cudaMemcpyAsync(c->h_mdot, c->d_mdot, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
+    P4B_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < k; i++) res[i] = c->h_mdot[i];
+    return 0;
 }
 int p4b_vec_wrms2(p4b_ctx *c, size_t n, const double *x, const double *y, double atol, double rtol, double *res) {
     P4B_CHECK(launch_wrms(c->stream, (long long)n, x, y, atol, rtol, c->d_scal + 8, c->red));

@@ -39,6 +39,8 @@ struct DeviceOps {
         cu(cudaStreamSynchronize(st));          // the host buffer may go away right after
     }
     double dot(size_t n, const double *x, const double *y) { double r = NAN; chk(p4b_vec_dot(c, n, x, y, &r)); return r; }
+    bool gmres_cgs() const;
+    void mdot(size_t n, int k, const double *const *X, const double *y, double *res) { chk(p4b_vec_mdot(c, n, k, X, y, res)); }
     double norm2(size_t n, const double *x) { double r = NAN; chk(p4b_vec_norm2(c, n, x, &r)); return r; }
     double norminf(size_t n, const double *x) { double r = NAN; chk(p4b_vec_norminf(c, n, x, &r)); return r; }
     void axpy(size_t n, double a, const double *x, double *y) { chk(p4b_vec_axpy(c, n, a, x, y)); }
@@ -103,6 +105,9 @@ struct DeviceOps {
     void pattern_inject(int Mx, int My, const double *yf, double *yc) { chk(p4b_pattern_inject(c, Mx, My, yf, yc)); }
     void set_linearisation(const double *) {}             // the kernels take the state as an argument
 };
+
+extern long long g_gmres_cgs;
+inline bool DeviceOps::gmres_cgs() const { return g_gmres_cgs != 0; }
 
 // The same operations with the RESIDUAL supplied by the caller as a host callback -- the FormFunctionLocal contract of
 // the reference's drivers (c/ch7/minimal.c:210-282 is registered with DMDASNESSetFunctionLocal, :138-140): the iterate
@@ -265,6 +270,7 @@ extern "C" int p4b_snes2d_solve(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_re
 
 namespace p4b {
 long long g_recognise_residual = 1;     // p4b_tune("recognise_residual", 0): always evaluate the caller's residual on the host
+long long g_gmres_cgs = 0;              // p4b_tune("gmres_cgs", 1): classical Gram-Schmidt with the dots of a step batched
 }
 static int g_snes2d_route = 0;
 

@@ -327,9 +327,18 @@ KSPInfo gmres(Ops *ops, size_t n, Mult mult, const double *b, double *x, Prec pr
         while (k < restart && its < max_it) {
             mult(V[k], t);
             prec(t, w);
-            for (int i = 0; i <= k; i++) {                     // modified Gram-Schmidt
-                h(i, k) = ops->dot(n, w, V[i]);
-                ops->axpy(n, -h(i, k), V[i], w);
+            if (ops->gmres_cgs() && restart < 64) {            // classical Gram-Schmidt ([PETSc]'s default): h = V^T w in one
+                double hc[64];                                 // batch of dots (one read-back), then w -= V h
+                ops->mdot(n, k + 1, V.data(), w, hc);
+                for (int i = 0; i <= k; i++) {
+                    h(i, k) = hc[i];
+                    ops->axpy(n, -hc[i], V[i], w);
+                }
+            } else {
+                for (int i = 0; i <= k; i++) {                 // modified Gram-Schmidt
+                    h(i, k) = ops->dot(n, w, V[i]);
+                    ops->axpy(n, -h(i, k), V[i], w);
+                }
             }
             h(k + 1, k) = ops->norm2(n, w);
             if (h(k + 1, k) != 0.0) ops->axpby(n, 1.0 / h(k + 1, k), w, 0.0, nullptr, V[k + 1]);

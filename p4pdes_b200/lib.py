@@ -195,6 +195,7 @@ _SIGS = {
     "p4b_snes2d_solve_monitored": (C.c_int, [_P, C.POINTER(MinimalOpts), RESIDUAL2D_FN, MONITOR2D_FN, _P, _P, LINE_FN, _P, _P,
                                             C.c_size_t, C.POINTER(MinimalResult)]),
     "p4b_snes2d_last_route": (C.c_int, []),
+    "p4b_vec_mdot": (C.c_int, [_P, C.c_size_t, C.c_int, _P, _D, _P]),
     "p4b_pattern_default_opts": (C.c_int, [C.POINTER(PatternOpts)]),
     "p4b_pattern_solve": (C.c_int, [_P, C.POINTER(PatternOpts), LINE_FN, _P, _D, C.c_size_t, C.POINTER(PatternResult)]),
     "p4b_pattern_solve_from": (C.c_int, [_P, C.POINTER(PatternOpts), _D, LINE_FN, _P, _D, C.c_size_t,

@@ -1056,6 +1056,8 @@ static PetscErrorCode snes_solve_newtonls(SNES snes, Vec x) {
          * residual the library has as a kernel (p4b200.h, "Recognition") */
         const char *v = opt_value("-p4b_recognise_residual");
         P4B(p4b_tune("recognise_residual", v ? atol(v) : 1));
+        v = opt_value("-p4b_gmres_cgs");                 /* GMRES orthogonalisation: 0 modified (default), 1 classical, batched dots */
+        P4B(p4b_tune("gmres_cgs", v ? atol(v) : 0));
     }
     const double t0 = wall();
     PetscCall(vec_to_host(x));
@@ -1815,6 +1817,10 @@ static PetscErrorCode ts_solve(TS ts, Vec x, struct ts_work *W) {
                      "pass -mg_levels_pc_type jacobi");
     if (strcmp(ksp->type, KSPGMRES)) SHIM_ERR(56, "TSSolve: the stage solves are GMRES ([PETSc] default)");
     PetscCall(ensure_ctx());
+    {
+        const char *v = opt_value("-p4b_gmres_cgs");
+        P4B(p4b_tune("gmres_cgs", v ? atol(v) : 0));
+    }
     const double t_start = wall();
 
     const int m = dm->M[0];

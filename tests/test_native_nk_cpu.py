@@ -153,3 +153,16 @@ def test_native_bdf_matches_the_oracle_on_an_adaptive_run(exe):
         assert (d["nsteps"], d["rejected"]) == (len(o.steps), o.rejected) and o.rejected == 5
         want = float((o.Y[..., 0] + 3.0 * o.Y[..., 1]).sum())
         assert abs(d["sum"] - want) <= 1e-8 * abs(want)
+
+
+def test_classical_gram_schmidt_with_batched_dots_changes_nothing_visible(exe):
+    """p4b_tune("gmres_cgs", 1) / -gmres_cgs: [PETSc]'s default orthogonalisation (classical Gram-Schmidt, the dots of a step
+    as one VecMDot) instead of modified Gram-Schmidt.  Same iterates up to rounding: the goldens stay verbatim, the
+    Krylov totals equal."""
+    for argv, golden in ((TEST1, GOLDEN_TEST1), (TEST4, GOLDEN_TEST4), (TEST5 + " -pc_type mg", GOLDEN_TEST5)):
+        lines, d = run(exe, "-pattern", *argv.split(), "-gmres_cgs")
+        ref, d0 = run(exe, "-pattern", *argv.split())
+        assert lines == golden == ref and d["ksp_its_total"] == d0["ksp_its_total"]
+    a, da = run(exe, "-snes_fd_color", "-snes_grid_sequence", 3, "-pc_type", "mg", "-monitor")
+    b, db = run(exe, "-snes_fd_color", "-snes_grid_sequence", 3, "-pc_type", "mg", "-monitor", "-gmres_cgs")
+    assert a == b and [s["ksp_its"] for s in da["stages"]] == [s["ksp_its"] for s in db["stages"]]

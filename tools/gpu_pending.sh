@@ -26,6 +26,10 @@ C5="-da_grid_x 8 -da_grid_y 8 -da_refine 8 -ts_monitor -snes_converged_reason -p
 ( time timeout 600 ./p4pdes_b200/bin/pattern $C5 -ts_type beuler -ts_dt 5 -ts_max_time 25 ) > "$out/pattern_c5_beuler.log" 2>&1
 ( time timeout 600 ./p4pdes_b200/bin/pattern $C5 -ts_max_time 50 ) > "$out/pattern_c5_arkimex.log" 2>&1
 grep -h "SNESSolve\|residual\|real" "$out"/minimal_c4_*.log "$out"/pattern_c5_*.log | tee -a "$out/summary.txt"
+# 3b. GMRES orthogonalisation A/B on the same box: modified Gram-Schmidt (default) vs classical with batched dots
+( time timeout 600 ./p4pdes_b200/bin/minimal $C4 -p4b_gmres_cgs 1 ) > "$out/minimal_c4_cgs.log" 2>&1
+( time timeout 600 ./p4pdes_b200/bin/pattern $C5 -ts_type beuler -ts_dt 5 -ts_max_time 25 -p4b_gmres_cgs 1 ) > "$out/pattern_c5_beuler_cgs.log" 2>&1
+grep -h "SNESSolve\|real" "$out"/minimal_c4_cgs.log "$out"/pattern_c5_beuler_cgs.log | tee -a "$out/summary.txt"
 # 4. native hosts against the Python hosts (same kernels, no interpreter between them)
 python - <<'PY' 2>&1 | tee -a "$out/summary.txt"
 import time
