@@ -1218,9 +1218,9 @@ static PetscErrorCode ksponly_matrix_checks(SNES snes, p4b_mg *mg, Vec u, Vec F0
 
 /* KSPONLY with -mat_type sellcuda: the Jacobian callback's values are kept as inserted (any coefficients), converted to
  * CSR on the host and to SELL-32 on the device (p4b_sell_create); KSPCG runs here as a host loop over the library's
- * SpMV and Vec kernels ([PETSc] KSPSolve_CG, preconditioned norm).  Preconditioners: none, or jacobi when the
- * diagonal is constant (the library has no pointwise Vec product); PCMG needs the structured type (-mat_type stencilcuda):
- * its coarse operators are rediscretised stencils, not assembled matrices. */
+ * SpMV and Vec kernels ([PETSc] KSPSolve_CG, preconditioned norm).  Preconditioners: none, or jacobi (D^-1 as a
+ * second, diagonal SELL matrix); PCMG needs the structured type (-mat_type stencilcuda): its coarse operators are
+ * rediscretised stencils, not assembled matrices. */
 static int cmp_int(const void *a, const void *b) { return *(const int *)a - *(const int *)b; }
 static PetscErrorCode ksponly_solve_assembled(SNES snes, Vec u, Vec F, Vec Y, double fnorm0) {
     DM dm = snes->dm;
@@ -1247,7 +1247,7 @@ static PetscErrorCode ksponly_solve_assembled(SNES snes, Vec u, Vec F, Vec Y, do
     double *vals = (double *)malloc(sizeof(double) * n * W);
     if (!rowptr || !colind || !vals) SHIM_ERR(55, "out of host memory for the CSR copy");
     double dmin = 1e300, dmax = -1e300;
-    size_t nnz = 0;
+    size_t nnz = 0, ndiag = 0;
     for (size_t r = 0; r < n; r++) {
         rowptr[r] = (int)nnz;
         const int cnt = J->ccnt[r];
@@ -1260,7 +1260,7 @@ static PetscErrorCode ksponly_solve_assembled(SNES snes, Vec u, Vec F, Vec Y, do
                 if (J->ccol[r * W + q] == order[k]) val = J->cval[r * W + q];
             colind[nnz] = order[k];
             vals[nnz] = val;
-            if ((size_t)order[k] == r) { if (val < dmin) dmin = val; if (val > dmax) dmax = val; }
+            if ((size_t)order[k] == r) { ndiag++; if (val < dmin) dmin = val; if (val > dmax) dmax = val; }
             nnz++;
         }
     }
@@ -1268,14 +1268,24 @@ static PetscErrorCode ksponly_solve_assembled(SNES snes, Vec u, Vec F, Vec Y, do
     MatDestroy(&J);
     g_t_jac += wall() - t_jac0;
     const int jacobi = !strcmp(pc->type, PCJACOBI);
-    if (jacobi && !(dmax - dmin <= 1e-14 * fabs(dmax) && dmin > 0.0)) {
+    if (jacobi && !(ndiag == n && dmin * dmax > 0.0)) {
         free(rowptr); free(colind); free(vals);
-        SHIM_ERR(56, "-mat_type sellcuda -pc_type jacobi: provided for a constant positive diagonal (the library has no pointwise "
-                     "Vec product); use -pc_type none");
+        SHIM_ERR(71, "-pc_type jacobi: zero (or missing) diagonal entry");
     }
-    const double dinv = jacobi ? 1.0 / dmax : 1.0;
-    p4b_sell *A = NULL;
+    p4b_sell *A = NULL, *Dinv = NULL;
     int prc = p4b_sell_create(g_ctx, (int)n, rowptr, colind, vals, &A);
+    if (!prc && jacobi) {
+        /* [PETSc] PCApply_Jacobi z = D^-1 r as the SpMV of the diagonal matrix D^-1 (the library has no pointwise Vec product) */
+        for (size_t r = 0; r < n; r++) {
+            double d = 1.0;
+            for (int k = rowptr[r]; k < rowptr[r + 1]; k++)
+                if ((size_t)colind[k] == r) d = vals[k];
+            vals[r] = 1.0 / d;                      /* (vals[r] with r <= rowptr[r] is no longer needed: rows are non-empty) */
+        }
+        for (size_t r = 0; r <= n; r++) rowptr[r] = (int)r;
+        for (size_t r = 0; r < n; r++) colind[r] = (int)r;
+        prc = p4b_sell_create(g_ctx, (int)n, rowptr, colind, vals, &Dinv);
+    }
     free(rowptr); free(colind); free(vals);
     if (prc) return PetscShimError(PETSC_COMM_SELF, __LINE__, __func__, __FILE__, prc, p4b_last_error());
     /* [PETSc] KSPSolve_CG on A y = F0 from y = 0 */
@@ -1286,8 +1296,8 @@ static PetscErrorCode ksponly_solve_assembled(SNES snes, Vec u, Vec F, Vec Y, do
     const double t_ksp0 = wall();
     P4B(p4b_vec_aypx(g_ctx, n, 0.0, F->d, R->d));                    /* r = b */
     P4B(p4b_vec_aypx(g_ctx, n, -1.0, Y->d, Y->d));                   /* y = y - y = 0 */
-    P4B(p4b_vec_aypx(g_ctx, n, 0.0, R->d, Z->d));                    /* z = M^-1 r */
-    if (jacobi) P4B(p4b_vec_aypx(g_ctx, n, dinv - 1.0, Z->d, Z->d));
+    if (jacobi) P4B(p4b_sell_spmv(Dinv, R->d, Z->d));                /* z = M^-1 r */
+    else P4B(p4b_vec_aypx(g_ctx, n, 0.0, R->d, Z->d));
     P4B(p4b_vec_aypx(g_ctx, n, 0.0, Z->d, P->d));
     double beta = 0.0, dp = 0.0;
     P4B(p4b_vec_dot(g_ctx, n, Z->d, R->d, &beta));
@@ -1303,8 +1313,8 @@ static PetscErrorCode ksponly_solve_assembled(SNES snes, Vec u, Vec F, Vec Y, do
         const double a = beta / pw;
         P4B(p4b_vec_axpy(g_ctx, n, a, P->d, Y->d));
         P4B(p4b_vec_axpy(g_ctx, n, -a, Wv->d, R->d));
-        P4B(p4b_vec_aypx(g_ctx, n, 0.0, R->d, Z->d));
-        if (jacobi) P4B(p4b_vec_aypx(g_ctx, n, dinv - 1.0, Z->d, Z->d));
+        if (jacobi) P4B(p4b_sell_spmv(Dinv, R->d, Z->d));
+        else P4B(p4b_vec_aypx(g_ctx, n, 0.0, R->d, Z->d));
         P4B(p4b_vec_norm2(g_ctx, n, Z->d, &dp));
         its++;
         if (ksp->monitor_flag) printf("    %d KSP Residual norm %14.12e\n", its, dp);
@@ -1323,6 +1333,7 @@ static PetscErrorCode ksponly_solve_assembled(SNES snes, Vec u, Vec F, Vec Y, do
         else printf("    Linear solve did not converge due to %s iterations %d\n", reason_name(reason), its);
     }
     p4b_sell_destroy(A);
+    if (Dinv) p4b_sell_destroy(Dinv);
     vec_free(R); vec_free(Z); vec_free(P); vec_free(Wv);
     /* u = u0 - y, the post-solve norm, the reason line: as the structured path */
     PetscCall(VecAXPY(u, -1.0, Y));
