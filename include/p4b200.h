@@ -324,7 +324,7 @@ int p4b_minimal_default_opts(p4b_minimal_opts *o);
 int p4b_minimal_solve(p4b_ctx *ctx, const p4b_minimal_opts *opts, p4b_line_fn line, void *line_ctx, double *u_out,
                       size_t u_capacity, p4b_minimal_result *result);
 /* ---- the same Newton-Krylov-multigrid solve for ANY residual on a 2-D DMDA with the BOX stencil, supplied by the caller as
- * a host callback: the FormFunctionLocal contract (DMDASNESSetFunctionLocal, c/ch7/minimal.c:138-140).  The
+ * a host callback: the FormFunctionLocal contract (DMDASNESSetFunctionLocal, c/ch7/minimal.c:140-141).  The
  * callback is invoked on the host with the whole mx x my grid (one logical rank: xs = 0, xm = mx, ...), arrays in DMDA
  * natural ordering (a binding wraps DMDALocalInfo and a[j][i] pointer tables around them), on every grid of the
  * hierarchy and of the grid sequence; Jacobians by coloured finite differences of it; the algebra stays on the device.
@@ -334,7 +334,7 @@ typedef int (*p4b_residual2d_fn)(void *user, int mx, int my, const double *u_hos
 int p4b_snes2d_solve(p4b_ctx *ctx, const p4b_minimal_opts *opts, p4b_residual2d_fn residual, void *user,
                      const double *u0_host, p4b_line_fn line, void *line_ctx, double *u_out_host, size_t u_capacity,
                      p4b_minimal_result *result);
-/* the same with a caller's monitor ([PETSc] SNESMonitorSet, c/ch7/minimal.c:144-146 registers MSEMonitor :286-345): called
+/* the same with a caller's monitor ([PETSc] SNESMonitorSet, c/ch7/minimal.c:146-148 registers MSEMonitor :286-345): called
  * on the host before the first and after every Newton iteration of every grid-sequence stage, ahead of the -snes_monitor
  * line, with the current iterate on that stage's grid; tablevel = the stages still to come ([PETSc] PetscObjectGetTabLevel
  * of the SNES under -snes_grid_sequence).  A non-zero return aborts the solve (error 66).  monitor may be NULL. */
@@ -382,7 +382,7 @@ int p4b_pattern_default_opts(p4b_pattern_opts *o);
 int p4b_pattern_solve(p4b_ctx *ctx, const p4b_pattern_opts *opts, p4b_line_fn line, void *line_ctx, double *Y_out,
                       size_t Y_capacity, p4b_pattern_result *result);
 /* the same from the CALLER's initial state Y0 (device, 2*m*m doubles; Y_out may alias it): what TSSolve(ts, x) of the
- * PETSc-shaped shim binds (c/ch5/pattern.c:121-123).  Only the solver's own lines are reported (no banner, no call-back
+ * PETSc-shaped shim binds (c/ch5/pattern.c:123-125).  Only the solver's own lines are reported (no banner, no call-back
  * report: the caller prints those, pattern.c:94-96,127-135).  Y0 = NULL is p4b_pattern_solve. */
 int p4b_pattern_solve_from(p4b_ctx *ctx, const p4b_pattern_opts *opts, const double *Y0, p4b_line_fn line, void *line_ctx,
                            double *Y_out, size_t Y_capacity, p4b_pattern_result *result);

@@ -121,7 +121,7 @@ struct CallbackOps : DeviceOps {
     std::vector<double> hu, hF;
     CallbackOps(p4b_ctx *c_, cudaStream_t st_, p4b_residual2d_fn f, p4b_monitor2d_fn m, void *u)
         : DeviceOps{c_, st_}, fn(f), user(u), mon(m) {}
-    // [PETSc] SNESMonitorSet (c/ch7/minimal.c:144-146): the caller's monitor sees the current iterate on the host
+    // [PETSc] SNESMonitorSet (c/ch7/minimal.c:146-148): the caller's monitor sees the current iterate on the host
     void user_monitor(int mx, int my, int its, double fnorm, int tablevel, const double *u) {
         if (!mon || err) return;
         const size_t n = (size_t)mx * my;

@@ -958,7 +958,7 @@ static const char *reason_name(int r) {
 }
 
 /* ---- SNESNEWTONLS: the callback-contract solve of the C ABI (p4b_snes2d_solve_monitored) --------------------------
- * What c/ch7/minimal.c:134-162 sets up -- a 2-D DMDA, FormFunctionLocal registered with DMDASNESSetFunctionLocal,
+ * What c/ch7/minimal.c:130-161 sets up -- a 2-D DMDA, FormFunctionLocal registered with DMDASNESSetFunctionLocal,
  * optionally a monitor -- becomes one library call: Newton + bt line search, GMRES/CG, multigrid on finite-difference
  * coloured Jacobians of the user's residual, -snes_grid_sequence; vectors and algebra on the device, the user's
  * callbacks on the host, called as PETSc calls them (whole grid of one logical rank, a[j][i] views). */
@@ -1020,7 +1020,7 @@ static PetscErrorCode snes_solve_newtonls(SNES snes, Vec x) {
                      "fish.c is linear: -snes_type ksponly (fish.c:230-231)");
     if (!snes->fd_color && !snes->mf_operator)
         SHIM_ERR(56, "newtonls needs the Jacobian of the registered residual: pass -snes_fd_color or -snes_mf_operator "
-                     "(minimal.c:141-142: the Jacobian callback registered there is Poisson's, 'thus ONLY APPROXIMATE')");
+                     "(minimal.c:142-143: the Jacobian callback registered there is Poisson's, 'thus ONLY APPROXIMATE')");
     p4b_minimal_opts o;
     P4B(p4b_minimal_default_opts(&o));
     if (!strcmp(ksp->type, KSPGMRES)) o.ksp_type = 0;
@@ -1082,7 +1082,7 @@ static PetscErrorCode snes_solve_newtonls(SNES snes, Vec x) {
     snes->reason = R->stage[R->nstages - 1].reason;
     ksp->its = snes->its ? R->stage[R->nstages - 1].ksp_its[snes->its - 1] : 0;
     /* under -snes_grid_sequence the SNES ends up with the refined DM and a solution on it: the caller fetches both
-     * with SNESGetDM / SNESGetSolution (minimal.c:161-165) */
+     * with SNESGetDM / SNESGetSolution (minimal.c:163-165) */
     if (R->mx != dm->M[0] || R->my != dm->M[1]) {
         DM fine = (DM)malloc(sizeof *fine);
         *fine = *dm;

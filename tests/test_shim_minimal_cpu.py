@@ -65,7 +65,7 @@ def test_golden_test2_structure(exe):
 
 
 def test_golden_test3_monitor_lines(exe):
-    """-ms_monitor (SNESMonitorSet(MSEMonitor), minimal.c:144-146,286-345) under -snes_grid_sequence 2 -pc_type mg: the
+    """-ms_monitor (SNESMonitorSet(MSEMonitor), minimal.c:146-148,286-345) under -snes_grid_sequence 2 -pc_type mg: the
     golden ran -snes_mf_operator on 2 ranks; with -snes_fd_color the Newton path is the same to ~1e-7 in the printed
     areas, and every other character -- tab levels, iteration counts, the lines of the initial, interpolated and
     converged iterates, the final error -- is identical."""
