@@ -334,17 +334,17 @@ typedef int (*p4b_residual2d_fn)(void *user, int mx, int my, const double *u_hos
 int p4b_snes2d_solve(p4b_ctx *ctx, const p4b_minimal_opts *opts, p4b_residual2d_fn residual, void *user,
                      const double *u0_host, p4b_line_fn line, void *line_ctx, double *u_out_host, size_t u_capacity,
                      p4b_minimal_result *result);
-/* the same with a caller's monitor ([PETSc] SNESMonitorSet, c/ch7/minimal.c:146-148 registers MSEMonitor :286-345): called
- * on the host before the first and after every Newton iteration of every grid-sequence stage, ahead of the -snes_monitor
- * line, with the current iterate on that stage's grid; tablevel = the stages still to come ([PETSc] PetscObjectGetTabLevel
- * of the SNES under -snes_grid_sequence).  A non-zero return aborts the solve (error 66).  monitor may be NULL. */
 /* Recognition: before the solve the residual callback is probed on every grid the solve will touch (F(0) gives the
  * Dirichlet data, a generic iterate the exponent q, a second one the check; 2 evaluations per grid + 1).  If it IS
  * c/ch7/minimal.c:210-282 -- the unchanged minimal.c under the shim -- to rounding, the solve keeps the residual on the
  * device (minimal_function_kernel) and calls the callback no more; otherwise every evaluation is a host callback (nine per
  * level Jacobian).  p4b_snes2d_last_route(): 1 = device residual after recognition, 0 = host callbacks. */
-typedef int (*p4b_monitor2d_fn)(void *user, int mx, int my, int its, double fnorm, int tablevel, const double *u_host);
 int p4b_snes2d_last_route(void);
+/* the same with a caller's monitor ([PETSc] SNESMonitorSet, c/ch7/minimal.c:146-148 registers MSEMonitor :286-345): called
+ * on the host before the first and after every Newton iteration of every grid-sequence stage, ahead of the -snes_monitor
+ * line, with the current iterate on that stage's grid; tablevel = the stages still to come ([PETSc] PetscObjectGetTabLevel
+ * of the SNES under -snes_grid_sequence).  A non-zero return aborts the solve (error 66).  monitor may be NULL. */
+typedef int (*p4b_monitor2d_fn)(void *user, int mx, int my, int its, double fnorm, int tablevel, const double *u_host);
 int p4b_snes2d_solve_monitored(p4b_ctx *ctx, const p4b_minimal_opts *opts, p4b_residual2d_fn residual,
                                p4b_monitor2d_fn monitor, void *user, const double *u0_host, p4b_line_fn line, void *line_ctx,
                                double *u_out_host, size_t u_capacity, p4b_minimal_result *result);
