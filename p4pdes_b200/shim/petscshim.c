@@ -1154,7 +1154,7 @@ int MPI_Allreduce(const void *sendbuf, void *recvbuf, int count, MPI_Datatype da
  *                       callback, A v by the device MatMult; a disagreement is an error, not a silent substitution
  *   -mat_is_symmetric   (x, A y) = (y, A x) for two pseudo-random vectors to the tolerance, on the device; PETSc prints
  *                       its line once for the matrix DMCreateMatrix hands out and once per Jacobian assembly */
-static PetscErrorCode ksponly_matrix_checks(SNES snes, p4b_mg *mg, Vec u, Vec F0) {
+static PetscErrorCode ksponly_matrix_checks(SNES snes, p4b_mg *mg, p4b_sell *As, Vec u, Vec F0) {
     DM dm = snes->dm;
     Vec v = NULL, w = NULL, Av = NULL, Aw = NULL;
     PetscCall(vec_new(dm, &v));
@@ -1172,8 +1172,13 @@ static PetscErrorCode ksponly_matrix_checks(SNES snes, p4b_mg *mg, Vec u, Vec F0
     PetscCall(vec_to_dev(w));
     PetscCall(vec_to_dev(Av));
     PetscCall(vec_to_dev(Aw));
-    P4B(p4b_mg_matmult(mg, v->d, Av->d));
-    P4B(p4b_mg_matmult(mg, w->d, Aw->d));
+    if (As) {                                          /* the assembled type: the same checks on the SELL matrix */
+        P4B(p4b_sell_spmv(As, v->d, Av->d));
+        P4B(p4b_sell_spmv(As, w->d, Aw->d));
+    } else {
+        P4B(p4b_mg_matmult(mg, v->d, Av->d));
+        P4B(p4b_mg_matmult(mg, w->d, Aw->d));
+    }
     Av->valid = Aw->valid = LOC_DEV;
     if (snes->fd_color) {
         Vec up = NULL, Fp = NULL;
@@ -1288,6 +1293,7 @@ static PetscErrorCode ksponly_solve_assembled(SNES snes, Vec u, Vec F, Vec Y, do
     }
     free(rowptr); free(colind); free(vals);
     if (prc) return PetscShimError(PETSC_COMM_SELF, __LINE__, __func__, __FILE__, prc, p4b_last_error());
+    if (snes->fd_color || snes->sym_check) PetscCall(ksponly_matrix_checks(snes, NULL, A, u, F));
     /* [PETSc] KSPSolve_CG on A y = F0 from y = 0 */
     Vec R = NULL, Z = NULL, P = NULL, Wv = NULL;
     PetscCall(vec_new(dm, &R)); PetscCall(vec_new(dm, &Z)); PetscCall(vec_new(dm, &P)); PetscCall(vec_new(dm, &Wv));
@@ -1467,7 +1473,7 @@ PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
     p4b_mg *mg = NULL;
     P4B(p4b_mg_create_stencil(g_ctx, &g, &o, coef, nlev, &mg));
     const int pct = !strcmp(pc->type, PCMG) ? P4B_PC_MG : (!strcmp(pc->type, PCJACOBI) ? P4B_PC_JACOBI : P4B_PC_NONE);
-    if (snes->fd_color || snes->sym_check) PetscCall(ksponly_matrix_checks(snes, mg, u, F));
+    if (snes->fd_color || snes->sym_check) PetscCall(ksponly_matrix_checks(snes, mg, NULL, u, F));
     PetscCall(vec_to_dev(F));
     PetscCall(vec_to_dev(Y));
     p4b_ksp_result res;

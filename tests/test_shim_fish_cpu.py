@@ -149,6 +149,9 @@ def test_variable_coefficients_need_and_get_the_assembled_type(exe, tmp_path):
     got = lines[-1].split()
     assert lines[-1].startswith("done on 33 x 33 grid: sum ")
     assert abs(float(got[7]) - u.sum()) <= 1e-9 * abs(u.sum()) and abs(float(got[9]) - u[idx(m // 2, m // 2)]) <= 1e-10
+    # the -snes_fd_color consistency check and the symmetry report work on the assembled matrix as well
+    chk, _ = fish(out, "-da_refine 2 -pc_type jacobi -mat_type sellcuda -mat_is_symmetric 1e-10 -snes_fd_color")
+    assert chk[:2] == ["Matrix is symmetric (tolerance 1e-10)"] * 2 and chk[2].startswith("done on 17 x 17 grid")
     # Jacobi with a varying diagonal: D^-1 applied as a diagonal SELL matrix; fewer iterations, same answer
     jl, _ = fish(out, "-da_refine 3 -pc_type jacobi -ksp_rtol 1e-13 -mat_type sellcuda -ksp_converged_reason")
     its = lambda ls: int(ls[0].split()[-1])
