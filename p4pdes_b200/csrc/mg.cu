@@ -605,6 +605,8 @@ static int smooth(p4b_mg *m, int l, bool zero_guess, double *dot2_out = nullptr,
 
 static int coarse_solve(p4b_mg *m) {
     Level &L = m->lev[0];
+    if (!m->Ainv)
+        return fail(61, "coarsest grid has %lld nodes (> 2400): increase -pc_mg_levels", (long long)L.d.nglobal());
     ProfScope ps(m, 0, P4B_K_COARSE);
     return launch_dense_matvec(m->ctx->stream, m->n0, m->Ainv, L.b, L.x);
 }
@@ -732,7 +734,9 @@ static int mg_apply_internal(p4b_mg *m, double *dot2 = nullptr) {
 static int build_coarse_inverse(p4b_mg *m) {
     const LevelDesc &L = m->lev[0].d;
     const long long n = L.nglobal();
-    if (n > 2400) return fail(61, "coarsest grid has %lld nodes (> 2400): increase -pc_mg_levels", n);
+    // too large for a dense inverse: only -pc_type mg needs it, and coarse_solve() says so when it is asked for
+    // (-pc_type none / jacobi run on a one-level "hierarchy" of any size)
+    if (n > 2400) { m->n0 = 0; return 0; }
     m->n0 = (int)n;
     std::vector<double> A((size_t)n * n, 0.0);
     auto bd = [&](int i, int j, int k) {

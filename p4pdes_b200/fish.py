@@ -505,7 +505,8 @@ def fish_main(argv, ctx: Context | None = None, keep_solution=False, echo=False)
     fnorm0 = ctx.norm2(F)
     if o.snes_monitor_short:
         out("  0 SNES Function norm %s" % _snes_short(fnorm0))
-    opts = mg_options(levels=o.pc_mg_levels, cycle=o.pc_mg_cycle_type, smoother=o.mg_levels_ksp_type,
+    # [PETSc] PCSetUp_MG on a DMDA: refine+1 levels unless -pc_mg_levels, the grid before -da_refine being the coarsest
+    opts = mg_options(levels=o.pc_mg_levels or (o.da_refine + 1 if o.pc_type == "mg" else 1), cycle=o.pc_mg_cycle_type, smoother=o.mg_levels_ksp_type,
                       smooth_its=o.mg_levels_ksp_max_it, eig=o.mg_eigenvalues, esteig=o.mg_esteig, fuse=o.fuse)
     mg = Multigrid(ctx, g, opts)
     y = ctx.empty(n)

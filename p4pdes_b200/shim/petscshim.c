@@ -1409,8 +1409,11 @@ PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
     int Ml[P4B_MAX_LEVELS][3];
     memcpy(Ml[0], dm->M, sizeof(int) * 3);
     if (!strcmp(pc->type, PCMG)) {
+        /* [PETSc] PCSetUp_MG on a DMDA: without -pc_mg_levels there are refine+1 levels, the DMDA as created (before
+         * -da_refine) being the coarsest */
+        const int want = pc->levels > 0 ? pc->levels : dm->refine + 1;
         for (;;) {
-            if (pc->levels > 0 && nlev >= pc->levels) break;
+            if (nlev >= want) break;
             int ok = 1;
             for (int d = 0; d < dm->dim; d++)
                 if (Ml[nlev - 1][d] <= 3 || (Ml[nlev - 1][d] - 1) % 2) ok = 0;

@@ -10,8 +10,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "gpu_pending: needs a CUDA device; written after the round's GPU budget was spent and "
-                                       "not yet run on one (-m gpu_pending); promoted to `gpu` once validated")
+    config.addinivalue_line("markers", "gpu_pending: needs a CUDA device and has not run on one yet (-m gpu_pending); "
+                                       "promoted to `gpu` once validated")
+    config.addinivalue_line("markers", "slow: full BASELINE-size cases that take more than a few seconds")
 
 
 @pytest.fixture(scope="session")

@@ -34,6 +34,8 @@ def main():
                     help="also solve with the other setting of fused_halo (same process, fresh hierarchy) and report "
                          "whether history and solution are bit-identical")
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--c-oracle", action="store_true",
+                    help="check against oracle/fish_cpu.c (OpenMP; for the BASELINE sizes the NumPy oracle cannot run)")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -82,7 +84,15 @@ def main():
         assert u.size == g.n
         import hashlib
         out["sol_sha1"] = hashlib.sha1(u.tobytes()).hexdigest()
-        if not a.no_oracle:
+        if a.c_oracle:
+            from oracle import fish_cpu as fc
+            want = fc.solve(dim=a.dim, refine=a.refine, levels=a.levels, cycle=a.cycle, rtol=a.rtol, want_arrays=True)
+            out["oracle_its"] = want["its"]
+            out["sol_rel"] = float(np.linalg.norm(u - want["u"]) / np.linalg.norm(want["u"]))
+            h, w = np.array(res.history), np.array(want["history"])
+            out["hist_rel"] = float(np.max(np.abs(h - w) / (w + 4e-16 * w[0]))) if h.size == w.size else None
+            out["bnorm_rel"] = abs(bnorm - want["fnorm0"]) / want["fnorm0"]
+        elif not a.no_oracle:
             from oracle import fish_oracle as fo
             want = fo.fish(dim=a.dim, refine=a.refine, rtol=a.rtol,
                            mg=fo.MGOptions(levels=a.levels or None, cycle=a.cycle))

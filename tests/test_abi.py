@@ -149,7 +149,7 @@ def test_c_example_hosts_build_as_c99_and_refuse_to_run_without_a_device():
     exes = p4build.build_examples()
     assert set(exes) == {"minimal_native", "pattern_native"}
     if torch.cuda.is_available():
-        pytest.skip("a device is present: the run itself is covered by the gpu_pending tests")
+        pytest.skip("a device is present: the run itself is covered by tests/test_gpu_r2_*.py")
     for exe in exes.values():
         p = subprocess.run([exe], capture_output=True, text=True, timeout=60)
         assert p.returncode == 1 and "no CPU fallback" in p.stderr

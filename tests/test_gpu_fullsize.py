@@ -79,3 +79,36 @@ def test_solve_is_bitwise_reproducible_at_257(ctx):
     res2 = mg.cg_solve(b, x, rtol=1e-10)
     assert res.history == res2.history and torch.equal(x, x1)      # fixed-order reductions, no fp atomics
     mg.close()
+
+
+def _direct_parity(ctx, refine, levels):
+    """The same solve by the C oracle (oracle/fish_cpu.c, pinned by tests/test_fish_cpu_oracle.py) and on the device:
+    the north-star bar -- equal KSP iteration count, preconditioned residual history within 1e-10 relative, solution
+    within 1e-12 relative (fp64)."""
+    from oracle import fish_cpu as fc
+    want = fc.solve(dim=3, refine=refine, levels=levels, rtol=1e-10, want_arrays=True)
+    g, mg, b, x, u0, ue, res = solve(ctx, refine, levels)
+    assert res.reason == L.CONVERGED_RTOL and res.its == want["its"], (res.its, want["its"])
+    np.testing.assert_allclose(res.history, want["history"], rtol=1e-10, atol=4e-16 * want["history"][0])
+    bw = torch.from_numpy(want["b"]).cuda()
+    assert float(torch.linalg.vector_norm(b - bw) / torch.linalg.vector_norm(bw)) < 1e-13      # F(u0): the right-hand side
+    del bw
+    ctx.axpy(-1.0, x, u0)                       # u = u0 - y (SNESSolve_KSPONLY)
+    uw = torch.from_numpy(want["u"]).cuda()
+    rel = float(torch.linalg.vector_norm(u0 - uw) / torch.linalg.vector_norm(uw))
+    assert rel < 1e-12, rel
+    mg.close()
+    return res.its, rel
+
+
+def test_direct_oracle_parity_at_257(ctx):
+    """BASELINE config 2: fish 3-D 257^3, -da_refine 7 -pc_mg_levels 6 (c/ch8/cluster.sh:63 with Chebyshev/Jacobi)."""
+    its, rel = _direct_parity(ctx, 7, 6)
+    print("257^3: %d its, solution rel. diff vs C oracle %.2e" % (its, rel))
+
+
+@pytest.mark.slow
+def test_direct_oracle_parity_at_513(ctx):
+    """BASELINE config 3's grid on one GPU: 513^3, -da_refine 8 -pc_mg_levels 7 (the bench.py workload)."""
+    its, rel = _direct_parity(ctx, 8, 7)
+    print("513^3: %d its, solution rel. diff vs C oracle %.2e" % (its, rel))

@@ -65,6 +65,16 @@ def test_fused_exchange_is_bit_identical_to_push_kernels(nproc, args):
     assert r["hist_rel"] < 1e-10 and r["sol_rel"] < 1e-12
 
 
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+def test_slab_solve_matches_c_oracle_at_257(nproc):
+    """BASELINE config 2's grid (257^3, -pc_mg_levels 6) on slabs, against oracle/fish_cpu.c directly."""
+    if ngpu() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
+    r = run_worker(nproc, "--refine", 7, "--levels", 6, "--rtol", 1e-10, "--c-oracle")
+    assert r["its"] == r["oracle_its"]
+    assert r["hist_rel"] is not None and r["hist_rel"] < 1e-10 and r["sol_rel"] < 1e-12 and r["bnorm_rel"] < 1e-13
+
+
 def test_peer_transport_is_bit_identical_to_nccl_on_two_ranks():
     """A two-term sum has one rounding whatever the allreduce algorithm, so at 2 ranks NCCL send/recv/allreduce and the
     peer-memory transport must agree to the bit."""

@@ -1,6 +1,6 @@
-"""minimal.c on the device through p4b_minimal_solve (host logic in C++ inside the library): tests written AFTER this
-round's GPU budget was spent, marked `gpu_pending` (see tests/test_gpu_pending_pattern.py).  The C++ host logic itself is
-CPU-checked against the Python oracle (tests/test_native_nk_cpu.py); pending is its device instantiation."""
+"""minimal.c on the device through p4b_minimal_solve (host logic in C++ inside the library): the device instantiation of the
+C++ host logic that tests/test_native_nk_cpu.py checks on the CPU against the Python oracle.
+First run on a B200 in round 2 (profiles/r02_pending.md) and promoted to the `gpu` marker."""
 import numpy as np
 import pytest
 import torch
@@ -8,7 +8,7 @@ import torch
 from p4pdes_b200 import minimal as pm
 from p4pdes_b200.fish import Context
 
-pytestmark = [pytest.mark.gpu_pending, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
 
 
 @pytest.fixture(scope="module")

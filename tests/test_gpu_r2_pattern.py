@@ -1,8 +1,7 @@
-"""pattern.c on the device: tests written AFTER this round's GPU budget was spent.  They have not run on a GPU yet, so they
-carry their own marker (`gpu_pending`, run with `python -m pytest tests -m gpu_pending` on a B200) instead of `gpu`:
-the validated suite stays exactly what was validated.  Everything they exercise is CPU-checked (tests/test_pattern_cpu.py,
+"""pattern.c on the device: First run on a B200 in round 2 (profiles/r02_pending.md) and promoted to the `gpu` marker.
+Everything they exercise is also CPU-checked (tests/test_pattern_cpu.py,
 tests/test_native_nk_cpu.py: the same driver / the same C++ host logic on NumPy / plain-C++ operations reproduce the
-goldens verbatim); what is pending is the device instantiation: p4b_vec_wrms2, the ARKIMEX and Crank-Nicolson runs of
+goldens verbatim); here is the device instantiation: p4b_vec_wrms2, the ARKIMEX and Crank-Nicolson runs of
 the Python host, and p4b_pattern_solve."""
 import numpy as np
 import pytest
@@ -13,7 +12,7 @@ from p4pdes_b200.fish import Context
 from tests.test_pattern_cpu import (GOLDEN_TEST1, GOLDEN_TEST2, GOLDEN_TEST3, GOLDEN_TEST4, GOLDEN_TEST5, TEST1, TEST2,
                                     TEST3, TEST4, TEST5)
 
-pytestmark = [pytest.mark.gpu_pending, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
 
 
 @pytest.fixture(scope="module")

@@ -1,6 +1,6 @@
 """The reference's UNCHANGED c/ch5/pattern.c on the device: p4pdes_b200/bin/pattern = pattern.c compiled against
 include/petsc.h, linked with the shim and libp4b200.so (p4pdes_b200/build.py:DRIVERS; the prebuilt binary travels to the
-GPU box).  Written AFTER this round's GPU budget was spent: `gpu_pending`, never run on a B200 yet.  The same binary
+GPU box).  First run on a B200 in round 2 (profiles/r02_pending.md) and promoted to the `gpu` marker.  The same binary
 over the host stand-in is checked on the CPU (tests/test_shim_pattern_cpu.py)."""
 import json
 import os
@@ -14,7 +14,7 @@ EXE = os.path.join(ROOT, "p4pdes_b200", "bin", "pattern")
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "pattern_goldens.json")))
 MG = " -pc_type mg -mg_levels_pc_type jacobi"
 
-pytestmark = [pytest.mark.gpu_pending, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device"),
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device"),
               pytest.mark.skipif(not os.path.exists(EXE), reason="p4pdes_b200/bin/pattern was not built")]
 
 

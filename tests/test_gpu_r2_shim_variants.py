@@ -2,7 +2,7 @@
 (tests/shim_cases/*.c, compiled here against include/petsc.h and the in-tree libraries): the model written differently
 must be recognised and run device-resident; a system the library has no kernels for must run through host callbacks.
 The expected numbers were produced on the CPU through the host stand-in and confirmed there by independent NumPy solves
-(tests/test_shim_minimal_cpu.py, tests/test_shim_pattern_cpu.py).  `gpu_pending`: never run on a B200 yet."""
+(tests/test_shim_minimal_cpu.py, tests/test_shim_pattern_cpu.py).  First run on a B200 in round 2 (profiles/r02_pending.md) and promoted to the `gpu` marker."""
 import os
 import subprocess
 
@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "p4pdes_b200", "lib")
 MG = " -pc_type mg -mg_levels_pc_type jacobi"
 
-pytestmark = [pytest.mark.gpu_pending, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device"),
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device"),
               pytest.mark.skipif(not os.path.exists(os.path.join(LIB, "libpetsc_p4b200.so")), reason="shim library not built")]
 
 

@@ -6,7 +6,7 @@ oracle/native/p4b_standin.cpp (the SAME solver template over plain loops; test i
 shim's host logic: option handling, the DMDALocalInfo / a[j][i] views it builds around FormFunctionLocal on every level
 and stage, SNESMonitorSet monitors seeing the stage's DM and iterate, the DM / solution replacement under
 -snes_grid_sequence, error behaviour -- against the reference's goldens (tests/golden/minimal_goldens.json).
-The device instantiation of the same binary (p4pdes_b200/bin/minimal) is tests/test_gpu_pending_shim_minimal.py."""
+The device instantiation of the same binary (p4pdes_b200/bin/minimal) is tests/test_gpu_r2_shim_minimal.py."""
 import json
 import os
 import re

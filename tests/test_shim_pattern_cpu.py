@@ -7,7 +7,7 @@ two-component DMDA (ghosted a[j][i] views, coordinates), identification of the m
 callbacks, verification of those callbacks (functions at a generic state, every Jacobian row), which callbacks are
 invoked for which -ts_type, option mapping, and that callbacks which are NOT the model are refused -- against the
 reference's goldens (tests/golden/pattern_goldens.json) and a variants driver written for this purpose
-(tests/shim_cases/ts_variants.c).  The device run of the same binary is tests/test_gpu_pending_shim_pattern.py."""
+(tests/shim_cases/ts_variants.c).  The device run of the same binary is tests/test_gpu_r2_shim_pattern.py."""
 import json
 import os
 import subprocess
