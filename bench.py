@@ -11,8 +11,9 @@ copied from pinned host memory, solved, and x copied back, all inside the timed 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--refine R]
 
 N > 1: launched by torchrun, one rank per GPU; the grid is split into z-slabs (strong scaling:
-the total problem is fixed), ghost planes and dot products go over NCCL.
---impl reference: the CPU restatement of the same algorithm (oracle/) on the host cores.
+the total problem is fixed); ghost planes and dot products go through peer memory over NVLink, fused into the kernels
+(--comm nccl: ncclSend/Recv/AllReduce instead, A/B).
+--impl reference: the CPU restatement of the same algorithm (oracle/) on the host cores, on the same grid.
 """
 import argparse
 import ctypes as C
@@ -91,34 +92,69 @@ def cpu_reference(refine, levels, threads=None, repeats=1):
     return fish_cpu.timed_solve(refine=refine, levels=levels, rtol=1e-10, threads=threads, repeats=repeats)
 
 
+CPU_PORT_NOTE = ("OpenMP C restatement oracle/fish_cpu.c of the same algorithm and options (PETSc/MPI are not installable "
+                 "here); matrix-free 7-point MatMult (16 B/node where PETSc's AIJ MatMult reads ~104 B/node), one loop per "
+                 "PETSc operation (MatMult, PCApply, VecAXPY... unfused), so it moves ~2.7x the fused algorithmic bytes "
+                 "the GPU roofline counts")
+
+
+def cpu_stream_triad():
+    """Host STREAM-triad GB/s (HARDWARE.md:14-21 of the reference: the CPU's own roofline), all cores."""
+    try:
+        from oracle import fish_cpu
+        return round(fish_cpu.stream_triad_gbs(n=1 << 26, reps=5, threads=os.cpu_count()), 1)
+    except Exception:
+        return None
+
+
+def workload_string(refine, n=None):
+    m = 2 ** (refine + 1) + 1
+    return ("fish.c 3-D Poisson manuexp %d^3 (%d unknowns), CG + V-cycle GMG, Chebyshev(2)/Jacobi, rtol 1e-10"
+            % (m, n if n is not None else m ** 3))
+
+
 def run_reference(args):
+    """--impl reference: the CPU arm on the SAME workload as the GPU arm (same grid, same options).  PETSc cannot be
+    built here, so the arm is the OpenMP C restatement (kind "port").  A 513^3 solve takes ~15 s on 16 cores, so the
+    number of solves is clamped to a wall-clock budget and the line says how many ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    refine = args.cpu_refine
-    levels = max(2, refine - 1)
+    refine = args.cpu_refine if args.cpu_refine else args.refine
+    levels = args.levels or max(2, refine - 1)
     cores = os.cpu_count()
-    vals = []
-    for i in range(args.warmup + args.steps):
+    budget = args.cpu_budget_s
+    t_start = time.perf_counter()
+    warm = min(args.warmup, 1)            # a CPU solve needs one pass to fault its pages in, not three
+    vals, ran_warm = [], 0
+    for i in range(warm + args.steps):
+        if i >= warm + 1 and vals:
+            # stop when the next solve would overrun the budget
+            if time.perf_counter() - t_start + vals[-1]["seconds"] * 1.3 > budget:
+                break
         r = cpu_reference(refine, levels, threads=cores)
-        if i >= args.warmup:
+        if i >= warm:
             vals.append(r)
+        else:
+            ran_warm += 1
     secs = sum(v["seconds"] for v in vals) / len(vals)
     n = vals[0]["n"]
     mdofs = n / secs / 1e6
     m = 2 ** (refine + 1) + 1
     line = {
         "impl": "reference", "metric": "fish3d_cg_gmg_solve_mdof_per_s", "value": mdofs, "unit": "MDOF/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3,
+        "n_gpus": args.gpus, "steps": len(vals), "warmup": ran_warm, "steps_requested": args.steps,
+        "warmup_requested": args.warmup, "ms_per_step": secs * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "fish.c 3-D Poisson manuexp 513^3, CG + V-cycle GMG, Chebyshev(2)/Jacobi, rtol 1e-10",
-                   "options": OPTIONS.format(refine=8, levels=7)},
+        "config": {"workload": workload_string(refine, n), "options": OPTIONS.format(refine=refine, levels=levels),
+                   "levels": vals[0]["nlevels"]},
         "cpu_baseline": {"value": mdofs, "unit": "MDOF/s", "cores": vals[0]["threads"], "kind": "port",
-                         "sample": "same algorithm and options on a %d^3 grid (%d unknowns), %d KSP its, OpenMP C "
-                                   "restatement oracle/fish_cpu.c (PETSc/MPI are not installable here)"
-                                   % (m, n, vals[0]["its"])},
+                         "stream_triad_gbs": cpu_stream_triad(),
+                         "sample": "%d timed solve(s) of the full %d^3 workload (%d unknowns, %d KSP its, %.1f s each; "
+                                   "solve count clamped to a %d s budget); %s"
+                                   % (len(vals), m, n, vals[0]["its"], secs, budget, CPU_PORT_NOTE)},
         "e2e": {"value": mdofs, "unit": "MDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "ksp_its": vals[0]["its"],
+        "gpu_launches": 0, "ksp_its": vals[0]["its"], "errinf": vals[0]["errinf"],
     }
     print(json.dumps(line))
     return 0
@@ -132,8 +168,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--refine", type=int, default=8, help="-da_refine (8 = 513^3, 7 = 257^3)")
     ap.add_argument("--levels", type=int, default=0, help="-pc_mg_levels (default refine-1: coarse grid 9^3)")
-    ap.add_argument("--cpu-refine", type=int, default=7, help="grid of the bounded CPU baseline sample (7 = 257^3)")
+    ap.add_argument("--cpu-refine", type=int, default=0, help="grid of the CPU arm / cpu_baseline (default: --refine, "
+                                                               "i.e. the same workload)")
+    ap.add_argument("--cpu-budget-s", type=float, default=200.0, help="wall-clock budget of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=1,
+                    help="how many of the timed solves carry per-kernel CUDA-event brackets (the roofline source)")
+    ap.add_argument("--port-stats", action="store_true", help="collect in-kernel wait / fence times (comm_stats)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fuse", action="store_true")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="multi-GPU transport (A/B)")
@@ -166,7 +207,7 @@ def main():
     torch.cuda.set_stream(side)
     L.tune("comm_peer", 1 if args.comm == "peer" else 0)
     L.tune("fused_halo", 0 if args.no_fused_halo else 1)
-    L.tune("port_opts", args.port_opts)
+    L.tune("port_opts", args.port_opts | (4 if args.port_stats else 0))
     L.tune("force_mg", args.force_mg)
     if args.rep_points:
         L.tune("rep_points", args.rep_points)
@@ -218,7 +259,11 @@ def main():
         launches0 = lib.p4b_launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(ctx.stream)
-        for _ in range(args.steps):
+        for i in range(args.steps):
+            # kernel brackets (CUDA events around every finest-level launch) in the first --profile-steps timed
+            # solves only: the event records cost GPU front-end time between kernels, which the thin slabs of an
+            # 8-GPU run notice
+            mg.profile(i < args.profile_steps)
             res = mg.cg_solve(b, x, rtol=1e-10)
         ev1.record(ctx.stream)
         barrier()
@@ -237,7 +282,8 @@ def main():
     cs = (C.c_ulonglong * 5)()
     lib.p4b_comm_stats(ctx.h, C.byref(cs), 1)
     comm_stats = {"waits": cs[0], "wait_ms": cs[1] / 1e6, "wait_max_us": cs[2] / 1e3, "fences": cs[3],
-                  "fence_ms": cs[4] / 1e6, "note": "sums over boundary CTAs (rank 0), all warm-up + timed steps"}
+                  "fence_ms": cs[4] / 1e6, "note": "sums over boundary CTAs (rank 0), all warm-up + timed steps; "
+                                                   "collected only with --port-stats"}
     exchange = {k: stats.pop(k) for k in L.KERNEL_CLASSES[L.N_ROOFLINE_CLASSES:] if k in stats}
     if args.trace:
         mg.profile(2)
@@ -302,20 +348,27 @@ def main():
                 "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": None,
                 "alg_bytes_per_launch": s["bytes"] / s["launches"], "launches": s["launches"],
                 "ms_per_launch": s["ms"] / s["launches"],
-                "fine_level_kernel_ms_share_of_step": total_ms / (ms_step * args.steps)}
+                "profiled_steps": min(args.profile_steps, args.steps),
+                "fine_level_kernel_ms_share_of_step": total_ms / (ms_step * min(args.profile_steps, args.steps))}
+        # DRAM bytes per launch from the committed `ncu --set full` capture of these kernels on ONE GPU at this grid
+        # (profiles/traffic.json; not re-measured by this run).  Slabs of a multi-GPU run launch on 1/N of the grid, so
+        # the single-GPU capture does not describe them: null there.
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            roof["traffic"] = json.load(open(tp)).get(top)
+        if os.path.exists(tp) and world == 1 and refine == 8:
+            tj = json.load(open(tp))
+            roof["traffic"] = tj.get(top)
+            roof["traffic_source"] = "committed ncu --set full capture (%s), dram__bytes_read.sum + dram__bytes_write.sum "\
+                                     "per launch" % tj.get("_source", "profiles/traffic.json")
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = cpu_reference(args.cpu_refine, max(2, args.cpu_refine - 1), threads=os.cpu_count())
-            m = 2 ** (args.cpu_refine + 1) + 1
+            cref = args.cpu_refine if args.cpu_refine else refine
+            r = cpu_reference(cref, args.levels or max(2, cref - 1), threads=os.cpu_count())
+            m = 2 ** (cref + 1) + 1
             cpu = {"value": r["n"] / r["seconds"] / 1e6, "unit": "MDOF/s", "cores": r["threads"], "kind": "port",
-                   "solve_s": r["seconds"], "ksp_its": r["its"],
-                   "sample": "one solve, same algorithm/options, %d^3 grid (%d unknowns); OpenMP C restatement "
-                             "oracle/fish_cpu.c, not PETSc (PETSc/MPI absent from the image)" % (m, r["n"])}
+                   "solve_s": r["seconds"], "ksp_its": r["its"], "stream_triad_gbs": cpu_stream_triad(),
+                   "sample": "one solve of the full %d^3 workload (%d unknowns); %s" % (m, r["n"], CPU_PORT_NOTE)}
         except Exception as exc:  # the baseline is a reported number, never a reason to lose the GPU line
             cpu = {"value": None, "unit": "MDOF/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (exc,)}
 
@@ -325,8 +378,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "solve_s": ms_step * 1e-3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "fish.c 3-D Poisson manuexp %d^3 (%d unknowns), CG + V-cycle GMG, Chebyshev(2)/Jacobi, "
-                               "rtol 1e-10" % (m, ndof),
+        "config": {"workload": workload_string(refine, ndof),
                    "options": OPTIONS.format(refine=refine, levels=levels), "levels": mg.nlevels,
                    "parallelism": "z-slabs x%d" % world, "transport": (args.comm if world > 1 else None), "l2": "inputs (%.2f GB per vector) exceed the 126 MB L2"
                    % (8 * ndof / 1e9), "fused": not args.no_fuse, "cuda_graph_coarse_levels": not args.no_graph,
@@ -334,7 +386,7 @@ def main():
         "ksp_its": res.its, "ksp_reason": L.REASONS.get(res.reason), "rnorm0": res.rnorm0, "rnorm": res.rnorm,
         "errinf": errinf, "err2h": err2h,
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": table,
-        "exchange_ms_per_step": {k: v["ms"] / args.steps for k, v in exchange.items()},
+        "exchange_ms_per_step": {k: v["ms"] / max(1, min(args.profile_steps, args.steps)) for k, v in exchange.items()},
         "comm_stats": comm_stats,
         "cpu_baseline": cpu,
     }

@@ -24,6 +24,24 @@
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
+
+/* first touch by the threads that will stream the vector (static schedule, as every loop below): on a multi-socket host
+ * a serial calloc / memcpy would put every page on one NUMA node */
+static double *par_zeros(long n) {
+    double *v = malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    if (!v) return NULL;
+#pragma omp parallel for schedule(static)
+    for (long q = 0; q < n; q++) v[q] = 0.0;
+    return v;
+}
+static void par_copy(double *dst, const double *src, long n) {
+#pragma omp parallel for schedule(static)
+    for (long q = 0; q < n; q++) dst[q] = src[q];
+}
+static void par_zero(double *v, long n) {
+#pragma omp parallel for schedule(static)
+    for (long q = 0; q < n; q++) v[q] = 0.0;
+}
 #endif
 
 typedef struct {
@@ -211,7 +229,7 @@ static void cheb_smooth(level_t *g, int pc, int its, const double *b, double *x)
         double *t = pm1; pm1 = pk; pk = t;
         cm1 = ck; ck = cp1;
     }
-    if (pk != x) memcpy(x, pk, sizeof(double) * g->n);
+    if (pk != x) par_copy(x, pk, g->n);
 }
 
 static void rich_smooth(level_t *g, int pc, int its, const double *b, double *x) {
@@ -304,7 +322,7 @@ static void mcycle(mg_t *M, int l) {
     smooth(M, l, g->b, g->x);
     op_residual(g, g->b, g->x, g->r);
     restrict_to(g, c, g->r, c->b);
-    memset(c->x, 0, sizeof(double) * c->n);
+    par_zero(c->x, c->n);
     const int cycles = (l == 1 || M->cycle == 1) ? 1 : 2;
     for (int q = 0; q < cycles; q++) mcycle(M, l - 1);
     prolong_add(g, c, c->x, g->x);
@@ -313,10 +331,10 @@ static void mcycle(mg_t *M, int l) {
 
 static void pcmg_apply(mg_t *M, const double *r, double *z) {
     level_t *g = &M->lev[M->nlev - 1];
-    memcpy(g->b, r, sizeof(double) * g->n);
-    memset(g->x, 0, sizeof(double) * g->n);
+    par_copy(g->b, r, g->n);
+    par_zero(g->x, g->n);
     mcycle(M, M->nlev - 1);
-    memcpy(z, g->x, sizeof(double) * g->n);
+    par_copy(z, g->x, g->n);
 }
 
 static double lambda_max(const level_t *g) {
@@ -351,8 +369,8 @@ static int mg_setup(mg_t *M, const fishcpu_opts *o) {
         const double lam = o->smoother_pc == 1 ? 1.0 : lambda_max(g);
         if (o->emax > 0) { g->emin = o->emin; g->emax = o->emax; }
         else { g->emin = 0.1 * lam; g->emax = 1.1 * lam; }
-        g->x = calloc(g->n, sizeof(double)); g->b = calloc(g->n, sizeof(double)); g->r = calloc(g->n, sizeof(double));
-        g->t1 = calloc(g->n, sizeof(double)); g->t2 = calloc(g->n, sizeof(double));
+        g->x = par_zeros(g->n); g->b = par_zeros(g->n); g->r = par_zeros(g->n);
+        g->t1 = par_zeros(g->n); g->t2 = par_zeros(g->n);
         if (!g->x || !g->b || !g->r || !g->t1 || !g->t2) return 71;
     }
     /* coarsest operator, dense Cholesky  (PCLU on level 0) */
@@ -447,12 +465,12 @@ int fishcpu_solve(const fishcpu_opts *o, fishcpu_result *res, double *u_out, dou
     if (rc) return rc;
     level_t *g = &M.lev[M.nlev - 1];
     const long n = g->n;
-    double *u = calloc(n, sizeof(double)), *b = calloc(n, sizeof(double)), *x = calloc(n, sizeof(double));
-    double *r = calloc(n, sizeof(double)), *z = calloc(n, sizeof(double)), *p = calloc(n, sizeof(double));
-    double *w = calloc(n, sizeof(double));
+    double *u = par_zeros(n), *b = par_zeros(n), *x = par_zeros(n), *r = par_zeros(n), *z = par_zeros(n);
+    double *p = par_zeros(n), *w = par_zeros(n);
     if (!u || !b || !x || !r || !z || !p || !w) return 71;
     const long plane = (long)g->nx * g->ny;
     if (o->gonboundary)
+#pragma omp parallel for schedule(static)
         for (long q = 0; q < n; q++) {
             const int k = (int)(q / plane), j = (int)((q % plane) / g->nx), i = (int)(q % g->nx);
             if (is_bd(g, i, j, k)) {
@@ -466,7 +484,7 @@ int fishcpu_solve(const fishcpu_opts *o, fishcpu_result *res, double *u_out, dou
     res->nlevels = M.nlev;
     /* ---- KSPSolve_CG (timed) ---- */
     const double t0 = now();
-    memcpy(r, b, sizeof(double) * n);
+    par_copy(r, b, n);
     pcmg_apply(&M, r, z);
     double beta = dot(n, z, r), dp = sqrt(dot(n, z, z)), beta_old = 0.0;
     res->nhist = 0;
@@ -474,7 +492,7 @@ int fishcpu_solve(const fishcpu_opts *o, fishcpu_result *res, double *u_out, dou
     const double ttol = fmax(o->rtol * dp, 1e-50);
     int its = 0;
     while (dp > ttol && its < o->max_it) {
-        if (its == 0) memcpy(p, z, sizeof(double) * n);
+        if (its == 0) par_copy(p, z, n);
         else {
             const double bb = beta / beta_old;
 #pragma omp parallel for schedule(static)
@@ -497,6 +515,7 @@ int fishcpu_solve(const fishcpu_opts *o, fishcpu_result *res, double *u_out, dou
     if (y_out) memcpy(y_out, x, sizeof(double) * n);
     if (b_out) memcpy(b_out, b, sizeof(double) * n);
     double einf = 0.0, e2 = 0.0;
+#pragma omp parallel for schedule(static) reduction(max : einf) reduction(+ : e2)
     for (long q = 0; q < n; q++) {
         u[q] -= x[q];
         const int k = (int)(q / plane), j = (int)((q % plane) / g->nx), i = (int)(q % g->nx);

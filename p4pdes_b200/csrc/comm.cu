@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(512) halo_push_kernel(const double *lo_src, do
 }
 
 // sum nv (<= 3) doubles over all ranks; result overwrites vals on every rank
-__global__ void __launch_bounds__(64) allreduce_kernel(double *vals, int nv, int op_max, PeerTable peers, LocalSync *sync) {
+__global__ void __launch_bounds__(64) allreduce_kernel(double *vals, int nv, int op_max, PeerTable peers, LocalSync *sync,
+                                                       HostPoll *hp, unsigned long long seq) {
     const int r = threadIdx.x;
     const unsigned long long e = sync->red_epoch + 1;
     const int par = (int)(e & 1ull);
@@ -107,9 +108,25 @@ __global__ void __launch_bounds__(64) allreduce_kernel(double *vals, int nv, int
             s = op_max ? fmax(s, v) : s + v;
         }
         vals[r] = s;
+        if (hp) ((volatile double *)hp->v)[r] = s;
     }
     __syncthreads();
-    if (r == 0) sync->red_epoch = e;
+    if (r == 0) {
+        sync->red_epoch = e;
+        if (hp) {
+            __threadfence_system();
+            st_release_sys(&hp->seq, seq);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64) publish_kernel(const double *vals, int nv, HostPoll *hp, unsigned long long seq) {
+    if ((int)threadIdx.x < nv) ((volatile double *)hp->v)[threadIdx.x] = vals[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        st_release_sys(&hp->seq, seq);
+    }
 }
 
 // flag-only barrier: among the two slab neighbours (all = 0) or all ranks (all = 1)
@@ -136,7 +153,7 @@ __global__ void __launch_bounds__(512) gather_push_kernel(const double *src, lon
     __threadfence_system();
 }
 
-__global__ void __launch_bounds__(32) port_wait_kernel(const HaloPort port) { port_wait(port, true); }
+__global__ void __launch_bounds__(32) port_wait_kernel(const HaloPort port) { port_wait(port, true, true); }
 
 int launch_port_wait(cudaStream_t st, const HaloPort &port) {
     if (!port.sync) return 0;
@@ -155,9 +172,16 @@ int launch_halo_push(cudaStream_t st, const double *lo_src, double *lo_dst, cons
     P4B_LAUNCH_CHECK();
     return 0;
 }
-int launch_allreduce(cudaStream_t st, double *vals, int nv, int op_max, const PeerTable &peers, LocalSync *sync) {
+int launch_allreduce(cudaStream_t st, double *vals, int nv, int op_max, const PeerTable &peers, LocalSync *sync,
+                     HostPoll *hp, unsigned long long seq) {
     if (nv < 1 || nv > 3) return fail(62, "peer allreduce handles 1..3 values");
-    allreduce_kernel<<<1, 64, 0, st>>>(vals, nv, op_max, peers, sync);
+    allreduce_kernel<<<1, 64, 0, st>>>(vals, nv, op_max, peers, sync, hp, seq);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+int launch_publish(cudaStream_t st, const double *vals, int nv, HostPoll *hp, unsigned long long seq) {
+    if (nv < 1 || nv > 64) return fail(62, "publish handles 1..64 values");
+    publish_kernel<<<1, 64, 0, st>>>(vals, nv, hp, seq);
     P4B_LAUNCH_CHECK();
     return 0;
 }

@@ -28,6 +28,14 @@ struct LocalSync {
     unsigned long long wait_ns, wait_n, fence_ns, fence_n, wait_max_ns;
 };
 
+// Scalars the host must see (Krylov convergence tests, step-size control): the producing kernel stores them straight
+// into pinned, device-mapped host memory and then a sequence number (system-scope release); the host spins on the
+// sequence number.  No copy engine, no stream synchronisation: the round trip is ~2 us instead of ~30.
+struct HostPoll {
+    double v[64];
+    unsigned long long seq;
+};
+
 struct PeerTable {
     int rank, nranks;
     Mailbox *mbox[MAX_RANKS];                   // mbox[rank] is the local one
@@ -82,21 +90,39 @@ __device__ __forceinline__ unsigned long long port_ld_acquire_sys(const unsigned
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// gpu-scope release fence of a boundary CTA before it counts itself in (cheap: the stores only have to reach L2 order)
+__device__ __forceinline__ void port_fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void port_st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+constexpr int PORT_OPT_STATS = 4;     // HaloPort::opts bit: collect wait / fence times (globaltimer + atomics; off by default)
 // Only "boundary" CTAs -- those that read a ghost plane or store into a neighbour's -- take part in the protocol;
 // `boundary` must be uniform over the CTA, and the same CTAs must call port_signal with it.
 // All their threads, before the first ghost read / peer store:
-__device__ __forceinline__ void port_wait(const HaloPort &hp, bool boundary) {
+// (async_proxy: the ghost planes are read by bulk / TMA copies -- the plane-marching kernels -- so the generic-proxy
+// acquire must be carried over to the async proxy; kernels that read them with ordinary loads skip that fence)
+__device__ __forceinline__ void port_wait(const HaloPort &hp, bool boundary, bool async_proxy = false) {
     if (!hp.sync || !boundary) return;
     if (threadIdx.x == 0) {
-        const unsigned long long t0 = port_now_ns();
+        const bool stats = (hp.opts & PORT_OPT_STATS) != 0;
+        const unsigned long long t0 = stats ? port_now_ns() : 0ull;
         const unsigned long long e = *(volatile unsigned long long *)&hp.sync->halo_epoch;
-        if (hp.flag_lo) while (port_ld_acquire_sys(&hp.my_flags[0]) < e) { }
-        if (hp.flag_hi) while (port_ld_acquire_sys(&hp.my_flags[1]) < e) { }
-        asm volatile("fence.proxy.async;" ::: "memory");     // ghost planes may be read by bulk (TMA) copies
-        const unsigned long long dt = port_now_ns() - t0;
-        atomicAdd(&hp.sync->wait_ns, dt);
-        atomicAdd(&hp.sync->wait_n, 1ull);
-        atomicMax(&hp.sync->wait_max_ns, dt);
+        if (hp.opts & (8 | 16)) {
+            // spin with relaxed loads, then ONE acquire fence (an acquire load per spin invalidates L1 every time)
+            if (hp.flag_lo) while (*(volatile const unsigned long long *)&hp.my_flags[0] < e) { }
+            if (hp.flag_hi) while (*(volatile const unsigned long long *)&hp.my_flags[1] < e) { }
+            if (!(hp.opts & 16)) port_fence_sys();         // (16: attribution experiment only -- no acquire at all)
+        } else {
+            if (hp.flag_lo) while (port_ld_acquire_sys(&hp.my_flags[0]) < e) { }
+            if (hp.flag_hi) while (port_ld_acquire_sys(&hp.my_flags[1]) < e) { }
+        }
+        if (async_proxy) asm volatile("fence.proxy.async;" ::: "memory");
+        if (stats) {
+            const unsigned long long dt = port_now_ns() - t0;
+            atomicAdd(&hp.sync->wait_ns, dt);
+            atomicAdd(&hp.sync->wait_n, 1ull);
+            atomicMax(&hp.sync->wait_max_ns, dt);
+        }
     }
     __syncthreads();
 }
@@ -105,48 +131,65 @@ __device__ __forceinline__ void port_store(const HaloPort &hp, long long idx, do
     if (hp.lo_dst && idx < hp.plane) hp.lo_dst[idx] = v;
     if (hp.hi_dst && idx >= hp.hi_start) hp.hi_dst[idx - hp.hi_start] = v;
 }
+// Publication of a kernel's pushes: ONE system-scope fence per kernel.  Every boundary CTA orders its peer stores with
+// a gpu-scope release fence and counts itself in (pdone); the CTA that completes the count has thereby observed all of
+// them (gpu-scope acquire through the counter), so its single fence.acq_rel.sys -- cumulative in the PTX memory model
+// -- orders every boundary CTA's stores before the flags it then writes.  (Round 1 had every boundary CTA issue its
+// own system-scope fence, 4-5 us each and hundreds of them per kernel: measured with local stand-in targets, that --
+// not NVLink -- was a quarter of the 8-GPU step, profiles/r02_exchange.md.)
+__device__ __forceinline__ void port_publish(const HaloPort &hp, unsigned int nboundary, bool stored) {
+    if (stored && !(hp.opts & 32)) port_fence_gpu();       // (32: attribution experiment only)
+    if (atomicAdd(&hp.sync->pdone, 1u) == nboundary - 1u) {
+        const bool stats = (hp.opts & PORT_OPT_STATS) != 0;
+        const unsigned long long t0 = stats ? port_now_ns() : 0ull;
+        port_fence_sys();
+        const unsigned long long e = hp.sync->halo_epoch + 1ull;
+        if (hp.flag_lo) port_st_relaxed_sys(hp.flag_lo, e);
+        if (hp.flag_hi) port_st_relaxed_sys(hp.flag_hi, e);
+        hp.sync->halo_epoch = e;
+        hp.sync->pdone = 0u;
+        __threadfence();
+        if (stats) {
+            atomicAdd(&hp.sync->fence_ns, port_now_ns() - t0);
+            atomicAdd(&hp.sync->fence_n, 1ull);
+        }
+    }
+}
+// Variant with a dedicated signalling CTA (the plane-marching kernels, where the publishing CTA would otherwise stall
+// its own march for the 4-5 us of the system-scope fence): boundary CTAs only count themselves in (port_arrive, one
+// elected thread); one extra CTA of the grid waits for the count and publishes (port_signaller, one thread).
+__device__ __forceinline__ void port_arrive(const HaloPort &hp) {
+    if (!hp.sync || !hp.push) return;
+    port_fence_gpu();
+    atomicAdd(&hp.sync->pdone, 1u);
+}
+__device__ __forceinline__ void port_signaller(const HaloPort &hp, unsigned int nboundary) {
+    if (!hp.sync || !hp.push) return;
+    unsigned int seen;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(&hp.sync->pdone) : "memory");
+    } while (seen < nboundary);
+    port_fence_sys();
+    const unsigned long long e = hp.sync->halo_epoch + 1ull;
+    if (hp.flag_lo) port_st_relaxed_sys(hp.flag_lo, e);
+    if (hp.flag_hi) port_st_relaxed_sys(hp.flag_hi, e);
+    hp.sync->halo_epoch = e;
+    hp.sync->pdone = 0u;
+    __threadfence();
+}
 // All threads of the boundary CTAs, after their last peer store; nboundary = number of boundary CTAs of the grid.
-// The last of them to arrive bumps the exchange count and releases it to both neighbours.
 // (stored = false: this CTA is only counted, it has no peer stores of its own to publish)
 __device__ __forceinline__ void port_signal(const HaloPort &hp, bool boundary, unsigned int nboundary,
                                             bool stored = true) {
     if (!hp.sync || !hp.push || !boundary) return;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        if (stored) {
-            const unsigned long long t0 = port_now_ns();
-            port_fence_sys();
-            atomicAdd(&hp.sync->fence_ns, port_now_ns() - t0);
-            atomicAdd(&hp.sync->fence_n, 1ull);
-        }
-        if (atomicAdd(&hp.sync->pdone, 1u) == nboundary - 1u) {
-            // (the release stores below carry the fence that orders the other CTAs' pushes, observed through
-            // the counter, before the flags)
-            const unsigned long long e = hp.sync->halo_epoch + 1ull;
-            if (hp.flag_lo) port_st_release_sys(hp.flag_lo, e);
-            if (hp.flag_hi) port_st_release_sys(hp.flag_hi, e);
-            hp.sync->halo_epoch = e;
-            hp.sync->pdone = 0u;
-            __threadfence();
-        }
-    }
+    if (threadIdx.x == 0) port_publish(hp, nboundary, stored);
 }
 // The same for a caller that has just passed a __syncthreads() after its last peer store: `elected` is true in
 // exactly one thread of the CTA.
 __device__ __forceinline__ void port_signal_nosync(const HaloPort &hp, unsigned int nboundary, bool elected) {
     if (!hp.sync || !hp.push || !elected) return;
-    const unsigned long long t0 = port_now_ns();
-    port_fence_sys();
-    atomicAdd(&hp.sync->fence_ns, port_now_ns() - t0);
-    atomicAdd(&hp.sync->fence_n, 1ull);
-    if (atomicAdd(&hp.sync->pdone, 1u) == nboundary - 1u) {
-        const unsigned long long e = hp.sync->halo_epoch + 1ull;
-        if (hp.flag_lo) port_st_release_sys(hp.flag_lo, e);
-        if (hp.flag_hi) port_st_release_sys(hp.flag_hi, e);
-        hp.sync->halo_epoch = e;
-        hp.sync->pdone = 0u;
-        __threadfence();
-    }
+    port_publish(hp, nboundary, true);
 }
 // Launch-order remap of a block index that runs over planes / chunks of the slab: with an upper neighbour the block
 // that holds the LAST plane is scheduled second, so both boundary planes are produced (and signalled) first.
@@ -192,7 +235,11 @@ int launch_port_wait(cudaStream_t st, const HaloPort &port);
 int launch_halo_push(cudaStream_t st, const double *lo_src, double *lo_dst, const double *hi_src, double *hi_dst,
                      long long plane, unsigned long long *flag_prev, unsigned long long *flag_next,
                      const unsigned long long *my_flags, LocalSync *sync);
-int launch_allreduce(cudaStream_t st, double *vals, int nv, int op_max, const PeerTable &peers, LocalSync *sync);
+// hp != nullptr: the result is also published to the host (HostPoll) with sequence number seq
+int launch_allreduce(cudaStream_t st, double *vals, int nv, int op_max, const PeerTable &peers, LocalSync *sync,
+                     HostPoll *hp = nullptr, unsigned long long seq = 0);
+// vals[0..nv) -> hp->v, then hp->seq = seq (one tiny kernel; nv <= 64)
+int launch_publish(cudaStream_t st, const double *vals, int nv, HostPoll *hp, unsigned long long seq);
 int launch_barrier(cudaStream_t st, int all, const PeerTable &peers, LocalSync *sync);
 int launch_gather_push(cudaStream_t st, const double *src, long long n, long long off_doubles, const GatherTable &dst,
                        int rank, int nranks);

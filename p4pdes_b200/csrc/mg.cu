@@ -111,7 +111,9 @@ struct p4b_ctx {
     Reducer red;
     double *d_scal = nullptr;      // 16 device doubles: CG scalars
     double *h_scal = nullptr;      // 16 pinned host doubles
-    double *d_mdot = nullptr, *h_mdot = nullptr;      // 64 doubles each, on first use (p4b_vec_mdot)
+    double *d_mdot = nullptr;      // 64 doubles, on first use (p4b_vec_mdot)
+    HostPoll *h_poll = nullptr, *d_poll = nullptr;    // pinned host memory the kernels publish scalars into / its device alias
+    unsigned long long poll_seq = 0;
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -174,13 +176,47 @@ static int peer_setup(p4b_ctx *c) {
 
 static int ctx_allreduce_op(p4b_ctx *c, double *d, int count, int op_max) {
     if (c->nranks == 1) return 0;
-    if (c->peer) return launch_allreduce(c->stream, d, count, op_max, c->peers, c->sync);
+    if (c->peer && count <= 3) return launch_allreduce(c->stream, d, count, op_max, c->peers, c->sync);
+    if (c->peer) {      // longer vectors (p4b_vec_mdot): three values at a time
+        for (int q = 0; q < count; q += 3)
+            P4B_CHECK(launch_allreduce(c->stream, d + q, count - q < 3 ? count - q : 3, op_max, c->peers, c->sync));
+        return 0;
+    }
     P4B_NCCL(g_nccl.AllReduce(d, d, (size_t)count, ncclFloat64, op_max ? ncclMax : ncclSum, c->comm, c->stream));
     return 0;
 }
-
-static int ctx_allreduce_op(p4b_ctx *c, double *d, int count, int op_max);
 static int ctx_allreduce(p4b_ctx *c, double *d, int count) { return ctx_allreduce_op(c, d, count, 0); }
+
+// Wait until the kernels have published sequence number `seq` into the context's HostPoll, then copy `count` values.
+// The host spins on pinned memory (no cudaStreamSynchronize); every ~65k spins it asks the stream whether it died.
+static int poll_wait(p4b_ctx *c, unsigned long long seq, int count, double *h) {
+    volatile HostPoll *hp = c->h_poll;
+    unsigned long spins = 0;
+    while (__atomic_load_n(&hp->seq, __ATOMIC_ACQUIRE) < seq) {
+        if ((++spins & 0xFFFFul) == 0) {
+            const cudaError_t e = cudaStreamQuery(c->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady)
+                return fail(70, "CUDA error %d (%s) while waiting for a device scalar", (int)e, cudaGetErrorString(e));
+            if (e == cudaSuccess && __atomic_load_n(&hp->seq, __ATOMIC_ACQUIRE) < seq)
+                return fail(70, "stream is idle but the device scalar was never published (sequence %llu)", seq);
+        }
+        __builtin_ia32_pause();
+    }
+    for (int i = 0; i < count; i++) h[i] = hp->v[i];
+    return 0;
+}
+
+// all-reduce `count` device scalars (sum or max) and hand them to the host: on the peer path one kernel does both
+static int allreduce_fetch(p4b_ctx *c, double *d, int count, int op_max, double *h) {
+    const unsigned long long seq = ++c->poll_seq;
+    if (c->nranks > 1 && c->peer && count <= 3) {
+        P4B_CHECK(launch_allreduce(c->stream, d, count, op_max, c->peers, c->sync, c->d_poll, seq));
+    } else {
+        P4B_CHECK(ctx_allreduce_op(c, d, count, op_max));
+        P4B_CHECK(launch_publish(c->stream, d, count, c->d_poll, seq));
+    }
+    return poll_wait(c, seq, count, h);
+}
 
 // ------------------------------------------------------------------------------------------------
 // grid -> level descriptor
@@ -274,6 +310,8 @@ struct Prof {
     std::vector<Rec> recs;
     std::vector<cudaEvent_t> pool;
     size_t used = 0;
+    cudaEvent_t last = nullptr;  // the newest recorded event, reusable as the next bracket's start while
+    long long last_launch = -1;  // g_launch_count still has this value (nothing launched since)
     p4b_kernel_stat stat[P4B_K_NCLASSES];
     p4b_kernel_stat lstat[P4B_MAX_LEVELS][P4B_K_NCLASSES];
 };
@@ -326,35 +364,58 @@ static const char *k_names[P4B_K_NCLASSES] = {"apply_dot", "residual", "cheb_zer
                                               "prolong_add", "axpy2", "dot2", "aypx", "resid_restrict", "xp_update", "r_update",
                                               "halo", "gather", "allreduce", "coarse_solve", "subcycle"};
 
-// RAII-free profiling bracket: only finest-level launches are timed
+// Profiling bracket: only finest-level launches are timed (prof.on == 1), or every launch (2 = trace).  Consecutive
+// brackets share one event (the end of a kernel is the start of the next when nothing was launched in between), which
+// halves the number of event records the GPU front end has to process between kernels -- at 8 GPUs, with ~60 us
+// kernels, two records per boundary were a measurable part of the step.  A host synchronisation point breaks the chain
+// (prof_break), so host latency is never booked on the next kernel.
 struct ProfScope {
     p4b_mg *m;
     int idx = -1;
-    ProfScope(p4b_mg *mg, int level, int cls) : m(mg) {
-        if (!m->prof.on || (m->prof.on == 1 && level != m->top)) return;
-        Prof &P = m->prof;
-        while (P.pool.size() < P.used + 2) {
+    static cudaEvent_t next_event(Prof &P) {
+        if (P.pool.size() < P.used + 1) {
             cudaEvent_t e;
             cudaEventCreate(&e);
             P.pool.push_back(e);
         }
+        return P.pool[P.used++];
+    }
+    ProfScope(p4b_mg *mg, int level, int cls) : m(mg) {
+        if (!m->prof.on || (m->prof.on == 1 && level != m->top)) return;
+        Prof &P = m->prof;
         Prof::Rec r;
         r.cls = cls;
         r.level = level;
-        r.a = P.pool[P.used++];
-        r.b = P.pool[P.used++];
+        if (P.last && P.last_launch == g_launch_count) {
+            r.a = P.last;
+        } else {
+            r.a = next_event(P);
+            cudaEventRecord(r.a, m->ctx->stream);
+            P.last = r.a;
+            P.last_launch = g_launch_count;
+        }
+        r.b = nullptr;
         const Level &L = m->lev[level];
         const double N = (double)L.d.nlocal();
         const double Nc = level > 0 ? (double)m->lev[level - 1].d.nglobal() / (m->ctx->nranks) : 0.0;
         r.bytes = alg_bytes(cls, N, Nc);
-        cudaEventRecord(r.a, m->ctx->stream);
         idx = (int)P.recs.size();
         P.recs.push_back(r);
     }
     ~ProfScope() {
-        if (idx >= 0) cudaEventRecord(m->prof.recs[idx].b, m->ctx->stream);
+        if (idx < 0) return;
+        Prof &P = m->prof;
+        if (P.last && P.last_launch == g_launch_count) {
+            P.recs[idx].b = P.last;           // an inner bracket ended on the same launch
+        } else {
+            P.recs[idx].b = next_event(P);
+            cudaEventRecord(P.recs[idx].b, m->ctx->stream);
+            P.last = P.recs[idx].b;
+            P.last_launch = g_launch_count;
+        }
     }
 };
+static inline void prof_break(p4b_mg *m) { m->prof.last = nullptr; }
 
 static void prof_collect(p4b_mg *m) {
     Prof &P = m->prof;
@@ -375,6 +436,7 @@ static void prof_collect(p4b_mg *m) {
     }
     P.recs.clear();
     P.used = 0;
+    P.last = nullptr;
 }
 
 // ghost-plane exchange of a ghosted vector on a distributed level ([PETSc] DMGlobalToLocal)
@@ -910,6 +972,9 @@ int p4b_ctx_create(int device, void *stream, p4b_ctx **out) {
     P4B_CUDA(cudaMalloc(&c->d_scal, sizeof(double) * 16));
     P4B_CUDA(cudaMemset(c->d_scal, 0, sizeof(double) * 16));
     P4B_CUDA(cudaMallocHost(&c->h_scal, sizeof(double) * 16));
+    P4B_CUDA(cudaHostAlloc((void **)&c->h_poll, sizeof(HostPoll), cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(c->h_poll, 0, sizeof(HostPoll));
+    P4B_CUDA(cudaHostGetDevicePointer((void **)&c->d_poll, c->h_poll, 0));
     P4B_CUDA(cudaEventCreate(&c->ev0));
     P4B_CUDA(cudaEventCreate(&c->ev1));
     *out = c;
@@ -936,7 +1001,7 @@ int p4b_ctx_destroy(p4b_ctx *c) {
     cudaFree(c->d_scal);
     cudaFreeHost(c->h_scal);
     if (c->d_mdot) cudaFree(c->d_mdot);
-    if (c->h_mdot) cudaFreeHost(c->h_mdot);
+    if (c->h_poll) cudaFreeHost(c->h_poll);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -1118,38 +1183,22 @@ int p4b_residual_restrict(p4b_ctx *c, const p4b_grid *gf, const double *b, const
     return rc;
 }
 
-static int fetch_scal(p4b_ctx *c, const double *d, int count, double *h) {
-    P4B_CUDA(cudaMemcpyAsync(c->h_scal, d, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
-    P4B_CUDA(cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < count; i++) h[i] = c->h_scal[i];
-    return 0;
-}
-
 int p4b_vec_dot(p4b_ctx *c, size_t n, const double *x, const double *y, double *res) {
     P4B_CHECK(launch_dotn(c->stream, (long long)n, x, y, c->d_scal + 8, c->red));
-    P4B_CHECK(ctx_allreduce(c, c->d_scal + 8, 1));
-    return fetch_scal(c, c->d_scal + 8, 1, res);
+    return allreduce_fetch(c, c->d_scal + 8, 1, 0, res);
 }
 // k dot products (X[i], y) with ONE read-back: the launches of the single dot, one after the other on the stream, each
 // into its own slot ([PETSc] VecMDot; the orthogonalisation of one GMRES step with classical Gram-Schmidt)
 int p4b_vec_mdot(p4b_ctx *c, size_t n, int k, const double *const *X, const double *y, double *res) {
     if (k <= 0) return 0;
     if (k > 64) return fail(62, "p4b_vec_mdot: at most 64 vectors");
-    if (!c->d_mdot) {
-        P4B_CUDA(cudaMalloc(&c->d_mdot, sizeof(double) * 64));
-        P4B_CUDA(cudaMallocHost(&c->h_mdot, sizeof(double) * 64));
-    }
+    if (!c->d_mdot) P4B_CUDA(cudaMalloc(&c->d_mdot, sizeof(double) * 64));
     for (int i = 0; i < k; i++) P4B_CHECK(launch_dotn(c->stream, (long long)n, X[i], y, c->d_mdot + i, c->red));
-    P4B_CHECK(ctx_allreduce(c, c->d_mdot, k));
-    P4B_CUDA(cudaMemcpyAsync(c->h_mdot, c->d_mdot, sizeof(double) * k, cudaMemcpyDeviceToHost, c->stream));
-    P4B_CUDA(cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < k; i++) res[i] = c->h_mdot[i];
-    return 0;
+    return allreduce_fetch(c, c->d_mdot, k, 0, res);
 }
 int p4b_vec_wrms2(p4b_ctx *c, size_t n, const double *x, const double *y, double atol, double rtol, double *res) {
     P4B_CHECK(launch_wrms(c->stream, (long long)n, x, y, atol, rtol, c->d_scal + 8, c->red));
-    P4B_CHECK(ctx_allreduce(c, c->d_scal + 8, 1));
-    return fetch_scal(c, c->d_scal + 8, 1, res);
+    return allreduce_fetch(c, c->d_scal + 8, 1, 0, res);
 }
 int p4b_vec_norm2(p4b_ctx *c, size_t n, const double *x, double *res) {
     P4B_CHECK(p4b_vec_dot(c, n, x, x, res));
@@ -1158,8 +1207,7 @@ int p4b_vec_norm2(p4b_ctx *c, size_t n, const double *x, double *res) {
 }
 int p4b_vec_norminf(p4b_ctx *c, size_t n, const double *x, double *res) {
     P4B_CHECK(launch_absmax(c->stream, (long long)n, x, c->d_scal + 8, c->red));
-    P4B_CHECK(ctx_allreduce_op(c, c->d_scal + 8, 1, 1));
-    return fetch_scal(c, c->d_scal + 8, 1, res);
+    return allreduce_fetch(c, c->d_scal + 8, 1, 1, res);
 }
 int p4b_vec_axpy(p4b_ctx *c, size_t n, double a, const double *x, double *y) {
     return launch_axpy(c->stream, (long long)n, a, x, y);
@@ -1455,11 +1503,23 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
     int q = 0;
     double h[2];
     P4B_CHECK(precond(S + 2 * q));
-    {
-        ProfScope ps(m, m->top, P4B_K_ALLREDUCE);
-        P4B_CHECK(ctx_allreduce(c, S + 2 * q, 2));
-    }
-    P4B_CHECK(fetch_scal(c, S + 2 * q, 2, h));
+    // (z,z), (z,r): all-reduced and published to pinned host memory by one kernel; the host polls (no stream sync)
+    auto reduce_fetch2 = [&](double *dots) -> int {
+        const unsigned long long seq = ++c->poll_seq;
+        {
+            ProfScope ps(m, m->top, P4B_K_ALLREDUCE);
+            if (c->nranks > 1 && c->peer) {
+                P4B_CHECK(launch_allreduce(st, dots, 2, 0, c->peers, c->sync, c->d_poll, seq));
+            } else {
+                P4B_CHECK(ctx_allreduce(c, dots, 2));
+                P4B_CHECK(launch_publish(st, dots, 2, c->d_poll, seq));
+            }
+        }
+        const int rc = poll_wait(c, seq, 2, h);
+        prof_break(m);
+        return rc;
+    };
+    P4B_CHECK(reduce_fetch2(S + 2 * q));
     double dp = sqrt(h[0]);
     R.rnorm0 = dp;
     R.hist[R.nhist++] = dp;
@@ -1508,11 +1568,7 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
         }
         q ^= 1;
         P4B_CHECK(precond(S + 2 * q));
-        {
-            ProfScope ps(m, m->top, P4B_K_ALLREDUCE);
-            P4B_CHECK(ctx_allreduce(c, S + 2 * q, 2));
-        }
-        P4B_CHECK(fetch_scal(c, S + 2 * q, 2, h));
+        P4B_CHECK(reduce_fetch2(S + 2 * q));
         dp = sqrt(h[0]);
         its++;
         if (R.nhist < P4B_MAX_HIST) R.hist[R.nhist++] = dp;

@@ -93,6 +93,15 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && P <= 8) ? 2 : 1) stencil_mar
     constexpr int Q = NT * P;
     constexpr int HZ = 3;                                                  // halo nodes a thread may have to zero
     const int tid = threadIdx.x;
+    // MG grids carry one extra column of CTAs: (nbands, 0) is the signalling CTA (comm.h port_signaller), the rest of
+    // the column exits at once
+    const unsigned int nbands = MG ? gridDim.x - 1u : gridDim.x;
+    const unsigned int n_port_ctas =
+        nbands * (gridDim.y == 1 ? 1u : (op.port.flag_lo != nullptr) + (op.port.flag_hi != nullptr));
+    if (MG && blockIdx.x == nbands) {
+        if (blockIdx.y == 0 && tid == 0 && n_port_ctas > 0u) port_signaller(op.port, n_port_ctas);
+        return;
+    }
     const int nx = L.nx;
     const int plane = L.nx * L.ny;
     const int q0 = blockIdx.x * Q;
@@ -118,7 +127,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && P <= 8) ? 2 : 1) stencil_mar
     // CTAs of the first / last chunk read u's ghost plane and push out's boundary plane
     const bool port_cta = MG && op.port.sync != nullptr && ((chunk == 0 && op.port.flag_lo != nullptr) ||
                                                       (chunk == (int)gridDim.y - 1 && op.port.flag_hi != nullptr));
-    if (MG) port_wait(op.port, port_cta);
+    if (MG) port_wait(op.port, port_cta, true);
 
     // plane t of this chunk, t = 0 .. T-1 (one extra plane on each side), is local plane k0 - 1 + t going up
     // and k1 - t going down
@@ -245,8 +254,6 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && P <= 8) ? 2 : 1) stencil_mar
 
     // the iteration after which both boundary planes of this CTA have been pushed
     const int t_sig = ((chunk == (int)gridDim.y - 1 && op.port.flag_hi != nullptr && !rev) || (op.port.opts & 2)) ? T - 2 : 1;
-    const unsigned int n_port_ctas =
-        gridDim.x * (gridDim.y == 1 ? 1u : (op.port.flag_lo != nullptr) + (op.port.flag_hi != nullptr));
     for (int t = 0; t + 1 < T; t++) {
         const int kg = kg0 + dir * t;         // global plane computed in this iteration (when t >= 1)
         int slot_n = slot_c + 1;
@@ -336,7 +343,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && P <= 8) ? 2 : 1) stencil_mar
         __syncthreads();                       // everyone is done with slot_c (and with plane 0 at t = 0)
         if (tid == 0) issue_next();
         // boundary planes are out: publish them (one thread of another warp than the copy producer's)
-        if (MG && port_cta && t == t_sig) port_signal_nosync(op.port, n_port_ctas, tid == NT - 32);
+        if (MG && port_cta && t == t_sig && tid == NT - 32) port_arrive(op.port);
         outp += dstep;
         if (HAS_B) bp += dstep;
         if (HAS_PM1) pp += dstep;
@@ -354,7 +361,7 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && P <= 8) ? 2 : 1) stencil_mar
     }
     if (MG && port_cta && T - 1 <= t_sig) {          // (a chunk too short to have reached t_sig inside the loop)
         __syncthreads();
-        port_signal_nosync(op.port, n_port_ctas, tid == NT - 32);
+        if (tid == NT - 32) port_arrive(op.port);
     }
     if (MODE == ST_APPLY_DOT || MODE == ST_LIN_PM1_DOT2) {
         // one partial (per value) per CTA, summed in fixed order by the last CTA to finish
@@ -362,8 +369,8 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && P <= 8) ? 2 : 1) stencil_mar
         __shared__ double red[2][NT / 32];
         __shared__ bool is_last;
         const int lane = tid & 31, wid = tid >> 5;
-        const unsigned int nblk = gridDim.x * gridDim.y;
-        const unsigned int bid = blockIdx.y * gridDim.x + blockIdx.x;
+        const unsigned int nblk = nbands * gridDim.y;
+        const unsigned int bid = blockIdx.y * nbands + blockIdx.x;
 #pragma unroll
         for (int v = 0; v < NV; v++) {
             const double s = warp_sum(dv[v]);
@@ -407,11 +414,11 @@ __global__ void __launch_bounds__(NT, (NT <= 256 && P <= 8) ? 2 : 1) stencil_mar
 // ---------------------------------------------------------------------------------------------
 // host side: eligibility, configuration, launch
 // ---------------------------------------------------------------------------------------------
-struct MarchTune { int P, NT, NS, enabled, min_plane; };
+struct MarchTune { int P, NT, NS, enabled, min_plane, alt; };
 
 static MarchTune &tune() {
     static MarchTune t = [] {
-        MarchTune x = {0, 0, 4, 1, 16384};   // P = 0: per-mode default
+        MarchTune x = {0, 0, 4, 1, 16384, 1};   // P = 0: per-mode default; alt = 1: 7 nodes/thread where the wave model prefers it
         if (const char *e = getenv("P4B_MARCH")) {       // "P,NT,NS" or "0" to disable (tuning / A-B runs)
             int a = 0, b = 0, c = 0;
             const int n = sscanf(e, "%d,%d,%d", &a, &b, &c);
@@ -431,6 +438,7 @@ int tune_march(const char *key, long v) {
     else if (k == "march_P") t.P = (int)v;
     else if (k == "march_NT") t.NT = (int)v;
     else if (k == "march_NS") t.NS = (int)v;
+    else if (k == "march_alt") t.alt = (int)v;
     else return 1;
     return 0;
 }
@@ -441,6 +449,42 @@ bool stencil_fast_eligible(const LevelDesc &L) {
     const long long plane = (long long)L.nx * L.ny;
     const bool big = L.ay ? plane >= t.min_plane : plane >= t.min_plane / 16;
     return t.enabled && L.ax && L.az && big && L.zm >= 8 && plane * (L.zm + 2) < (1LL << 31);
+}
+
+// Number of z chunks for bands of Q nodes on `slots` resident CTAs: minimise waves * (planes per chunk + pipeline fill).
+// Returns that cost (in plane-steps of one wave); *nchunks = the chunk count to launch.
+static double march_plan(int plane, int zm, int Q, long long slots, int *nchunks) {
+    const int bands = (plane + Q - 1) / Q;
+    int best_nc = 1;
+    double best_cost = 1e300;
+    for (int nc = 1; nc <= zm / 4 && nc <= 256; nc++) {
+        const int KC = (zm + nc - 1) / nc;
+        const int nce = (zm + KC - 1) / KC;
+        const long long ctas = (long long)bands * nce;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double cost = (double)waves * (KC + 2 + 1.5);   // +1.5: pipeline fill per CTA
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_nc = nce; }
+    }
+    *nchunks = best_nc;
+    return best_cost;
+}
+// Wave model of a whole launch: every resident CTA streams Q nodes per plane-step, so time ~ cost * Q * CTAs per SM.
+// Used to choose between 8 and 7 nodes per thread: on thin slabs (multi-GPU) 129 bands x 2 chunks of Q = 2048 fill only
+// 258 of the 296 CTA slots, 147 bands of Q = 1792 fill 294 (measured on a 513 x 513 x 65 slab: 16 N modes 7 % faster).
+static double march_model(int plane, int zm, int P, int NT, int sm_count) {
+    const int occ = NT <= 256 ? 2 : 1;
+    int nc;
+    return march_plan(plane, zm, P * NT, (long long)sm_count * occ, &nc) * (double)(P * NT) * occ;
+}
+static int sm_count_cached() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
 }
 
 template <int MODE, int P, int NT, bool MG>
@@ -468,27 +512,23 @@ static int launch_march_mg(cudaStream_t st, const LevelDesc &L, const StencilOp 
                                       (int)smem));
         attr_smem = smem;
     }
-    int occ = 1;
-    P4B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stencil_march_kernel<MODE, P, NT, MG>, NT, smem));
-    if (occ < 1) occ = 1;
-    const int bands = (plane + Q - 1) / Q;
-    const long long slots = (long long)sm_count * occ;
-    // number of z chunks: minimise waves * (KC + 2)
-    int best_nc = 1;
-    double best_cost = 1e300;
-    for (int nc = 1; nc <= L.zm / 4 && nc <= 256; nc++) {
-        const int KC = (L.zm + nc - 1) / nc;
-        const int nce = (L.zm + KC - 1) / KC;
-        const long long ctas = (long long)bands * nce;
-        const long long waves = (ctas + slots - 1) / slots;
-        const double cost = (double)waves * (KC + 2 + 1.5);   // +1.5: pipeline fill per CTA
-        if (cost < best_cost - 1e-9) { best_cost = cost; best_nc = nce; }
+    // occupancy does not change between launches of one instantiation with one stage size: ask once
+    static int occ_cached = 0;
+    static size_t occ_smem = 0;
+    if (!occ_cached || occ_smem != smem) {
+        int occ = 1;
+        P4B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stencil_march_kernel<MODE, P, NT, MG>, NT, smem));
+        occ_cached = occ < 1 ? 1 : occ;
+        occ_smem = smem;
     }
+    const int bands = (plane + Q - 1) / Q;
+    int best_nc = 1;
+    march_plan(plane, L.zm, Q, (long long)sm_count * occ_cached, &best_nc);
     cfg.KC = (L.zm + best_nc - 1) / best_nc;
     const int nchunks = (L.zm + cfg.KC - 1) / cfg.KC;
     if ((MODE == ST_APPLY_DOT || MODE == ST_LIN_PM1_DOT2) && bands * nchunks > red.max_blocks)
         return fail(63, "reducer scratch too small");
-    dim3 grid(bands, nchunks);
+    dim3 grid(bands + (MG ? 1 : 0), nchunks);      // MG: + the column that holds the signalling CTA
     stencil_march_kernel<MODE, P, NT, MG><<<grid, NT, smem, st>>>(L, op, cfg, red.partials, red.ticket);
     P4B_LAUNCH_CHECK();
     return 0;
@@ -526,12 +566,21 @@ int launch_stencil_fast(cudaStream_t st, const LevelDesc &L, const StencilOp &op
         // wants 4 nodes/thread x 512 threads, the others 8 nodes/thread x 256 threads (2 CTAs/SM)
         if (op.mode == ST_LIN_PM1) return launch_march<ST_LIN_PM1, 4, 512>(st, L, op, red, t.NS);
         if (op.mode == ST_LIN_PM1_DOT2) return launch_march<ST_LIN_PM1_DOT2, 4, 512>(st, L, op, red, t.NS);
-        // with the slab-exchange code the two-operand mode no longer fits 128 registers at 8 nodes/thread
-        if (op.mode == ST_LIN && op.port.sync) return launch_march<ST_LIN, 4, 512>(st, L, op, red, t.NS);
+        // with the slab-exchange code the two-operand mode no longer fits 128 registers at 8 nodes/thread; at 7 it does
+        // (measured on thin slabs, profiles/r02_exchange.md: 0.084 ms against 0.098 ms with 4 x 512)
+        if (op.mode == ST_LIN && op.port.sync && op.port.push) return launch_march<ST_LIN, 7, 256>(st, L, op, red, t.NS);
+        // the 16 N modes are the ones the wave model describes (measured: the two-operand mode is as fast either way on
+        // thin slabs and 8 % slower with 7 nodes/thread on 513 planes)
+        const int plane = L.nx * L.ny, sms = sm_count_cached();
+        const bool one_operand = op.mode == ST_APPLY || op.mode == ST_APPLY_DOT || op.mode == ST_LIN_BU;
+        if (t.alt && one_operand && march_model(plane, L.zm, 7, 256, sms) < 0.97 * march_model(plane, L.zm, 8, 256, sms))
+            return launch_march_mode<7, 256>(st, L, op, red, t.NS);
         return launch_march_mode<8, 256>(st, L, op, red, t.NS);
     }
     if (t.P == 4 && t.NT == 512) return launch_march_mode<4, 512>(st, L, op, red, t.NS);
     if (t.P == 8 && t.NT == 256) return launch_march_mode<8, 256>(st, L, op, red, t.NS);
+    if (t.P == 7 && t.NT == 256) return launch_march_mode<7, 256>(st, L, op, red, t.NS);
+    if (t.P == 7 && t.NT == 512) return launch_march_mode<7, 512>(st, L, op, red, t.NS);
     return fail(62, "P4B_MARCH=%d,%d is not instantiated", t.P, t.NT);
 }
 

@@ -72,7 +72,8 @@ def test_slab_solve_matches_c_oracle_at_257(nproc):
         pytest.skip("needs %d GPUs" % nproc)
     r = run_worker(nproc, "--refine", 7, "--levels", 6, "--rtol", 1e-10, "--c-oracle")
     assert r["its"] == r["oracle_its"]
-    assert r["hist_rel"] is not None and r["hist_rel"] < 1e-10 and r["sol_rel"] < 1e-12 and r["bnorm_rel"] < 1e-13
+    assert r["hist_rel"] is not None and r["hist_rel"] < 1e-10 and r["sol_rel"] < 1e-12
+    assert r["bnorm_rel"] < 1e-10          # (the C oracle sums 17 M squares per-thread serially: its own rounding)
 
 
 def test_peer_transport_is_bit_identical_to_nccl_on_two_ranks():

@@ -339,5 +339,14 @@ def test_errors_are_loud(ctx):
         Multigrid(ctx, L.refined_grid(2, 2), mg_options(levels=9))
     with pytest.raises(L.P4BError):
         fish_main("-fsh_dim 4 -pc_type mg", ctx)
+    # a coarsest grid too large for the dense inverse: refused when the multigrid cycle asks for it (a one-level
+    # hierarchy of any size is what -pc_type none / jacobi run on)
+    mg = Multigrid(ctx, L.refined_grid(3, 5), mg_options(levels=2))
+    n = mg.nlocal
+    b, x = ctx.empty(n), ctx.empty(n)
+    b.fill_(1.0)
     with pytest.raises(L.P4BError, match="coarsest"):
-        Multigrid(ctx, L.refined_grid(3, 5), mg_options(levels=2))
+        mg.cg_solve(b, x, rtol=1e-5)
+    res = mg.cg_solve(b, x, rtol=1e-5, pc="jacobi")
+    assert res.reason == L.CONVERGED_RTOL
+    mg.close()
