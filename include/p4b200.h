@@ -184,6 +184,8 @@ int p4b_vec_set(p4b_ctx *ctx, size_t n, double a, double *y);
 /* ---- the fish problem on device ---- */
 /* f = f_rhs, gb = g_bdry = u_exact sampled at every node (any of the three may be NULL) */
 int p4b_fish_sample(p4b_ctx *ctx, const p4b_grid *g, int problem, double *f, double *gb);
+/* gonboundary: bit 0 = g on the boundary nodes (-fsh_initial_gonboundary); bit 1 = keep what u holds elsewhere (the
+ * RANDOM branch: the caller filled u with the VecSetRandom stream) instead of zeros */
 int p4b_initial_state(p4b_ctx *ctx, const p4b_grid *g, const double *gb, int gonboundary, double *u);
 int p4b_poisson_function(p4b_ctx *ctx, const p4b_grid *g, const double *u, const double *f,
                          const double *gb, double *F);
@@ -237,6 +239,19 @@ int p4b_mg_fish_setup(p4b_mg *mg, int problem, int gonboundary, double *b, doubl
 int p4b_minimal_sample(p4b_ctx *ctx, int mx, int my, int problem, double tent_H, double catenoid_c, double *g);
 int p4b_minimal_function(p4b_ctx *ctx, int mx, int my, double q, const double *u, const double *g, double *FF);
 int p4b_pattern_initial_state(p4b_ctx *ctx, int mx, int my, double L, double *Y);
+/* the same with noise (c/ch5/pattern.c:159-165, -ptn_noisy_init): noise (device, 2*mx*my doubles in [0,1), the
+ * VecSetRandom stream in natural (u,v)-interleaved order) is scaled by level and the patch added on top of it */
+int p4b_pattern_initial_state_noisy(p4b_ctx *ctx, int mx, int my, double L, const double *noise, double level, double *Y);
+
+/* ---- [PETSc] PetscRandom, default type rander48 (VecSetRandom at c/ch5/pattern.c:163 and
+ * c/ch6/poissonfunctions.c:268-270).  Host-only.  PETSc's generator is the 48-bit linear congruential generator of
+ * drand48 -- X <- (0x5DEECE66D X + 0xB) mod 2^48, X0 = (seed << 16) | 0x330E, value X / 2^48 -- seeded with
+ * 0x12345678 + 76543 * rank.  Restated from PETSc's rander48.c as remembered; PETSc is not installable here and no
+ * golden of the reference uses a random vector, so equality with PETSc's stream is UNPINNED (tests pin it on glibc's
+ * srand48/drand48, the same recurrence). */
+unsigned long long p4b_rander48_seed(unsigned long seed);
+/* n values in [0,1) into out (host); *state advances */
+int p4b_rander48_fill(unsigned long long *state, size_t n, double *out);
 int p4b_pattern_rhsfunction(p4b_ctx *ctx, int mx, int my, double phi, double kappa, const double *Y, double *G);
 int p4b_pattern_ifunction(p4b_ctx *ctx, int mx, int my, double L, double Du, double Dv, const double *Y,
                           const double *Ydot, double *F);

@@ -46,6 +46,17 @@ int p4b_tune(const char *key, long value) {
     return fail(62, "stand-in: unknown tuning key");
 }
 long long p4b_launch_count(void) { return 0; }
+// the VecSetRandom stream is host code in the product too (mg.cu): the same drand48 recurrence
+unsigned long long p4b_rander48_seed(unsigned long seed) { return (((unsigned long long)(seed & 0xffffffffUL)) << 16) | 0x330EULL; }
+int p4b_rander48_fill(unsigned long long *state, size_t n, double *out) {
+    unsigned long long x = *state & 0xFFFFFFFFFFFFULL;
+    for (size_t i = 0; i < n; i++) {
+        x = (0x5DEECE66DULL * x + 0xBULL) & 0xFFFFFFFFFFFFULL;
+        out[i] = (double)x * (1.0 / 281474976710656.0);
+    }
+    *state = x;
+    return 0;
+}
 int p4b_ctx_create(int, void *, p4b_ctx **ctx) { *ctx = new p4b_ctx{0}; return 0; }
 int p4b_ctx_destroy(p4b_ctx *ctx) { delete ctx; return 0; }
 int p4b_malloc(p4b_ctx *, size_t bytes, void **dptr) { *dptr = malloc(bytes ? bytes : 1); return *dptr ? 0 : 55; }

@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(256) initial_state_kernel(const LevelDesc L, c
     if (n >= L.nlocal()) return;
     int i, j, k;
     node_of(L, n, i, j, k);
-    u[n] = (gonboundary && on_bdry(L, i, j, k)) ? gb[n] : 0.0;
+    if ((gonboundary & 1) && on_bdry(L, i, j, k)) u[n] = gb[n];
+    else if (!(gonboundary & 2)) u[n] = 0.0;
 }
 
 // F(u).  u must have readable ghost planes when the slab is interior (k-1, k+1 reads).

@@ -83,7 +83,8 @@ int launch_poisson_function(cudaStream_t st, const LevelDesc &L, int dim, double
 int launch_minimal_sample(cudaStream_t st, int mx, int my, int zs, int zm, int problem, double tent_H, double c, double *g);
 int launch_minimal_function(cudaStream_t st, int mx, int my, int zs, int zm, double q, const double *u, const double *g,
                             double *FF);
-int launch_pattern_init(cudaStream_t st, int mx, int my, double L, double *Y);
+int launch_pattern_init(cudaStream_t st, int mx, int my, double L, double *Y, const double *noise = nullptr,
+                        double level = 0.0);
 int launch_pattern_rhs(cudaStream_t st, int n, double phi, double kappa, const double *Y, double *G);
 int launch_pattern_ifunction(cudaStream_t st, int mx, int my, double Cu, double Cv, int use_shift, double shift,
                              const double *Y, const double *Ydot, double *F);

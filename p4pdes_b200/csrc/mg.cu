@@ -1667,6 +1667,24 @@ int p4b_pattern_initial_state(p4b_ctx *c, int mx, int my, double L, double *Y) {
     if (mx < 3 || my < 3) return fail(60, "periodic grid needs at least 3 nodes per dimension");
     return launch_pattern_init(c->stream, mx, my, L, Y);
 }
+int p4b_pattern_initial_state_noisy(p4b_ctx *c, int mx, int my, double L, const double *noise, double level, double *Y) {
+    if (mx < 3 || my < 3) return fail(60, "periodic grid needs at least 3 nodes per dimension");
+    return launch_pattern_init(c->stream, mx, my, L, Y, noise, level);
+}
+// [PETSc] rander48 (the default PetscRandom type): drand48's 48-bit linear congruential generator, see p4b200.h
+unsigned long long p4b_rander48_seed(unsigned long seed) {
+    return (((unsigned long long)(seed & 0xffffffffUL)) << 16) | 0x330EULL;
+}
+int p4b_rander48_fill(unsigned long long *state, size_t n, double *out) {
+    if (!state || (n && !out)) return fail(62, "null argument");
+    unsigned long long x = *state & 0xFFFFFFFFFFFFULL;
+    for (size_t i = 0; i < n; i++) {
+        x = (0x5DEECE66DULL * x + 0xBULL) & 0xFFFFFFFFFFFFULL;
+        out[i] = (double)x * (1.0 / 281474976710656.0);      // X / 2^48: exact in fp64
+    }
+    *state = x;
+    return 0;
+}
 int p4b_pattern_rhsfunction(p4b_ctx *c, int mx, int my, double phi, double kappa, const double *Y, double *G) {
     return launch_pattern_rhs(c->stream, mx * my, phi, kappa, Y, G);
 }

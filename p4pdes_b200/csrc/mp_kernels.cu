@@ -98,19 +98,22 @@ int launch_minimal_function(cudaStream_t st, int mx, int my, int zs, int zm, dou
 }
 
 // ---------------------------------------------------------------------------------------------- pattern.c
-__global__ void __launch_bounds__(256) pattern_init_kernel(int mx, int my, double L, double2 *__restrict__ Y) {
+__global__ void __launch_bounds__(256) pattern_init_kernel(int mx, int my, double L, const double2 *__restrict__ noise,
+                                                            double level, double2 *__restrict__ Y) {
     const int n = blockIdx.x * 256 + threadIdx.x;
     if (n >= mx * my) return;
     const int j = n / mx, i = n - j * mx;
     const double x = i * (L / mx), y = j * (L / my);
     const double ledge = (L - 0.5) / 2.0, redge = L - ledge;
     const double PI = 3.14159265358979323846264338327950288;
-    double v = 0.0;
+    // pattern.c:159-165: Y = level * random, then v += patch, u += 1 - 2 v (the v that already carries its noise)
+    double u = 0.0, v = 0.0;
+    if (noise) { const double2 r = noise[n]; u = level * r.x; v = level * r.y; }
     if (x >= ledge && x <= redge && y >= ledge && y <= redge) {
         const double sx = sin(4.0 * PI * x), sy = sin(4.0 * PI * y);
-        v = 0.5 * sx * sx * sy * sy;
+        v += 0.5 * sx * sx * sy * sy;
     }
-    Y[n] = make_double2(1.0 - 2.0 * v, v);
+    Y[n] = make_double2(u + (1.0 - 2.0 * v), v);
 }
 
 __global__ void __launch_bounds__(256) pattern_rhs_kernel(int n, double phi, double kappa, const double2 *__restrict__ Y,
@@ -144,8 +147,9 @@ __global__ void __launch_bounds__(256) pattern_ifunction_kernel(int mx, int my, 
     F[n] = make_double2(d.x - Cu * lapu, d.y - Cv * lapv);
 }
 
-int launch_pattern_init(cudaStream_t st, int mx, int my, double L, double *Y) {
-    pattern_init_kernel<<<(mx * my + 255) / 256, 256, 0, st>>>(mx, my, L, reinterpret_cast<double2 *>(Y));
+int launch_pattern_init(cudaStream_t st, int mx, int my, double L, double *Y, const double *noise, double level) {
+    pattern_init_kernel<<<(mx * my + 255) / 256, 256, 0, st>>>(mx, my, L, reinterpret_cast<const double2 *>(noise), level,
+                                                               reinterpret_cast<double2 *>(Y));
     P4B_LAUNCH_CHECK();
     return 0;
 }

@@ -177,6 +177,17 @@ class Context:
     def pattern_initial_state(self, mx, my, Lside, Y):
         L.check(self.lib.p4b_pattern_initial_state(self.h, mx, my, Lside, Y.data_ptr()))
 
+    def rander48(self, n, seed=0x12345678):
+        """n values of the VecSetRandom stream ([PETSc] rander48 restated, include/p4b200.h) as a device tensor."""
+        state = C.c_ulonglong(self.lib.p4b_rander48_seed(seed))
+        host = torch.empty(n, dtype=torch.float64)
+        L.check(self.lib.p4b_rander48_fill(C.byref(state), n, host.data_ptr()))
+        return host.to(self.device)
+
+    def pattern_initial_state_noisy(self, mx, my, Lside, level, Y):
+        noise = self.rander48(2 * mx * my)
+        L.check(self.lib.p4b_pattern_initial_state_noisy(self.h, mx, my, Lside, noise.data_ptr(), level, Y.data_ptr()))
+
     def pattern_ifunction(self, mx, my, Lside, Du, Dv, Y, Ydot, F):
         L.check(self.lib.p4b_pattern_ifunction(self.h, mx, my, Lside, Du, Dv, Y.data_ptr(), Ydot.data_ptr(), F.data_ptr()))
 
@@ -436,8 +447,8 @@ def parse_options(argv) -> FishOptions:
         raise L.P4BError("cx=cy=cz=1 required for problem MANUEXP")              # fish.c:192
     if o.problem not in L.PROBLEMS:
         raise L.P4BError("unknown -fsh_problem %s" % o.problem)
-    if o.initial_type != "zeros":
-        raise L.P4BError("-fsh_initial_type random needs PETSc's rander48 stream; only zeros is provided")
+    if o.initial_type not in ("zeros", "random"):
+        raise L.P4BError("unknown -fsh_initial_type %s (zeros, random)" % o.initial_type)
     if o.ksp_type != "cg":
         raise L.P4BError("only -ksp_type cg is provided on the device")
     if o.pc_type not in ("mg", "jacobi", "none"):
@@ -492,7 +503,11 @@ def fish_main(argv, ctx: Context | None = None, keep_solution=False, echo=False)
     n = g.n
     f, gb, u, F = ctx.empty(n), ctx.empty(n), ctx.empty(n), ctx.empty(n)
     ctx.fish_sample(g, o.problem, f, gb)                       # f_rhs, g_bdry tables (fish.c:115-123)
-    ctx.initial_state(g, gb, o.gonboundary, u)                 # InitialState (fish.c:238)
+    if o.initial_type == "random":                             # poissonfunctions.c:267-271: VecSetRandom, then g on the boundary
+        u.copy_(ctx.rander48(n))
+        ctx.initial_state(g, gb, int(o.gonboundary) | 2, u)
+    else:
+        ctx.initial_state(g, gb, o.gonboundary, u)             # InitialState (fish.c:238)
     lines = []
 
     def out(s):

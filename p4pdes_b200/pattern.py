@@ -21,7 +21,7 @@ pattern.c:main -- periodic 2-dof DMDA, banner, InitialState, TSSolve -- and prin
                            enters: the reaction is explicit); the embedded 2nd-order solution gives the error estimate,
                            p4b_vec_wrms2 its weighted norm ([PETSc] TSErrorWeightedNorm2).
 
-BDF and `-ptn_noisy_init` (PETSc's random stream) are not provided.  No CPU path: `ops` must be a device Context (tests/ substitutes a NumPy
+`-ptn_noisy_init` uses the restated rander48 stream (unpinned, include/p4b200.h).  No CPU path: `ops` must be a device Context (tests/ substitutes a NumPy
 stand-in to exercise this file's control flow without a GPU).
 """
 from __future__ import annotations
@@ -45,6 +45,8 @@ class PatternOptions:
     kappa: float = 0.06
     no_rhsjacobian: bool = False
     call_back_report: bool = False
+    noisy_init: float = 0.0         # -ptn_noisy_init (pattern.c:72,159-165): uniform noise on [0, level] from the
+                                    # VecSetRandom stream ([PETSc] rander48, restated and unpinned: include/p4b200.h)
     grid_x: int = 3
     grid_y: int = 3
     refine: int = 0
@@ -81,7 +83,7 @@ def parse_options(argv) -> PatternOptions:
              "-ts_monitor": "ts_monitor", "-snes_converged_reason": "snes_converged_reason",
              "-ksp_converged_reason": "ksp_converged_reason", "-log_view": "log_view"}
     valued = {"-ptn_L": ("L", float), "-ptn_Du": ("Du", float), "-ptn_Dv": ("Dv", float), "-ptn_phi": ("phi", float),
-              "-ptn_kappa": ("kappa", float), "-da_grid_x": ("grid_x", int), "-da_grid_y": ("grid_y", int),
+              "-ptn_kappa": ("kappa", float), "-ptn_noisy_init": ("noisy_init", float), "-da_grid_x": ("grid_x", int), "-da_grid_y": ("grid_y", int),
               "-da_refine": ("refine", int), "-ts_type": ("ts_type", str), "-ts_dt": ("ts_dt", float),
               "-ts_max_time": ("ts_max_time", float), "-ts_max_steps": ("ts_max_steps", int), "-pc_type": ("pc_type", str),
               "-ts_rtol": ("ts_rtol", float), "-ts_atol": ("ts_atol", float),
@@ -105,8 +107,8 @@ def parse_options(argv) -> PatternOptions:
             if argv[i + 1] not in accepted[a]:
                 raise ValueError("%s %s: the device path provides %s only" % (a, argv[i + 1], "|".join(accepted[a])))
             i += 2
-        elif a in ("-ptn_noisy_init", "-ptn_no_ijacobian"):
-            raise ValueError("%s is not provided by the device path (PETSc random stream / finite-difference IJacobian)" % a)
+        elif a == "-ptn_no_ijacobian":
+            raise ValueError("%s is not provided by the device path (finite-difference IJacobian)" % a)
         else:
             raise ValueError("unknown or unsupported option %s" % a)
     if o.ts_type not in ("arkimex", "beuler", "cn", "bdf"):
@@ -273,7 +275,13 @@ def _pattern_native(opt: PatternOptions, ctx, out) -> PatternReport:
     res = L.PatternResult()
     cb = L.LINE_FN(lambda line, _ctx: out(line.decode()))
     t0 = time.perf_counter()
-    L.check(ctx.lib.p4b_pattern_solve(ctx.h, C.byref(o), cb, None, Y.data_ptr(), Y.numel(), C.byref(res)))
+    if opt.noisy_init > 0.0:        # the caller's initial state: what the shim's TSSolve does with pattern.c's Vec
+        out("running on %d x %d grid with square cells of side h = %.6f ..." % (m, m, opt.L / m))
+        initial_state(ctx, opt, m, Y)
+        L.check(ctx.lib.p4b_pattern_solve_from(ctx.h, C.byref(o), Y.data_ptr(), cb, None, Y.data_ptr(), Y.numel(),
+                                               C.byref(res)))
+    else:
+        L.check(ctx.lib.p4b_pattern_solve(ctx.h, C.byref(o), cb, None, Y.data_ptr(), Y.numel(), C.byref(res)))
     seconds = time.perf_counter() - t0
     steps = [(res.step_t[k], res.step_dt[k], res.step_newton[k]) for k in range(min(res.nsteps, 512))]
     if opt.log_view:
@@ -282,6 +290,14 @@ def _pattern_native(opt: PatternOptions, ctx, out) -> PatternReport:
     rep = PatternReport(m=res.m, steps=steps, Y=Y, seconds=seconds, lines=None)
     rep.rejected = res.rejected
     return rep
+
+
+def initial_state(ops, opt, m, Y):
+    """InitialState (pattern.c:146-179), with -ptn_noisy_init the noise of VecSetRandom underneath the patch."""
+    if opt.noisy_init > 0.0:
+        ops.pattern_initial_state_noisy(m, m, opt.L, opt.noisy_init, Y)
+    else:
+        ops.pattern_initial_state(m, m, opt.L, Y)
 
 
 def pattern_main(argv, ops, echo=False, native=False) -> PatternReport:
@@ -321,7 +337,7 @@ def pattern_main(argv, ops, echo=False, native=False) -> PatternReport:
     affine = ops.empty(n) if theta != 1.0 else None
     y, Jy, w, gnew = ops.empty(n), ops.empty(n), ops.empty(n), ops.empty(n)
     work = [ops.empty(n) for _ in range(opt.gmres_restart + 1)]
-    ops.pattern_initial_state(m, m, opt.L, Y)                                                          # :146-179
+    initial_state(ops, opt, m, Y)                                                                      # :146-179
     t0 = time.perf_counter()
     t, k, steps = 0.0, 0, []
     dt_last = opt.ts_dt
@@ -443,7 +459,7 @@ def _bdf(ops, opt: PatternOptions, levels, m, out, lines, order=2) -> PatternRep
     gwork = [ops.empty(n) for _ in range(opt.gmres_restart + 1)]
     tm, wk = [0.0] * 8, [ops.empty(n) for _ in range(8)]
     st = dict(k=0, n=0)
-    ops.pattern_initial_state(m, m, opt.L, Yacc)
+    initial_state(ops, opt, m, Yacc)
     t0 = time.perf_counter()
     tmax = opt.ts_max_time
     t, k, h, steps, rejected = 0.0, 0, min(opt.ts_dt, tmax), [], 0
@@ -626,7 +642,7 @@ def _arkimex(ops, opt: PatternOptions, levels, m, out, lines) -> PatternReport:
     FE = [ops.empty(n) for _ in range(4)]
     work = [ops.empty(n) for _ in range(opt.gmres_restart + 1)]
     ops.set(0.0, zero)
-    ops.pattern_initial_state(m, m, opt.L, Y)
+    initial_state(ops, opt, m, Y)
     t0 = time.perf_counter()
     # ([PETSc] TSSolve: TS_EXACTFINALTIME_MATCHSTEP clips the first step to the final time)
     t, k, h, steps, rejected, ksp_total = 0.0, 0, min(opt.ts_dt, opt.ts_max_time), [], 0, 0

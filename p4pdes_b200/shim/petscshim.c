@@ -605,12 +605,30 @@ PetscErrorCode VecSet(Vec x, PetscScalar a) {
     x->valid = LOC_HOST;
     return 0;
 }
-PetscErrorCode PetscRandomCreate(MPI_Comm comm, PetscRandom *r) { (void)comm; *r = NULL; return 0; }
-PetscErrorCode PetscRandomDestroy(PetscRandom *r) { *r = NULL; return 0; }
+/* [PETSc] PetscRandom, default type rander48: the drand48 recurrence seeded 0x12345678 (+ 76543 * rank); restated from
+ * memory of PETSc's rander48.c, UNPINNED (no PETSc here, no golden uses a random vector): include/p4b200.h */
+struct _p_PetscRandom { unsigned long long state; };
+static struct _p_PetscRandom g_default_random;
+static int g_default_random_set = 0;
+PetscErrorCode PetscRandomCreate(MPI_Comm comm, PetscRandom *r) {
+    (void)comm;
+    *r = (PetscRandom)malloc(sizeof(struct _p_PetscRandom));
+    if (!*r) SHIM_ERR(55, "out of memory");
+    (*r)->state = p4b_rander48_seed(0x12345678UL);
+    return 0;
+}
+PetscErrorCode PetscRandomDestroy(PetscRandom *r) {
+    if (r && *r) { free(*r); *r = NULL; }
+    return 0;
+}
 PetscErrorCode VecSetRandom(Vec x, PetscRandom r) {
-    (void)x; (void)r;
-    SHIM_ERR(56, "VecSetRandom needs PETSc's rander48 stream, which the shim does not reproduce "
-                 "(-fsh_initial_type random is not provided)");
+    if (!r) {       /* [PETSc] VecSetRandom(x, NULL): one library-owned generator, its stream continues across calls */
+        if (!g_default_random_set) { g_default_random.state = p4b_rander48_seed(0x12345678UL); g_default_random_set = 1; }
+        r = &g_default_random;
+    }
+    P4B(p4b_rander48_fill(&r->state, x->n, x->h));
+    x->valid = LOC_HOST;
+    return 0;
 }
 PetscErrorCode VecAXPY(Vec y, PetscScalar a, Vec x) {
     if (x->n != y->n) SHIM_ERR(75, "VecAXPY: incompatible vector sizes");

@@ -150,6 +150,19 @@ class FakeOps:
     def pattern_initial_state(self, mx, my, Lside, Y):
         Y.a[:] = mpo.pattern_initial_state(mx, my, Lside).ravel()
 
+    def pattern_initial_state_noisy(self, mx, my, Lside, level, Y):
+        # pattern.c:159-175 on the VecSetRandom stream (host code of the library: loads without a GPU)
+        import ctypes as C
+        from p4pdes_b200 import lib as L
+        lib = L.load()
+        state = C.c_ulonglong(lib.p4b_rander48_seed(0x12345678))
+        r = np.empty(2 * mx * my)
+        L.check(lib.p4b_rander48_fill(C.byref(state), r.size, r.ctypes.data))
+        y = mpo.pattern_initial_state(mx, my, Lside).reshape(-1, 2)
+        r = level * r.reshape(-1, 2)
+        v = y[:, 1] + r[:, 1]
+        Y.a[:] = np.stack([r[:, 0] + 1.0 - 2.0 * v, v], axis=1).ravel()
+
     def pattern_ifunction(self, mx, my, Lside, Du, Dv, Y, Ydot, F):
         F.a[:] = mpo.pattern_ifunction(Y.a.reshape(my, mx, 2), Ydot.a.reshape(my, mx, 2), Lside, Du, Dv).ravel()
 

@@ -58,7 +58,7 @@ def test_driver_matches_oracle(argv, okw):
 @pytest.mark.parametrize("argv,msg", [
     ("-da_refine 2 -ts_type rk", "arkimex"),
     ("-ts_type beuler -pc_type ilu", "sequential"),
-    ("-ts_type beuler -ptn_noisy_init 0.2", "not provided"),
+    ("-ts_type beuler -ptn_no_ijacobian", "not provided"),
     ("-ts_type beuler -da_grid_x 4 -da_grid_y 6", "requires mx == my"),   # pattern.c:89
 ])
 def test_error_paths(argv, msg):

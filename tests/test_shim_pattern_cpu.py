@@ -94,7 +94,6 @@ def test_model_parameters_are_identified_from_the_callbacks(exe):
     ("-da_refine 2 -pc_type mg", 56, "SOR"),
     ("-da_refine 2 -pc_type none -ts_type rk", 56, "-ts_type rk is not provided"),
     ("-da_refine 2 -pc_type none -ptn_no_ijacobian", 56, "no IJacobian callback registered"),
-    ("-da_refine 2 -pc_type none -ptn_noisy_init 0.2", 56, "VecSetRandom"),
     ("-da_grid_x 4 -da_refine 2 -pc_type none", 1, "pattern.c requires mx == my"),
     ("-da_grid_x 64 -da_grid_y 64" + MG, 61, "coarser -da_grid"),
 ])
