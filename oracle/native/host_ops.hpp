@@ -39,7 +39,9 @@ struct HostOps {
     void copy(size_t n, const double *x, double *y) { memmove(y, x, sizeof(double) * n); }
     void set(size_t n, double a, double *y) { for (size_t i = 0; i < n; i++) y[i] = a; }
     void user_monitor(int, int, int, double, int, const double *) {}
+    bool verify_converged(int, int, const double *, const double *) { return true; }
     void set_linearisation(const double *) {}
+    void set_time(double) {}
 
     // c/ch7/minimal.c:27-42  g_bdry_tent / g_bdry_catenoid at every node of the unit square
     void minimal_sample(int mx, int my, int problem, double H, double c, double *g) {
@@ -404,17 +406,19 @@ struct HostCallbackPatternOps : HostOps {
         const size_t n = (size_t)2 * m * m;
         std::vector<double> y(Y, Y + n), d(Ydot, Ydot + n), f(n);
         callbacks++;
-        if (ifn(user, m, 0.0, y.data(), d.data(), f.data()) && !err) err = 65;
+        if (ifn(user, m, tcur, y.data(), d.data(), f.data()) && !err) err = 65;
         memcpy(F, f.data(), sizeof(double) * n);
     }
     void pattern_rhsfunction(int m, const PO &, const double *Y, double *G) {
         const size_t n = (size_t)2 * m * m;
         std::vector<double> y(Y, Y + n), g(n);
         callbacks++;
-        if (gfn(user, m, 0.0, y.data(), g.data()) && !err) err = 65;
+        if (gfn(user, m, tcur, y.data(), g.data()) && !err) err = 65;
         memcpy(G, g.data(), sizeof(double) * n);
     }
     void set_linearisation(const double *Y) { lin = Y; r0_for = nullptr; }
+    double tcur = 0.0;
+    void set_time(double t) { tcur = t; }
     void resid(int m, const PO &o, double shift, bool rhs, const double *W, double *out) {
         const size_t n = (size_t)2 * m * m;
         wD.resize(n);

@@ -100,6 +100,7 @@ int p4b_snes2d_solve_monitored(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_res
             ops.monitor = [&](int mx, int my, int its, double fnorm, int tab, const double *uh) {
                 return monitor(user, mx, my, its, fnorm, tab, uh);
             };
+        ops.callback = resid;                   // re-verified at the converged iterate of every grid, as nk_device.cu does
         nk::MinimalOpts o2 = o;
         o2.q = model.q;
         g_route = 1;
@@ -111,7 +112,17 @@ int p4b_snes2d_solve_monitored(p4b_ctx *c, const p4b_minimal_opts *opts, p4b_res
             else memcpy(u_out_host, u, sizeof(double) * n);
         }
         if (u) ops.release(u);
-    } else {
+        u = nullptr;
+        if (rc == 68) {
+            fprintf(stderr, "[p4b200] SNES: the residual callback matched the library's kernel at the probes but not at a "
+                            "converged iterate (deviation %.3e): solving again with the callback evaluated on the host\n",
+                    ops.verify_worst);
+            g_route = 2;
+            rc = 0;
+        }
+    }
+    if (g_route != 1) {
+        g_route = 0;
         HostCallbackOps ops;
         ops.cgs = g_cgs != 0;
         ops.fn = residual;

@@ -65,6 +65,7 @@ struct DeviceOps {
     }
     void inject2d(int cmx, int cmy, const double *uf, double *uc) { chk(p4b_inject2d(c, cmx, cmy, uf, uc)); }
     void user_monitor(int, int, int, double, int, const double *) {}      // only the callback form has one (CallbackOps)
+    bool verify_converged(int, int, const double *, const double *) { return true; }   // only ModelOps has something to verify
     static p4b_grid grid2d(int mx, int my) {
         p4b_grid g;
         g.dim = 2; g.mx = mx; g.my = my; g.mz = 1;
@@ -104,6 +105,7 @@ struct DeviceOps {
     void pattern_prolong_add(int Mx, int My, const double *xc, double *xf) { chk(p4b_pattern_prolong_add(c, Mx, My, xc, xf)); }
     void pattern_inject(int Mx, int My, const double *yf, double *yc) { chk(p4b_pattern_inject(c, Mx, My, yf, yc)); }
     void set_linearisation(const double *) {}             // the kernels take the state as an argument
+    void set_time(double) {}                              // the model is autonomous; callbacks get the stage time
 };
 
 extern long long g_gmres_cgs;
@@ -174,6 +176,8 @@ struct CallbackPatternOps : DeviceOps {
     double r0_shift = 0.0;
     bool r0_rhs = false;
     long long callbacks = 0;
+    double tcur = 0.0;                                     // stage time handed to the callbacks (ts_solver.hpp set_time)
+    void set_time(double t) { tcur = t; }
     CallbackPatternOps(p4b_ctx *c_, cudaStream_t st_, p4b_ifunction2d_fn f, p4b_rhsfunction2d_fn g, void *u)
         : DeviceOps{c_, st_}, ifn(f), gfn(g), user(u) {}
     void free_work() { for (double *p : {wY, wD, wF, wR0}) release(p); wY = wD = wF = wR0 = nullptr; }
@@ -183,7 +187,7 @@ struct CallbackPatternOps : DeviceOps {
         to_host(Y, hY.data(), n);
         to_host(Ydot, hD.data(), n);
         callbacks++;
-        if (!err && ifn(user, m, 0.0, hY.data(), hD.data(), hF.data())) err = 65;
+        if (!err && ifn(user, m, tcur, hY.data(), hD.data(), hF.data())) err = 65;
         from_host(hF.data(), F, n);
     }
     void pattern_rhsfunction(int m, const PO &, const double *Y, double *G) {
@@ -191,7 +195,7 @@ struct CallbackPatternOps : DeviceOps {
         hY.resize(n); hF.resize(n);
         to_host(Y, hY.data(), n);
         callbacks++;
-        if (!err && gfn(user, m, 0.0, hY.data(), hF.data())) err = 65;
+        if (!err && gfn(user, m, tcur, hY.data(), hF.data())) err = 65;
         from_host(hF.data(), G, n);
     }
     void set_linearisation(const double *Y) { lin = Y; r0_for = nullptr; }
@@ -300,6 +304,7 @@ extern "C" int p4b_snes2d_solve_monitored(p4b_ctx *c, const p4b_minimal_opts *op
             ops.monitor = [&](int mx, int my, int its, double fnorm, int tab, const double *uh) {
                 return monitor(user, mx, my, its, fnorm, tab, uh);
             };
+        ops.callback = resid;
         nk::MinimalOpts o2 = o;
         o2.q = model.q;
         g_snes2d_route = 1;
@@ -310,8 +315,20 @@ extern "C" int p4b_snes2d_solve_monitored(p4b_ctx *c, const p4b_minimal_opts *op
             if (u_capacity < n) rc = 63;
             else ops.to_host(u, u_out_host, n);
         }
-    } else {
-        if (base.error()) return fail(base.error(), "p4b_snes2d_solve: probing the residual failed (%s)", p4b_last_error());
+        if (rc == 68) {
+            // the callback is NOT the model where the solve went: say so and solve again with the callback itself
+            fprintf(stderr, "[p4b200] SNES: the residual callback matched the library's kernel at the probes but not at a "
+                            "converged iterate (deviation %.3e): solving again with the callback evaluated on the host\n",
+                    ops.verify_worst);
+            if (u) { cudaFreeAsync(u, st); u = nullptr; }
+            g_snes2d_route = 2;
+            rc = 0;
+        }
+    }
+    if (g_snes2d_route != 1) {
+        const bool again = g_snes2d_route == 2;
+        g_snes2d_route = 0;
+        if (!again && base.error()) return fail(base.error(), "p4b_snes2d_solve: probing the residual failed (%s)", p4b_last_error());
         CallbackOps ops(c, st, residual, monitor, user);
         rc = nk::minimal_solve(&ops, o, pr, u_out_host ? &u : nullptr, &R, u0_host, false);
         if (!rc && ops.error()) rc = ops.error();

@@ -551,6 +551,9 @@ int newton(Ops *ops, std::vector<Level<Ops>> &lev, const MinimalOpts &opt, const
     res->its = it;
     res->nksp = it;
     res->reason = reason;
+    // a residual that was substituted by the library's kernel is checked against the caller's callback once more, at the
+    // iterate this grid converged to (ModelOps::verify_converged; a no-op for every other set of operations)
+    if (!rc && !ops->verify_converged(L.mx, L.my, L.u, L.F)) rc = 68;
     if (!rc && opt.snes_converged_reason)
         pr.out("%s  Nonlinear solve %s due to %s iterations %d", pad.c_str(), reason > 0 ? "converged" : "did not converge",
                snes_reason_name(reason), it);
@@ -791,6 +794,29 @@ struct ModelOps : Base {
         hu.resize(n);
         this->to_host(u, hu.data(), n);
         if (!this->err && monitor(mx, my, its, fnorm, tablevel, hu.data())) this->err = 66;
+    }
+    // The probes are a finite sample of the callback.  A callback that equals the model there but not where the solve
+    // ends up (a term that acts for u > 1, an obstacle, ...) is caught here: at the converged iterate of every grid the
+    // caller's residual is evaluated once more and must equal the kernel's to rounding; if not, the caller falls back
+    // to the host-callback route (nk_device.cu).  One callback evaluation per grid.
+    std::function<int(int, int, const double *, double *)> callback;
+    double verify_worst = 0.0;
+    bool verify_converged(int mx, int my, const double *u, const double *F) {
+        if (!callback || this->err) return true;
+        const size_t n = (size_t)mx * my;
+        std::vector<double> hF(n), hFk(n);
+        hu.resize(n);
+        this->to_host(u, hu.data(), n);
+        this->to_host(F, hFk.data(), n);
+        if (this->err || callback(mx, my, hu.data(), hF.data())) return false;
+        double d = 0.0, sc = 1.0;
+        for (size_t k = 0; k < n; k++) {
+            const double e = fabs(hF[k] - hFk[k]);
+            if (!(e <= d)) d = e;
+            sc = std::max(sc, fabs(hu[k]));
+        }
+        verify_worst = std::max(verify_worst, d / sc);
+        return d <= 1.0e-10 * sc;
     }
 };
 

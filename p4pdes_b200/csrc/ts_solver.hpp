@@ -335,6 +335,9 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
             int newton_step = 0;
             while (!rc) {
                 for (int i = 0; i < 4 && !rc; i++) {
+                    double ci = 0.0;                            // stage time t + c_i h, c_i = sum_j a^I_ij (callbacks may depend on t)
+                    for (int j = 0; j <= i; j++) ci += ARK3_AI[i][j];
+                    ops->set_time(t + ci * h);
                     ops->copy(n, Y, Z);
                     for (int j = 0; j < i; j++) {
                         if (ARK3_AE[i][j] != 0.0) ops->axpy(n, h * ARK3_AE[i][j], FE[j], Z);
@@ -461,6 +464,7 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
                 ops->set(n, 0.0, V0);
                 for (int i = 1; i < nn; i++) ops->axpy(n, a[i], wk[i], V0);
                 const double shift = a[0];
+                ops->set_time(tm[0]);
                 std::function<void(const double *, double *)> F = [&, shift](const double *W, double *f) {
                     ops->axpby(n, shift, W, 1.0, V0, Ydot);                           // Ydot = shift W + V0
                     ops->pattern_ifunction(m, opt, W, Ydot, f);
@@ -538,11 +542,13 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
                 const double shift = 1.0 / (theta * dt);
                 ops->copy(n, Y, Yprev);
                 if (theta != 1.0) {
+                    ops->set_time(t);
                     ops->set(n, 0.0, Ydot);
                     ops->pattern_ifunction(m, opt, Yprev, Ydot, affine);
                     ops->pattern_rhsfunction(m, opt, Yprev, G);
                     ops->axpy(n, -1.0, G, affine);
                 }
+                ops->set_time(t + dt);
                 // F(W, (W - Yprev)/(theta dt)) - G(W) + (1 - theta)/theta [F(Yprev, 0) - G(Yprev)]
                 std::function<void(const double *, double *)> F = [&](const double *W, double *f) {
                     ops->axpby(n, shift, W, -shift, Yprev, Ydot);

@@ -1090,6 +1090,11 @@ static PetscErrorCode snes_solve_newtonls(SNES snes, Vec x) {
                                         newton_line, NULL, uf, nf, R);
     fflush(stdout);
     g_t_snes += wall() - t0;
+    /* which route ran is always said (on stderr: stdout stays what PETSc would print) */
+    if (!rc && p4b_snes2d_last_route() == 1)
+        fprintf(stderr, "[p4b200] SNES: the registered FormFunctionLocal equals the library's minimal-surface residual (probed "
+                        "on every grid, re-verified at each converged iterate): evaluated on the device.  "
+                        "-p4b_recognise_residual 0 keeps it a host callback.\n");
     if (rc) {
         free(uf);
         free(R);
@@ -1818,6 +1823,31 @@ static PetscErrorCode ts_solve_general(TS ts, Vec x, struct ts_work *W, p4b_patt
     return 0;
 }
 
+/* Largest deviation, relative to the size of the values, between the registered IFunction / RHSFunction callbacks and the
+ * device kernels of the identified model at (t, Y, Ydot) (host arrays, n doubles).  Own buffers: also used after the solve. */
+static PetscErrorCode ts_model_deviation(DM dm, const p4b_pattern_opts *o, int m, double t, const double *Y, const double *D,
+                                         size_t n, double *devF, double *devG) {
+    double *Fu = (double *)malloc(sizeof(double) * n), *Fd = (double *)malloc(sizeof(double) * n);
+    double *dY = NULL, *dD = NULL, *dF = NULL, scale;
+    PetscErrorCode rc = 0;
+    if (!Fu || !Fd) { free(Fu); free(Fd); SHIM_ERR(55, "out of host memory"); }
+    if (p4b_malloc(g_ctx, n * sizeof(double), (void **)&dY) || p4b_malloc(g_ctx, n * sizeof(double), (void **)&dD) ||
+        p4b_malloc(g_ctx, n * sizeof(double), (void **)&dF)) rc = 55;
+    if (!rc) rc = p4b_memcpy_h2d(g_ctx, dY, Y, n * sizeof(double)) || p4b_memcpy_h2d(g_ctx, dD, D, n * sizeof(double));
+    if (!rc) rc = ts_eval_ifunc(dm, t, Y, D, Fu);
+    if (!rc) rc = p4b_pattern_ifunction(g_ctx, m, m, o->L, o->Du, o->Dv, dY, dD, dF) || p4b_memcpy_d2h(g_ctx, Fd, dF, n * sizeof(double));
+    if (!rc) { *devF = maxabs_diff(Fu, Fd, n, &scale); *devF /= (scale > 1.0 ? scale : 1.0); }
+    if (!rc) rc = ts_eval_rhs(dm, t, Y, Fu);
+    if (!rc) rc = p4b_pattern_rhsfunction(g_ctx, m, m, o->phi, o->kappa, dY, dF) || p4b_memcpy_d2h(g_ctx, Fd, dF, n * sizeof(double));
+    if (!rc) { *devG = maxabs_diff(Fu, Fd, n, &scale); *devG /= (scale > 1.0 ? scale : 1.0); }
+    if (dY) p4b_free(g_ctx, dY);
+    if (dD) p4b_free(g_ctx, dD);
+    if (dF) p4b_free(g_ctx, dF);
+    free(Fu); free(Fd);
+    if (rc) SHIM_ERR(rc, "TSSolve: comparing the callbacks with the device kernels failed");
+    return 0;
+}
+
 static PetscErrorCode ts_solve(TS ts, Vec x, struct ts_work *W) {
     DM dm = ts->dm;
     KSP ksp = &ts->snes->ksp;
@@ -1924,6 +1954,25 @@ static PetscErrorCode ts_solve(TS ts, Vec x, struct ts_work *W) {
                      o.phi, o.kappa, dev);
         }
     }
+    /* (2b) the same at later times and at states far from the initial one: a forcing that depends on t, or a term that
+     *      only acts for larger values, must not slip through one probe at t = 0 */
+    for (int probe = 1; probe <= 2 && is_model; probe++) {
+        const double tp = probe == 1 ? 0.37 * ts->max_time : ts->max_time, amp = probe == 1 ? 0.6 : 1.5;
+        for (size_t i = 0; i < n; i++) {
+            lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
+            Y[i] = (probe == 1 ? x->h[i] : 0.0) + amp * ((double)(lcg >> 11) / 9007199254740992.0 - (probe == 1 ? 0.5 : 0.0));
+            lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
+            D[i] = (double)(lcg >> 11) / 9007199254740992.0 - 0.5;
+        }
+        double dF = 0.0, dG = 0.0;
+        PetscCall(ts_model_deviation(dm, &o, m, tp, Y, D, n, &dF, &dG));
+        if (!(dF <= 1.0e-11) || !(dG <= 1.0e-11)) {
+            is_model = 0;
+            snprintf(msg, sizeof msg, "TSSolve: the registered callbacks equal the reaction-diffusion model at t = 0 near the "
+                     "initial state but not at t = %g, amplitude %g (deviation F %.3e, G %.3e): not the model the device path "
+                     "has as kernels", tp, amp, dF, dG);
+        }
+    }
     if (is_model && opt_value("-p4b_recognise_residual") && !atol(opt_value("-p4b_recognise_residual"))) {
         is_model = 0;                  /* A/B: run the model through the general route as well */
         snprintf(msg, sizeof msg, "TSSolve: -p4b_recognise_residual 0");
@@ -1980,10 +2029,35 @@ static PetscErrorCode ts_solve(TS ts, Vec x, struct ts_work *W) {
     p4b_pattern_result *R = W->R = (p4b_pattern_result *)calloc(1, sizeof *R);
     if (!R) SHIM_ERR(55, "out of host memory");
     fflush(stdout);
+    fprintf(stderr, "[p4b200] TS: the registered callbacks equal the library's reaction-diffusion model (F, G at three "
+                    "times and states, every Jacobian row; re-verified at the final state): time stepping on the device.  "
+                    "-p4b_recognise_residual 0 -pc_type none runs the host callbacks.\n");
     int rc = p4b_pattern_solve_from(g_ctx, &o, x->d, newton_line, NULL, x->d, n, R);
     fflush(stdout);
     if (rc) return PetscShimError(PETSC_COMM_SELF, __LINE__, __func__, __FILE__, rc, p4b_last_error());
     x->valid = LOC_DEV;
+    {   /* (4) once more where the solve ended up: the final state at the final time.  The probes are a finite sample;
+         *     what they could not see is reported loudly here (the trajectory has been printed already, so this is an
+         *     error, not a silent re-run) */
+        double *Yf = (double *)malloc(sizeof(double) * n), *Df = (double *)malloc(sizeof(double) * n), dF = 0.0, dG = 0.0;
+        if (!Yf || !Df) { free(Yf); free(Df); SHIM_ERR(55, "out of host memory"); }
+        PetscCall(vec_to_host(x));
+        unsigned long long l2 = 0xD1B54A32D192ED03ULL;
+        for (size_t i = 0; i < n; i++) {
+            Yf[i] = x->h[i];
+            l2 = l2 * 6364136223846793005ULL + 1442695040888963407ULL;
+            Df[i] = (double)(l2 >> 11) / 9007199254740992.0 - 0.5;
+        }
+        PetscErrorCode rv = ts_model_deviation(dm, &o, m, R->t_final, Yf, Df, n, &dF, &dG);
+        free(Yf); free(Df);
+        if (rv) return rv;
+        if (!(dF <= 1.0e-10) || !(dG <= 1.0e-10)) {
+            snprintf(msg, sizeof msg, "TSSolve: the registered callbacks matched the device kernels at every probe but not at "
+                     "the final state (t = %g, deviation F %.3e, G %.3e): the trajectory above is the MODEL's, not the "
+                     "callbacks'; run again with -p4b_recognise_residual 0 -pc_type none (host callbacks)", R->t_final, dF, dG);
+            SHIM_ERR(56, msg);
+        }
+    }
     g_t_snes += wall() - t_start;
     return 0;
 }

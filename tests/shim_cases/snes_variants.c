@@ -3,6 +3,9 @@
  * that the library's kernel does not have -- to check both routes of p4b_snes2d_solve under the shim:
  *   -variant 0   the model with other boundary data and exponent (must be RECOGNISED: residual on the device)
  *   -variant 1   the model + 5 hx hy u^3 (must NOT be recognised: the callback is evaluated on the host every time)
+ *   -variant 2   the model + a term that acts only where u < -0.05: the probes (interior values in [0, 0.5]) cannot see
+ *                it, the converged iterate (negative near x = 1) does -- the re-verification at the converged iterate must
+ *                catch it and the solve must be repeated with the callback on the host
  * Prints sum(u) and max(u) of the converged iterate so that a test can compare with an independent solve. */
 #include <petsc.h>
 
@@ -27,6 +30,7 @@ static PetscErrorCode Residual(DMDALocalInfo *info, PetscReal **au, PetscReal **
             const PetscReal Ds = diffusivity((e + se - w - sw) / (4.0 * hx), (c - s) / hy, user->q);
             aF[j][i] = -(hy / hx) * (De * (e - c) - Dw * (c - w)) - (hx / hy) * (Dn * (n - c) - Ds * (c - s));
             if (user->variant == 1) aF[j][i] += 5.0 * hx * hy * c * c * c;
+            if (user->variant == 2 && c < -0.05) aF[j][i] += 40.0 * hx * hy * (c + 0.05) * (c + 0.05);
         }
 #undef VAL
     return 0;
@@ -42,7 +46,7 @@ int main(int argc, char **argv) {
     PetscCall(PetscInitialize(&argc, &argv, NULL, "SNES variants for the p4b200 shim\n"));
     user.q = -0.35; user.variant = 0;
     PetscOptionsBegin(PETSC_COMM_WORLD, "", "variants", "");
-    PetscCall(PetscOptionsInt("-variant", "0 = the model, 1 = model + reaction", "snes_variants.c", user.variant, &user.variant, NULL));
+    PetscCall(PetscOptionsInt("-variant", "0 = the model, 1 = model + reaction, 2 = model + a term the probes cannot see", "snes_variants.c", user.variant, &user.variant, NULL));
     PetscCall(PetscOptionsReal("-q", "exponent of the diffusivity", "snes_variants.c", user.q, &user.q, NULL));
     PetscOptionsEnd();
     PetscCall(DMDACreate2d(PETSC_COMM_WORLD, DM_BOUNDARY_NONE, DM_BOUNDARY_NONE, DMDA_STENCIL_BOX, 5, 5, PETSC_DECIDE, PETSC_DECIDE,

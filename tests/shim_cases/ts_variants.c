@@ -5,18 +5,19 @@
  *   -variant 1   reaction with an extra cubic term in G^u
  *   -variant 2   anisotropic diffusion in F (x and y edges weighted differently)
  *   -variant 3   IJacobian with a wrong corner weight
- *   -variant 4   RHSJacobian with a wrong off-diagonal entry (fully implicit types only) */
+ *   -variant 4   RHSJacobian with a wrong off-diagonal entry (fully implicit types only)
+ *   -variant 5   a forcing in G^u that grows with t (zero at t = 0: one probe at t = 0 cannot see it) */
 #include <petsc.h>
 
 typedef struct { PetscReal u, v; } Field;
 typedef struct { PetscReal L, Du, Dv, phi, kappa; PetscInt variant; } Ctx;
 
 static PetscErrorCode RHS(DMDALocalInfo *info, PetscReal t, Field **aY, Field **aG, Ctx *user) {
-    (void)t;
     for (PetscInt j = info->ys; j < info->ys + info->ym; j++)
         for (PetscInt i = info->xs; i < info->xs + info->xm; i++) {
             const PetscReal u = aY[j][i].u, v = aY[j][i].v, uv2 = u * v * v;
-            aG[j][i].u = -uv2 + user->phi * (1.0 - u) + (user->variant == 1 ? 1.0e-3 * u * u * u : 0.0);
+            aG[j][i].u = -uv2 + user->phi * (1.0 - u) + (user->variant == 1 ? 1.0e-3 * u * u * u : 0.0)
+                         + (user->variant == 5 ? 1.0e-4 * t : 0.0);
             aG[j][i].v = uv2 - (user->phi + user->kappa) * v;
         }
     return 0;

@@ -150,7 +150,8 @@ def test_minimal_c_is_recognised_and_both_routes_print_the_same(exe):
     two routes print the same lines."""
     g = GOLD["minimal.test4"]
     a, (route, q, ncb) = run_report(exe, g["options"] + EXTRA)
-    assert a == g["lines"] and route == 1 and q == -0.5 and ncb == 2 * 3 + 1            # grids 3x3, 5x5, 9x9
+    # grids 3x3, 5x5, 9x9: two probes each + one to identify q, then one re-verification at each converged iterate
+    assert a == g["lines"] and route == 1 and q == -0.5 and ncb == 2 * 3 + 1 + 3
     b, (route0, _, ncb0) = run_report(exe, g["options"] + EXTRA + " -p4b_recognise_residual 0")
     assert b == g["lines"] and route0 == 0 and ncb0 > 200
     # another exponent and boundary problem, with the monitor: identified exactly as the option was parsed
@@ -181,7 +182,7 @@ def test_a_residual_that_is_not_the_model_stays_a_host_callback(snes_variants):
     argv = "-snes_fd_color -da_refine 2 -snes_rtol 1e-12" + EXTRA
     a, (route, q, ncb) = run_report(snes_variants, "-variant 0 " + argv)
     b, (route0, _, _) = run_report(snes_variants, "-variant 0 -p4b_recognise_residual 0 " + argv)
-    assert route == 1 and q == float("-0.35") and ncb == 2 * 3 + 1 and route0 == 0 and a == b
+    assert route == 1 and q == float("-0.35") and ncb == 2 * 3 + 1 + 1 and route0 == 0 and a == b
     c, (route1, _, ncb1) = run_report(snes_variants, "-variant 1 " + argv)
     assert route1 == 0 and ncb1 > 100 and c != a
     m = 17
@@ -196,3 +197,19 @@ def test_a_residual_that_is_not_the_model_stays_a_host_callback(snes_variants):
         r = mo.newton(F, np.full((m, m), 0.1), lambda J, uu: fo.ILU0PC(J).apply, snes_rtol=1e-12)
         got = re.fullmatch(r"done on 17 x 17 grid: sum (\S+) max (\S+)", lines[-1])
         assert abs(float(got.group(1)) - r.u.sum()) <= 1e-8 * abs(r.u.sum()) and abs(float(got.group(2)) - r.u.max()) <= 1e-9
+
+
+def test_a_term_the_probes_cannot_see_is_caught_at_the_converged_iterate(snes_variants):
+    """ADVICE r1 (probe_minimal_model): a callback that equals the model at the probe states but not where the solve ends
+    up.  Variant 2 adds a term that acts only where u < -0.05; the probes' interior values lie in [0, 0.5].  The callback
+    is recognised, the device solve converges -- to the model's answer, not the caller's -- the re-verification at the
+    converged iterate sees the difference, says so on stderr, and the solve is repeated through the host callback."""
+    argv = "-snes_fd_color -da_refine 2 -snes_rtol 1e-12" + EXTRA
+    p = subprocess.run([snes_variants] + ("-variant 2 " + argv).split(), capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, P4B_STANDIN_REPORT="1"))
+    assert p.returncode == 0, p.stderr
+    assert "matched the library's kernel at the probes but not at a converged iterate" in p.stderr
+    assert _route(p)[0] == 0                                   # the answer came from the host-callback route
+    forced, _ = run_report(snes_variants, "-variant 2 -p4b_recognise_residual 0 " + argv)
+    model, _ = run_report(snes_variants, "-variant 0 " + argv)
+    assert p.stdout.splitlines()[-1] == forced[-1] and forced[-1] != model[-1]

@@ -109,6 +109,12 @@ def test_other_parameter_values_run_and_other_models_take_the_general_route(vari
     for v, what in ((1, "RHSFunction is not G"), (2, "IFunction is not F")):
         _, p = run(variants, "-variant %d -da_refine 2" % v + MG, check=False)
         assert p.returncode == 56 and what in p.stderr and "max deviation" in p.stderr and "pass -pc_type none" in p.stderr
+    # a forcing that vanishes at t = 0 is seen by the probes at later times (one probe at t = 0 is not enough)
+    _, p = run(variants, "-variant 5 -da_refine 2" + MG, check=False)
+    assert p.returncode == 56 and "but not at t = " in p.stderr and "pass -pc_type none" in p.stderr
+    v5, _ = run(variants, "-variant 5 -da_refine 2 -pc_type none -ts_type beuler -ts_dt 2 -ts_max_time 6 -snes_rtol 1e-10")
+    v0, _ = run(variants, "-variant 0 -da_refine 2 -pc_type none -ts_type beuler -ts_dt 2 -ts_max_time 6 -snes_rtol 1e-10")
+    assert v5[-1].startswith("done: |Y|_2 = ") and v5[-1] != v0[-1]
     # ... a Jacobian callback that contradicts its own (model) functions is refused outright
     _, p = run(variants, "-variant 3 -da_refine 2" + MG, check=False)
     assert p.returncode == 56 and "IJacobian does not insert" in p.stderr
