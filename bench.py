@@ -160,12 +160,184 @@ def run_reference(args):
     return 0
 
 
+def _time_kernel(fn, reps=30, warm=5):
+    import torch
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def run_secondary(args):
+    """The other BASELINE.json configurations (one GPU): one JSON line each, same keys as the headline line.  A step =
+    one complete run of the driver's solve (c1: KSP solve; c4: grid-sequenced Newton-Krylov-MG solve; c5: implicit
+    time steps).  `roofline` is the dominant kernel of that driver timed ALONE in this process with CUDA events (these
+    solves are launch-latency bound on 4 M unknowns: the kernel table is context, the solve time is the number)."""
+    if args.impl == "reference":
+        print(json.dumps({"impl": "reference", "config": {"workload": args.config},
+                          "unavailable": "the CPU restatement that is timed as the reference arm exists for the fish "
+                                         "configurations (c1, c2, c3); minimal.c / pattern.c need PETSc itself"}))
+        return 0
+    import torch
+    from p4pdes_b200 import lib as L
+    from p4pdes_b200 import minimal as pm, pattern as pp
+    from p4pdes_b200.fish import Context, Multigrid, mg_options
+    torch.cuda.set_device(0)
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    ctx = Context(0)
+    lib = ctx.lib
+    peak, peak_src = peaks()
+    sampler = ClockSampler(0)
+    roof, extra, cpu = None, {}, None
+    if args.config == "c1":
+        refine = 6
+        g = L.refined_grid(2, refine)
+        mg = Multigrid(ctx, g, mg_options(levels=refine + 1))
+        n = mg.nlocal
+        b, x, u0, ue = ctx.empty(n), ctx.empty(n), ctx.empty(n), ctx.empty(n)
+        mg.fish_setup("manuexp", True, b=b, u0=u0, uexact=ue)
+        for _ in range(args.warmup):
+            res = mg.cg_solve(b, x, rtol=1e-10)
+        torch.cuda.synchronize()
+        sampler.start()
+        l0 = lib.p4b_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ctx.stream)
+        for _ in range(args.steps):
+            res = mg.cg_solve(b, x, rtol=1e-10)
+        e1.record(ctx.stream)
+        torch.cuda.synchronize()
+        launches = lib.p4b_launch_count() - l0
+        ms = e0.elapsed_time(e1) / args.steps
+        bh, xh = torch.empty(n, dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory()
+        bh.copy_(b)
+        mg.cg_solve_host(bh, xh, rtol=1e-10)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            mg.cg_solve_host(bh, xh, rtol=1e-10)
+        torch.cuda.synchronize()
+        ms_e2e = (time.perf_counter() - t0) / args.steps * 1e3
+        ctx.axpy(-1.0, x, u0)
+        ctx.axpy(-1.0, ue, u0)
+        ndof = g.n
+        workload = "fish.c 2-D Poisson manuexp %d^2 (-fsh_dim 2 -da_refine 6), CG + V-cycle GMG, Chebyshev(2)/Jacobi, rtol 1e-10" % g.mx
+        options = "-fsh_dim 2 -da_refine 6 -pc_type mg -mg_levels_ksp_type chebyshev -mg_levels_ksp_max_it 2 -mg_levels_pc_type jacobi -ksp_rtol 1e-10"
+        metric = "fish2d_cg_gmg_solve_mdof_per_s"
+        extra = {"ksp_its": res.its, "errinf": ctx.norminf(u0), "note": "16 641 unknowns: every kernel is launch-latency bound"}
+        h2d = d2h = 8 * n
+        try:
+            from oracle import fish_cpu
+            r = fish_cpu.solve(dim=2, refine=6, rtol=1e-10, threads=os.cpu_count())
+            cpu = {"value": r["n"] / r["seconds"] / 1e6, "unit": "MDOF/s", "cores": r["threads"], "kind": "port",
+                   "solve_s": r["seconds"], "ksp_its": r["its"], "sample": "the same solve; " + CPU_PORT_NOTE}
+        except Exception as exc:
+            cpu = {"value": None, "unit": "MDOF/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (exc,)}
+    elif args.config == "c4":
+        argv = "-da_grid_x 33 -da_grid_y 33 -snes_grid_sequence 6 -snes_fd_color -pc_type mg"      # c/ch8/cluster.sh:70
+        for _ in range(max(1, min(args.warmup, 2))):
+            rep = pm.minimal_main(argv, ctx, native=True)
+        torch.cuda.synchronize()
+        sampler.start()
+        l0 = lib.p4b_launch_count()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rep = pm.minimal_main(argv, ctx, native=True, keep_solution=True)
+            uh = rep.u.cpu()                       # the step's result reaches the host
+        torch.cuda.synchronize()
+        ms = ms_e2e = (time.perf_counter() - t0) / args.steps * 1e3
+        launches = lib.p4b_launch_count() - l0
+        ndof = 2049 * 2049
+        workload = "minimal.c catenoid, grid-sequenced Newton-GMRES-MG to 2049^2 (c/ch8/cluster.sh:70), FD-coloured Jacobians"
+        options = argv + " -mg_levels_pc_type jacobi"
+        metric = "minimal2d_newton_krylov_mg_solve_mdof_per_s"
+        extra = {"newton_its": [s.its for s in rep.stages], "errinf": rep.errinf,
+                 "note": "whole run incl. the six coarser grids of the sequence; wall clock (host loop + kernels); the "
+                         "initial iterate is generated on the device, the solution (33.6 MB) is copied to the host"}
+        h2d, d2h = 0, 8 * ndof
+        from p4pdes_b200 import callbacks as cb
+        m = 2049
+        gtab = cb.minimal_g(ctx, m, m, "catenoid", 1.0, 1.1)
+        u = gtab.clone() * 0.9
+        F0 = ctx.empty(m * m)
+        cb.minimal_form_function(ctx, m, m, u, gtab, -0.5, out=F0)
+        vals = ctx.empty(9 * m * m)
+        L.check(lib.p4b_minimal_jacobian_fd(ctx.h, m, m, -0.5, u.data_ptr(), gtab.data_ptr(), F0.data_ptr(), vals.data_ptr()))
+        xx, bb, out = ctx.empty(m * m), ctx.empty(m * m), ctx.empty(m * m)
+        kms = _time_kernel(lambda: L.check(lib.p4b_stencil9_lin(ctx.h, m, m, vals.data_ptr(), xx.data_ptr(), bb.data_ptr(),
+                                                                 None, 0.0, 1.0, 0.5, 1, out.data_ptr())))
+        by = 96.0 * m * m
+        roof = {"bound": "hbm", "kernel": "stencil9_lin (Chebyshev/Jacobi step on the assembled 9-point Jacobian)",
+                "achieved": by / kms / 1e6, "peak": peak, "unit": "GB/s", "frac": by / kms / 1e6 / peak,
+                "alg_bytes_per_launch": by, "ms_per_launch": kms, "traffic": None,
+                "how": "kernel timed alone (30 launches, CUDA events) on the 2049^2 operator; 37 MB per operand: partly L2 resident"}
+    else:
+        argv = ("-da_grid_x 8 -da_grid_y 8 -da_refine 8 -ts_type beuler -ts_dt 5 -ts_max_time 50 -pc_type mg "
+                "-p4b_mg_rscale 0.25")
+        for _ in range(max(1, min(args.warmup, 2))):
+            rep = pp.pattern_main(argv, ctx, native=True)
+        torch.cuda.synchronize()
+        sampler.start()
+        l0 = lib.p4b_launch_count()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rep = pp.pattern_main(argv, ctx, native=True)
+            yh = rep.Y.cpu()
+        torch.cuda.synchronize()
+        nsteps = len(rep.steps)
+        ms = ms_e2e = (time.perf_counter() - t0) / args.steps * 1e3
+        launches = lib.p4b_launch_count() - l0
+        m = 2048
+        ndof = 2 * m * m * nsteps                  # unknowns advanced: 8.4 M per implicit step x steps per run
+        workload = ("pattern.c Gray-Scott 2048^2 x 2 dof, %d backward-Euler steps (dt 5), Newton-GMRES-MG per step, "
+                    "matrix-free stage Jacobian" % nsteps)
+        options = argv + " -mg_levels_pc_type jacobi"
+        metric = "pattern2d_implicit_steps_mdof_per_s"
+        extra = {"ts_steps": nsteps, "ms_per_ts_step": ms / nsteps, "newton_per_step": [s[2] for s in rep.steps],
+                 "note": "one GPU; -p4b_mg_rscale 0.25 (averaging restriction) keeps GMRES counts mesh independent "
+                         "(DESIGN.md section 8); the final state (67 MB) is copied to the host"}
+        h2d, d2h = 0, 16 * m * m
+        from p4pdes_b200 import callbacks as cb
+        Y = cb.pattern_initial_state(ctx, m, m)
+        X, bb, out = Y.clone(), Y.clone(), ctx.empty(2 * m * m)
+        kms = _time_kernel(lambda: L.check(lib.p4b_pattern_jac_lin(ctx.h, m, m, 2.5, 8.0e-5, 4.0e-5, 0.024, 0.06, 0.2,
+                                                                    Y.data_ptr(), X.data_ptr(), bb.data_ptr(), None, 0.0, 1.0,
+                                                                    0.5, 1, out.data_ptr())))
+        by = 64.0 * m * m
+        roof = {"bound": "hbm", "kernel": "pattern_jac_kernel (matrix-free stage-Jacobian smoother step)",
+                "achieved": by / kms / 1e6, "peak": peak, "unit": "GB/s", "frac": by / kms / 1e6 / peak,
+                "alg_bytes_per_launch": by, "ms_per_launch": kms, "traffic": None,
+                "how": "kernel timed alone (30 launches, CUDA events) at 2048^2 x 2; 67 MB per operand: partly L2 resident"}
+    clocks = sampler.stop()
+    line = {"metric": metric, "value": ndof / (ms * 1e-3) / 1e6, "unit": "MDOF/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "solve_s": ms * 1e-3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "options": options, "baseline_config": args.config,
+                       "l2": "vectors of this configuration fit the 126 MB L2; nothing is flushed between solves (the solve "
+                             "itself streams every level many times)"},
+            "e2e": {"value": ndof / (ms_e2e * 1e-3) / 1e6, "unit": "MDOF/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+    line.update(extra)
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configuration: c3 (default) = fish 3-D 513^3, the headline; c2 = fish 3-D 257^3; "
+                         "c1 = fish 2-D -da_refine 6; c4 = minimal.c 2049^2 (c/ch8/cluster.sh:70); c5 = pattern.c 2048^2 x 2")
     ap.add_argument("--refine", type=int, default=8, help="-da_refine (8 = 513^3, 7 = 257^3)")
     ap.add_argument("--levels", type=int, default=0, help="-pc_mg_levels (default refine-1: coarse grid 9^3)")
     ap.add_argument("--cpu-refine", type=int, default=0, help="grid of the CPU arm / cpu_baseline (default: --refine, "
@@ -186,6 +358,10 @@ def main():
     ap.add_argument("--trace", default="", help="after the timed steps, run one more solve with every launch on every "
                                                 "level bracketed by CUDA events and write the table to this JSON file")
     args = ap.parse_args()
+    if args.config == "c2":
+        args.refine = 7
+    if args.config in ("c1", "c4", "c5"):
+        return run_secondary(args)
     if args.impl == "reference":
         return run_reference(args)
 

@@ -401,6 +401,13 @@ int p4b_pattern_solve(p4b_ctx *ctx, const p4b_pattern_opts *opts, p4b_line_fn li
  * report: the caller prints those, pattern.c:94-96,127-135).  Y0 = NULL is p4b_pattern_solve. */
 int p4b_pattern_solve_from(p4b_ctx *ctx, const p4b_pattern_opts *opts, const double *Y0, p4b_line_fn line, void *line_ctx,
                            double *Y_out, size_t Y_capacity, p4b_pattern_result *result);
+/* Multi-GPU (BASELINE config 5: 2048^2 on 8 GPUs): with a context that carries a communicator (p4b_comm_init)
+ * p4b_pattern_solve / p4b_pattern_solve_from run on y-slabs of the periodic DMDA (c/ch5/pattern.c:79-84) -- ring
+ * exchange of one ghost row per side ([PETSc] DMGlobalToLocal), all-reduced dot products, small levels replicated.
+ * Y0 / Y_out are then THIS RANK's rows, 2 * m * (m / nranks) doubles; p4b_pattern_slab_plan (host only) says which
+ * levels are distributed and which rows a rank owns on each (arrays of >= 32 ints; returns the number of levels,
+ * finest first, or a negative error code). */
+int p4b_pattern_slab_plan(int m, int grid_x, int mg, int nranks, int rank, int *level_m, int *distributed, int *ys, int *ym);
 /* ---- the same time steppers for ANY two-component system on the periodic m x m DMDA given by HOST callbacks and no
  * Jacobian: F(t, Y, Ydot) and G(t, Y) of the DMDATSSet{IFunction,RHSFunction}Local contract (c/ch5/pattern.c:103-114,
  * 185-199, 242-267; arrays whole-grid, (u,v) interleaved, natural ordering).  The stage operator is the differenced residual

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256) pattern_jac_kernel(int mx, int my, double
                                                            double kappa, const double2 *__restrict__ Y,
                                                            const double2 *__restrict__ X, const double2 *b,
                                                            const double2 *pm1, double ca, double cb, double cg,
-                                                           int jacobi, double2 *out) {
+                                                           int jacobi, int ywrap, double2 *out) {
     const int n = blockIdx.x * 256 + threadIdx.x;
     if (n >= mx * my) return;
     const int j = n / mx, i = n - j * mx;
@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(256) pattern_jac_kernel(int mx, int my, double
         return;
     }
     const int iw = (i == 0) ? mx - 1 : i - 1, ie = (i == mx - 1) ? 0 : i + 1;      // periodic wrap
-    const int js = (j == 0) ? my - 1 : j - 1, jn = (j == my - 1) ? 0 : j + 1;
+    // ywrap = 0: a y-slab with its ghost rows -1 and my in memory (mp_kernels.cu pattern_ifunction_kernel)
+    const int js = (j == 0 && ywrap) ? my - 1 : j - 1, jn = (j == my - 1 && ywrap) ? 0 : j + 1;
     const double2 c = X[n];
     const double2 nw = X[jn * mx + iw], nn = X[jn * mx + i], ne = X[jn * mx + ie];
     const double2 ww = X[j * mx + iw], ee = X[j * mx + ie];
@@ -230,16 +231,16 @@ __global__ void __launch_bounds__(256) pattern_jac_kernel(int mx, int my, double
 
 int launch_pattern_jac(cudaStream_t st, int mode, int mx, int my, double Cu, double Cv, double shift, double phi,
                        double kappa, const double *Y, const double *X, const double *b, const double *pm1, double ca,
-                       double cb, double cg, int jacobi, double *out) {
+                       double cb, double cg, int jacobi, double *out, int ywrap) {
     const int N = mx * my;
     if (N <= 0) return 0;
     const unsigned nb = (unsigned)((N + 255) / 256);
     const double2 *Y2 = reinterpret_cast<const double2 *>(Y), *X2 = reinterpret_cast<const double2 *>(X);
     const double2 *b2 = reinterpret_cast<const double2 *>(b), *p2 = reinterpret_cast<const double2 *>(pm1);
     double2 *o2 = reinterpret_cast<double2 *>(out);
-    if (mode == 0) pattern_jac_kernel<0><<<nb, 256, 0, st>>>(mx, my, Cu, Cv, shift, phi, kappa, Y2, X2, b2, p2, ca, cb, cg, jacobi, o2);
-    else if (mode == 1) pattern_jac_kernel<1><<<nb, 256, 0, st>>>(mx, my, Cu, Cv, shift, phi, kappa, Y2, X2, b2, p2, ca, cb, cg, jacobi, o2);
-    else pattern_jac_kernel<2><<<nb, 256, 0, st>>>(mx, my, Cu, Cv, shift, phi, kappa, Y2, X2, b2, p2, ca, cb, cg, jacobi, o2);
+    if (mode == 0) pattern_jac_kernel<0><<<nb, 256, 0, st>>>(mx, my, Cu, Cv, shift, phi, kappa, Y2, X2, b2, p2, ca, cb, cg, jacobi, ywrap, o2);
+    else if (mode == 1) pattern_jac_kernel<1><<<nb, 256, 0, st>>>(mx, my, Cu, Cv, shift, phi, kappa, Y2, X2, b2, p2, ca, cb, cg, jacobi, ywrap, o2);
+    else pattern_jac_kernel<2><<<nb, 256, 0, st>>>(mx, my, Cu, Cv, shift, phi, kappa, Y2, X2, b2, p2, ca, cb, cg, jacobi, ywrap, o2);
     P4B_LAUNCH_CHECK();
     return 0;
 }
@@ -247,7 +248,10 @@ int launch_pattern_jac(cudaStream_t st, int mode, int mx, int my, double Cu, dou
 // [PETSc] DMCreateInterpolation on a PERIODIC 2-dof DMDA (ratio 2, fine m = 2 M): fine node 2I coincides with coarse I,
 // fine node 2I+1 averages coarse I and (I+1) mod M; tensor product in x and y, the same for both components.
 // mode 0: restriction b_c = P^T r      mode 1: prolongation x_f += P x_c      mode 2: injection y_c(I,J) = y_f(2I,2J)
-__global__ void __launch_bounds__(256) pattern_transfer_kernel(int mode, int Mx, int My, const double2 *__restrict__ src,
+// ywrap = 0: y-slabs of a multi-GPU run (My coarse rows, 2 My fine rows of this rank): the restriction reads the fine
+// ghost row -1, the prolongation the coarse ghost row My, both in memory; no wrap in y.
+__global__ void __launch_bounds__(256) pattern_transfer_kernel(int mode, int Mx, int My, int ywrap,
+                                                                const double2 *__restrict__ src,
                                                                 double2 *__restrict__ dst) {
     const int fx = 2 * Mx, fy = 2 * My;
     const int n = blockIdx.x * 256 + threadIdx.x;
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(256) pattern_transfer_kernel(int mode, int Mx,
         if (n >= fx * fy) return;
         const int j = n / fx, i = n - j * fx;
         const int I0 = i >> 1, I1 = (i & 1) ? (I0 + 1 == Mx ? 0 : I0 + 1) : I0;
-        const int J0 = j >> 1, J1 = (j & 1) ? (J0 + 1 == My ? 0 : J0 + 1) : J0;
+        const int J0 = j >> 1, J1 = (j & 1) ? ((J0 + 1 == My && ywrap) ? 0 : J0 + 1) : J0;
         const double2 a = src[J0 * Mx + I0], b = src[J0 * Mx + I1], c = src[J1 * Mx + I0], d = src[J1 * Mx + I1];
         double2 o = dst[n];
         o.x += 0.25 * ((a.x + b.x) + (c.x + d.x));
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(256) pattern_transfer_kernel(int mode, int Mx,
 #pragma unroll
     for (int dj = -1; dj <= 1; dj++) {
         int jf = 2 * J + dj;
-        jf = jf < 0 ? jf + fy : (jf >= fy ? jf - fy : jf);
+        if (ywrap) jf = jf < 0 ? jf + fy : (jf >= fy ? jf - fy : jf);
         const double wj = dj ? 0.5 : 1.0;
         double ru = 0.0, rv = 0.0;
 #pragma unroll
@@ -291,10 +295,11 @@ __global__ void __launch_bounds__(256) pattern_transfer_kernel(int mode, int Mx,
     dst[n] = make_double2(su, sv);
 }
 
-int launch_pattern_transfer(cudaStream_t st, int mode, int Mx, int My, const double *src, double *dst) {
+int launch_pattern_transfer(cudaStream_t st, int mode, int Mx, int My, const double *src, double *dst, int ywrap) {
     const int N = (mode == 1) ? 4 * Mx * My : Mx * My;
     if (N <= 0) return 0;
-    pattern_transfer_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(mode, Mx, My, reinterpret_cast<const double2 *>(src),
+    pattern_transfer_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(mode, Mx, My, ywrap,
+                                                                       reinterpret_cast<const double2 *>(src),
                                                                        reinterpret_cast<double2 *>(dst));
     P4B_LAUNCH_CHECK();
     return 0;

@@ -83,11 +83,13 @@ int launch_poisson_function(cudaStream_t st, const LevelDesc &L, int dim, double
 int launch_minimal_sample(cudaStream_t st, int mx, int my, int zs, int zm, int problem, double tent_H, double c, double *g);
 int launch_minimal_function(cudaStream_t st, int mx, int my, int zs, int zm, double q, const double *u, const double *g,
                             double *FF);
+// ys, ym: rows [ys, ys + ym) only (a y-slab; ym < 0 = the whole grid).  ywrap = 0 in the stencil / transfer launchers:
+// the my rows are a slab with ghost rows -1 and my in memory (multi-GPU y-slabs of the periodic grid)
 int launch_pattern_init(cudaStream_t st, int mx, int my, double L, double *Y, const double *noise = nullptr,
-                        double level = 0.0);
+                        double level = 0.0, int ys = 0, int ym = -1);
 int launch_pattern_rhs(cudaStream_t st, int n, double phi, double kappa, const double *Y, double *G);
 int launch_pattern_ifunction(cudaStream_t st, int mx, int my, double Cu, double Cv, int use_shift, double shift,
-                             const double *Y, const double *Ydot, double *F);
+                             const double *Y, const double *Ydot, double *F, int ywrap = 1);
 struct Sell;
 int sell_build(cudaStream_t st, int nrows, const int *rowptr, const int *colind, const double *vals, Sell **out);
 int sell_spmv(cudaStream_t st, const Sell *A, const double *x, double *y);
@@ -105,8 +107,8 @@ int launch_fd_extract(cudaStream_t st, int mx, int my, int ci, int cj, double h,
 int launch_stencil9_apply(cudaStream_t st, int mx, int my, const double *vals, const double *x, double *y);
 int launch_pattern_jac(cudaStream_t st, int mode, int mx, int my, double Cu, double Cv, double shift, double phi,
                        double kappa, const double *Y, const double *X, const double *b, const double *pm1, double ca,
-                       double cb, double cg, int jacobi, double *out);
-int launch_pattern_transfer(cudaStream_t st, int mode, int Mx, int My, const double *src, double *dst);
+                       double cb, double cg, int jacobi, double *out, int ywrap = 1);
+int launch_pattern_transfer(cudaStream_t st, int mode, int Mx, int My, const double *src, double *dst, int ywrap = 1);
 int launch_stencil9_rowratio(cudaStream_t st, int mx, int my, const double *vals, double *out);
 int launch_inject2d(cudaStream_t st, int cmx, int cmy, int fmx, const double *uf, double *uc);
 int launch_stencil9_lin(cudaStream_t st, int mx, int my, const double *vals, const double *u, const double *b,

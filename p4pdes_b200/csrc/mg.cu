@@ -928,6 +928,37 @@ static int plan_levels(const p4b_grid *g, const p4b_mg_opts &o, int P, LevelPlan
 
 namespace p4b {
 cudaStream_t ctx_stream(p4b_ctx *c) { return c->stream; }     // for the other translation units (nk_device.cu)
+int ctx_rank(p4b_ctx *c) { return c->rank; }
+int ctx_nranks(p4b_ctx *c) { return c->nranks; }
+// y-slabs of a PERIODIC 2-D grid (pattern.c, DM_BOUNDARY_PERIODIC: c/ch5/pattern.c:79-84): ring exchange of one ghost row
+// on each side ([PETSc] DMGlobalToLocal).  `owned` = first owned row, nrows rows of rowlen doubles; the ghost rows are
+// owned - rowlen and owned + nrows * rowlen.  Grouped ncclSend / ncclRecv with the two ring neighbours (with two ranks
+// both neighbours are the same peer: sends and receives pair up in issue order).
+int ctx_ring_halo(p4b_ctx *c, double *owned, size_t rowlen, int nrows) {
+    if (c->nranks == 1) {      // the rank is its own neighbour on both sides
+        P4B_CUDA(cudaMemcpyAsync(owned - rowlen, owned + (size_t)(nrows - 1) * rowlen, sizeof(double) * rowlen,
+                                 cudaMemcpyDeviceToDevice, c->stream));
+        P4B_CUDA(cudaMemcpyAsync(owned + (size_t)nrows * rowlen, owned, sizeof(double) * rowlen, cudaMemcpyDeviceToDevice,
+                                 c->stream));
+        return 0;
+    }
+    const int prev = (c->rank + c->nranks - 1) % c->nranks, next = (c->rank + 1) % c->nranks;
+    g_launch_count++;          // (one NCCL kernel per grouped exchange)
+    P4B_NCCL(g_nccl.GroupStart());
+    P4B_NCCL(g_nccl.Send(owned, rowlen, ncclFloat64, prev, c->comm, c->stream));                                   // my first row
+    P4B_NCCL(g_nccl.Send(owned + (size_t)(nrows - 1) * rowlen, rowlen, ncclFloat64, next, c->comm, c->stream));   // my last row
+    P4B_NCCL(g_nccl.Recv(owned + (size_t)nrows * rowlen, rowlen, ncclFloat64, next, c->comm, c->stream));         // next's first
+    P4B_NCCL(g_nccl.Recv(owned - rowlen, rowlen, ncclFloat64, prev, c->comm, c->stream));                         // prev's last
+    P4B_NCCL(g_nccl.GroupEnd());
+    return 0;
+}
+// in-place all-gather: rank r's `count` doubles live at full + r * count
+int ctx_allgather(p4b_ctx *c, double *full, size_t count) {
+    if (c->nranks == 1) return 0;
+    g_launch_count++;
+    P4B_NCCL(g_nccl.AllGather(full + (size_t)c->rank * count, full, count, ncclFloat64, c->comm, c->stream));
+    return 0;
+}
 extern long long g_recognise_residual, g_gmres_cgs;           // defined in nk_device.cu
 }  // namespace p4b
 

@@ -98,11 +98,13 @@ int launch_minimal_function(cudaStream_t st, int mx, int my, int zs, int zm, dou
 }
 
 // ---------------------------------------------------------------------------------------------- pattern.c
-__global__ void __launch_bounds__(256) pattern_init_kernel(int mx, int my, double L, const double2 *__restrict__ noise,
-                                                            double level, double2 *__restrict__ Y) {
+// (rows [ys, ys + ym) of the my-row grid: a y-slab of a multi-GPU run; ys = 0, ym = my is the whole grid)
+__global__ void __launch_bounds__(256) pattern_init_kernel(int mx, int my, int ys, int ym, double L,
+                                                            const double2 *__restrict__ noise, double level,
+                                                            double2 *__restrict__ Y) {
     const int n = blockIdx.x * 256 + threadIdx.x;
-    if (n >= mx * my) return;
-    const int j = n / mx, i = n - j * mx;
+    if (n >= mx * ym) return;
+    const int jl = n / mx, i = n - jl * mx, j = jl + ys;
     const double x = i * (L / mx), y = j * (L / my);
     const double ledge = (L - 0.5) / 2.0, redge = L - ledge;
     const double PI = 3.14159265358979323846264338327950288;
@@ -126,15 +128,17 @@ __global__ void __launch_bounds__(256) pattern_rhs_kernel(int n, double phi, dou
 }
 
 // F = Ydot - C L9(Y)  (use_shift = 0)   or   J X = shift*X - C L9(X)  (use_shift = 1, Ydot ignored)
+// ywrap = 1: the my rows are the whole periodic grid.  ywrap = 0: they are a y-slab whose ghost rows -1 and my are in
+// memory on both sides (multi-GPU; filled by the ring exchange), so there is no wrap in y.
 __global__ void __launch_bounds__(256) pattern_ifunction_kernel(int mx, int my, double Cu, double Cv, int use_shift,
-                                                                 double shift, const double2 *__restrict__ Y,
+                                                                 double shift, int ywrap, const double2 *__restrict__ Y,
                                                                  const double2 *__restrict__ Ydot,
                                                                  double2 *__restrict__ F) {
     const int n = blockIdx.x * 256 + threadIdx.x;
     if (n >= mx * my) return;
     const int j = n / mx, i = n - j * mx;
     const int iw = (i == 0) ? mx - 1 : i - 1, ie = (i == mx - 1) ? 0 : i + 1;      // periodic wrap
-    const int js = (j == 0) ? my - 1 : j - 1, jn = (j == my - 1) ? 0 : j + 1;
+    const int js = (j == 0 && ywrap) ? my - 1 : j - 1, jn = (j == my - 1 && ywrap) ? 0 : j + 1;
     const double2 c = Y[n];
     const double2 nw = Y[jn * mx + iw], nn = Y[jn * mx + i], ne = Y[jn * mx + ie];
     const double2 ww = Y[j * mx + iw], ee = Y[j * mx + ie];
@@ -147,9 +151,11 @@ __global__ void __launch_bounds__(256) pattern_ifunction_kernel(int mx, int my, 
     F[n] = make_double2(d.x - Cu * lapu, d.y - Cv * lapv);
 }
 
-int launch_pattern_init(cudaStream_t st, int mx, int my, double L, double *Y, const double *noise, double level) {
-    pattern_init_kernel<<<(mx * my + 255) / 256, 256, 0, st>>>(mx, my, L, reinterpret_cast<const double2 *>(noise), level,
-                                                               reinterpret_cast<double2 *>(Y));
+int launch_pattern_init(cudaStream_t st, int mx, int my, double L, double *Y, const double *noise, double level, int ys,
+                        int ym) {
+    if (ym < 0) ym = my;
+    pattern_init_kernel<<<(mx * ym + 255) / 256, 256, 0, st>>>(mx, my, ys, ym, L, reinterpret_cast<const double2 *>(noise),
+                                                               level, reinterpret_cast<double2 *>(Y));
     P4B_LAUNCH_CHECK();
     return 0;
 }
@@ -160,10 +166,10 @@ int launch_pattern_rhs(cudaStream_t st, int n, double phi, double kappa, const d
     return 0;
 }
 int launch_pattern_ifunction(cudaStream_t st, int mx, int my, double Cu, double Cv, int use_shift, double shift,
-                             const double *Y, const double *Ydot, double *F) {
+                             const double *Y, const double *Ydot, double *F, int ywrap) {
     pattern_ifunction_kernel<<<(mx * my + 255) / 256, 256, 0, st>>>(
-        mx, my, Cu, Cv, use_shift, shift, reinterpret_cast<const double2 *>(Y), reinterpret_cast<const double2 *>(Ydot),
-        reinterpret_cast<double2 *>(F));
+        mx, my, Cu, Cv, use_shift, shift, ywrap, reinterpret_cast<const double2 *>(Y),
+        reinterpret_cast<const double2 *>(Ydot), reinterpret_cast<double2 *>(F));
     P4B_LAUNCH_CHECK();
     return 0;
 }

@@ -13,8 +13,12 @@
 
 namespace p4b {
 
-// defined in mg.cu (the context owns the stream and the reduction scratch)
+// defined in mg.cu (the context owns the stream, the reduction scratch and the communicator)
 cudaStream_t ctx_stream(p4b_ctx *c);
+int ctx_rank(p4b_ctx *c);
+int ctx_nranks(p4b_ctx *c);
+int ctx_ring_halo(p4b_ctx *c, double *owned, size_t rowlen, int nrows);
+int ctx_allgather(p4b_ctx *c, double *full, size_t count);
 
 struct DeviceOps {
     p4b_ctx *c;
@@ -110,6 +114,196 @@ struct DeviceOps {
 
 extern long long g_gmres_cgs;
 inline bool DeviceOps::gmres_cgs() const { return g_gmres_cgs != 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// pattern.c on y-slabs (BASELINE config 5: 2048^2 on 8 GPUs).  The DMDA of c/ch5/pattern.c:79-84 is periodic in both
+// directions with a box stencil of width 1; [PETSc] splits it over the ranks and DMGlobalToLocal fills one ghost row per
+// side from the ring neighbours.  Here: rank r owns rows [r m/P, (r+1) m/P) of every level whose rows divide evenly
+// into an even number per rank; the coarser levels (and always the base grid, whose operator is inverted densely) are
+// REPLICATED on every rank -- computed redundantly, without communication -- after one all-gather of the restricted
+// residual ([PETSc]'s PCREDUNDANT idea applied to whole levels, as the fish hierarchy does).  ts_solver.hpp does not
+// know: it passes global sizes (m, n = 2 m^2) and this set of operations translates them --
+//   vectors of a distributed level are stored [ghost row | owned rows | ghost row]; the pointer handed out is the first
+//   owned row; BLAS-1 operations run over the owned rows, dot products and norms are all-reduced (p4b_vec_*);
+//   stencil kernels (F, J x, smoother steps) exchange the operand's ghost rows first and run with ywrap = 0;
+//   restriction / injection onto the first replicated level compute this rank's coarse rows in place and all-gather;
+//   prolongation from it reads the rank's coarse rows (+ the wrapped row above) out of the replicated copy.
+// Every node's arithmetic is the single-GPU kernels' arithmetic on the same neighbour values, so a run differs from the
+// one-GPU run only by the rounding of the all-reduced dot products.
+// ---------------------------------------------------------------------------------------------------------
+struct SlabPlan {
+    struct Lev { int m; bool dist; int ys, ym; };
+    std::vector<Lev> lev;       // finest first
+    int P = 1, rank = 0;
+    // levels of the periodic hierarchy m, m/2, ... down to base (ts_solver.hpp StageOperator::create)
+    int build(int m, int base, bool mg, int P_, int rank_) {
+        P = P_; rank = rank_;
+        std::vector<int> sizes{m};
+        if (mg) while (sizes.back() > base && sizes.back() % 2 == 0) sizes.push_back(sizes.back() / 2);
+        lev.clear();
+        bool dist = true;
+        for (size_t l = 0; l < sizes.size(); l++) {
+            const int ml = sizes[l];
+            const bool last = mg && sizes.size() > 1 && l + 1 == sizes.size();
+            // a distributed level feeds its coarser level with ym / 2 rows per rank: ym must be even (>= 2)
+            if (ml % P != 0 || (ml / P) % 2 != 0 || last) dist = false;
+            Lev L;
+            L.m = ml; L.dist = dist;
+            L.ym = dist ? ml / P : ml;
+            L.ys = dist ? rank * (ml / P) : 0;
+            lev.push_back(L);
+        }
+        return lev[0].dist ? 0 : 60;
+    }
+    const Lev *find(int m) const {
+        for (auto &L : lev) if (L.m == m) return &L;
+        return nullptr;
+    }
+    const Lev *find_n(size_t n) const {
+        for (auto &L : lev) if ((size_t)2 * L.m * L.m == n) return &L;
+        return nullptr;
+    }
+};
+
+struct SlabPatternOps : DeviceOps {
+    SlabPlan plan;
+    std::vector<std::pair<double *, double *>> owned_base;      // (pointer handed out, allocation)
+    double *tmp = nullptr;
+    size_t tmp_cap = 0;
+    SlabPatternOps(p4b_ctx *c_, cudaStream_t st_) : DeviceOps{c_, st_} {}
+    size_t local_n(size_t n) const {
+        const SlabPlan::Lev *L = plan.find_n(n);
+        return (L && L->dist) ? (size_t)2 * L->m * L->ym : n;
+    }
+    double *alloc(size_t n) {
+        const SlabPlan::Lev *L = plan.find_n(n);
+        if (!L || !L->dist) return DeviceOps::alloc(n);
+        const size_t row = (size_t)2 * L->m;
+        double *base = DeviceOps::alloc(row * (size_t)(L->ym + 2));
+        if (!base) return nullptr;
+        cu(cudaMemsetAsync(base, 0, sizeof(double) * row * (size_t)(L->ym + 2), st));
+        owned_base.push_back({base + row, base});
+        return base + row;
+    }
+    void release(double *p) {
+        for (size_t i = 0; i < owned_base.size(); i++)
+            if (owned_base[i].first == p) {
+                DeviceOps::release(owned_base[i].second);
+                owned_base.erase(owned_base.begin() + i);
+                return;
+            }
+        DeviceOps::release(p);
+    }
+    double *scratch(size_t n) {
+        if (n > tmp_cap) {
+            if (tmp) DeviceOps::release(tmp);
+            tmp = DeviceOps::alloc(n);
+            tmp_cap = n;
+        }
+        return tmp;
+    }
+    void finish() { if (tmp) DeviceOps::release(tmp); tmp = nullptr; tmp_cap = 0; }
+    // BLAS-1 over the owned rows; reductions are all-reduced inside p4b_vec_* (the context knows its communicator)
+    double dot(size_t n, const double *x, const double *y) { return DeviceOps::dot(local_n(n), x, y); }
+    void mdot(size_t n, int k, const double *const *X, const double *y, double *res) { DeviceOps::mdot(local_n(n), k, X, y, res); }
+    double norm2(size_t n, const double *x) { return DeviceOps::norm2(local_n(n), x); }
+    double norminf(size_t n, const double *x) { return DeviceOps::norminf(local_n(n), x); }
+    double wrms2(size_t n, const double *x, const double *y, double atol, double rtol) {
+        // [PETSc] TSErrorWeightedNorm2 divides the global sum by the global length: the caller does (ts_solver.hpp)
+        return DeviceOps::wrms2(local_n(n), x, y, atol, rtol);
+    }
+    void axpy(size_t n, double a, const double *x, double *y) { DeviceOps::axpy(local_n(n), a, x, y); }
+    void aypx(size_t n, double a, const double *x, double *y) { DeviceOps::aypx(local_n(n), a, x, y); }
+    void axpby(size_t n, double a, const double *x, double b, const double *y, double *out) { DeviceOps::axpby(local_n(n), a, x, b, y, out); }
+    void copy(size_t n, const double *x, double *y) { DeviceOps::copy(local_n(n), x, y); }
+    void set(size_t n, double a, double *y) { DeviceOps::set(local_n(n), a, y); }
+    void halo(const SlabPlan::Lev &L, const double *v) { chk(ctx_ring_halo(c, const_cast<double *>(v), (size_t)2 * L.m, L.ym)); }
+    static void coef(const PO &o, int m, double *Cu, double *Cv) {
+        const double h = o.L / (double)m;                      // pattern.c:246
+        *Cu = o.Du / (6.0 * h * h);
+        *Cv = o.Dv / (6.0 * h * h);
+    }
+    void pattern_initial_state(int mx, int my, double L, double *Y) {
+        const SlabPlan::Lev *lv = plan.find(mx);
+        if (!lv || !lv->dist) { DeviceOps::pattern_initial_state(mx, my, L, Y); return; }
+        chk(launch_pattern_init(st, mx, my, L, Y, nullptr, 0.0, lv->ys, lv->ym));
+    }
+    void pattern_ifunction(int m, const PO &o, const double *Y, const double *Ydot, double *F) {
+        const SlabPlan::Lev *lv = plan.find(m);
+        if (!lv || !lv->dist) { DeviceOps::pattern_ifunction(m, o, Y, Ydot, F); return; }
+        double Cu, Cv;
+        coef(o, m, &Cu, &Cv);
+        halo(*lv, Y);
+        chk(launch_pattern_ifunction(st, m, lv->ym, Cu, Cv, 0, 0.0, Y, Ydot, F, 0));
+    }
+    void pattern_rhsfunction(int m, const PO &o, const double *Y, double *G) {
+        const SlabPlan::Lev *lv = plan.find(m);
+        if (!lv || !lv->dist) { DeviceOps::pattern_rhsfunction(m, o, Y, G); return; }
+        chk(launch_pattern_rhs(st, m * lv->ym, o.phi, o.kappa, Y, G));
+    }
+    void jac(int mode, int m, const PO &o, double shift, const double *Y, const double *X, const double *b, const double *pm1,
+             double ca, double cb, double cg, int jacobi, double *out) {
+        const SlabPlan::Lev *lv = plan.find(m);
+        double Cu, Cv;
+        coef(o, m, &Cu, &Cv);
+        if (!lv || !lv->dist) {
+            chk(launch_pattern_jac(st, mode, m, m, Cu, Cv, shift, o.phi, o.kappa, Y, X, b, pm1, ca, cb, cg, jacobi, out, 1));
+            return;
+        }
+        if (mode != 2) halo(*lv, X);
+        chk(launch_pattern_jac(st, mode, m, lv->ym, Cu, Cv, shift, o.phi, o.kappa, Y, X, b, pm1, ca, cb, cg, jacobi, out, 0));
+    }
+    void pattern_jac_apply(int m, const PO &o, double shift, const double *Y, const double *X, double *out) {
+        jac(0, m, o, shift, Y, X, nullptr, nullptr, 0, 0, 0, 0, out);
+    }
+    void pattern_jac_lin(int m, const PO &o, double shift, const double *Y, const double *X, const double *b, const double *pm1,
+                         double ca, double cb, double cg, int jacobi, double *out) {
+        jac(1, m, o, shift, Y, X, b, pm1, ca, cb, cg, jacobi, out);
+    }
+    double pattern_jac_gershgorin(int m, const PO &o, double shift, const double *Y, double *work) {
+        jac(2, m, o, shift, Y, Y, nullptr, nullptr, 0, 0, 0, 0, work);
+        return norminf((size_t)2 * m * m, work);          // max over the owned rows, all-reduced (max) over the ranks
+    }
+    // coarse level Mc x Mc, fine 2 Mc x 2 Mc
+    void pattern_restrict(int Mx, int My, const double *rf, double *bc) {
+        const SlabPlan::Lev *F = plan.find(2 * Mx), *C = plan.find(Mx);
+        if (!F || !C || !F->dist) { DeviceOps::pattern_restrict(Mx, My, rf, bc); return; }
+        halo(*F, rf);
+        const int ymc = F->ym / 2;
+        if (C->dist) { chk(launch_pattern_transfer(st, 0, Mx, ymc, rf, bc, 0)); return; }
+        const size_t cnt = (size_t)2 * Mx * ymc;
+        chk(launch_pattern_transfer(st, 0, Mx, ymc, rf, bc + (size_t)plan.rank * cnt, 0));
+        chk(ctx_allgather(c, bc, cnt));
+    }
+    void pattern_inject(int Mx, int My, const double *yf, double *yc) {
+        const SlabPlan::Lev *F = plan.find(2 * Mx), *C = plan.find(Mx);
+        if (!F || !C || !F->dist) { DeviceOps::pattern_inject(Mx, My, yf, yc); return; }
+        const int ymc = F->ym / 2;
+        if (C->dist) { chk(launch_pattern_transfer(st, 2, Mx, ymc, yf, yc, 0)); return; }
+        const size_t cnt = (size_t)2 * Mx * ymc;
+        chk(launch_pattern_transfer(st, 2, Mx, ymc, yf, yc + (size_t)plan.rank * cnt, 0));
+        chk(ctx_allgather(c, yc, cnt));
+    }
+    void pattern_prolong_add(int Mx, int My, const double *xc, double *xf) {
+        const SlabPlan::Lev *F = plan.find(2 * Mx), *C = plan.find(Mx);
+        if (!F || !C || !F->dist) { DeviceOps::pattern_prolong_add(Mx, My, xc, xf); return; }
+        const int ymc = F->ym / 2;
+        if (C->dist) {
+            halo(*C, xc);
+            chk(launch_pattern_transfer(st, 1, Mx, ymc, xc, xf, 0));
+            return;
+        }
+        // the rank's coarse rows and the (periodically wrapped) row above them, out of the replicated copy
+        const size_t row = (size_t)2 * Mx;
+        const int ysc = F->ys / 2;
+        double *t = scratch(row * (size_t)(ymc + 1));
+        cu(cudaMemcpyAsync(t, xc + (size_t)ysc * row, sizeof(double) * row * (size_t)ymc, cudaMemcpyDeviceToDevice, st));
+        cu(cudaMemcpyAsync(t + (size_t)ymc * row, xc + (size_t)((ysc + ymc) % Mx) * row, sizeof(double) * row,
+                           cudaMemcpyDeviceToDevice, st));
+        chk(launch_pattern_transfer(st, 1, Mx, ymc, t, xf, 0));
+    }
+};
+
 
 // The same operations with the RESIDUAL supplied by the caller as a host callback -- the FormFunctionLocal contract of
 // the reference's drivers (c/ch7/minimal.c:210-282 is registered with DMDASNESSetFunctionLocal, :138-140): the iterate
@@ -388,6 +582,23 @@ extern "C" int p4b_pattern_default_opts(p4b_pattern_opts *o) {
     return 0;
 }
 
+// host only: which levels of the periodic hierarchy m, m/2, ... grid_x are distributed over y-slabs on nranks ranks, and
+// the rows rank `rank` owns on each (see SlabPlan above).  Arrays of length >= 32; returns the number of levels.
+extern "C" int p4b_pattern_slab_plan(int m, int grid_x, int mg, int nranks, int rank, int *level_m, int *distributed, int *ys,
+                                     int *ym) {
+    if (m < 3 || grid_x < 3 || nranks < 1 || rank < 0 || rank >= nranks) return -fail(62, "p4b_pattern_slab_plan: bad argument");
+    SlabPlan pl;
+    if (pl.build(m, grid_x, mg != 0, nranks, rank) && nranks > 1)
+        return -fail(60, "pattern on %d ranks: the %d rows of the grid must split into an even number of rows per rank", nranks, m);
+    int nl = 0;
+    for (auto &L : pl.lev) {
+        if (nl >= 32) break;
+        level_m[nl] = L.m; distributed[nl] = L.dist ? 1 : 0; ys[nl] = L.ys; ym[nl] = L.ym;
+        nl++;
+    }
+    return nl;
+}
+
 extern "C" int p4b_pattern_solve(p4b_ctx *c, const p4b_pattern_opts *opts, p4b_line_fn line, void *line_ctx, double *Y_out,
                                  size_t Y_capacity, p4b_pattern_result *result) {
     return p4b_pattern_solve_from(c, opts, nullptr, line, line_ctx, Y_out, Y_capacity, result);
@@ -401,19 +612,39 @@ extern "C" int p4b_pattern_solve_from(p4b_ctx *c, const p4b_pattern_opts *opts, 
     if (o.grid_x < 3 || o.grid_y < 3) return fail(60, "periodic grid needs at least 3 nodes per dimension");
     if ((o.grid_x << o.refine) != (o.grid_y << o.refine)) return fail(1, "pattern.c requires mx == my");            // pattern.c:89
     if (o.ts_type < nk::TS_ARKIMEX || o.ts_type > nk::TS_BDF) return fail(62, "ts_type: arkimex (0), beuler (1), cn (2), bdf (3)");
-    DeviceOps ops{c, ctx_stream(c)};
     nk::Printer pr{line, line_ctx};
     double *Y = nullptr;
     nk::PatternResult &R = *reinterpret_cast<nk::PatternResult *>(result);
-    int rc = nk::pattern_solve(&ops, o, pr, Y_out ? &Y : nullptr, &R, Y0);
-    if (!rc && ops.error()) rc = ops.error();
-    if (!rc && Y_out) {
-        const size_t n = (size_t)2 * R.m * R.m;
-        if (Y_capacity < n) rc = 63;
-        else if (cudaMemcpyAsync(Y_out, Y, sizeof(double) * n, cudaMemcpyDeviceToDevice, ops.st) != cudaSuccess) rc = 70;
+    int rc = 0;
+    if (ctx_nranks(c) > 1) {
+        // y-slabs: Y0 / Y_out are this rank's rows (2 m * m/P doubles, p4b_pattern_slab), lines come from every rank
+        SlabPatternOps ops(c, ctx_stream(c));
+        const int m = o.grid_x << o.refine;
+        if (ops.plan.build(m, o.grid_x, o.pc_type == nk::PC_MG, ctx_nranks(c), ctx_rank(c)))
+            return fail(60, "pattern on %d ranks: the %d rows of the grid must split into an even number of rows per rank",
+                        ctx_nranks(c), m);
+        rc = nk::pattern_solve(&ops, o, pr, Y_out ? &Y : nullptr, &R, Y0);
+        if (!rc && ops.error()) rc = ops.error();
+        if (!rc && Y_out) {
+            const size_t n = ops.local_n((size_t)2 * R.m * R.m);
+            if (Y_capacity < n) rc = 63;
+            else if (cudaMemcpyAsync(Y_out, Y, sizeof(double) * n, cudaMemcpyDeviceToDevice, ops.st) != cudaSuccess) rc = 70;
+        }
+        if (Y) ops.release(Y);
+        ops.finish();
+        cudaStreamSynchronize(ops.st);
+    } else {
+        DeviceOps ops{c, ctx_stream(c)};
+        rc = nk::pattern_solve(&ops, o, pr, Y_out ? &Y : nullptr, &R, Y0);
+        if (!rc && ops.error()) rc = ops.error();
+        if (!rc && Y_out) {
+            const size_t n = (size_t)2 * R.m * R.m;
+            if (Y_capacity < n) rc = 63;
+            else if (cudaMemcpyAsync(Y_out, Y, sizeof(double) * n, cudaMemcpyDeviceToDevice, ops.st) != cudaSuccess) rc = 70;
+        }
+        if (Y) cudaFreeAsync(Y, ops.st);
+        cudaStreamSynchronize(ops.st);
     }
-    if (Y) cudaFreeAsync(Y, ops.st);
-    cudaStreamSynchronize(ops.st);
     if (rc == 61) return fail(61, "base grid of the periodic hierarchy has more than 512 unknowns: use a coarser -da_grid_x/_y");
     if (rc == 62) return fail(62, "base-grid stage Jacobian is singular");
     if (rc == 63) return fail(63, "Y_out holds %zu doubles, the grid needs 2 x %d x %d", Y_capacity, R.m, R.m);

@@ -169,6 +169,7 @@ _SIGS = {
     "p4b_minimal_function": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, _D, _D]),
     "p4b_pattern_initial_state": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D]),
     "p4b_pattern_initial_state_noisy": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, C.c_double, _D]),
+    "p4b_pattern_slab_plan": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int)] * 4),
     "p4b_rander48_seed": (C.c_ulonglong, [C.c_ulong]),
     "p4b_rander48_fill": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_size_t, C.c_void_p]),
     "p4b_pattern_rhsfunction": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, _D, _D]),

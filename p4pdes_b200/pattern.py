@@ -271,13 +271,28 @@ def _pattern_native(opt: PatternOptions, ctx, out) -> PatternReport:
     o.ksp_rtol, o.ksp_max_it, o.gmres_restart = opt.ksp_rtol, opt.ksp_max_it, opt.gmres_restart
     o.snes_converged_reason, o.ksp_converged_reason = int(opt.snes_converged_reason), int(opt.ksp_converged_reason)
     m = opt.grid_x * 2 ** opt.refine
-    Y = ctx.empty(2 * m * m)
+    # a context with a communicator (Context(distributed=True) under torchrun) runs on y-slabs: this rank's rows only
+    nranks, rank = getattr(ctx, "nranks", 1), getattr(ctx, "rank", 0)
+    rows, ys = m, 0
+    if nranks > 1:
+        if m % nranks or (m // nranks) % 2:
+            raise ValueError("pattern on %d ranks: %d rows must split into an even number of rows per rank" % (nranks, m))
+        rows, ys = m // nranks, rank * (m // nranks)
+    Y = ctx.empty(2 * m * rows)
     res = L.PatternResult()
-    cb = L.LINE_FN(lambda line, _ctx: out(line.decode()))
+    say = out if rank == 0 else (lambda s: None)
+    cb = L.LINE_FN(lambda line, _ctx: say(line.decode()))
     t0 = time.perf_counter()
-    if opt.noisy_init > 0.0:        # the caller's initial state: what the shim's TSSolve does with pattern.c's Vec
-        out("running on %d x %d grid with square cells of side h = %.6f ..." % (m, m, opt.L / m))
-        initial_state(ctx, opt, m, Y)
+    if opt.noisy_init > 0.0:
+        # the caller's initial state (what the shim's TSSolve does with pattern.c's Vec); on slabs: rows [ys, ys + rows)
+        say("running on %d x %d grid with square cells of side h = %.6f ..." % (m, m, opt.L / m))
+        if nranks > 1:
+            full = ctx.empty(2 * m * m)
+            initial_state(ctx, opt, m, full)
+            Y.copy_(full[2 * m * ys:2 * m * (ys + rows)])
+            del full
+        else:
+            initial_state(ctx, opt, m, Y)
         L.check(ctx.lib.p4b_pattern_solve_from(ctx.h, C.byref(o), Y.data_ptr(), cb, None, Y.data_ptr(), Y.numel(),
                                                C.byref(res)))
     else:

@@ -86,3 +86,35 @@ def test_peer_transport_is_bit_identical_to_nccl_on_two_ranks():
     nccl = run_worker(2, *args, "--comm-peer", 0)
     assert peer["history"] == nccl["history"]
     assert peer["sol_sha1"] == nccl["sol_sha1"]
+
+
+# ---- pattern.c on y-slabs (BASELINE config 5 names 8 GPUs; c/ch5/pattern.c:79-84 periodic DMDA, ring neighbours) ----
+def run_pattern_worker(nproc, argv, *extra, timeout=900):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", "29537", os.path.join(ROOT, "tests", "mgpu_pattern_worker.py"),
+           "--argv", argv, *extra]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    for line in p.stdout.splitlines():
+        if line.startswith("MGPU_RESULT "):
+            return json.loads(line[len("MGPU_RESULT "):])
+    raise AssertionError("worker failed:\n" + p.stdout[-3000:] + "\n" + p.stderr[-3000:])
+
+
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+@pytest.mark.parametrize("argv", [
+    "-da_grid_x 4 -da_grid_y 4 -da_refine 4 -ts_monitor -ts_max_time 40 -pc_type mg",                   # ARKIMEX, adaptive (64^2)
+    "-da_grid_x 4 -da_grid_y 4 -da_refine 5 -ts_type beuler -ts_dt 5 -ts_max_time 15 -ts_monitor -pc_type mg "
+    "-snes_converged_reason -ksp_converged_reason",                                                       # Newton + GMRES + MG (128^2)
+    "-da_grid_x 4 -da_grid_y 4 -da_refine 4 -ts_type cn -ts_dt 4 -ts_max_time 12 -ts_monitor -pc_type none",
+    "-da_grid_x 4 -da_grid_y 4 -da_refine 4 -ts_type bdf -ts_max_time 20 -ts_monitor -pc_type mg",
+    "-da_grid_x 4 -da_grid_y 4 -da_refine 4 -ts_monitor -ts_max_time 20 -pc_type mg -ptn_noisy_init 0.15",
+])
+def test_pattern_on_slabs_equals_the_single_gpu_run(nproc, argv):
+    """Same printed lines (adaptive step sequence, Newton and Krylov counts), final state within 1e-12 relative of the
+    one-GPU run: per node the slab kernels do the single-GPU arithmetic; only the all-reduced dot products round
+    differently."""
+    if ngpu() < nproc:
+        pytest.skip("needs %d GPUs" % nproc)
+    r = run_pattern_worker(nproc, argv)
+    assert r["world"] == nproc and r["same_steps"] and r["same_lines"], r["lines"]
+    assert r["rel_diff"] < 1e-12, r["rel_diff"]
