@@ -188,10 +188,21 @@ def run_secondary(args):
     from p4pdes_b200 import lib as L
     from p4pdes_b200 import minimal as pm, pattern as pp
     from p4pdes_b200.fish import Context, Multigrid, mg_options
-    torch.cuda.set_device(0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and args.config != "c5":
+        if rank == 0:
+            print(json.dumps({"config": {"workload": args.config}, "n_gpus": world,
+                              "unavailable": "this configuration runs on one GPU (only c3 / c2 z-slabs and c5 y-slabs shard)"}))
+        return 0
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     side = torch.cuda.Stream()
     torch.cuda.set_stream(side)
-    ctx = Context(0)
+    ctx = Context(local_rank, distributed=world > 1)
     lib = ctx.lib
     peak, peak_src = peaks()
     sampler = ClockSampler(0)
@@ -283,15 +294,23 @@ def run_secondary(args):
         for _ in range(max(1, min(args.warmup, 2))):
             rep = pp.pattern_main(argv, ctx, native=True)
         torch.cuda.synchronize()
-        sampler.start()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        if rank == 0:
+            sampler.start()
         l0 = lib.p4b_launch_count()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             rep = pp.pattern_main(argv, ctx, native=True)
-            yh = rep.Y.cpu()
+            yh = rep.Y.cpu()                       # each rank's rows reach its host
         torch.cuda.synchronize()
         nsteps = len(rep.steps)
         ms = ms_e2e = (time.perf_counter() - t0) / args.steps * 1e3
+        if world > 1:                              # max over ranks (every rank sits in the same all-reduces)
+            tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = ms_e2e = float(tt.item())
         launches = lib.p4b_launch_count() - l0
         m = 2048
         ndof = 2 * m * m * nsteps                  # unknowns advanced: 8.4 M per implicit step x steps per run
@@ -300,9 +319,13 @@ def run_secondary(args):
         options = argv + " -mg_levels_pc_type jacobi"
         metric = "pattern2d_implicit_steps_mdof_per_s"
         extra = {"ts_steps": nsteps, "ms_per_ts_step": ms / nsteps, "newton_per_step": [s[2] for s in rep.steps],
-                 "note": "one GPU; -p4b_mg_rscale 0.25 (averaging restriction) keeps GMRES counts mesh independent "
+                 "parallelism": "y-slabs x%d (ring ghost rows + all-reduce over NCCL; levels below 16 rows replicated)" % world,
+                 "note": "-p4b_mg_rscale 0.25 (averaging restriction) keeps GMRES counts mesh independent "
                          "(DESIGN.md section 8); the final state (67 MB) is copied to the host"}
         h2d, d2h = 0, 16 * m * m
+        if rank != 0:
+            dist.destroy_process_group()
+            return 0
         from p4pdes_b200 import callbacks as cb
         Y = cb.pattern_initial_state(ctx, m, m)
         X, bb, out = Y.clone(), Y.clone(), ctx.empty(2 * m * m)
@@ -315,7 +338,7 @@ def run_secondary(args):
                 "alg_bytes_per_launch": by, "ms_per_launch": kms, "traffic": None,
                 "how": "kernel timed alone (30 launches, CUDA events) at 2048^2 x 2; 67 MB per operand: partly L2 resident"}
     clocks = sampler.stop()
-    line = {"metric": metric, "value": ndof / (ms * 1e-3) / 1e6, "unit": "MDOF/s", "n_gpus": 1, "steps": args.steps,
+    line = {"metric": metric, "value": ndof / (ms * 1e-3) / 1e6, "unit": "MDOF/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "solve_s": ms * 1e-3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload, "options": options, "baseline_config": args.config,
@@ -326,6 +349,8 @@ def run_secondary(args):
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
     line.update(extra)
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 

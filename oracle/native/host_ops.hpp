@@ -38,6 +38,11 @@ struct HostOps {
     }
     void copy(size_t n, const double *x, double *y) { memmove(y, x, sizeof(double) * n); }
     void set(size_t n, double a, double *y) { for (size_t i = 0; i < n; i++) y[i] = a; }
+    void band_inverse(int n, int bw, const std::vector<double> &B, double *Ainv) {
+        std::vector<double> inv;
+        p4b::nk::band_inverse_host(B, n, bw, &inv);
+        memcpy(Ainv, inv.data(), sizeof(double) * inv.size());
+    }
     void user_monitor(int, int, int, double, int, const double *) {}
     bool verify_converged(int, int, const double *, const double *) { return true; }
     void set_linearisation(const double *) {}

@@ -229,6 +229,35 @@ __global__ void __launch_bounds__(256) pattern_jac_kernel(int mx, int my, double
     }
 }
 
+// A^-1 from banded LU factors (nk_solver.hpp stencil9_band_lu): thread `col` solves L U x = e_col in place in column
+// `col` of the row-major inverse.  All threads of a warp touch the same row r of consecutive columns at the same time
+// (coalesced), the band entry they multiply with is a broadcast.  n = 1089, bw = 34 (the 33 x 33 base grid of
+// c/ch8/cluster.sh:70): ~0.3 ms against ~50 ms for the same loops on the host.
+__global__ void __launch_bounds__(128) band_inverse_kernel(int n, int bw, const double *__restrict__ B, double *Ainv) {
+    const int col = blockIdx.x * 128 + threadIdx.x;
+    if (col >= n) return;
+    const int W = 2 * bw + 1;
+    double *x = Ainv + col;                                    // x[r] = Ainv[r * n + col]
+    for (int r = 0; r < n; r++) x[(size_t)r * n] = (r == col) ? 1.0 : 0.0;
+    for (int r = col + 1; r < n; r++) {                        // forward: L y = e_col (y_r = 0 for r < col)
+        double s = 0.0;
+        const int c0 = max(col, r - bw);
+        for (int c = c0; c < r; c++) s += B[(size_t)r * W + (c - r + bw)] * x[(size_t)c * n];
+        x[(size_t)r * n] -= s;
+    }
+    for (int r = n - 1; r >= 0; r--) {                         // backward: U x = y
+        double s = x[(size_t)r * n];
+        const int c1 = min(n - 1, r + bw);
+        for (int c = r + 1; c <= c1; c++) s -= B[(size_t)r * W + (c - r + bw)] * x[(size_t)c * n];
+        x[(size_t)r * n] = s / B[(size_t)r * W + bw];
+    }
+}
+int launch_band_inverse(cudaStream_t st, int n, int bw, const double *B, double *Ainv) {
+    band_inverse_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, bw, B, Ainv);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_pattern_jac(cudaStream_t st, int mode, int mx, int my, double Cu, double Cv, double shift, double phi,
                        double kappa, const double *Y, const double *X, const double *b, const double *pm1, double ca,
                        double cb, double cg, int jacobi, double *out, int ywrap) {

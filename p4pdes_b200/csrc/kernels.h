@@ -104,6 +104,7 @@ int fd_jacobian_minimal(cudaStream_t st, int mx, int my, double q, double unorm,
 int launch_fd_perturb(cudaStream_t st, int mx, int my, int ci, int cj, double h, const double *u, double *up);
 int launch_fd_extract(cudaStream_t st, int mx, int my, int ci, int cj, double h, const double *F0, const double *Fp,
                       double *vals);
+int launch_band_inverse(cudaStream_t st, int n, int bw, const double *B, double *Ainv);   // dense A^-1 from band LU factors
 int launch_stencil9_apply(cudaStream_t st, int mx, int my, const double *vals, const double *x, double *y);
 int launch_pattern_jac(cudaStream_t st, int mode, int mx, int my, double Cu, double Cv, double shift, double phi,
                        double kappa, const double *Y, const double *X, const double *b, const double *pm1, double ca,

@@ -81,6 +81,13 @@ struct DeviceOps {
     void prolong_add2d(int fmx, int fmy, const double *xc, double *xf) { p4b_grid g = grid2d(fmx, fmy); chk(p4b_prolong_add(c, &g, xc, xf)); }
     void initial_state2d(int mx, int my, const double *g, double *u) { p4b_grid gr = grid2d(mx, my); chk(p4b_initial_state(c, &gr, g, 1, u)); }
     void dense_matvec(int n, const double *Ainv, const double *b, double *x) { chk(p4b_dense_matvec(c, n, Ainv, b, x)); }
+    // base-grid inverse from the band LU factors (host): the n column solves run on the device
+    void band_inverse(int n, int bw, const std::vector<double> &B, double *Ainv) {
+        double *dB = alloc(B.size());
+        from_host(B.data(), dB, B.size());
+        chk(launch_band_inverse(st, n, bw, dB, Ainv));
+        release(dB);
+    }
     // pattern.c
     typedef nk::PatternOpts PO;
     double wrms2(size_t n, const double *x, const double *y, double atol, double rtol) {

@@ -120,9 +120,13 @@ inline std::string g6(double v) {
 // diagonally dominant M-matrices plus finite-difference noise), then n banded solves.  [PETSc] PCLU on the base grid.
 // vals: 9 planes of n = mx*my doubles (host copy); Ainv: n*n doubles, row-major.
 // ---------------------------------------------------------------------------------------------------------
-inline int stencil9_inverse(const double *vals, int mx, int my, std::vector<double> *Ainv) {
+// Banded LU (no pivoting: the base-grid Jacobian is an M-matrix up to the differencing noise) of the 9-point matrix in
+// stencil9 layout.  Band storage B[r*W + (c - r + bw)], bw = mx + 1, W = 2 bw + 1; L unit lower.  O(n bw^2): about a
+// millisecond on the host for the 33 x 33 base grid of c/ch8/cluster.sh:70.
+inline int stencil9_band_lu(const double *vals, int mx, int my, std::vector<double> *Bout) {
     const int n = mx * my, bw = mx + 1, W = 2 * bw + 1;
-    std::vector<double> B((size_t)n * W, 0.0);                 // band storage: B[r*W + (c - r + bw)]
+    std::vector<double> &B = *Bout;
+    B.assign((size_t)n * W, 0.0);
     for (int j = 0; j < my; j++)
         for (int i = 0; i < mx; i++) {
             const int r = j * mx + i;
@@ -146,6 +150,14 @@ inline int stencil9_inverse(const double *vals, int mx, int my, std::vector<doub
             for (int c = k + 1; c <= cmax; c++) B[(size_t)r * W + (c - r + bw)] -= l * B[(size_t)k * W + (c - k + bw)];
         }
     }
+    return 0;
+}
+// A^-1 (dense, row-major) from the band factors: n independent column solves.  This is the host form (the CPU
+// instantiation of the solver templates); the library does the same on the device, one thread per column
+// (assembled.cu band_inverse_kernel) -- on the host it took ~50 ms per Newton step at n = 1089 and was, 30 Newton steps
+// over, most of the 2049^2 cluster run.
+inline void band_inverse_host(const std::vector<double> &B, int n, int bw, std::vector<double> *Ainv) {
+    const int W = 2 * bw + 1;
     Ainv->assign((size_t)n * n, 0.0);
     std::vector<double> x(n);
     for (int col = 0; col < n; col++) {
@@ -165,6 +177,22 @@ inline int stencil9_inverse(const double *vals, int mx, int my, std::vector<doub
         }
         for (int r = 0; r < n; r++) (*Ainv)[(size_t)r * n + col] = x[r];
     }
+}
+// both steps on the host (kept for callers that want the inverse there)
+inline int stencil9_inverse(const double *vals, int mx, int my, std::vector<double> *Ainv) {
+    std::vector<double> B;
+    if (stencil9_band_lu(vals, mx, my, &B)) return 1;
+    band_inverse_host(B, mx * my, mx + 1, Ainv);
+    return 0;
+}
+// base-grid inverse into Ops memory: band LU on the host, the n column solves wherever the operations run
+template <class Ops>
+inline int stencil9_inverse_ops(Ops *ops, const double *vals_dev, int mx, int my, double *Ainv_dev) {
+    const size_t n = (size_t)mx * my;
+    std::vector<double> hv(9 * n), B;
+    ops->to_host(vals_dev, hv.data(), 9 * n);
+    if (stencil9_band_lu(hv.data(), mx, my, &B)) return 62;
+    ops->band_inverse((int)n, mx + 1, B, Ainv_dev);
     return 0;
 }
 
@@ -233,16 +261,12 @@ struct AssembledMG {
         }
         Level<Ops> &C = L.back();
         if (C.n > 4225) return 61;                            // base grid larger than 65 x 65: refuse the dense solve
-        std::vector<double> hv(9 * C.n), inv;
-        ops->to_host(C.vals, hv.data(), 9 * C.n);
-        if (stencil9_inverse(hv.data(), C.mx, C.my, &inv)) return 62;
         if (!Ainv || n0 != (int)C.n) {
             if (Ainv) ops->release(Ainv);
             Ainv = ops->alloc(C.n * C.n);
             n0 = (int)C.n;
         }
-        ops->from_host(inv.data(), Ainv, C.n * C.n);
-        return 0;
+        return stencil9_inverse_ops(ops, C.vals, C.mx, C.my, Ainv);
     }
     void destroy() {
         if (Ainv) ops->release(Ainv);
@@ -501,11 +525,9 @@ int newton(Ops *ops, std::vector<Level<Ops>> &lev, const MinimalOpts &opt, const
             L.assemble(q, true);
             if (opt.pc_type == PC_MG) {                        // a single level: the "multigrid" is the direct solve
                 if (n > 4225) { rc = 61; break; }
-                std::vector<double> hv(9 * n), inv;
-                ops->to_host(L.vals, hv.data(), 9 * n);
-                if (stencil9_inverse(hv.data(), L.mx, L.my, &inv)) { rc = 62; break; }
                 if (!dense) dense = ops->alloc(n * n);
-                ops->from_host(inv.data(), dense, n * n);
+                rc = stencil9_inverse_ops(ops, L.vals, L.mx, L.my, dense);
+                if (rc) break;
                 M.dense = dense;
             }
         }

@@ -47,8 +47,12 @@ def main():
         if a.time:
             one = pp.pattern_main(a.argv, Context(local), native=True)
         out["one_gpu_seconds"] = one.seconds
-        out["same_steps"] = [[s[0], s[1], s[2]] for s in one.steps] == out["steps"]
+        # the all-reduced error norm rounds differently: times / steps agree to rounding, Newton counts exactly
+        a, b = [[s[0], s[1], s[2]] for s in one.steps], out["steps"]
+        out["same_steps"] = len(a) == len(b) and all(x[2] == y[2] and abs(x[0] - y[0]) <= 1e-9 * max(1.0, abs(x[0])) and
+                                                     abs(x[1] - y[1]) <= 1e-9 * max(1.0, abs(x[1])) for x, y in zip(a, b))
         out["same_lines"] = one.lines == rep.lines
+        out["one_gpu_lines"] = one.lines
         out["rel_diff"] = float(torch.linalg.vector_norm(Y - one.Y) / torch.linalg.vector_norm(one.Y))
         print("MGPU_RESULT " + json.dumps(out), flush=True)
     dist.barrier()

@@ -116,5 +116,18 @@ def test_pattern_on_slabs_equals_the_single_gpu_run(nproc, argv):
     if ngpu() < nproc:
         pytest.skip("needs %d GPUs" % nproc)
     r = run_pattern_worker(nproc, argv)
-    assert r["world"] == nproc and r["same_steps"] and r["same_lines"], r["lines"]
-    assert r["rel_diff"] < 1e-12, r["rel_diff"]
+    assert r["world"] == nproc and r["same_steps"], r["lines"]
+    # printed lines: identical, except that a GMRES count may move by one where the residual sits on the tolerance (the
+    # all-reduced dot products round differently): the north star's "same iteration count +-1"
+    import re
+    krylov_moved = False
+    assert len(r["lines"]) == len(r["one_gpu_lines"])
+    for a, b in zip(r["lines"], r["one_gpu_lines"]):
+        if a == b:
+            continue
+        ma, mb = re.fullmatch(r"(.*iterations )(\d+)", a), re.fullmatch(r"(.*iterations )(\d+)", b)
+        assert ma and mb and ma.group(1) == mb.group(1) and "Linear solve" in a, (a, b)
+        assert abs(int(ma.group(2)) - int(mb.group(2))) <= 1, (a, b)
+        krylov_moved = True
+    # same Krylov counts: the states agree to rounding; a moved count leaves the difference of two inexact solves
+    assert r["rel_diff"] < (1e-7 if krylov_moved else 1e-12), r["rel_diff"]
