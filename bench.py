@@ -250,6 +250,48 @@ def run_secondary(args):
                    "solve_s": r["seconds"], "ksp_its": r["its"], "sample": "the same solve; " + CPU_PORT_NOTE}
         except Exception as exc:
             cpu = {"value": None, "unit": "MDOF/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (exc,)}
+    elif args.config == "f3":
+        from p4pdes_b200.bratu import bratu_main
+        refine = args.refine if args.refine != 8 else 12          # --refine 12 (20481^2) unless given
+        argv = ("-da_grid_x 6 -da_grid_y 6 -lb_exact -snes_rtol 1.0e-10 -snes_converged_reason -lb_showcounts -snes_type fas "
+                "-snes_fas_type full -fas_levels_snes_type ngs -fas_levels_snes_ngs_sweeps 2 -fas_levels_snes_max_it 1 "
+                "-fas_coarse_snes_type ngs -fas_coarse_snes_ngs_sweeps 2 -fas_coarse_snes_max_it 4 -da_refine %d" % refine)   # bratu2D.c:15
+        for _ in range(max(1, min(args.warmup, 2))):
+            rep = bratu_main(argv, ctx)
+        torch.cuda.synchronize()
+        sampler.start()
+        l0 = lib.p4b_launch_count()
+        dev_ms, t0 = 0.0, time.perf_counter()
+        for _ in range(args.steps):
+            rep = bratu_main(argv, ctx, keep_solution=True)
+            dev_ms += rep.solve_ms
+            uh = torch.empty(rep.mx * rep.my, dtype=torch.float64).pin_memory() if _ == 0 else uh
+            uh.copy_(rep.u)                          # the solution reaches the host
+            del rep.u
+        torch.cuda.synchronize()
+        ms_e2e = (time.perf_counter() - t0) / args.steps * 1e3
+        ms = dev_ms / args.steps
+        launches = lib.p4b_launch_count() - l0
+        ndof = rep.mx * rep.my
+        workload = ("bratu2D.c Liouville-Bratu %d^2 (%d unknowns), FAS full cycles + nonlinear Gauss-Seidel (red-black), "
+                    "rtol 1e-10 (c/ch7/solns/bratu2D.c:15)" % (rep.mx, ndof))
+        options = argv
+        metric = "bratu2d_fas_ngs_solve_mdof_per_s"
+        extra = {"fas_its": rep.its, "errinf": rep.errinf, "residual_calls": rep.residual_calls, "ngs_calls": rep.ngs_calls,
+                 "reference_published": {"value": 12.7, "unit": "MDOF/s", "what": "4.0e8 unknowns in 31.50 s, mpiexec -n 20 on a "
+                                         "40-core workstation, lexicographic NGS (c/ch7/solns/bratu2D.c:9-19, BASELINE.md 1 "
+                                         "'adjacent'): other hardware, reported beside, not a same-box baseline"},
+                 "note": "ms_per_step = CUDA events around the solve; e2e adds the allocation of the hierarchy and the D2H "
+                         "copy of the solution (wall clock); the problem has no input vector (u0 = 0, analytic boundary data)"}
+        h2d, d2h = 0, 8 * ndof
+        m = rep.mx
+        uu, ff = ctx.zeros(m * m), ctx.empty(m * m)
+        kms = _time_kernel(lambda: L.check(lib.p4b_bratu_ngs(ctx.h, m, m, 1.0, 1, 1, None, uu.data_ptr())), reps=10, warm=2)
+        by = 2 * 16.0 * m * m                        # two half sweeps, each reads and writes u (the other colour's lines ride along)
+        roof = {"bound": "hbm", "kernel": "bratu_ngs_kernel (one red-black sweep = two half-sweep launches)",
+                "achieved": by / kms / 1e6, "peak": peak, "unit": "GB/s", "frac": by / kms / 1e6 / peak,
+                "alg_bytes_per_launch": by, "ms_per_launch": kms, "traffic": None,
+                "how": "one sweep (2 launches) timed alone, 10 repetitions, CUDA events; 3.4 GB per vector: exceeds L2"}
     elif args.config == "c4":
         argv = "-da_grid_x 33 -da_grid_y 33 -snes_grid_sequence 6 -snes_fd_color -pc_type mg"      # c/ch8/cluster.sh:70
         for _ in range(max(1, min(args.warmup, 2))):
@@ -360,9 +402,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5"],
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5", "f3"],
                     help="BASELINE.json configuration: c3 (default) = fish 3-D 513^3, the headline; c2 = fish 3-D 257^3; "
-                         "c1 = fish 2-D -da_refine 6; c4 = minimal.c 2049^2 (c/ch8/cluster.sh:70); c5 = pattern.c 2048^2 x 2")
+                         "c1 = fish 2-D -da_refine 6; c4 = minimal.c 2049^2 (c/ch8/cluster.sh:70); c5 = pattern.c 2048^2 x 2; "
+                         "f3 = c/ch7/solns/bratu2D.c FAS+NGS at 20481^2 (SURVEY 8 f3, the reference's one published throughput)")
     ap.add_argument("--refine", type=int, default=8, help="-da_refine (8 = 513^3, 7 = 257^3)")
     ap.add_argument("--levels", type=int, default=0, help="-pc_mg_levels (default refine-1: coarse grid 9^3)")
     ap.add_argument("--cpu-refine", type=int, default=0, help="grid of the CPU arm / cpu_baseline (default: --refine, "
@@ -385,7 +428,7 @@ def main():
     args = ap.parse_args()
     if args.config == "c2":
         args.refine = 7
-    if args.config in ("c1", "c4", "c5"):
+    if args.config in ("c1", "c4", "c5", "f3"):
         return run_secondary(args)
     if args.impl == "reference":
         return run_reference(args)

@@ -401,6 +401,40 @@ int p4b_pattern_solve(p4b_ctx *ctx, const p4b_pattern_opts *opts, p4b_line_fn li
  * report: the caller prints those, pattern.c:94-96,127-135).  Y0 = NULL is p4b_pattern_solve. */
 int p4b_pattern_solve_from(p4b_ctx *ctx, const p4b_pattern_opts *opts, const double *Y0, p4b_line_fn line, void *line_ctx,
                            double *Y_out, size_t Y_capacity, p4b_pattern_result *result);
+/* ---- c/ch7/solns/bratu2D.c: - lap u - lambda e^u = 0 by FAS multigrid + nonlinear Gauss-Seidel ----
+ *   p4b_bratu_function   FormFunctionLocal, bratu2D.c:196-225 (F = residual - b when b != NULL)
+ *   p4b_bratu_ngs        NonlinearGS, :229-299: `sweeps` RED-BLACK sweeps of pointwise Newton (the reference's sweep is
+ *                        lexicographic, i.e. sequential; same fixed point)
+ *   p4b_bratu_exact      g_liouville at every node (exact = 1; :40-45) or zeros
+ *   p4b_bratu_solve      ./bratu2D -snes_type fas [-snes_fas_type full] -fas_levels_snes_type ngs -fas_coarse_snes_type ngs:
+ *                        VecSet(u,0), the FAS cycle ([PETSc] SNESFAS restated with the golden's components; which parts are
+ *                        pinned by c/ch7/solns/output/bratu2D.test1 is stated in oracle/bratu_oracle.py), error norm */
+typedef struct {
+    double lambda;                 /* -lb_lambda */
+    int exact;                     /* -lb_exact */
+    int grid_x, grid_y, refine;    /* -da_grid_x/_y (3), -da_refine */
+    int levels;                    /* -snes_fas_levels (0 = refine + 1: down to the -da_grid base) */
+    double snes_rtol;
+    int snes_max_it;
+    int smooth_sweeps, smooth_its; /* -fas_levels_snes_ngs_sweeps, -fas_levels_snes_max_it */
+    int coarse_sweeps, coarse_its; /* -fas_coarse_snes_ngs_sweeps, -fas_coarse_snes_max_it */
+    int full_cycle;                /* -snes_fas_type full (1) | multiplicative (0) */
+    int monitor, converged_reason; /* -snes_monitor_short, -snes_converged_reason */
+} p4b_bratu_opts;
+typedef struct {
+    int mx, my, its, reason, nnorm;
+    double fnorm[64];
+    double errinf;                 /* |u - uexact|_inf with -lb_exact, else -1 */
+    long long residual_calls, ngs_calls;
+    double solve_ms;               /* CUDA events around the solve */
+} p4b_bratu_result;
+int p4b_bratu_default_opts(p4b_bratu_opts *o);
+int p4b_bratu_function(p4b_ctx *ctx, int mx, int my, double lambda, int exact, const double *u, const double *b, double *F);
+int p4b_bratu_ngs(p4b_ctx *ctx, int mx, int my, double lambda, int exact, int sweeps, const double *b, double *u);
+int p4b_bratu_exact(p4b_ctx *ctx, int mx, int my, int exact, double *g);
+int p4b_bratu_solve(p4b_ctx *ctx, const p4b_bratu_opts *opts, p4b_line_fn line, void *line_ctx, double *u_out,
+                    size_t u_capacity, p4b_bratu_result *result);
+
 /* Multi-GPU (BASELINE config 5: 2048^2 on 8 GPUs): with a context that carries a communicator (p4b_comm_init)
  * p4b_pattern_solve / p4b_pattern_solve_from run on y-slabs of the periodic DMDA (c/ch5/pattern.c:79-84) -- ring
  * exchange of one ghost row per side ([PETSc] DMGlobalToLocal), all-reduced dot products, small levels replicated.

@@ -1,0 +1,197 @@
+"""CPU restatement of c/ch7/solns/bratu2D.c solved by FAS + nonlinear Gauss-Seidel.
+TEST INFRASTRUCTURE ONLY: imported by tests/ and by bench.py's cpu_baseline leg, never by the product.
+
+What is restated from the reference itself (pinned below on c/ch7/solns/output/bratu2D.test1):
+  residual         FormFunctionLocal   c/ch7/solns/bratu2D.c:196-225   F = u - g on the boundary,
+                                        hy/hx (2u - W - E) + hx/hy (2u - S - N) - hx hy lambda e^u inside
+  g_liouville      :40-45              Liouville's exact solution for lambda = 1
+  NGS              NonlinearGS :229-299 pointwise Newton on phi(u) = F_ij(u) - b_ij, lexicographic order (the reference),
+                                        boundary nodes set to g; tolerances of [PETSc] SNESNGS (atol 1e-50, rtol 1e-5?...)
+What is [PETSc] and NOT pinned: the cycle.  The golden's command line is `-snes_type fas -snes_fas_type full
+-fas_levels_snes_type ngs -fas_levels_snes_ngs_sweeps 2 -fas_levels_snes_max_it 1 -fas_coarse_snes_type ngs
+-fas_coarse_snes_ngs_sweeps 2 -fas_coarse_snes_max_it 4`; SNESFAS's full cycle (stages, norm schedules, where it
+re-evaluates F) lives in PETSc (un-vendored, no pinned version) and its call counts ("residual calls = 69, NGS calls = 58")
+could only be reproduced by reproducing that file.  Here the cycle is the textbook one with the golden's components:
+  coarse solve   = 4 x NGS(2 sweeps)                         (-fas_coarse_snes_max_it 4, ngs_sweeps 2)
+  smoother       = 1 x NGS(2 sweeps) before and after        (-fas_levels_snes_max_it 1, ngs_sweeps 2)
+  FAS correction   x_c0 = inject(x), b_c = F_c(x_c0) - R (F(x) - b), solve, x += P (x_c - x_c0)   (R = P^T, DMDA Q1)
+  full cycle     = first cycle: solve on the coarsest grid, then on every finer grid interpolate and do one V cycle (F
+                   cycle); later cycles: V cycles; stop when ||F|| <= rtol ||F(u0)||
+PARITY of the cycle: UNPINNED (stated in DESIGN.md).  Pinned by the golden: ||F(u0)|| = 9.04754 on the 9 x 9 grid (a pure
+callback number) and the converged error |u - uexact|_inf = 3.169e-04 (the discretisation error, cycle independent).
+`order="redblack"` is the GPU's ordering (SOR is sequential; north star: Jacobi-type smoothers); same fixed point."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+def g_liouville(x, y):
+    r2 = (x + 1.0) ** 2 + (y + 1.0) ** 2
+    qq = r2 * r2 + 1.0
+    return np.log(32.0 * r2 / (qq * qq))
+
+
+def boundary_values(m, exact):
+    x = np.linspace(0.0, 1.0, m)
+    X, Y = np.meshgrid(x, x)                      # Y[j, i] = y_j
+    return g_liouville(X, Y) if exact else np.zeros((m, m))
+
+
+def residual(u, lam, g, b=None):
+    """bratu2D.c:196-225 (square grid, hx = hy: hy/hx = hx/hy = 1)."""
+    m = u.shape[0]
+    h = 1.0 / (m - 1)
+    F = u - g
+    c = u[1:-1, 1:-1]
+    F[1:-1, 1:-1] = (2.0 * c - u[1:-1, :-2] - u[1:-1, 2:]) + (2.0 * c - u[:-2, 1:-1] - u[2:, 1:-1]) - h * h * lam * np.exp(c)
+    if b is not None:
+        F = F - b
+    return F
+
+
+NGS_ATOL, NGS_RTOL, NGS_STOL, NGS_MAXIT = 1.0e-50, 1.0e-8, 1.0e-8, 50      # [PETSc] SNESNGS defaults as this repo restates them
+
+
+def _point_newton(uu, nb, bij, darea_lam):
+    """bratu2D.c:262-285 on arrays: Newton on phi(u) = 4 u - nb - darea lambda e^u - b (hx = hy)."""
+    uu = uu.copy()
+    active = np.ones(uu.shape, bool)
+    phi0 = None
+    for k in range(NGS_MAXIT):
+        e = np.exp(uu)
+        phi = 4.0 * uu - nb - darea_lam * e - bij
+        if k == 0:
+            phi0 = np.abs(phi)
+        s = -phi / (4.0 - darea_lam * e)
+        uu = np.where(active, uu + s, uu)
+        done = (NGS_ATOL > np.abs(phi)) | (NGS_RTOL * phi0 > np.abs(phi)) | (NGS_STOL * np.abs(uu) > np.abs(s))
+        active &= ~done
+        if not active.any():
+            break
+    return uu
+
+
+def ngs(u, b, lam, g, sweeps, order="lexicographic"):
+    """NonlinearGS (bratu2D.c:229-299): `sweeps` sweeps; boundary nodes are set to g."""
+    m = u.shape[0]
+    h = 1.0 / (m - 1)
+    dl = h * h * lam
+    u = u.copy()
+    bb = b if b is not None else np.zeros_like(u)
+    for _ in range(sweeps):
+        u[0, :], u[-1, :], u[:, 0], u[:, -1] = g[0, :], g[-1, :], g[:, 0], g[:, -1]
+        if order == "lexicographic":
+            for j in range(1, m - 1):
+                for i in range(1, m - 1):
+                    nb = u[j, i - 1] + u[j, i + 1] + u[j - 1, i] + u[j + 1, i]
+                    u[j, i] = _point_newton(np.array([u[j, i]]), np.array([nb]), np.array([bb[j, i]]), dl)[0]
+        else:
+            jj, ii = np.meshgrid(np.arange(m), np.arange(m), indexing="ij")
+            inner = (jj > 0) & (jj < m - 1) & (ii > 0) & (ii < m - 1)
+            for colour in (0, 1):
+                sel = inner & (((ii + jj) & 1) == colour)
+                nb = np.zeros_like(u)
+                nb[1:-1, 1:-1] = u[1:-1, :-2] + u[1:-1, 2:] + u[:-2, 1:-1] + u[2:, 1:-1]
+                u[sel] = _point_newton(u[sel], nb[sel], bb[sel], dl)
+    return u
+
+
+def restrict(r):
+    """R = P^T of the DMDA Q1 interpolation (vertex centred, ratio 2; boundary nodes included)."""
+    mf = r.shape[0]
+    mc = (mf - 1) // 2 + 1
+    rx = r[:, 0::2].copy()
+    rx[:, :-1] += 0.5 * r[:, 1::2]
+    rx[:, 1:] += 0.5 * r[:, 1::2]
+    out = rx[0::2, :].copy()
+    out[:-1, :] += 0.5 * rx[1::2, :]
+    out[1:, :] += 0.5 * rx[1::2, :]
+    assert out.shape == (mc, mc)
+    return out
+
+
+def prolong(xc):
+    mc = xc.shape[0]
+    mf = 2 * (mc - 1) + 1
+    xr = np.zeros((mc, mf))
+    xr[:, 0::2] = xc
+    xr[:, 1::2] = 0.5 * (xc[:, :-1] + xc[:, 1:])
+    out = np.zeros((mf, mf))
+    out[0::2, :] = xr
+    out[1::2, :] = 0.5 * (xr[:-1, :] + xr[1:, :])
+    return out
+
+
+@dataclass
+class BratuResult:
+    m: int
+    its: int
+    fnorm: list
+    u: np.ndarray = field(repr=False, default=None)
+    errinf: float | None = None
+    residual_calls: int = 0
+    ngs_calls: int = 0
+
+
+def fas_solve(refine=2, lam=1.0, exact=True, rtol=1.0e-8, max_it=50, levels=None, order="lexicographic",
+              smooth_sweeps=2, coarse_its=4, coarse_sweeps=2, base=3, full_every=True, full_cycle=True) -> BratuResult:
+    ms = [base]
+    for _ in range(refine):
+        ms.append(2 * (ms[-1] - 1) + 1)
+    if levels:
+        ms = ms[-levels:]
+    G = [boundary_values(m, exact) for m in ms]
+    counts = {"F": 0, "ngs": 0}
+
+    def Fl(l, u, b=None):
+        counts["F"] += 1
+        return residual(u, lam, G[l], b)
+
+    def smooth(l, u, b, times=1, sweeps=smooth_sweeps):
+        for _ in range(times):
+            counts["ngs"] += 1
+            u = ngs(u, b, lam, G[l], sweeps, order)
+        return u
+
+    def vcycle(l, u, b):
+        if l == 0:
+            return smooth(0, u, b, coarse_its, coarse_sweeps)
+        u = smooth(l, u, b)
+        r = Fl(l, u, b)
+        xc0 = u[0::2, 0::2].copy()                         # injection ([PETSc] DMCreateInjection)
+        bc = Fl(l - 1, xc0) - restrict(r)
+        xc = vcycle(l - 1, xc0.copy(), bc)
+        u = u + prolong(xc - xc0)
+        return smooth(l, u, b)
+
+    top = len(ms) - 1
+    u = np.zeros((ms[top], ms[top]))
+    f0 = float(np.linalg.norm(Fl(top, u)))
+    norms = [f0]
+    its = 0
+    while its < max_it:
+        if top > 0 and full_cycle and (its == 0 or full_every):
+            # full cycle: the fine problem's right-hand sides down the hierarchy, coarsest solve, then one V cycle per level
+            us, bs = [None] * (top + 1), [None] * (top + 1)
+            us[top], bs[top] = u, None
+            for l in range(top, 0, -1):
+                r = Fl(l, us[l], bs[l])
+                us[l - 1] = us[l][0::2, 0::2].copy()
+                bs[l - 1] = Fl(l - 1, us[l - 1]) - restrict(r)
+            x0 = [x.copy() for x in us]
+            xs = smooth(0, us[0].copy(), bs[0], coarse_its, coarse_sweeps)
+            for l in range(1, top + 1):
+                us[l] = us[l] + prolong(xs - x0[l - 1])
+                xs = vcycle(l, us[l], bs[l])
+            u = xs
+        else:
+            u = vcycle(top, u, None)
+        its += 1
+        fn = float(np.linalg.norm(Fl(top, u)))
+        norms.append(fn)
+        if fn <= rtol * f0 or fn < 1.0e-50:
+            break
+    err = float(np.max(np.abs(u - G[top]))) if exact else None
+    return BratuResult(ms[top], its, norms, u, err, counts["F"], counts["ngs"])

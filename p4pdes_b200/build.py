@@ -14,7 +14,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libp4b200.so")
-SOURCES = ["mg.cu", "stencil.cu", "stencil_fast.cu", "transfer.cu", "vecops.cu", "fishfn.cu", "comm.cu", "mp_kernels.cu", "assembled.cu", "nk_device.cu"]
+SOURCES = ["mg.cu", "stencil.cu", "stencil_fast.cu", "transfer.cu", "vecops.cu", "fishfn.cu", "comm.cu", "mp_kernels.cu", "assembled.cu", "nk_device.cu", "bratu.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "kernels.h"), os.path.join(CSRC, "comm.h"),
            os.path.join(CSRC, "nk_solver.hpp"), os.path.join(CSRC, "ts_solver.hpp"),
            os.path.join(ROOT, "include", "p4b200.h")]

@@ -104,6 +104,20 @@ RHSFUNCTION2D_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_double, C.POINT
 MONITOR2D_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double))
 
 
+class BratuOpts(C.Structure):
+    """p4b_bratu_opts (include/p4b200.h)."""
+    _fields_ = [("lam", C.c_double), ("exact", C.c_int), ("grid_x", C.c_int), ("grid_y", C.c_int), ("refine", C.c_int),
+                ("levels", C.c_int), ("snes_rtol", C.c_double), ("snes_max_it", C.c_int), ("smooth_sweeps", C.c_int),
+                ("smooth_its", C.c_int), ("coarse_sweeps", C.c_int), ("coarse_its", C.c_int), ("full_cycle", C.c_int),
+                ("monitor", C.c_int), ("converged_reason", C.c_int)]
+
+
+class BratuResult(C.Structure):
+    _fields_ = [("mx", C.c_int), ("my", C.c_int), ("its", C.c_int), ("reason", C.c_int), ("nnorm", C.c_int),
+                ("fnorm", C.c_double * 64), ("errinf", C.c_double), ("residual_calls", C.c_longlong),
+                ("ngs_calls", C.c_longlong), ("solve_ms", C.c_double)]
+
+
 class KernelStat(C.Structure):
     _fields_ = [("launches", C.c_longlong), ("ms", C.c_double), ("bytes", C.c_double)]
 
@@ -169,6 +183,11 @@ _SIGS = {
     "p4b_minimal_function": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, _D, _D]),
     "p4b_pattern_initial_state": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D]),
     "p4b_pattern_initial_state_noisy": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, C.c_double, _D]),
+    "p4b_bratu_default_opts": (C.c_int, [C.POINTER(BratuOpts)]),
+    "p4b_bratu_function": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int, _D, _D, _D]),
+    "p4b_bratu_ngs": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _D, _D]),
+    "p4b_bratu_exact": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _D]),
+    "p4b_bratu_solve": (C.c_int, [_P, C.POINTER(BratuOpts), LINE_FN, C.c_void_p, _D, C.c_size_t, C.POINTER(BratuResult)]),
     "p4b_pattern_slab_plan": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int)] * 4),
     "p4b_rander48_seed": (C.c_ulonglong, [C.c_ulong]),
     "p4b_rander48_fill": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_size_t, C.c_void_p]),
