@@ -50,31 +50,37 @@ __global__ void __launch_bounds__(256) bratu_function_kernel(int mx, int my, dou
 
 struct NgsTol { double atol, rtol, stol; int maxits; };
 
-// one half sweep: the interior nodes with (i + j) % 2 == colour; colour 0 also sets the boundary nodes to g
+// one half sweep: the interior nodes with (i + j) % 2 == colour.  A thread owns ONE node of that colour (row j, column
+// 2 k + ((colour + j) & 1)): every lane of a warp runs the Newton iteration -- with one thread per node of either colour
+// half the lanes idled through it, and this kernel is bound by the fp64 exp and divide, not by HBM (measured at
+// 20481^2: 0.19 of the HBM roofline).  Boundary nodes are set to g by the colour-0 launch.
 __global__ void __launch_bounds__(256) bratu_ngs_kernel(int mx, int my, double lambda, int exact, int colour, NgsTol tol,
                                                          const double *__restrict__ b, double *u) {
-    const long long n = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (n >= (long long)mx * my) return;
-    const int j = (int)(n / mx), i = (int)(n - (long long)j * mx);
+    const int half = (mx + 1) / 2;                             // threads per row
+    const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (t >= (long long)half * my) return;
+    const int j = (int)(t / half), k = (int)(t - (long long)j * half);
+    const int i = 2 * k + ((colour + j) & 1);
     const double hx = 1.0 / (mx - 1), hy = 1.0 / (my - 1);
-    if (i == 0 || j == 0 || i == mx - 1 || j == my - 1) {
-        if (colour == 0) u[n] = bratu_g(exact, i * hx, j * hy);
-        return;
+    if (colour == 0) {
+        // the boundary nodes of this thread's pair {2k, 2k+1} (whatever their colour): u = g  (bratu2D.c:252-254)
+        for (int ii = 2 * k; ii <= 2 * k + 1 && ii < mx; ii++)
+            if (ii == 0 || j == 0 || ii == mx - 1 || j == my - 1) u[(long long)j * mx + ii] = bratu_g(exact, ii * hx, j * hy);
     }
-    if (((i + j) & 1) != colour) return;
+    if (i <= 0 || j <= 0 || i >= mx - 1 || j >= my - 1) return;
+    const long long n = (long long)j * mx + i;
     const double hyhx = hy / hx, hxhy = hx / hy, dl = hx * hy * lambda, bij = b ? b[n] : 0.0;
-    // neighbours on the boundary: the reference has set them to g at the start of the sweep (lexicographic order reaches
-    // the boundary rows first); in a red-black sweep the colour-0 pass does it, and reads them through g here so that
-    // the result does not depend on which thread gets there first
+    // neighbours on the boundary are read through g, so the result does not depend on whether the thread that sets
+    // them has run yet
     auto nb = [&](int ii, int jj, long long q) {
         return (ii == 0 || jj == 0 || ii == mx - 1 || jj == my - 1) ? bratu_g(exact, ii * hx, jj * hy) : u[q];
     };
     const double sx = nb(i - 1, j, n - 1) + nb(i + 1, j, n + 1), sy = nb(i, j - 1, n - mx) + nb(i, j + 1, n + mx);
     double uu = u[n], phi0 = 0.0;
-    for (int k = 0; k < tol.maxits; k++) {
+    for (int kk = 0; kk < tol.maxits; kk++) {
         const double e = exp(uu);
         const double phi = hyhx * (2.0 * uu - sx) + hxhy * (2.0 * uu - sy) - dl * e - bij;
-        if (k == 0) phi0 = phi;
+        if (kk == 0) phi0 = phi;
         const double s = -phi / (2.0 * (hyhx + hxhy) - dl * e);
         uu += s;
         if (tol.atol > fabs(phi) || tol.rtol * fabs(phi0) > fabs(phi) || tol.stol * fabs(uu) > fabs(s)) break;
@@ -99,7 +105,7 @@ static int launch_bratu_function(cudaStream_t st, int mx, int my, double lambda,
     return 0;
 }
 static int launch_bratu_ngs(cudaStream_t st, int mx, int my, double lambda, int exact, int sweeps, const double *b, double *u) {
-    const long long N = (long long)mx * my;
+    const long long N = (long long)((mx + 1) / 2) * my;          // one thread per node of the colour
     for (int s = 0; s < sweeps; s++)
         for (int colour = 0; colour < 2; colour++) {
             bratu_ngs_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(mx, my, lambda, exact, colour, NGS_DEFAULT, b, u);
@@ -174,9 +180,12 @@ int p4b_bratu_solve(p4b_ctx *c, const p4b_bratu_opts *o, p4b_line_fn line, void 
         BratuLevel &V = L[l];
         V.mx = shapes[l].first; V.my = shapes[l].second;
         V.n = (size_t)V.mx * V.my;
-        cu(cudaMalloc(&V.u, sizeof(double) * V.n));
-        cu(cudaMalloc(&V.r, sizeof(double) * V.n));
-        if (l < top) { cu(cudaMalloc(&V.b, sizeof(double) * V.n)); cu(cudaMalloc(&V.x0, sizeof(double) * V.n)); }
+        // stream-ordered allocations: the context keeps the device pool's memory between solves (p4b_ctx_create), so a
+        // second solve of the same size pays no allocation (a 20481^2 hierarchy is 11 GB: cudaMalloc/cudaFree of it took
+        // longer than the solve)
+        cu(cudaMallocAsync((void **)&V.u, sizeof(double) * V.n, st));
+        cu(cudaMallocAsync((void **)&V.r, sizeof(double) * V.n, st));
+        if (l < top) { cu(cudaMallocAsync((void **)&V.b, sizeof(double) * V.n, st)); cu(cudaMallocAsync((void **)&V.x0, sizeof(double) * V.n, st)); }
         memset(&V.d, 0, sizeof V.d);
         V.d.nx = V.mx; V.d.ny = 1; V.d.nz = V.my; V.d.ax = 1; V.d.ay = 0; V.d.az = 1; V.d.zs = 0; V.d.zm = V.my;
     }
@@ -271,8 +280,10 @@ int p4b_bratu_solve(p4b_ctx *c, const p4b_bratu_opts *o, p4b_line_fn line, void 
         if (u_capacity < L[top].n) rc = fail(63, "u_out holds %zu doubles, the grid needs %d x %d", u_capacity, L[top].mx, L[top].my);
         else cu(cudaMemcpyAsync(u_out, L[top].u, sizeof(double) * L[top].n, cudaMemcpyDeviceToDevice, st));
     }
+    for (BratuLevel &V : L)
+        for (double *p : {V.u, V.b, V.r, V.x0})
+            if (p) cudaFreeAsync(p, st);
     cudaStreamSynchronize(st);
-    for (BratuLevel &V : L) { cudaFree(V.u); cudaFree(V.b); cudaFree(V.r); cudaFree(V.x0); }
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     return rc;

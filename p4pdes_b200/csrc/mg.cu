@@ -993,6 +993,15 @@ int p4b_ctx_create(int device, void *stream, p4b_ctx **out) {
     if (e != cudaSuccess || ndev <= 0)
         return fail(70, "no CUDA device available (%s): p4b200 has no CPU fallback", cudaGetErrorString(e));
     P4B_CUDA(cudaSetDevice(device));
+    {   // stream-ordered allocations (cudaMallocAsync in the Newton / time-stepping / FAS hosts): keep freed memory in the
+        // device's pool instead of returning it to the driver at every synchronisation point (the default threshold is 0)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     p4b_ctx *c = new p4b_ctx();
     c->device = device;
     c->stream = (cudaStream_t)stream;   // exactly the caller's stream; NULL is the (legacy) default stream
