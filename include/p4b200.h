@@ -138,6 +138,8 @@ int p4b_tune(const char *key, long value);
 /* stream: the cudaStream_t every kernel, copy and NCCL call of this context is issued on
  * (NULL = the default stream), so the library's work is ordered with the caller's own. */
 int p4b_ctx_create(int device, void *stream, p4b_ctx **ctx);
+/* the same on a stream the context creates and owns (for C hosts without CUDA headers; one per GPU and host thread) */
+int p4b_ctx_create_own_stream(int device, p4b_ctx **ctx);
 int p4b_ctx_destroy(p4b_ctx *ctx);
 int p4b_ctx_sync(p4b_ctx *ctx);
 /* multi-GPU: rank 0 makes a 128-byte id, the host side ships it to the other ranks (torch.distributed

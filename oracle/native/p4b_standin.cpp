@@ -58,6 +58,11 @@ int p4b_rander48_fill(unsigned long long *state, size_t n, double *out) {
     return 0;
 }
 int p4b_ctx_create(int, void *, p4b_ctx **ctx) { *ctx = new p4b_ctx{0}; return 0; }
+// -p4b_gpus N needs GPUs: the stand-in has none (the shim's multi-GPU route is covered by tests/test_gpu_multi.py)
+int p4b_ctx_create_own_stream(int, p4b_ctx **) { return fail(70, "stand-in: -p4b_gpus needs CUDA devices"); }
+int p4b_comm_unique_id(void *) { return fail(70, "stand-in: -p4b_gpus needs CUDA devices"); }
+int p4b_comm_init(p4b_ctx *, const void *, int, int) { return fail(70, "stand-in: -p4b_gpus needs CUDA devices"); }
+int p4b_mg_local_range(p4b_mg *, int *, int *, size_t *) { return fail(70, "stand-in: -p4b_gpus needs CUDA devices"); }
 int p4b_ctx_destroy(p4b_ctx *ctx) { delete ctx; return 0; }
 int p4b_malloc(p4b_ctx *, size_t bytes, void **dptr) { *dptr = malloc(bytes ? bytes : 1); return *dptr ? 0 : 55; }
 int p4b_free(p4b_ctx *, void *dptr) { free(dptr); return 0; }

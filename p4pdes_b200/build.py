@@ -85,7 +85,7 @@ def build_shim(force=False):
             and all(os.path.getmtime(d) < os.path.getmtime(SHIM_LIB) for d in deps)):
         return SHIM_LIB
     cmd = ["gcc", "-std=c99", "-O2", "-Wall", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), SHIM_SRC,
-           "-o", SHIM_LIB, "-L", LIBDIR, "-lp4b200", "-Wl,-rpath,$ORIGIN", "-lm"]
+           "-o", SHIM_LIB, "-L", LIBDIR, "-lp4b200", "-Wl,-rpath,$ORIGIN", "-lm", "-lpthread"]
     subprocess.check_call(cmd)
     return SHIM_LIB
 

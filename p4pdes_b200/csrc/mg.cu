@@ -13,7 +13,9 @@
 #include <nccl.h>
 #include <stdarg.h>
 #include <string.h>
+#include <unistd.h>
 
+#include <mutex>
 #include <vector>
 
 #include <array>
@@ -61,7 +63,9 @@ struct Nccl {
 };
 static Nccl g_nccl;
 
+static std::mutex g_nccl_mutex;
 static int nccl_load() {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
     if (g_nccl.h) return 0;
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     void *h = nullptr;
@@ -120,6 +124,7 @@ struct p4b_ctx {
     // peer-memory path (comm.cu): mailboxes of all ranks mapped through CUDA IPC
     bool peer = false;
     Mailbox *mbox = nullptr;
+    bool mbox_ipc[MAX_RANKS] = {};      // which peer mailboxes were opened through CUDA IPC (other processes)
     LocalSync *sync = nullptr;
     PeerTable peers;
     // p4b_tune("force_mg"): single-GPU stand-ins for the neighbours (kernel A/B measurements only)
@@ -130,17 +135,49 @@ struct p4b_ctx {
 
 static long long g_comm_peer = 1;      // p4b_tune("comm_peer", 0) keeps everything on NCCL
 
-// all-gather one CUDA IPC handle per rank (over NCCL, as raw bytes)
-static int ipc_allgather(p4b_ctx *c, const cudaIpcMemHandle_t &mine, std::vector<cudaIpcMemHandle_t> *all) {
-    const size_t hb = sizeof(cudaIpcMemHandle_t);
+// Map one device allocation of every rank into this rank.  Ranks in other PROCESSES (torchrun, one process per GPU) are
+// mapped through CUDA IPC; ranks in THIS process (the PETSc-shaped shim driving N GPUs with one host thread each,
+// -p4b_gpus N) are reached through the raw pointer after cudaDeviceEnablePeerAccess -- an IPC handle cannot be opened
+// by the process that exported it.  The records travel over NCCL as raw bytes.  own[r] says which mappings have to be
+// closed with cudaIpcCloseMemHandle.
+struct PeerRecord {
+    cudaIpcMemHandle_t handle;
+    long long pid;
+    void *ptr;
+    int device;
+};
+static int map_peers(p4b_ctx *c, void *mine, void **mapped, bool *ipc_opened) {
+    PeerRecord rec;
+    memset(&rec, 0, sizeof rec);
+    P4B_CUDA(cudaIpcGetMemHandle(&rec.handle, mine));
+    rec.pid = (long long)getpid();
+    rec.ptr = mine;
+    rec.device = c->device;
+    const size_t hb = sizeof(PeerRecord);
     char *d = nullptr;
     P4B_CUDA(cudaMalloc(&d, hb * c->nranks));
-    P4B_CUDA(cudaMemcpy(d + hb * c->rank, &mine, hb, cudaMemcpyHostToDevice));
+    P4B_CUDA(cudaMemcpy(d + hb * c->rank, &rec, hb, cudaMemcpyHostToDevice));
     P4B_NCCL(g_nccl.AllGather(d + hb * c->rank, d, hb, ncclChar, c->comm, c->stream));
     P4B_CUDA(cudaStreamSynchronize(c->stream));
-    all->resize(c->nranks);
-    P4B_CUDA(cudaMemcpy(all->data(), d, hb * c->nranks, cudaMemcpyDeviceToHost));
+    std::vector<PeerRecord> all(c->nranks);
+    P4B_CUDA(cudaMemcpy(all.data(), d, hb * c->nranks, cudaMemcpyDeviceToHost));
     P4B_CUDA(cudaFree(d));
+    for (int r = 0; r < c->nranks; r++) {
+        ipc_opened[r] = false;
+        if (r == c->rank) { mapped[r] = mine; continue; }
+        if (all[r].pid == rec.pid) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(72, "cudaDeviceEnablePeerAccess(%d) failed: %s", all[r].device, cudaGetErrorString(e));
+            cudaGetLastError();
+            mapped[r] = all[r].ptr;
+        } else {
+            void *p = nullptr;
+            P4B_CUDA(cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess));
+            mapped[r] = p;
+            ipc_opened[r] = true;
+        }
+    }
     return 0;
 }
 
@@ -157,18 +194,11 @@ static int peer_setup(p4b_ctx *c) {
     P4B_CUDA(cudaMemset(c->mbox, 0, sizeof(Mailbox)));
     P4B_CUDA(cudaMalloc(&c->sync, sizeof(LocalSync)));
     P4B_CUDA(cudaMemset(c->sync, 0, sizeof(LocalSync)));
-    cudaIpcMemHandle_t mine;
-    P4B_CUDA(cudaIpcGetMemHandle(&mine, c->mbox));
-    std::vector<cudaIpcMemHandle_t> all;
-    P4B_CHECK(ipc_allgather(c, mine, &all));
     c->peers.rank = c->rank;
     c->peers.nranks = c->nranks;
-    for (int r = 0; r < c->nranks; r++) {
-        if (r == c->rank) { c->peers.mbox[r] = c->mbox; continue; }
-        void *p = nullptr;
-        P4B_CUDA(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
-        c->peers.mbox[r] = (Mailbox *)p;
-    }
+    void *mapped[MAX_RANKS];
+    P4B_CHECK(map_peers(c, c->mbox, mapped, c->mbox_ipc));
+    for (int r = 0; r < c->nranks; r++) c->peers.mbox[r] = (Mailbox *)mapped[r];
     P4B_CHECK(nccl_barrier(c));
     c->peer = true;
     return 0;
@@ -330,6 +360,7 @@ struct p4b_mg {
     // peer-memory path: arenas of all ranks mapped through CUDA IPC
     bool peer = false;
     GatherTable peer_arena;
+    bool arena_ipc[MAX_RANKS] = {};
     const double *last_halo = nullptr;     // the vector exchanged most recently (hazard tracking, comm.cu "Hazards")
     const double *pushed = nullptr;        // the vector whose ghost planes are current (exchanged, not written since)
     bool dot2_fused = false;     // set by smooth() when the last smoother kernel also produced (z,z), (z,r)
@@ -1021,6 +1052,24 @@ int p4b_ctx_create(int device, void *stream, p4b_ctx **out) {
     return 0;
 }
 
+// the same with a stream of its own (non-blocking, so the coarse levels can be captured into a CUDA graph): for C hosts
+// that have no CUDA headers -- the PETSc-shaped shim creates one context per GPU this way (-p4b_gpus N)
+int p4b_ctx_create_own_stream(int device, p4b_ctx **out) {
+    if (!out) return fail(62, "null ctx pointer");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(70, "no CUDA device available (%s): p4b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(62, "device %d of %d", device, ndev);
+    P4B_CUDA(cudaSetDevice(device));
+    cudaStream_t st = nullptr;
+    P4B_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const int rc = p4b_ctx_create(device, (void *)st, out);
+    if (rc) { cudaStreamDestroy(st); return rc; }
+    (*out)->own_stream = true;
+    return 0;
+}
+
 int p4b_ctx_destroy(p4b_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
@@ -1028,7 +1077,7 @@ int p4b_ctx_destroy(p4b_ctx *c) {
     if (c->peer) {
         nccl_barrier(c);
         for (int r = 0; r < c->nranks; r++)
-            if (r != c->rank && c->peers.mbox[r]) cudaIpcCloseMemHandle(c->peers.mbox[r]);
+            if (r != c->rank && c->peers.mbox[r] && c->mbox_ipc[r]) cudaIpcCloseMemHandle(c->peers.mbox[r]);
         nccl_barrier(c);
         cudaFree(c->mbox);
         cudaFree(c->sync);
@@ -1405,16 +1454,9 @@ static int mg_create_impl(p4b_ctx *c, const p4b_grid *g, const p4b_mg_opts *oin,
     if (c->peer) {
         // map every rank's arena (neighbours for ghost planes, everyone for the replicated-level gather)
         P4B_CUDA(cudaStreamSynchronize(c->stream));
-        cudaIpcMemHandle_t mine;
-        P4B_CUDA(cudaIpcGetMemHandle(&mine, m->arena));
-        std::vector<cudaIpcMemHandle_t> all;
-        P4B_CHECK(ipc_allgather(c, mine, &all));
-        for (int r = 0; r < P; r++) {
-            if (r == R) { m->peer_arena.base[r] = m->arena; continue; }
-            void *pp = nullptr;
-            P4B_CUDA(cudaIpcOpenMemHandle(&pp, all[r], cudaIpcMemLazyEnablePeerAccess));
-            m->peer_arena.base[r] = (double *)pp;
-        }
+        void *mapped[MAX_RANKS];
+        P4B_CHECK(map_peers(c, m->arena, mapped, m->arena_ipc));
+        for (int r = 0; r < P; r++) m->peer_arena.base[r] = (double *)mapped[r];
         P4B_CHECK(nccl_barrier(c));
         m->peer = true;
     }
@@ -1456,7 +1498,7 @@ int p4b_mg_destroy(p4b_mg *m) {
     if (m->peer) {      // collective: nobody may still be storing into an arena that is about to be freed
         nccl_barrier(m->ctx);
         for (int r = 0; r < m->ctx->nranks; r++)
-            if (r != m->ctx->rank && m->peer_arena.base[r]) cudaIpcCloseMemHandle(m->peer_arena.base[r]);
+            if (r != m->ctx->rank && m->peer_arena.base[r] && m->arena_ipc[r]) cudaIpcCloseMemHandle(m->peer_arena.base[r]);
         nccl_barrier(m->ctx);
     }
     cudaFree(m->arena);

@@ -477,7 +477,7 @@ static double march_model(int plane, int zm, int P, int NT, int sm_count) {
     return march_plan(plane, zm, P * NT, (long long)sm_count * occ, &nc) * (double)(P * NT) * occ;
 }
 static int sm_count_cached() {
-    static int n = 0;
+    static thread_local int n = 0;
     if (!n) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -489,13 +489,21 @@ static int sm_count_cached() {
 
 template <int MODE, int P, int NT, bool MG>
 static int launch_march_mg(cudaStream_t st, const LevelDesc &L, const StencilOp &op, const Reducer &red, int NS) {
-    static int sm_count = 0, max_smem = 0;
-    if (!sm_count) {
+    // per-device facts and attributes of this instantiation, cached per host thread and device (function attributes are
+    // per device: a process that drives several GPUs, one host thread each, must set them on every one)
+    struct Cache { int dev = -1, sm_count = 0, max_smem = 0, occ = 0; size_t attr_smem = 0, occ_smem = 0; };
+    static thread_local Cache K;
+    {
         int dev = 0;
         P4B_CUDA(cudaGetDevice(&dev));
-        P4B_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        P4B_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        if (K.dev != dev) {
+            K = Cache();
+            K.dev = dev;
+            P4B_CUDA(cudaDeviceGetAttribute(&K.sm_count, cudaDevAttrMultiProcessorCount, dev));
+            P4B_CUDA(cudaDeviceGetAttribute(&K.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        }
     }
+    const int sm_count = K.sm_count, max_smem = K.max_smem;
     constexpr int Q = NT * P;
     const int plane = L.nx * L.ny;
     MarchCfg cfg;
@@ -506,21 +514,19 @@ static int launch_march_mg(cudaStream_t st, const LevelDesc &L, const StencilOp 
     cfg.NS = NS;
     const size_t smem = 128 + NS * stage_bytes;
     if (smem + 1024 > (size_t)max_smem) return fail(62, "plane-marching stage does not fit shared memory");
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
+    if (smem > K.attr_smem) {
         P4B_CUDA(cudaFuncSetAttribute(stencil_march_kernel<MODE, P, NT, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-        attr_smem = smem;
+        K.attr_smem = smem;
     }
     // occupancy does not change between launches of one instantiation with one stage size: ask once
-    static int occ_cached = 0;
-    static size_t occ_smem = 0;
-    if (!occ_cached || occ_smem != smem) {
+    if (!K.occ || K.occ_smem != smem) {
         int occ = 1;
         P4B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stencil_march_kernel<MODE, P, NT, MG>, NT, smem));
-        occ_cached = occ < 1 ? 1 : occ;
-        occ_smem = smem;
+        K.occ = occ < 1 ? 1 : occ;
+        K.occ_smem = smem;
     }
+    const int occ_cached = K.occ;
     const int bands = (plane + Q - 1) / Q;
     int best_nc = 1;
     march_plan(plane, L.zm, Q, (long long)sm_count * occ_cached, &best_nc);

@@ -1377,6 +1377,79 @@ static PetscErrorCode ksponly_solve_assembled(SNES snes, Vec u, Vec F, Vec Y, do
     return 0;
 }
 
+/* ---- -p4b_gpus N: the KSP solve of the unchanged fish.c on N GPUs of this box -------------------------------------
+ * fish.c creates its DMDA on PETSC_COMM_WORLD and the reference runs it under `mpiexec -n P` (c/testit.sh:22,
+ * c/ch6/makefile:21,30).  There is no MPI here; SURVEY.md 5 proposed "one host thread drives all GPUs; callbacks see a
+ * single logical rank owning the whole grid".  So the callbacks (F(u0), the level Jacobians) run once on the host over
+ * the whole grid, and the solve -- where the time is -- runs on z-slabs: one host thread per GPU, each with its own
+ * context, stream and slab of the hierarchy, talking through the library's communicator (peer memory over NVLink fused
+ * into the kernels, csrc/comm.h; the threads map each other's memory directly instead of through CUDA IPC). */
+#include <pthread.h>
+struct mg_worker {
+    int rank, nranks, dim, nlev, pct, max_it, rc;
+    unsigned char id[128];
+    p4b_grid g;
+    p4b_mg_opts o;
+    const double *coef, *F;
+    double *Y, rtol, abstol;
+    p4b_ksp_result res;
+    char err[512];
+};
+static void *mg_worker_main(void *arg) {
+    struct mg_worker *w = (struct mg_worker *)arg;
+    p4b_ctx *ctx = NULL;
+    p4b_mg *mg = NULL;
+    double *b = NULL, *x = NULL;
+    int zs = 0, zm = 0;
+    size_t nloc = 0;
+#define WK(call) do { if (!w->rc && (call)) { w->rc = 70; snprintf(w->err, sizeof w->err, "%s", p4b_last_error()); } } while (0)
+    WK(p4b_ctx_create_own_stream(w->rank, &ctx));
+    WK(p4b_comm_init(ctx, w->id, w->rank, w->nranks));
+    WK(p4b_mg_create_stencil(ctx, &w->g, &w->o, w->coef, w->nlev, &mg));
+    if (!w->rc) WK(p4b_mg_local_range(mg, &zs, &zm, &nloc));
+    if (!w->rc) {
+        const size_t plane = w->dim == 3 ? (size_t)w->g.mx * w->g.my : (size_t)w->g.mx;      /* nodes per slab index */
+        const size_t off = (size_t)zs * plane;
+        WK(p4b_malloc(ctx, nloc * sizeof(double), (void **)&b));
+        WK(p4b_malloc(ctx, nloc * sizeof(double), (void **)&x));
+        WK(p4b_memcpy_h2d(ctx, b, w->F + off, nloc * sizeof(double)));
+        WK(p4b_cg_solve(mg, w->pct, b, x, w->rtol, w->abstol, w->max_it, &w->res));
+        WK(p4b_memcpy_d2h(ctx, w->Y + off, x, nloc * sizeof(double)));
+    }
+    /* collective teardown: every thread gets here (a failed rank would otherwise leave the others waiting) */
+    if (mg) p4b_mg_destroy(mg);
+    if (b) p4b_free(ctx, b);
+    if (x) p4b_free(ctx, x);
+    if (ctx) p4b_ctx_destroy(ctx);
+#undef WK
+    return NULL;
+}
+static PetscErrorCode ksp_solve_multi_gpu(int ngpu, const p4b_grid *g, const p4b_mg_opts *o, const double *coef, int nlev,
+                                          int pct, const double *F, double *Y, double rtol, double abstol, int max_it,
+                                          p4b_ksp_result *res) {
+    struct mg_worker *w = (struct mg_worker *)calloc((size_t)ngpu, sizeof *w);
+    pthread_t *th = (pthread_t *)calloc((size_t)ngpu, sizeof *th);
+    if (!w || !th) { free(w); free(th); SHIM_ERR(55, "out of memory"); }
+    unsigned char id[128];
+    if (p4b_comm_unique_id(id)) { free(w); free(th); SHIM_ERR(70, p4b_last_error()); }
+    for (int r = 0; r < ngpu; r++) {
+        w[r].rank = r; w[r].nranks = ngpu; w[r].dim = g->dim; w[r].nlev = nlev; w[r].pct = pct; w[r].max_it = max_it;
+        memcpy(w[r].id, id, sizeof id);
+        w[r].g = *g; w[r].o = *o; w[r].coef = coef; w[r].F = F; w[r].Y = Y; w[r].rtol = rtol; w[r].abstol = abstol;
+        if (pthread_create(&th[r], NULL, mg_worker_main, &w[r])) { free(w); free(th); SHIM_ERR(55, "cannot create a host thread"); }
+    }
+    for (int r = 0; r < ngpu; r++) pthread_join(th[r], NULL);
+    char msg[640] = "";
+    for (int r = 0; r < ngpu && !msg[0]; r++)
+        if (w[r].rc) snprintf(msg, sizeof msg, "-p4b_gpus %d, rank %d: %s", ngpu, r, w[r].err);
+    *res = w[0].res;                             /* the Krylov scalars are all-reduced: identical on every rank */
+    for (int r = 1; r < ngpu; r++)
+        if (w[r].res.solve_ms > res->solve_ms) res->solve_ms = w[r].res.solve_ms;
+    free(w); free(th);
+    if (msg[0]) SHIM_ERR(70, msg);
+    return 0;
+}
+
 PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
     if (b) SHIM_ERR(56, "SNESSolve with a right-hand side is not provided");
     if (!strcmp(snes->type, SNESNEWTONLS)) return snes_solve_newtonls(snes, x);
@@ -1496,18 +1569,43 @@ PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
     o.cycle = pc->cycle; o.smoother = pc->smoother; o.smooth_its = pc->smooth_its;
     if (pc->have_eig) { o.emin = pc->emin; o.emax = pc->emax; }
     o.est_lo = pc->est_lo; o.est_hi = pc->est_hi; o.fuse = pc->fuse;
-    p4b_mg *mg = NULL;
-    P4B(p4b_mg_create_stencil(g_ctx, &g, &o, coef, nlev, &mg));
     const int pct = !strcmp(pc->type, PCMG) ? P4B_PC_MG : (!strcmp(pc->type, PCJACOBI) ? P4B_PC_JACOBI : P4B_PC_NONE);
+    int ngpu = 1;
+    {
+        const char *v = opt_value("-p4b_gpus");
+        if (!v) v = getenv("P4B_GPUS");
+        if (v) ngpu = atoi(v);
+        if (ngpu < 1) SHIM_ERR(62, "-p4b_gpus must be at least 1");
+        if (ngpu > 1 && dm->dim == 1) SHIM_ERR(62, "-p4b_gpus: 1-D grids are not distributed");
+    }
+    p4b_mg *mg = NULL;
+    p4b_ksp_result res;
+    if (ngpu > 1) {
+        /* N GPUs, one host thread each (see ksp_solve_multi_gpu); the matrix checks below need the one-GPU hierarchy */
+        if (snes->fd_color || snes->sym_check) {
+            P4B(p4b_mg_create_stencil(g_ctx, &g, &o, coef, nlev, &mg));
+            PetscCall(ksponly_matrix_checks(snes, mg, NULL, u, F));
+            P4B(p4b_mg_destroy(mg));
+            mg = NULL;
+        }
+        PetscCall(vec_to_host(F));
+        PetscCall(vec_to_host(Y));
+        const double t_ksp0 = wall();
+        PetscCall(ksp_solve_multi_gpu(ngpu, &g, &o, coef, nlev, pct, F->h, Y->h, ksp->rtol, ksp->abstol, ksp->max_it, &res));
+        g_t_ksp += wall() - t_ksp0;
+        g_t_ksp_dev_ms += res.solve_ms;
+        Y->valid = LOC_HOST;
+    } else {
+    P4B(p4b_mg_create_stencil(g_ctx, &g, &o, coef, nlev, &mg));
     if (snes->fd_color || snes->sym_check) PetscCall(ksponly_matrix_checks(snes, mg, NULL, u, F));
     PetscCall(vec_to_dev(F));
     PetscCall(vec_to_dev(Y));
-    p4b_ksp_result res;
     const double t_ksp0 = wall();
     P4B(p4b_cg_solve(mg, pct, F->d, Y->d, ksp->rtol, ksp->abstol, ksp->max_it, &res));
     g_t_ksp += wall() - t_ksp0;
     g_t_ksp_dev_ms += res.solve_ms;
     Y->valid = LOC_DEV;
+    }
     ksp->its = res.its;
     ksp->reason = res.reason;
     if (ksp->monitor_flag)
@@ -1516,7 +1614,7 @@ PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
         if (res.reason > 0) printf("    Linear solve converged due to %s iterations %d\n", reason_name(res.reason), res.its);
         else printf("    Linear solve did not converge due to %s iterations %d\n", reason_name(res.reason), res.its);
     }
-    P4B(p4b_mg_destroy(mg));
+    if (mg) P4B(p4b_mg_destroy(mg));
 
     /* u = u0 - y ; then the post-solve function norm PETSc's KSPONLY monitor prints */
     PetscCall(VecAXPY(u, -1.0, Y));

@@ -131,3 +131,38 @@ def test_pattern_on_slabs_equals_the_single_gpu_run(nproc, argv):
         krylov_moved = True
     # same Krylov counts: the states agree to rounding; a moved count leaves the difference of two inexact solves
     assert r["rel_diff"] < (1e-7 if krylov_moved else 1e-12), r["rel_diff"]
+
+
+# ---- the unchanged fish.c on N GPUs from ONE process: -p4b_gpus N (one host thread per GPU inside the shim) ----
+@pytest.mark.parametrize("ngpu", [2, 4, 8])
+@pytest.mark.parametrize("argv", [
+    "-fsh_dim 3 -da_refine 5 -pc_type mg -mg_levels_pc_type jacobi -ksp_rtol 1e-10 -ksp_converged_reason -ksp_monitor",
+    "-fsh_dim 3 -da_refine 6 -pc_mg_levels 5 -pc_type mg -mg_levels_pc_type jacobi -ksp_rtol 1e-10 -ksp_converged_reason "
+    "-snes_monitor_short",
+    "-fsh_dim 2 -da_refine 8 -pc_type mg -mg_levels_pc_type jacobi -ksp_rtol 1e-8 -ksp_converged_reason",
+])
+def test_unchanged_fish_c_on_n_gpus_from_one_process(ngpu, argv):
+    """c/testit.sh:22 runs the reference's binary under `mpiexec -n P`; here the same binary takes -p4b_gpus P: the
+    callbacks see one logical rank, the KSP solve runs on P slabs (peer memory between host threads of one process).
+    Same report as the one-GPU run: iteration counts equal, monitored norms to rounding, error norms to the digits
+    printed."""
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if n < ngpu:
+        pytest.skip("needs %d GPUs" % ngpu)
+    exe = os.path.join(ROOT, "p4pdes_b200", "bin", "fish")
+    if not os.path.exists(exe):
+        pytest.skip("unchanged driver not built")
+
+    def run(extra):
+        p = subprocess.run([exe] + (argv + extra).split(), capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr
+        return p.stdout.splitlines()
+
+    one, many = run(""), run(" -p4b_gpus %d" % ngpu)
+    assert len(one) == len(many)
+    for a, b in zip(one, many):
+        if "KSP Residual norm" in a:
+            fa, fb = float(a.split()[-1]), float(b.split()[-1])
+            assert a.split()[:4] == b.split()[:4] and abs(fa - fb) <= 1e-10 * max(fa, 1e-300) + 1e-16 * float(one[0].split()[-1] if "KSP" in one[0] else 1.0)
+        else:
+            assert a == b, (a, b)
