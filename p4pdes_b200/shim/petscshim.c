@@ -1431,6 +1431,7 @@ static PetscErrorCode ksp_solve_multi_gpu(int ngpu, const p4b_grid *g, const p4b
     pthread_t *th = (pthread_t *)calloc((size_t)ngpu, sizeof *th);
     if (!w || !th) { free(w); free(th); SHIM_ERR(55, "out of memory"); }
     unsigned char id[128];
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);      /* NCCL's banner ("NCCL version ...") must not land in the driver's stdout */
     if (p4b_comm_unique_id(id)) { free(w); free(th); SHIM_ERR(70, p4b_last_error()); }
     for (int r = 0; r < ngpu; r++) {
         w[r].rank = r; w[r].nranks = ngpu; w[r].dim = g->dim; w[r].nlev = nlev; w[r].pct = pct; w[r].max_it = max_it;
