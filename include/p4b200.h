@@ -57,7 +57,10 @@ enum { P4B_CYCLE_V = 1, P4B_CYCLE_W = 2 };
 enum { P4B_SMOOTH_CHEBYSHEV = 0, P4B_SMOOTH_RICHARDSON = 1 };
 enum { P4B_PC_NONE = 0, P4B_PC_JACOBI = 1, P4B_PC_MG = 2 };
 enum { P4B_PROBLEM_MANUPOLY = 0, P4B_PROBLEM_MANUEXP = 1, P4B_PROBLEM_ZERO = 2 };
-enum { P4B_CONVERGED_RTOL = 2, P4B_CONVERGED_ATOL = 3, P4B_DIVERGED_ITS = -3, P4B_DIVERGED_NAN = -9 };
+/* [PETSc] KSPConvergedReason values: KSPSolve_CG stops with INDEFINITE_MAT when (p, A p) <= 0, with INDEFINITE_PC when
+ * (z, r) <= 0, with DTOL when the residual norm exceeds dtol (1e5) times the initial one */
+enum { P4B_CONVERGED_RTOL = 2, P4B_CONVERGED_ATOL = 3, P4B_DIVERGED_ITS = -3, P4B_DIVERGED_DTOL = -4,
+       P4B_DIVERGED_INDEFINITE_PC = -8, P4B_DIVERGED_NAN = -9, P4B_DIVERGED_INDEFINITE_MAT = -10 };
 
 /* -pc_mg_* and -mg_levels_* options. */
 typedef struct {

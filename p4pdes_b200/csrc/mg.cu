@@ -1610,6 +1610,7 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
     R.reason = 0;
     if (!(dp == dp)) R.reason = P4B_DIVERGED_NAN;
     else if (dp <= ttol) R.reason = (dp <= abstol) ? P4B_CONVERGED_ATOL : P4B_CONVERGED_RTOL;
+    else if (h[1] <= 0.0) R.reason = P4B_DIVERGED_INDEFINITE_PC;       // [PETSc] KSPSolve_CG: beta = (z, r) must be positive
     while (!R.reason) {
         if (its >= max_it) { R.reason = P4B_DIVERGED_ITS; break; }
         if (m->o.fuse) {
@@ -1634,9 +1635,15 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
             wrote(m, m->w);
             P4B_CHECK(launch_stencil(st, T.d, op, red));
         }
-        {
+        {   // (p, A p): all-reduced; it also goes to the host (slot 2, read with the next poll) for KSPSolve_CG's
+            // indefinite-matrix test
             ProfScope ps(m, m->top, P4B_K_ALLREDUCE);
-            P4B_CHECK(ctx_allreduce(c, S + 4, 1));
+            if (c->nranks > 1 && c->peer) {
+                P4B_CHECK(launch_allreduce(st, S + 4, 1, 0, c->peers, c->sync, c->d_poll, 0, 2));
+            } else {
+                P4B_CHECK(ctx_allreduce(c, S + 4, 1));
+                P4B_CHECK(launch_publish(st, S + 4, 1, c->d_poll, 0, 2));
+            }
         }
         if (m->o.fuse) {
             ProfScope ps(m, m->top, P4B_K_R_UPDATE);
@@ -1654,8 +1661,13 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
         dp = sqrt(h[0]);
         its++;
         if (R.nhist < P4B_MAX_HIST) R.hist[R.nhist++] = dp;
-        if (!(dp == dp)) R.reason = P4B_DIVERGED_NAN;
+        const double pw = c->h_poll->v[2];              // (p, A p) of this iteration (published before the poll returned)
+        // [PETSc] KSPSolve_CG's order of tests: indefinite matrix, NaN, convergence / divergence tolerance, indefinite PC
+        if (pw <= 0.0) R.reason = P4B_DIVERGED_INDEFINITE_MAT;
+        else if (!(dp == dp)) R.reason = P4B_DIVERGED_NAN;
         else if (dp <= ttol) R.reason = (dp <= abstol) ? P4B_CONVERGED_ATOL : P4B_CONVERGED_RTOL;
+        else if (dp >= 1.0e5 * R.rnorm0) R.reason = P4B_DIVERGED_DTOL;
+        else if (h[1] <= 0.0) R.reason = P4B_DIVERGED_INDEFINITE_PC;
     }
     if (m->o.fuse && its >= 1)      // the last iteration's x += alpha p is still pending
         P4B_CHECK(launch_x_flush(st, n, S + 2 * (1 - q) + 1, S + 4, m->p, x));

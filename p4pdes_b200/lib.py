@@ -19,7 +19,8 @@ SMOOTH_CHEBYSHEV, SMOOTH_RICHARDSON = 0, 1
 PC_NONE, PC_JACOBI, PC_MG = 0, 1, 2
 PROBLEMS = {"manupoly": 0, "manuexp": 1, "zero": 2}
 CONVERGED_RTOL, CONVERGED_ATOL, DIVERGED_ITS, DIVERGED_NAN = 2, 3, -3, -9
-REASONS = {2: "CONVERGED_RTOL", 3: "CONVERGED_ATOL", -3: "DIVERGED_ITS", -9: "DIVERGED_NANORINF"}
+REASONS = {2: "CONVERGED_RTOL", 3: "CONVERGED_ATOL", -3: "DIVERGED_ITS", -4: "DIVERGED_DTOL", -8: "DIVERGED_INDEFINITE_PC",
+           -9: "DIVERGED_NANORINF", -10: "DIVERGED_INDEFINITE_MAT"}
 KERNEL_CLASSES = ["apply_dot", "residual", "cheb_zero", "cheb_first", "cheb_next", "restrict", "prolong_add",
                   "axpy2", "dot2", "aypx", "resid_restrict", "xp_update", "r_update",
                   "halo", "gather", "allreduce", "coarse_solve", "subcycle"]

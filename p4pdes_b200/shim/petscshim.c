@@ -62,9 +62,10 @@ static PetscErrorCode ensure_ctx(void) {
 
 /* ---- options ---- */
 static int opt_find(const char *name) {
-    for (int i = 0; i < g_nopt; i++)
-        if (!strcmp(g_opt[i].name, name)) { g_opt[i].used = 1; return i; }
-    return -1;
+    int found = -1;
+    for (int i = 0; i < g_nopt; i++)            /* [PETSc] the options database keeps the LAST value given */
+        if (!strcmp(g_opt[i].name, name)) { g_opt[i].used = 1; found = i; }
+    return found;
 }
 static const char *opt_value(const char *name) {
     int i = opt_find(name);
@@ -91,7 +92,10 @@ PetscErrorCode PetscInitialize(int *argc, char ***argv, const char file[], const
     for (int i = 1; argc && i < *argc; i++) {
         const char *a = (*argv)[i];
         if (a[0] != '-' || is_number(a)) continue;
-        if (g_nopt >= MAXOPT) break;
+        if (g_nopt >= MAXOPT) {
+            fprintf(stderr, "[p4b200 shim] more than %d options on the command line: %s and what follows are ignored\n", MAXOPT, a);
+            break;
+        }
         g_opt[g_nopt].name = strdup(a);
         g_opt[g_nopt].value = NULL;
         g_opt[g_nopt].used = 0;
@@ -971,6 +975,9 @@ static const char *reason_name(int r) {
         case P4B_CONVERGED_RTOL: return "CONVERGED_RTOL";
         case P4B_CONVERGED_ATOL: return "CONVERGED_ATOL";
         case P4B_DIVERGED_ITS: return "DIVERGED_ITS";
+        case P4B_DIVERGED_DTOL: return "DIVERGED_DTOL";
+        case P4B_DIVERGED_INDEFINITE_MAT: return "DIVERGED_INDEFINITE_MAT";
+        case P4B_DIVERGED_INDEFINITE_PC: return "DIVERGED_INDEFINITE_PC";
         default: return "DIVERGED_NANORINF";
     }
 }
@@ -1334,11 +1341,14 @@ static PetscErrorCode ksponly_solve_assembled(SNES snes, Vec u, Vec F, Vec Y, do
     const double ttol = ksp->rtol * dp > ksp->abstol ? ksp->rtol * dp : ksp->abstol;
     int its = 0, reason = P4B_DIVERGED_ITS;
     if (ksp->monitor_flag) printf("    %d KSP Residual norm %14.12e\n", 0, dp);
+    const double dp0 = dp;
     if (dp <= ttol) reason = P4B_CONVERGED_ATOL;
+    else if (beta <= 0.0) reason = P4B_DIVERGED_INDEFINITE_PC;       /* [PETSc] KSPSolve_CG: (z, r) must be positive */
     while (reason == P4B_DIVERGED_ITS && its < ksp->max_it) {
         double pw = 0.0, bnew = 0.0;
         P4B(p4b_sell_spmv(A, P->d, Wv->d));
         P4B(p4b_vec_dot(g_ctx, n, P->d, Wv->d, &pw));
+        if (pw <= 0.0) { reason = P4B_DIVERGED_INDEFINITE_MAT; break; }      /* any coefficients can arrive here */
         const double a = beta / pw;
         P4B(p4b_vec_axpy(g_ctx, n, a, P->d, Y->d));
         P4B(p4b_vec_axpy(g_ctx, n, -a, Wv->d, R->d));
@@ -1349,7 +1359,9 @@ static PetscErrorCode ksponly_solve_assembled(SNES snes, Vec u, Vec F, Vec Y, do
         if (ksp->monitor_flag) printf("    %d KSP Residual norm %14.12e\n", its, dp);
         if (!(dp == dp)) { reason = P4B_DIVERGED_NAN; break; }
         if (dp <= ttol) { reason = dp <= ksp->abstol ? P4B_CONVERGED_ATOL : P4B_CONVERGED_RTOL; break; }
+        if (dp >= 1.0e5 * dp0) { reason = P4B_DIVERGED_DTOL; break; }        /* [PETSc] -ksp_divtol default */
         P4B(p4b_vec_dot(g_ctx, n, Z->d, R->d, &bnew));
+        if (bnew <= 0.0) { reason = P4B_DIVERGED_INDEFINITE_PC; break; }
         P4B(p4b_vec_aypx(g_ctx, n, bnew / beta, Z->d, P->d));          /* p = z + (beta_new / beta) p */
         beta = bnew;
     }
