@@ -440,6 +440,13 @@ int p4b_bratu_exact(p4b_ctx *ctx, int mx, int my, int exact, double *g);
 int p4b_bratu_solve(p4b_ctx *ctx, const p4b_bratu_opts *opts, p4b_line_fn line, void *line_ctx, double *u_out,
                     size_t u_capacity, p4b_bratu_result *result);
 
+/* [PETSc] TSMonitorSet with a solution viewer (-ts_monitor binary:t.dat -ts_monitor_solution binary:u.dat, c/ch5/MOVIES.md:44):
+ * a process-wide step monitor of p4b_pattern_solve / p4b_ts2d_solve.  It is called at step 0 and after every accepted
+ * step with the time and a HOST copy of the state (this rank's rows on slabs); a non-zero return aborts the solve.
+ * fn = NULL removes it. */
+typedef int (*p4b_ts_step_fn)(void *user, int step, double t, const double *Y_host, size_t n);
+int p4b_set_ts_step_monitor(p4b_ts_step_fn fn, void *user);
+
 /* Multi-GPU (BASELINE config 5: 2048^2 on 8 GPUs): with a context that carries a communicator (p4b_comm_init)
  * p4b_pattern_solve / p4b_pattern_solve_from run on y-slabs of the periodic DMDA (c/ch5/pattern.c:79-84) -- ring
  * exchange of one ghost row per side ([PETSc] DMGlobalToLocal), all-reduced dot products, small levels replicated.

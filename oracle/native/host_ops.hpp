@@ -47,6 +47,12 @@ struct HostOps {
     bool verify_converged(int, int, const double *, const double *) { return true; }
     void set_linearisation(const double *) {}
     void set_time(double) {}
+    // TS step monitor: the stand-in's own registration (p4b_standin.cpp) or none (nk_host_main.cpp)
+    static int (*&ts_fn())(void *, int, double, const double *, size_t) { static int (*f)(void *, int, double, const double *, size_t) = nullptr; return f; }
+    static void *&ts_user() { static void *u = nullptr; return u; }
+    void ts_step(int k, double t, const double *Y, size_t n) {
+        if (ts_fn() && !err && ts_fn()(ts_user(), k, t, Y, n)) err = 66;
+    }
 
     // c/ch7/minimal.c:27-42  g_bdry_tent / g_bdry_catenoid at every node of the unit square
     void minimal_sample(int mx, int my, int problem, double H, double c, double *g) {

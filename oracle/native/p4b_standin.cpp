@@ -46,6 +46,7 @@ int p4b_tune(const char *key, long value) {
     return fail(62, "stand-in: unknown tuning key");
 }
 long long p4b_launch_count(void) { return 0; }
+int p4b_set_ts_step_monitor(p4b_ts_step_fn fn, void *user) { HostOps::ts_fn() = fn; HostOps::ts_user() = user; return 0; }
 // the VecSetRandom stream is host code in the product too (mg.cu): the same drand48 recurrence
 unsigned long long p4b_rander48_seed(unsigned long seed) { return (((unsigned long long)(seed & 0xffffffffUL)) << 16) | 0x330EULL; }
 int p4b_rander48_fill(unsigned long long *state, size_t n, double *out) {

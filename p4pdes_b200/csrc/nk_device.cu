@@ -20,10 +20,22 @@ int ctx_nranks(p4b_ctx *c);
 int ctx_ring_halo(p4b_ctx *c, double *owned, size_t rowlen, int nrows);
 int ctx_allgather(p4b_ctx *c, double *full, size_t count);
 
+// process-wide TS step monitor (p4b_set_ts_step_monitor)
+static p4b_ts_step_fn g_ts_step_fn = nullptr;
+static void *g_ts_step_user = nullptr;
+
 struct DeviceOps {
     p4b_ctx *c;
     cudaStream_t st;
     int err = 0;
+    std::vector<double> ts_host;
+    void ts_step_n(int k, double t, const double *Y, size_t nloc) {
+        if (!g_ts_step_fn || err) return;
+        ts_host.resize(nloc);
+        to_host(Y, ts_host.data(), nloc);
+        if (!err && g_ts_step_fn(g_ts_step_user, k, t, ts_host.data(), nloc)) err = 66;
+    }
+    void ts_step(int k, double t, const double *Y, size_t n) { ts_step_n(k, t, Y, n); }
     int error() const { return err; }
     void chk(int rc) { if (rc && !err) err = rc; }
     void cu(cudaError_t e) { if (e != cudaSuccess && !err) err = 70 + (int)e % 20; }
@@ -224,6 +236,7 @@ struct SlabPatternOps : DeviceOps {
     void axpby(size_t n, double a, const double *x, double b, const double *y, double *out) { DeviceOps::axpby(local_n(n), a, x, b, y, out); }
     void copy(size_t n, const double *x, double *y) { DeviceOps::copy(local_n(n), x, y); }
     void set(size_t n, double a, double *y) { DeviceOps::set(local_n(n), a, y); }
+    void ts_step(int k, double t, const double *Y, size_t n) { ts_step_n(k, t, Y, local_n(n)); }
     void halo(const SlabPlan::Lev &L, const double *v) { chk(ctx_ring_halo(c, const_cast<double *>(v), (size_t)2 * L.m, L.ym)); }
     static void coef(const PO &o, int m, double *Cu, double *Cv) {
         const double h = o.L / (double)m;                      // pattern.c:246
@@ -586,6 +599,12 @@ extern "C" int p4b_pattern_default_opts(p4b_pattern_opts *o) {
     if (!o) return fail(62, "null options");
     static_assert(sizeof(p4b_pattern_opts) == sizeof(nk::PatternOpts), "p4b_pattern_opts and nk::PatternOpts must agree");
     nk::default_opts(reinterpret_cast<nk::PatternOpts *>(o));
+    return 0;
+}
+
+extern "C" int p4b_set_ts_step_monitor(p4b_ts_step_fn fn, void *user) {
+    g_ts_step_fn = fn;
+    g_ts_step_user = user;
     return 0;
 }
 

@@ -329,6 +329,7 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
         for (int i = 0; i < 4; i++) { Ys[i] = take(); FI[i] = take(); FE[i] = take(); }
         ops->set(n, 0.0, zero);
         while (t < tmax - 1e-12 * std::max(1.0, fabs(tmax)) && k < opt.ts_max_steps && !rc) {
+            ops->ts_step(k, t, Y, n);                        // [PETSc] TSMonitor: step, time, solution
             if (opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(h).c_str(), fmt_g(t).c_str());
             bool prev_accept = true;
             double hnext = h;
@@ -401,6 +402,7 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
             k++;
             if (ops->error()) rc = ops->error();
         }
+        if (!rc) ops->ts_step(k, t, Y, n);
         if (!rc && opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(h).c_str(), fmt_g(t).c_str());
     } else {
         double *Yprev = take(), *Ydot = take(), *G = take(), *affine = take(), *y = take(), *Jy = take(), *wv = take(), *gnew = take();
@@ -475,7 +477,8 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
             };
             double dt_next = h;
             while (t < tmax - 1e-12 * std::max(1.0, fabs(tmax)) && k < opt.ts_max_steps && !rc) {
-                if (opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(h).c_str(), fmt_g(t).c_str());
+                ops->ts_step(k, t, Y, n);                        // [PETSc] TSMonitor: step, time, solution
+            if (opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(h).c_str(), fmt_g(t).c_str());
                 ops->copy(n, Y, Yprev);                              // lev[0].Y is the linearisation point from here on
                 if (!restart) { kord = std::min(kord + 1, order); advance(t, Yprev); }
                 bool accept = true;
@@ -531,14 +534,16 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
                 k++;
                 if (ops->error()) rc = ops->error();
             }
-            if (!rc && opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(dt_next).c_str(), fmt_g(t).c_str());
+            if (!rc) ops->ts_step(k, t, Y, n);
+        if (!rc && opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(dt_next).c_str(), fmt_g(t).c_str());
         } else {
             const double theta = opt.ts_type == TS_CN ? 0.5 : 1.0;
             double dt_last = opt.ts_dt;
             while (t < tmax - 1e-14 * std::max(1.0, fabs(tmax)) && k < opt.ts_max_steps && !rc) {
                 const double dt = std::min(opt.ts_dt, tmax - t);     // TS_EXACTFINALTIME_MATCHSTEP (:118)
                 dt_last = dt;
-                if (opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(dt).c_str(), fmt_g(t).c_str());
+                ops->ts_step(k, t, Y, n);                        // [PETSc] TSMonitor: step, time, solution
+            if (opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(dt).c_str(), fmt_g(t).c_str());
                 const double shift = 1.0 / (theta * dt);
                 ops->copy(n, Y, Yprev);
                 if (theta != 1.0) {
@@ -568,7 +573,8 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
                 k++;
                 if (ops->error()) rc = ops->error();
             }
-            if (!rc && opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(dt_last).c_str(), fmt_g(t).c_str());
+            if (!rc) ops->ts_step(k, t, Y, n);
+        if (!rc && opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(dt_last).c_str(), fmt_g(t).c_str());
         }
     }
     R->nsteps = k;

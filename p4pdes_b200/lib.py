@@ -102,6 +102,7 @@ RESIDUAL2D_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c
 IFUNCTION2D_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double),
                              C.POINTER(C.c_double))
 RHSFUNCTION2D_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double))
+TS_STEP_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double), C.c_size_t)
 MONITOR2D_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double))
 
 
@@ -190,6 +191,7 @@ _SIGS = {
     "p4b_bratu_ngs": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, _D, _D]),
     "p4b_bratu_exact": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _D]),
     "p4b_bratu_solve": (C.c_int, [_P, C.POINTER(BratuOpts), LINE_FN, C.c_void_p, _D, C.c_size_t, C.POINTER(BratuResult)]),
+    "p4b_set_ts_step_monitor": (C.c_int, [TS_STEP_FN, C.c_void_p]),
     "p4b_pattern_slab_plan": (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int)] * 4),
     "p4b_rander48_seed": (C.c_ulonglong, [C.c_ulong]),
     "p4b_rander48_fill": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_size_t, C.c_void_p]),

@@ -57,6 +57,8 @@ class PatternOptions:
     ts_rtol: float = 1.0e-4
     ts_atol: float = 1.0e-4
     ts_monitor: bool = False
+    ts_monitor_file: str = ""           # -ts_monitor binary:FILE            (c/ch5/MOVIES.md:44: PETSc binary Real records)
+    ts_monitor_solution_file: str = ""  # -ts_monitor_solution binary:FILE   (PETSc binary Vec records; native host only)
     pc_type: str = "mg"
     smooth_its: int = 2
     mg_rscale: float = 1.0          # -p4b_mg_rscale: factor on the restricted residual.  1 = [PETSc] R = P^T.  pattern.c's
@@ -96,7 +98,12 @@ def parse_options(argv) -> PatternOptions:
     i = 0
     while i < len(argv):
         a = argv[i]
-        if a in flags:
+        if a in ("-ts_monitor", "-ts_monitor_solution") and i + 1 < len(argv) and argv[i + 1].startswith("binary:"):
+            setattr(o, "ts_monitor_file" if a == "-ts_monitor" else "ts_monitor_solution_file", argv[i + 1][len("binary:"):])
+            i += 2
+        elif a == "-ts_monitor_solution":
+            raise ValueError("-ts_monitor_solution: the binary viewer is provided (binary:FILE)")
+        elif a in flags:
             setattr(o, flags[a], True)
             i += 1
         elif a in valued:
@@ -282,6 +289,25 @@ def _pattern_native(opt: PatternOptions, ctx, out) -> PatternReport:
     res = L.PatternResult()
     say = out if rank == 0 else (lambda s: None)
     cb = L.LINE_FN(lambda line, _ctx: say(line.decode()))
+    step_cb, files = None, []
+    if opt.ts_monitor_file or opt.ts_monitor_solution_file:
+        # [PETSc] binary viewers on the TS monitors: times and states as PETSc binary records (petscbin.py)
+        import numpy as np
+        from . import petscbin
+        suffix = ".rank%d" % rank if nranks > 1 else ""          # on slabs every rank writes its rows
+        ft = open(opt.ts_monitor_file, "wb") if (opt.ts_monitor_file and rank == 0) else None
+        fu = open(opt.ts_monitor_solution_file + suffix, "wb") if opt.ts_monitor_solution_file else None
+        files = [f for f in (ft, fu) if f]
+
+        def _step(_user, _k, t, Yp, n):
+            if ft:
+                petscbin.write_real(ft, t)
+            if fu:
+                petscbin.write_vec(fu, np.ctypeslib.as_array(Yp, shape=(n,)))
+            return 0
+
+        step_cb = L.TS_STEP_FN(_step)
+        L.check(ctx.lib.p4b_set_ts_step_monitor(step_cb, None))
     t0 = time.perf_counter()
     if opt.noisy_init > 0.0:
         # the caller's initial state (what the shim's TSSolve does with pattern.c's Vec); on slabs: rows [ys, ys + rows)
@@ -298,6 +324,10 @@ def _pattern_native(opt: PatternOptions, ctx, out) -> PatternReport:
     else:
         L.check(ctx.lib.p4b_pattern_solve(ctx.h, C.byref(o), cb, None, Y.data_ptr(), Y.numel(), C.byref(res)))
     seconds = time.perf_counter() - t0
+    if step_cb is not None:
+        L.check(ctx.lib.p4b_set_ts_step_monitor(C.cast(None, L.TS_STEP_FN), None))
+        for f in files:
+            f.close()
     steps = [(res.step_t[k], res.step_dt[k], res.step_newton[k]) for k in range(min(res.nsteps, 512))]
     if opt.log_view:
         out("TSSolve %.6f s (%d steps, %d rejected, %d GMRES iterations)" % (seconds, res.nsteps, res.rejected,
@@ -329,6 +359,8 @@ def pattern_main(argv, ops, echo=False, native=False) -> PatternReport:
         rep = _pattern_native(opt, ops, out)
         rep.lines = lines
         return rep
+    if opt.ts_monitor_file or opt.ts_monitor_solution_file:
+        raise ValueError("-ts_monitor[_solution] binary:FILE: provided by the native host (pattern_main(..., native=True))")
 
     mx, my = opt.grid_x * 2 ** opt.refine, opt.grid_y * 2 ** opt.refine     # periodic: -da_refine doubles
     if mx != my:

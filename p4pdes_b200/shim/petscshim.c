@@ -72,6 +72,11 @@ static const char *opt_value(const char *name) {
     return i < 0 ? NULL : g_opt[i].value;
 }
 static int opt_has(const char *name) { return opt_find(name) >= 0; }
+static const char *binary_target(const char *optname) {        /* "binary:FILE" -> FILE */
+    const char *v = opt_value(optname);
+    return (v && !strncmp(v, "binary:", 7) && v[7]) ? v + 7 : NULL;
+}
+
 static int opt_bool(const char *name, int dflt) {
     int i = opt_find(name);
     if (i < 0) return dflt;
@@ -1756,7 +1761,7 @@ PetscErrorCode TSSetFromOptions(TS ts) {
         else if (!strcmp(v, "interpolate")) ts->eft = TS_EXACTFINALTIME_INTERPOLATE;
         else SHIM_ERR(62, "-ts_exact_final_time: stepover, interpolate or matchstep");
     }
-    ts->monitor = opt_has("-ts_monitor");
+    ts->monitor = opt_has("-ts_monitor") && !binary_target("-ts_monitor");      /* a binary viewer prints nothing */
     /* KSP / PC / SNES options of the stage solves.  -snes_fd_color (pattern.test3) asks PETSc to difference the residual
      * instead of calling the Jacobian callbacks: the device stage operator IS the analytic Jacobian those differences
      * approximate, so the option only means that the Jacobian callbacks are not called (nor checked) */
@@ -1931,6 +1936,30 @@ static PetscErrorCode ts_solve_general(TS ts, Vec x, struct ts_work *W, p4b_patt
     if (prc) return PetscShimError(PETSC_COMM_SELF, __LINE__, __func__, __FILE__, prc, p4b_last_error());
     x->valid = LOC_HOST;
     g_ts_general++;
+    return 0;
+}
+
+/* [PETSc] binary viewers on the TS monitors (c/ch5/MOVIES.md:44: -ts_monitor binary:t.dat -ts_monitor_solution binary:u.dat):
+ * big-endian records, class id first -- Real 1211213 + one double per step into the first file, Vec 1211214 + length +
+ * values into the second; what $PETSC_DIR/lib/petsc/bin/PetscBinaryIO.py (c/ch5/plotTS.py:44-46) reads. */
+static struct { FILE *ft, *fu; } g_tsbin;
+static void put_be32(FILE *f, int v) {
+    unsigned char b[4] = {(unsigned char)((unsigned)v >> 24), (unsigned char)((unsigned)v >> 16), (unsigned char)((unsigned)v >> 8), (unsigned char)v};
+    fwrite(b, 1, 4, f);
+}
+static void put_be64(FILE *f, const double *v, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        unsigned long long u;
+        unsigned char b[8];
+        memcpy(&u, v + i, 8);
+        for (int k = 0; k < 8; k++) b[k] = (unsigned char)(u >> (56 - 8 * k));
+        fwrite(b, 1, 8, f);
+    }
+}
+static int ts_binary_monitor(void *user, int step, double t, const double *Y, size_t n) {
+    (void)user; (void)step;
+    if (g_tsbin.ft) { put_be32(g_tsbin.ft, 1211213); put_be64(g_tsbin.ft, &t, 1); }
+    if (g_tsbin.fu) { put_be32(g_tsbin.fu, 1211214); put_be32(g_tsbin.fu, (int)n); put_be64(g_tsbin.fu, Y, n); }
     return 0;
 }
 
@@ -2176,7 +2205,22 @@ static PetscErrorCode ts_solve(TS ts, Vec x, struct ts_work *W) {
 PetscErrorCode TSSolve(TS ts, Vec x) {
     struct ts_work W;
     memset(&W, 0, sizeof W);
+    {
+        const char *ft = binary_target("-ts_monitor"), *fu = binary_target("-ts_monitor_solution");
+        if (opt_value("-ts_monitor_solution") && !fu)
+            SHIM_ERR(56, "-ts_monitor_solution: the binary viewer is provided (binary:FILE); draw / ascii viewers are not");
+        g_tsbin.ft = ft ? fopen(ft, "wb") : NULL;
+        g_tsbin.fu = fu ? fopen(fu, "wb") : NULL;
+        if ((ft && !g_tsbin.ft) || (fu && !g_tsbin.fu)) SHIM_ERR(65, "cannot open the binary viewer's file for writing");
+        if (g_tsbin.ft || g_tsbin.fu) P4B(p4b_set_ts_step_monitor(ts_binary_monitor, NULL));
+    }
     PetscErrorCode rc = ts_solve(ts, x, &W);
+    if (g_tsbin.ft || g_tsbin.fu) {
+        p4b_set_ts_step_monitor(NULL, NULL);
+        if (g_tsbin.ft) fclose(g_tsbin.ft);
+        if (g_tsbin.fu) fclose(g_tsbin.fu);
+        g_tsbin.ft = g_tsbin.fu = NULL;
+    }
     ts_work_release(&W);                         /* also on every error return of ts_solve */
     return rc;
 }

@@ -62,3 +62,27 @@ def test_unchanged_pattern_c_with_the_cluster_script_noise():
     want = pp.pattern_main(argv.replace(" -mg_levels_pc_type jacobi", ""), Context())
     got = [l for l in p.stdout.splitlines() if "TS dt" in l]
     assert got and got == [l for l in want.lines if "TS dt" in l]
+
+
+def test_ts_binary_monitors_on_device(ctx, tmp_path):
+    """c/ch5/MOVIES.md:44 on the device: times and states of every step as PETSc binary records (native host and the
+    unchanged pattern.c under the shim write the same files)."""
+    from p4pdes_b200 import petscbin
+    t, u = str(tmp_path / "t.dat"), str(tmp_path / "u.dat")
+    argv = "-da_refine 3 -ts_max_time 30 -pc_type mg"
+    ref = pp.pattern_main(argv + " -ts_monitor", ctx, native=True)
+    rep = pp.pattern_main(argv + " -ts_monitor binary:%s -ts_monitor_solution binary:%s" % (t, u), ctx, native=True)
+    times, states = petscbin.read_file(t), petscbin.read_file(u)
+    nlines = len([l for l in ref.lines if " TS dt " in l])
+    assert len(times) == len(states) == nlines and not any(" TS dt " in l for l in rep.lines)
+    assert abs(times[-1] - 30.0) < 1e-12 and times[0] == 0.0
+    assert float(np.max(np.abs(states[-1] - rep.Y.cpu().numpy()))) == 0.0
+    exe = os.path.join(ROOT, "p4pdes_b200", "bin", "pattern")
+    if os.path.exists(exe):
+        t2, u2 = str(tmp_path / "t2.dat"), str(tmp_path / "u2.dat")
+        p = subprocess.run([exe] + (argv + " -mg_levels_pc_type jacobi -ts_monitor binary:%s -ts_monitor_solution binary:%s"
+                                    % (t2, u2)).split(), capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr
+        s2 = petscbin.read_file(u2)
+        assert len(s2) == len(states) and float(np.max(np.abs(s2[-1] - states[-1]))) < 1e-9
+        np.testing.assert_allclose(petscbin.read_file(t2), times, rtol=1e-12)
