@@ -1468,6 +1468,61 @@ static PetscErrorCode ksp_solve_multi_gpu(int ngpu, const p4b_grid *g, const p4b
     return 0;
 }
 
+/* -p4b_gpus N for the unchanged pattern.c: the time stepping of the recognised model on y-slabs, one host thread per GPU
+ * (p4b_pattern_solve_from on a communicator: ring ghost rows, all-reduced dots).  Rank 0 prints. */
+struct ts_worker {
+    int rank, nranks, m, rc;
+    unsigned char id[128];
+    p4b_pattern_opts o;
+    double *Y;                   /* host: the whole grid, 2 m m doubles; every rank reads and writes its rows */
+    p4b_pattern_result res;
+    char err[512];
+};
+static void newton_line_fwd(const char *line, void *ctx) { (void)ctx; puts(line); }
+static void *ts_worker_main(void *arg) {
+    struct ts_worker *w = (struct ts_worker *)arg;
+    p4b_ctx *ctx = NULL;
+    double *y = NULL;
+    const size_t rows = (size_t)(w->m / w->nranks), nloc = 2 * (size_t)w->m * rows, off = nloc * (size_t)w->rank;
+#define WK(call) do { if (!w->rc && (call)) { w->rc = 70; snprintf(w->err, sizeof w->err, "%s", p4b_last_error()); } } while (0)
+    WK(p4b_ctx_create_own_stream(w->rank, &ctx));
+    WK(p4b_comm_init(ctx, w->id, w->rank, w->nranks));
+    WK(p4b_malloc(ctx, nloc * sizeof(double), (void **)&y));
+    WK(p4b_memcpy_h2d(ctx, y, w->Y + off, nloc * sizeof(double)));
+    WK(p4b_pattern_solve_from(ctx, &w->o, y, w->rank == 0 ? newton_line_fwd : NULL, NULL, y, nloc, &w->res));
+    WK(p4b_memcpy_d2h(ctx, w->Y + off, y, nloc * sizeof(double)));
+    if (y) p4b_free(ctx, y);
+    if (ctx) p4b_ctx_destroy(ctx);
+#undef WK
+    return NULL;
+}
+static PetscErrorCode ts_solve_multi_gpu(int ngpu, int m, const p4b_pattern_opts *o, double *Y, p4b_pattern_result *res) {
+    if (m % ngpu || (m / ngpu) % 2) {
+        char msg[256];
+        snprintf(msg, sizeof msg, "-p4b_gpus %d: the %d rows of the grid must split into an even number of rows per GPU", ngpu, m);
+        SHIM_ERR(60, msg);
+    }
+    struct ts_worker *w = (struct ts_worker *)calloc((size_t)ngpu, sizeof *w);
+    pthread_t *th = (pthread_t *)calloc((size_t)ngpu, sizeof *th);
+    if (!w || !th) { free(w); free(th); SHIM_ERR(55, "out of memory"); }
+    unsigned char id[128];
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+    if (p4b_comm_unique_id(id)) { free(w); free(th); SHIM_ERR(70, p4b_last_error()); }
+    for (int r = 0; r < ngpu; r++) {
+        w[r].rank = r; w[r].nranks = ngpu; w[r].m = m; w[r].o = *o; w[r].Y = Y;
+        memcpy(w[r].id, id, sizeof id);
+        if (pthread_create(&th[r], NULL, ts_worker_main, &w[r])) { free(w); free(th); SHIM_ERR(55, "cannot create a host thread"); }
+    }
+    for (int r = 0; r < ngpu; r++) pthread_join(th[r], NULL);
+    char msg[640] = "";
+    for (int r = 0; r < ngpu && !msg[0]; r++)
+        if (w[r].rc) snprintf(msg, sizeof msg, "-p4b_gpus %d, rank %d: %s", ngpu, r, w[r].err);
+    *res = w[0].res;
+    free(w); free(th);
+    if (msg[0]) SHIM_ERR(70, msg);
+    return 0;
+}
+
 PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
     if (b) SHIM_ERR(56, "SNESSolve with a right-hand side is not provided");
     if (!strcmp(snes->type, SNESNEWTONLS)) return snes_solve_newtonls(snes, x);
@@ -2172,10 +2227,27 @@ static PetscErrorCode ts_solve(TS ts, Vec x, struct ts_work *W) {
     fprintf(stderr, "[p4b200] TS: the registered callbacks equal the library's reaction-diffusion model (F, G at three "
                     "times and states, every Jacobian row; re-verified at the final state): time stepping on the device.  "
                     "-p4b_recognise_residual 0 -pc_type none runs the host callbacks.\n");
+    int ngpu = 1;
+    {
+        const char *v = opt_value("-p4b_gpus");
+        if (!v) v = getenv("P4B_GPUS");
+        if (v) ngpu = atoi(v);
+        if (ngpu < 1) SHIM_ERR(62, "-p4b_gpus must be at least 1");
+        if (ngpu > 1 && (g_tsbin.ft || g_tsbin.fu))
+            SHIM_ERR(56, "-ts_monitor[_solution] binary: with -p4b_gpus > 1 is not provided (every GPU holds its rows only)");
+    }
+    if (ngpu > 1) {
+        PetscCall(vec_to_host(x));
+        fflush(stdout);
+        PetscCall(ts_solve_multi_gpu(ngpu, m, &o, x->h, R));
+        fflush(stdout);
+        x->valid = LOC_HOST;
+    } else {
     int rc = p4b_pattern_solve_from(g_ctx, &o, x->d, newton_line, NULL, x->d, n, R);
     fflush(stdout);
     if (rc) return PetscShimError(PETSC_COMM_SELF, __LINE__, __func__, __FILE__, rc, p4b_last_error());
     x->valid = LOC_DEV;
+    }
     {   /* (4) once more where the solve ended up: the final state at the final time.  The probes are a finite sample;
          *     what they could not see is reported loudly here (the trajectory has been printed already, so this is an
          *     error, not a silent re-run) */

@@ -166,3 +166,27 @@ def test_unchanged_fish_c_on_n_gpus_from_one_process(ngpu, argv):
             assert a.split()[:4] == b.split()[:4] and abs(fa - fb) <= 1e-10 * max(fa, 1e-300) + 1e-16 * float(one[0].split()[-1] if "KSP" in one[0] else 1.0)
         else:
             assert a == b, (a, b)
+
+
+@pytest.mark.parametrize("ngpu", [2, 8])
+@pytest.mark.parametrize("argv", [
+    "-da_grid_x 4 -da_grid_y 4 -da_refine 4 -ts_monitor -ts_max_time 40 -pc_type mg -mg_levels_pc_type jacobi",
+    "-da_grid_x 4 -da_grid_y 4 -da_refine 5 -ts_type beuler -ts_dt 5 -ts_max_time 15 -ts_monitor -pc_type mg "
+    "-mg_levels_pc_type jacobi -snes_converged_reason -ptn_noisy_init 0.1",
+])
+def test_unchanged_pattern_c_on_n_gpus_from_one_process(ngpu, argv):
+    """BASELINE config 5 ("pattern.c ... 8 B200") through the reference's own driver: ./pattern ... -p4b_gpus N runs the
+    time stepping on y-slabs, one host thread per GPU; stdout equals the one-GPU run's."""
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if n < ngpu:
+        pytest.skip("needs %d GPUs" % ngpu)
+    exe = os.path.join(ROOT, "p4pdes_b200", "bin", "pattern")
+    if not os.path.exists(exe):
+        pytest.skip("unchanged driver not built")
+
+    def run(extra):
+        p = subprocess.run([exe] + (argv + extra).split(), capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr
+        return [l for l in p.stdout.splitlines() if not l.startswith("NCCL version")]
+
+    assert run("") == run(" -p4b_gpus %d" % ngpu)
