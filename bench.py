@@ -31,7 +31,7 @@ OPTIONS = ("-fsh_dim 3 -da_refine {refine} -pc_type mg -pc_mg_levels {levels} -m
            "-mg_levels_ksp_max_it 2 -mg_levels_pc_type jacobi -ksp_rtol 1e-10")
 ALG_BYTES = {"apply_dot": "16N", "residual": "24N", "cheb_zero": "16N", "cheb_first": "24N", "cheb_next": "32N",
              "restrict": "8N+8Nc", "prolong_add": "16N+8Nc", "axpy2": "48N", "dot2": "16N", "aypx": "24N",
-             "resid_restrict": "16N+8Nc", "xp_update": "40N", "r_update": "24N"}
+             "xp_update": "40N", "r_update": "24N"}
 
 
 def peaks():
@@ -84,6 +84,28 @@ class ClockSampler:
                         reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def bind_to_gpu_cpus(index):
+    """Pin this process to the CPUs that are local to GPU `index` (NVML's ideal affinity) BEFORE pinned host memory is
+    allocated: under torchrun nothing binds the ranks, and eight ranks that pin their e2e buffers on one NUMA node share
+    one memory controller and one inter-socket link for their PCIe copies (round 1: the 8-GPU e2e copies took 17 ms
+    where 4.7 ms were possible).  Best effort: a restricted cpuset or a missing NVML leaves the affinity alone."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(index)
+        if all(hasattr(pr, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):      # immune to CUDA_VISIBLE_DEVICES
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08X:%02X:%02X.0" % (pr.pci_domain_id, pr.pci_bus_id,
+                                                                              pr.pci_device_id)).encode())
+        else:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return {"cpus_before": before, "cpus_after": len(os.sched_getaffinity(0))}
+    except Exception as exc:
+        return {"error": repr(exc)[:120]}
 
 
 def cpu_reference(refine, levels, threads=None, repeats=1):
@@ -444,6 +466,7 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
     torch.cuda.set_device(local_rank)
+    affinity = bind_to_gpu_cpus(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # everything runs on one explicit (capturable) stream: torch ops, the library's kernels, its CUDA graph
@@ -568,7 +591,7 @@ def main():
         ms_e2e = max_over_ranks(max(e0.elapsed_time(e1) / nst, 0.0))
         e2e = {"value": ndof / (ms_e2e * 1e-3) / 1e6, "unit": "MDOF/s", "h2d_bytes_per_step": 8 * nloc * world,
                "d2h_bytes_per_step": 8 * nloc * world, "ms_per_step": ms_e2e, "wall_ms_per_step": wall * 1e3,
-               "api": "p4b_cg_solve_host (pinned host b -> device, solve, x -> pinned host)"}
+               "api": "p4b_cg_solve_host (pinned host b -> device, solve, x -> pinned host)", "cpu_affinity": affinity}
 
     if rank != 0:
         if world > 1:

@@ -97,7 +97,7 @@ enum {
     P4B_K_AXPY2,           /* x += a p ; r -= a w                  48 N */
     P4B_K_DOT2,            /* (z,z), (z,r)                         16 N */
     P4B_K_AYPX,            /* p = z + b p                          24 N */
-    P4B_K_RESID_RESTRICT,  /* b_c = P^T (b - A x) fused            16 N + 8 N_c */
+    P4B_K_RESID_RESTRICT,  /* reserved (no fused residual+restriction kernel exists: DESIGN.md section 4) */
     P4B_K_XP_UPDATE,       /* x += a p ; p = z + b p (one pass)    40 N */
     P4B_K_R_UPDATE,        /* r -= a w                             24 N */
     /* not kernels of the roofline table: exchange / latency items, timed the same way (0 algorithmic bytes) */
@@ -171,6 +171,9 @@ int p4b_cheb_jacobi(p4b_ctx *ctx, const p4b_grid *g, double emin, double emax, i
 /* fine grid g; coarse arrays have ((mx-1)/2+1) ... nodes per used dimension */
 int p4b_restrict(p4b_ctx *ctx, const p4b_grid *gfine, const double *rfine, double *bcoarse);
 int p4b_prolong_add(p4b_ctx *ctx, const p4b_grid *gfine, const double *xcoarse, double *xfine);
+/* b_c = P^T (b - A x): a COMPOSITION of p4b_stencil_residual and p4b_restrict over a scratch vector (32 N + 8 N_c bytes),
+ * kept as a convenience for callers; there is no fused kernel (DESIGN.md section 4 says why) and the multigrid cycle
+ * does not use this entry point */
 int p4b_residual_restrict(p4b_ctx *ctx, const p4b_grid *gfine, const double *b, const double *x, double *bcoarse);
 int p4b_lambda_max_jacobi(const p4b_grid *g, double *lam);
 

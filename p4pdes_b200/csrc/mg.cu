@@ -1261,7 +1261,7 @@ int p4b_prolong_add(p4b_ctx *c, const p4b_grid *gf, const double *xc, double *xf
 }
 
 int p4b_residual_restrict(p4b_ctx *c, const p4b_grid *gf, const double *b, const double *x, double *bc) {
-    // unfused composition (scratch vector from the async pool); the fused kernel replaces it inside Mg
+    // a composition over a scratch vector from the async pool (no fused kernel exists: DESIGN.md section 4)
     LevelDesc F;
     P4B_CHECK(make_desc(gf, &F));
     double *t = nullptr;
