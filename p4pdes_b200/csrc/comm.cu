@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(512) halo_push_kernel(const double *lo_src, do
 
 // sum nv (<= 3) doubles over all ranks; result overwrites vals on every rank
 __global__ void __launch_bounds__(64) allreduce_kernel(double *vals, int nv, int op_max, PeerTable peers, LocalSync *sync,
-                                                       HostPoll *hp, unsigned long long seq, int slot) {
+                                                       HostPoll *hp, unsigned long long seq, const double *extra) {
     const int r = threadIdx.x;
     const unsigned long long e = sync->red_epoch + 1;
     const int par = (int)(e & 1ull);
@@ -108,12 +108,13 @@ __global__ void __launch_bounds__(64) allreduce_kernel(double *vals, int nv, int
             s = op_max ? fmax(s, v) : s + v;
         }
         vals[r] = s;
-        if (hp) ((volatile double *)hp->v)[slot + r] = s;
+        if (hp) ((volatile double *)hp->v)[r] = s;
     }
     __syncthreads();
     if (r == 0) {
         sync->red_epoch = e;
-        if (hp && seq) {
+        if (hp) {
+            if (extra) ((volatile double *)hp->v)[nv] = extra[0];
             __threadfence_system();
             st_release_sys(&hp->seq, seq);
         }
@@ -121,10 +122,11 @@ __global__ void __launch_bounds__(64) allreduce_kernel(double *vals, int nv, int
 }
 
 __global__ void __launch_bounds__(64) publish_kernel(const double *vals, int nv, HostPoll *hp, unsigned long long seq,
-                                                     int slot) {
-    if ((int)threadIdx.x < nv) ((volatile double *)hp->v)[slot + threadIdx.x] = vals[threadIdx.x];
+                                                     const double *extra) {
+    if ((int)threadIdx.x < nv) ((volatile double *)hp->v)[threadIdx.x] = vals[threadIdx.x];
+    if (extra && (int)threadIdx.x == nv) ((volatile double *)hp->v)[nv] = extra[0];
     __syncthreads();
-    if (threadIdx.x == 0 && seq) {
+    if (threadIdx.x == 0) {
         __threadfence_system();
         st_release_sys(&hp->seq, seq);
     }
@@ -174,15 +176,15 @@ int launch_halo_push(cudaStream_t st, const double *lo_src, double *lo_dst, cons
     return 0;
 }
 int launch_allreduce(cudaStream_t st, double *vals, int nv, int op_max, const PeerTable &peers, LocalSync *sync,
-                     HostPoll *hp, unsigned long long seq, int slot) {
+                     HostPoll *hp, unsigned long long seq, const double *extra) {
     if (nv < 1 || nv > 3) return fail(62, "peer allreduce handles 1..3 values");
-    allreduce_kernel<<<1, 64, 0, st>>>(vals, nv, op_max, peers, sync, hp, seq, slot);
+    allreduce_kernel<<<1, 64, 0, st>>>(vals, nv, op_max, peers, sync, hp, seq, extra);
     P4B_LAUNCH_CHECK();
     return 0;
 }
-int launch_publish(cudaStream_t st, const double *vals, int nv, HostPoll *hp, unsigned long long seq, int slot) {
-    if (nv < 1 || slot < 0 || slot + nv > 64) return fail(62, "publish handles 1..64 values");
-    publish_kernel<<<1, 64, 0, st>>>(vals, nv, hp, seq, slot);
+int launch_publish(cudaStream_t st, const double *vals, int nv, HostPoll *hp, unsigned long long seq, const double *extra) {
+    if (nv < 1 || nv > 64 || (extra && nv > 63)) return fail(62, "publish handles 1..64 values");
+    publish_kernel<<<1, 64, 0, st>>>(vals, nv, hp, seq, extra);
     P4B_LAUNCH_CHECK();
     return 0;
 }

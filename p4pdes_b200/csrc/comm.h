@@ -236,11 +236,12 @@ int launch_halo_push(cudaStream_t st, const double *lo_src, double *lo_dst, cons
                      long long plane, unsigned long long *flag_prev, unsigned long long *flag_next,
                      const unsigned long long *my_flags, LocalSync *sync);
 // hp != nullptr: the result is also published to the host (HostPoll) with sequence number seq
-// (the values land in hp->v[slot .. slot + nv); seq = 0: values only, the sequence number is left alone)
+// (extra != nullptr: one more device scalar, already reduced, rides along into hp->v[nv] under the same sequence number)
 int launch_allreduce(cudaStream_t st, double *vals, int nv, int op_max, const PeerTable &peers, LocalSync *sync,
-                     HostPoll *hp = nullptr, unsigned long long seq = 0, int slot = 0);
-// vals[0..nv) -> hp->v[slot ..), then hp->seq = seq (one tiny kernel; slot + nv <= 64)
-int launch_publish(cudaStream_t st, const double *vals, int nv, HostPoll *hp, unsigned long long seq, int slot = 0);
+                     HostPoll *hp = nullptr, unsigned long long seq = 0, const double *extra = nullptr);
+// vals[0..nv) -> hp->v [, extra[0] -> hp->v[nv]], then hp->seq = seq (one tiny kernel; nv < 64)
+int launch_publish(cudaStream_t st, const double *vals, int nv, HostPoll *hp, unsigned long long seq,
+                   const double *extra = nullptr);
 int launch_barrier(cudaStream_t st, int all, const PeerTable &peers, LocalSync *sync);
 int launch_gather_push(cudaStream_t st, const double *src, long long n, long long off_doubles, const GatherTable &dst,
                        int rank, int nranks);

@@ -1586,18 +1586,21 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
     double h[2];
     P4B_CHECK(precond(S + 2 * q));
     // (z,z), (z,r): all-reduced and published to pinned host memory by one kernel; the host polls (no stream sync)
+    // (the iteration's (p, A p), already all-reduced in S[4], rides along as a third value: KSPSolve_CG's indefinite-matrix test)
+    double h3[3] = {0.0, 0.0, 1.0};
     auto reduce_fetch2 = [&](double *dots) -> int {
         const unsigned long long seq = ++c->poll_seq;
         {
             ProfScope ps(m, m->top, P4B_K_ALLREDUCE);
             if (c->nranks > 1 && c->peer) {
-                P4B_CHECK(launch_allreduce(st, dots, 2, 0, c->peers, c->sync, c->d_poll, seq));
+                P4B_CHECK(launch_allreduce(st, dots, 2, 0, c->peers, c->sync, c->d_poll, seq, S + 4));
             } else {
                 P4B_CHECK(ctx_allreduce(c, dots, 2));
-                P4B_CHECK(launch_publish(st, dots, 2, c->d_poll, seq));
+                P4B_CHECK(launch_publish(st, dots, 2, c->d_poll, seq, S + 4));
             }
         }
-        const int rc = poll_wait(c, seq, 2, h);
+        const int rc = poll_wait(c, seq, 3, h3);
+        h[0] = h3[0]; h[1] = h3[1];
         prof_break(m);
         return rc;
     };
@@ -1635,15 +1638,9 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
             wrote(m, m->w);
             P4B_CHECK(launch_stencil(st, T.d, op, red));
         }
-        {   // (p, A p): all-reduced; it also goes to the host (slot 2, read with the next poll) for KSPSolve_CG's
-            // indefinite-matrix test
+        {
             ProfScope ps(m, m->top, P4B_K_ALLREDUCE);
-            if (c->nranks > 1 && c->peer) {
-                P4B_CHECK(launch_allreduce(st, S + 4, 1, 0, c->peers, c->sync, c->d_poll, 0, 2));
-            } else {
-                P4B_CHECK(ctx_allreduce(c, S + 4, 1));
-                P4B_CHECK(launch_publish(st, S + 4, 1, c->d_poll, 0, 2));
-            }
+            P4B_CHECK(ctx_allreduce(c, S + 4, 1));
         }
         if (m->o.fuse) {
             ProfScope ps(m, m->top, P4B_K_R_UPDATE);
@@ -1661,7 +1658,7 @@ int p4b_cg_solve(p4b_mg *m, int pc_type, const double *b, double *x, double rtol
         dp = sqrt(h[0]);
         its++;
         if (R.nhist < P4B_MAX_HIST) R.hist[R.nhist++] = dp;
-        const double pw = c->h_poll->v[2];              // (p, A p) of this iteration (published before the poll returned)
+        const double pw = h3[2];                        // (p, A p) of this iteration
         // [PETSc] KSPSolve_CG's order of tests: indefinite matrix, NaN, convergence / divergence tolerance, indefinite PC
         if (pw <= 0.0) R.reason = P4B_DIVERGED_INDEFINITE_MAT;
         else if (!(dp == dp)) R.reason = P4B_DIVERGED_NAN;
