@@ -23,7 +23,7 @@ def test_fish_random_initial_iterate(ctx):
     base = "-fsh_dim 3 -da_refine 4 -pc_type mg -ksp_rtol 1e-12 -ksp_converged_reason"
     a = fish_main(base, ctx, keep_solution=True)
     b = fish_main(base + " -fsh_initial_type random", ctx, keep_solution=True)
-    assert b.fnorm0 > 10 * a.fnorm0                      # the random interior makes the first residual large
+    assert b.fnorm0 > 1.5 * a.fnorm0                     # the random interior makes the first residual larger
     assert float((a.u - b.u).abs().max()) < 1e-9         # ... and CG converges to the same discrete solution
     assert "%.3e" % a.errinf == "%.3e" % b.errinf
     # boundary values of g are on the boundary, the stream's first values just inside (natural ordering)
