@@ -469,6 +469,7 @@ static size_t da_n(DM dm) { return (size_t)dm->M[0] * dm->M[1] * dm->M[2] * (siz
 
 static PetscErrorCode vec_new(DM dm, Vec *v) {
     Vec x = (Vec)calloc(1, sizeof *x);
+    if (!x) SHIM_ERR(55, "out of host memory for a Vec");
     x->n = da_n(dm);
     x->dm = dm;
     x->h = (double *)calloc(x->n, sizeof(double));
@@ -1285,7 +1286,11 @@ static PetscErrorCode ksponly_solve_assembled(SNES snes, Vec u, Vec F, Vec Y, do
     /* CSR with sorted columns; the diagonal for Jacobi */
     int *rowptr = (int *)malloc(sizeof(int) * (n + 1)), *colind = (int *)malloc(sizeof(int) * n * W);
     double *vals = (double *)malloc(sizeof(double) * n * W);
-    if (!rowptr || !colind || !vals) SHIM_ERR(55, "out of host memory for the CSR copy");
+    if (!rowptr || !colind || !vals) {
+        free(rowptr); free(colind); free(vals);
+        MatDestroy(&J);
+        SHIM_ERR(55, "out of host memory for the CSR copy");
+    }
     double dmin = 1e300, dmax = -1e300;
     size_t nnz = 0, ndiag = 0;
     for (size_t r = 0; r < n; r++) {
@@ -1609,7 +1614,7 @@ PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
         PetscErrorCode rc = dm->jac(&info, au, J, J, dm->jacctx);
         PetscCall(DMDAVecRestoreArrayRead(&cd, ul, &au));
         if (l) vec_free(ul);
-        if (rc) return rc;
+        if (rc) { MatDestroy(&J); vec_free(F); vec_free(Y); return rc; }
         if (J->general || !J->have_diag || J->rows_set != (long long)da_n(&cd)) {
             char msg[640];
             snprintf(msg, sizeof msg,
@@ -1617,6 +1622,8 @@ PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
                      "\"stencilcuda\" represents (%s; %lld of %zu rows set); pass -mat_type sellcuda for the assembled device path",
                      l, J->general ? J->why : "incomplete", J->rows_set, da_n(&cd));
             MatDestroy(&J);
+            vec_free(F);
+            vec_free(Y);
             SHIM_ERR(56, msg);
         }
         coef[4 * l + 0] = J->diag;
