@@ -177,6 +177,16 @@ int p4b_prolong_add(p4b_ctx *ctx, const p4b_grid *gfine, const double *xcoarse, 
 int p4b_residual_restrict(p4b_ctx *ctx, const p4b_grid *gfine, const double *b, const double *x, double *bcoarse);
 int p4b_lambda_max_jacobi(const p4b_grid *g, double *lam);
 
+/* ---- reduced-space variational inequalities: what [PETSc] SNESVINEWTONRSLS needs beyond the Poisson kernels for
+ * c/ch12/obstacle.c (host logic in p4pdes_b200/obstacle.py) ----
+ *   p4b_vi_inactive_mask    mask_i = 0 where the lower bound is active (u_i <= lower_i + 1e-8 and F_i > 0: the rule of
+ *                           [PETSc] vi.c that obstacle.c:196-205 repeats), 1 elsewhere
+ *   p4b_vec_pointwise_mult  out = x .* y (restriction of vectors and of the matrix-free Jacobian to the inactive set)
+ *   p4b_vec_pointwise_max   out = max(x, y) (projection onto u >= psi: SNESVIProjectOntoBounds, the line search's path) */
+int p4b_vi_inactive_mask(p4b_ctx *ctx, size_t n, const double *u, const double *lower, const double *F, double *mask);
+int p4b_vec_pointwise_mult(p4b_ctx *ctx, size_t n, const double *x, const double *y, double *out);
+int p4b_vec_pointwise_max(p4b_ctx *ctx, size_t n, const double *x, const double *y, double *out);
+
 int p4b_vec_dot(p4b_ctx *ctx, size_t n, const double *x, const double *y, double *result_host);
 int p4b_vec_norm2(p4b_ctx *ctx, size_t n, const double *x, double *result_host);
 /* sum_i ((x_i - y_i) / (atol + rtol max(|x_i|, |y_i|)))^2: [PETSc] TSErrorWeightedNorm2 (TSAdapt's error estimate) */

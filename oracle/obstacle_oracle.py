@@ -1,0 +1,148 @@
+"""CPU restatement of c/ch12/obstacle.c solved by [PETSc] SNESVINEWTONRSLS.  TEST INFRASTRUCTURE ONLY.
+
+From the reference itself: psi, u_exact, the bounds (obstacle.c:16-47,236-255), the residual and Jacobian of
+c/ch6/poissonfunctions.c (Poisson2DFunctionLocal :37-66, f = 0, g = u_exact on the boundary; the fish oracle's) on
+(-2,2)^2, the active-set count and area (obstacle.c:187-219), the error report (:160-175).
+From [PETSc] (src/snes/impls/vi/rs/virs.c, vi.c; un-vendored): the reduced-space active-set Newton method --
+  project the initial iterate onto the bounds; F = F(u);
+  inactive set I = { i : not (u_i <= psi_i + 1e-8 and F_i > 0) }   (upper bound = +infinity);  ||F||_VI = ||F_I||_2
+  each iteration: solve J_II y_I = F_I (y = 0 on the active set), then a backtracking line search on ||F||_VI along
+  the PROJECTED path  w(lambda) = max(u - lambda y, psi)  (SNESLineSearchBT with the VI projection and norm).
+Pinned on c/ch12/output/obstacle.test1 (tests/test_obstacle_oracle.py): the three monitored norms, the error line and
+the active-area error; test2 / test4 share the error line.  The KSP counts of the goldens belong to ILU / ASM+LU on the
+reduced matrix and are reproduced only where the oracle has that preconditioner (test1: CG + ILU(0))."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from oracle import fish_oracle as fo
+
+AFREE, A_, B_ = 0.697965148223374, 0.680259411891719, 0.471519893402112
+
+
+def psi(x, y):
+    r = np.sqrt(x * x + y * y)
+    r0 = 0.9
+    psi0 = np.sqrt(1.0 - r0 * r0)
+    dpsi0 = -r0 / psi0
+    return np.where(r <= r0, np.sqrt(np.maximum(1.0 - r * r, 0.0)), psi0 + dpsi0 * (r - r0))
+
+
+def u_exact(x, y):
+    r = np.sqrt(x * x + y * y)
+    with np.errstate(divide="ignore"):
+        return np.where(r <= AFREE, psi(x, y), -A_ * np.log(np.maximum(r, 1e-300)) + B_)
+
+
+def grid_xy(m):
+    x = -2.0 + 4.0 * np.arange(m) / (m - 1)
+    return np.meshgrid(x, x)          # X[j, i] = x_i, Y[j, i] = y_j
+
+
+def residual(u, g):
+    """Poisson2DFunctionLocal with f = 0 on (-2,2)^2, hx = hy: scaled boundary rows, g substituted for boundary neighbours."""
+    m = u.shape[0]
+    F = 4.0 * (u - g)                  # boundary rows: scdiag (u - g), scx = scy = 1 for hx = hy
+    v = u.copy()
+    v[0, :], v[-1, :], v[:, 0], v[:, -1] = g[0, :], g[-1, :], g[:, 0], g[:, -1]
+    F[1:-1, 1:-1] = 4.0 * u[1:-1, 1:-1] - v[1:-1, :-2] - v[1:-1, 2:] - v[:-2, 1:-1] - v[2:, 1:-1]
+    return F
+
+
+def jacobian(m):
+    g = fo.Grid(2, (m, m, 1), (4.0, 4.0, 1.0))
+    return fo.jacobian(g)
+
+
+@dataclass
+class ObstacleResult:
+    m: int
+    its: int
+    fnorm: list
+    ksp_its: list
+    u: np.ndarray = field(repr=False, default=None)
+    err1: float = 0.0
+    errinf: float = 0.0
+    area_err: float = 0.0
+    reason: str = ""
+
+
+def vi_norm(u, F, lo):
+    inact = ~((u <= lo + 1.0e-8) & (F > 0.0))
+    return float(np.sqrt(np.sum(F[inact] ** 2))), inact
+
+
+def rsls(m, u0=None, snes_rtol=1.0e-8, ksp_rtol=1.0e-5, pc="ilu", max_it=50, snes_stol=1.0e-8, snes_atol=1.0e-50):
+    X, Y = grid_xy(m)
+    lo, g = psi(X, Y), u_exact(X, Y)
+    J = jacobian(m)
+    u = np.maximum(np.zeros((m, m)) if u0 is None else u0, lo)            # SNESVIProjectOntoBounds
+    F = residual(u, g)
+    fnorm, inact = vi_norm(u, F, lo)
+    norms, ksp_its = [fnorm], []
+    f0 = fnorm
+    its, reason = 0, "DIVERGED_MAX_IT"
+    if fnorm < snes_atol:
+        reason = "CONVERGED_FNORM_ABS"
+    while reason == "DIVERGED_MAX_IT" and its < max_it:
+        idx = np.flatnonzero(inact.ravel())
+        Jr = sp.csr_matrix(J[idx][:, idx])
+        rhs = F.ravel()[idx]
+        if pc == "exact":
+            y_i, k = spla.spsolve(sp.csc_matrix(Jr), rhs), 1
+        else:
+            M = fo.ILU0PC(Jr).apply if pc == "ilu" else (lambda r: r.copy())
+            y_i, k, _ = fo.cg(Jr, rhs, M, rtol=ksp_rtol)
+        ksp_its.append(k)
+        y = np.zeros(m * m)
+        y[idx] = y_i
+        y = y.reshape(m, m)
+        # [PETSc] SNESLineSearchApply_BT with the VI projection: full step first, then quadratic / cubic backtracking
+        lam, ok = 1.0, False
+        gprev, lamprev = None, None
+        fy = float(np.sum(F[inact] * (J @ y.ravel()).reshape(m, m)[inact]))      # initial slope (F, J y) on the inactive set
+        slope = -fy if fy > 0 else -fnorm * fnorm
+        for _ in range(40):
+            w = np.maximum(u - lam * y, lo)
+            Fw = residual(w, g)
+            gn, inact_w = vi_norm(w, Fw, lo)
+            if 0.5 * gn * gn <= 0.5 * fnorm * fnorm + 1.0e-4 * lam * slope:
+                ok = True
+                break
+            if lamprev is None:
+                lamnew = -slope / (gn * gn - fnorm * fnorm - 2.0 * slope)
+            else:
+                t1 = 0.5 * (gn * gn - fnorm * fnorm) - lam * slope
+                t2 = 0.5 * (gprev * gprev - fnorm * fnorm) - lamprev * slope
+                a = (t1 / (lam * lam) - t2 / (lamprev * lamprev)) / (lam - lamprev)
+                b = (-lamprev * t1 / (lam * lam) + lam * t2 / (lamprev * lamprev)) / (lam - lamprev)
+                d = b * b - 3.0 * a * slope
+                d = max(d, 0.0)
+                lamnew = -slope / (2.0 * b) if a == 0.0 else (-b + np.sqrt(d)) / (3.0 * a)
+            lamnew = min(max(lamnew, 0.1 * lam), 0.5 * lam)
+            lamprev, gprev, lam = lam, gn, lamnew
+        if not ok:
+            reason = "DIVERGED_LINE_SEARCH"
+            break
+        snorm = float(np.linalg.norm(w - u))
+        xnorm = float(np.linalg.norm(w))
+        u, F, fnorm, inact = w, Fw, gn, inact_w
+        its += 1
+        norms.append(fnorm)
+        if fnorm < snes_atol:
+            reason = "CONVERGED_FNORM_ABS"
+        elif fnorm <= snes_rtol * f0:
+            reason = "CONVERGED_FNORM_RELATIVE"
+        elif snorm < snes_stol * xnorm:
+            reason = "CONVERGED_SNORM_RELATIVE"
+    # obstacle.c:160-175, 187-219
+    act = int(np.sum((u <= lo + 1.0e-8) & (F > 0.0)))
+    dx = 4.0 / (m - 1)
+    exactarea = np.pi * AFREE * AFREE
+    e = u - g
+    return ObstacleResult(m, its, norms, ksp_its, u, float(np.sum(np.abs(e))) / (m * m), float(np.max(np.abs(e))),
+                          abs(dx * dx * act - exactarea) / exactarea, reason)

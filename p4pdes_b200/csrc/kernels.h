@@ -69,6 +69,10 @@ int launch_scale_copy(cudaStream_t st, long long n, double a, const double *x, d
 int launch_axpby_out(cudaStream_t st, long long n, double a, const double *x, double b, const double *y,
                      double *out);                                                              // out = a x + b y
 
+// reduced-space VI helpers: inactive-set mask, pointwise product (op 0) / maximum (op 1)
+int launch_vi_mask(cudaStream_t st, long long n, const double *u, const double *lo, const double *F, double *mask);
+int launch_pointwise(cudaStream_t st, long long n, int op, const double *x, const double *y, double *out);
+
 // dense coarse solve x = Ainv b   (n x n, row-major Ainv)
 int launch_dense_matvec(cudaStream_t st, int n, const double *Ainv, const double *b, double *x);
 

@@ -1860,6 +1860,15 @@ int p4b_inject2d(p4b_ctx *c, int cmx, int cmy, const double *uf, double *uc) {
 int p4b_vec_axpby(p4b_ctx *c, size_t n, double a, const double *x, double b, const double *y, double *out) {
     return launch_axpby_out(c->stream, (long long)n, a, x, b, y, out);
 }
+int p4b_vi_inactive_mask(p4b_ctx *c, size_t n, const double *u, const double *lower, const double *F, double *mask) {
+    return launch_vi_mask(c->stream, (long long)n, u, lower, F, mask);
+}
+int p4b_vec_pointwise_mult(p4b_ctx *c, size_t n, const double *x, const double *y, double *out) {
+    return launch_pointwise(c->stream, (long long)n, 0, x, y, out);
+}
+int p4b_vec_pointwise_max(p4b_ctx *c, size_t n, const double *x, const double *y, double *out) {
+    return launch_pointwise(c->stream, (long long)n, 1, x, y, out);
+}
 int p4b_vec_copy(p4b_ctx *c, size_t n, const double *x, double *y) {
     P4B_CUDA(cudaMemcpyAsync(y, x, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
     return 0;

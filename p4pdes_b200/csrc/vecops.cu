@@ -233,6 +233,37 @@ __global__ void __launch_bounds__(VT) axpby_kernel(long long n, double a, const 
     }
 }
 
+// ---- reduced-space variational inequalities ([PETSc] SNESVINEWTONRSLS under c/ch12/obstacle.c) --------
+// mask_i = 0 where the lower bound is active (u_i <= lo_i + 1e-8 and F_i > 0, [PETSc] vi.c / obstacle.c:196-205), else 1
+__global__ void __launch_bounds__(VT) vi_mask_kernel(long long n, const double *__restrict__ u, const double *__restrict__ lo,
+                                                      const double *__restrict__ F, double *__restrict__ mask) {
+    const long long stride = (long long)gridDim.x * VT;
+    for (long long i = (long long)blockIdx.x * VT + threadIdx.x; i < n; i += stride)
+        mask[i] = (u[i] <= lo[i] + 1.0e-8 && F[i] > 0.0) ? 0.0 : 1.0;
+}
+// out = x .* y   (op 0)     out = max(x, y)   (op 1: projection onto the bound)
+__global__ void __launch_bounds__(VT) pointwise_kernel(long long n, int op, const double *x, const double *y, double *out) {
+    const long long stride = (long long)gridDim.x * VT;
+    for (long long i = (long long)blockIdx.x * VT + threadIdx.x; i < n; i += stride)
+        out[i] = op ? fmax(x[i], y[i]) : x[i] * y[i];
+}
+int launch_vi_mask(cudaStream_t st, long long n, const double *u, const double *lo, const double *F, double *mask) {
+    if (n <= 0) return 0;
+    long long nb = (n + VT - 1) / VT;
+    if (nb > STREAM_BLOCKS * 4) nb = STREAM_BLOCKS * 4;
+    vi_mask_kernel<<<(unsigned)nb, VT, 0, st>>>(n, u, lo, F, mask);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+int launch_pointwise(cudaStream_t st, long long n, int op, const double *x, const double *y, double *out) {
+    if (n <= 0) return 0;
+    long long nb = (n + VT - 1) / VT;
+    if (nb > STREAM_BLOCKS * 4) nb = STREAM_BLOCKS * 4;
+    pointwise_kernel<<<(unsigned)nb, VT, 0, st>>>(n, op, x, y, out);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+
 #define RED_CHECK(nb)                                                                                   \
     if ((int)(nb) > red.max_blocks) return fail(63, "reduction: %u blocks exceed scratch %d", (unsigned)(nb), red.max_blocks)
 

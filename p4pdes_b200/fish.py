@@ -129,6 +129,15 @@ class Context:
     def set(self, a, y):
         L.check(self.lib.p4b_vec_set(self.h, y.numel(), a, y.data_ptr()))
 
+    def vi_inactive_mask(self, u, lower, F, mask):
+        L.check(self.lib.p4b_vi_inactive_mask(self.h, u.numel(), u.data_ptr(), lower.data_ptr(), F.data_ptr(), mask.data_ptr()))
+
+    def pointwise_mult(self, x, y, out):
+        L.check(self.lib.p4b_vec_pointwise_mult(self.h, x.numel(), x.data_ptr(), y.data_ptr(), out.data_ptr()))
+
+    def pointwise_max(self, x, y, out):
+        L.check(self.lib.p4b_vec_pointwise_max(self.h, x.numel(), x.data_ptr(), y.data_ptr(), out.data_ptr()))
+
     def to_host(self, t):
         self.sync()
         return t.detach().cpu().numpy()

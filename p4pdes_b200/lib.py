@@ -185,6 +185,9 @@ _SIGS = {
     "p4b_minimal_function": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, _D, _D]),
     "p4b_pattern_initial_state": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D]),
     "p4b_pattern_initial_state_noisy": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, C.c_double, _D]),
+    "p4b_vi_inactive_mask": (C.c_int, [_P, C.c_size_t, _D, _D, _D, _D]),
+    "p4b_vec_pointwise_mult": (C.c_int, [_P, C.c_size_t, _D, _D, _D]),
+    "p4b_vec_pointwise_max": (C.c_int, [_P, C.c_size_t, _D, _D, _D]),
     "p4b_ctx_create_own_stream": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "p4b_bratu_default_opts": (C.c_int, [C.POINTER(BratuOpts)]),
     "p4b_bratu_function": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int, _D, _D, _D]),

@@ -97,7 +97,38 @@ class FakeOps:
 
     def prolong_add(self, grid, xc, xf):
         self._count("prolong_add")
+        if hasattr(grid, "mx"):
+            grid = (grid.mx, grid.my)
         xf.a += self._P(grid) @ xc.a
+
+    # fish.c kernels on an L.Grid (obstacle.py drives them): restated from the fish oracle
+    @staticmethod
+    def _fo_grid(g):
+        return fo.Grid(g.dim, (g.mx, g.my, g.mz), (g.Lx, g.Ly, g.Lz))
+
+    def stencil_apply(self, g, u, y):
+        y.a[:] = fo.jacobian(self._fo_grid(g), (g.cx, g.cy, g.cz)) @ u.a
+
+    def poisson_function(self, g, u, f, gb, F):
+        # Poisson2DFunctionLocal with node-sampled f and g (c/ch6/poissonfunctions.c:37-66); square 2-D grids, hx = hy
+        m = g.mx
+        uu, gg, ff = u.a.reshape(m, m), gb.a.reshape(m, m), f.a.reshape(m, m)
+        h = g.Lx / (m - 1)
+        out = 4.0 * (uu - gg)
+        v = uu.copy()
+        v[0, :], v[-1, :], v[:, 0], v[:, -1] = gg[0, :], gg[-1, :], gg[:, 0], gg[:, -1]
+        out[1:-1, 1:-1] = (4.0 * uu[1:-1, 1:-1] - v[1:-1, :-2] - v[1:-1, 2:] - v[:-2, 1:-1] - v[2:, 1:-1]
+                           - h * h * ff[1:-1, 1:-1])
+        F.a[:] = out.ravel()
+
+    def vi_inactive_mask(self, u, lower, F, mask):
+        mask.a[:] = np.where((u.a <= lower.a + 1.0e-8) & (F.a > 0.0), 0.0, 1.0)
+
+    def pointwise_mult(self, x, y, out):
+        out.a[:] = x.a * y.a
+
+    def pointwise_max(self, x, y, out):
+        out.a[:] = np.maximum(x.a, y.a)
 
     def inject2d(self, cmx, cmy, uf, uc):
         uc.a[:] = uf.a.reshape(2 * cmy - 1, 2 * cmx - 1)[::2, ::2].ravel()

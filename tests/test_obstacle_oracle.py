@@ -1,0 +1,52 @@
+"""oracle/obstacle_oracle.py ([PETSc] SNESVINEWTONRSLS restated) against the reference's goldens c/ch12/output/obstacle.test1-4
+(c/ch12/makefile:16-27), and the product's host logic (p4pdes_b200/obstacle.py) over the NumPy stand-in of the device
+operations against the same lines."""
+import numpy as np
+
+from oracle import obstacle_oracle as oo
+from p4pdes_b200.obstacle import obstacle_main
+from tests.fake_ops import FakeOps
+
+TEST1 = ["  0 SNES Function norm 3.86571", "  1 SNES Function norm 1.3323", "  2 SNES Function norm < 1.e-11",
+         "done on 9 x 9 grid ... CONVERGED_FNORM_RELATIVE, SNES iters = 2, last KSP iters = 11",
+         "errors: av |u-uexact| = 3.076e-03, |u-uexact|_inf = 1.334e-02, active area error = 47.016%"]
+TEST3_ERRORS = "errors: av |u-uexact| = 2.707e-03, |u-uexact|_inf = 1.428e-02, active area error = 18.430%"
+
+
+def short(x):
+    return "%g" % x if x > 1e-9 else ("%5.3e" % x if x > 1e-11 else "< 1.e-11")
+
+
+def test_oracle_reproduces_obstacle_test1_completely():
+    # -da_refine 2 -snes_monitor_short -ksp_rtol 1.0e-12 -snes_rtol 1.0e-10 -ksp_converged_reason, default PC = ILU(0), CG
+    r = oo.rsls(9, snes_rtol=1e-10, ksp_rtol=1e-12, pc="ilu")
+    assert ["  %d SNES Function norm %s" % (i, short(v)) for i, v in enumerate(r.fnorm)] == TEST1[:3]
+    assert r.ksp_its == [11, 11] and r.its == 2 and r.reason == "CONVERGED_FNORM_RELATIVE"          # both "iterations 11" lines
+    assert ("errors: av |u-uexact| = %.3e, |u-uexact|_inf = %.3e, active area error = %.3f%%"
+            % (r.err1, r.errinf, 100 * r.area_err)) == TEST1[4]
+
+
+def test_oracle_error_lines_of_the_other_goldens():
+    # obstacle.test2 (GMRES + ASM/LU on 4 ranks) and test4 (vinewtonssls) end on the same discrete solution as test1
+    r = oo.rsls(9, pc="exact")
+    assert ("%.3e %.3e %.3f" % (r.err1, r.errinf, 100 * r.area_err)) == "3.076e-03 1.334e-02 47.016"
+    # obstacle.test3: grid sequence to 17 x 17; the converged state does not depend on the path
+    r = oo.rsls(17, pc="exact", snes_rtol=1e-10)
+    assert ("errors: av |u-uexact| = %.3e, |u-uexact|_inf = %.3e, active area error = %.3f%%"
+            % (r.err1, r.errinf, 100 * r.area_err)) == TEST3_ERRORS
+
+
+def test_host_logic_prints_the_goldens_over_the_stand_in():
+    rep = obstacle_main("-da_refine 2 -snes_monitor_short -ksp_rtol 1.0e-12 -snes_rtol 1.0e-10 -pc_type none", FakeOps())
+    assert rep.lines[:3] == TEST1[:3] and rep.lines[-1] == TEST1[4]
+    assert rep.lines[3].startswith("done on 9 x 9 grid ... CONVERGED_FNORM_RELATIVE, SNES iters = 2, last KSP iters = ")
+    rep = obstacle_main("-snes_grid_sequence 3 -snes_converged_reason -pc_type jacobi", FakeOps())
+    assert rep.lines[-1] == TEST3_ERRORS and rep.lines[-2].startswith("done on 17 x 17 grid ... CONVERGED_FNORM_RELATIVE")
+    assert [l.count("Nonlinear solve converged") for l in rep.lines[:4]] == [1, 1, 1, 1]
+    assert [len(l) - len(l.lstrip()) for l in rep.lines[:4]] == [8, 6, 4, 2]               # PETSc's grid-sequence indentation
+    # same states as the oracle with the same (unpreconditioned CG) solves
+    want = oo.rsls(33, pc="none", ksp_rtol=1e-10)
+    got = obstacle_main("-da_refine 4 -pc_type none -ksp_rtol 1e-10", FakeOps(), keep_solution=True)
+    assert got.its == want.its and got.ksp_its == want.ksp_its
+    np.testing.assert_allclose(got.fnorm, want.fnorm, rtol=1e-9, atol=1e-14)
+    assert np.max(np.abs(got.u.a.reshape(33, 33) - want.u)) < 1e-12
