@@ -58,10 +58,12 @@ def test_device_equals_the_oracle(ctx, refine, pc):
     assert abs(got.area_err - want.area_err) < 1e-12 and abs(got.errinf - want.errinf) < 1e-10
 
 
-def test_larger_grid_converges_and_the_free_boundary_sharpens(ctx):
+def test_grid_sequence_to_larger_grids(ctx):
+    """From u = 0 the active set moves about one cell per Newton step, so fine grids are reached the reference's way, by
+    -snes_grid_sequence (c/ch12/makefile:23): a few steps per grid, errors and the free boundary improve with h."""
     errs = []
-    for refine in (6, 7, 8):                              # 129^2 .. 513^2
-        rep = obstacle_main("-da_refine %d -pc_type jacobi" % refine, ctx)
-        assert rep.reason.startswith("CONVERGED")
+    for seq in (5, 6, 7):                                 # 65^2, 129^2, 257^2 from the 3 x 3 DMDA
+        rep = obstacle_main("-snes_grid_sequence %d -snes_converged_reason -pc_type jacobi" % seq, ctx)
+        assert rep.reason.startswith("CONVERGED") and rep.its <= 6 and rep.m == 2 ** (seq + 1) + 1
         errs.append((rep.errinf, rep.area_err))
     assert errs[2][0] < errs[0][0] and errs[2][1] < errs[0][1]
