@@ -279,6 +279,10 @@ int p4b_pattern_ijacobian_mult(p4b_ctx *ctx, int mx, int my, double L, double Du
  *   p4b_minimal_jacobian_fd  [PETSc] SNESComputeJacobianDefaultColor on c/ch7/minimal.c:210-282 (-snes_fd_color):
  *                            9 colours (DMDA BOX stencil), MatFDColoring's default "wp" differencing (one step
  *                            h = sqrt(eps) sqrt(1 + ||u||_2) for every column); F0 = F(u) already computed
+ *   p4b_poisson_stencil9     the matrix c/ch6/poissonfunctions.c:152-193 (Poisson2DJacobianLocal) inserts on an
+ *                            Lx x Ly rectangle, in the same layout: what c/ch7/minimal.c:142-145 registers as its
+ *                            (approximate) Jacobian -- Newton's matrix without -snes_fd_color / -snes_mf_operator,
+ *                            the preconditioner's under -snes_mf_operator
  *   p4b_stencil9_apply       [PETSc] MatMult on that matrix
  *   p4b_stencil9_lin         [PETSc] KSPSolve_Chebyshev/Richardson step + PCApply_Jacobi on it:
  *                            out = ca*pm1 + cb*u + cg*B(b - A u), B = diag(A)^-1 (jacobi != 0) or I
@@ -287,6 +291,7 @@ int p4b_pattern_ijacobian_mult(p4b_ctx *ctx, int mx, int my, double L, double Du
  * Matrix layout "stencil9": 9*mx*my doubles, vals[s*mx*my + j*mx + i] = dF(i,j)/du(i+di, j+dj), s = 3(dj+1) + (di+1). */
 int p4b_minimal_jacobian_fd(p4b_ctx *ctx, int mx, int my, double q, const double *u, const double *g, const double *F0,
                             double *vals9);
+int p4b_poisson_stencil9(p4b_ctx *ctx, int mx, int my, double Lx, double Ly, double cx, double cy, double *vals9);
 int p4b_stencil9_apply(p4b_ctx *ctx, int mx, int my, const double *vals9, const double *x, double *y);
 int p4b_stencil9_lin(p4b_ctx *ctx, int mx, int my, const double *vals9, const double *u, const double *b,
                      const double *pm1, double ca, double cb, double cg, int jacobi, double *out);
@@ -336,7 +341,10 @@ typedef struct {
     int snes_monitor;            /* 0 off, 1 -snes_monitor, 2 -snes_monitor_short */
     int snes_converged_reason, ksp_converged_reason;
     int mf_operator;             /* -snes_mf_operator: J v by differencing the residual ([PETSc] MatMFFD "wp"); the
-                                    FD-coloured Jacobian then only builds the preconditioner */
+                                    assembled matrix then only builds the preconditioner */
+    int jacobian;                /* the assembled matrix: 0 = FD-coloured Jacobian of the residual (-snes_fd_color);
+                                    1 = what c/ch7/minimal.c:142-145 registers, Poisson2DJacobianLocal ("ONLY APPROXIMATE"):
+                                    PETSc's choice when -snes_fd_color is absent, with or without -snes_mf_operator */
 } p4b_minimal_opts;
 typedef struct {
     int mx, my, its, reason, nksp;   /* reason: 2 FNORM_ABS, 3 FNORM_RELATIVE, 4 SNORM_RELATIVE, < 0 diverged ([PETSc] numbering) */

@@ -266,7 +266,11 @@ def newton(F, u0, make_pc, jac=None, ksp="gmres", snes_rtol=1.0e-8, snes_stol=1.
         solver = gmres if ksp == "gmres" else fo.cg
         y, kits, _ = solver(A, f.ravel(), M, rtol=ksp_rtol)
         res.ksp_its.append(kits)
-        xnew, fnew, fnormnew, lam = linesearch_bt(Ff, u.ravel(), f.ravel(), fnorm, y, A @ y)
+        try:
+            xnew, fnew, fnormnew, lam = linesearch_bt(Ff, u.ravel(), f.ravel(), fnorm, y, A @ y)
+        except RuntimeError:                   # [PETSc] SNES_DIVERGED_LINE_SEARCH: the solve stops at the current iterate
+            res.reason = "DIVERGED_LINE_SEARCH"
+            return res
         res.lambdas.append(lam)
         snorm = float(np.linalg.norm(xnew - u.ravel()))
         xnorm = float(np.linalg.norm(xnew))
@@ -312,10 +316,12 @@ class MinimalResult:
 
 def minimal(mx=3, my=3, refine=0, grid_sequence=0, problem="catenoid", q=-0.5, catenoid_c=1.1, tent_H=1.0,
             pc="ilu", ksp="gmres", mg_levels=0, smooth_its=2, snes_rtol=1.0e-8, ksp_rtol=1.0e-5, mf_operator=False,
-            monitor=None):
+            monitor=None, poisson_jacobian=False, max_it=50):
     """minimal.c:main with -da_grid_x mx -da_grid_y my -da_refine refine -snes_grid_sequence grid_sequence -snes_fd_color.
     pc: "ilu" (PETSc's default on one rank), "none", "mg" (Chebyshev/Jacobi PCMG, levels down to the base grid unless
-    mg_levels)."""
+    mg_levels).  poisson_jacobian: neither -snes_fd_color nor -snes_mf_operator -- Newton's matrix is the one minimal.c
+    registers (minimal.c:142-145), Poisson2DJacobianLocal on the unit square (poissonfunctions.c:147-190), and "mg" is
+    PCMG rediscretising THAT operator on every level (Chebyshev targets from the Gershgorin bound, as for the FD matrices)."""
     base = (my, mx)                                    # the -da_grid DMDA: the coarsest grid PCMG coarsens down to
     for _ in range(refine):
         mx, my = 2 * mx - 1, 2 * my - 1
@@ -355,6 +361,9 @@ def minimal(mx=3, my=3, refine=0, grid_sequence=0, problem="catenoid", q=-0.5, c
                     return lambda r: inv @ r
                 mats = [J]
                 for s, uu in zip(shapes[1:], us[1:]):
+                    if poisson_jacobian:                 # [PETSc] PCMG calls the registered callback on the coarsened DMs
+                        mats.append(fo.jacobian(fo.Grid(2, (s[1], s[0], 1))))
+                        continue
                     _, Fl = problem_on(s[0], s[1])
                     mats.append(fd_jacobian(Fl, uu))
                 # AssembledMG wants interpolation shapes coarse -> finer for each finer level: shapes[1:], finest first
@@ -362,7 +371,9 @@ def minimal(mx=3, my=3, refine=0, grid_sequence=0, problem="catenoid", q=-0.5, c
                 return mg.apply
             raise ValueError(pc)
 
-        r = newton(F, u, make_pc, ksp=ksp, snes_rtol=snes_rtol, ksp_rtol=ksp_rtol, mf_operator=mf_operator,
+        jac = (lambda w, shape=shape: fo.jacobian(fo.Grid(2, (shape[1], shape[0], 1)))) if poisson_jacobian else None
+        r = newton(F, u, make_pc, jac=jac, ksp=ksp, snes_rtol=snes_rtol, ksp_rtol=ksp_rtol, mf_operator=mf_operator,
+                   max_it=max_it,
                    monitor=(lambda it, w, st=stage: monitor(st, it, w)) if monitor else None)
         stages.append(r)
         u = r.u

@@ -101,6 +101,23 @@ struct HostOps {
     // column, h = sqrt(DBL_EPSILON) sqrt(1 + ||u||_2) (pinned by minimal.test1, oracle/minimal_solver_oracle.py);
     // vals in the stencil9 layout
     double fd_step(size_t n, const double *u) { return 1.4901161193847656e-08 * sqrt(1.0 + norm2(n, u)); }
+    // the rows c/ch6/poissonfunctions.c:152-193 inserts on the unit square with cx = cy = 1 (what c/ch7/minimal.c:142-145
+    // registers as its Jacobian), stencil9 layout
+    void poisson_stencil9(int mx, int my, double *vals) {
+        const int N = mx * my;
+        const double hx = 1.0 / (mx - 1), hy = 1.0 / (my - 1), scx = hy / hx, scy = hx / hy;
+        memset(vals, 0, sizeof(double) * 9 * (size_t)N);
+        for (int j = 0; j < my; j++)
+            for (int i = 0; i < mx; i++) {
+                const int n = j * mx + i;
+                vals[(size_t)4 * N + n] = 2.0 * (scx + scy);
+                if (i == 0 || i == mx - 1 || j == 0 || j == my - 1) continue;
+                if (i - 1 > 0) vals[(size_t)3 * N + n] = -scx;
+                if (i + 1 < mx - 1) vals[(size_t)5 * N + n] = -scx;
+                if (j - 1 > 0) vals[(size_t)1 * N + n] = -scy;
+                if (j + 1 < my - 1) vals[(size_t)7 * N + n] = -scy;
+            }
+    }
     void minimal_jacobian_fd(int mx, int my, double q, const double *u, const double *g, const double *F0, double *vals) {
         const int N = mx * my;
         std::vector<double> up(N), Fp(N);

@@ -78,7 +78,7 @@ int main(int argc, char **argv) {
     MinimalOpts o;
     default_opts(&o);
     const char *cb_lib = nullptr;
-    bool cgs = false;
+    bool cgs = false, fd_color = false, mf_poisson = false;
     for (int i = 1; i < argc; i++) {
         if (std::string(argv[i]) == "-callback" && i + 1 < argc) { cb_lib = argv[i + 1]; for (int k = i; k + 2 < argc; k++) argv[k] = argv[k + 2]; argc -= 2; break; }
     }
@@ -96,12 +96,16 @@ int main(int argc, char **argv) {
         else if (a == "-ksp_type") o.ksp_type = std::string(next()) == "cg" ? KSP_CG : KSP_GMRES;
         else if (a == "-pc_type") o.pc_type = std::string(next()) == "mg" ? PC_MG : PC_NONE;
         else if (a == "-pc_mg_levels") o.mg_levels = atoi(next());
-        else if (a == "-snes_fd_color") { }
+        else if (a == "-snes_fd_color") fd_color = true;
         else if (a == "-snes_mf_operator") o.mf_operator = 1;
+        else if (a == "-p4b_mf_pmat") mf_poisson = std::string(next()) == "poisson";
+        else if (a == "-snes_max_it") o.snes_max_it = atoi(next());
         else if (a == "-gmres_cgs") cgs = true;
         else if (a == "-monitor") { o.snes_monitor = 2; o.snes_converged_reason = 1; o.ksp_converged_reason = 1; }
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
+    // the matrix: FD-coloured, or the Poisson one minimal.c registers (no -snes_fd_color; under -snes_mf_operator on request)
+    o.jacobian = (!fd_color && !o.mf_operator) || (o.mf_operator && mf_poisson) ? 1 : 0;
     MinimalResult R;
     double *u = nullptr;
     Printer pr{print_line, nullptr};

@@ -84,6 +84,36 @@ int fd_jacobian_minimal(cudaStream_t st, int mx, int my, double q, double unorm,
     return 0;
 }
 
+// The matrix Poisson2DJacobianLocal inserts (c/ch6/poissonfunctions.c:152-193), in the stencil9 layout: minimal.c registers
+// it as its Jacobian callback (c/ch7/minimal.c:142-145, "ONLY APPROXIMATE"), so it is Newton's matrix when neither
+// -snes_fd_color nor -snes_mf_operator is given and the preconditioner's matrix under -snes_mf_operator.  Diagonal
+// 2 (scx + scy) on every row, -scx / -scy to INTERIOR neighbours of interior rows only (boundary columns eliminated),
+// scx = cx hy/hx, scy = cy hx/hy; the four corner planes are zero.
+__global__ void __launch_bounds__(256) poisson_stencil9_kernel(int mx, int my, double scx, double scy,
+                                                                double *__restrict__ vals) {
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    const int N = mx * my;
+    if (n >= N) return;
+    const int j = n / mx, i = n - j * mx;
+    const bool in = i > 0 && i < mx - 1 && j > 0 && j < my - 1;
+    double v[9] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    v[4] = 2.0 * (scx + scy);
+    if (in) {
+        if (i - 1 > 0) v[3] = -scx;
+        if (i + 1 < mx - 1) v[5] = -scx;
+        if (j - 1 > 0) v[1] = -scy;
+        if (j + 1 < my - 1) v[7] = -scy;
+    }
+#pragma unroll
+    for (int s = 0; s < 9; s++) vals[(size_t)s * N + n] = v[s];
+}
+int launch_poisson_stencil9(cudaStream_t st, int mx, int my, double Lx, double Ly, double cx, double cy, double *vals) {
+    const double hx = Lx / (mx - 1), hy = Ly / (my - 1);
+    poisson_stencil9_kernel<<<(unsigned)((mx * my + 255) / 256), 256, 0, st>>>(mx, my, cx * hy / hx, cy * hx / hy, vals);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+
 // MODE 0: out = A u          MODE 1: out = ca*pm1 + cb*u + cg*B(b - A u), B = 1/diag when jacobi else 1
 // (pm1 may be null (ca ignored) and may alias out; b may be null (treated as zero))
 template <int MODE>

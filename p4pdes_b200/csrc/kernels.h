@@ -115,6 +115,7 @@ int launch_pattern_jac(cudaStream_t st, int mode, int mx, int my, double Cu, dou
                        double cb, double cg, int jacobi, double *out, int ywrap = 1);
 int launch_pattern_transfer(cudaStream_t st, int mode, int Mx, int My, const double *src, double *dst, int ywrap = 1);
 int launch_stencil9_rowratio(cudaStream_t st, int mx, int my, const double *vals, double *out);
+int launch_poisson_stencil9(cudaStream_t st, int mx, int my, double Lx, double Ly, double cx, double cy, double *vals);
 int launch_inject2d(cudaStream_t st, int cmx, int cmy, int fmx, const double *uf, double *uc);
 int launch_stencil9_lin(cudaStream_t st, int mx, int my, const double *vals, const double *u, const double *b,
                         const double *pm1, double ca, double cb, double cg, int jacobi, double *out);

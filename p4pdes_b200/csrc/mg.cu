@@ -1840,6 +1840,10 @@ int p4b_minimal_jacobian_fd(p4b_ctx *c, int mx, int my, double q, const double *
     cudaFreeAsync(tmp, c->stream);
     return rc;
 }
+int p4b_poisson_stencil9(p4b_ctx *c, int mx, int my, double Lx, double Ly, double cx, double cy, double *vals9) {
+    if (mx < 3 || my < 3) return fail(60, "Poisson matrix: grid must be at least 3 x 3");
+    return launch_poisson_stencil9(c->stream, mx, my, Lx, Ly, cx, cy, vals9);
+}
 int p4b_stencil9_apply(p4b_ctx *c, int mx, int my, const double *vals9, const double *x, double *y) {
     return launch_stencil9_apply(c->stream, mx, my, vals9, x, y);
 }

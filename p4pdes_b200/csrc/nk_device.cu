@@ -66,6 +66,8 @@ struct DeviceOps {
     void set(size_t n, double a, double *y) { chk(p4b_vec_set(c, n, a, y)); }
     void minimal_sample(int mx, int my, int problem, double H, double cc, double *g) { chk(p4b_minimal_sample(c, mx, my, problem, H, cc, g)); }
     void minimal_function(int mx, int my, double q, const double *u, const double *g, double *F) { chk(p4b_minimal_function(c, mx, my, q, u, g, F)); }
+    // the matrix minimal.c registers (Poisson2DJacobianLocal on the unit square, cx = cy = 1: minimal.c:77-78,136,142-145)
+    void poisson_stencil9(int mx, int my, double *vals) { chk(p4b_poisson_stencil9(c, mx, my, 1.0, 1.0, 1.0, 1.0, vals)); }
     void minimal_jacobian_fd(int mx, int my, double q, const double *u, const double *g, const double *F0, double *vals) {
         chk(p4b_minimal_jacobian_fd(c, mx, my, q, u, g, F0, vals));
     }

@@ -51,6 +51,10 @@ struct MinimalOpts {
     int snes_converged_reason, ksp_converged_reason;
     int mf_operator;             // -snes_mf_operator: J v by differencing the residual ([PETSc] MatMFFD "wp"); the assembled
                                  // (FD-coloured) Jacobian is the preconditioner's matrix only
+    int jacobian;                // which matrix is assembled: 0 the FD-coloured Jacobian of the residual (-snes_fd_color),
+                                 // 1 the one minimal.c REGISTERS, Poisson2DJacobianLocal (minimal.c:142-145, "ONLY
+                                 // APPROXIMATE"): Newton's matrix when mf_operator == 0 ([PETSc] without -snes_fd_color),
+                                 // the preconditioner's under -snes_mf_operator ([PETSc]'s choice there)
 };
 
 inline void default_opts(MinimalOpts *o) {
@@ -207,9 +211,12 @@ struct Level {
     double *g = nullptr, *vals = nullptr, *u = nullptr, *F = nullptr, *x = nullptr, *b = nullptr, *t = nullptr;
     double scale = 0.0;
     std::vector<double> omega;
+    bool poisson = false, poisson_ready = false;
 
     void create(Ops *o, int mx_, int my_, const MinimalOpts &opt) {
         ops = o; mx = mx_; my = my_; n = (size_t)mx * my;
+        poisson = opt.jacobian == 1;
+        poisson_ready = false;
         g = ops->alloc(n); vals = ops->alloc(9 * n); u = ops->alloc(n); F = ops->alloc(n);
         x = ops->alloc(n); b = ops->alloc(n); t = ops->alloc(n);
         ops->minimal_sample(mx, my, opt.problem, opt.tent_H, opt.catenoid_c, g);
@@ -220,6 +227,11 @@ struct Level {
         ops = nullptr;
     }
     void assemble(double q, bool F_known) {
+        if (poisson) {                                         // the same at every iterate: filled once
+            if (!poisson_ready) ops->poisson_stencil9(mx, my, vals);
+            poisson_ready = true;
+            return;
+        }
         if (!F_known) ops->minimal_function(mx, my, q, u, g, F);
         ops->minimal_jacobian_fd(mx, my, q, u, g, F, vals);
     }
@@ -254,6 +266,7 @@ struct AssembledMG {
 
     int setup(double q) {
         std::vector<Level<Ops>> &L = *lev;
+        if (L[0].poisson && L[0].poisson_ready && Ainv && n0 == (int)L.back().n) return 0;
         for (size_t l = 0; l < L.size(); l++) {
             if (l > 0) ops->inject2d(L[l].mx, L[l].my, L[l - 1].u, L[l].u);
             L[l].assemble(q, l == 0);

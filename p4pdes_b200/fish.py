@@ -163,6 +163,9 @@ class Context:
         L.check(self.lib.p4b_minimal_jacobian_fd(self.h, mx, my, q, u.data_ptr(), g.data_ptr(), F0.data_ptr(),
                                                  vals.data_ptr()))
 
+    def poisson_stencil9(self, mx, my, Lx, Ly, cx, cy, vals):
+        L.check(self.lib.p4b_poisson_stencil9(self.h, mx, my, Lx, Ly, cx, cy, vals.data_ptr()))
+
     def stencil9_apply(self, mx, my, vals, x, y):
         L.check(self.lib.p4b_stencil9_apply(self.h, mx, my, vals.data_ptr(), x.data_ptr(), y.data_ptr()))
 

@@ -65,7 +65,7 @@ class MinimalOpts(C.Structure):
                 ("gmres_restart", C.c_int), ("pc_type", C.c_int), ("mg_levels", C.c_int), ("smooth_its", C.c_int),
                 ("snes_rtol", C.c_double), ("snes_stol", C.c_double), ("snes_atol", C.c_double), ("snes_max_it", C.c_int),
                 ("snes_monitor", C.c_int), ("snes_converged_reason", C.c_int), ("ksp_converged_reason", C.c_int),
-                ("mf_operator", C.c_int)]
+                ("mf_operator", C.c_int), ("jacobian", C.c_int)]
 
 
 class MinimalStage(C.Structure):
@@ -203,6 +203,7 @@ _SIGS = {
     "p4b_pattern_ijacobian_mult": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                              _D, _D]),
     "p4b_minimal_jacobian_fd": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, _D, _D, _D]),
+    "p4b_poisson_stencil9": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, _D]),
     "p4b_stencil9_apply": (C.c_int, [_P, C.c_int, C.c_int, _D, _D, _D]),
     "p4b_stencil9_lin": (C.c_int, [_P, C.c_int, C.c_int, _D, _D, _D, _D, C.c_double, C.c_double, C.c_double, C.c_int,
                                    _D]),

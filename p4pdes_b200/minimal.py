@@ -48,6 +48,8 @@ class MinimalOptions:
     grid_sequence: int = 0
     fd_color: bool = False
     mf_operator: bool = False
+    poisson_jacobian: bool = False      # set by parse_options when neither of the two is given (minimal.c's default)
+    mf_pmat: str = "fd"                 # -p4b_mf_pmat fd|poisson: what -snes_mf_operator preconditions with (newton())
     ksp_type: str = "gmres"
     ksp_rtol: float = 1.0e-5
     ksp_max_it: int = 10000
@@ -81,7 +83,7 @@ def parse_options(argv) -> MinimalOptions:
               "-ksp_gmres_restart": ("gmres_restart", int), "-pc_type": ("pc_type", str),
               "-pc_mg_levels": ("mg_levels", int), "-mg_levels_ksp_max_it": ("smooth_its", int),
               "-snes_rtol": ("snes_rtol", float), "-snes_stol": ("snes_stol", float), "-snes_atol": ("snes_atol", float),
-              "-snes_max_it": ("snes_max_it", int)}
+              "-snes_max_it": ("snes_max_it", int), "-p4b_mf_pmat": ("mf_pmat", str)}
     accepted = {"-mg_levels_ksp_type": ("chebyshev",), "-mg_levels_pc_type": ("jacobi",), "-snes_type": ("newtonls",)}
     i = 0
     while i < len(argv):
@@ -112,10 +114,16 @@ def parse_options(argv) -> MinimalOptions:
         raise ValueError("-ksp_type %s: the device path provides gmres and cg" % o.ksp_type)
     if o.pc_type not in ("mg", "none"):
         raise ValueError("-pc_type %s: the device path provides mg and none (ilu/sor/icc are sequential)" % o.pc_type)
-    if not (o.fd_color or o.mf_operator):
-        raise ValueError("the device path takes the Jacobian from the residual: pass -snes_fd_color (coloured finite "
-                         "differences) or -snes_mf_operator (matrix-free action, FD-coloured preconditioner matrix); "
-                         "minimal.c:142-145 registers only the approximate Poisson Jacobian otherwise")
+    # neither -snes_fd_color nor -snes_mf_operator: [PETSc] uses the Jacobian minimal.c registers, which is Poisson's
+    # ("ONLY APPROXIMATE", minimal.c:142-145): Newton with the constant 5-point matrix on every level (Level.assemble)
+    o.poisson_jacobian = not (o.fd_color or o.mf_operator)
+    # -snes_mf_operator: [PETSc] builds the preconditioner from the REGISTERED Jacobian, i.e. Poisson's ("-p4b_mf_pmat
+    # poisson": nothing is differenced but the operator's action); the default here ("fd") keeps round 1's stronger
+    # choice, the FD-coloured Jacobian of the residual itself
+    if o.mf_pmat not in ("fd", "poisson"):
+        raise ValueError("-p4b_mf_pmat %s: fd or poisson" % o.mf_pmat)
+    if o.mf_pmat == "poisson" and not o.mf_operator:
+        raise ValueError("-p4b_mf_pmat poisson is an option of -snes_mf_operator")
     return o
 
 
@@ -136,10 +144,19 @@ class Level:
         self.emin = self.emax = 0.0
         self.scale, self.omega = 0.0, []
         self.grid = ops.grid2d(mx, my)
+        # which matrix the level carries: the FD-coloured Jacobian of the residual, or the one minimal.c registers --
+        # Poisson2DJacobianLocal (minimal.c:142-145), the same at every iterate, so filled once
+        self.poisson = opt.poisson_jacobian or (opt.mf_operator and opt.mf_pmat == "poisson")
+        self.poisson_ready = False
 
     def assemble(self, q, F_known=False):
-        """J = dF/du at self.u by coloured finite differences; Chebyshev targets from the Gershgorin bound."""
+        """J = dF/du at self.u by coloured finite differences (or the registered Poisson matrix, see __init__)."""
         ops = self.ops
+        if self.poisson:
+            if not self.poisson_ready:
+                ops.poisson_stencil9(self.mx, self.my, 1.0, 1.0, 1.0, 1.0, self.vals)     # unit square, cx = cy = 1
+                self.poisson_ready = True
+            return
         if not F_known:
             ops.minimal_function(self.mx, self.my, q, self.u, self.g, self.F)
         ops.minimal_jacobian_fd(self.mx, self.my, q, self.u, self.g, self.F, self.vals)
@@ -173,6 +190,8 @@ class AssembledMG:
     def setup(self, q):
         """Level Jacobians at the injected iterate (levels[0].u and .F are current), smoothers, dense base-grid inverse."""
         ops = self.ops
+        if self.levels[0].poisson and self.Ainv is not None:
+            return                                       # the registered Poisson matrix does not depend on the iterate
         for l, L in enumerate(self.levels):
             if l > 0:
                 ops.inject2d(L.mx, L.my, self.levels[l - 1].u, L.u)
@@ -486,7 +505,11 @@ def newton(ops, levels, opt: MinimalOptions, out, indent=0) -> SNESResult:
             out("%s    Linear solve %s due to %s iterations %d" % (pad, "converged" if k.reason.startswith("CONV")
                                                                      else "did not converge", k.reason, k.its))
         mult(y, Jy)
-        gnorm, lam = linesearch_bt(ops, F, L.u, L.F, fnorm, y, Jy, w, gnew)
+        try:
+            gnorm, lam = linesearch_bt(ops, F, L.u, L.F, fnorm, y, Jy, w, gnew)
+        except RuntimeError:                          # [PETSc] stops the solve with a reason, it is not an error
+            res.reason = "DIVERGED_LINE_SEARCH"
+            break
         res.lambdas.append(lam)
         ops.axpby(1.0, w, -1.0, L.u, y)               # step actually taken (y is free now)
         snorm = ops.norm2(y)
@@ -557,6 +580,7 @@ def _minimal_native(opt: MinimalOptions, ctx, out, keep_solution) -> MinimalRepo
     o.snes_monitor = 2 if opt.snes_monitor_short else (1 if opt.snes_monitor else 0)
     o.snes_converged_reason, o.ksp_converged_reason = int(opt.snes_converged_reason), int(opt.ksp_converged_reason)
     o.mf_operator = int(opt.mf_operator)
+    o.jacobian = int(opt.poisson_jacobian or (opt.mf_operator and opt.mf_pmat == "poisson"))
     mx, my = opt.grid_x, opt.grid_y
     for _ in range(opt.refine + opt.grid_sequence):
         mx, my = 2 * mx - 1, 2 * my - 1

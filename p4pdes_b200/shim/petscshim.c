@@ -1041,6 +1041,57 @@ static int newton_monitor(void *user, int mx, int my, int its, double fnorm, int
 
 static void newton_line(const char *line, void *ctx) { (void)ctx; puts(line); }
 
+/* Without -snes_fd_color PETSc fills Newton's matrix (under -snes_mf_operator: the preconditioner's) by calling the Jacobian
+ * callback the driver REGISTERED.  minimal.c:142-145 registers Poisson2DJacobianLocal (c/ch6/poissonfunctions.c:152-193), which
+ * the library has as a kernel (p4b_poisson_stencil9: unit square, cx = cy = 1).  Before that kernel stands in for the
+ * callback, the callback is run -- on the grid the solve starts on and on the one it ends on -- and what it inserts is
+ * compared with the kernel's matrix: a constant star stencil with eliminated boundary columns (the "stencilcuda" recognition
+ * of MatSetValuesStencil) whose three numbers are the kernel's.  Any other callback is refused, naming -snes_fd_color. */
+static PetscErrorCode check_registered_poisson_jacobian(SNES snes) {
+    DM dm = snes->dm;
+    int gx = dm->M[0], gy = dm->M[1];
+    for (int pass = 0; pass < (snes->grid_sequence > 0 ? 2 : 1); pass++) {
+        if (pass == 1)
+            for (int k = 0; k < snes->grid_sequence; k++) { gx = 2 * gx - 1; gy = 2 * gy - 1; }
+        struct _p_DM cd = *dm;
+        cd.M[0] = gx; cd.M[1] = gy; cd.M[2] = 1;
+        memset(cd.pool, 0, sizeof cd.pool);
+        memset(cd.pool_busy, 0, sizeof cd.pool_busy);
+        const size_t n = (size_t)gx * gy;
+        double *u = (double *)calloc(n, sizeof(double));
+        Mat J = (Mat)calloc(1, sizeof *J);
+        if (!u || !J) { free(u); free(J); SHIM_ERR(55, "out of host memory for the Jacobian check"); }
+        J->dm = &cd;
+        J->type = MATSTENCILCUDA;
+        DMDALocalInfo info;
+        PetscCall(DMDAGetLocalInfo(&cd, &info));
+        void *au = make_tables(2, cd.M, u);
+        const double t0 = wall();
+        PetscErrorCode rc = dm->jac(&info, au, J, J, dm->jacctx);
+        g_t_jac += wall() - t0;
+        free(au);
+        free(u);
+        const double hx = 1.0 / (gx - 1), hy = 1.0 / (gy - 1), scx = hy / hx, scy = hx / hy, diag = 2.0 * (scx + scy);
+        const int general = J->general, complete = J->rows_set == (long long)n && J->have_diag;
+        const double dev = complete ? fmax(fabs(J->diag - diag), fmax(J->have_c[0] ? fabs(J->c[0] - scx) : (gx > 3 ? 1.0 : 0.0),
+                                                                     J->have_c[1] ? fabs(J->c[1] - scy) : (gy > 3 ? 1.0 : 0.0)))
+                                    : 1.0;
+        char why[200];
+        snprintf(why, sizeof why, "%s", general ? J->why : "");
+        free(J);
+        if (rc) return rc;
+        if (general || !complete || !(dev <= 1.0e-12 * diag)) {
+            char msg[512];
+            snprintf(msg, sizeof msg, "the registered Jacobian callback is not Poisson2DJacobianLocal on the unit square with "
+                     "cx = cy = 1 on the %d x %d grid (%s%s; deviation %.3e): the device path has that matrix only -- pass "
+                     "-snes_fd_color to difference the residual instead", gx, gy, general ? why : "",
+                     complete ? "" : " not every row was set", dev);
+            SHIM_ERR(56, msg);
+        }
+    }
+    return 0;
+}
+
 static PetscErrorCode snes_solve_newtonls(SNES snes, Vec x) {
     KSP ksp = &snes->ksp;
     PC pc = &ksp->pc;
@@ -1049,9 +1100,16 @@ static PetscErrorCode snes_solve_newtonls(SNES snes, Vec x) {
     if (dm->dim != 2 || dm->dof != 1)
         SHIM_ERR(56, "-snes_type newtonls is provided for 2-D DMDAs with one degree of freedom (minimal.c); "
                      "fish.c is linear: -snes_type ksponly (fish.c:230-231)");
-    if (!snes->fd_color && !snes->mf_operator)
-        SHIM_ERR(56, "newtonls needs the Jacobian of the registered residual: pass -snes_fd_color or -snes_mf_operator "
-                     "(minimal.c:142-143: the Jacobian callback registered there is Poisson's, 'thus ONLY APPROXIMATE')");
+    /* which matrix: -snes_fd_color differences the residual; without it PETSc calls the REGISTERED Jacobian callback --
+     * minimal.c:142-145 registers Poisson2DJacobianLocal ('thus ONLY APPROXIMATE').  The library has that matrix as a
+     * kernel (p4b_poisson_stencil9); the callback's rows are checked against it before it is used (below). */
+    const char *mfp = opt_value("-p4b_mf_pmat");
+    if (mfp && strcmp(mfp, "fd") && strcmp(mfp, "poisson")) SHIM_ERR(56, "-p4b_mf_pmat: fd or poisson");
+    const int registered = !snes->fd_color && (!snes->mf_operator || (mfp && !strcmp(mfp, "poisson")));
+    if (registered) {
+        if (!dm->jac) SHIM_ERR(73, "no Jacobian callback registered (DMDASNESSetJacobianLocal): pass -snes_fd_color");
+        PetscCall(check_registered_poisson_jacobian(snes));
+    }
     p4b_minimal_opts o;
     P4B(p4b_minimal_default_opts(&o));
     if (!strcmp(ksp->type, KSPGMRES)) o.ksp_type = 0;
@@ -1082,6 +1140,7 @@ static PetscErrorCode snes_solve_newtonls(SNES snes, Vec x) {
      * preconditioner from the registered (Poisson) Jacobian callback, here it is built from the FD-coloured Jacobian of the
      * residual -- the better matrix; Newton iterates depend on it only through the inexactness of the linear solves */
     o.mf_operator = snes->mf_operator && !snes->fd_color;
+    o.jacobian = registered;
     PetscCall(ensure_ctx());
     {   /* -p4b_recognise_residual 0: evaluate the registered FormFunctionLocal on the host every time, also when it is the
          * residual the library has as a kernel (p4b200.h, "Recognition") */

@@ -151,6 +151,15 @@ class FakeOps:
         v[3 * (dj + 1) + (di + 1), A.row] = A.data
         vals.a[:] = v.ravel()
 
+    def poisson_stencil9(self, mx, my, Lx, Ly, cx, cy, vals):
+        self._count("poisson_stencil9")
+        A = fo.jacobian(fo.Grid(2, (mx, my, 1), (Lx, Ly, 1.0)), (cx, cy, 1.0)).tocoo()
+        v = np.zeros((9, my * mx))
+        dj = A.col // mx - A.row // mx
+        di = A.col % mx - A.row % mx
+        v[3 * (dj + 1) + (di + 1), A.row] = A.data
+        vals.a[:] = v.ravel()
+
     def _csr(self, mx, my, vals):
         from p4pdes_b200.minimal import stencil9_to_csr
         rp, ci, d = stencil9_to_csr(vals.a, mx, my)

@@ -6,10 +6,13 @@
  *   -variant 2   the model + a term that acts only where u < -0.05: the probes (interior values in [0, 0.5]) cannot see
  *                it, the converged iterate (negative near x = 1) does -- the re-verification at the converged iterate must
  *                catch it and the solve must be repeated with the callback on the host
+ *   -jac k       registers a Jacobian callback as well (PETSc calls it when -snes_fd_color is absent): 1 = the 5-point
+ *                Laplacian rows of the unit square with the boundary columns dropped (what the library has as a kernel: must
+ *                be ACCEPTED), 2 = those rows times two, 3 = the same rows with the boundary columns kept (both must be REFUSED)
  * Prints sum(u) and max(u) of the converged iterate so that a test can compare with an independent solve. */
 #include <petsc.h>
 
-typedef struct { PetscReal q; PetscInt variant; } Ctx;
+typedef struct { PetscReal q; PetscInt variant, jac; } Ctx;
 
 static PetscReal gfun(PetscReal x, PetscReal y) { return 0.4 * PetscSinReal(3.0 * x + 1.0) * PetscCosReal(2.0 * y) + 0.2 * x * y; }
 static PetscReal diffusivity(PetscReal ux, PetscReal uy, PetscReal q) { return PetscPowReal(1.0 + ux * ux + uy * uy, q); }
@@ -36,6 +39,38 @@ static PetscErrorCode Residual(DMDALocalInfo *info, PetscReal **au, PetscReal **
     return 0;
 }
 
+/* the Laplacian as an approximate Jacobian of the residual above: one MatSetValuesStencil per row */
+static PetscErrorCode LaplaceRows(DMDALocalInfo *info, PetscReal **au, Mat J, Mat P, Ctx *user) {
+    const PetscInt mx = info->mx, my = info->my;
+    const PetscReal rx = (PetscReal)(mx - 1) / (my - 1), ry = 1.0 / rx, f = user->jac == 2 ? 2.0 : 1.0;
+    (void)au;
+    for (PetscInt j = info->ys; j < info->ys + info->ym; j++)
+        for (PetscInt i = info->xs; i < info->xs + info->xm; i++) {
+            MatStencil row, col[5];
+            PetscReal v[5];
+            PetscInt n = 0;
+            const PetscInt di[4] = {-1, 1, 0, 0}, dj[4] = {0, 0, -1, 1};
+            row.i = i; row.j = j; row.k = 0; row.c = 0;
+            col[n] = row; v[n++] = f * 2.0 * (rx + ry);
+            if (i > 0 && j > 0 && i < mx - 1 && j < my - 1)
+                for (PetscInt d = 0; d < 4; d++) {
+                    const PetscInt ii = i + di[d], jj = j + dj[d];
+                    const int bd = ii == 0 || jj == 0 || ii == mx - 1 || jj == my - 1;
+                    if (bd && user->jac != 3) continue;
+                    col[n] = row; col[n].i = ii; col[n].j = jj;
+                    v[n++] = -f * (d < 2 ? rx : ry);
+                }
+            PetscCall(MatSetValuesStencil(P, 1, &row, n, col, v, INSERT_VALUES));
+        }
+    PetscCall(MatAssemblyBegin(P, MAT_FINAL_ASSEMBLY));
+    PetscCall(MatAssemblyEnd(P, MAT_FINAL_ASSEMBLY));
+    if (J != P) {
+        PetscCall(MatAssemblyBegin(J, MAT_FINAL_ASSEMBLY));
+        PetscCall(MatAssemblyEnd(J, MAT_FINAL_ASSEMBLY));
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
     Ctx user;
     DM da;
@@ -44,9 +79,10 @@ int main(int argc, char **argv) {
     DMDALocalInfo info;
     PetscReal **a, sum = 0.0, mxv = -1.0e300;
     PetscCall(PetscInitialize(&argc, &argv, NULL, "SNES variants for the p4b200 shim\n"));
-    user.q = -0.35; user.variant = 0;
+    user.q = -0.35; user.variant = 0; user.jac = 0;
     PetscOptionsBegin(PETSC_COMM_WORLD, "", "variants", "");
     PetscCall(PetscOptionsInt("-variant", "0 = the model, 1 = model + reaction, 2 = model + a term the probes cannot see", "snes_variants.c", user.variant, &user.variant, NULL));
+    PetscCall(PetscOptionsInt("-jac", "0 = no Jacobian callback, 1 = Laplacian rows, 2 = twice those, 3 = boundary columns kept", "snes_variants.c", user.jac, &user.jac, NULL));
     PetscCall(PetscOptionsReal("-q", "exponent of the diffusivity", "snes_variants.c", user.q, &user.q, NULL));
     PetscOptionsEnd();
     PetscCall(DMDACreate2d(PETSC_COMM_WORLD, DM_BOUNDARY_NONE, DM_BOUNDARY_NONE, DMDA_STENCIL_BOX, 5, 5, PETSC_DECIDE, PETSC_DECIDE,
@@ -57,6 +93,7 @@ int main(int argc, char **argv) {
     PetscCall(SNESCreate(PETSC_COMM_WORLD, &snes));
     PetscCall(SNESSetDM(snes, da));
     PetscCall(DMDASNESSetFunctionLocal(da, INSERT_VALUES, (DMDASNESFunctionFn *)Residual, &user));
+    if (user.jac) PetscCall(DMDASNESSetJacobianLocal(da, (DMDASNESJacobianFn *)LaplaceRows, &user));
     PetscCall(SNESSetFromOptions(snes));
     PetscCall(DMGetGlobalVector(da, &u0));
     PetscCall(VecSet(u0, 0.1));

@@ -25,7 +25,7 @@ def test_reference_command_lines_parse():
     ("-snes_fd_color -ms_exact_init -ms_q -0.25", "only possible if q=-0.5"),                  # :120
     ("-snes_fd_color -pc_type ilu", "sequential"),
     ("-snes_fd_color -mg_levels_pc_type sor", "sequential"),
-    ("-pc_type mg", "-snes_fd_color"),
+    ("-snes_fd_color -p4b_mf_pmat poisson", "option of -snes_mf_operator"),
 ])
 def test_error_paths(argv, msg):
     with pytest.raises(ValueError, match=msg):
@@ -73,6 +73,37 @@ def test_driver_matches_oracle(argv, okw):
     assert np.max(np.abs(u - o.u)) <= 1e-11 * max(1.0, np.max(np.abs(o.u)))
     if o.errinf is not None:
         assert abs(r.errinf - o.errinf) <= 1e-11
+
+
+@pytest.mark.parametrize("argv,okw", [
+    ("-da_refine 2 -pc_type none -ms_problem tent -ms_q 0.0", dict(refine=2, problem="tent", q=0.0, pc="none")),
+    ("-da_refine 3 -pc_type none", dict(refine=3, pc="none")),
+    ("-da_refine 2 -pc_type none -ksp_type cg -ms_problem tent", dict(refine=2, problem="tent", pc="none", ksp="cg")),
+    ("-snes_grid_sequence 2 -pc_type none -ms_catenoid_c 1.5", dict(grid_sequence=2, pc="none", catenoid_c=1.5)),
+    ("-da_refine 3 -pc_type mg -ms_problem tent -ms_q 0.0", dict(refine=3, problem="tent", q=0.0, pc="mg")),
+    ("-da_refine 3 -pc_type mg -pc_mg_levels 2 -snes_max_it 8", dict(refine=3, pc="mg", mg_levels=2, max_it=8)),
+    # -snes_mf_operator with what [PETSc] preconditions it with: the registered Poisson matrix (minimal.test3's route)
+    ("-snes_mf_operator -p4b_mf_pmat poisson -snes_grid_sequence 2 -pc_type mg",
+     dict(grid_sequence=2, pc="mg", mf_operator=True)),
+    ("-snes_mf_operator -p4b_mf_pmat poisson -da_refine 3 -pc_type mg -ms_problem tent",
+     dict(refine=3, problem="tent", pc="mg", mf_operator=True)),
+])
+def test_default_route_uses_the_registered_poisson_jacobian(argv, okw):
+    """minimal.c:142-145: without -snes_fd_color / -snes_mf_operator Newton's matrix is Poisson2DJacobianLocal ("ONLY
+    APPROXIMATE": exact for -ms_q 0, a slowly converging fixed-point iteration otherwise).  Driver == oracle, step by step."""
+    r = pm.minimal_main(argv, FakeOps())
+    o = mo.minimal(poisson_jacobian=True, **okw)
+    assert [s.its for s in r.stages] == [s.its for s in o.stages]
+    assert [s.ksp_its for s in r.stages] == [s.ksp_its for s in o.stages]
+    assert [s.reason for s in r.stages] == [s.reason for s in o.stages]
+    for a, b in zip(r.stages, o.stages):
+        np.testing.assert_allclose(a.fnorms, b.fnorms, rtol=1e-3, atol=1e-10 * b.fnorms[0])
+    assert np.max(np.abs(r.u.a.reshape(o.u.shape) - o.u)) <= 1e-10
+    if okw.get("q") == 0.0 and okw["pc"] == "none":
+        # Laplace: the Poisson matrix IS the Jacobian up to the boundary rows' scaling (4 against minimal.c's 1).  (With
+        # multigrid the coarse corrections leave O(ksp_rtol) on the boundary rows, which that scaling then removes only by a
+        # factor 3/4 per step, in PETSc as here: the oracle shows the same 13 iterations.)
+        assert r.stages[0].its <= 3
 
 
 def test_stencil9_csr_round_trip():

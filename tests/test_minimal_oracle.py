@@ -136,3 +136,29 @@ def test_golden_minimal_test3_matrix_free_operator():
     area = lambda l: float(l.split()[2].rstrip(";"))
     assert len(got[True]) == 14 and max(abs(area(a) - area(b)) for a, b in zip(got[True], golden)) <= 6e-8
     assert [l.split(";")[1] for l in got[True]] == [l.split(";")[1] for l in golden]
+
+
+def test_golden_minimal_test3_with_the_registered_poisson_preconditioner():
+    """minimal.test3's actual route: -snes_mf_operator makes [PETSc] precondition with the matrix the REGISTERED Jacobian
+    callback fills, Poisson2DJacobianLocal (minimal.c:142-145, help text :9-10), under -pc_type mg rediscretised per level
+    (= fish.c's PCMG).  Restated (poisson_jacobian=True): the golden's Newton counts 5, 3, 3 (:7, :12, :17), its error line
+    (:18) and every monitor line up to three that carry the golden's own inexact 2-rank Chebyshev/SOR solves (<= 6e-8 in the area)."""
+    fmt = lambda t: "area = %.8f; %.4f <= D <= %.4f" % t
+    golden = ["area = 2.14201032; 0.2985 <= D <= 0.8826", "area = 1.60235989; 0.4166 <= D <= 0.9873",
+              "area = 1.39125969; 0.5789 <= D <= 0.9362", "area = 1.32285324; 0.6106 <= D <= 0.9561",
+              "area = 1.32217567; 0.6158 <= D <= 0.9510", "area = 1.32217567; 0.6158 <= D <= 0.9510",
+              "area = 1.32217583; 0.6035 <= D <= 0.9518", "area = 1.33231935; 0.5757 <= D <= 0.9872",
+              "area = 1.33230219; 0.5755 <= D <= 0.9872", "area = 1.33230217; 0.5755 <= D <= 0.9872",
+              "area = 1.33230220; 0.5684 <= D <= 0.9872", "area = 1.33475595; 0.5153 <= D <= 0.9968",
+              "area = 1.33475385; 0.5156 <= D <= 0.9968", "area = 1.33475385; 0.5156 <= D <= 0.9968"]
+    got = []
+    o = mo.minimal(grid_sequence=2, pc="mg", mf_operator=True, poisson_jacobian=True,
+                   monitor=lambda st, it, u: got.append(fmt(mo.mse_monitor(u, -0.5, 2))))
+    assert [s.its for s in o.stages] == [5, 3, 3]
+    assert all(s.reason == "CONVERGED_FNORM_RELATIVE" for s in o.stages)
+    assert "%.5e" % o.errinf == "6.79501e-04"
+    same = [a == b for a, b in zip(got, golden)]
+    assert len(got) == 14 and same.count(False) <= 3
+    area = lambda l: float(l.split()[2].rstrip(";"))
+    assert max(abs(area(a) - area(b)) for a, b in zip(got, golden)) <= 6e-8
+    assert [l.split(";")[1] for l in got] == [l.split(";")[1] for l in golden]

@@ -57,6 +57,28 @@ def test_native_solver_matches_python_oracle(exe, argv, okw):
     assert d["allocs"] == d["frees"]                      # every vector the solver took from Ops went back
 
 
+@pytest.mark.parametrize("argv,okw", [
+    (("-da_refine", 2, "-pc_type", "none", "-ms_problem", "tent", "-ms_q", 0.0), dict(refine=2, problem="tent", q=0.0, pc="none")),
+    (("-da_refine", 3, "-pc_type", "mg", "-snes_max_it", 7), dict(refine=3, pc="mg", max_it=7)),
+    (("-snes_grid_sequence", 2, "-pc_type", "mg", "-ms_problem", "tent", "-ms_tent_H", 0.3, "-snes_max_it", 12),
+     dict(grid_sequence=2, pc="mg", problem="tent", tent_H=0.3, max_it=12)),
+    (("-snes_mf_operator", "-p4b_mf_pmat", "poisson", "-snes_grid_sequence", 2, "-pc_type", "mg"),
+     dict(grid_sequence=2, pc="mg", mf_operator=True)),
+])
+def test_native_solver_on_the_registered_poisson_jacobian(exe, argv, okw):
+    """MinimalOpts.jacobian = 1 (no -snes_fd_color): the matrix minimal.c registers, minimal.c:142-145 -- Newton's matrix,
+    or the preconditioner's under -snes_mf_operator; the oracle with poisson_jacobian=True, step by step."""
+    _, d = run(exe, *argv)
+    o = mo.minimal(poisson_jacobian=True, **okw)
+    assert [s["its"] for s in d["stages"]] == [s.its for s in o.stages]
+    assert [s["ksp_its"] for s in d["stages"]] == [s.ksp_its for s in o.stages]
+    assert all(s["reason"] == t.reason for s, t in zip(d["stages"], o.stages))
+    for s, t in zip(d["stages"], o.stages):
+        np.testing.assert_allclose(s["fnorm"], t.fnorms, rtol=1e-4, atol=1e-10 * t.fnorms[0])
+    assert abs(d["sum"] - float(o.u.sum())) <= 1e-9 * abs(float(o.u.sum()))
+    assert d["allocs"] == d["frees"]
+
+
 def test_native_solver_on_the_catenoid_cold_start(exe):
     """The catenoid runs start at u = 0 in the interior (the case the per-entry "ds" differencing could not handle:
     tests/test_minimal_oracle.py): same Newton counts on every stage, same solution and error."""

@@ -116,7 +116,7 @@ def test_solution_and_dm_after_grid_sequencing(exe):
 
 
 @pytest.mark.parametrize("argv,code,msg", [
-    ("-pc_type mg -mg_levels_pc_type jacobi", 56, "pass -snes_fd_color"),
+    ("-snes_fd_color -pc_type none -p4b_mf_pmat ilu", 56, "-p4b_mf_pmat: fd or poisson"),
     ("-snes_fd_color", 56, "ILU"),
     ("-snes_fd_color -pc_type mg", 56, "SOR"),
     ("-snes_fd_color -pc_type jacobi", 56, "-pc_type mg and -pc_type none"),
@@ -213,3 +213,59 @@ def test_a_term_the_probes_cannot_see_is_caught_at_the_converged_iterate(snes_va
     forced, _ = run_report(snes_variants, "-variant 2 -p4b_recognise_residual 0 " + argv)
     model, _ = run_report(snes_variants, "-variant 0 " + argv)
     assert p.stdout.splitlines()[-1] == forced[-1] and forced[-1] != model[-1]
+
+
+# ---- the Jacobian callback minimal.c REGISTERS (minimal.c:142-145: Poisson's, "ONLY APPROXIMATE") -------------------------
+@pytest.mark.parametrize("argv", [
+    "-da_refine 2 -pc_type none -ms_problem tent -ms_q 0.0 -snes_converged_reason -snes_monitor_short",
+    "-da_refine 3 -pc_type mg -snes_converged_reason -snes_max_it 6 -snes_monitor",
+    "-da_grid_x 5 -da_grid_y 9 -snes_grid_sequence 2 -pc_type mg -ms_problem tent -ms_tent_H 0.3 -snes_converged_reason "
+    "-snes_max_it 12 -snes_monitor -ksp_converged_reason",
+    "-snes_mf_operator -p4b_mf_pmat poisson -snes_grid_sequence 2 -pc_type mg -snes_converged_reason -snes_monitor "
+    "-ksp_converged_reason",
+])
+def test_without_fd_color_the_registered_poisson_jacobian_is_newtons_matrix(exe, argv):
+    """What [PETSc] does with the unchanged minimal.c when -snes_fd_color is absent: the matrix comes from the registered
+    callback.  The shim runs that callback (start and final grid), checks that its rows are the library's Poisson matrix and
+    lets the kernel stand in for it; the printed lines are those of the Python host over the NumPy stand-in, character for
+    character (that driver == the oracle: tests/test_minimal_driver_cpu.py)."""
+    from p4pdes_b200 import minimal as pm
+    from tests.fake_ops import FakeOps
+    lines, _ = run(exe, argv + (" -mg_levels_pc_type jacobi" if "-pc_type mg" in argv else ""))
+    want = pm.minimal_main(argv, FakeOps()).lines
+    assert len(lines) == len(want)
+    for a, b in zip(lines, want):
+        if "SNES Function norm" in a and a != b:        # late norms carry the rounding of the differenced operator
+            assert a.split()[:4] == b.split()[:4] and abs(float(a.split()[-1]) - float(b.split()[-1])) <= 1e-4 * float(b.split()[-1]) + 1e-11
+        else:
+            assert a == b
+
+
+def test_golden_test3_on_petscs_own_route(exe):
+    """minimal.test3 once more, now as [PETSc] ran it: -snes_mf_operator preconditioned by the REGISTERED Poisson matrix
+    (-p4b_mf_pmat poisson; the default keeps the FD-coloured Jacobian).  Newton counts 5 / 3 / 3, tab levels, error line
+    equal; areas to <= 1e-7 (the golden's Chebyshev/SOR solves on 2 ranks against Chebyshev/Jacobi here)."""
+    g = GOLD["minimal.test3"]
+    lines, _ = run(exe, g["options"] + " -mg_levels_pc_type jacobi -p4b_mf_pmat poisson")
+    assert len(lines) == len(g["lines"])
+    for a, b in zip(lines, g["lines"]):
+        if "area" in b:
+            fa, fb = [float(x) for x in re.findall(r"[0-9.]+", a)], [float(x) for x in re.findall(r"[0-9.]+", b)]
+            assert a[:a.index("area")] == b[:b.index("area")] and fa[1:] == fb[1:] and abs(fa[0] - fb[0]) <= 1e-7
+        else:
+            assert a == b
+
+
+def test_a_registered_jacobian_that_is_not_the_librarys_is_refused(snes_variants):
+    # no callback registered and no -snes_fd_color: PETSc would difference densely; here an error that names the option
+    _, p = run(snes_variants, "-variant 0 -pc_type none", check=False)
+    assert p.returncode == 73 and "no Jacobian callback registered" in p.stderr and "-snes_fd_color" in p.stderr
+    # the Laplacian rows of the unit square: accepted, and a (slowly converging) Newton iteration runs on them
+    ok, p = run(snes_variants, "-variant 0 -jac 1 -da_refine 1 -pc_type none -snes_max_it 4 -snes_converged_reason")
+    assert ok[0].strip() == "Nonlinear solve did not converge due to DIVERGED_MAX_IT iterations 4" and ok[-1].startswith("done on 9 x 9")
+    fd, _ = run(snes_variants, "-variant 0 -jac 1 -da_refine 1 -pc_type none -snes_fd_color -snes_converged_reason")
+    assert "CONVERGED_FNORM_RELATIVE" in fd[0]          # with -snes_fd_color the callback is not used at all
+    for k, why in ((2, "deviation"), (3, "column to a boundary node was not dropped")):
+        _, p = run(snes_variants, "-variant 0 -jac %d -da_refine 1 -pc_type none" % k, check=False)
+        assert p.returncode == 56 and "is not Poisson2DJacobianLocal" in p.stderr and why in p.stderr \
+            and "pass -snes_fd_color" in p.stderr
