@@ -486,6 +486,17 @@ typedef int (*p4b_rhsfunction2d_fn)(void *user, int m, double t, const double *Y
 int p4b_ts2d_solve(p4b_ctx *ctx, const p4b_pattern_opts *opts, p4b_ifunction2d_fn ifunction, p4b_rhsfunction2d_fn rhsfunction,
                    void *user, double *Y_inout_host, size_t Y_capacity, p4b_line_fn line, void *line_ctx,
                    p4b_pattern_result *result);
+/* ---- ... and for the method-of-lines system of ANY DMDA driver: the state is a field of n doubles whose layout only the
+ * callbacks know (m is passed as 0).  This is how the unchanged c/ch5/heat.c runs under the shim (one component, Neumann in
+ * x, periodic in y, RHSFunction only: heat.c:60-75,141-163).  Same steppers, plus opts->ts_type = 4: [PETSc] TSRK "3bs"
+ * (Bogacki-Shampine 3(2), explicit, TSAdaptBasic at order 3 -- pinned by c/ch5/output/heat.test2), for which the system must
+ * be Ydot = G(t, Y): the IFunction is not called.  pc_type is ignored for rk and must be 0 otherwise.
+ * p4b_ts_time_step(): the step the running integrator is about to take (at the last monitor call: proposes next) -- what
+ * [PETSc] TSGetTimeStep answers inside a TSMonitorSet monitor (heat.c:133). ---- */
+int p4b_ts_solve_callbacks(p4b_ctx *ctx, const p4b_pattern_opts *opts, p4b_ifunction2d_fn ifunction,
+                           p4b_rhsfunction2d_fn rhsfunction, void *user, double *Y_inout_host, size_t n, p4b_line_fn line,
+                           void *line_ctx, p4b_pattern_result *result);
+double p4b_ts_time_step(void);
 typedef struct p4b_sell p4b_sell;
 int p4b_sell_create(p4b_ctx *ctx, int nrows, const int *rowptr_host, const int *colind_host, const double *vals_host,
                     p4b_sell **A);

@@ -242,6 +242,7 @@ typedef int MPI_Op;
 #define TSBEULER "beuler"
 #define TSCN "cn"
 #define TSBDF "bdf"
+#define TSRK "rk"
 typedef enum { TS_LINEAR = 0, TS_NONLINEAR } TSProblemType;
 typedef enum { TS_EXACTFINALTIME_UNSPECIFIED = 0, TS_EXACTFINALTIME_STEPOVER, TS_EXACTFINALTIME_INTERPOLATE,
                TS_EXACTFINALTIME_MATCHSTEP } TSExactFinalTimeOption;
@@ -287,6 +288,13 @@ PetscErrorCode TSSetExactFinalTime(TS ts, TSExactFinalTimeOption eftopt);
 PetscErrorCode TSSetFromOptions(TS ts);
 PetscErrorCode TSSolve(TS ts, Vec u);
 PetscErrorCode TSDestroy(TS *ts);
+/* + c/ch5/heat.c:72,83-84,117,133 */
+PetscErrorCode TSMonitorSet(TS ts, PetscErrorCode (*monitor)(TS, PetscInt, PetscReal, Vec, void *), void *mctx,
+                            PetscErrorCode (*mdestroy)(void **));
+PetscErrorCode TSGetTime(TS ts, PetscReal *t);
+PetscErrorCode TSGetMaxTime(TS ts, PetscReal *maxtime);
+PetscErrorCode TSGetTimeStep(TS ts, PetscReal *dt);
+PetscErrorCode TSGetDM(TS ts, DM *dm);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,8 @@ struct HostOps {
     void ts_step(int k, double t, const double *Y, size_t n) {
         if (ts_fn() && !err && ts_fn()(ts_user(), k, t, Y, n)) err = 66;
     }
+    static double &ts_h() { static double h = 0.0; return h; }
+    void set_step_size(double h) { ts_h() = h; }
 
     // c/ch7/minimal.c:27-42  g_bdry_tent / g_bdry_catenoid at every node of the unit square
     void minimal_sample(int mx, int my, int problem, double H, double c, double *g) {
@@ -430,15 +432,17 @@ struct HostCallbackPatternOps : HostOps {
     bool r0_rhs = false;
     std::vector<double> wY, wD, wF, wR0;
     long long callbacks = 0;
+    size_t nfield = 0;                     // != 0: a field of that many doubles (p4b_ts_solve_callbacks), m is 0
+    size_t fsize(int m) const { return nfield ? nfield : (size_t)2 * m * m; }
     void pattern_ifunction(int m, const PO &, const double *Y, const double *Ydot, double *F) {
-        const size_t n = (size_t)2 * m * m;
+        const size_t n = fsize(m);
         std::vector<double> y(Y, Y + n), d(Ydot, Ydot + n), f(n);
         callbacks++;
         if (ifn(user, m, tcur, y.data(), d.data(), f.data()) && !err) err = 65;
         memcpy(F, f.data(), sizeof(double) * n);
     }
     void pattern_rhsfunction(int m, const PO &, const double *Y, double *G) {
-        const size_t n = (size_t)2 * m * m;
+        const size_t n = fsize(m);
         std::vector<double> y(Y, Y + n), g(n);
         callbacks++;
         if (gfn(user, m, tcur, y.data(), g.data()) && !err) err = 65;
@@ -448,14 +452,14 @@ struct HostCallbackPatternOps : HostOps {
     double tcur = 0.0;
     void set_time(double t) { tcur = t; }
     void resid(int m, const PO &o, double shift, bool rhs, const double *W, double *out) {
-        const size_t n = (size_t)2 * m * m;
+        const size_t n = fsize(m);
         wD.resize(n);
         for (size_t i = 0; i < n; i++) wD[i] = shift * W[i];
         pattern_ifunction(m, o, W, wD.data(), out);
         if (rhs) { wF.resize(n); pattern_rhsfunction(m, o, W, wF.data()); axpy(n, -1.0, wF.data(), out); }
     }
     void pattern_jac_apply(int m, const PO &o, double shift, const double *Y, const double *X, double *out) {
-        const size_t n = (size_t)2 * m * m;
+        const size_t n = fsize(m);
         const bool rhs = Y != nullptr;
         if (!lin) { if (!err) err = 68; return; }
         if (r0_for != lin || r0_shift != shift || r0_rhs != rhs) {

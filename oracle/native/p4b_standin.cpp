@@ -239,6 +239,37 @@ int p4b_ts2d_solve(p4b_ctx *c, const p4b_pattern_opts *opts, p4b_ifunction2d_fn 
     return 0;
 }
 
+int p4b_ts_solve_callbacks(p4b_ctx *c, const p4b_pattern_opts *opts, p4b_ifunction2d_fn ifunction, p4b_rhsfunction2d_fn rhsfunction,
+                           void *user, double *Y_inout_host, size_t n, p4b_line_fn line, void *line_ctx,
+                           p4b_pattern_result *result) {
+    if (!c || !opts || !ifunction || !rhsfunction || !Y_inout_host || !result || !n)
+        return fail(62, "p4b_ts_solve_callbacks: null argument");
+    nk::PatternOpts o = *reinterpret_cast<const nk::PatternOpts *>(opts);
+    if (o.ts_type < nk::TS_ARKIMEX || o.ts_type > nk::TS_RK) return fail(62, "ts_type: arkimex (0), beuler (1), cn (2), bdf (3), rk (4)");
+    if (o.pc_type != nk::PC_NONE && o.ts_type != nk::TS_RK) return fail(56, "p4b_ts_solve_callbacks: -pc_type none only");
+    o.pc_type = nk::PC_NONE;
+    HostCallbackPatternOps ops;
+    ops.cgs = g_cgs != 0;
+    ops.ifn = ifunction;
+    ops.gfn = rhsfunction;
+    ops.user = user;
+    ops.nfield = n;
+    nk::Printer pr{line, line_ctx};
+    double *Y = nullptr;
+    std::vector<double> Y0(Y_inout_host, Y_inout_host + n);
+    nk::PatternResult &R = *reinterpret_cast<nk::PatternResult *>(result);
+    int rc = nk::pattern_solve(&ops, o, pr, &Y, &R, Y0.data(), n);
+    if (!rc && ops.error()) rc = ops.error();
+    if (!rc) memcpy(Y_inout_host, Y, sizeof(double) * n);
+    if (Y) ops.release(Y);
+    if (getenv("P4B_STANDIN_REPORT")) fprintf(stderr, "standin: ts callbacks %lld\n", ops.callbacks);
+    if (rc == 64) return fail(64, "TSSolve: a stage solve did not converge (or an explicit step produced NaN)");
+    if (rc == 65) return fail(65, "a callback returned an error");
+    if (rc) return fail(rc, "p4b_ts_solve_callbacks failed");
+    return 0;
+}
+double p4b_ts_time_step(void) { return HostOps::ts_h(); }
+
 // ---- fish.c: the operator the shim's Mat type recognised (finest level) and a Jacobi-preconditioned CG on it.  There is
 // NO multigrid here: iteration counts are not the device path's; what the stand-in lets a CPU test see is everything
 // the shim does around the solve (callbacks, Mat recognition, Vec bookkeeping, the reference's own report lines). ----

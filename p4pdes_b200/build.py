@@ -74,7 +74,8 @@ REFERENCE = os.environ.get("P4B_REFERENCE", "/root/reference")
 # the reference's unchanged drivers and the files each one is made of (c/ch6/makefile:5-7)
 DRIVERS = {"fish": ["c/ch6/fish.c", "c/ch6/poissonfunctions.c"],
            "minimal": ["c/ch7/minimal.c", "c/ch6/poissonfunctions.c"],
-           "pattern": ["c/ch5/pattern.c"]}
+           "pattern": ["c/ch5/pattern.c"],
+           "heat": ["c/ch5/heat.c"]}
 
 
 def build_shim(force=False):

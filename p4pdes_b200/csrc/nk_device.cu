@@ -23,6 +23,7 @@ int ctx_allgather(p4b_ctx *c, double *full, size_t count);
 // process-wide TS step monitor (p4b_set_ts_step_monitor)
 static p4b_ts_step_fn g_ts_step_fn = nullptr;
 static void *g_ts_step_user = nullptr;
+static double g_ts_time_step = 0.0;      // the step the integrator is about to take / proposes (p4b_ts_time_step)
 
 struct DeviceOps {
     p4b_ctx *c;
@@ -36,6 +37,7 @@ struct DeviceOps {
         if (!err && g_ts_step_fn(g_ts_step_user, k, t, ts_host.data(), nloc)) err = 66;
     }
     void ts_step(int k, double t, const double *Y, size_t n) { ts_step_n(k, t, Y, n); }
+    void set_step_size(double h) { g_ts_time_step = h; }
     int error() const { return err; }
     void chk(int rc) { if (rc && !err) err = rc; }
     void cu(cudaError_t e) { if (e != cudaSuccess && !err) err = 70 + (int)e % 20; }
@@ -393,12 +395,14 @@ struct CallbackPatternOps : DeviceOps {
     bool r0_rhs = false;
     long long callbacks = 0;
     double tcur = 0.0;                                     // stage time handed to the callbacks (ts_solver.hpp set_time)
+    size_t nfield = 0;                                     // != 0: a field of that many doubles (p4b_ts_solve_callbacks), m is 0
+    size_t fsize(int m) const { return nfield ? nfield : (size_t)2 * m * m; }
     void set_time(double t) { tcur = t; }
     CallbackPatternOps(p4b_ctx *c_, cudaStream_t st_, p4b_ifunction2d_fn f, p4b_rhsfunction2d_fn g, void *u)
         : DeviceOps{c_, st_}, ifn(f), gfn(g), user(u) {}
     void free_work() { for (double *p : {wY, wD, wF, wR0}) release(p); wY = wD = wF = wR0 = nullptr; }
     void pattern_ifunction(int m, const PO &, const double *Y, const double *Ydot, double *F) {
-        const size_t n = (size_t)2 * m * m;
+        const size_t n = fsize(m);
         hY.resize(n); hD.resize(n); hF.resize(n);
         to_host(Y, hY.data(), n);
         to_host(Ydot, hD.data(), n);
@@ -407,7 +411,7 @@ struct CallbackPatternOps : DeviceOps {
         from_host(hF.data(), F, n);
     }
     void pattern_rhsfunction(int m, const PO &, const double *Y, double *G) {
-        const size_t n = (size_t)2 * m * m;
+        const size_t n = fsize(m);
         hY.resize(n); hF.resize(n);
         to_host(Y, hY.data(), n);
         callbacks++;
@@ -417,13 +421,13 @@ struct CallbackPatternOps : DeviceOps {
     void set_linearisation(const double *Y) { lin = Y; r0_for = nullptr; }
     // R(W) = F(W, shift W) - [rhs ? G(W) : 0]
     void resid(int m, const PO &o, double shift, bool rhs, const double *W, double *out) {
-        const size_t n = (size_t)2 * m * m;
+        const size_t n = fsize(m);
         axpby(n, shift, W, 0.0, nullptr, wD);
         pattern_ifunction(m, o, W, wD, out);
         if (rhs) { pattern_rhsfunction(m, o, W, wF); axpy(n, -1.0, wF, out); }
     }
     void pattern_jac_apply(int m, const PO &o, double shift, const double *Y, const double *X, double *out) {
-        const size_t n = (size_t)2 * m * m;
+        const size_t n = fsize(m);
         const bool rhs = Y != nullptr;                     // (nullptr: IMEX or -ptn_no_rhsjacobian, G' stays out)
         if (!lin) { if (!err) err = 68; return; }
         if (!wY) { wY = alloc(n); wD = alloc(n); wF = alloc(n); wR0 = alloc(n); }
@@ -596,6 +600,40 @@ extern "C" int p4b_ts2d_solve(p4b_ctx *c, const p4b_pattern_opts *opts, p4b_ifun
     if (rc) return fail(rc, "p4b_ts2d_solve failed (%s)", p4b_last_error());
     return 0;
 }
+
+extern "C" int p4b_ts_solve_callbacks(p4b_ctx *c, const p4b_pattern_opts *opts, p4b_ifunction2d_fn ifunction,
+                                      p4b_rhsfunction2d_fn rhsfunction, void *user, double *Y_inout_host, size_t n,
+                                      p4b_line_fn line, void *line_ctx, p4b_pattern_result *result) {
+    if (!c || !opts || !ifunction || !rhsfunction || !Y_inout_host || !result || !n)
+        return fail(62, "p4b_ts_solve_callbacks: null argument");
+    const nk::PatternOpts &o = *reinterpret_cast<const nk::PatternOpts *>(opts);
+    if (o.ts_type < nk::TS_ARKIMEX || o.ts_type > nk::TS_RK)
+        return fail(62, "ts_type: arkimex (0), beuler (1), cn (2), bdf (3), rk (4)");
+    if (o.pc_type != nk::PC_NONE && o.ts_type != nk::TS_RK)
+        return fail(56, "p4b_ts_solve_callbacks: callbacks without a Jacobian give a matrix-free stage operator; no matrix, no "
+                        "multigrid: -pc_type none only");
+    nk::PatternOpts o2 = o;
+    o2.pc_type = nk::PC_NONE;
+    CallbackPatternOps ops(c, ctx_stream(c), ifunction, rhsfunction, user);
+    ops.nfield = n;
+    nk::Printer pr{line, line_ctx};
+    double *Y = nullptr, *Y0 = ops.alloc(n);
+    ops.from_host(Y_inout_host, Y0, n);
+    nk::PatternResult &R = *reinterpret_cast<nk::PatternResult *>(result);
+    int rc = nk::pattern_solve(&ops, o2, pr, &Y, &R, Y0, n);
+    if (!rc && ops.error()) rc = ops.error();
+    if (!rc) ops.to_host(Y, Y_inout_host, n);
+    ops.release(Y0);
+    if (Y) ops.release(Y);
+    ops.free_work();
+    cudaStreamSynchronize(ops.st);
+    if (rc == 64) return fail(64, "TSSolve: a stage solve did not converge (or an explicit step produced NaN)");
+    if (rc == 65) return fail(65, "a callback returned an error");
+    if (rc) return fail(rc, "p4b_ts_solve_callbacks failed (%s)", p4b_last_error());
+    return 0;
+}
+
+extern "C" double p4b_ts_time_step(void) { return g_ts_time_step; }
 
 extern "C" int p4b_pattern_default_opts(p4b_pattern_opts *o) {
     if (!o) return fail(62, "null options");

@@ -8,6 +8,9 @@
 //                      derivatives, extrapolated initial guess, LTE from the next-higher difference, TSAdaptBasic.
 //                      c/ch5/output/pattern.test5 pins the restart step (Newton counts 3, 2; next step 1.10972); later
 //                      steps have no golden (checked for second-order accuracy against the oracle): parity unpinned there
+//   -ts_type rk        [PETSc] TSRK default "3bs": Bogacki-Shampine 3(2), explicit, TSAdaptBasic on the embedded 2nd-order
+//                      solution with order 3 (c/ch5/output/heat.test2 pins the step sequence); only through the
+//                      callback route (p4b_ts_solve_callbacks: c/ch5/heat.c), and only for Ydot = G(t, Y)
 //   stage solves       GMRES(30) preconditioned by a V cycle on the rediscretised, matrix-free stage operator
 //                      J = shift*I - C L9 - G'(Y) (FormIJacobianLocal / FormRHSJacobianLocal, pattern.c:202-318)
 #pragma once
@@ -18,7 +21,7 @@
 namespace p4b {
 namespace nk {
 
-enum { TS_ARKIMEX = 0, TS_BEULER = 1, TS_CN = 2, TS_BDF = 3 };
+enum { TS_ARKIMEX = 0, TS_BEULER = 1, TS_CN = 2, TS_BDF = 3, TS_RK = 4 };
 
 struct PatternOpts {
     double L, Du, Dv, phi, kappa;          // -ptn_L -ptn_Du -ptn_Dv -ptn_phi -ptn_kappa (pattern.c:47-52)
@@ -140,17 +143,18 @@ struct StageOperator {
     double *Ainv = nullptr;
     bool ready = false;
 
-    void create(Ops *o, const PatternOpts *op, int m, bool imex) {
+    // n_field != 0: a field of that many doubles in a layout only the callbacks know (one level, no multigrid)
+    void create(Ops *o, const PatternOpts *op, int m, bool imex, size_t n_field = 0) {
         ops = o; opt = op;
         no_rhs = op->no_rhsjacobian || imex;        // IMEX: the reaction is explicit, G' never enters the stage matrix
         std::vector<int> sizes{m};
-        if (op->pc_type == PC_MG)
+        if (op->pc_type == PC_MG && !n_field)
             while (sizes.back() > op->grid_x && sizes.back() % 2 == 0) sizes.push_back(sizes.back() / 2);
         lev.resize(sizes.size());
         for (size_t l = 0; l < sizes.size(); l++) {
             PLevel<Ops> &L = lev[l];
             L.m = sizes[l];
-            L.n = (size_t)2 * L.m * L.m;
+            L.n = n_field ? n_field : (size_t)2 * L.m * L.m;
             L.Y = ops->alloc(L.n); L.x = ops->alloc(L.n); L.b = ops->alloc(L.n); L.t = ops->alloc(L.n);
         }
     }
@@ -295,17 +299,20 @@ inline void lagrange_ders(int n, double t, const double *T, double *dL) {
 
 // Y0 (optional, Ops memory, 2*m*m doubles): the caller's initial state -- then the run is the caller's (pattern.c under the
 // PETSc-shaped shim prints its own banner and call-back report): only the solver's lines are printed.
+// n_field != 0 (with Y0): the state is a field of n_field doubles whose layout only the callbacks behind Ops know (the
+// method-of-lines system of any DMDA driver, e.g. c/ch5/heat.c: one component, Neumann in x, periodic in y); m is 0 then.
 template <class Ops>
 int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **Y_out, PatternResult *R,
-                  const double *Y0 = nullptr) {
+                  const double *Y0 = nullptr, size_t n_field = 0) {
     memset(R, 0, sizeof *R);
     const int mx = opt.grid_x << opt.refine, my = opt.grid_y << opt.refine;      // periodic: -da_refine doubles
-    if (mx != my) return 1;                                                      // pattern.c:89
-    const int m = mx;
+    if (!n_field && mx != my) return 1;                                          // pattern.c:89
+    if (n_field && (!Y0 || opt.pc_type == PC_MG)) return 62;
+    const int m = n_field ? 0 : mx;
     R->m = m;
     if (!Y0) pr.out("running on %d x %d grid with square cells of side h = %.6f ...", m, m, opt.L / m);      // :94-96
     StageOperator<Ops> A;
-    A.create(ops, &opt, m, opt.ts_type == TS_ARKIMEX);
+    A.create(ops, &opt, m, opt.ts_type == TS_ARKIMEX, n_field);
     const size_t n = A.lev[0].n;
     double *Y = A.lev[0].Y;
     std::vector<double *> V;
@@ -329,6 +336,7 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
         for (int i = 0; i < 4; i++) { Ys[i] = take(); FI[i] = take(); FE[i] = take(); }
         ops->set(n, 0.0, zero);
         while (t < tmax - 1e-12 * std::max(1.0, fabs(tmax)) && k < opt.ts_max_steps && !rc) {
+            ops->set_step_size(h);                           // (what TSGetTimeStep answers inside a monitor)
             ops->ts_step(k, t, Y, n);                        // [PETSc] TSMonitor: step, time, solution
             if (opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(h).c_str(), fmt_g(t).c_str());
             bool prev_accept = true;
@@ -402,6 +410,54 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
             k++;
             if (ops->error()) rc = ops->error();
         }
+        ops->set_step_size(h);
+        if (!rc) ops->ts_step(k, t, Y, n);
+        if (!rc && opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(h).c_str(), fmt_g(t).c_str());
+    } else if (opt.ts_type == TS_RK) {
+        // [PETSc] TSRK "3bs" (Bogacki & Shampine 1989): c = (0, 1/2, 3/4, 1), third-order weights = the last row,
+        // embedded second-order weights (7/24, 1/4, 1/3, 1/8); TSAdaptBasic with the order of the method (3) -- the rule
+        // c/ch5/output/heat.test2 pins (dt 0.001, 0.00226419, 0.00336791, ...; order 2 gives 0.00359127 instead)
+        static const double RA[4][4] = {{0, 0, 0, 0}, {0.5, 0, 0, 0}, {0, 0.75, 0, 0}, {2.0 / 9.0, 1.0 / 3.0, 4.0 / 9.0, 0}};
+        static const double RC[4] = {0.0, 0.5, 0.75, 1.0}, RBE[4] = {7.0 / 24.0, 0.25, 1.0 / 3.0, 0.125};
+        double *K[4], *Ynew = take(), *Yemb = take();
+        for (int i = 0; i < 4; i++) K[i] = take();
+        while (t < tmax - 1e-12 * std::max(1.0, fabs(tmax)) && k < opt.ts_max_steps && !rc) {
+            ops->set_step_size(h);
+            ops->ts_step(k, t, Y, n);
+            if (opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(h).c_str(), fmt_g(t).c_str());
+            bool prev_accept = true;
+            double hnext = h;
+            while (!rc) {
+                for (int i = 0; i < 4; i++) {
+                    ops->copy(n, Y, Z);
+                    for (int j = 0; j < i; j++)
+                        if (RA[i][j] != 0.0) ops->axpy(n, h * RA[i][j], K[j], Z);
+                    ops->set_time(t + RC[i] * h);
+                    ops->pattern_rhsfunction(m, opt, Z, K[i]);
+                }
+                ops->copy(n, Y, Ynew);
+                ops->copy(n, Y, Yemb);
+                for (int j = 0; j < 4; j++) {
+                    if (RA[3][j] != 0.0) ops->axpy(n, h * RA[3][j], K[j], Ynew);
+                    ops->axpy(n, h * RBE[j], K[j], Yemb);
+                }
+                const double enorm = sqrt(ops->wrms2(n, Ynew, Yemb, opt.ts_atol, opt.ts_rtol) / (double)n);
+                if (ops->error()) { rc = ops->error(); break; }
+                if (enorm != enorm) { rc = 64; break; }
+                if (adapt_basic(h, enorm, prev_accept, &hnext, 3)) break;
+                prev_accept = false;
+                R->rejected++;
+                h = hnext;
+            }
+            if (rc) break;
+            ops->copy(n, Ynew, Y);
+            t += h;
+            record(h, 0);
+            R->dt_last = h;
+            h = match_step(t, hnext, tmax);
+            k++;
+        }
+        ops->set_step_size(h);
         if (!rc) ops->ts_step(k, t, Y, n);
         if (!rc && opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(h).c_str(), fmt_g(t).c_str());
     } else {
@@ -477,6 +533,7 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
             };
             double dt_next = h;
             while (t < tmax - 1e-12 * std::max(1.0, fabs(tmax)) && k < opt.ts_max_steps && !rc) {
+                ops->set_step_size(h);
                 ops->ts_step(k, t, Y, n);                        // [PETSc] TSMonitor: step, time, solution
             if (opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(h).c_str(), fmt_g(t).c_str());
                 ops->copy(n, Y, Yprev);                              // lev[0].Y is the linearisation point from here on
@@ -534,6 +591,7 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
                 k++;
                 if (ops->error()) rc = ops->error();
             }
+            ops->set_step_size(dt_next);
             if (!rc) ops->ts_step(k, t, Y, n);
         if (!rc && opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(dt_next).c_str(), fmt_g(t).c_str());
         } else {
@@ -542,6 +600,7 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
             while (t < tmax - 1e-14 * std::max(1.0, fabs(tmax)) && k < opt.ts_max_steps && !rc) {
                 const double dt = std::min(opt.ts_dt, tmax - t);     // TS_EXACTFINALTIME_MATCHSTEP (:118)
                 dt_last = dt;
+                ops->set_step_size(dt);
                 ops->ts_step(k, t, Y, n);                        // [PETSc] TSMonitor: step, time, solution
             if (opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(dt).c_str(), fmt_g(t).c_str());
                 const double shift = 1.0 / (theta * dt);
@@ -573,6 +632,7 @@ int pattern_solve(Ops *ops, const PatternOpts &opt, const Printer &pr, double **
                 k++;
                 if (ops->error()) rc = ops->error();
             }
+            ops->set_step_size(dt_last);
             if (!rc) ops->ts_step(k, t, Y, n);
         if (!rc && opt.ts_monitor) pr.out("%d TS dt %s time %s", k, fmt_g(dt_last).c_str(), fmt_g(t).c_str());
         }

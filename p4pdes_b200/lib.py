@@ -233,6 +233,9 @@ _SIGS = {
                                         C.POINTER(PatternResult)]),
     "p4b_ts2d_solve": (C.c_int, [_P, C.POINTER(PatternOpts), IFUNCTION2D_FN, RHSFUNCTION2D_FN, _P, _P, C.c_size_t, LINE_FN,
                                 _P, C.POINTER(PatternResult)]),
+    "p4b_ts_solve_callbacks": (C.c_int, [_P, C.POINTER(PatternOpts), IFUNCTION2D_FN, RHSFUNCTION2D_FN, _P, _P, C.c_size_t,
+                                        LINE_FN, _P, C.POINTER(PatternResult)]),
+    "p4b_ts_time_step": (C.c_double, []),
     "p4b_sell_create": (C.c_int, [_P, C.c_int, _P, _P, _P, C.POINTER(_P)]),
     "p4b_sell_spmv": (C.c_int, [_P, _D, _D]),
     "p4b_sell_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

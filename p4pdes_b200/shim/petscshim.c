@@ -138,11 +138,35 @@ PetscErrorCode PetscFinalize(void) {
     return 0;
 }
 
+/* [PETSc] PetscVSNPrintf: a plain %g whose output shows neither '.' nor an exponent gets a '.' appended ("t0=0." in
+ * c/ch5/output/heat.test1:1, "time 0." in every TS monitor line), so that reals read as reals.  The same is done here: each
+ * plain %g is bracketed by two marker bytes in a copy of the format, and the bracketed text is fixed up after vsnprintf. */
+static void petsc_vprintf(FILE *f, const char *format, va_list ap) {
+    char fmt[1024], buf[4096];
+    size_t k = 0;
+    for (const char *p = format; *p && k + 6 < sizeof fmt; p++) {
+        if (p[0] == '%' && p[1] == '%') { fmt[k++] = *p++; fmt[k++] = *p; continue; }
+        if (p[0] == '%' && p[1] == 'g') { fmt[k++] = 1; fmt[k++] = '%'; fmt[k++] = 'g'; fmt[k++] = 2; p++; continue; }
+        fmt[k++] = *p;
+    }
+    fmt[k] = 0;
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    for (const char *p = buf; *p; p++) {
+        if (*p != 1) { fputc(*p, f); continue; }
+        int real = 0;
+        for (p++; *p && *p != 2; p++) {
+            if (*p == '.' || *p == 'e' || *p == 'n' || *p == 'i') real = 1;      /* 1.5, 1e-05, nan, inf */
+            fputc(*p, f);
+        }
+        if (!real) fputc('.', f);
+        if (!*p) break;
+    }
+}
 PetscErrorCode PetscPrintf(MPI_Comm comm, const char format[], ...) {
     (void)comm;
     va_list ap;
     va_start(ap, format);
-    vprintf(format, ap);
+    petsc_vprintf(stdout, format, ap);
     va_end(ap);
     fflush(stdout);
     return 0;
@@ -383,11 +407,11 @@ static PetscErrorCode da_create(int dim, const DMBoundaryType *b, DMDAStencilTyp
             SHIM_ERR(56, "DM_BOUNDARY_NONE and DM_BOUNDARY_PERIODIC grids are provided by the shim");
         }
     }
-    if (dim == 2 ? (d->b[0] != d->b[1]) : (d->b[0] == DM_BOUNDARY_PERIODIC)) {
+    if (dim != 2 && (d->b[0] == DM_BOUNDARY_PERIODIC || d->b[1] == DM_BOUNDARY_PERIODIC || d->b[2] == DM_BOUNDARY_PERIODIC)) {
         free(d);
-        SHIM_ERR(56, "periodic DMDAs are provided in 2-D, periodic in both directions (pattern.c:79-84)");
+        SHIM_ERR(56, "periodic DMDAs are provided in 2-D (pattern.c:79-84, heat.c:60-65)");
     }
-    if (dof < 1 || (dof > 1 && d->b[0] != DM_BOUNDARY_PERIODIC)) {
+    if (dof < 1 || (dof > 1 && !(d->b[0] == DM_BOUNDARY_PERIODIC && d->b[1] == DM_BOUNDARY_PERIODIC))) {
         free(d);
         SHIM_ERR(56, "dof > 1 is provided on the periodic 2-D DMDA only");
     }
@@ -1225,7 +1249,7 @@ PetscErrorCode PetscViewerASCIIPrintf(PetscViewer viewer, const char format[], .
     va_list ap;
     for (int i = 0; i < viewer->tab; i++) fputs("  ", stdout);
     va_start(ap, format);
-    vprintf(format, ap);
+    petsc_vprintf(stdout, format, ap);
     va_end(ap);
     return 0;
 }
@@ -1589,6 +1613,8 @@ static PetscErrorCode ts_solve_multi_gpu(int ngpu, int m, const p4b_pattern_opts
 
 PetscErrorCode SNESSolve(SNES snes, Vec b, Vec x) {
     if (b) SHIM_ERR(56, "SNESSolve with a right-hand side is not provided");
+    if (snes->dm && (snes->dm->b[0] == DM_BOUNDARY_PERIODIC || snes->dm->b[1] == DM_BOUNDARY_PERIODIC))
+        SHIM_ERR(56, "SNESSolve is provided on DM_BOUNDARY_NONE DMDAs (fish.c:203-213, minimal.c:130-134)");
     if (!strcmp(snes->type, SNESNEWTONLS)) return snes_solve_newtonls(snes, x);
     if (strcmp(snes->type, SNESKSPONLY))
         SHIM_ERR(56, "-snes_type: ksponly (fish.c:230-231) and newtonls (minimal.c) are provided by the shim");
@@ -1811,6 +1837,10 @@ struct _p_TS {
     double t0, max_time, dt, rtol, atol;
     int max_steps, monitor, eft;
     SNES snes;               /* holds the KSP / PC / SNES options of the stage solves */
+    int nmon;                /* TSMonitorSet monitors (heat.c:72): run at step 0 and after every accepted step */
+    struct { PetscErrorCode (*f)(TS, PetscInt, PetscReal, Vec, void *); void *ctx; PetscErrorCode (*destroy)(void **); } mon[5];
+    double tcur;             /* time of the monitor call in progress (TSGetTime); t0 outside a solve */
+    int in_solve;
 };
 
 PetscErrorCode DMDASetFieldName(DM da, PetscInt nf, const char name[]) { (void)da; (void)nf; (void)name; return 0; }
@@ -1897,25 +1927,32 @@ PetscErrorCode TSDestroy(TS *ts) {
     return 0;
 }
 
-/* ghosted (width 1, periodic in both directions) host copy of a field with dof components and a[j][i] views of it
- * that are valid for j, i in [-1, m]: what DMGlobalToLocal + DMDAVecGetArray hand a periodic callback */
+/* ghosted (width 1) host copy of a field with dof components and a[j][i] views of it that are valid for j, i in [-1, m]:
+ * what DMGlobalToLocal + DMDAVecGetArray hand a callback.  Ghost nodes of a periodic direction hold the wrapped values; a
+ * DM_BOUNDARY_NONE direction has no ghost nodes in PETSc -- the cells exist here and hold zeros, which no correct callback
+ * reads (heat.c:152-155 mirrors at i = 0 and i = mx-1 instead). */
 struct ghosted { double *buf; double **rows; void *a; };
-static int ghosted_make(const double *Y, int mx, int my, int dof, struct ghosted *g) {
+static int ghosted_make(const double *Y, int mx, int my, int dof, int px, int py, struct ghosted *g) {
     const int gx = mx + 2, gy = my + 2;
-    g->buf = (double *)malloc(sizeof(double) * (size_t)gx * gy * dof);
+    g->buf = (double *)calloc((size_t)gx * gy * dof, sizeof(double));
     g->rows = (double **)malloc(sizeof(double *) * (size_t)gy);
     if (!g->buf || !g->rows) return 1;
     for (int jj = 0; jj < gy; jj++) {
-        const int j = (jj - 1 + my) % my;
         double *row = g->buf + (size_t)jj * gx * dof;
-        memcpy(row + dof, Y + (size_t)j * mx * dof, sizeof(double) * (size_t)mx * dof);
-        memcpy(row, Y + ((size_t)j * mx + (mx - 1)) * dof, sizeof(double) * dof);
-        memcpy(row + (size_t)(mx + 1) * dof, Y + (size_t)j * mx * dof, sizeof(double) * dof);
         g->rows[jj] = row + dof;                     /* a[j][0] is the first owned node; a[j][-1] the left ghost */
+        if (!py && (jj == 0 || jj == gy - 1)) continue;
+        const int j = (jj - 1 + my) % my;
+        memcpy(row + dof, Y + (size_t)j * mx * dof, sizeof(double) * (size_t)mx * dof);
+        if (px) {
+            memcpy(row, Y + ((size_t)j * mx + (mx - 1)) * dof, sizeof(double) * dof);
+            memcpy(row + (size_t)(mx + 1) * dof, Y + (size_t)j * mx * dof, sizeof(double) * dof);
+        }
     }
     g->a = g->rows + 1;                              /* a[-1] is the lower ghost row */
     return 0;
 }
+#define DM_PX(dm) ((dm)->b[0] == DM_BOUNDARY_PERIODIC)
+#define DM_PY(dm) ((dm)->b[1] == DM_BOUNDARY_PERIODIC)
 static void ghosted_free(struct ghosted *g) { free(g->buf); free(g->rows); g->buf = NULL; g->rows = NULL; }
 
 /* the user's G(t, Y) and F(t, Y, Ydot) on host arrays of the whole grid */
@@ -1923,7 +1960,7 @@ static PetscErrorCode ts_eval_rhs(DM dm, double t, const double *Y, double *G) {
     DMDALocalInfo info;
     struct ghosted gY;
     PetscCall(DMDAGetLocalInfo(dm, &info));
-    if (ghosted_make(Y, dm->M[0], dm->M[1], dm->dof, &gY)) SHIM_ERR(55, "out of host memory");
+    if (ghosted_make(Y, dm->M[0], dm->M[1], dm->dof, DM_PX(dm), DM_PY(dm), &gY)) SHIM_ERR(55, "out of host memory");
     void *aG = make_tables_dof(2, dm->M, dm->dof, G);
     const double t0 = wall();
     PetscErrorCode rc = dm->rhsfunc(&info, t, gY.a, aG, dm->rhsfuncctx);
@@ -1935,9 +1972,13 @@ static PetscErrorCode ts_eval_rhs(DM dm, double t, const double *Y, double *G) {
 static PetscErrorCode ts_eval_ifunc(DM dm, double t, const double *Y, const double *Ydot, double *F) {
     DMDALocalInfo info;
     struct ghosted gY, gD;
+    if (!dm->ifunc) {                        /* no IFunction registered: [PETSc] F = Ydot, the system is Ydot = G(t, Y) */
+        memcpy(F, Ydot, sizeof(double) * (size_t)dm->M[0] * dm->M[1] * dm->dof);
+        return 0;
+    }
     PetscCall(DMDAGetLocalInfo(dm, &info));
-    if (ghosted_make(Y, dm->M[0], dm->M[1], dm->dof, &gY)) SHIM_ERR(55, "out of host memory");
-    if (ghosted_make(Ydot, dm->M[0], dm->M[1], dm->dof, &gD)) SHIM_ERR(55, "out of host memory");
+    if (ghosted_make(Y, dm->M[0], dm->M[1], dm->dof, DM_PX(dm), DM_PY(dm), &gY)) SHIM_ERR(55, "out of host memory");
+    if (ghosted_make(Ydot, dm->M[0], dm->M[1], dm->dof, DM_PX(dm), DM_PY(dm), &gD)) SHIM_ERR(55, "out of host memory");
     void *aF = make_tables_dof(2, dm->M, dm->dof, F);
     const double t0 = wall();
     PetscErrorCode rc = dm->ifunc(&info, t, gY.a, gD.a, aF, dm->ifuncctx);
@@ -1998,18 +2039,21 @@ static PetscErrorCode ts_solve_general(TS ts, Vec x, struct ts_work *W, p4b_patt
     KSP ksp = &ts->snes->ksp;
     const size_t n = x->n;
     char msg[768];
-    if (o->pc_type != 0) {
+    const int pattern_shape = dm->dof == 2 && DM_PX(dm) && DM_PY(dm) && dm->M[0] == dm->M[1];
+    if (o->pc_type != 0 && o->ts_type != 4) {
         snprintf(msg, sizeof msg, "%s.  Arbitrary callbacks run through the matrix-free route (stage operator = differenced "
                  "residual, no Jacobian matrix, hence no multigrid): pass -pc_type none", why);
         SHIM_ERR(56, msg);
     }
+    if (o->ts_type == 4 && dm->ifunc)
+        SHIM_ERR(56, "-ts_type rk integrates Ydot = G(t, Y): an IFunction is registered ([PETSc] TSRK refuses implicit systems too)");
     /* F(Y, a D) - F(Y, 0) must be a (F(Y, D) - F(Y, 0)) and must not depend on Y */
     double *Y = W->Y, *D = W->D, *F0 = W->Fu, *F1 = W->Fd;
     double *F2 = (double *)malloc(sizeof(double) * n), *T = (double *)malloc(sizeof(double) * n);
     if (!F2 || !T) { free(F2); free(T); SHIM_ERR(55, "out of host memory"); }
     PetscErrorCode rc = 0;
     double worst = 0.0, scale = 1.0;
-    do {
+    if (dm->ifunc) do {
         memset(T, 0, sizeof(double) * n);
         if ((rc = ts_eval_ifunc(dm, 0.0, Y, T, F0))) break;
         if ((rc = ts_eval_ifunc(dm, 0.0, Y, D, F1))) break;
@@ -2052,7 +2096,8 @@ static PetscErrorCode ts_solve_general(TS ts, Vec x, struct ts_work *W, p4b_patt
     p4b_pattern_result *R = W->R = (p4b_pattern_result *)calloc(1, sizeof *R);
     if (!R) SHIM_ERR(55, "out of host memory");
     fflush(stdout);
-    int prc = p4b_ts2d_solve(g_ctx, o, ts_ifn, ts_gfn, ts, x->h, n, newton_line, NULL, R);
+    int prc = pattern_shape ? p4b_ts2d_solve(g_ctx, o, ts_ifn, ts_gfn, ts, x->h, n, newton_line, NULL, R)
+                            : p4b_ts_solve_callbacks(g_ctx, o, ts_ifn, ts_gfn, ts, x->h, n, newton_line, NULL, R);
     fflush(stdout);
     if (prc) return PetscShimError(PETSC_COMM_SELF, __LINE__, __func__, __FILE__, prc, p4b_last_error());
     x->valid = LOC_HOST;
@@ -2109,14 +2154,72 @@ static PetscErrorCode ts_model_deviation(DM dm, const p4b_pattern_opts *o, int m
     return 0;
 }
 
+/* TSSolve on a 2-D DMDA that is not pattern.c's (any dof, any boundary types) -- c/ch5/heat.c: one component, Neumann in x,
+ * periodic in y, RHSFunction + RHSJacobian, no IFunction.  The library has no kernels for such a system, so this is the
+ * callback route from the start: G (and F, if registered) are the user's host callbacks on ghosted a[j][i] views, the
+ * integrators and all vector algebra run on the device, implicit stages are solved matrix-free (Newton + GMRES on the
+ * differenced residual: -pc_type none; the registered Jacobian callback is not called).  -ts_type rk is [PETSc]'s
+ * default TSRK scheme 3bs with its adaptivity (c/ch5/output/heat.test2). */
+static PetscErrorCode ts_solve_any_dmda(TS ts, Vec x, struct ts_work *W) {
+    DM dm = ts->dm;
+    KSP ksp = &ts->snes->ksp;
+    PC pc = &ksp->pc;
+    char msg[256];
+    if (!dm->rhsfunc) SHIM_ERR(73, "TSSolve: call DMDATSSetRHSFunctionLocal()");
+    p4b_pattern_opts o;
+    P4B(p4b_pattern_default_opts(&o));
+    if (!strcmp(ts->type, TSARKIMEX)) o.ts_type = 0;
+    else if (!strcmp(ts->type, TSBEULER)) o.ts_type = 1;
+    else if (!strcmp(ts->type, TSCN)) o.ts_type = 2;
+    else if (!strcmp(ts->type, TSBDF)) o.ts_type = 3;
+    else if (!strcmp(ts->type, TSRK)) o.ts_type = 4;
+    else {
+        snprintf(msg, sizeof msg, "-ts_type %s is not provided on the device path (arkimex, beuler, cn, bdf, rk are)", ts->type);
+        SHIM_ERR(56, msg);
+    }
+    if (o.ts_type == 4 && opt_value("-ts_rk_type") && strcmp(opt_value("-ts_rk_type"), "3bs"))
+        SHIM_ERR(56, "-ts_rk_type: 3bs ([PETSc]'s default) is the explicit scheme provided");
+    if (ts->t0 != 0.0) SHIM_ERR(56, "TSSolve: the device path starts at t = 0 (heat.c:77)");
+    if (ts->eft != TS_EXACTFINALTIME_MATCHSTEP)
+        SHIM_ERR(56, "TSSolve: TS_EXACTFINALTIME_MATCHSTEP is what the device path provides (heat.c:80)");
+    if (o.ts_type != 4) {
+        if (!pc->type[0])
+            SHIM_ERR(56, "PETSc's default PC (ILU(0) on one rank) is sequential and not provided on the device: pass -pc_type none "
+                         "(the stage solves of this route are matrix-free)");
+        if (!strcmp(pc->type, PCNONE)) o.pc_type = 0;
+        else SHIM_ERR(56, "TSSolve on this DMDA: the stage operator is the differenced residual (no matrix): -pc_type none");
+        if (strcmp(ksp->type, KSPGMRES)) SHIM_ERR(56, "TSSolve: the stage solves are GMRES ([PETSc] default)");
+    } else o.pc_type = 0;
+    PetscCall(ensure_ctx());
+    const size_t n = x->n;
+    PetscCall(vec_to_host(x));
+    W->Y = (double *)calloc(n, sizeof(double)); W->D = (double *)calloc(n, sizeof(double));
+    W->Fu = (double *)malloc(sizeof(double) * n); W->Fd = (double *)malloc(sizeof(double) * n);
+    if (!W->Y || !W->D || !W->Fu || !W->Fd) SHIM_ERR(55, "out of host memory");
+    unsigned long long lcg = 0x9E3779B97F4A7C15ULL;
+    for (size_t i = 0; i < n; i++) {             /* a generic state and Ydot for the M Ydot + f(Y) check of an IFunction */
+        lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
+        W->Y[i] = x->h[i] + 0.05 * ((double)(lcg >> 11) / 9007199254740992.0 - 0.5);
+        lcg = lcg * 6364136223846793005ULL + 1442695040888963407ULL;
+        W->D[i] = (double)(lcg >> 11) / 9007199254740992.0 - 0.5;
+    }
+    const double t_start = wall();
+    PetscErrorCode rc = ts_solve_general(ts, x, W, &o, "this DMDA is not pattern.c's");
+    g_t_snes += wall() - t_start;
+    if (!rc)
+        fprintf(stderr, "[p4b200] TS: callbacks evaluated on the host (no kernels for this system), integrator and vector algebra "
+                        "on the device%s.\n", o.ts_type == 4 ? "" : ", matrix-free stage operator");
+    return rc;
+}
+
 static PetscErrorCode ts_solve(TS ts, Vec x, struct ts_work *W) {
     DM dm = ts->dm;
     KSP ksp = &ts->snes->ksp;
     PC pc = &ksp->pc;
     char msg[512];
     if (!dm) SHIM_ERR(73, "TSSolve: call TSSetDM() first");
-    if (dm->dim != 2 || dm->dof != 2 || dm->b[0] != DM_BOUNDARY_PERIODIC || dm->b[1] != DM_BOUNDARY_PERIODIC)
-        SHIM_ERR(56, "TSSolve is provided for the periodic 2-D DMDA with two components (pattern.c:79-84)");
+    if (dm->dim != 2) SHIM_ERR(56, "TSSolve is provided for 2-D DMDAs (pattern.c:79-84, heat.c:60-65)");
+    if (dm->dof != 2 || !DM_PX(dm) || !DM_PY(dm)) return ts_solve_any_dmda(ts, x, W);
     if (dm->M[0] != dm->M[1]) SHIM_ERR(56, "TSSolve: the device path needs mx == my (pattern.c:89)");
     if (!dm->ifunc || !dm->rhsfunc) SHIM_ERR(73, "TSSolve: call DMDATSSetIFunctionLocal() and DMDATSSetRHSFunctionLocal()");
     if (!dm->ijac && !ts->snes->fd_color)
@@ -2246,7 +2349,7 @@ static PetscErrorCode ts_solve(TS ts, Vec x, struct ts_work *W) {
         struct _p_Mat P;
         const double t_jac0 = wall();
         PetscCall(DMDAGetLocalInfo(dm, &info));
-        if (ghosted_make(Y, m, m, 2, &W->gY) || ghosted_make(D, m, m, 2, &W->gD)) SHIM_ERR(55, "out of host memory");
+        if (ghosted_make(Y, m, m, 2, 1, 1, &W->gY) || ghosted_make(D, m, m, 2, 1, 1, &W->gD)) SHIM_ERR(55, "out of host memory");
         memset(&chk, 0, sizeof chk);
         chk.m = m; chk.shift = 1.0 / ts->dt; chk.C[0] = o.Du / (6.0 * h * h); chk.C[1] = o.Dv / (6.0 * h * h);
         chk.phi = o.phi; chk.kappa = o.kappa; chk.Y = Y;
@@ -2340,6 +2443,37 @@ static PetscErrorCode ts_solve(TS ts, Vec x, struct ts_work *W) {
     return 0;
 }
 
+/* [PETSc] TSMonitorSet (heat.c:72): user monitors run at step 0 and after every accepted step with the step number, the time
+ * and the solution; inside one, TSGetDM / TSGetTime / TSGetTimeStep answer for the solve in progress (heat.c:117,133). */
+PetscErrorCode TSMonitorSet(TS ts, PetscErrorCode (*monitor)(TS, PetscInt, PetscReal, Vec, void *), void *mctx,
+                            PetscErrorCode (*mdestroy)(void **)) {
+    if (ts->nmon >= 5) SHIM_ERR(63, "too many monitors set");
+    ts->mon[ts->nmon].f = monitor;
+    ts->mon[ts->nmon].ctx = mctx;
+    ts->mon[ts->nmon].destroy = mdestroy;
+    ts->nmon++;
+    return 0;
+}
+PetscErrorCode TSGetTime(TS ts, PetscReal *t) { *t = ts->in_solve ? ts->tcur : ts->t0; return 0; }
+PetscErrorCode TSGetMaxTime(TS ts, PetscReal *maxtime) { *maxtime = ts->max_time; return 0; }
+PetscErrorCode TSGetTimeStep(TS ts, PetscReal *dt) { *dt = ts->in_solve ? p4b_ts_time_step() : ts->dt; return 0; }
+PetscErrorCode TSGetDM(TS ts, DM *dm) { *dm = ts->dm; return 0; }
+
+static int ts_step_dispatch(void *user, int step, double t, const double *Y, size_t n) {
+    TS ts = (TS)user;
+    if ((g_tsbin.ft || g_tsbin.fu) && ts_binary_monitor(NULL, step, t, Y, n)) return 1;
+    if (!ts->nmon) return 0;
+    struct _p_Vec v;
+    memset(&v, 0, sizeof v);
+    v.n = n; v.dm = ts->dm; v.h = (double *)Y; v.valid = LOC_HOST;
+    ts->tcur = t;
+    PetscErrorCode rc = 0;
+    for (int i = 0; i < ts->nmon && !rc; i++) rc = ts->mon[i].f(ts, step, t, &v, ts->mon[i].ctx);
+    free(v.tables);
+    fflush(stdout);
+    return rc != 0;
+}
+
 PetscErrorCode TSSolve(TS ts, Vec x) {
     struct ts_work W;
     memset(&W, 0, sizeof W);
@@ -2350,10 +2484,12 @@ PetscErrorCode TSSolve(TS ts, Vec x) {
         g_tsbin.ft = ft ? fopen(ft, "wb") : NULL;
         g_tsbin.fu = fu ? fopen(fu, "wb") : NULL;
         if ((ft && !g_tsbin.ft) || (fu && !g_tsbin.fu)) SHIM_ERR(65, "cannot open the binary viewer's file for writing");
-        if (g_tsbin.ft || g_tsbin.fu) P4B(p4b_set_ts_step_monitor(ts_binary_monitor, NULL));
+        if (g_tsbin.ft || g_tsbin.fu || ts->nmon) P4B(p4b_set_ts_step_monitor(ts_step_dispatch, ts));
     }
+    ts->in_solve = 1;
     PetscErrorCode rc = ts_solve(ts, x, &W);
-    if (g_tsbin.ft || g_tsbin.fu) {
+    ts->in_solve = 0;
+    if (g_tsbin.ft || g_tsbin.fu || ts->nmon) {
         p4b_set_ts_step_monitor(NULL, NULL);
         if (g_tsbin.ft) fclose(g_tsbin.ft);
         if (g_tsbin.fu) fclose(g_tsbin.fu);
