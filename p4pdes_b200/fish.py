@@ -163,6 +163,11 @@ class Context:
         L.check(self.lib.p4b_minimal_jacobian_fd(self.h, mx, my, q, u.data_ptr(), g.data_ptr(), F0.data_ptr(),
                                                  vals.data_ptr()))
 
+    def sell_matrix(self, rowptr, colind, vals):
+        """An assembled matrix on this device ([PETSc] MATSELL), from host CSR arrays."""
+        from .callbacks import SellMatrix
+        return SellMatrix(self, rowptr, colind, vals)
+
     def poisson_stencil9(self, mx, my, Lx, Ly, cx, cy, vals):
         L.check(self.lib.p4b_poisson_stencil9(self.h, mx, my, Lx, Ly, cx, cy, vals.data_ptr()))
 

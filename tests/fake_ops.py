@@ -151,6 +151,15 @@ class FakeOps:
         v[3 * (dj + 1) + (di + 1), A.row] = A.data
         vals.a[:] = v.ravel()
 
+    def sell_matrix(self, rowptr, colind, vals):
+        A = sp.csr_matrix((vals, colind, rowptr), shape=(len(rowptr) - 1, len(rowptr) - 1))
+
+        class _M:
+            def mult(self, x, y):
+                y.a[:] = A @ x.a
+                return y
+        return _M()
+
     def poisson_stencil9(self, mx, my, Lx, Ly, cx, cy, vals):
         self._count("poisson_stencil9")
         A = fo.jacobian(fo.Grid(2, (mx, my, 1), (Lx, Ly, 1.0)), (cx, cy, 1.0)).tocoo()
