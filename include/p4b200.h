@@ -497,6 +497,17 @@ int p4b_ts_solve_callbacks(p4b_ctx *ctx, const p4b_pattern_opts *opts, p4b_ifunc
                            p4b_rhsfunction2d_fn rhsfunction, void *user, double *Y_inout_host, size_t n, p4b_line_fn line,
                            void *line_ctx, p4b_pattern_result *result);
 double p4b_ts_time_step(void);
+/* ---- c/ch5/heat.c device-resident.  p4b_heat_rhs = FormRHSFunctionLocal (heat.c:141-163): G = D0 lap_h(u) + f on the unit
+ * square, mx nodes with hx = 1/(mx-1) and the Neumann data through mirrored ghost values in x, my nodes with hy = 1/my
+ * periodic in y, f_source and gamma_neumann of heat.c:16-23; u, G device arrays of mx*my doubles, n = j mx + i.
+ * p4b_heat_jac_apply = (shift I - dG/du) X, the rows of FormRHSJacobianLocal (heat.c:166-208) applied matrix-free.
+ * p4b_heat_solve = TSSolve for that system (Ydot = G(u), heat.c:66-92) with the steppers of p4b_ts_solve_callbacks, G and
+ * the stage operator being these kernels; one level, so opts->pc_type must be 0 unless ts_type is rk.  The shim calls it
+ * when the registered callback IS this function (probed, and re-checked at the final state). ---- */
+int p4b_heat_rhs(p4b_ctx *ctx, int mx, int my, double D0, const double *u, double *G);
+int p4b_heat_jac_apply(p4b_ctx *ctx, int mx, int my, double D0, double shift, const double *X, double *JX);
+int p4b_heat_solve(p4b_ctx *ctx, const p4b_pattern_opts *opts, int mx, int my, double D0, double *Y_inout_host,
+                   p4b_line_fn line, void *line_ctx, p4b_pattern_result *result);
 typedef struct p4b_sell p4b_sell;
 int p4b_sell_create(p4b_ctx *ctx, int nrows, const int *rowptr_host, const int *colind_host, const double *vals_host,
                     p4b_sell **A);

@@ -476,3 +476,29 @@ struct HostCallbackPatternOps : HostOps {
         axpby(n, 1.0 / h, out, -1.0 / h, wR0.data(), out);
     }
 };
+
+// c/ch5/heat.c with plain loops: the CPU counterpart of HeatOps in p4pdes_b200/csrc/nk_device.cu (heat.c:141-163: G; :166-208:
+// the rows of dG/du, applied without being stored)
+struct HostHeatOps : HostOps {
+    int mx = 0, my = 0;
+    double D0 = 1.0;
+    void heat(int mode, double shift, const double *u, double *out) {
+        const double hx = 1.0 / (mx - 1), hy = 1.0 / my, PI = 3.14159265358979323846;
+        for (int j = 0; j < my; j++)
+            for (int i = 0; i < mx; i++) {
+                const int n = j * mx + i, js = j == 0 ? my - 1 : j - 1, jn = j == my - 1 ? 0 : j + 1;
+                const double x = hx * i, y = hy * j, c = u[n];
+                double ul = i == 0 ? u[n + 1] : u[n - 1];
+                if (i == 0 && mode == 0) ul += 2.0 * hx * sin(6.0 * PI * y);
+                const double ur = i == mx - 1 ? u[n - 1] : u[n + 1];
+                const double lap = (ul - 2.0 * c + ur) / (hx * hx) + (u[js * mx + i] - 2.0 * c + u[jn * mx + i]) / (hy * hy);
+                out[n] = mode == 0 ? D0 * lap + 3.0 * exp(-25.0 * (x - 0.6) * (x - 0.6)) * sin(2.0 * PI * y) : shift * c - D0 * lap;
+            }
+    }
+    void pattern_ifunction(int, const PO &, const double *, const double *Ydot, double *F) { copy((size_t)mx * my, Ydot, F); }
+    void pattern_rhsfunction(int, const PO &, const double *Y, double *G) { heat(0, 0.0, Y, G); }
+    void pattern_jac_apply(int, const PO &, double shift, const double *Y, const double *X, double *out) {
+        if (Y) heat(1, shift, X, out);
+        else axpby((size_t)mx * my, shift, X, 0.0, nullptr, out);
+    }
+};

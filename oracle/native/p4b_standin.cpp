@@ -269,6 +269,42 @@ int p4b_ts_solve_callbacks(p4b_ctx *c, const p4b_pattern_opts *opts, p4b_ifuncti
     return 0;
 }
 double p4b_ts_time_step(void) { return HostOps::ts_h(); }
+int p4b_heat_rhs(p4b_ctx *, int mx, int my, double D0, const double *u, double *G) {
+    HostHeatOps ops;
+    ops.mx = mx; ops.my = my; ops.D0 = D0;
+    ops.heat(0, 0.0, u, G);
+    return 0;
+}
+int p4b_heat_jac_apply(p4b_ctx *, int mx, int my, double D0, double shift, const double *X, double *JX) {
+    HostHeatOps ops;
+    ops.mx = mx; ops.my = my; ops.D0 = D0;
+    ops.heat(1, shift, X, JX);
+    return 0;
+}
+int p4b_heat_solve(p4b_ctx *c, const p4b_pattern_opts *opts, int mx, int my, double D0, double *Y_inout_host, p4b_line_fn line,
+                   void *line_ctx, p4b_pattern_result *result) {
+    if (!c || !opts || !Y_inout_host || !result) return fail(62, "p4b_heat_solve: null argument");
+    nk::PatternOpts o = *reinterpret_cast<const nk::PatternOpts *>(opts);
+    if (o.ts_type < nk::TS_ARKIMEX || o.ts_type > nk::TS_RK) return fail(62, "ts_type: arkimex (0), beuler (1), cn (2), bdf (3), rk (4)");
+    if (o.pc_type != nk::PC_NONE && o.ts_type != nk::TS_RK) return fail(56, "p4b_heat_solve: -pc_type none only");
+    o.pc_type = nk::PC_NONE;
+    o.no_rhsjacobian = 0;
+    const size_t n = (size_t)mx * my;
+    HostHeatOps ops;
+    ops.cgs = g_cgs != 0;
+    ops.mx = mx; ops.my = my; ops.D0 = D0;
+    nk::Printer pr{line, line_ctx};
+    double *Y = nullptr;
+    std::vector<double> Y0(Y_inout_host, Y_inout_host + n);
+    nk::PatternResult &R = *reinterpret_cast<nk::PatternResult *>(result);
+    int rc = nk::pattern_solve(&ops, o, pr, &Y, &R, Y0.data(), n);
+    if (!rc && ops.error()) rc = ops.error();
+    if (!rc) memcpy(Y_inout_host, Y, sizeof(double) * n);
+    if (Y) ops.release(Y);
+    if (rc == 64) return fail(64, "TSSolve: a stage solve did not converge (or an explicit step produced NaN)");
+    if (rc) return fail(rc, "p4b_heat_solve failed");
+    return 0;
+}
 
 // ---- fish.c: the operator the shim's Mat type recognised (finest level) and a Jacobi-preconditioned CG on it.  There is
 // NO multigrid here: iteration counts are not the device path's; what the stand-in lets a CPU test see is everything

@@ -92,6 +92,8 @@ int launch_minimal_function(cudaStream_t st, int mx, int my, int zs, int zm, dou
 int launch_pattern_init(cudaStream_t st, int mx, int my, double L, double *Y, const double *noise = nullptr,
                         double level = 0.0, int ys = 0, int ym = -1);
 int launch_pattern_rhs(cudaStream_t st, int n, double phi, double kappa, const double *Y, double *G);
+int launch_heat_rhs(cudaStream_t st, int mx, int my, double D0, const double *u, double *G);
+int launch_heat_jac_apply(cudaStream_t st, int mx, int my, double D0, double shift, const double *X, double *out);
 int launch_pattern_ifunction(cudaStream_t st, int mx, int my, double Cu, double Cv, int use_shift, double shift,
                              const double *Y, const double *Ydot, double *F, int ywrap = 1);
 struct Sell;

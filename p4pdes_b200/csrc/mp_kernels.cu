@@ -7,6 +7,8 @@
 //   pattern_ifunction_kernel  c/ch5/pattern.c:242-267  FormIFunctionLocal  F = Ydot - C L9(Y), periodic, (u,v)
 //                             interleaved; with Ydot := shift*Y it is the action of FormIJacobianLocal (:274-318)
 //   pattern_init_kernel       c/ch5/pattern.c:146-179  InitialState (no noise)
+//   heat_rhs_kernel           c/ch5/heat.c:141-163     FormRHSFunctionLocal (5-point Laplacian, Neumann in x through
+//                             mirrored ghosts, periodic in y, source f); without the data: the action of :166-208
 //   sell_spmv_kernel          [PETSc] MatMult_SeqAIJ for assembled Jacobians, as SELL-32 (sliced ELLPACK)       [K6]
 //
 // All fp64 and HBM-bound; none is a dense contraction, so no tensor cores.
@@ -159,6 +161,43 @@ int launch_pattern_init(cudaStream_t st, int mx, int my, double L, double *Y, co
     P4B_LAUNCH_CHECK();
     return 0;
 }
+// ---------------------------------------------------------------------------------------------- heat.c
+// MODE 0: G = D0 (uxx + uyy) + f(x, y), with ul = u[i+1] + 2 hx gamma(y) at i = 0 and ur = u[i-1] at i = mx-1
+//         (c/ch5/heat.c:141-163; f_source :16-19, gamma_neumann :21-23; hx = 1/(mx-1), hy = 1/my, :99-103)
+// MODE 1: out = shift u - D0 (uxx + uyy) with the homogeneous mirror conditions: the stage operator shift I - dG/du,
+//         i.e. the rows FormRHSJacobianLocal inserts (:166-208), applied without being stored
+template <int MODE>
+__global__ void __launch_bounds__(256) heat_rhs_kernel(int mx, int my, double D0, double shift, const double *__restrict__ u,
+                                                        double *__restrict__ out) {
+    const int n = blockIdx.x * 256 + threadIdx.x;
+    if (n >= mx * my) return;
+    const int j = n / mx, i = n - j * mx;
+    const double hx = 1.0 / (double)(mx - 1), hy = 1.0 / (double)my;
+    const double x = hx * i, y = hy * j;
+    const double c = u[n];
+    double ul, ur;
+    if (i == 0) {
+        ul = u[n + 1];
+        if (MODE == 0) ul += 2.0 * hx * sin(6.0 * M_PI * y);
+    } else ul = u[n - 1];
+    ur = (i == mx - 1) ? u[n - 1] : u[n + 1];
+    const int js = (j == 0) ? my - 1 : j - 1, jn = (j == my - 1) ? 0 : j + 1;
+    const double uxx = (ul - 2.0 * c + ur) / (hx * hx);
+    const double uyy = (u[js * mx + i] - 2.0 * c + u[jn * mx + i]) / (hy * hy);
+    if (MODE == 0) out[n] = D0 * (uxx + uyy) + 3.0 * exp(-25.0 * (x - 0.6) * (x - 0.6)) * sin(2.0 * M_PI * y);
+    else out[n] = shift * c - D0 * (uxx + uyy);
+}
+int launch_heat_rhs(cudaStream_t st, int mx, int my, double D0, const double *u, double *G) {
+    heat_rhs_kernel<0><<<(mx * my + 255) / 256, 256, 0, st>>>(mx, my, D0, 0.0, u, G);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+int launch_heat_jac_apply(cudaStream_t st, int mx, int my, double D0, double shift, const double *X, double *out) {
+    heat_rhs_kernel<1><<<(mx * my + 255) / 256, 256, 0, st>>>(mx, my, D0, shift, X, out);
+    P4B_LAUNCH_CHECK();
+    return 0;
+}
+
 int launch_pattern_rhs(cudaStream_t st, int n, double phi, double kappa, const double *Y, double *G) {
     pattern_rhs_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, phi, kappa, reinterpret_cast<const double2 *>(Y),
                                                           reinterpret_cast<double2 *>(G));

@@ -444,6 +444,22 @@ struct CallbackPatternOps : DeviceOps {
     }
 };
 
+// c/ch5/heat.c device-resident: G is the library's kernel (recognised by the caller: the shim probes the registered
+// FormRHSFunctionLocal against it), F = Ydot (no IFunction), and the stage operator shift I - dG/du is applied matrix-free by
+// the same kernel without its data -- exact, where the callback route differences the residual.  One level: -pc_type none.
+struct HeatOps : DeviceOps {
+    int mx, my;
+    double D0;
+    HeatOps(p4b_ctx *c_, cudaStream_t st_, int mx_, int my_, double D0_) : DeviceOps{c_, st_}, mx(mx_), my(my_), D0(D0_) {}
+    void pattern_ifunction(int, const PO &, const double *, const double *Ydot, double *F) { copy((size_t)mx * my, Ydot, F); }
+    void pattern_rhsfunction(int, const PO &, const double *Y, double *G) { chk(launch_heat_rhs(st, mx, my, D0, Y, G)); }
+    void pattern_jac_apply(int, const PO &, double shift, const double *Y, const double *X, double *out) {
+        // Y == nullptr: the right-hand side is explicit (IMEX) and stays out of the stage matrix, which is then shift I
+        if (Y) chk(launch_heat_jac_apply(st, mx, my, D0, shift, X, out));
+        else axpby((size_t)mx * my, shift, X, 0.0, nullptr, out);
+    }
+};
+
 }  // namespace p4b
 
 using namespace p4b;
@@ -634,6 +650,44 @@ extern "C" int p4b_ts_solve_callbacks(p4b_ctx *c, const p4b_pattern_opts *opts, 
 }
 
 extern "C" double p4b_ts_time_step(void) { return g_ts_time_step; }
+
+extern "C" int p4b_heat_rhs(p4b_ctx *c, int mx, int my, double D0, const double *u, double *G) {
+    if (!c || !u || !G) return fail(62, "p4b_heat_rhs: null argument");
+    if (mx < 3 || my < 3) return fail(60, "heat grid needs at least 3 nodes per dimension");
+    return launch_heat_rhs(ctx_stream(c), mx, my, D0, u, G);
+}
+extern "C" int p4b_heat_jac_apply(p4b_ctx *c, int mx, int my, double D0, double shift, const double *X, double *JX) {
+    if (!c || !X || !JX) return fail(62, "p4b_heat_jac_apply: null argument");
+    if (mx < 3 || my < 3) return fail(60, "heat grid needs at least 3 nodes per dimension");
+    return launch_heat_jac_apply(ctx_stream(c), mx, my, D0, shift, X, JX);
+}
+extern "C" int p4b_heat_solve(p4b_ctx *c, const p4b_pattern_opts *opts, int mx, int my, double D0, double *Y_inout_host,
+                              p4b_line_fn line, void *line_ctx, p4b_pattern_result *result) {
+    if (!c || !opts || !Y_inout_host || !result) return fail(62, "p4b_heat_solve: null argument");
+    if (mx < 3 || my < 3) return fail(60, "heat grid needs at least 3 nodes per dimension");
+    nk::PatternOpts o = *reinterpret_cast<const nk::PatternOpts *>(opts);
+    if (o.ts_type < nk::TS_ARKIMEX || o.ts_type > nk::TS_RK)
+        return fail(62, "ts_type: arkimex (0), beuler (1), cn (2), bdf (3), rk (4)");
+    if (o.pc_type != nk::PC_NONE && o.ts_type != nk::TS_RK)
+        return fail(56, "p4b_heat_solve: the stage operator is applied matrix-free on one level: -pc_type none only");
+    o.pc_type = nk::PC_NONE;
+    o.no_rhsjacobian = 0;
+    const size_t n = (size_t)mx * my;
+    HeatOps ops(c, ctx_stream(c), mx, my, D0);
+    nk::Printer pr{line, line_ctx};
+    double *Y = nullptr, *Y0 = ops.alloc(n);
+    ops.from_host(Y_inout_host, Y0, n);
+    nk::PatternResult &R = *reinterpret_cast<nk::PatternResult *>(result);
+    int rc = nk::pattern_solve(&ops, o, pr, &Y, &R, Y0, n);
+    if (!rc && ops.error()) rc = ops.error();
+    if (!rc) ops.to_host(Y, Y_inout_host, n);
+    ops.release(Y0);
+    if (Y) ops.release(Y);
+    cudaStreamSynchronize(ops.st);
+    if (rc == 64) return fail(64, "TSSolve: a stage solve did not converge (or an explicit step produced NaN)");
+    if (rc) return fail(rc, "p4b_heat_solve failed (%s)", p4b_last_error());
+    return 0;
+}
 
 extern "C" int p4b_pattern_default_opts(p4b_pattern_opts *o) {
     if (!o) return fail(62, "null options");

@@ -163,6 +163,12 @@ class Context:
         L.check(self.lib.p4b_minimal_jacobian_fd(self.h, mx, my, q, u.data_ptr(), g.data_ptr(), F0.data_ptr(),
                                                  vals.data_ptr()))
 
+    def heat_rhs(self, mx, my, D0, u, G):
+        L.check(self.lib.p4b_heat_rhs(self.h, mx, my, D0, u.data_ptr(), G.data_ptr()))
+
+    def heat_jac_apply(self, mx, my, D0, shift, X, JX):
+        L.check(self.lib.p4b_heat_jac_apply(self.h, mx, my, D0, shift, X.data_ptr(), JX.data_ptr()))
+
     def sell_matrix(self, rowptr, colind, vals):
         """An assembled matrix on this device ([PETSc] MATSELL), from host CSR arrays."""
         from .callbacks import SellMatrix

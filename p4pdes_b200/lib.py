@@ -236,6 +236,10 @@ _SIGS = {
     "p4b_ts_solve_callbacks": (C.c_int, [_P, C.POINTER(PatternOpts), IFUNCTION2D_FN, RHSFUNCTION2D_FN, _P, _P, C.c_size_t,
                                         LINE_FN, _P, C.POINTER(PatternResult)]),
     "p4b_ts_time_step": (C.c_double, []),
+    "p4b_heat_rhs": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, _D, _D]),
+    "p4b_heat_jac_apply": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_double, _D, _D]),
+    "p4b_heat_solve": (C.c_int, [_P, C.POINTER(PatternOpts), C.c_int, C.c_int, C.c_double, _P, LINE_FN, _P,
+                                C.POINTER(PatternResult)]),
     "p4b_sell_create": (C.c_int, [_P, C.c_int, _P, _P, _P, C.POINTER(_P)]),
     "p4b_sell_spmv": (C.c_int, [_P, _D, _D]),
     "p4b_sell_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),

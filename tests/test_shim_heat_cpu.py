@@ -1,10 +1,11 @@
 """The reference's UNCHANGED c/ch5/heat.c through the PETSc-shaped shim (p4pdes_b200/shim/petscshim.c), on the CPU.
 
-heat.c is not pattern.c's DMDA (one component, DM_BOUNDARY_NONE in x, periodic in y, RHSFunction + RHSJacobian only), and
-the library has no kernels for it: TSSolve takes the callback route from the start (ts_solve_any_dmda ->
-p4b_ts_solve_callbacks) -- the user's G on ghosted a[j][i] views on the host, the integrators and the vector algebra behind
-the C ABI (here the host stand-in oracle/native/p4b_standin.cpp, the same template over plain loops; on a GPU box
-tests/test_gpu_heat.py).  Checked: both goldens verbatim, TSMonitorSet / TSGetDM / TSGetTimeStep through heat.c's own
+heat.c is not pattern.c's DMDA (one component, DM_BOUNDARY_NONE in x, periodic in y, RHSFunction + RHSJacobian only):
+TSSolve (ts_solve_any_dmda) probes the registered RHSFunction against the library's heat kernel -- heat.c's IS that
+function, so its run is p4b_heat_solve (G and the stage operator are kernels) -- and otherwise, or with
+-p4b_recognise_residual 0, takes the callback route (p4b_ts_solve_callbacks: the user's G on ghosted a[j][i] views on the
+host, the integrators and the vector algebra behind the C ABI).  Here the library is the host stand-in
+oracle/native/p4b_standin.cpp (the same templates over plain loops); on a GPU box: tests/test_gpu_heat.py.  Checked: both goldens verbatim, TSMonitorSet / TSGetDM / TSGetTimeStep through heat.c's own
 EnergyMonitor, the solution (through the binary viewer) against the oracle, every -ts_type, and the error paths."""
 import json
 import os
@@ -37,11 +38,15 @@ def run(exe, argv, check=True):
     return p.stdout.splitlines(), p
 
 
-def test_goldens_verbatim(exe):
-    lines, p = run(exe, GOLD["heat.test2"]["options"])                       # explicit: no preconditioner to name
+ROUTES = [("", "equals the library's heat-equation kernel"), (" -p4b_recognise_residual 0", "callbacks evaluated on the host")]
+
+
+@pytest.mark.parametrize("route,says", ROUTES)
+def test_goldens_verbatim(exe, route, says):
+    lines, p = run(exe, GOLD["heat.test2"]["options"] + route)               # explicit: no preconditioner to name
     assert lines == GOLD["heat.test2"]["lines"]
-    assert "callbacks evaluated on the host" in p.stderr                     # the route is always said
-    lines, _ = run(exe, GOLD["heat.test1"]["options"] + " -pc_type none")    # (PETSc's default ILU is not on the device)
+    assert says in p.stderr                                                  # the route is always said
+    lines, _ = run(exe, GOLD["heat.test1"]["options"] + " -pc_type none" + route)    # (PETSc's default ILU is not on the device)
     assert lines == GOLD["heat.test1"]["lines"]
 
 
@@ -51,13 +56,14 @@ def states(exe, argv, tmp_path):
     return np.array(petscbin.read_file(t)), petscbin.read_file(u)
 
 
+@pytest.mark.parametrize("route", [r for r, _ in ROUTES])
 @pytest.mark.parametrize("ts_type,tol", [("rk", 1e-13), ("beuler", 2e-7), ("cn", 2e-7)])
-def test_solution_equals_the_oracle(exe, tmp_path, ts_type, tol):
+def test_solution_equals_the_oracle(exe, tmp_path, ts_type, tol, route):
     """The states the binary viewer records (c/ch5/MOVIES.md:44) against the NumPy integration of the same system: the
     explicit scheme is the same arithmetic; the implicit ones inherit the stage solves' tolerances (Newton 1e-8 on a
     matrix-free GMRES at 1e-5 against sparse LU)."""
     extra = "" if ts_type == "rk" else " -pc_type none"
-    T, U = states(exe, "-da_refine 2 -ts_type %s -ts_max_time 0.01%s" % (ts_type, extra), tmp_path)
+    T, U = states(exe, "-da_refine 2 -ts_type %s -ts_max_time 0.01%s%s" % (ts_type, extra, route), tmp_path)
     want_t = []
     mon = lambda k, t, h, w: want_t.append(t)
     if ts_type == "rk":
@@ -108,3 +114,36 @@ def test_default_type_bdf_and_other_options(exe, tmp_path):
 def test_error_paths(exe, argv, code, msg):
     _, p = run(exe, argv, check=False)
     assert p.returncode == code and msg in p.stderr and "PETSC ERROR" in p.stderr
+
+
+@pytest.fixture(scope="module")
+def variants(exe, tmp_path_factory):
+    """tests/shim_cases/heat_variants.c against the same shim + stand-in objects."""
+    d = tmp_path_factory.mktemp("hv")
+    obj, out = str(d / "hv.o"), str(d / "hv")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), "-c",
+                           os.path.join(ROOT, "tests", "shim_cases", "heat_variants.c"), "-o", obj])
+    o = os.path.join(ROOT, "oracle", "_ref", "obj")
+    subprocess.check_call(["g++", obj, os.path.join(o, "petscshim.o"), os.path.join(o, "p4b_standin.o"), "-o", out, "-lm"])
+    return out
+
+
+def test_recognition_of_the_heat_kernel_and_its_limits(variants):
+    """The model written differently (and with another diffusivity) is recognised: 4 host evaluations of G in the whole run
+    (two to identify D0, one at a generic state, one at the final state).  The model plus a cubic term is not: host
+    callbacks throughout, and a different answer.  A term the probes cannot see is caught at the final state: loud error."""
+    tail = lambda l: (float(l.split()[7]), float(l.split()[9]), int(l.split("(")[1].split()[0]))
+    a, p = run(variants, "-variant 0 -da_refine 2 -pc_type none")
+    assert "equals the library's heat-equation kernel (D0 = 1;" in p.stderr and tail(a[-1])[2] == 4
+    b, p = run(variants, "-variant 0 -da_refine 2 -pc_type none -p4b_recognise_residual 0")
+    assert "callbacks evaluated on the host" in p.stderr and tail(b[-1])[2] > 100
+    assert abs(tail(a[-1])[1] - tail(b[-1])[1]) <= 1e-7 * tail(b[-1])[1]            # same answer on both routes
+    c, p = run(variants, "-variant 0 -D0 0.3 -da_refine 2 -ts_type rk")
+    assert "(D0 = 0.3;" in p.stderr and tail(c[-1])[2] == 4
+    d, p = run(variants, "-variant 1 -da_refine 2 -pc_type none")
+    assert "callbacks evaluated on the host" in p.stderr and tail(d[-1])[2] > 100
+    assert abs(tail(d[-1])[1] - tail(a[-1])[1]) > 1e-6 * tail(a[-1])[1]
+    _, p = run(variants, "-variant 2 -da_refine 2 -pc_type none", check=False)
+    assert p.returncode == 56 and "not at the final state" in p.stderr and "-p4b_recognise_residual 0" in p.stderr
+    e, p = run(variants, "-variant 2 -da_refine 2 -pc_type none -p4b_recognise_residual 0")
+    assert tail(e[-1])[0] < -1e-3                                                     # the extra sink removes heat
