@@ -32,4 +32,6 @@ def test_large_tridiagonal_system_on_device(ctx, tmp_path, ksp, pc):
     ls.write_system(A, bb, csr, b)
     rep = ls.loadsolve_main("-fA %s -fb %s -ksp_type %s -pc_type %s -ksp_rtol 1e-10" % (A, bb, ksp, pc), ctx)
     assert rep.reason == "CONVERGED_RTOL" and rep.its <= 40 and rep.n == m
-    np.testing.assert_allclose(rep.x, xexact, rtol=1e-8)
+    # the residual is reduced by 1e-10 in the 2-norm (cond(A) <= 5): the error is small in norm, single entries to ~1e-7
+    assert np.linalg.norm(rep.x - xexact) <= 1e-8 * np.linalg.norm(xexact)
+    np.testing.assert_allclose(rep.x, xexact, rtol=1e-6)
