@@ -2,6 +2,7 @@
 sizes that exceed the 126 MB L2, with CUDA events on the launching stream.  Prints one JSON line per kernel.
 
     python profiles/microbench.py > profiles/r01_microbench.jsonl
+    python profiles/microbench.py --only-heat      (the kernels added late in round 2)
 """
 import json
 import os
@@ -38,8 +39,31 @@ def report(name, size, bytes_alg, ms, note=""):
                       "frac_of_hbm_peak": gbs / PEAK, "working_set_MB": bytes_alg / 1e6, "note": note}), flush=True)
 
 
+def heat_and_poisson(ctx):
+    """Round 2, late additions: heat.c's kernels (c/ch5/heat.c:141-208) and the Poisson matrix fill (minimal.c:142-145)."""
+    for mx, my in ((2049, 2048), (8193, 8192)):
+        n = mx * my
+        u = torch.randn(n, dtype=torch.float64, device="cuda")
+        G = ctx.empty(n)
+        note = "L2 resident" if 16 * n < 100e6 else "exceeds L2"
+        ms = timeit(lambda: ctx.heat_rhs(mx, my, 1.0, u, G))
+        report("heat_rhs", "%d x %d" % (mx, my), 16.0 * n, ms, note)
+        ms = timeit(lambda: ctx.heat_jac_apply(mx, my, 1.0, 1000.0, u, G))
+        report("heat_jac_apply", "%d x %d" % (mx, my), 16.0 * n, ms, note)
+        del u, G
+    for m in (2049, 4097):
+        n = m * m
+        vals = ctx.empty(9 * n)
+        ms = timeit(lambda: ctx.poisson_stencil9(m, m, 1.0, 1.0, 1.0, 1.0, vals))
+        report("poisson_stencil9 (fill)", "%d^2" % m, 72.0 * n, ms, "write-only, %s" % ("L2 resident" if 72 * n < 100e6 else "exceeds L2"))
+        del vals
+
+
 def main():
     ctx = Context()
+    if "--only-heat" in sys.argv:
+        heat_and_poisson(ctx)
+        return
     for m in (2049, 8193):
         n = m * m
         g = cb.minimal_g(ctx, m, m, "catenoid", 1.0, 1.1)
