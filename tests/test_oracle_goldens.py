@@ -76,6 +76,33 @@ def test_fish_discretisation_goldens(goldens, name, args):
     check_errors(r, g)
 
 
+def test_fish_test7_complete_galerkin_two_ranks(goldens):
+    """-fsh_dim 3 -fsh_problem manupoly -snes_fd_color -ksp_rtol 1.0e-12 -pc_type mg -pc_mg_galerkin -da_refine 2 on 2 ranks
+    (c/ch6/makefile:29): 11 iterations.  Three ingredients, each needed: Galerkin coarse operators P^T A P, the DMDA's
+    2-rank split in z for the block SSOR smoother ([PETSc] da3.c picks a 1 x 1 x 2 process grid for 9^3 on 2 ranks), and
+    KSPChebyshev's own lambda_hat -- 10 GMRES iterations on a noisy right-hand side -- which is 1.22 / 1.18 (5^3 / 9^3 level) for the
+    two-block smoother (one block: 1.0); whatever the noise vector, the count is the golden's."""
+    g = goldens["fish.test7"]
+    assert g["ranks"] == 2 and g["ksp_its"] == 11
+    for seed in range(4):
+        r = fo.fish(3, 2, "manupoly", rtol=1e-12, mg=fo.MGOptions(smoother_pc="sor", nranks=2, galerkin=True, estimate="gmres",
+                                                                  seed=seed))
+        assert r.its == g["ksp_its"]
+        check_errors(r, g)
+    M = fo.PCMG(fo.refined_grid(3, 2), opts=fo.MGOptions(smoother_pc="sor", nranks=2, galerkin=True))
+    lams = [fo.gmres_lambda_max(M.A[l], M.pc[l]) for l in (1, 2)]                  # the 5^3 and the 9^3 level
+    assert 1.20 < lams[0] < 1.24 and 1.15 < lams[1] < 1.20
+    # every ingredient is needed (guards against a vacuous match)
+    miss = [fo.fish(3, 2, "manupoly", rtol=1e-12, mg=fo.MGOptions(smoother_pc="sor", **kw)).its for kw in (
+        dict(nranks=2, galerkin=True),                             # analytic target lambda_hat = 1
+        dict(nranks=1, galerkin=True, estimate="gmres"),           # one rank
+        dict(nranks=2, galerkin=False, estimate="gmres"))]         # rediscretised coarse operators
+    assert miss[0] == 23 and miss[1] == 9 and miss[2] != 11
+    # and the estimate leaves the goldens that were pinned with lambda_hat = 1 where they are (one block: 0.999...)
+    assert fo.fish(1, 3, "manupoly", rtol=1e-12, mg=fo.MGOptions(smoother_pc="sor", estimate="gmres")).its == goldens["fish.test1"]["ksp_its"]
+    assert fo.fish(2, 1, "manuexp", gonboundary=False, mg=fo.MGOptions(smoother_pc="sor", estimate="gmres")).its == goldens["fish.test3"]["ksp_its"]
+
+
 def test_jacobian_symmetric_constant_diagonal():
     # fish.test2,5,8 print "Matrix is symmetric"; poissonfunctions.h:33-38 promises a constant diagonal
     for dim, ref, c in ((1, 3, (1, 1, 1)), (2, 3, (1.0, 2.0, 1.0)), (3, 2, (0.01, 2.0, 100.0))):
