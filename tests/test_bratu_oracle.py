@@ -1,7 +1,8 @@
 """oracle/bratu_oracle.py against the reference's golden c/ch7/solns/output/bratu2D.test1 (c/ch7/solns/makefile:12):
-what the golden pins -- the residual callback (||F(u0)|| = 9.04754 on the 9 x 9 grid with Liouville's boundary data) and
-the discretisation (converged error 3.169e-04) -- and what it cannot pin without PETSc's SNESFAS source (the cycle:
-same number of outer iterations, norms of the same size; parity of the cycle UNPINNED, see the oracle's header)."""
+the residual callback (||F(u0)|| = 9.04754 on the 9 x 9 grid with Liouville's boundary data), the discretisation
+(converged error 3.169e-04) and -- with cycle="petsc", the restatement of [PETSc] SNESFASCycle_Full found by matching this
+golden -- every printed digit of its residual norms and its count of NGS calls.  The textbook F cycle the device runs has
+the same components and convergence class but not the same iterates."""
 import numpy as np
 import pytest
 
@@ -19,6 +20,24 @@ def test_golden_bratu2d_test1(order):
     assert r.its == GOLDEN["its"]                                          # F cycle per outer iteration, as the golden's 3
     for mine, theirs in zip(r.fnorm[1:], GOLDEN["norms"][1:]):            # same size (PETSc's cycle differs in detail)
         assert 0.2 < mine / theirs < 5.0
+
+
+def test_golden_bratu2d_test1_verbatim_with_petscs_full_cycle():
+    """c/ch7/solns/output/bratu2D.test1:1-6.  The cycle is pinned by the numbers: each ingredient switched off misses them."""
+    r = bo.fas_solve(refine=2, cycle="petsc")
+    assert r.its == 3 and r.ngs_calls == 58                                # :5 "iterations 3", :6 "NGS calls = 58"
+    assert ["%g" % float("%.6g" % x) for x in r.fnorm] == ["9.04754", "0.000449564", "1.87245e-06", "8.93257e-09"]      # :1-4
+    assert "%.3e" % r.errinf == GOLDEN["errinf"]                           # :7
+    for variant, second in (("no_downsweep", "3.75084e-06"), ("no_presmooth", "0.000107976"), ("no_final_v", "0.00392143")):
+        v = bo.fas_solve(refine=2, cycle="petsc", variant=variant)
+        assert "%g" % float("%.6g" % v.fnorm[2]) == second != "1.87245e-06"
+    # the reference's sweep sets a boundary node when the loop reaches it (bratu2D.c:250-256): with the edges set
+    # beforehand (the red-black ordering does that) the first cycle already differs
+    rb = bo.fas_solve(refine=2, cycle="petsc", order="redblack")
+    assert "%g" % float("%.6g" % rb.fnorm[1]) != "0.000449564" and rb.its == 3
+    # the device's textbook F cycle = this cycle without the smoothing on the way down: same first iterate
+    tb = bo.fas_solve(refine=2)
+    assert "%g" % float("%.6g" % tb.fnorm[1]) == "0.000449564" and tb.ngs_calls == 54
 
 
 def test_transfer_operators_are_the_dmda_q1_pair():
