@@ -26,6 +26,24 @@ def test_oracle_reproduces_obstacle_test1_completely():
             % (r.err1, r.errinf, 100 * r.area_err)) == TEST1[4]
 
 
+def test_oracle_reproduces_obstacle_test2_completely():
+    """c/ch12/makefile:20 on 4 ranks: -da_refine 2 -snes_monitor_short -ksp_type gmres -pc_type asm -sub_pc_type lu.  The
+    third and fourth norm carry the inexactness of the GMRES(rtol 1e-5) + additive-Schwarz solves: they pin PCASM's defaults
+    (restricted, overlap 1, one block per rank of the 2 x 2 DMDA) -- every other reading misses them."""
+    golden = ["  0 SNES Function norm 3.86571", "  1 SNES Function norm 1.3323", "  2 SNES Function norm 4.84465e-06",
+              "  3 SNES Function norm 1.511e-11",
+              "done on 9 x 9 grid ... CONVERGED_FNORM_RELATIVE, SNES iters = 3, last KSP iters = 4",
+              "errors: av |u-uexact| = 3.076e-03, |u-uexact|_inf = 1.334e-02, active area error = 47.016%"]
+    r = oo.rsls(9, pc="asm", ranks=(2, 2))
+    got = ["  %d SNES Function norm %s" % (i, short(v)) for i, v in enumerate(r.fnorm)]
+    got.append("done on 9 x 9 grid ... %s, SNES iters = %d, last KSP iters = %d" % (r.reason, r.its, r.ksp_its[-1]))
+    got.append("errors: av |u-uexact| = %.3e, |u-uexact|_inf = %.3e, active area error = %.3f%%" % (r.err1, r.errinf, 100 * r.area_err))
+    assert got == golden
+    for kw in (dict(ranks=(1, 4)), dict(ranks=(4, 1)), dict(asm_overlap=0), dict(asm_overlap=2), dict(asm_restricted=False)):
+        v = oo.rsls(9, pc="asm", **kw)
+        assert short(v.fnorm[2]) != "4.84465e-06" and v.its == 3          # same Newton path, other linear-solve errors
+
+
 def test_oracle_error_lines_of_the_other_goldens():
     # obstacle.test2 (GMRES + ASM/LU on 4 ranks) and test4 (vinewtonssls) end on the same discrete solution as test1
     r = oo.rsls(9, pc="exact")
