@@ -13,8 +13,12 @@ both KSP counts 11, the error line, the active-area error) and on obstacle.test2
 PCASM with LU subdomain solves: four norms incl. the inexact-solve digits 4.84465e-06 and 1.511e-11, 3 iterations, last
 KSP count 4) -- which pins PCASM as restricted additive Schwarz with overlap 1 (measured in the reduced matrix's own
 graph) on the DMDA's 2 x 2 process grid (RASMPC below; 17 other readings -- unrestricted, overlap 0 or 2, 1 x 4 strips --
-miss the golden's third norm).  test3 (multigrid on the reduced systems) and test4 (vinewtonssls) share their error lines
-with the oracle's converged states; their iteration counts belong to methods that are not restated."""
+miss the golden's third norm), and on obstacle.test3 (-snes_grid_sequence 3 -pc_type mg: Newton counts 1, 2, 2, 3 of the four
+grids, last KSP count 4, error line) with multigrid on the reduced systems (ReducedMG below: the inactive mask coarsened
+by injection, reduced Q1 interpolation, Chebyshev(2)/SOR with the GMRES eigenvalue estimate; exact solves give 1, 1, 1, 2 and
+a Jacobi smoother 1, 1, 2, 3 -- the golden prints counts only, so Galerkin and rediscretised reduced coarse operators are not
+told apart).  test4 (vinewtonssls) shares its error line with the oracle's converged state; its iteration counts belong
+to a method that is not restated."""
 from __future__ import annotations
 
 from dataclasses import dataclass, field
@@ -118,14 +122,51 @@ class RASMPC:
         return z
 
 
+class ReducedMG:
+    """[PETSc] PCMG on the reduced system J_II of an RSLS step (DMSetVI / DMCoarsen on the inactive set): a coarse node is
+    inactive iff the fine node it coincides with is; interpolation = the rows / columns of the DMDA Q1 interpolation that
+    belong to the two inactive sets; coarse operators P^T A P; Chebyshev(2) + SOR smoothing with the targets (0.1, 1.1) x
+    the GMRES estimate (fish_oracle.gmres_lambda_max); LU on the coarsest level."""
+
+    def __init__(self, Jr, idx, m, nlevels, smoother="sor"):
+        self.A, self.P = [sp.csr_matrix(Jr)], []
+        mask = np.zeros(m * m, dtype=bool)
+        mask[idx] = True
+        for _ in range(1, nlevels):
+            mc = (m - 1) // 2 + 1
+            cmask = mask.reshape(m, m)[::2, ::2].ravel()
+            P = sp.kron(fo.interp1d(mc), fo.interp1d(mc), format="csr")[np.flatnonzero(mask)][:, np.flatnonzero(cmask)]
+            self.P.append(sp.csr_matrix(P))
+            self.A.append(sp.csr_matrix(P.T @ self.A[-1] @ P))
+            m, mask = mc, cmask
+        self.coarse = spla.splu(sp.csc_matrix(self.A[-1]))
+        self.pc, self.eig = [], []
+        for A in self.A[:-1]:
+            pc = fo.BlockSSORPC(A, [(0, A.shape[0])]) if smoother == "sor" else fo.JacobiPC(A)
+            lam = fo.gmres_lambda_max(A, pc)
+            self.pc.append(pc)
+            self.eig.append((0.1 * lam, 1.1 * lam))
+
+    def _cycle(self, l, b, x):
+        if l == len(self.A) - 1:
+            return self.coarse.solve(b)
+        x = fo.chebyshev_smooth(self.A[l], self.pc[l], b, x, self.eig[l][0], self.eig[l][1], 2)
+        xc = self._cycle(l + 1, self.P[l].T @ (b - self.A[l] @ x), np.zeros(self.P[l].shape[1]))
+        return fo.chebyshev_smooth(self.A[l], self.pc[l], b, x + self.P[l] @ xc, self.eig[l][0], self.eig[l][1], 2)
+
+    def apply(self, r):
+        return self._cycle(0, r, np.zeros_like(r))
+
+
 def vi_norm(u, F, lo):
     inact = ~((u <= lo + 1.0e-8) & (F > 0.0))
     return float(np.sqrt(np.sum(F[inact] ** 2))), inact
 
 
 def rsls(m, u0=None, snes_rtol=1.0e-8, ksp_rtol=1.0e-5, pc="ilu", max_it=50, snes_stol=1.0e-8, snes_atol=1.0e-50,
-         ranks=(2, 2), asm_overlap=1, asm_restricted=True):
-    """pc: "ilu" | "none" (KSPCG), "exact", or "asm" = KSPGMRES(30) + RASMPC on the ranks[0] x ranks[1] process grid."""
+         ranks=(2, 2), asm_overlap=1, asm_restricted=True, mg_levels=1, mg_smoother="sor"):
+    """pc: "ilu" | "none" (KSPCG), "exact", "asm" = KSPGMRES(30) + RASMPC on the ranks[0] x ranks[1] process grid, or "mg" =
+    KSPCG + ReducedMG with mg_levels levels (one level: the exact solve)."""
     owner = dmda_owner(m, *ranks) if pc == "asm" else None
     X, Y = grid_xy(m)
     lo, g = psi(X, Y), u_exact(X, Y)
@@ -144,8 +185,10 @@ def rsls(m, u0=None, snes_rtol=1.0e-8, ksp_rtol=1.0e-5, pc="ilu", max_it=50, sne
         rhs = F.ravel()[idx]
         if pc == "asm":
             y_i, k, _ = mso.gmres(Jr, rhs, RASMPC(Jr, owner[idx], asm_overlap, asm_restricted).apply, rtol=ksp_rtol)
-        elif pc == "exact":
-            y_i, k = spla.spsolve(sp.csc_matrix(Jr), rhs), 1
+        elif pc == "exact" or (pc == "mg" and (mg_levels < 2 or idx.size < 2)):
+            y_i, k = spla.spsolve(sp.csc_matrix(Jr), rhs) if idx.size > 1 else rhs / Jr.toarray().ravel(), 1
+        elif pc == "mg":
+            y_i, k, _ = fo.cg(Jr, rhs, ReducedMG(Jr, idx, m, mg_levels, mg_smoother).apply, rtol=ksp_rtol)
         else:
             M = fo.ILU0PC(Jr).apply if pc == "ilu" else (lambda r: r.copy())
             y_i, k, _ = fo.cg(Jr, rhs, M, rtol=ksp_rtol)
@@ -198,3 +241,17 @@ def rsls(m, u0=None, snes_rtol=1.0e-8, ksp_rtol=1.0e-5, pc="ilu", max_it=50, sne
     e = u - g
     return ObstacleResult(m, its, norms, ksp_its, u, float(np.sum(np.abs(e))) / (m * m), float(np.max(np.abs(e))),
                           abs(dx * dx * act - exactarea) / exactarea, reason)
+
+
+def rsls_grid_sequence(nseq, base=3, **kw):
+    """-snes_grid_sequence nseq from the base x base grid ([PETSc]: DMRefine + Q1 interpolation of the iterate, which rsls
+    then projects onto the bounds); with pc="mg" stage s preconditions with s + 1 levels.  Returns the stages' results."""
+    out, u, m = [], None, base
+    for stage in range(nseq + 1):
+        if u is not None:
+            u = mso.interpolate(u)
+            m = u.shape[0]
+        r = rsls(m, u0=u, mg_levels=stage + 1, **kw)
+        out.append(r)
+        u = r.u
+    return out

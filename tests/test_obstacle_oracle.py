@@ -44,6 +44,20 @@ def test_oracle_reproduces_obstacle_test2_completely():
         assert short(v.fnorm[2]) != "4.84465e-06" and v.its == 3          # same Newton path, other linear-solve errors
 
 
+def test_oracle_reproduces_obstacle_test3():
+    """c/ch12/makefile:23: -snes_grid_sequence 3 -snes_converged_reason -pc_type mg.  Everything the golden prints: the
+    Newton counts of the four grids, the last KSP count, the error line.  The counts need the INEXACT multigrid solves (rtol
+    1e-5): exact solves converge one iteration earlier on three of the four grids."""
+    st = oo.rsls_grid_sequence(3, pc="mg")
+    assert [r.m for r in st] == [3, 5, 9, 17] and all(r.reason == "CONVERGED_FNORM_RELATIVE" for r in st[1:])
+    assert [r.its for r in st] == [1, 2, 2, 3] and st[-1].ksp_its[-1] == 4
+    r = st[-1]
+    assert ("errors: av |u-uexact| = %.3e, |u-uexact|_inf = %.3e, active area error = %.3f%%"
+            % (r.err1, r.errinf, 100 * r.area_err)) == TEST3_ERRORS
+    assert [r.its for r in oo.rsls_grid_sequence(3, pc="exact")] == [1, 1, 1, 2]
+    assert [r.its for r in oo.rsls_grid_sequence(3, pc="mg", mg_smoother="jacobi")] == [1, 1, 2, 3]
+
+
 def test_oracle_error_lines_of_the_other_goldens():
     # obstacle.test2 (GMRES + ASM/LU on 4 ranks) and test4 (vinewtonssls) end on the same discrete solution as test1
     r = oo.rsls(9, pc="exact")
