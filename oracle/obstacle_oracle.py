@@ -17,8 +17,9 @@ miss the golden's third norm), and on obstacle.test3 (-snes_grid_sequence 3 -pc_
 grids, last KSP count 4, error line) with multigrid on the reduced systems (ReducedMG below: the inactive mask coarsened
 by injection, reduced Q1 interpolation, Chebyshev(2)/SOR with the GMRES eigenvalue estimate; exact solves give 1, 1, 1, 2 and
 a Jacobi smoother 1, 1, 2, 3 -- the golden prints counts only, so Galerkin and rediscretised reduced coarse operators are not
-told apart).  test4 (vinewtonssls) shares its error line with the oracle's converged state; its iteration counts belong
-to a method that is not restated."""
+told apart), and on obstacle.test4 (-snes_grid_sequence 2 -snes_type vinewtonssls: Newton counts 4, 6, 5, last KSP count 6, error
+line) with the semismooth method restated in ssls() below ([PETSc] src/snes/impls/vi/ss/vissls.c: Newton + backtracking
+on the Fischer-Burmeister function of (u - psi, F(u)); without the initial projection onto the bounds the first count is 5)."""
 from __future__ import annotations
 
 from dataclasses import dataclass, field
@@ -254,4 +255,82 @@ def rsls_grid_sequence(nseq, base=3, **kw):
         r = rsls(m, u0=u, mg_levels=stage + 1, **kw)
         out.append(r)
         u = r.u
+    return out
+
+
+def fischer(a, b):
+    """[PETSc] Fischer(a, b) = sqrt(a^2 + b^2) - (a + b), in the cancellation-free form PETSc evaluates."""
+    n = np.sqrt(a * a + b * b)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(a + b <= 0.0, n - (a + b), -2.0 * a * b / np.where(n + a + b != 0.0, n + a + b, 1.0))
+
+
+def ssls(m, u0=None, snes_rtol=1.0e-8, ksp_rtol=1.0e-5, pc="ilu", max_it=50, snes_stol=1.0e-8, snes_atol=1.0e-50, project=True):
+    """[PETSc] SNESVINEWTONSSLS with a lower bound only: phi_i = Fischer(u_i - psi_i, F_i(u)); each iteration solves
+    (Da + Db J) y = phi with Da = (u - psi)/n - 1, Db = F/n - 1, n = |(u - psi, F)| (an element of the B-subdifferential;
+    (1/sqrt2 - 1) for both where u = psi and F = 0), KSPCG as obstacle.c:119 sets it + ILU(0), then SNESLineSearchBT on
+    ||phi||_2 along u - lambda y (no projection of the trial points: phi itself carries the constraint)."""
+    X, Y = grid_xy(m)
+    lo, g = psi(X, Y), u_exact(X, Y)
+    J = jacobian(m)
+    u = np.zeros((m, m)) if u0 is None else u0.copy()
+    if project:
+        u = np.maximum(u, lo)                                   # SNESVIProjectOntoBounds
+
+    def phi_of(w):
+        Fw = residual(w, g)
+        return fischer(w - lo, Fw), Fw
+
+    phi, F = phi_of(u)
+    pn = float(np.linalg.norm(phi))
+    norms, ksp_its, p0 = [pn], [], pn
+    its, reason = 0, "DIVERGED_MAX_IT"
+    if pn < snes_atol:
+        reason = "CONVERGED_FNORM_ABS"
+    while reason == "DIVERGED_MAX_IT" and its < max_it:
+        a, b = (u - lo).ravel(), F.ravel()
+        n = np.sqrt(a * a + b * b)
+        safe = np.where(n > 0.0, n, 1.0)
+        da = np.where(n > 0.0, a / safe - 1.0, 1.0 / np.sqrt(2.0) - 1.0)
+        db = np.where(n > 0.0, b / safe - 1.0, 1.0 / np.sqrt(2.0) - 1.0)
+        Js = sp.csr_matrix(sp.diags(da) + sp.diags(db) @ J)
+        if pc == "exact":
+            y, k = spla.spsolve(sp.csc_matrix(Js), phi.ravel()), 1
+        else:
+            y, k, _ = fo.cg(Js, phi.ravel(), fo.ILU0PC(Js).apply if pc == "ilu" else (lambda r: r.copy()), rtol=ksp_rtol)
+        ksp_its.append(k)
+        try:
+            xnew, _, _, _ = mso.linesearch_bt(lambda w: phi_of(w.reshape(m, m))[0].ravel(), u.ravel(), phi.ravel(), pn, y, Js @ y)
+        except RuntimeError:
+            reason = "DIVERGED_LINE_SEARCH"
+            break
+        snorm, xnorm = float(np.linalg.norm(xnew - u.ravel())), float(np.linalg.norm(xnew))
+        u = xnew.reshape(m, m)
+        phi, F = phi_of(u)
+        pn = float(np.linalg.norm(phi))
+        its += 1
+        norms.append(pn)
+        if pn < snes_atol:
+            reason = "CONVERGED_FNORM_ABS"
+        elif pn <= snes_rtol * p0:
+            reason = "CONVERGED_FNORM_RELATIVE"
+        elif snorm < snes_stol * xnorm:
+            reason = "CONVERGED_SNORM_RELATIVE"
+    act = int(np.sum((u <= lo + 1.0e-8) & (F > 0.0)))
+    dx = 4.0 / (m - 1)
+    exactarea = np.pi * AFREE * AFREE
+    e = u - g
+    return ObstacleResult(m, its, norms, ksp_its, u, float(np.sum(np.abs(e))) / (m * m), float(np.max(np.abs(e))),
+                          abs(dx * dx * act - exactarea) / exactarea, reason)
+
+
+def ssls_grid_sequence(nseq, base=3, **kw):
+    out, u = [], None
+    m = base
+    for _ in range(nseq + 1):
+        if u is not None:
+            u = mso.interpolate(u)
+            m = u.shape[0]
+        out.append(ssls(m, u0=u, **kw))
+        u = out[-1].u
     return out

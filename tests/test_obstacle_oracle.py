@@ -58,6 +58,23 @@ def test_oracle_reproduces_obstacle_test3():
     assert [r.its for r in oo.rsls_grid_sequence(3, pc="mg", mg_smoother="jacobi")] == [1, 1, 2, 3]
 
 
+def test_oracle_reproduces_obstacle_test4_semismooth():
+    """c/ch12/makefile:28: -snes_grid_sequence 2 -snes_converged_reason -snes_type vinewtonssls (KSPCG + ILU(0) as obstacle.c
+    leaves them).  Everything the golden prints: Newton counts 4, 6, 5, last KSP count 6, the error line (the same discrete
+    solution as the reduced-space method's)."""
+    st = oo.ssls_grid_sequence(2)
+    assert [r.m for r in st] == [3, 5, 9] and all(r.reason == "CONVERGED_FNORM_RELATIVE" for r in st)
+    assert [r.its for r in st] == [4, 6, 5] and st[-1].ksp_its[-1] == 6
+    r = st[-1]
+    assert ("errors: av |u-uexact| = %.3e, |u-uexact|_inf = %.3e, active area error = %.3f%%"
+            % (r.err1, r.errinf, 100 * r.area_err)) == TEST1[4]
+    assert [r.its for r in oo.ssls_grid_sequence(2, project=False)] == [5, 6, 5]       # the initial projection is needed
+    # Fischer-Burmeister: zero exactly on the complementarity set, both evaluation branches agree
+    a, b = np.array([0.0, 2.0, 0.0, 1e-9, 3.0]), np.array([1.5, 0.0, 0.0, 1e-9, -4.0])
+    np.testing.assert_allclose(oo.fischer(a, b), np.sqrt(a * a + b * b) - (a + b), atol=1e-15)
+    assert np.all(oo.fischer(a[:3], b[:3]) == 0.0)
+
+
 def test_oracle_error_lines_of_the_other_goldens():
     # obstacle.test2 (GMRES + ASM/LU on 4 ranks) and test4 (vinewtonssls) end on the same discrete solution as test1
     r = oo.rsls(9, pc="exact")
